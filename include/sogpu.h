@@ -1,0 +1,134 @@
+/* sogpu.h — C-ABI of the B200 (sm_100a) spherical-overdensity hot path.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, int return codes
+ * (0 = ok, nonzero = error, text via sogpu_last_error()).  Nothing here throws or exits.
+ * The entry points are what a binding of the reference's hot path needs — they replace
+ *
+ *      kdBuildTree(KD)                      /root/reference/kd2.h:269, kd2.c:1096-1185
+ *      kdSO(KD, float rhovir, int nSmooth)  /root/reference/kd2.h:265, kd2.c:864-895
+ *        └ kdRvir                           kd2.c:723-840
+ *      smBallGather(SMX, float, float*)     /root/reference/smooth2.h:99, smooth2.c:58-114
+ *
+ * and the particle hand-over that kdReadTipsy does into PINIT[] (kd2.c:352-416).
+ * INTEGRATION.md shows the few lines a maintainer of the reference adds to kd2.c to route
+ * these calls here; so_b200/host/ is a complete host program built that way.
+ *
+ * There is no CPU fallback: every compute entry point fails with SOGPU_ERR_CUDA when no
+ * sm_100-class device is usable.
+ */
+#ifndef SOGPU_H
+#define SOGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOGPU_OK            0
+#define SOGPU_ERR_ARG       1   /* bad argument / call order                    */
+#define SOGPU_ERR_CUDA      2   /* CUDA runtime error (see sogpu_last_error)    */
+#define SOGPU_ERR_NOMEM     3   /* host or device allocation failed             */
+#define SOGPU_ERR_UNSUPPORTED 4 /* input outside the supported contract         */
+
+typedef struct sogpu sogpu_t;
+
+/* Per-halo error codes, stored in BOTH rvir and mvir exactly like kdRvir does
+ * (kd2.c:774-776, 793-795, 837-838; documented so.c:146-154):
+ *   -1  fewer than nMembers particles inside the first ball (1.2 fRgtp)
+ *   -2  density already below threshold at nMembers particles
+ *   -3  threshold never reached before the ball schedule ends (0.25 * |period|) */
+
+/* ---- life cycle --------------------------------------------------------------------------- */
+
+/* device: CUDA ordinal, or -1 for the current device. */
+int sogpu_create(sogpu_t **out, int device);
+void sogpu_destroy(sogpu_t *h);
+/* Thread-local text of the last failure in this thread ("" if none). */
+const char *sogpu_last_error(void);
+/* All work of this handle is enqueued on `cuda_stream` (a cudaStream_t cast to void*;
+ * NULL = the handle's own stream).  Lets a caller time the kernels with its own events. */
+int sogpu_set_stream(sogpu_t *h, void *cuda_stream);
+/* Tuning knob: target mean particles per grid cell (default 2.0). */
+int sogpu_set_cell_occupancy(sogpu_t *h, float particles_per_cell);
+
+/* ---- particles: replaces the PINIT[] fill of kdReadTipsy (kd2.c:352-416) -------------------- */
+
+/* Host particles, any AoS/SoA layout: x,y,z of particle i are three consecutive floats at
+ * (char*)pos + i*pos_stride; its mass one float at (char*)mass + i*mass_stride (mass_stride 0 =
+ * one shared value).  Works directly on PINIT[] (stride 60) or tipsy dark records (stride 36).
+ * period/center are kdInit's fPeriod/fCenter (kd2.c:62-75); center only places the cell grid.
+ * Data is packed to float4 {x,y,z,m} and copied to the device; the host arrays are not kept. */
+int sogpu_set_particles_host(sogpu_t *h, const void *pos, size_t pos_stride, const void *mass,
+                             size_t mass_stride, int64_t n, const float period[3],
+                             const float center[3]);
+/* Device-resident float4 {x,y,z,m} array (borrowed: must outlive the handle's use of it). */
+int sogpu_set_particles_device(sogpu_t *h, const void *d_xyzm, int64_t n, const float period[3],
+                               const float center[3]);
+
+/* ---- kdBuildTree replacement (kd2.c:1096-1185) ------------------------------------------- */
+
+/* Counting sort of the particles by cell key (z-order over (iy,iz) rows, ix fastest) into a
+ * periodic uniform grid: sorted float4 array + original-index array + cell-end table. */
+int sogpu_build_grid(sogpu_t *h);
+
+/* ---- kdSO / kdRvir replacement (kd2.c:864-895, 723-840), without tagging ------------------- */
+
+/* For each of the nh halos (any order; halos are independent):
+ *   rvir[i], mvir[i]  R_Delta / M_Delta exactly as kdRvir stores them, or -1/-2/-3 in both
+ *   ndelta[i]         N_Delta = number of member particles (0 on error)
+ * centers: nh*3 floats, rgtp: nh floats (GRPNODE.pos / .fRgtp, kd2.c:250-252,268-270).
+ * rho_thr = fThreshold (so.c:477-481), n_members = kd->nMembers (so.c:229).
+ * Host pointers.  Member lists are kept on the device until fetched with sogpu_members(). */
+int sogpu_so(sogpu_t *h, const float *centers, const float *rgtp, int32_t nh, float rho_thr,
+             int32_t n_members, float *rvir, float *mvir, int32_t *ndelta);
+
+/* Same, with centers/rgtp already on the device and results left there:
+ * d_out_n (int32[nh]) = N_Delta or error code (-1/-2/-3), d_out_m (float[nh]) = M_Delta.
+ * Any of the outputs may be NULL.  Asynchronous on the handle's stream. */
+int sogpu_so_device(sogpu_t *h, const void *d_centers, const void *d_rgtp, int32_t nh,
+                    float rho_thr, int32_t n_members, void *d_out_n, void *d_out_m);
+
+/* Member particle lists of the last sogpu_so()/sogpu_so_device() call.
+ * offsets: nh+1 int64 (caller-allocated); *members / *d2: library-owned pinned host arrays,
+ * valid until the next sogpu_so* call or sogpu_destroy.  Members of halo i are the ORIGINAL
+ * particle indices (PINIT.iOrder, kd2.c:361) at [offsets[i], offsets[i+1]), ascending in
+ * (fDist2, index) — the order kdTagParticles walks them (kd2.c:670).  d2 may be NULL. */
+int sogpu_members(sogpu_t *h, int64_t *offsets, const int32_t **members, const float **d2);
+
+/* ---- smBallGather replacement (smooth2.c:58-114) + the qsort of kd2.c:514,781 -------------- */
+
+/* All particles with fDist2 <= ball2 around center, ascending (fDist2, index).  Writes up to
+ * cap entries into idx/d2 (host, either may be NULL) and the full count into *n. */
+int sogpu_ball_gather(sogpu_t *h, const float center[3], float ball2, int32_t *idx, float *d2,
+                      int64_t cap, int64_t *n);
+
+/* ---- introspection --------------------------------------------------------------------------- */
+
+typedef struct {
+    int64_t n_particles;
+    int32_t cells_per_axis;
+    int32_t equal_mass;          /* 1: all particle masses identical (fast exact path)        */
+    int64_t last_evals;          /* r^2 evaluations of the last sogpu_so* call (all passes)   */
+    int64_t last_evals_first;    /* ... of which in the first (histogram) pass of each ball   */
+    int64_t last_members;        /* sum of N_Delta of the last call                           */
+    int32_t last_kernel_launches;/* kernels launched by the last build or so call             */
+    int32_t last_deferred;       /* halos the warp kernel handed to the block kernel          */
+} sogpu_stats_t;
+int sogpu_get_stats(sogpu_t *h, sogpu_stats_t *out);
+
+/* ---- host-side helpers of the exact-arithmetic contract (no GPU needed; unit-tested) -------- */
+
+/* S[k] = sequential fp32 sum of k equal masses m, S[0]=0, S[k]=fl(S[k-1]+m) (kd2.c:787,807),
+ * evaluated from the compressed segment table the kernels use.  Returns 0 on success. */
+int sogpu_mass_prefix(float m, int64_t kmax, const int64_t *k, int64_t nk, float *out);
+/* Ball radii of kdRvir's schedule (kd2.c:745,765-768); returns the count (<= cap written). */
+int sogpu_ball_schedule(float rgtp, const float period[3], float *balls, int cap);
+/* R_Delta from M_Delta (kd2.c:817-818). */
+float sogpu_rdelta(float mvir, float rho_thr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOGPU_H */

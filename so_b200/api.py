@@ -1,0 +1,285 @@
+"""ctypes binding of the C-ABI library (include/sogpu.h -> so_b200/libsogpu.so).
+
+This is the call a Python user makes; tests and bench.py go through it, i.e. through the
+C-ABI.  There is NO fallback: if the CUDA library is missing or no B200 is usable the calls
+raise SoGpuError (the oracle under oracle/ is test infrastructure and is never imported here).
+
+Names mirror the reference's hot-path API (/root/reference/kd2.h:258-276):
+    KD.kdBuildTree()            kd2.c:1096-1185 -> sogpu_build_grid
+    KD.kdSO(rhovir, ...)        kd2.c:864-895   -> sogpu_so  (+ host replay of kdTagParticles)
+    KD.smBallGather(ball2, ri)  smooth2.c:58-114 -> sogpu_ball_gather
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsogpu.so")
+
+SYMBOLS = [
+    "sogpu_create", "sogpu_destroy", "sogpu_last_error", "sogpu_set_stream",
+    "sogpu_set_cell_occupancy", "sogpu_set_particles_host", "sogpu_set_particles_device",
+    "sogpu_build_grid", "sogpu_so", "sogpu_so_device", "sogpu_members", "sogpu_ball_gather",
+    "sogpu_get_stats", "sogpu_mass_prefix", "sogpu_ball_schedule", "sogpu_rdelta",
+]
+
+
+class SoGpuError(RuntimeError):
+    pass
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_particles", C.c_int64), ("cells_per_axis", C.c_int32), ("equal_mass", C.c_int32),
+                ("last_evals", C.c_int64), ("last_evals_first", C.c_int64), ("last_members", C.c_int64),
+                ("last_kernel_launches", C.c_int32), ("last_deferred", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libsogpu.so (built by __graft_entry__.build() / make -C so_b200/csrc)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SoGpuError("CUDA extension missing: %s (run `python -c 'import __graft_entry__ as g; "
+                         "g.build()'` or `make -C so_b200/csrc`); there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    fp, vp = C.POINTER(C.c_float), C.c_void_p
+    i32p, i64p = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+    L.sogpu_create.restype = C.c_int
+    L.sogpu_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.sogpu_destroy.restype = None
+    L.sogpu_destroy.argtypes = [vp]
+    L.sogpu_last_error.restype = C.c_char_p
+    L.sogpu_last_error.argtypes = []
+    L.sogpu_set_stream.argtypes = [vp, vp]
+    L.sogpu_set_cell_occupancy.argtypes = [vp, C.c_float]
+    L.sogpu_set_particles_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_int64, fp, fp]
+    L.sogpu_set_particles_device.argtypes = [vp, vp, C.c_int64, fp, fp]
+    L.sogpu_build_grid.argtypes = [vp]
+    L.sogpu_so.argtypes = [vp, fp, fp, C.c_int32, C.c_float, C.c_int32, fp, fp, i32p]
+    L.sogpu_so_device.argtypes = [vp, vp, vp, C.c_int32, C.c_float, C.c_int32, vp, vp]
+    L.sogpu_members.argtypes = [vp, i64p, C.POINTER(i32p), C.POINTER(fp)]
+    L.sogpu_ball_gather.argtypes = [vp, fp, C.c_float, i32p, fp, C.c_int64, i64p]
+    L.sogpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.sogpu_mass_prefix.argtypes = [C.c_float, C.c_int64, i64p, C.c_int64, fp]
+    L.sogpu_ball_schedule.restype = C.c_int
+    L.sogpu_ball_schedule.argtypes = [C.c_float, fp, fp, C.c_int]
+    L.sogpu_rdelta.restype = C.c_float
+    L.sogpu_rdelta.argtypes = [C.c_float, C.c_float]
+    for name in ("sogpu_set_stream", "sogpu_set_cell_occupancy", "sogpu_set_particles_host",
+                 "sogpu_set_particles_device", "sogpu_build_grid", "sogpu_so", "sogpu_so_device",
+                 "sogpu_members", "sogpu_ball_gather", "sogpu_get_stats", "sogpu_mass_prefix"):
+        getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _check(rc):
+    if rc != 0:
+        raise SoGpuError("sogpu error %d: %s" % (rc, lib().sogpu_last_error().decode()))
+
+
+# ---- host-only helpers (no GPU needed) ----------------------------------------------------------
+
+def mass_prefix(m, k):
+    """S[k] = sequential fp32 sum of k equal masses m (kd2.c:787,807) from the kernels' table."""
+    k = np.ascontiguousarray(k, np.int64)
+    out = np.zeros(len(k), np.float32)
+    kmax = int(k.max()) if len(k) else 0
+    _check(lib().sogpu_mass_prefix(C.c_float(m), kmax, k.ctypes.data_as(C.POINTER(C.c_int64)), len(k), _fp(out)))
+    return out
+
+
+def ball_schedule(rgtp, period=(1.0, 1.0, 1.0)):
+    per = np.asarray(period, np.float32)
+    out = np.zeros(256, np.float32)
+    k = lib().sogpu_ball_schedule(C.c_float(rgtp), _fp(per), _fp(out), 256)
+    return out[:k].copy()
+
+
+def rdelta(mvir, thr):
+    return float(lib().sogpu_rdelta(C.c_float(mvir), C.c_float(thr)))
+
+
+# ---- the handle ---------------------------------------------------------------------------------
+
+class SoGpu:
+    """One GPU context: particles -> cell grid -> SO queries."""
+
+    def __init__(self, device=-1, stream=None):
+        self._h = C.c_void_p()
+        _check(lib().sogpu_create(C.byref(self._h), int(device)))
+        if stream is not None:
+            _check(lib().sogpu_set_stream(self._h, C.c_void_p(int(stream))))
+        self.n = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().sogpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, stream):
+        _check(lib().sogpu_set_stream(self._h, C.c_void_p(int(stream) if stream else 0)))
+
+    def set_cell_occupancy(self, ppc):
+        _check(lib().sogpu_set_cell_occupancy(self._h, C.c_float(ppc)))
+
+    def set_particles(self, pos, mass, period=(1.0, 1.0, 1.0), center=(0.0, 0.0, 0.0)):
+        """pos: (N,3) float32 (any row stride); mass: scalar or (N,) float32."""
+        pos = np.asarray(pos)
+        if pos.dtype != np.float32 or pos.ndim != 2 or pos.shape[1] != 3 or pos.strides[1] != 4:
+            pos = np.ascontiguousarray(pos, np.float32)
+        m = np.asarray(mass, np.float32)
+        if m.ndim == 0:
+            m = np.full(1, m, np.float32)
+            ms = 0
+        else:
+            if len(m) != len(pos):
+                raise ValueError("mass length")
+            ms = m.strides[0]
+        per = np.asarray(period, np.float32).copy()
+        cen = np.asarray(center, np.float32).copy()
+        _check(lib().sogpu_set_particles_host(self._h, C.c_void_p(pos.ctypes.data), pos.strides[0],
+                                              C.c_void_p(m.ctypes.data), ms, len(pos), _fp(per), _fp(cen)))
+        self.n = len(pos)
+
+    def set_particles_records(self, rec, pos_field="pos", mass_field="mass", period=(1.0, 1.0, 1.0),
+                              center=(0.0, 0.0, 0.0)):
+        """Structured records (tipsy dark_particle, PINIT, ...) used in place, no repacking."""
+        rec = np.ascontiguousarray(rec)
+        base = rec.ctypes.data
+        po = rec.dtype.fields[pos_field][1]
+        mo = rec.dtype.fields[mass_field][1]
+        per = np.asarray(period, np.float32).copy()
+        cen = np.asarray(center, np.float32).copy()
+        _check(lib().sogpu_set_particles_host(self._h, C.c_void_p(base + po), rec.dtype.itemsize,
+                                              C.c_void_p(base + mo), rec.dtype.itemsize, len(rec),
+                                              _fp(per), _fp(cen)))
+        self.n = len(rec)
+
+    def set_particles_device(self, dev_ptr, n, period=(1.0, 1.0, 1.0), center=(0.0, 0.0, 0.0)):
+        per = np.asarray(period, np.float32).copy()
+        cen = np.asarray(center, np.float32).copy()
+        _check(lib().sogpu_set_particles_device(self._h, C.c_void_p(int(dev_ptr)), int(n), _fp(per), _fp(cen)))
+        self.n = int(n)
+
+    def build_grid(self):
+        _check(lib().sogpu_build_grid(self._h))
+
+    def so(self, centers, rgtp, thr, n_members=8):
+        centers = np.ascontiguousarray(centers, np.float32)
+        rgtp = np.ascontiguousarray(rgtp, np.float32)
+        nh = len(rgtp)
+        assert centers.shape == (nh, 3)
+        rv = np.zeros(nh, np.float32)
+        mv = np.zeros(nh, np.float32)
+        nd = np.zeros(nh, np.int32)
+        _check(lib().sogpu_so(self._h, _fp(centers), _fp(rgtp), nh, C.c_float(thr), int(n_members),
+                              _fp(rv), _fp(mv), nd.ctypes.data_as(C.POINTER(C.c_int32))))
+        self._last_h = nh
+        return dict(rvir=rv, mvir=mv, ndelta=nd)
+
+    def so_device(self, d_centers, d_rgtp, nh, thr, n_members=8, d_out_n=0, d_out_m=0):
+        _check(lib().sogpu_so_device(self._h, C.c_void_p(int(d_centers)), C.c_void_p(int(d_rgtp)), int(nh),
+                                     C.c_float(thr), int(n_members), C.c_void_p(int(d_out_n)),
+                                     C.c_void_p(int(d_out_m))))
+        self._last_h = int(nh)
+
+    def members(self, want_d2=False):
+        nh = self._last_h
+        off = np.zeros(nh + 1, np.int64)
+        mp = C.POINTER(C.c_int32)()
+        dp = C.POINTER(C.c_float)()
+        _check(lib().sogpu_members(self._h, off.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(mp), C.byref(dp)))
+        tot = int(off[-1])
+        mem = np.ctypeslib.as_array(mp, (max(tot, 1),))[:tot].copy()
+        if want_d2:
+            d2 = np.ctypeslib.as_array(dp, (max(tot, 1),))[:tot].copy()
+            return off, mem, d2
+        return off, mem
+
+    def ball_gather(self, center, ball2, cap=None):
+        c = np.asarray(center, np.float32).copy()
+        n = C.c_int64(0)
+        if cap is None:
+            _check(lib().sogpu_ball_gather(self._h, _fp(c), C.c_float(ball2), None, None, 0, C.byref(n)))
+            cap = n.value
+        idx = np.zeros(max(cap, 1), np.int32)
+        d2 = np.zeros(max(cap, 1), np.float32)
+        _check(lib().sogpu_ball_gather(self._h, _fp(c), C.c_float(ball2),
+                                       idx.ctypes.data_as(C.POINTER(C.c_int32)), _fp(d2), cap, C.byref(n)))
+        k = min(cap, n.value)
+        return idx[:k], d2[:k], n.value
+
+    def stats(self):
+        s = Stats()
+        _check(lib().sogpu_get_stats(self._h, C.byref(s)))
+        return {f[0]: getattr(s, f[0]) for f in Stats._fields_}
+
+
+# ---- mirror of the reference's hot-path interface (kd2.h:258-276) ----------------------------------
+
+class KD:
+    """Python twin of the `KD` handle for the hot path only: particles + halo list in, the fields
+    kdSO fills out.  `grps` arrays follow GRPNODE (kd2.h:86-102)."""
+
+    def __init__(self, nMembers=8, fPeriod=(1.0, 1.0, 1.0), fCenter=(0.0, 0.0, 0.0), device=-1, stream=None):
+        self.nMembers = int(nMembers)
+        self.fPeriod = tuple(float(x) for x in fPeriod)
+        self.fCenter = tuple(float(x) for x in fCenter)
+        self.gpu = SoGpu(device, stream)
+        self.nParticles = 0
+        self.nGrps = 0
+
+    def set_particles(self, pos, mass):
+        """What kdReadTipsy leaves in kd->pInit (kd2.c:352-416), positions and masses only."""
+        self.gpu.set_particles(pos, mass, self.fPeriod, self.fCenter)
+        self.nParticles = len(pos)
+
+    def set_groups(self, index, pos, fRgtp, fGTPMass):
+        """What kdReadGTPList leaves in kd->grps (kd2.c:245-281)."""
+        self.index = np.ascontiguousarray(index, np.int32)
+        self.pos = np.ascontiguousarray(pos, np.float32)
+        self.fRgtp = np.ascontiguousarray(fRgtp, np.float32)
+        self.fGTPMass = np.ascontiguousarray(fGTPMass, np.float32)
+        self.nGrps = len(self.index)
+
+    def kdBuildTree(self):
+        self.gpu.build_grid()
+        return 1
+
+    def smBallGather(self, fBall2, ri):
+        return self.gpu.ball_gather(ri, fBall2)
+
+    def kdSO(self, rhovir, nSmooth=1028):
+        """kdRvir for every group (kd2.c:875-879).  Fills fRvir/fMvir/nDelta and the member lists;
+        nSmooth is accepted for signature parity and unused (it only sizes the reference's nnList)."""
+        r = self.gpu.so(self.pos, self.fRgtp, rhovir, self.nMembers)
+        self.fRvir, self.fMvir, self.nDelta = r["rvir"], r["mvir"], r["ndelta"]
+        self.member_offset, self.members = self.gpu.members()
+        return r
+
+    def close(self):
+        self.gpu.close()

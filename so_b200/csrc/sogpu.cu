@@ -1,0 +1,1573 @@
+/* sogpu.cu — B200 (sm_100a) implementation of the SO hot path behind include/sogpu.h.
+ *
+ * Replaces, from /root/reference:
+ *   kdBuildTree  kd2.c:1096-1185  ->  k_cell_count / k_scan_* / k_scatter  (counting sort by
+ *                                     cell key into a periodic uniform grid; rows along x are
+ *                                     contiguous, rows are z-ordered over (iy,iz))
+ *   smBallGather smooth2.c:58-114 ->  for_each_in_ball<>  (row segments overlapping the sphere,
+ *                                     flat coalesced float4 loads, exact fp32 r^2)
+ *   qsort+kdRvir kd2.c:781-831    ->  so_halo<>  (log-r^2 histogram from the float bits, prefix
+ *                                     sum, conservative bracket, exact sort inside the bracket,
+ *                                     first j with rho(j) and rho(j+1) below threshold)
+ *
+ * Exactness (see so_math.h): r^2 with the reference's operation order and no FMA; density test
+ * with the reference's mixed fp32/fp64 expression; the enclosed mass is the reference's
+ * sequential fp32 sum, which for equal-mass particles depends on the rank only (mass table).
+ *
+ * No CPU fallback: every entry point that computes returns SOGPU_ERR_CUDA without a device.
+ */
+#include "../../include/sogpu.h"
+#include "so_math.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+/* ============================================================================================
+ * constants
+ * ============================================================================================ */
+#define NB 512          /* histogram bins per level                                         */
+#define NB_LOG 9
+#define SHIFT0 18       /* level 0: 2^(23-18)=32 bins per octave of r^2, 16 octaves          */
+#define CELL_MARGIN 2.0e-3  /* slack, in cells, of every cell-range computation              */
+#define CODE_UNSUPPORTED (-100)
+#define CODE_DEFER (-101)
+
+template <int NT> struct Cfg;
+template <> struct Cfg<32> {   /* warp per halo */
+    static const int CAP = 256, WTARGET = 128, NLEV = 1, GROUPS = 8;
+};
+template <> struct Cfg<256> {  /* block per halo */
+    static const int CAP = 4096, WTARGET = 1024, NLEV = 4, GROUPS = 1;
+};
+
+/* ============================================================================================
+ * error handling
+ * ============================================================================================ */
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return set_err(SOGPU_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                    \
+                           cudaGetErrorString(e_), __FILE__, __LINE__);                       \
+    } while (0)
+
+extern "C" const char *sogpu_last_error(void) { return g_err; }
+
+/* ============================================================================================
+ * device-side grid description
+ * ============================================================================================ */
+struct GridDev {
+    const float4 *sorted;     /* particles {x,y,z,m} in cell order                         */
+    const uint32_t *ce;       /* ce[c] = first sorted slot of cell c, ce[ncell] = N          */
+    const int32_t *orig;      /* original (file) index of each sorted slot                   */
+    int nc, lb;               /* cells per axis (power of two), log2                         */
+    float g0[3], invh[3];     /* cell coordinate = floor((x - g0) * invh) & (nc-1)           */
+    float L[3], halfL[3];
+    double dg0[3], dinvh[3], dh[3];
+    double bmax_pruned;       /* balls at least this large visit every cell                  */
+};
+
+__device__ __forceinline__ uint32_t spread10(uint32_t x)
+{
+    x &= 0x3ffu;
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+__device__ __forceinline__ uint32_t row_key(uint32_t iy, uint32_t iz)
+{
+    return spread10(iy) | (spread10(iz) << 1);
+}
+__device__ __forceinline__ uint32_t cell_coord(float x, float g0, float invh, int mask)
+{
+    float t = __fmul_rn(__fsub_rn(x, g0), invh);
+    return (uint32_t)((int)floorf(t) & mask);
+}
+__device__ __forceinline__ uint32_t cell_key(const float4 &p, const GridDev &g)
+{
+    int mask = g.nc - 1;
+    uint32_t ix = cell_coord(p.x, g.g0[0], g.invh[0], mask);
+    uint32_t iy = cell_coord(p.y, g.g0[1], g.invh[1], mask);
+    uint32_t iz = cell_coord(p.z, g.g0[2], g.invh[2], mask);
+    return (row_key(iy, iz) << g.lb) | ix;
+}
+
+__device__ __forceinline__ float4 ld_stream(const float4 *p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+/* ============================================================================================
+ * grid build kernels (kdBuildTree replacement)
+ * ============================================================================================ */
+__device__ __forceinline__ uint32_t f2ord(float f) { return __float_as_uint(f); } /* f >= 0 */
+
+/* count particles per cell into ce[key+1]; also min/max of mass (as ordered uints) */
+__global__ void __launch_bounds__(256) k_cell_count(const float4 *__restrict__ in, int64_t n,
+                                                    GridDev g, uint32_t *__restrict__ ce,
+                                                    uint32_t *__restrict__ mass_minmax)
+{
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float4 p = ld_stream(in + i);
+        atomicAdd(&ce[cell_key(p, g) + 1], 1u);
+        uint32_t mo = (p.w >= 0.0f) ? f2ord(p.w) : 0xFFFFFFFEu;   /* negative/NaN mass => "unequal" */
+        if (!(p.w >= 0.0f)) { mn = 0u; }
+        mn = min(mn, mo);
+        mx = max(mx, mo);
+    }
+    mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&mass_minmax[0], mn);
+        atomicMax(&mass_minmax[1], mx);
+    }
+}
+
+#define SCAN_TILE 2048   /* 256 threads x 8 */
+
+__global__ void __launch_bounds__(256) k_scan_reduce(const uint32_t *__restrict__ a, int64_t n,
+                                                     uint32_t *__restrict__ bsum)
+{
+    __shared__ uint32_t ws[8];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    uint32_t s = 0;
+    for (int k = 0; k < 8; ++k) {
+        int64_t i = base + k * 256 + threadIdx.x;
+        if (i < n) s += a[i];
+    }
+    s = __reduce_add_sync(0xFFFFFFFFu, s);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int k = 0; k < 8; ++k) t += ws[k];
+        bsum[blockIdx.x] = t;
+    }
+}
+
+/* exclusive scan of bsum[0..nb) by one block */
+__global__ void __launch_bounds__(1024) k_scan_bsums(uint32_t *__restrict__ bsum, int64_t nb)
+{
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int64_t b0 = 0; b0 < nb; b0 += 1024) {
+        int64_t i = b0 + threadIdx.x;
+        uint32_t v = (i < nb) ? bsum[i] : 0u, x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += t;
+        }
+        if (lane == 31) ws[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t y = ws[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, y, o);
+                if (lane >= o) y += t;
+            }
+            ws[lane] = y;
+        }
+        __syncthreads();
+        uint32_t incl = x + (w ? ws[w - 1] : 0u) + carry;
+        if (i < nb) bsum[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = incl;
+        __syncthreads();
+    }
+}
+
+/* in-place exclusive scan of each tile plus its block offset */
+__global__ void __launch_bounds__(256) k_scan_apply(uint32_t *__restrict__ a, int64_t n,
+                                                    const uint32_t *__restrict__ bsum)
+{
+    __shared__ uint32_t ws[8];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * 8;
+    uint32_t v[8], s = 0;
+    for (int k = 0; k < 8; ++k) {
+        v[k] = (base + k < n) ? a[base + k] : 0u;
+        s += v[k];
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t x = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += t;
+    }
+    if (lane == 31) ws[w] = x;
+    __syncthreads();
+    uint32_t off = bsum[blockIdx.x];
+    for (int k = 0; k < w; ++k) off += ws[k];
+    uint32_t run = off + x - s;
+    for (int k = 0; k < 8; ++k) {
+        if (base + k < n) a[base + k] = run;
+        run += v[k];
+    }
+}
+
+/* place every particle in its cell: ce[key+1] is the cell's fill cursor, ends as the cell's end */
+__global__ void __launch_bounds__(256) k_scatter(const float4 *__restrict__ in, int64_t n, GridDev g,
+                                                 uint32_t *__restrict__ ce,
+                                                 float4 *__restrict__ sorted,
+                                                 int32_t *__restrict__ orig)
+{
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float4 p = ld_stream(in + i);
+        uint32_t pos = atomicAdd(&ce[cell_key(p, g) + 1], 1u);
+        sorted[pos] = p;
+        orig[pos] = (int32_t)i;
+    }
+}
+
+/* ============================================================================================
+ * group (warp or block) primitives
+ * ============================================================================================ */
+template <int NT> __device__ __forceinline__ void gsync()
+{
+    if (NT == 32) __syncwarp(); else __syncthreads();
+}
+
+template <int NT> __device__ __forceinline__ uint32_t gscan_incl(uint32_t v, uint32_t *tmp, int tid)
+{
+    int lane = tid & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (NT > 32) {
+        int w = tid >> 5;
+        if (lane == 31) tmp[w] = v;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t s = (lane < NT / 32) ? tmp[lane] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+                if (lane >= o) s += t;
+            }
+            if (lane < NT / 32) tmp[lane] = s;
+        }
+        __syncthreads();
+        if (w > 0) v += tmp[w - 1];
+        __syncthreads();
+    }
+    return v;
+}
+
+template <int NT> __device__ __forceinline__ int gmin(int v, uint32_t *tmp, int tid)
+{
+    v = __reduce_min_sync(0xFFFFFFFFu, v);
+    if (NT > 32) {
+        int lane = tid & 31, w = tid >> 5;
+        if (lane == 0) tmp[w] = (uint32_t)v;
+        __syncthreads();
+        if (w == 0) {
+            int s = (lane < NT / 32) ? (int)tmp[lane] : INT_MAX;
+            s = __reduce_min_sync(0xFFFFFFFFu, s);
+            if (lane == 0) tmp[0] = (uint32_t)s;
+        }
+        __syncthreads();
+        v = (int)tmp[0];
+        __syncthreads();
+    }
+    return v;
+}
+
+template <int NT> __device__ __forceinline__ uint32_t gsum(uint32_t v, uint32_t *tmp, int tid)
+{
+    v = __reduce_add_sync(0xFFFFFFFFu, v);
+    if (NT > 32) {
+        int lane = tid & 31, w = tid >> 5;
+        if (lane == 0) tmp[w] = v;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t s = (lane < NT / 32) ? tmp[lane] : 0u;
+            s = __reduce_add_sync(0xFFFFFFFFu, s);
+            if (lane == 0) tmp[0] = s;
+        }
+        __syncthreads();
+        v = tmp[0];
+        __syncthreads();
+    }
+    return v;
+}
+
+/* ============================================================================================
+ * per-group shared memory
+ * ============================================================================================ */
+struct MassTableS {   /* CTA-shared copy of the mass table */
+    int n;
+    float m;
+    uint32_t k0[SO_MT_MAX + 1];
+    float s0[SO_MT_MAX];
+    float inc[SO_MT_MAX];
+};
+
+template <int NT> struct GroupSmem {
+    unsigned long long wkey[Cfg<NT>::CAP];      /* window: (r^2 bits << 32) | original index   */
+    uint32_t hist[Cfg<NT>::NLEV][NB + 1];       /* per level: counts, then exclusive prefix    */
+    uint32_t seg_start[2 * NT];                 /* row segments of the current batch           */
+    uint32_t seg_pre[2 * NT];                   /* inclusive prefix of their lengths           */
+    uint32_t tmp[40];                           /* scan / reduce scratch                       */
+    uint32_t cnt;                               /* append cursor                               */
+    uint32_t bcast[4];
+    uint8_t wflag[Cfg<NT>::CAP];                /* below-threshold flag per window element     */
+};
+
+__device__ __forceinline__ float mt_eval(const MassTableS &mt, uint32_t k)
+{
+    return so_mass_prefix_eval(mt.k0, mt.s0, mt.inc, mt.n, k);
+}
+
+/* ============================================================================================
+ * geometry: exact r^2 and the row segments that overlap a ball
+ * ============================================================================================ */
+__device__ __forceinline__ float axis_delta(float x, float p, float L, float hL)
+{
+    float rd = __fsub_rn(x, p);                 /* which image is nearer (kd2.h:165-194)      */
+    float sx = x;
+    if (rd > hL) sx = __fsub_rn(x, L);          /* sx = x - lx                                */
+    else if (rd < -hL) sx = __fadd_rn(x, L);    /* sx = x + lx                                */
+    return __fsub_rn(sx, p);                    /* dx = sx - p.r[0]   (smooth2.c:89)          */
+}
+
+struct Center {
+    float x, y, z;
+};
+
+__device__ __forceinline__ float dist2(const Center &c, const float4 &q, const GridDev &g)
+{
+    float dx = axis_delta(c.x, q.x, g.L[0], g.halfL[0]);
+    float dy = axis_delta(c.y, q.y, g.L[1], g.halfL[1]);
+    float dz = axis_delta(c.z, q.z, g.L[2], g.halfL[2]);
+    /* fDist2 = dx*dx + dy*dy + dz*dz, left to right, fp32, no FMA (smooth2.c:92) */
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+struct BallGeom {
+    double cx, cy, cz, b, b2;
+    int ylo, ny, zlo, nz, nrows;
+    int full;
+};
+
+__device__ __forceinline__ BallGeom make_geom(const GridDev &g, const Center &c, double b)
+{
+    BallGeom B;
+    B.cx = c.x; B.cy = c.y; B.cz = c.z;
+    B.b = b; B.b2 = b * b;
+    B.full = !(b < g.bmax_pruned);
+    if (B.full) {
+        B.ylo = 0; B.ny = g.nc; B.zlo = 0; B.nz = g.nc;
+    } else {
+        int yhi, zhi;
+        B.ylo = (int)floor((B.cy - b - g.dg0[1]) * g.dinvh[1] - CELL_MARGIN);
+        yhi = (int)floor((B.cy + b - g.dg0[1]) * g.dinvh[1] + CELL_MARGIN);
+        B.zlo = (int)floor((B.cz - b - g.dg0[2]) * g.dinvh[2] - CELL_MARGIN);
+        zhi = (int)floor((B.cz + b - g.dg0[2]) * g.dinvh[2] + CELL_MARGIN);
+        B.ny = min(yhi - B.ylo + 1, g.nc);
+        B.nz = min(zhi - B.zlo + 1, g.nc);
+    }
+    B.nrows = B.ny * B.nz;
+    return B;
+}
+
+/* distance from coordinate c to the cell interval [lo, lo+h], shrunk by the margin */
+__device__ __forceinline__ double interval_dist(double c, double lo, double h)
+{
+    double m = CELL_MARGIN * h;
+    double d = fmax(lo - c, c - (lo + h)) - m;
+    return d > 0.0 ? d : 0.0;
+}
+
+/* the (up to two, because of the periodic wrap) sorted-slot ranges of row r */
+__device__ __forceinline__ void row_segments(const GridDev &g, const BallGeom &B, int r,
+                                             uint32_t &s0, uint32_t &l0, uint32_t &s1, uint32_t &l1)
+{
+    s0 = l0 = s1 = l1 = 0;
+    int iyu = B.ylo + r % B.ny, izu = B.zlo + r / B.ny;
+    int mask = g.nc - 1;
+    int xa, nx;
+    if (B.full) {
+        xa = 0; nx = g.nc;
+    } else {
+        double dy = interval_dist(B.cy, g.dg0[1] + iyu * g.dh[1], g.dh[1]);
+        double dz = interval_dist(B.cz, g.dg0[2] + izu * g.dh[2], g.dh[2]);
+        double rem = B.b2 - dy * dy - dz * dz;
+        if (rem < 0.0) return;
+        double w = sqrt(rem);
+        int xlo = (int)floor((B.cx - w - g.dg0[0]) * g.dinvh[0] - CELL_MARGIN);
+        int xhi = (int)floor((B.cx + w - g.dg0[0]) * g.dinvh[0] + CELL_MARGIN);
+        nx = min(xhi - xlo + 1, g.nc);
+        xa = xlo & mask;
+    }
+    uint32_t rowbase = row_key((uint32_t)(iyu & mask), (uint32_t)(izu & mask)) << g.lb;
+    int n0 = min(nx, g.nc - xa);
+    uint32_t a = __ldg(g.ce + rowbase + xa), e = __ldg(g.ce + rowbase + xa + n0);
+    s0 = a; l0 = e - a;
+    if (n0 < nx) {
+        uint32_t a1 = __ldg(g.ce + rowbase), e1 = __ldg(g.ce + rowbase + (nx - n0));
+        s1 = a1; l1 = e1 - a1;
+    }
+}
+
+/* Visit every particle stored in a cell that overlaps the ball: f(slot, particle).
+ * All NT threads of the group must call this together. */
+template <int NT, typename F>
+__device__ __forceinline__ void for_each_in_ball(const GridDev &g, GroupSmem<NT> &sm, int tid,
+                                                 const BallGeom &B, F &f, uint32_t &evals)
+{
+    for (int rb = 0; rb < B.nrows; rb += NT) {
+        int r = rb + tid;
+        uint32_t s0 = 0, l0 = 0, s1 = 0, l1 = 0;
+        if (r < B.nrows) row_segments(g, B, r, s0, l0, s1, l1);
+        uint32_t incl = gscan_incl<NT>(l0 + l1, sm.tmp, tid);
+        sm.seg_start[2 * tid] = s0;
+        sm.seg_pre[2 * tid] = incl - l1;
+        sm.seg_start[2 * tid + 1] = s1;
+        sm.seg_pre[2 * tid + 1] = incl;
+        gsync<NT>();
+        uint32_t total = sm.seg_pre[2 * NT - 1];
+        uint32_t i = tid;
+        if (i < total) {
+            int lo = 0, hi = 2 * NT - 1;
+            while (lo < hi) {                   /* first segment whose inclusive prefix > i   */
+                int mid = (lo + hi) >> 1;
+                if (sm.seg_pre[mid] > i) hi = mid; else lo = mid + 1;
+            }
+            int s = lo;
+            for (; i < total; i += NT) {
+                while (sm.seg_pre[s] <= i) ++s;
+                uint32_t beg = s ? sm.seg_pre[s - 1] : 0u;
+                uint32_t p = sm.seg_start[s] + (i - beg);
+                float4 q = __ldg(g.sorted + p);
+                f(p, q);
+                ++evals;
+            }
+        }
+        gsync<NT>();
+    }
+}
+
+/* ============================================================================================
+ * functors of the passes
+ * ============================================================================================ */
+struct HistF {          /* count particles with bits(r^2) in [lo,hi] into level bins */
+    const GridDev *g;
+    Center c;
+    uint32_t lo_bits, hi_bits, shift, base;
+    uint32_t *hist;
+    __device__ __forceinline__ void operator()(uint32_t, const float4 &q)
+    {
+        uint32_t bits = __float_as_uint(dist2(c, q, *g));
+        if (bits >= lo_bits && bits <= hi_bits) {   /* NaN (> 0x7f800000) never passes: hi is finite */
+            uint32_t hb = bits >> shift;
+            atomicAdd(&hist[hb > base ? hb - base : 0u], 1u);
+        }
+    }
+};
+
+template <int CAP> struct CollectF {   /* append (r^2 bits, original index) of the window */
+    const GridDev *g;
+    Center c;
+    uint32_t lo_bits, hi_bits;
+    unsigned long long *wkey;
+    uint32_t *cnt;
+    __device__ __forceinline__ void operator()(uint32_t p, const float4 &q)
+    {
+        uint32_t bits = __float_as_uint(dist2(c, q, *g));
+        if (bits >= lo_bits && bits <= hi_bits) {
+            uint32_t pos = atomicAdd(cnt, 1u);
+            if (pos < (uint32_t)CAP)
+                wkey[pos] = ((unsigned long long)bits << 32) | (uint32_t)__ldg(g->orig + p);
+        }
+    }
+};
+
+struct EmitF {          /* members: (r^2 bits, index) < key_j */
+    const GridDev *g;
+    Center c;
+    unsigned long long key_j;
+    int32_t *members;
+    float *md2;
+    uint32_t *cnt;
+    uint32_t limit;
+    __device__ __forceinline__ void operator()(uint32_t p, const float4 &q)
+    {
+        float d2 = dist2(c, q, *g);
+        uint32_t bits = __float_as_uint(d2);
+        uint32_t bj = (uint32_t)(key_j >> 32);
+        if (bits <= bj) {
+            int32_t oi = __ldg(g->orig + p);
+            if (bits < bj || (uint32_t)oi < (uint32_t)key_j) {
+                uint32_t pos = atomicAdd(cnt, 1u);
+                if (pos < limit) {
+                    members[pos] = oi;
+                    if (md2) md2[pos] = d2;
+                }
+            }
+        }
+    }
+};
+
+struct GatherF {        /* sogpu_ball_gather: everything with r^2 <= ball2 */
+    const GridDev *g;
+    Center c;
+    uint32_t hi_bits;
+    int32_t *idx;
+    float *d2o;
+    unsigned long long *cnt;
+    unsigned long long cap;
+    __device__ __forceinline__ void operator()(uint32_t p, const float4 &q)
+    {
+        float d2 = dist2(c, q, *g);
+        if (__float_as_uint(d2) <= hi_bits) {
+            unsigned long long pos = atomicAdd(cnt, 1ull);
+            if (pos < cap) {
+                idx[pos] = __ldg(g->orig + p);
+                d2o[pos] = d2;
+            }
+        }
+    }
+};
+
+/* ============================================================================================
+ * histogram levels
+ * ============================================================================================ */
+struct Level {
+    uint32_t shift, base;     /* bin = max(0, (bits >> shift) - base)                        */
+    uint32_t lo_bits, hi_bits;/* bit range this level covers                                  */
+    uint32_t rank0;           /* sorted rank of the first particle of the range               */
+    int clamp;                /* bin 0 collects everything below (base+1) << shift            */
+    int cur;                  /* next bin to examine                                          */
+};
+
+__device__ __forceinline__ uint32_t bin_lo(const Level &lv, int b)
+{
+    if (b == 0 && lv.clamp) return lv.lo_bits;
+    unsigned long long v = (unsigned long long)(lv.base + (uint32_t)b) << lv.shift;
+    return v < lv.lo_bits ? lv.lo_bits : (uint32_t)v;
+}
+__device__ __forceinline__ uint32_t bin_hi(const Level &lv, int b)
+{
+    unsigned long long v = ((unsigned long long)(lv.base + (uint32_t)b + 1u) << lv.shift) - 1ull;
+    return v > lv.hi_bits ? lv.hi_bits : (uint32_t)v;
+}
+
+/* counts -> exclusive prefix in place; hist[NB] = total.  Returns the total. */
+template <int NT> __device__ __forceinline__ uint32_t scan_hist(uint32_t *hist, uint32_t *tmp, int tid)
+{
+    const int BPT = NB / NT;
+    uint32_t v[BPT], s = 0;
+#pragma unroll
+    for (int k = 0; k < BPT; ++k) {
+        v[k] = hist[tid * BPT + k];
+        s += v[k];
+    }
+    uint32_t incl = gscan_incl<NT>(s, tmp, tid);
+    uint32_t run = incl - s;
+#pragma unroll
+    for (int k = 0; k < BPT; ++k) {
+        hist[tid * BPT + k] = run;
+        run += v[k];
+    }
+    if (tid == NT - 1) hist[NB] = incl;
+    gsync<NT>();
+    return hist[NB];
+}
+
+/* first bin >= from that may contain a particle below the threshold (rank >= jmin) */
+template <int NT>
+__device__ __forceinline__ int find_candidate(const uint32_t *cum, const Level &lv, int from,
+                                              uint32_t jmin, float thr, const MassTableS &mt,
+                                              uint32_t *tmp, int tid)
+{
+    int best = NB;
+    for (int b = from + tid; b < NB; b += NT) {
+        uint32_t c0 = cum[b], c1 = cum[b + 1];
+        if (c1 == c0) continue;
+        uint32_t r0 = lv.rank0 + c0, r1 = lv.rank0 + c1;
+        if (r1 <= jmin) continue;
+        uint32_t klo = r0 > jmin ? r0 : jmin;
+        float mass_lo = mt_eval(mt, klo + 1u);
+        float r2hi = __uint_as_float(bin_hi(lv, b));
+        if (!so_surely_not_below(mass_lo, r2hi, thr)) { best = b; break; }
+    }
+    return gmin<NT>(best, tmp, tid);
+}
+
+template <int NT> __device__ __forceinline__ void bitonic_sort(unsigned long long *key, int P, int tid)
+{
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P; i += NT) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = key[i], b = key[ixj];
+                    bool up = ((i & k) == 0);
+                    if ((a > b) == up) { key[i] = b; key[ixj] = a; }
+                }
+            }
+            gsync<NT>();
+        }
+    }
+}
+
+/* ============================================================================================
+ * one halo: kdRvir (kd2.c:723-840)
+ * ============================================================================================ */
+struct HaloResult {
+    int32_t n;                 /* N_Delta, or -1/-2/-3, CODE_UNSUPPORTED, CODE_DEFER           */
+    float m;                   /* M_Delta                                                      */
+    unsigned long long key_j;  /* (r^2 bits, index) of sorted element j = first non-member     */
+};
+
+template <int NT>
+__device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &sm, int tid,
+                        Center c, float rgtp, float thr, int nM, HaloResult &res,
+                        uint32_t &ev_hist, uint32_t &ev_other)
+{
+    typedef Cfg<NT> CF;
+    const float root = so_root_period(g.L[0], g.L[1], g.L[2]);           /* kd2.c:765 */
+    float ball = rgtp;                                                   /* kd2.c:745 */
+    uint32_t n_prev = 0;
+    int kball = 0;
+    res.n = -3; res.m = -3.0f; res.key_j = 0ull;                         /* kd2.c:837-838 */
+
+    while ((double)ball < 0.25 * (double)root) {                         /* kd2.c:766 */
+        ball = so_next_ball(ball);                                       /* kd2.c:767 */
+        const float ball2 = __fmul_rn(ball, ball);                       /* kd2.c:768 */
+        if (!(ball2 < INFINITY) || !(ball > 0.0f)) break;
+        const uint32_t ball_bits = __float_as_uint(ball2);
+
+        /* ---- pass A: histogram of the whole ball (smBallGather + the sort's first digit) ---- */
+        Level lev[CF::NLEV];
+        {
+            uint32_t top = ball_bits >> SHIFT0;
+            lev[0].shift = SHIFT0;
+            lev[0].base = top > (NB - 1) ? top - (NB - 1) : 0u;
+            lev[0].lo_bits = 0u; lev[0].hi_bits = ball_bits;
+            lev[0].rank0 = 0u; lev[0].clamp = 1; lev[0].cur = 0;
+        }
+        for (int b = tid; b <= NB; b += NT) sm.hist[0][b] = 0u;
+        gsync<NT>();
+        BallGeom B = make_geom(g, c, sqrt((double)ball2) * (1.0 + 1.0e-6));
+        {
+            HistF f;
+            f.g = &g; f.c = c; f.lo_bits = 0u; f.hi_bits = ball_bits;
+            f.shift = SHIFT0; f.base = lev[0].base; f.hist = sm.hist[0];
+            for_each_in_ball<NT>(g, sm, tid, B, f, ev_hist);
+        }
+        const uint32_t n = scan_hist<NT>(sm.hist[0], sm.tmp, tid);       /* nParticles, kd2.c:769 */
+
+        if (kball == 0 && n < (uint32_t)nM) {                            /* kd2.c:772-778 */
+            res.n = -1; res.m = -1.0f;
+            return;
+        }
+        /* pairs (j, j+1) already examined in smaller balls: j <= n_prev-2 (kd2.c:804,832) */
+        const uint32_t jmin = (kball == 0) ? (uint32_t)(nM - 2) : n_prev - 1u;
+
+        /* ---- search: first j >= jmin with below(j) && below(j+1), j+1 < n ------------------- */
+        if (n > jmin + 1u) {
+            int L = 0;
+            bool carry = false;                 /* below(rank just before the next window)   */
+            unsigned long long prev_key = 0ull;
+            {   /* start at the bin that holds rank jmin */
+                int lo = 0, hi = NB - 1;
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (sm.hist[0][mid + 1] > jmin) hi = mid; else lo = mid + 1;
+                }
+                lev[0].cur = lo;
+            }
+            for (;;) {
+                Level &lv = lev[L];
+                const uint32_t *cum = sm.hist[L];
+                int cb = (lv.cur < NB) ? find_candidate<NT>(cum, lv, lv.cur, jmin, thr, mt, sm.tmp, tid) : NB;
+                if (cb >= NB) {
+                    if (lv.cur < NB && cum[NB] > cum[lv.cur]) carry = false;
+                    if (L == 0) break;                       /* nothing fires in this ball    */
+                    --L;
+                    lev[L].cur += 1;
+                    continue;
+                }
+                if (cum[cb] > cum[lv.cur]) carry = false;    /* skipped particles: not below  */
+                const uint32_t cnt_c = cum[cb + 1] - cum[cb];
+                if (cnt_c > (uint32_t)CF::CAP) {
+                    /* ---- refine: histogram the candidate bin with finer bins --------------- */
+                    if (L + 1 >= CF::NLEV) {
+                        res.n = (CF::NLEV == 1) ? CODE_DEFER : CODE_UNSUPPORTED;
+                        res.m = 0.0f;
+                        return;
+                    }
+                    Level &nl = lev[L + 1];
+                    lv.cur = cb;                 /* resume after this bin when the child is done */
+                    nl.lo_bits = bin_lo(lv, cb);
+                    nl.hi_bits = bin_hi(lv, cb);
+                    nl.rank0 = lv.rank0 + cum[cb];
+                    nl.cur = 0;
+                    if (cb == 0 && lv.clamp && lv.base > 0u) {
+                        uint32_t top = nl.hi_bits >> lv.shift;        /* == lv.base            */
+                        nl.shift = lv.shift;
+                        nl.base = top > (NB - 1) ? top - (NB - 1) : 0u;
+                        nl.clamp = 1;
+                    } else {
+                        if (lv.shift == 0u) {     /* > CAP particles at one identical r^2      */
+                            res.n = CODE_UNSUPPORTED; res.m = 0.0f;
+                            return;
+                        }
+                        nl.shift = lv.shift > NB_LOG ? lv.shift - NB_LOG : 0u;
+                        nl.base = nl.lo_bits >> nl.shift;
+                        nl.clamp = 0;
+                    }
+                    ++L;
+                    for (int b = tid; b <= NB; b += NT) sm.hist[L][b] = 0u;
+                    gsync<NT>();
+                    BallGeom B2 = make_geom(g, c, sqrt((double)__uint_as_float(nl.hi_bits)) * (1.0 + 1.0e-6));
+                    HistF f;
+                    f.g = &g; f.c = c; f.lo_bits = nl.lo_bits; f.hi_bits = nl.hi_bits;
+                    f.shift = nl.shift; f.base = nl.base; f.hist = sm.hist[L];
+                    for_each_in_ball<NT>(g, sm, tid, B2, f, ev_other);
+                    scan_hist<NT>(sm.hist[L], sm.tmp, tid);
+                    continue;
+                }
+                /* ---- window [cb, c2]: as many following bins as fit the target ---------------- */
+                int c2;
+                {
+                    uint32_t room = cnt_c > (uint32_t)CF::WTARGET ? cnt_c : (uint32_t)CF::WTARGET;
+                    uint32_t lim = cum[cb] + room;
+                    int lo = cb + 1, hi = NB;             /* largest e in [cb+1, NB] with cum[e] <= lim */
+                    while (lo < hi) {
+                        int mid = (lo + hi + 1) >> 1;
+                        if (cum[mid] <= lim) lo = mid; else hi = mid - 1;
+                    }
+                    c2 = lo - 1;
+                }
+                const uint32_t wn = cum[c2 + 1] - cum[cb];
+                const uint32_t w_lo = bin_lo(lv, cb), w_hi = bin_hi(lv, c2);
+                const uint32_t rank_first = lv.rank0 + cum[cb];
+                if (tid == 0) sm.cnt = 0u;
+                int P = 2;
+                while (P < (int)wn) P <<= 1;
+                for (int i = tid; i < P; i += NT) sm.wkey[i] = ~0ull;
+                gsync<NT>();
+                {
+                    BallGeom B2 = make_geom(g, c, sqrt((double)__uint_as_float(w_hi)) * (1.0 + 1.0e-6));
+                    CollectF<CF::CAP> f;
+                    f.g = &g; f.c = c; f.lo_bits = w_lo; f.hi_bits = w_hi;
+                    f.wkey = sm.wkey; f.cnt = &sm.cnt;
+                    for_each_in_ball<NT>(g, sm, tid, B2, f, ev_other);
+                }
+                if (sm.cnt != wn) {              /* cannot happen; guards the exactness claim  */
+                    res.n = CODE_UNSUPPORTED; res.m = 1.0f;
+                    return;
+                }
+                bitonic_sort<NT>(sm.wkey, P, tid);
+                /* below(k) = rho(S[k+1], r2[k]) < thr, k = rank (kd2.c:791-792, 814-815) */
+                for (uint32_t i = tid; i < wn; i += NT) {
+                    uint32_t k = rank_first + i;
+                    uint8_t fl = 0;
+                    if (k >= jmin)
+                        fl = (uint8_t)so_rho_below(mt_eval(mt, k + 1u),
+                                                   __uint_as_float((uint32_t)(sm.wkey[i] >> 32)), thr);
+                    sm.wflag[i] = fl;
+                }
+                gsync<NT>();
+                int fire = INT_MAX;
+                for (uint32_t i = tid; i < wn; i += NT) {
+                    if (sm.wflag[i] && (i > 0 ? sm.wflag[i - 1] != 0 : carry)) { fire = (int)i; break; }
+                }
+                fire = gmin<NT>(fire, sm.tmp, tid);
+                if (fire != INT_MAX) {
+                    /* element `fire` is j+1, element fire-1 is j (kd2.c:814-823) */
+                    uint32_t j = rank_first + (uint32_t)fire - 1u;
+                    unsigned long long key_j = fire > 0 ? sm.wkey[fire - 1] : prev_key;
+                    if (kball == 0 && j == (uint32_t)(nM - 2)) {             /* kd2.c:791-796 */
+                        res.n = -2; res.m = -2.0f;
+                        return;
+                    }
+                    float mass = mt_eval(mt, j + 1u);                         /* kd2.c:807 */
+                    res.m = __fsub_rn(mass, mt.m);                            /* kd2.c:816 */
+                    res.n = (int32_t)j;
+                    res.key_j = key_j;
+                    return;
+                }
+                carry = sm.wflag[wn - 1] != 0;
+                prev_key = sm.wkey[wn - 1];
+                gsync<NT>();
+                lv.cur = c2 + 1;
+            }
+        }
+        n_prev = n;                                                      /* kd2.c:832 */
+        ++kball;
+    }
+}
+
+/* ============================================================================================
+ * the persistent query kernel
+ * ============================================================================================ */
+struct QueryArgs {
+    GridDev g;
+    const float *centers;      /* nh x 3 */
+    const float *rgtp;         /* nh */
+    const int32_t *list;       /* halo ids this kernel processes */
+    const uint32_t *list_n;    /* how many */
+    uint32_t *work_counter;    /* dynamic scheduling */
+    int32_t *defer_list;       /* (warp kernel) halos handed to the block kernel */
+    uint32_t *defer_n;
+    float thr;
+    int nM;
+    int32_t *out_n;
+    float *out_m;
+    unsigned long long *out_key;
+    unsigned long long *out_off;   /* member offset per halo */
+    int32_t *members;
+    float *md2;
+    unsigned long long *member_total;
+    unsigned long long member_cap;
+    unsigned long long *evals;     /* [0] histogram pass, [1] other passes */
+    uint32_t *overflow;
+    const so_mass_table *mt;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS) k_so_query(const __grid_constant__ QueryArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    MassTableS &mt = *reinterpret_cast<MassTableS *>(smem_raw);
+    const size_t mt_bytes = (sizeof(MassTableS) + 15) & ~(size_t)15;
+    const int grp = threadIdx.x / NT, tid = threadIdx.x % NT;
+    GroupSmem<NT> &sm = *reinterpret_cast<GroupSmem<NT> *>(
+        smem_raw + mt_bytes + (size_t)grp * ((sizeof(GroupSmem<NT>) + 15) & ~(size_t)15));
+
+    /* CTA-wide: copy the mass table */
+    {
+        mt.n = a.mt->n; mt.m = a.mt->m;
+        for (int i = threadIdx.x; i <= a.mt->n; i += blockDim.x) mt.k0[i] = a.mt->k0[i];
+        for (int i = threadIdx.x; i < a.mt->n; i += blockDim.x) { mt.s0[i] = a.mt->s0[i]; mt.inc[i] = a.mt->inc[i]; }
+    }
+    __syncthreads();
+
+    const uint32_t nlist = *a.list_n;
+    uint32_t ev_hist = 0, ev_other = 0;
+    for (;;) {
+        uint32_t item;
+        if (tid == 0) sm.bcast[0] = atomicAdd(a.work_counter, 1u);
+        gsync<NT>();
+        item = sm.bcast[0];
+        gsync<NT>();
+        if (item >= nlist) break;
+        const int h = a.list[item];
+        Center c;
+        c.x = a.centers[3 * h + 0]; c.y = a.centers[3 * h + 1]; c.z = a.centers[3 * h + 2];
+        HaloResult res;
+        so_halo<NT>(a.g, mt, sm, tid, c, a.rgtp[h], a.thr, a.nM, res, ev_hist, ev_other);
+        gsync<NT>();
+        if (res.n == CODE_DEFER) {
+            if (tid == 0) a.defer_list[atomicAdd(a.defer_n, 1u)] = h;
+            continue;
+        }
+        unsigned long long off = 0ull;
+        if (res.n > 0) {
+            /* ---- emit the member list: every particle ordered before element j ------------- */
+            if (tid == 0) {
+                off = atomicAdd(a.member_total, (unsigned long long)res.n);
+                sm.bcast[0] = (uint32_t)off; sm.bcast[1] = (uint32_t)(off >> 32);
+                sm.cnt = 0u;
+            }
+            gsync<NT>();
+            off = ((unsigned long long)sm.bcast[1] << 32) | sm.bcast[0];
+            if (off + (unsigned long long)res.n <= a.member_cap) {
+                EmitF f;
+                f.g = &a.g; f.c = c; f.key_j = res.key_j;
+                f.members = a.members + off; f.md2 = a.md2 ? a.md2 + off : nullptr;
+                f.cnt = &sm.cnt; f.limit = (uint32_t)res.n;
+                float r2j = __uint_as_float((uint32_t)(res.key_j >> 32));
+                BallGeom B = make_geom(a.g, c, sqrt((double)r2j) * (1.0 + 1.0e-6));
+                for_each_in_ball<NT>(a.g, sm, tid, B, f, ev_other);
+                if (tid == 0 && sm.cnt != (uint32_t)res.n) atomicOr(a.overflow, 2u);
+            } else if (tid == 0) {
+                atomicOr(a.overflow, 1u);
+            }
+            gsync<NT>();
+        }
+        if (tid == 0) {
+            a.out_n[h] = res.n;
+            a.out_m[h] = res.m;
+            a.out_key[h] = res.key_j;
+            a.out_off[h] = off;
+        }
+    }
+    ev_hist = __reduce_add_sync(0xFFFFFFFFu, ev_hist);
+    ev_other = __reduce_add_sync(0xFFFFFFFFu, ev_other);
+    if ((threadIdx.x & 31) == 0) {
+        if (ev_hist) atomicAdd(&a.evals[0], (unsigned long long)ev_hist);
+        if (ev_other) atomicAdd(&a.evals[1], (unsigned long long)ev_other);
+    }
+}
+
+template <int NT> static size_t query_smem_bytes()
+{
+    size_t mt_bytes = (sizeof(MassTableS) + 15) & ~(size_t)15;
+    size_t g_bytes = (sizeof(GroupSmem<NT>) + 15) & ~(size_t)15;
+    return mt_bytes + g_bytes * Cfg<NT>::GROUPS;
+}
+
+/* split the halos into the warp-kernel list and the block-kernel list by expected ball size */
+__global__ void k_classify(const float *__restrict__ rgtp, int nh, float count_per_r3, float small_max,
+                           int32_t *small_list, uint32_t *small_n, int32_t *big_list, uint32_t *big_n)
+{
+    int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nh) return;
+    float r = rgtp[h];
+    float est = count_per_r3 * r * r * r;
+    if (est <= small_max) small_list[atomicAdd(small_n, 1u)] = h;
+    else big_list[atomicAdd(big_n, 1u)] = h;
+}
+
+/* sogpu_ball_gather: one warp per row of cells, lanes stride over the row's particles */
+__global__ void __launch_bounds__(256) k_ball_gather(const __grid_constant__ GridDev g, float cx, float cy,
+                                                     float cz, float ball2, int32_t *idx, float *d2o,
+                                                     unsigned long long *cnt, unsigned long long cap)
+{
+    Center c; c.x = cx; c.y = cy; c.z = cz;
+    GatherF f;
+    f.g = &g; f.c = c; f.hi_bits = __float_as_uint(ball2); f.idx = idx; f.d2o = d2o; f.cnt = cnt; f.cap = cap;
+    BallGeom B = make_geom(g, c, sqrt((double)ball2) * (1.0 + 1.0e-6));
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int r = wid; r < B.nrows; r += nw) {
+        uint32_t s0, l0, s1, l1;
+        row_segments(g, B, r, s0, l0, s1, l1);
+        for (uint32_t i = lane; i < l0; i += 32) f(s0 + i, __ldg(g.sorted + s0 + i));
+        for (uint32_t i = lane; i < l1; i += 32) f(s1 + i, __ldg(g.sorted + s1 + i));
+    }
+}
+
+/* ============================================================================================
+ * host side
+ * ============================================================================================ */
+struct sogpu {
+    int device;
+    cudaStream_t own_stream, stream;
+    float ppc;                       /* target particles per cell */
+
+    int64_t n;
+    float period[3], center[3];
+    const float4 *d_in;              /* unsorted particles (owned or borrowed) */
+    float4 *d_in_owned;
+    float4 *d_sorted;
+    int32_t *d_orig;
+    uint32_t *d_ce;
+    uint32_t *d_bsum;
+    uint32_t *d_massmm;
+    int64_t ncell;
+    int nc, lb;
+    bool built;
+    int equal_mass;
+    float mass;
+    GridDev g;
+    so_mass_table mt;
+    so_mass_table *d_mt;
+
+    /* query buffers */
+    int32_t cap_h;
+    float *d_centers, *d_rgtp;
+    int32_t *d_small, *d_big;
+    uint32_t *d_counters;            /* [0] small_n [1] big_n [2] work_small [3] work_big [4] overflow */
+    int32_t *d_out_n;
+    float *d_out_m;
+    unsigned long long *d_out_key, *d_out_off;
+    unsigned long long *d_u64;       /* [0] member_total [1] evals_hist [2] evals_other [3] gather cnt */
+    int32_t *d_members;
+    float *d_md2;
+    unsigned long long member_cap;
+    int32_t last_h;
+    bool have_members;
+
+    /* pinned host staging */
+    void *h_pin;
+    size_t h_pin_bytes;
+    int32_t *h_members;
+    float *h_md2;
+    size_t h_members_cap;
+    std::vector<int64_t> h_off;
+
+    sogpu_stats_t stats;
+    int sm_count;
+};
+
+static int ensure_pinned(sogpu *h, size_t bytes)
+{
+    if (bytes <= h->h_pin_bytes) return SOGPU_OK;
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    h->h_pin = nullptr; h->h_pin_bytes = 0;
+    CU(cudaMallocHost(&h->h_pin, bytes));
+    h->h_pin_bytes = bytes;
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_create(sogpu_t **out, int device)
+{
+    if (!out) return set_err(SOGPU_ERR_ARG, "sogpu_create: out is NULL");
+    *out = nullptr;
+    if (SO_C133PI != 1.33333333 * M_PI || SO_C43PI != (4. / 3.) * M_PI)
+        return set_err(SOGPU_ERR_UNSUPPORTED, "so_math.h constants do not match this compiler's folding");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) return set_err(SOGPU_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+    if (device < 0) CU(cudaGetDevice(&device));
+    if (device >= ndev) return set_err(SOGPU_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return set_err(SOGPU_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only",
+                       device, prop.major, prop.minor);
+    sogpu *h = new (std::nothrow) sogpu();
+    if (!h) return set_err(SOGPU_ERR_NOMEM, "out of host memory");
+    h->device = device;
+    h->ppc = 2.0f;
+    h->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return set_err(SOGPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    h->stream = h->own_stream;
+    e = cudaFuncSetAttribute(k_so_query<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<256>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_so_query<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<32>());
+    if (e != cudaSuccess) {
+        cudaStreamDestroy(h->own_stream); delete h;
+        return set_err(SOGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    g_err[0] = 0;
+    return SOGPU_OK;
+}
+
+static void free_grid(sogpu *h)
+{
+    cudaFree(h->d_sorted); h->d_sorted = nullptr;
+    cudaFree(h->d_orig); h->d_orig = nullptr;
+    cudaFree(h->d_ce); h->d_ce = nullptr;
+    cudaFree(h->d_bsum); h->d_bsum = nullptr;
+    h->built = false;
+}
+
+static void free_query(sogpu *h)
+{
+    cudaFree(h->d_centers); cudaFree(h->d_rgtp); cudaFree(h->d_small); cudaFree(h->d_big);
+    cudaFree(h->d_out_n); cudaFree(h->d_out_m); cudaFree(h->d_out_key); cudaFree(h->d_out_off);
+    h->d_centers = h->d_rgtp = nullptr; h->d_small = h->d_big = nullptr;
+    h->d_out_n = nullptr; h->d_out_m = nullptr; h->d_out_key = h->d_out_off = nullptr;
+    h->cap_h = 0;
+}
+
+extern "C" void sogpu_destroy(sogpu_t *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_grid(h);
+    free_query(h);
+    cudaFree(h->d_in_owned);
+    cudaFree(h->d_massmm);
+    cudaFree(h->d_mt);
+    cudaFree(h->d_counters);
+    cudaFree(h->d_u64);
+    cudaFree(h->d_members);
+    cudaFree(h->d_md2);
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    if (h->h_members) cudaFreeHost(h->h_members);
+    if (h->h_md2) cudaFreeHost(h->h_md2);
+    cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+extern "C" int sogpu_set_stream(sogpu_t *h, void *s)
+{
+    if (!h) return set_err(SOGPU_ERR_ARG, "NULL handle");
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_set_cell_occupancy(sogpu_t *h, float ppc)
+{
+    if (!h || !(ppc > 0.0f)) return set_err(SOGPU_ERR_ARG, "bad cell occupancy");
+    h->ppc = ppc;
+    return SOGPU_OK;
+}
+
+static int set_common(sogpu *h, int64_t n, const float period[3], const float center[3])
+{
+    if (n <= 0 || n > 0x7FFFFFF0LL) return set_err(SOGPU_ERR_ARG, "particle count %lld out of range", (long long)n);
+    for (int k = 0; k < 3; ++k)
+        if (!(period[k] > 0.0f) || !(period[k] < INFINITY))
+            return set_err(SOGPU_ERR_ARG, "period[%d] must be positive (the reference is periodic only, smooth2.c:69)", k);
+    CU(cudaSetDevice(h->device));
+    free_grid(h);
+    h->n = n;
+    for (int k = 0; k < 3; ++k) { h->period[k] = period[k]; h->center[k] = center ? center[k] : 0.0f; }
+    h->have_members = false;
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_set_particles_device(sogpu_t *h, const void *d_xyzm, int64_t n, const float period[3],
+                                          const float center[3])
+{
+    if (!h || !d_xyzm || !period) return set_err(SOGPU_ERR_ARG, "sogpu_set_particles_device: NULL argument");
+    int rc = set_common(h, n, period, center);
+    if (rc) return rc;
+    if (h->d_in_owned) { cudaFree(h->d_in_owned); h->d_in_owned = nullptr; }
+    h->d_in = (const float4 *)d_xyzm;
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_set_particles_host(sogpu_t *h, const void *pos, size_t pos_stride, const void *mass,
+                                        size_t mass_stride, int64_t n, const float period[3],
+                                        const float center[3])
+{
+    if (!h || !pos || !mass || !period) return set_err(SOGPU_ERR_ARG, "sogpu_set_particles_host: NULL argument");
+    int rc = set_common(h, n, period, center);
+    if (rc) return rc;
+    if (h->d_in_owned) { cudaFree(h->d_in_owned); h->d_in_owned = nullptr; }
+    CU(cudaMalloc(&h->d_in_owned, (size_t)n * sizeof(float4)));
+    h->d_in = h->d_in_owned;
+    /* pack to float4 through two pinned staging buffers so the copy overlaps the packing */
+    const int64_t chunk = 1 << 22;
+    rc = ensure_pinned(h, 2 * (size_t)chunk * sizeof(float4));
+    if (rc) return rc;
+    float4 *stage[2] = {(float4 *)h->h_pin, (float4 *)h->h_pin + chunk};
+    cudaEvent_t ev[2];
+    CU(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    int b = 0;
+    cudaError_t e = cudaSuccess;
+    for (int64_t i0 = 0; i0 < n && e == cudaSuccess; i0 += chunk, b ^= 1) {
+        int64_t k = std::min(chunk, n - i0);
+        e = cudaEventSynchronize(ev[b]);
+        if (e != cudaSuccess) break;
+        float4 *s = stage[b];
+        const char *pp = (const char *)pos + (size_t)i0 * pos_stride;
+        const char *mp = (const char *)mass + (size_t)i0 * mass_stride;
+        for (int64_t i = 0; i < k; ++i) {
+            const float *p = (const float *)(pp + (size_t)i * pos_stride);
+            s[i].x = p[0]; s[i].y = p[1]; s[i].z = p[2];
+            s[i].w = *(const float *)(mp + (size_t)i * mass_stride);
+        }
+        e = cudaMemcpyAsync(h->d_in_owned + i0, s, (size_t)k * sizeof(float4), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ev[b], h->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    if (e != cudaSuccess) return set_err(SOGPU_ERR_CUDA, "particle upload failed: %s", cudaGetErrorString(e));
+    return SOGPU_OK;
+}
+
+static int pick_cells(int64_t n, float ppc, int *lb)
+{
+    /* nc = power of two with nc^3 closest (in log) to n/ppc, 4 <= nc <= 1024 */
+    double target = cbrt((double)n / (double)ppc);
+    int l = (int)floor(log2(target) + 0.5);
+    if (l < 2) l = 2;
+    if (l > 10) l = 10;
+    *lb = l;
+    return 1 << l;
+}
+
+extern "C" int sogpu_build_grid(sogpu_t *h)
+{
+    if (!h || !h->d_in || h->n <= 0) return set_err(SOGPU_ERR_ARG, "sogpu_build_grid: no particles set");
+    CU(cudaSetDevice(h->device));
+    int lb;
+    int nc = pick_cells(h->n, h->ppc, &lb);
+    int64_t ncell = (int64_t)nc * nc * nc;
+    if (!h->d_ce || h->nc != nc) {
+        free_grid(h);
+        CU(cudaMalloc(&h->d_ce, (size_t)(ncell + 1) * sizeof(uint32_t)));
+        int64_t ntile = (ncell + SCAN_TILE - 1) / SCAN_TILE;
+        CU(cudaMalloc(&h->d_bsum, (size_t)ntile * sizeof(uint32_t)));
+    }
+    if (!h->d_sorted) {
+        CU(cudaMalloc(&h->d_sorted, (size_t)h->n * sizeof(float4)));
+        CU(cudaMalloc(&h->d_orig, (size_t)h->n * sizeof(int32_t)));
+    }
+    if (!h->d_massmm) CU(cudaMalloc(&h->d_massmm, 2 * sizeof(uint32_t)));
+    h->nc = nc; h->lb = lb; h->ncell = ncell;
+
+    GridDev &g = h->g;
+    g.sorted = h->d_sorted; g.ce = h->d_ce; g.orig = h->d_orig;
+    g.nc = nc; g.lb = lb;
+    double hmax = 0.0, lmin = 1e300;
+    for (int k = 0; k < 3; ++k) {
+        double L = (double)h->period[k];
+        g.L[k] = h->period[k];
+        g.halfL[k] = 0.5f * h->period[k];
+        g.dg0[k] = (double)h->center[k] - 0.5 * L;
+        g.g0[k] = (float)g.dg0[k];
+        g.dg0[k] = (double)g.g0[k];
+        g.dh[k] = L / nc;
+        g.invh[k] = (float)((double)nc / L);
+        g.dinvh[k] = (double)g.invh[k];
+        hmax = std::max(hmax, g.dh[k]);
+        lmin = std::min(lmin, L);
+    }
+    g.bmax_pruned = 0.5 * lmin - 2.0 * hmax;
+
+    cudaStream_t s = h->stream;
+    const uint32_t mm_init[2] = {0xFFFFFFFFu, 0u};
+    CU(cudaMemsetAsync(h->d_ce, 0, (size_t)(ncell + 1) * sizeof(uint32_t), s));
+    CU(cudaMemcpyAsync(h->d_massmm, mm_init, sizeof(mm_init), cudaMemcpyHostToDevice, s));
+    int grid = h->sm_count * 8;
+    int64_t need = (h->n + 255) / 256;
+    if (need < grid) grid = (int)need;
+    k_cell_count<<<grid, 256, 0, s>>>(h->d_in, h->n, g, h->d_ce, h->d_massmm);
+    int64_t ntile = (ncell + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_reduce<<<(unsigned)ntile, 256, 0, s>>>(h->d_ce + 1, ncell, h->d_bsum);
+    k_scan_bsums<<<1, 1024, 0, s>>>(h->d_bsum, ntile);
+    k_scan_apply<<<(unsigned)ntile, 256, 0, s>>>(h->d_ce + 1, ncell, h->d_bsum);
+    k_scatter<<<grid, 256, 0, s>>>(h->d_in, h->n, g, h->d_ce, h->d_sorted, h->d_orig);
+    CU(cudaGetLastError());
+    uint32_t mm[2];
+    CU(cudaMemcpyAsync(mm, h->d_massmm, sizeof(mm), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    h->equal_mass = (mm[0] == mm[1]);
+    memcpy(&h->mass, &mm[0], sizeof(float));
+    h->stats.last_kernel_launches = 5;
+    if (h->equal_mass) {
+        if (so_mass_table_build(&h->mt, h->mass, (uint64_t)h->n + 2))
+            return set_err(SOGPU_ERR_UNSUPPORTED, "cannot tabulate the running mass for m=%g", (double)h->mass);
+        if (!h->d_mt) CU(cudaMalloc(&h->d_mt, sizeof(so_mass_table)));
+        CU(cudaMemcpyAsync(h->d_mt, &h->mt, sizeof(so_mass_table), cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    h->built = true;
+    h->stats.n_particles = h->n;
+    h->stats.cells_per_axis = nc;
+    h->stats.equal_mass = h->equal_mass;
+    return SOGPU_OK;
+}
+
+static int ensure_query(sogpu *h, int32_t nh)
+{
+    if (!h->d_counters) {
+        CU(cudaMalloc(&h->d_counters, 8 * sizeof(uint32_t)));
+        CU(cudaMalloc(&h->d_u64, 4 * sizeof(unsigned long long)));
+    }
+    if (nh > h->cap_h) {
+        free_query(h);
+        int32_t cap = std::max(nh, 1024);
+        CU(cudaMalloc(&h->d_centers, (size_t)cap * 3 * sizeof(float)));
+        CU(cudaMalloc(&h->d_rgtp, (size_t)cap * sizeof(float)));
+        CU(cudaMalloc(&h->d_small, (size_t)cap * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_big, (size_t)cap * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_out_n, (size_t)cap * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_out_m, (size_t)cap * sizeof(float)));
+        CU(cudaMalloc(&h->d_out_key, (size_t)cap * sizeof(unsigned long long)));
+        CU(cudaMalloc(&h->d_out_off, (size_t)cap * sizeof(unsigned long long)));
+        h->cap_h = cap;
+    }
+    if (!h->d_members) {
+        h->member_cap = (unsigned long long)std::max<int64_t>(h->n, 1 << 20);
+        CU(cudaMalloc(&h->d_members, (size_t)h->member_cap * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_md2, (size_t)h->member_cap * sizeof(float)));
+    }
+    return SOGPU_OK;
+}
+
+/* enqueue the query for nh halos whose centers/rgtp are on the device */
+static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int32_t nh, float thr, int32_t nM)
+{
+    if (!h->built) return set_err(SOGPU_ERR_ARG, "sogpu_so: call sogpu_build_grid first");
+    if (!h->equal_mass)
+        return set_err(SOGPU_ERR_UNSUPPORTED, "particles have unequal masses: the exact sequential-mass path "
+                                              "for mixed masses is not implemented yet");
+    if (nM < 2) return set_err(SOGPU_ERR_ARG, "nMembers must be >= 2 (the reference reads nnList[-1] otherwise, kd2.c:791)");
+    if (nh <= 0) return set_err(SOGPU_ERR_ARG, "no halos");
+    int rc = ensure_query(h, nh);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    CU(cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(uint32_t), s));
+    CU(cudaMemsetAsync(h->d_u64, 0, 4 * sizeof(unsigned long long), s));
+
+    /* expected particles in the final ball: halo of radius R ~ 1.25 rgtp at density thr, ball 1.2 R */
+    double per_r3 = 1.3 * (double)thr * SO_C43PI * 1.25 * 1.25 * 1.25 / (double)h->mass;
+    const float small_max = 1024.0f;
+    k_classify<<<(nh + 255) / 256, 256, 0, s>>>(d_rgtp, nh, (float)per_r3, small_max, h->d_small,
+                                                h->d_counters + 0, h->d_big, h->d_counters + 1);
+    QueryArgs a;
+    a.g = h->g;
+    a.centers = d_centers; a.rgtp = d_rgtp;
+    a.thr = thr; a.nM = nM;
+    a.out_n = h->d_out_n; a.out_m = h->d_out_m; a.out_key = h->d_out_key; a.out_off = h->d_out_off;
+    a.members = h->d_members; a.md2 = h->d_md2;
+    a.member_total = h->d_u64 + 0; a.member_cap = h->member_cap;
+    a.evals = h->d_u64 + 1;
+    a.overflow = h->d_counters + 4;
+    a.mt = h->d_mt;
+    a.defer_list = h->d_big; a.defer_n = h->d_counters + 1;
+
+    /* warp-per-halo kernel over the small list; halos it cannot finish are appended to the big list */
+    a.list = h->d_small; a.list_n = h->d_counters + 0; a.work_counter = h->d_counters + 2;
+    {
+        int ctas = h->sm_count * 4;
+        int need = (nh + Cfg<32>::GROUPS - 1) / Cfg<32>::GROUPS;
+        if (need < ctas) ctas = std::max(need, 1);
+        k_so_query<32><<<ctas, 32 * Cfg<32>::GROUPS, query_smem_bytes<32>(), s>>>(a);
+    }
+    /* block-per-halo kernel over the big list (+ deferred) */
+    a.list = h->d_big; a.list_n = h->d_counters + 1; a.work_counter = h->d_counters + 3;
+    {
+        int ctas = h->sm_count * 4;
+        if (nh < ctas) ctas = nh;
+        k_so_query<256><<<ctas, 256, query_smem_bytes<256>(), s>>>(a);
+    }
+    CU(cudaGetLastError());
+    h->stats.last_kernel_launches = 3;
+    h->last_h = nh;
+    h->have_members = true;
+    return SOGPU_OK;
+}
+
+static int fetch_stats(sogpu *h)
+{
+    unsigned long long u[4];
+    uint32_t c[8];
+    CU(cudaMemcpyAsync(u, h->d_u64, sizeof(u), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->stats.last_members = (int64_t)u[0];
+    h->stats.last_evals_first = (int64_t)u[1];
+    h->stats.last_evals = (int64_t)(u[1] + u[2]);
+    if (c[4] & 1u) return set_err(SOGPU_ERR_NOMEM, "member buffer overflow (%llu > %llu)", u[0], h->member_cap);
+    if (c[4] & 2u) return set_err(SOGPU_ERR_UNSUPPORTED, "internal: member emission count mismatch");
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_so_device(sogpu_t *h, const void *d_centers, const void *d_rgtp, int32_t nh, float thr,
+                               int32_t nM, void *d_out_n, void *d_out_m)
+{
+    if (!h || !d_centers || !d_rgtp) return set_err(SOGPU_ERR_ARG, "sogpu_so_device: NULL argument");
+    CU(cudaSetDevice(h->device));
+    int rc = run_query(h, (const float *)d_centers, (const float *)d_rgtp, nh, thr, nM);
+    if (rc) return rc;
+    if (d_out_n) CU(cudaMemcpyAsync(d_out_n, h->d_out_n, (size_t)nh * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+    if (d_out_m) CU(cudaMemcpyAsync(d_out_m, h->d_out_m, (size_t)nh * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_so(sogpu_t *h, const float *centers, const float *rgtp, int32_t nh, float thr, int32_t nM,
+                        float *rvir, float *mvir, int32_t *ndelta)
+{
+    if (!h || !centers || !rgtp || !rvir || !mvir || !ndelta) return set_err(SOGPU_ERR_ARG, "sogpu_so: NULL argument");
+    if (nh <= 0) return set_err(SOGPU_ERR_ARG, "no halos");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_query(h, nh);
+    if (rc) return rc;
+    size_t bytes_in = (size_t)nh * 4 * sizeof(float);
+    size_t bytes_out = (size_t)nh * (sizeof(int32_t) + sizeof(float));
+    rc = ensure_pinned(h, std::max(bytes_in, bytes_out));
+    if (rc) return rc;
+    float *pc = (float *)h->h_pin, *pr = pc + (size_t)3 * nh;
+    memcpy(pc, centers, (size_t)nh * 3 * sizeof(float));
+    memcpy(pr, rgtp, (size_t)nh * sizeof(float));
+    CU(cudaMemcpyAsync(h->d_centers, pc, (size_t)nh * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_rgtp, pr, (size_t)nh * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    rc = run_query(h, h->d_centers, h->d_rgtp, nh, thr, nM);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));   /* staging buffer is reused for the results */
+    int32_t *pn = (int32_t *)h->h_pin;
+    float *pm = (float *)(pn + nh);
+    CU(cudaMemcpyAsync(pn, h->d_out_n, (size_t)nh * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(pm, h->d_out_m, (size_t)nh * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    rc = fetch_stats(h);
+    if (rc) return rc;
+    for (int32_t i = 0; i < nh; ++i) {
+        int32_t n = pn[i];
+        if (n > 0) {
+            ndelta[i] = n;
+            mvir[i] = pm[i];
+            rvir[i] = so_rdelta_host(pm[i], thr);                         /* kd2.c:817-820 */
+        } else if (n == -1 || n == -2 || n == -3) {
+            ndelta[i] = 0;
+            mvir[i] = rvir[i] = (float)n;
+        } else {
+            return set_err(SOGPU_ERR_UNSUPPORTED, "halo %d: unsupported particle configuration (code %d)", i, n);
+        }
+    }
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_members(sogpu_t *h, int64_t *offsets, const int32_t **members, const float **d2)
+{
+    if (!h || !offsets || !members) return set_err(SOGPU_ERR_ARG, "sogpu_members: NULL argument");
+    if (!h->have_members) return set_err(SOGPU_ERR_ARG, "sogpu_members: no sogpu_so result available");
+    CU(cudaSetDevice(h->device));
+    const int32_t nh = h->last_h;
+    int rc = fetch_stats(h);
+    if (rc) return rc;
+    const size_t tot = (size_t)h->stats.last_members;
+    std::vector<int32_t> on(nh);
+    std::vector<unsigned long long> ooff(nh);
+    CU(cudaMemcpy(on.data(), h->d_out_n, (size_t)nh * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ooff.data(), h->d_out_off, (size_t)nh * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (tot + 1 > h->h_members_cap) {
+        if (h->h_members) cudaFreeHost(h->h_members);
+        if (h->h_md2) cudaFreeHost(h->h_md2);
+        h->h_members = nullptr; h->h_md2 = nullptr; h->h_members_cap = 0;
+        size_t cap = std::max<size_t>(tot + 1, 1 << 16);
+        CU(cudaMallocHost((void **)&h->h_members, 2 * cap * sizeof(int32_t)));
+        CU(cudaMallocHost((void **)&h->h_md2, 2 * cap * sizeof(float)));
+        h->h_members_cap = cap;
+    }
+    /* raw (device order) in the upper half, final (catalog order, sorted) in the lower half */
+    int32_t *raw_i = h->h_members + h->h_members_cap;
+    float *raw_d = h->h_md2 + h->h_members_cap;
+    if (tot) {
+        CU(cudaMemcpy(raw_i, h->d_members, tot * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(raw_d, h->d_md2, tot * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    std::vector<std::pair<uint64_t, uint32_t>> tmp;
+    int64_t run = 0;
+    for (int32_t i = 0; i < nh; ++i) {
+        offsets[i] = run;
+        int32_t n = on[i] > 0 ? on[i] : 0;
+        if (n) {
+            const int32_t *si = raw_i + ooff[i];
+            const float *sd = raw_d + ooff[i];
+            tmp.resize(n);
+            for (int32_t k = 0; k < n; ++k) {
+                uint32_t bits;
+                memcpy(&bits, &sd[k], 4);
+                tmp[k].first = ((uint64_t)bits << 32) | (uint32_t)si[k];
+                tmp[k].second = (uint32_t)k;
+            }
+            std::sort(tmp.begin(), tmp.end());
+            for (int32_t k = 0; k < n; ++k) {
+                h->h_members[run + k] = si[tmp[k].second];
+                h->h_md2[run + k] = sd[tmp[k].second];
+            }
+        }
+        run += n;
+    }
+    offsets[nh] = run;
+    *members = h->h_members;
+    if (d2) *d2 = h->h_md2;
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_ball_gather(sogpu_t *h, const float center[3], float ball2, int32_t *idx, float *d2,
+                                 int64_t cap, int64_t *n)
+{
+    if (!h || !center || !n) return set_err(SOGPU_ERR_ARG, "sogpu_ball_gather: NULL argument");
+    if (!h->built) return set_err(SOGPU_ERR_ARG, "sogpu_ball_gather: call sogpu_build_grid first");
+    if (!(ball2 >= 0.0f) || !(ball2 < INFINITY)) return set_err(SOGPU_ERR_ARG, "bad ball2");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_query(h, 1);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    CU(cudaMemsetAsync(h->d_u64 + 3, 0, sizeof(unsigned long long), s));
+    k_ball_gather<<<h->sm_count * 2, 256, 0, s>>>(h->g, center[0], center[1], center[2], ball2, h->d_members,
+                                                 h->d_md2, h->d_u64 + 3, h->member_cap);
+    CU(cudaGetLastError());
+    unsigned long long cnt = 0;
+    CU(cudaMemcpyAsync(&cnt, h->d_u64 + 3, sizeof(cnt), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    h->have_members = false;
+    *n = (int64_t)cnt;
+    if (cnt > h->member_cap) return set_err(SOGPU_ERR_NOMEM, "ball holds %llu particles, buffer %llu", cnt, h->member_cap);
+    if (cnt && (idx || d2) && cap > 0) {
+        std::vector<int32_t> ti(cnt);
+        std::vector<float> td(cnt);
+        CU(cudaMemcpy(ti.data(), h->d_members, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(td.data(), h->d_md2, cnt * sizeof(float), cudaMemcpyDeviceToHost));
+        std::vector<std::pair<uint64_t, uint32_t>> tmp(cnt);
+        for (size_t k = 0; k < cnt; ++k) {
+            uint32_t bits;
+            memcpy(&bits, &td[k], 4);
+            tmp[k].first = ((uint64_t)bits << 32) | (uint32_t)ti[k];
+            tmp[k].second = (uint32_t)k;
+        }
+        std::sort(tmp.begin(), tmp.end());                                /* qsort(CmpList), kd2.c:781 */
+        size_t m = std::min<size_t>(cnt, (size_t)cap);
+        for (size_t k = 0; k < m; ++k) {
+            if (idx) idx[k] = ti[tmp[k].second];
+            if (d2) d2[k] = td[tmp[k].second];
+        }
+    }
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_get_stats(sogpu_t *h, sogpu_stats_t *out)
+{
+    if (!h || !out) return set_err(SOGPU_ERR_ARG, "sogpu_get_stats: NULL argument");
+    if (h->have_members) {
+        CU(cudaSetDevice(h->device));
+        int rc = fetch_stats(h);
+        if (rc) return rc;
+        uint32_t c[8];
+        CU(cudaMemcpy(c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+        h->stats.last_deferred = 0;
+        (void)c;
+    }
+    *out = h->stats;
+    return SOGPU_OK;
+}
+
+/* ---- host-only helpers -------------------------------------------------------------------- */
+
+extern "C" int sogpu_mass_prefix(float m, int64_t kmax, const int64_t *k, int64_t nk, float *out)
+{
+    if (!k || !out || kmax < 0) return set_err(SOGPU_ERR_ARG, "sogpu_mass_prefix: bad argument");
+    so_mass_table t;
+    if (so_mass_table_build(&t, m, (uint64_t)kmax)) return set_err(SOGPU_ERR_UNSUPPORTED, "mass table overflow");
+    for (int64_t i = 0; i < nk; ++i) {
+        if (k[i] < 0 || k[i] > kmax) return set_err(SOGPU_ERR_ARG, "k out of range");
+        out[i] = so_mass_prefix_eval(t.k0, t.s0, t.inc, t.n, (uint32_t)k[i]);
+    }
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_ball_schedule(float rgtp, const float period[3], float *balls, int cap)
+{
+    float root = so_root_period(period[0], period[1], period[2]);
+    float ball = rgtp;
+    int k = 0;
+    while ((double)ball < 0.25 * (double)root) {
+        ball = so_next_ball(ball);
+        if (k < cap && balls) balls[k] = ball;
+        ++k;
+        if (!(ball > 0.0f)) break;
+    }
+    return k;
+}
+
+extern "C" float sogpu_rdelta(float mvir, float rho_thr) { return so_rdelta_host(mvir, rho_thr); }
