@@ -245,6 +245,8 @@ def run_so_ref(snap_path, gtp_path, out_base, delta=None, extra=(), inst=False, 
 def read_inst_file(path):
     """Records written by so_ref_inst: {index: (j, iOrder[j], fDist2[j])}."""
     out = {}
+    if not os.path.exists(path):      # no halo succeeded: the hook never opened the file
+        return out
     with open(path, "rb") as f:
         buf = f.read()
     off = 0

@@ -1,0 +1,52 @@
+"""The oracle against the reference binary itself, on fresh seeded inputs (runs wherever
+oracle/_ref/so_ref_inst exists: it is built from /root/reference by oracle/Makefile and
+travels to the GPU box as a prebuilt file)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from so_b200 import synth, tipsy
+
+pytestmark = pytest.mark.skipif(not po.ref_available("so_ref_inst"),
+                                reason="reference binary not built (oracle/_ref/so_ref_inst)")
+
+
+@pytest.mark.parametrize("seed,omega0,delta", [(101, 1.0, 200.0), (102, 0.3, 200.0), (103, 1.0, 500.0)])
+def test_oracle_bit_exact_against_reference_binary(tmp_path, seed, omega0, delta):
+    s = synth.make_snapshot(40 ** 3, 25, seed=seed, nmax=6000, omega0=omega0)
+    snap, gtp, out, inst = (str(tmp_path / n) for n in ("s.tipsy", "h.gtp", "o", "o.inst"))
+    tipsy.write_tipsy(snap, s.time, dark=tipsy.dark_from_arrays(s.pos, s.mass))
+    tipsy.write_gtp(gtp, s.time, s.centers, s.rgtp, s.gtp_mass)
+    po.run_so_ref(snap, gtp, out, delta=delta, extra=["-gtp", "-O", repr(omega0)], inst=True, inst_file=inst)
+    rec = po.read_inst_file(inst)
+    _, star = tipsy.read_gtp(out + ".sogtp")
+    thr = np.float32(np.float32(delta) * np.float32(omega0))
+    res = po.Oracle(s.pos, s.mass).so(s.centers, s.rgtp, thr, 8)
+    for i in range(s.h):
+        if res["rvir"][i] > 0 and star["eps"][i] > -10:
+            assert res["rvir"][i].tobytes() == star["eps"][i].tobytes()
+            assert res["mvir"][i].tobytes() == star["mass"][i].tobytes()
+        if res["ndelta"][i] > 0:
+            j, order, _ = rec[i + 1]
+            assert j == res["ndelta"][i]
+            a = res["members"][res["member_offset"][i]:res["member_offset"][i + 1]]
+            assert np.array_equal(np.sort(a), np.sort(order))
+        else:
+            assert (i + 1) not in rec and star["eps"][i] == res["rvir"][i]
+
+
+def test_timed_driver_agrees_with_reference_main(tmp_path):
+    """so_ref_timed (pristine reference objects, our timing main) = so_ref's .sogtp."""
+    if not po.ref_available("so_ref_timed"):
+        pytest.skip("so_ref_timed not built")
+    s = synth.make_snapshot(32 ** 3, 12, seed=104, nmax=2000)
+    snap, gtp = str(tmp_path / "s.tipsy"), str(tmp_path / "h.gtp")
+    tipsy.write_tipsy(snap, s.time, dark=tipsy.dark_from_arrays(s.pos, s.mass))
+    tipsy.write_gtp(gtp, s.time, s.centers, s.rgtp, s.gtp_mass)
+    po.run_so_ref(snap, gtp, str(tmp_path / "a"), delta=200.0, extra=["-gtp"])
+    t = po.run_so_ref_timed(snap, gtp, 200.0, 8, 1.0, str(tmp_path / "b"))
+    assert t["n"] == s.n and t["h"] == s.h and t["t_build"] > 0 and t["t_so"] > 0
+    a = open(str(tmp_path / "a.sogtp"), "rb").read()
+    b = open(str(tmp_path / "b.sogtp"), "rb").read()
+    # bytes 28..31 are the uninitialised padding of `struct dump` (kd2.c:1272,1297)
+    assert a[:28] == b[:28] and a[32:] == b[32:]

@@ -1,0 +1,235 @@
+"""Parity of the CUDA path (through the C-ABI) with the oracle and with the reference's golden
+outputs.  Integer/index results and the fp32 outputs are compared BIT-EXACT; the north-star
+tolerance for R_Delta / M_Delta is 1e-6 relative, which bit equality satisfies trivially."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from so_b200 import api, synth
+from tests.util import GOLDEN_CASES, assert_so_equal, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(pos, mass, centers, rgtp, thr, n_members=8, period=(1.0, 1.0, 1.0), center=(0.0, 0.0, 0.0),
+            ppc=None):
+    g = api.SoGpu()
+    if ppc:
+        g.set_cell_occupancy(ppc)
+    g.set_particles(pos, mass, period, center)
+    g.build_grid()
+    r = g.so(centers, rgtp, thr, n_members)
+    r["member_offset"], r["members"], r["members_d2"] = g.members(want_d2=True)
+    r["stats"] = g.stats()
+    g.close()
+    return r
+
+
+def check_against_oracle(pos, mass, centers, rgtp, thr, n_members=8, period=(1.0, 1.0, 1.0), **kw):
+    r = run_gpu(pos, mass, centers, rgtp, thr, n_members, period, **kw)
+    ref = po.Oracle(pos, mass, period).so(centers, rgtp, np.float32(thr), n_members)
+    assert_so_equal(r, ref["rvir"], ref["mvir"], ref["ndelta"])
+    assert np.array_equal(r["member_offset"], ref["member_offset"])
+    assert np.array_equal(r["members"], ref["members"])          # same (r^2, index) order
+    assert r["stats"]["last_members"] == int(ref["member_offset"][-1])
+    return r, ref
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_reference_outputs(name):
+    """CUDA path vs what the reference binary itself produced (tests/golden)."""
+    s, g = load_golden(name)
+    r = run_gpu(s.pos, s.mass, g["centers"], g["rgtp"], g["thr"], int(g["n_members"]))
+    sub = g["rvir"] <= -10.0
+    err = (g["rvir"] < 0) & ~sub
+    ok = ~err & ~sub
+    assert np.array_equal(r["rvir"][err], g["rvir"][err]) and np.array_equal(r["mvir"][err], g["rvir"][err])
+    assert r["rvir"][ok].tobytes() == g["rvir"][ok].tobytes()
+    assert r["mvir"][ok].tobytes() == g["mvir_sogtp"][ok].tobytes()
+    assert np.array_equal(r["ndelta"], g["ndelta"])
+    for i in range(len(g["rgtp"])):
+        a = r["members"][r["member_offset"][i]:r["member_offset"][i + 1]]
+        b = g["members"][g["member_offset"][i]:g["member_offset"][i + 1]]
+        assert np.array_equal(np.sort(a), np.sort(b)), "halo %d" % i
+
+
+@pytest.mark.parametrize("seed,n,h,nmax", [(1, 32 ** 3, 20, 2000), (2, 64 ** 3, 200, 8000), (3, 100000, 64, 20000)])
+def test_seeded_snapshots_vs_oracle(seed, n, h, nmax):
+    s = synth.make_snapshot(n, h, seed=seed, nmax=nmax)
+    check_against_oracle(s.pos, s.mass, s.centers, s.rgtp, 200.0)
+
+
+def test_config0_full_size_vs_oracle():
+    """BASELINE.json configs[0]: 128^3, 1000 halos, Delta = 200 rho_crit, z = 0."""
+    s = synth.config(0)
+    r, ref = check_against_oracle(s.pos, s.mass, s.centers, s.rgtp, 200.0)
+    assert (ref["rvir"] > 0).all()
+
+
+def test_non_power_of_two_mass_sequential_sum():
+    """m = 0.3/N is not a power of two: M_Delta must be the SEQUENTIAL fp32 sum (SURVEY trap #1)."""
+    s = synth.make_snapshot(60 ** 3, 5, seed=31, omega0=0.3, sizes=[50000, 20000, 7000, 900, 50], nmax=1e5)
+    thr = np.float32(np.float32(200.0) * np.float32(0.3))
+    r, ref = check_against_oracle(s.pos, s.mass, s.centers, s.rgtp, thr)
+    assert ref["ndelta"].max() > 30000
+
+
+def test_large_halos_use_block_kernel_and_refinement():
+    s = synth.make_snapshot(128 ** 3, 6, seed=32, sizes=[400000, 150000, 60000, 20000, 3000, 100], nmax=1e6)
+    r, ref = check_against_oracle(s.pos, s.mass, s.centers, s.rgtp, 200.0)
+    assert ref["ndelta"].max() > 300000
+
+
+def test_centers_on_the_periodic_boundary():
+    s = synth.make_snapshot(48 ** 3, 30, seed=33, nmax=3000)
+    # shift everything so that halos straddle the box faces, re-wrap into [-0.5,0.5)
+    shift = np.array([0.5 - s.centers[0, 0], 0.5 - s.centers[1, 1], 0.5 - s.centers[2, 2]], np.float64)
+    pos = synth._wrap(s.pos.astype(np.float64) + shift)
+    cen = synth._wrap(s.centers.astype(np.float64) + shift)
+    check_against_oracle(pos, s.mass, cen, s.rgtp, 200.0)
+    # centres given outside the box (one period away) must give the same member sets
+    cen2 = cen.copy()
+    cen2[::2, 0] += np.float32(1.0)
+    check_against_oracle(pos, s.mass, cen2, s.rgtp, 200.0)
+
+
+def test_other_period_and_grid_center():
+    rng = np.random.default_rng(5)
+    s = synth.make_snapshot(40 ** 3, 20, seed=34, nmax=2500)
+    L = 2.5
+    pos = (s.pos * np.float32(L)).astype(np.float32)
+    cen = (s.centers * np.float32(L)).astype(np.float32)
+    rg = (s.rgtp * np.float32(L)).astype(np.float32)
+    thr = np.float32(200.0 / L ** 3)
+    check_against_oracle(pos, s.mass, cen, rg, thr, period=(L, L, L))
+    # data in [0,L): grid centred at L/2, and (second run) left at the default 0 -> cells wrap
+    pos2 = (pos + np.float32(L / 2)).astype(np.float32)
+    pos2[pos2 >= np.float32(L)] -= np.float32(L)
+    cen2 = (cen + np.float32(L / 2)).astype(np.float32)
+    check_against_oracle(pos2, s.mass, cen2, rg, thr, period=(L, L, L), center=(L / 2, L / 2, L / 2))
+    check_against_oracle(pos2, s.mass, cen2, rg, thr, period=(L, L, L))
+    del rng
+
+
+@pytest.mark.parametrize("nmem", [2, 4, 8, 16, 64])
+def test_nmembers_and_error_codes(nmem):
+    s = synth.make_snapshot(32 ** 3, 12, seed=35, nmax=1500)
+    rng = np.random.default_rng(7)
+    vc = (rng.random((12, 3)) - 0.5).astype(np.float32)
+    vr = np.concatenate([np.full(6, 0.015), np.full(6, 0.07)]).astype(np.float32)
+    centers = np.concatenate([s.centers, vc])
+    rgtp = np.concatenate([s.rgtp, vr])
+    r, ref = check_against_oracle(s.pos, s.mass, centers, rgtp, 200.0, n_members=nmem)
+    assert set(np.unique(ref["rvir"][ref["rvir"] < 0])) <= {-1.0, -2.0, -3.0}
+
+
+def test_threshold_never_reached_gives_minus3():
+    s = synth.make_snapshot(24 ** 3, 4, seed=36, nmax=600)
+    r, ref = check_against_oracle(s.pos, s.mass, s.centers, s.rgtp, 0.5)
+    assert (r["rvir"] == -3.0).all() and (r["mvir"] == -3.0).all() and (r["ndelta"] == 0).all()
+
+
+def test_cell_size_does_not_change_results():
+    s = synth.make_snapshot(48 ** 3, 40, seed=37, nmax=5000)
+    base = run_gpu(s.pos, s.mass, s.centers, s.rgtp, 200.0)
+    for ppc in (0.25, 8.0, 64.0):
+        r = run_gpu(s.pos, s.mass, s.centers, s.rgtp, 200.0, ppc=ppc)
+        assert_so_equal(r, base["rvir"], base["mvir"], base["ndelta"])
+        assert np.array_equal(r["members"], base["members"])
+
+
+def test_records_layout_and_tiny_inputs():
+    """AoS input with stride (tipsy dark records) and N smaller than the reference's nSmooth."""
+    from so_b200 import tipsy
+    s = synth.make_snapshot(900, 2, seed=38, nmin=20, nmax=120)
+    d = tipsy.dark_from_arrays(s.pos, s.mass)
+    g = api.SoGpu()
+    g.set_particles_records(d)
+    g.build_grid()
+    r = g.so(s.centers, s.rgtp, 200.0)
+    off, mem = g.members()
+    ref = po.Oracle(s.pos, s.mass).so(s.centers, s.rgtp, np.float32(200.0), 8)
+    assert_so_equal(r, ref["rvir"], ref["mvir"], ref["ndelta"])
+    assert np.array_equal(mem, ref["members"])
+    g.close()
+
+
+def test_ball_gather_matches_oracle_ball():
+    """smBallGather + qsort replacement (smooth2.c:58-114, kd2.c:781)."""
+    s = synth.make_snapshot(40 ** 3, 10, seed=39, nmax=4000)
+    o = po.Oracle(s.pos, s.mass)
+    g = api.SoGpu()
+    g.set_particles(s.pos, s.mass)
+    g.build_grid()
+    for i in range(s.h):
+        for f in (0.5, 1.2, 3.0):
+            b = np.float32(s.rgtp[i] * f)
+            b2 = np.float32(b * b)
+            idx, d2, n = g.ball_gather(s.centers[i], b2)
+            oi, od = o.ball(s.centers[i], b2)
+            assert n == len(oi) and np.array_equal(idx, oi) and d2.tobytes() == od.tobytes()
+    # empty ball, and a ball wider than half the box
+    idx, d2, n = g.ball_gather((0.1234, -0.3, 0.2), np.float32(1e-12))
+    assert n == len(o.ball((0.1234, -0.3, 0.2), np.float32(1e-12))[0])
+    g.close()
+
+
+def test_unequal_masses_are_rejected_loudly():
+    s = synth.make_snapshot(5000, 3, seed=40, nmax=300)
+    m = np.full(s.n, s.mass, np.float32)
+    m[::7] *= np.float32(3.0)
+    g = api.SoGpu()
+    g.set_particles(s.pos, m)
+    g.build_grid()
+    assert g.stats()["equal_mass"] == 0
+    with pytest.raises(api.SoGpuError):
+        g.so(s.centers, s.rgtp, 200.0)
+    g.close()
+
+
+def test_bad_arguments_return_errors():
+    g = api.SoGpu()
+    with pytest.raises(api.SoGpuError):
+        g.build_grid()                       # no particles yet
+    s = synth.make_snapshot(3000, 2, seed=41, nmax=200)
+    with pytest.raises(api.SoGpuError):
+        g.set_particles(s.pos, s.mass, period=(0.0, 1.0, 1.0))
+    g.set_particles(s.pos, s.mass)
+    with pytest.raises(api.SoGpuError):
+        g.so(s.centers, s.rgtp, 200.0)       # grid not built
+    g.build_grid()
+    with pytest.raises(api.SoGpuError):
+        g.so(s.centers, s.rgtp, 200.0, n_members=1)
+    g.close()
+
+
+def test_config1_full_size_properties():
+    """BASELINE.json configs[1] (256^3, 10 000 halos): too big for the oracle to be the only
+    check, so: size-independent properties + the oracle on a random subsample of the halos."""
+    s = synth.config(1)
+    r = run_gpu(s.pos, s.mass, s.centers, s.rgtp, 200.0)
+    off, mem, d2 = r["member_offset"], r["members"], r["members_d2"]
+    ok = r["ndelta"] > 0
+    assert ok.sum() > 0.95 * s.h
+    # counts, sortedness, uniqueness, M = sequential sum of N equal masses, R from M
+    assert np.array_equal(np.diff(off), np.where(ok, r["ndelta"], 0))
+    for i in np.nonzero(ok)[0][:2000]:
+        seg = d2[off[i]:off[i + 1]]
+        assert np.all(np.diff(seg) >= 0)
+        assert len(np.unique(mem[off[i]:off[i + 1]])) == r["ndelta"][i]
+    k = r["ndelta"][ok].astype(np.int64)
+    s_next = api.mass_prefix(s.mass, k + 1)
+    assert np.array_equal(r["mvir"][ok], (s_next - s.mass).astype(np.float32))
+    assert np.array_equal(r["rvir"][ok], np.array([api.rdelta(m, 200.0) for m in r["mvir"][ok]], np.float32))
+    # idempotence: a second context gives identical bits
+    r2 = run_gpu(s.pos, s.mass, s.centers, s.rgtp, 200.0)
+    assert_so_equal(r2, r["rvir"], r["mvir"], r["ndelta"])
+    assert np.array_equal(r2["members"], mem)
+    # oracle on a subsample
+    pick = np.random.default_rng(0).choice(s.h, 300, replace=False)
+    ref = po.Oracle(s.pos, s.mass).so(s.centers[pick], s.rgtp[pick], np.float32(200.0), 8)
+    assert np.array_equal(r["ndelta"][pick], ref["ndelta"])
+    assert r["mvir"][pick].tobytes() == ref["mvir"].tobytes()
+    assert r["rvir"][pick].tobytes() == ref["rvir"].tobytes()
+    for n, i in enumerate(pick):
+        assert np.array_equal(mem[off[i]:off[i + 1]], ref["members"][ref["member_offset"][n]:ref["member_offset"][n + 1]])
