@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py — halos/sec of the SO hot path (grid build + SO radius solve + member lists).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU code (oracle/_ref)
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+    kdBuildTree (sogpu_build_grid) + kdSO (sogpu_so_device) for every halo of the catalog.
+Workload at N=1: BASELINE.json configs[1] — 256^3 periodic snapshot (16.8 M particles), 10 000
+NFW halos, Delta = 200 rho_crit.  At N>1 (weak scaling) every rank holds the same snapshot
+(replicated by one NCCL broadcast) and the catalog grows to N x 10 000 centres, sharded across
+ranks by LPT on the estimated particle count; no data-path collective.
+
+`value`  = halos/s with inputs already in HBM, timed with CUDA events, max over ranks.
+`e2e`    = the same through the public API with HOST buffers: pack + H2D of the particles
+           (rank 0, then NCCL broadcast), H2D of the catalog, D2H of R/M/N and the member lists.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "halos/sec"
+UNIT = "halos/s"
+THR = 200.0
+NMEM = 8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index (default 1)")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink N and H together (debug)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-scale", type=float, default=0.125,
+                    help="--impl reference: fraction of the workload timed per step")
+    return ap.parse_args()
+
+
+def workload_name(s, h_total):
+    return "%s: %d particles, %d halo centres, Delta=200 rho_crit, z=0" % (s.name, s.n, h_total)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks: sample NVML while the GPU works
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake_slowdown": 0x80, "sw_power_cap": 0x4}
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                util = nv.nvmlDeviceGetUtilizationRates(self.h).gpu
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((mhz, util))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        busy = [m for m, u in self.samples if u > 0] or [m for m, _ in self.samples]
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference arm / cpu baseline: oracle/_ref/so_ref_timed = the reference's own kdBuildTree +
+# kdSO, unmodified objects, timed around the two calls
+# ---------------------------------------------------------------------------------------------
+def write_inputs(s, tmpdir):
+    from so_b200 import tipsy
+    snap, gtp = os.path.join(tmpdir, "snap.tipsy"), os.path.join(tmpdir, "halos.gtp")
+    tipsy.write_tipsy(snap, s.time, dark=tipsy.dark_from_arrays(s.pos, s.mass))
+    tipsy.write_gtp(gtp, s.time, s.centers, s.rgtp, s.gtp_mass)
+    return snap, gtp
+
+
+def time_reference(s, steps, warmup, tmpdir):
+    """Returns (list of seconds per step (kdBuildTree + kdSO), kind, h)."""
+    from oracle import pyoracle as po
+    if po.ref_available("so_ref_timed"):
+        snap, gtp = write_inputs(s, tmpdir)
+        ts = []
+        for i in range(warmup + steps):
+            t = po.run_so_ref_timed(snap, gtp, THR * s.omega0, NMEM, 1.0)
+            if i >= warmup:
+                ts.append(t["t_build"] + t["t_so"])
+        os.remove(snap)
+        os.remove(gtp)
+        return ts, "reference"
+    # reference binary absent: time the oracle port (cell list build + kdSO restatement)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        o = po.Oracle(s.pos, s.mass)
+        o.so(s.centers, s.rgtp, np.float32(THR * s.omega0), NMEM, want_members=True)
+        o.close()
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    return ts, "port"
+
+
+def tmp_dir():
+    import tempfile
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    return tempfile.TemporaryDirectory(dir=base)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from so_b200 import synth
+    scale = args.scale * args.ref_scale
+    s = synth.config(args.config, scale)
+    with tmp_dir() as tmp:
+        ts, kind = time_reference(s, args.steps, args.warmup, tmp)
+    sec = float(np.mean(ts))
+    value = s.h / sec
+    sample = ("%s scaled by %g (%d particles, %d halos) per step; kdBuildTree+kdSO of the reference, "
+              "single-threaded as shipped" % (s.name, scale, s.n, s.h))
+    full = synth.config  # noqa: F841
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[%d] (%s)" % (args.config, s.name), "sample": sample,
+                   "delta": THR, "n_members": NMEM},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+ALG_BYTES = {  # algorithmic bytes per unit of each kernel
+    "k_cell_count": ("particle", 16.0), "k_scatter": ("particle", 36.0),
+    "k_scan(3 launches)": ("cell", 12.0), "k_so_query<32>": ("eval", 16.0),
+    "k_so_query<256>": ("eval", 16.0), "k_so_emit<32>": ("member", 20.0), "k_so_emit<256>": ("member", 20.0),
+    "k_coarse_hist": ("particle", 16.0), "k_partition": ("particle", 40.0), "k_fine_count": ("particle", 4.0),
+    "k_fine_scatter": ("particle", 44.0),
+}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from so_b200 import api, parallel, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- inputs (rank 0 generates; everything else is replicated / sharded from it) ----------
+    if rank == 0:
+        s = synth.config(args.config, args.scale)
+        n, h_base = s.n, s.h
+        reps = world if args.scaling == "weak" else 1
+        cen, rg = [s.centers], [s.rgtp]
+        for r in range(1, reps):   # extra catalog copies: same halos, re-estimated centres
+            rng = np.random.default_rng(7000 + r)
+            d = synth._unit_vectors(rng, s.h) * (rng.random(s.h) * 0.05 * s.r200)[:, None]
+            cen.append(synth._wrap(s.centers.astype(np.float64) + d))
+            rg.append(s.rgtp)
+        centers = np.concatenate(cen).astype(np.float32)
+        rgtp = np.concatenate(rg).astype(np.float32)
+        meta = [n, len(rgtp), float(s.mass), s.name]
+    else:
+        s, centers, rgtp, meta = None, None, None, [0, 0, 0.0, ""]
+    if world > 1:
+        dist.broadcast_object_list(meta, src=0)
+    n, h_total, mass, name = int(meta[0]), int(meta[1]), np.float32(meta[2]), meta[3]
+    cat = torch.empty((h_total, 4), dtype=torch.float32, device=dev)
+    if rank == 0:
+        cat.copy_(torch.from_numpy(np.concatenate([centers, rgtp[:, None]], axis=1)))
+    if world > 1:
+        dist.broadcast(cat, src=0)
+    cat_h = cat.cpu().numpy()
+    centers, rgtp = np.ascontiguousarray(cat_h[:, :3]), np.ascontiguousarray(cat_h[:, 3])
+    rank_of, load = parallel.lpt_assign(parallel.halo_cost(rgtp, n, 1.0), world)
+    mine = parallel.shard_indices(rank_of, rank)
+    h_mine = len(mine)
+
+    # host-side particle buffer of the e2e leg (pinned), only rank 0 owns the snapshot
+    if rank == 0:
+        pos_pin = torch.from_numpy(s.pos).pin_memory()
+    xyzm = torch.empty((n, 4), dtype=torch.float32, device=dev)   # device-resident float4 particles
+    # a real (non-default) stream: the library launches on it and torch's events time it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    g = api.SoGpu(device=local, stream=stream.cuda_stream)
+    g.profile_enable(True)
+
+    def upload_and_replicate():
+        """e2e leg: rank 0 packs + copies the snapshot (pinned host memory) into its device buffer
+        through the C-ABI, then the array is replicated to the other GPUs by one NCCL broadcast."""
+        if rank == 0:
+            g.upload_particles(pos_pin.numpy(), mass, xyzm.data_ptr())
+        if world > 1:
+            dist.broadcast(xyzm, src=0)
+        g.set_particles_device(xyzm.data_ptr(), n)
+
+    upload_and_replicate()   # initial residency for the device-timed leg
+    d_centers = torch.from_numpy(np.ascontiguousarray(centers[mine])).to(dev)
+    d_rgtp = torch.from_numpy(np.ascontiguousarray(rgtp[mine])).to(dev)
+    d_out_n = torch.empty(max(h_mine, 1), dtype=torch.int32, device=dev)
+    d_out_m = torch.empty(max(h_mine, 1), dtype=torch.float32, device=dev)
+    thr = np.float32(THR)
+
+    def step_device():
+        g.build_grid()
+        if h_mine:
+            g.so_device(d_centers.data_ptr(), d_rgtp.data_ptr(), h_mine, thr, NMEM,
+                        d_out_n.data_ptr(), d_out_m.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    g.profile_read(reset=True)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = g.profile_read(reset=True)
+    st = g.stats()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    evals = torch.tensor([float(st["last_evals"]), float(st["last_members"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(evals, op=dist.ReduceOp.SUM)
+    evals_total, members_total = float(evals[0].item()), float(evals[1].item())
+
+    # parity spot check of what was just timed (rank 0, a few halos, against the oracle)
+    res_n = d_out_n[:h_mine].cpu().numpy()
+    res_m = d_out_m[:h_mine].cpu().numpy()
+
+    # ---- e2e: host buffers in, host results out, every step ----------------------------------
+    def step_e2e():
+        upload_and_replicate()
+        g.build_grid()
+        if h_mine:
+            r = g.so(centers[mine], rgtp[mine], thr, NMEM)
+            off, mem = g.members(copy=False)
+            return r, off, mem
+        return None
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    clocks = sampler.stop()
+    n_members_mine = int(out[1][-1]) if out else 0
+    h2d = (16 * n if rank == 0 else 0) + 16 * h_mine
+    d2h = 8 * h_mine + 8 * (h_mine + 1) + 4 * n_members_mine
+    io = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(io, op=dist.ReduceOp.SUM)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (rank 0's launches, live CUDA-event times) ----------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    units = {"particle": float(n), "cell": float(st["cells_per_axis"]) ** 3,
+             "eval": float(st["last_evals"]), "member": float(st["last_members"])}
+    total_ms = sum(v[0] for v in prof.values())
+    kernels = {}
+    for kname, (kms, launches) in prof.items():
+        if launches == 0:
+            continue
+        per = kms / args.steps
+        ent = {"ms_per_step": per, "share": kms / total_ms if total_ms else 0.0,
+               "launches_per_step": launches / args.steps}
+        if kname in ALG_BYTES:
+            unit, b = ALG_BYTES[kname]
+            ent["alg_bytes"] = b * units[unit]
+            ent["gbs"] = ent["alg_bytes"] / (per * 1e-3) / 1e9 if per > 0 else 0.0
+        kernels[kname] = ent
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    dk = kernels[dom]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": dk.get("gbs"), "peak": peak, "unit": "GB/s",
+                "frac": (dk.get("gbs") or 0.0) / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": dk.get("alg_bytes"), "share_of_step": dk["share"]}
+    launches = int(round(sum(v[1] for v in prof.values()) / args.steps))
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        with tmp_dir() as tmp:
+            ts, kind = time_reference(s, 1, 0, tmp)
+        cpu_baseline = {"value": s.h / ts[0], "unit": UNIT, "cores": 1, "kind": kind,
+                        "sample": "the full workload once (%d particles, %d halos): kdBuildTree + kdSO of "
+                                  "the reference, %.1f s" % (s.n, s.h, ts[0])}
+
+    # sanity of the timed result: codes are valid and most halos resolved
+    ok = int((res_n > 0).sum())
+    line = {
+        "metric": METRIC, "value": h_total / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(s, h_total), "baseline_config": args.config,
+                   "delta": THR, "n_members": NMEM, "cells_per_axis": st["cells_per_axis"],
+                   "halos_per_rank": [int((rank_of == r).sum()) for r in range(world)],
+                   "l2": "inputs (%.0f MB float4 particles) exceed the 126 MB L2; no flush between steps"
+                         % (16 * n / 1e6),
+                   "parallelism": "halos sharded by LPT over %d rank(s), particles replicated" % world},
+        "evals_per_s": evals_total / (ms_step * 1e-3), "evals_per_step": evals_total,
+        "members_per_step": members_total, "halos_resolved_rank0": ok,
+        "e2e": {"value": h_total / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item())},
+        "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))

@@ -50,6 +50,9 @@ const char *sogpu_last_error(void);
 /* All work of this handle is enqueued on `cuda_stream` (a cudaStream_t cast to void*;
  * NULL = the handle's own stream).  Lets a caller time the kernels with its own events. */
 int sogpu_set_stream(sogpu_t *h, void *cuda_stream);
+/* Tuning knob: grid build strategy. -1 auto (default), 0 single counting sort, 1 coarse MSD
+ * partition first (keeps the scatter inside an L2-resident window; wins for N >~ 10^5). */
+int sogpu_set_build_mode(sogpu_t *h, int mode);
 /* Tuning knob: target mean particles per grid cell (default 2.0). */
 int sogpu_set_cell_occupancy(sogpu_t *h, float particles_per_cell);
 
@@ -63,6 +66,11 @@ int sogpu_set_cell_occupancy(sogpu_t *h, float particles_per_cell);
 int sogpu_set_particles_host(sogpu_t *h, const void *pos, size_t pos_stride, const void *mass,
                              size_t mass_stride, int64_t n, const float period[3],
                              const float center[3]);
+/* Pack + copy host particles (same layout rules) into a CALLER-owned device float4 array, without
+ * touching the handle's particle state: used when the array is then replicated to other GPUs
+ * (NCCL broadcast) and handed to each handle with sogpu_set_particles_device. */
+int sogpu_upload_particles(sogpu_t *h, const void *pos, size_t pos_stride, const void *mass,
+                           size_t mass_stride, int64_t n, void *d_xyzm_dst);
 /* Device-resident float4 {x,y,z,m} array (borrowed: must outlive the handle's use of it). */
 int sogpu_set_particles_device(sogpu_t *h, const void *d_xyzm, int64_t n, const float period[3],
                                const float center[3]);
@@ -90,12 +98,23 @@ int sogpu_so(sogpu_t *h, const float *centers, const float *rgtp, int32_t nh, fl
 int sogpu_so_device(sogpu_t *h, const void *d_centers, const void *d_rgtp, int32_t nh,
                     float rho_thr, int32_t n_members, void *d_out_n, void *d_out_m);
 
-/* Member particle lists of the last sogpu_so()/sogpu_so_device() call.
+/* Turn the packed device results of sogpu_so_device (copied to the host by the caller) into
+ * what kdRvir stores: rvir/mvir (error codes in both) and ndelta.  Host arithmetic only
+ * (R_Delta = pow(M/((4/3) pi rho), 0.3333333333), kd2.c:817-818). */
+int sogpu_finish_host(const int32_t *code_or_n, const float *m, int32_t nh, float rho_thr,
+                      float *rvir, float *mvir, int32_t *ndelta);
+
+/* Member particle lists (CSR) of the last sogpu_so()/sogpu_so_device() call.
  * offsets: nh+1 int64 (caller-allocated); *members / *d2: library-owned pinned host arrays,
  * valid until the next sogpu_so* call or sogpu_destroy.  Members of halo i are the ORIGINAL
- * particle indices (PINIT.iOrder, kd2.c:361) at [offsets[i], offsets[i+1]), ascending in
- * (fDist2, index) — the order kdTagParticles walks them (kd2.c:670).  d2 may be NULL. */
-int sogpu_members(sogpu_t *h, int64_t *offsets, const int32_t **members, const float **d2);
+ * particle indices (PINIT.iOrder, kd2.c:361) at [offsets[i], offsets[i+1]).
+ * sorted = 0: the set, in no particular order (all that kdTagParticles needs unless a slurp
+ *             occurs, kd2.c:694-703);
+ * sorted = 1: ascending (fDist2, index) — the order kdTagParticles walks them (kd2.c:670,781).
+ * d2 (may be NULL) and sorted = 1 need sogpu_keep_member_d2(h, 1) before the sogpu_so call. */
+int sogpu_members(sogpu_t *h, int64_t *offsets, const int32_t **members, const float **d2,
+                  int sorted);
+int sogpu_keep_member_d2(sogpu_t *h, int on);
 
 /* ---- smBallGather replacement (smooth2.c:58-114) + the qsort of kd2.c:514,781 -------------- */
 
@@ -117,6 +136,15 @@ typedef struct {
     int32_t last_deferred;       /* halos the warp kernel handed to the block kernel          */
 } sogpu_stats_t;
 int sogpu_get_stats(sogpu_t *h, sogpu_stats_t *out);
+
+/* ---- per-kernel timing (CUDA events on the handle's stream) ------------------------------------ */
+
+int sogpu_profile_enable(sogpu_t *h, int on);
+int sogpu_profile_kernels(void);                 /* number of kernel slots                    */
+const char *sogpu_profile_name(int kernel_id);
+/* Accumulated milliseconds and launch counts per kernel slot since the last reset
+ * (synchronises the stream). */
+int sogpu_profile_read(sogpu_t *h, double *ms, int64_t *launches, int n_slots, int reset);
 
 /* ---- host-side helpers of the exact-arithmetic contract (no GPU needed; unit-tested) -------- */
 

@@ -24,6 +24,9 @@ SYMBOLS = [
     "sogpu_set_cell_occupancy", "sogpu_set_particles_host", "sogpu_set_particles_device",
     "sogpu_build_grid", "sogpu_so", "sogpu_so_device", "sogpu_members", "sogpu_ball_gather",
     "sogpu_get_stats", "sogpu_mass_prefix", "sogpu_ball_schedule", "sogpu_rdelta",
+    "sogpu_finish_host", "sogpu_keep_member_d2", "sogpu_profile_enable", "sogpu_profile_kernels",
+    "sogpu_profile_name", "sogpu_profile_read", "sogpu_upload_particles",
+    "sogpu_set_build_mode",
 ]
 
 
@@ -59,12 +62,24 @@ def lib():
     L.sogpu_last_error.argtypes = []
     L.sogpu_set_stream.argtypes = [vp, vp]
     L.sogpu_set_cell_occupancy.argtypes = [vp, C.c_float]
+    L.sogpu_set_build_mode.argtypes = [vp, C.c_int]
+    L.sogpu_set_build_mode.restype = C.c_int
     L.sogpu_set_particles_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_int64, fp, fp]
     L.sogpu_set_particles_device.argtypes = [vp, vp, C.c_int64, fp, fp]
+    L.sogpu_upload_particles.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_int64, vp]
+    L.sogpu_upload_particles.restype = C.c_int
     L.sogpu_build_grid.argtypes = [vp]
     L.sogpu_so.argtypes = [vp, fp, fp, C.c_int32, C.c_float, C.c_int32, fp, fp, i32p]
     L.sogpu_so_device.argtypes = [vp, vp, vp, C.c_int32, C.c_float, C.c_int32, vp, vp]
-    L.sogpu_members.argtypes = [vp, i64p, C.POINTER(i32p), C.POINTER(fp)]
+    L.sogpu_members.argtypes = [vp, i64p, C.POINTER(i32p), C.POINTER(fp), C.c_int]
+    L.sogpu_keep_member_d2.argtypes = [vp, C.c_int]
+    L.sogpu_finish_host.argtypes = [i32p, fp, C.c_int32, C.c_float, fp, fp, i32p]
+    L.sogpu_profile_enable.argtypes = [vp, C.c_int]
+    L.sogpu_profile_kernels.restype = C.c_int
+    L.sogpu_profile_kernels.argtypes = []
+    L.sogpu_profile_name.restype = C.c_char_p
+    L.sogpu_profile_name.argtypes = [C.c_int]
+    L.sogpu_profile_read.argtypes = [vp, C.POINTER(C.c_double), i64p, C.c_int, C.c_int]
     L.sogpu_ball_gather.argtypes = [vp, fp, C.c_float, i32p, fp, C.c_int64, i64p]
     L.sogpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.sogpu_mass_prefix.argtypes = [C.c_float, C.c_int64, i64p, C.c_int64, fp]
@@ -74,7 +89,8 @@ def lib():
     L.sogpu_rdelta.argtypes = [C.c_float, C.c_float]
     for name in ("sogpu_set_stream", "sogpu_set_cell_occupancy", "sogpu_set_particles_host",
                  "sogpu_set_particles_device", "sogpu_build_grid", "sogpu_so", "sogpu_so_device",
-                 "sogpu_members", "sogpu_ball_gather", "sogpu_get_stats", "sogpu_mass_prefix"):
+                 "sogpu_members", "sogpu_ball_gather", "sogpu_get_stats", "sogpu_mass_prefix",
+                 "sogpu_finish_host", "sogpu_keep_member_d2", "sogpu_profile_enable", "sogpu_profile_read"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -143,6 +159,10 @@ class SoGpu:
     def set_stream(self, stream):
         _check(lib().sogpu_set_stream(self._h, C.c_void_p(int(stream) if stream else 0)))
 
+    def set_build_mode(self, mode):
+        """-1 auto, 0 single counting sort, 1 coarse partition first."""
+        _check(lib().sogpu_set_build_mode(self._h, int(mode)))
+
     def set_cell_occupancy(self, ppc):
         _check(lib().sogpu_set_cell_occupancy(self._h, C.c_float(ppc)))
 
@@ -164,6 +184,20 @@ class SoGpu:
         _check(lib().sogpu_set_particles_host(self._h, C.c_void_p(pos.ctypes.data), pos.strides[0],
                                               C.c_void_p(m.ctypes.data), ms, len(pos), _fp(per), _fp(cen)))
         self.n = len(pos)
+
+    def upload_particles(self, pos, mass, d_xyzm_dst):
+        """Pack + H2D into a caller-owned device float4 array (e.g. a torch tensor's data_ptr())."""
+        pos = np.asarray(pos)
+        if pos.dtype != np.float32 or pos.ndim != 2 or pos.shape[1] != 3 or pos.strides[1] != 4:
+            pos = np.ascontiguousarray(pos, np.float32)
+        m = np.asarray(mass, np.float32)
+        if m.ndim == 0:
+            m = np.full(1, m, np.float32)
+            ms = 0
+        else:
+            ms = m.strides[0]
+        _check(lib().sogpu_upload_particles(self._h, C.c_void_p(pos.ctypes.data), pos.strides[0],
+                                            C.c_void_p(m.ctypes.data), ms, len(pos), C.c_void_p(int(d_xyzm_dst))))
 
     def set_particles_records(self, rec, pos_field="pos", mass_field="mass", period=(1.0, 1.0, 1.0),
                               center=(0.0, 0.0, 0.0)):
@@ -207,18 +241,47 @@ class SoGpu:
                                      C.c_void_p(int(d_out_m))))
         self._last_h = int(nh)
 
-    def members(self, want_d2=False):
+    def keep_member_d2(self, on=True):
+        """Ask the next so() call to also keep r^2 of every member (needed for sorted lists)."""
+        _check(lib().sogpu_keep_member_d2(self._h, 1 if on else 0))
+
+    def members(self, want_d2=False, sorted=False, copy=True):
+        """CSR member lists of the last so(): (offsets, members[, d2])."""
         nh = self._last_h
         off = np.zeros(nh + 1, np.int64)
         mp = C.POINTER(C.c_int32)()
         dp = C.POINTER(C.c_float)()
-        _check(lib().sogpu_members(self._h, off.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(mp), C.byref(dp)))
+        _check(lib().sogpu_members(self._h, off.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(mp),
+                                   C.byref(dp) if want_d2 else None, 1 if sorted else 0))
         tot = int(off[-1])
-        mem = np.ctypeslib.as_array(mp, (max(tot, 1),))[:tot].copy()
+        mem = np.ctypeslib.as_array(mp, (max(tot, 1),))[:tot]
+        if copy:
+            mem = mem.copy()
         if want_d2:
-            d2 = np.ctypeslib.as_array(dp, (max(tot, 1),))[:tot].copy()
-            return off, mem, d2
+            d2 = np.ctypeslib.as_array(dp, (max(tot, 1),))[:tot]
+            return off, mem, (d2.copy() if copy else d2)
         return off, mem
+
+    def finish_host(self, code_or_n, m, thr):
+        """rvir/mvir/ndelta from the packed device outputs of so_device()."""
+        code_or_n = np.ascontiguousarray(code_or_n, np.int32)
+        m = np.ascontiguousarray(m, np.float32)
+        nh = len(m)
+        rv, mv, nd = np.zeros(nh, np.float32), np.zeros(nh, np.float32), np.zeros(nh, np.int32)
+        _check(lib().sogpu_finish_host(code_or_n.ctypes.data_as(C.POINTER(C.c_int32)), _fp(m), nh,
+                                       C.c_float(thr), _fp(rv), _fp(mv), nd.ctypes.data_as(C.POINTER(C.c_int32))))
+        return dict(rvir=rv, mvir=mv, ndelta=nd)
+
+    def profile_enable(self, on=True):
+        _check(lib().sogpu_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self, reset=True):
+        """{kernel name: (milliseconds, launches)} accumulated since the last reset."""
+        nk = lib().sogpu_profile_kernels()
+        ms = (C.c_double * nk)()
+        ln = (C.c_int64 * nk)()
+        _check(lib().sogpu_profile_read(self._h, ms, ln, nk, 1 if reset else 0))
+        return {lib().sogpu_profile_name(k).decode(): (ms[k], ln[k]) for k in range(nk)}
 
     def ball_gather(self, center, ball2, cap=None):
         c = np.asarray(center, np.float32).copy()
@@ -273,12 +336,13 @@ class KD:
     def smBallGather(self, fBall2, ri):
         return self.gpu.ball_gather(ri, fBall2)
 
-    def kdSO(self, rhovir, nSmooth=1028):
+    def kdSO(self, rhovir, nSmooth=1028, sorted_members=False):
         """kdRvir for every group (kd2.c:875-879).  Fills fRvir/fMvir/nDelta and the member lists;
         nSmooth is accepted for signature parity and unused (it only sizes the reference's nnList)."""
+        self.gpu.keep_member_d2(sorted_members)
         r = self.gpu.so(self.pos, self.fRgtp, rhovir, self.nMembers)
         self.fRvir, self.fMvir, self.nDelta = r["rvir"], r["mvir"], r["ndelta"]
-        self.member_offset, self.members = self.gpu.members()
+        self.member_offset, self.members = self.gpu.members(sorted=sorted_members)
         return r
 
     def close(self):

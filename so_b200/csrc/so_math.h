@@ -38,15 +38,25 @@ typedef struct {
     float inc[SO_MT_MAX];
 } so_mass_table;
 
-static inline float so_f32_add(float a, float b)
+#ifdef __CUDACC__
+#define SO_HD_FN __host__ __device__ inline
+#else
+#define SO_HD_FN static inline
+#endif
+
+SO_HD float so_f32_add(float a, float b)
 {
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(a, b);
+#else
     volatile float r = a + b;   /* force fp32 rounding on any host */
     return r;
+#endif
 }
 
 /* Build the table for k = 0..kmax.  Returns 0, or -1 if it would need more than SO_MT_MAX
  * entries (does not happen for normal, positive m). */
-static inline int so_mass_table_build(so_mass_table *t, float m, uint64_t kmax)
+SO_HD_FN int so_mass_table_build(so_mass_table *t, float m, uint64_t kmax)
 {
     uint64_t k = 0;
     float S = 0.0f;

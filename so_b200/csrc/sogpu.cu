@@ -27,6 +27,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 /* ============================================================================================
@@ -245,6 +246,152 @@ __global__ void __launch_bounds__(256) k_scatter(const float4 *__restrict__ in, 
         uint32_t pos = atomicAdd(&ce[cell_key(p, g) + 1], 1u);
         sorted[pos] = p;
         orig[pos] = (int32_t)i;
+    }
+}
+
+/* ---- two-level build for large N: MSD partition into coarse buckets (coalesced, staged through
+ * shared memory), then the counting sort runs bucket by bucket so that its random accesses (cell
+ * counters, scattered 16-byte stores) stay inside an L2-resident window ---------------------- */
+#define PART_T 4096          /* particles per tile (256 threads x 16)                          */
+#define PART_BMAX 256        /* coarse buckets (one per thread of the partition CTA)            */
+
+/* coarse histogram (shared-memory atomics, one global atomic per bucket per CTA) + mass min/max */
+__global__ void __launch_bounds__(256) k_coarse_hist(const float4 *__restrict__ in, int64_t n, GridDev g,
+                                                     int kshift, uint32_t *__restrict__ ghist,
+                                                     uint32_t *__restrict__ mass_minmax)
+{
+    __shared__ uint32_t sh[PART_BMAX];
+    sh[threadIdx.x] = 0u;
+    __syncthreads();
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float4 p = ld_stream(in + i);
+        atomicAdd(&sh[cell_key(p, g) >> kshift], 1u);
+        uint32_t mo = (p.w >= 0.0f) ? f2ord(p.w) : 0xFFFFFFFEu;
+        if (!(p.w >= 0.0f)) mn = 0u;
+        mn = min(mn, mo);
+        mx = max(mx, mo);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
+    mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&mass_minmax[0], mn);
+        atomicMax(&mass_minmax[1], mx);
+    }
+}
+
+/* exclusive scan of the <=256 coarse counts into the bucket cursors (in place) */
+__global__ void __launch_bounds__(256) k_coarse_scan(uint32_t *__restrict__ ghist)
+{
+    __shared__ uint32_t ws[8];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t v = ghist[threadIdx.x], x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += t;
+    }
+    if (lane == 31) ws[w] = x;
+    __syncthreads();
+    uint32_t off = 0;
+    for (int k = 0; k < w; ++k) off += ws[k];
+    ghist[threadIdx.x] = off + x - v;
+}
+
+/* tile-wise stable-enough partition: every tile is counting-sorted by coarse bucket in shared
+ * memory, claims a run in each bucket with one atomic, and writes runs (coalesced) */
+__global__ void __launch_bounds__(256) k_partition(const float4 *__restrict__ in, int64_t n, GridDev g,
+                                                   int kshift, uint32_t *__restrict__ gcursor,
+                                                   float4 *__restrict__ tmp4, uint32_t *__restrict__ tmpk,
+                                                   int32_t *__restrict__ tmpi)
+{
+    extern __shared__ __align__(16) unsigned char raw[];
+    float4 *s4 = reinterpret_cast<float4 *>(raw);
+    uint32_t *sk = reinterpret_cast<uint32_t *>(s4 + PART_T);
+    uint16_t *sr = reinterpret_cast<uint16_t *>(sk + PART_T);
+    uint16_t *perm = sr + PART_T;
+    uint8_t *sd = reinterpret_cast<uint8_t *>(perm + PART_T);
+    __shared__ uint32_t scnt[PART_BMAX], soff[PART_BMAX], sbase[PART_BMAX], ws[8];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int64_t ntiles = (n + PART_T - 1) / PART_T;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = tile * PART_T;
+        const int cnt = (int)min((int64_t)PART_T, n - base);
+        scnt[t] = 0u;
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < PART_T / 256; ++k) {
+            int i = k * 256 + t;
+            if (i < cnt) {
+                float4 p = ld_stream(in + base + i);
+                uint32_t key = cell_key(p, g);
+                uint32_t d = key >> kshift;
+                s4[i] = p;
+                sk[i] = key;
+                sd[i] = (uint8_t)d;
+                sr[i] = (uint16_t)atomicAdd(&scnt[d], 1u);
+            }
+        }
+        __syncthreads();
+        {
+            uint32_t c = scnt[t], x = c;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t u = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                if (lane >= o) x += u;
+            }
+            if (lane == 31) ws[w] = x;
+            __syncthreads();
+            uint32_t off = 0;
+            for (int k = 0; k < w; ++k) off += ws[k];
+            soff[t] = off + x - c;
+            sbase[t] = c ? atomicAdd(&gcursor[t], c) : 0u;
+        }
+        __syncthreads();
+        for (int i = t; i < cnt; i += 256) perm[soff[sd[i]] + sr[i]] = (uint16_t)i;
+        __syncthreads();
+        for (int slot = t; slot < cnt; slot += 256) {
+            int i = perm[slot];
+            uint32_t d = sd[i];
+            uint32_t dst = sbase[d] + ((uint32_t)slot - soff[d]);
+            tmp4[dst] = s4[i];
+            tmpk[dst] = sk[i];
+            tmpi[dst] = (int32_t)(base + i);
+        }
+        __syncthreads();
+    }
+}
+
+/* fine cell counts from the partitioned keys: neighbouring threads hit neighbouring counters */
+__global__ void __launch_bounds__(256) k_fine_count(const uint32_t *__restrict__ tmpk, int64_t n,
+                                                    uint32_t *__restrict__ ce)
+{
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(&ce[__ldg(tmpk + i) + 1], 1u);
+}
+
+/* final placement, bucket by bucket: reads are streaming, writes stay in the bucket's window */
+__global__ void __launch_bounds__(256) k_fine_scatter(const float4 *__restrict__ tmp4,
+                                                      const uint32_t *__restrict__ tmpk,
+                                                      const int32_t *__restrict__ tmpi, int64_t n,
+                                                      uint32_t *__restrict__ ce, float4 *__restrict__ sorted,
+                                                      int32_t *__restrict__ orig)
+{
+    /* CTAs walk the array in order (chunk per CTA per round) so the active window is a few buckets */
+    const int64_t chunk = 256 * 8;
+    for (int64_t c0 = (int64_t)blockIdx.x * chunk; c0 < n; c0 += (int64_t)gridDim.x * chunk) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int64_t i = c0 + k * 256 + threadIdx.x;
+            if (i < n) {
+                float4 p = ld_stream(tmp4 + i);
+                uint32_t pos = atomicAdd(&ce[__ldg(tmpk + i) + 1], 1u);
+                sorted[pos] = p;
+                orig[pos] = __ldg(tmpi + i);
+            }
+        }
     }
 }
 
@@ -833,8 +980,10 @@ __device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &s
 }
 
 /* ============================================================================================
- * the persistent query kernel
+ * the persistent query / emit kernels
  * ============================================================================================ */
+#define CODE_UNEQUAL_MASS (-102)
+
 struct QueryArgs {
     GridDev g;
     const float *centers;      /* nh x 3 */
@@ -846,18 +995,27 @@ struct QueryArgs {
     uint32_t *defer_n;
     float thr;
     int nM;
-    int32_t *out_n;
-    float *out_m;
-    unsigned long long *out_key;
-    unsigned long long *out_off;   /* member offset per halo */
+    int32_t *out_n;            /* N_Delta or a negative code */
+    float *out_m;              /* M_Delta */
+    unsigned long long *out_key;   /* (r^2 bits, index) of sorted element j */
+    const unsigned long long *out_off;   /* (emit) first member slot per halo */
     int32_t *members;
     float *md2;
-    unsigned long long *member_total;
     unsigned long long member_cap;
     unsigned long long *evals;     /* [0] histogram pass, [1] other passes */
-    uint32_t *overflow;
+    uint32_t *flags;               /* bit0 member buffer too small, bit1 emit count mismatch */
     const so_mass_table *mt;
 };
+
+template <int NT>
+__device__ __forceinline__ uint32_t next_item(uint32_t *counter, GroupSmem<NT> &sm, int tid)
+{
+    if (tid == 0) sm.bcast[0] = atomicAdd(counter, 1u);
+    gsync<NT>();
+    uint32_t item = sm.bcast[0];
+    gsync<NT>();
+    return item;
+}
 
 template <int NT>
 __global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS) k_so_query(const __grid_constant__ QueryArgs a)
@@ -869,62 +1027,38 @@ __global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS) k_so_query(const __grid_c
     GroupSmem<NT> &sm = *reinterpret_cast<GroupSmem<NT> *>(
         smem_raw + mt_bytes + (size_t)grp * ((sizeof(GroupSmem<NT>) + 15) & ~(size_t)15));
 
-    /* CTA-wide: copy the mass table */
-    {
-        mt.n = a.mt->n; mt.m = a.mt->m;
-        for (int i = threadIdx.x; i <= a.mt->n; i += blockDim.x) mt.k0[i] = a.mt->k0[i];
-        for (int i = threadIdx.x; i < a.mt->n; i += blockDim.x) { mt.s0[i] = a.mt->s0[i]; mt.inc[i] = a.mt->inc[i]; }
+    /* CTA-wide: copy the mass table (built on the device by k_mass_table) */
+    const int mtn = a.mt->n;
+    if (mtn > 0) {
+        if (threadIdx.x == 0) { mt.n = mtn; mt.m = a.mt->m; }
+        for (int i = threadIdx.x; i <= mtn; i += blockDim.x) mt.k0[i] = a.mt->k0[i];
+        for (int i = threadIdx.x; i < mtn; i += blockDim.x) { mt.s0[i] = a.mt->s0[i]; mt.inc[i] = a.mt->inc[i]; }
     }
     __syncthreads();
 
     const uint32_t nlist = *a.list_n;
     uint32_t ev_hist = 0, ev_other = 0;
     for (;;) {
-        uint32_t item;
-        if (tid == 0) sm.bcast[0] = atomicAdd(a.work_counter, 1u);
-        gsync<NT>();
-        item = sm.bcast[0];
-        gsync<NT>();
+        const uint32_t item = next_item<NT>(a.work_counter, sm, tid);
         if (item >= nlist) break;
         const int h = a.list[item];
-        Center c;
-        c.x = a.centers[3 * h + 0]; c.y = a.centers[3 * h + 1]; c.z = a.centers[3 * h + 2];
         HaloResult res;
-        so_halo<NT>(a.g, mt, sm, tid, c, a.rgtp[h], a.thr, a.nM, res, ev_hist, ev_other);
-        gsync<NT>();
+        if (mtn <= 0) {                      /* unequal particle masses: not handled by this path */
+            res.n = CODE_UNEQUAL_MASS; res.m = 0.0f; res.key_j = 0ull;
+        } else {
+            Center c;
+            c.x = a.centers[3 * h + 0]; c.y = a.centers[3 * h + 1]; c.z = a.centers[3 * h + 2];
+            so_halo<NT>(a.g, mt, sm, tid, c, a.rgtp[h], a.thr, a.nM, res, ev_hist, ev_other);
+            gsync<NT>();
+        }
         if (res.n == CODE_DEFER) {
             if (tid == 0) a.defer_list[atomicAdd(a.defer_n, 1u)] = h;
             continue;
-        }
-        unsigned long long off = 0ull;
-        if (res.n > 0) {
-            /* ---- emit the member list: every particle ordered before element j ------------- */
-            if (tid == 0) {
-                off = atomicAdd(a.member_total, (unsigned long long)res.n);
-                sm.bcast[0] = (uint32_t)off; sm.bcast[1] = (uint32_t)(off >> 32);
-                sm.cnt = 0u;
-            }
-            gsync<NT>();
-            off = ((unsigned long long)sm.bcast[1] << 32) | sm.bcast[0];
-            if (off + (unsigned long long)res.n <= a.member_cap) {
-                EmitF f;
-                f.g = &a.g; f.c = c; f.key_j = res.key_j;
-                f.members = a.members + off; f.md2 = a.md2 ? a.md2 + off : nullptr;
-                f.cnt = &sm.cnt; f.limit = (uint32_t)res.n;
-                float r2j = __uint_as_float((uint32_t)(res.key_j >> 32));
-                BallGeom B = make_geom(a.g, c, sqrt((double)r2j) * (1.0 + 1.0e-6));
-                for_each_in_ball<NT>(a.g, sm, tid, B, f, ev_other);
-                if (tid == 0 && sm.cnt != (uint32_t)res.n) atomicOr(a.overflow, 2u);
-            } else if (tid == 0) {
-                atomicOr(a.overflow, 1u);
-            }
-            gsync<NT>();
         }
         if (tid == 0) {
             a.out_n[h] = res.n;
             a.out_m[h] = res.m;
             a.out_key[h] = res.key_j;
-            a.out_off[h] = off;
         }
     }
     ev_hist = __reduce_add_sync(0xFFFFFFFFu, ev_hist);
@@ -935,6 +1069,46 @@ __global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS) k_so_query(const __grid_c
     }
 }
 
+/* K5: member lists in CSR form.  Halo h owns members[out_off[h] .. out_off[h]+N_Delta). */
+template <int NT>
+__global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS) k_so_emit(const __grid_constant__ QueryArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const size_t mt_bytes = (sizeof(MassTableS) + 15) & ~(size_t)15;
+    const int grp = threadIdx.x / NT, tid = threadIdx.x % NT;
+    GroupSmem<NT> &sm = *reinterpret_cast<GroupSmem<NT> *>(
+        smem_raw + mt_bytes + (size_t)grp * ((sizeof(GroupSmem<NT>) + 15) & ~(size_t)15));
+    const uint32_t nlist = *a.list_n;
+    uint32_t ev = 0;
+    for (;;) {
+        const uint32_t item = next_item<NT>(a.work_counter, sm, tid);
+        if (item >= nlist) break;
+        const int h = a.list[item];
+        const int32_t n = a.out_n[h];
+        const unsigned long long off = a.out_off[h], key_j = a.out_key[h];
+        if (n <= 0) continue;
+        if (off + (unsigned long long)n > a.member_cap) {
+            if (tid == 0) atomicOr(a.flags, 1u);
+            continue;
+        }
+        Center c;
+        c.x = a.centers[3 * h + 0]; c.y = a.centers[3 * h + 1]; c.z = a.centers[3 * h + 2];
+        if (tid == 0) sm.cnt = 0u;
+        gsync<NT>();
+        EmitF f;
+        f.g = &a.g; f.c = c; f.key_j = key_j;
+        f.members = a.members + off; f.md2 = a.md2 ? a.md2 + off : nullptr;
+        f.cnt = &sm.cnt; f.limit = (uint32_t)n;
+        const float r2j = __uint_as_float((uint32_t)(key_j >> 32));
+        BallGeom B = make_geom(a.g, c, sqrt((double)r2j) * (1.0 + 1.0e-6));
+        for_each_in_ball<NT>(a.g, sm, tid, B, f, ev);
+        if (tid == 0 && sm.cnt != (uint32_t)n) atomicOr(a.flags, 2u);
+        gsync<NT>();
+    }
+    ev = __reduce_add_sync(0xFFFFFFFFu, ev);
+    if ((threadIdx.x & 31) == 0 && ev) atomicAdd(&a.evals[1], (unsigned long long)ev);
+}
+
 template <int NT> static size_t query_smem_bytes()
 {
     size_t mt_bytes = (sizeof(MassTableS) + 15) & ~(size_t)15;
@@ -942,16 +1116,74 @@ template <int NT> static size_t query_smem_bytes()
     return mt_bytes + g_bytes * Cfg<NT>::GROUPS;
 }
 
-/* split the halos into the warp-kernel list and the block-kernel list by expected ball size */
-__global__ void k_classify(const float *__restrict__ rgtp, int nh, float count_per_r3, float small_max,
-                           int32_t *small_list, uint32_t *small_n, int32_t *big_list, uint32_t *big_n)
+/* split the halos into the warp-kernel list and the block-kernel list by expected ball size:
+ * a halo of radius R ~ 1.25 rgtp at mean density thr holds thr*(4pi/3)R^3/m particles, the final
+ * ball (1.2 R) about 1.3x that */
+__global__ void k_classify(const float *__restrict__ rgtp, int nh, float thr, const so_mass_table *mt,
+                           float small_max, int32_t *small_list, uint32_t *small_n, int32_t *big_list,
+                           uint32_t *big_n)
 {
     int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= nh) return;
-    float r = rgtp[h];
-    float est = count_per_r3 * r * r * r;
-    if (est <= small_max) small_list[atomicAdd(small_n, 1u)] = h;
+    float r = 1.25f * rgtp[h];
+    float m = mt->n > 0 ? mt->m : 1.0f;
+    float est = 1.3f * thr * 4.18879f * r * r * r / m;
+    if (!(est > small_max)) small_list[atomicAdd(small_n, 1u)] = h;
     else big_list[atomicAdd(big_n, 1u)] = h;
+}
+
+/* exclusive scan of max(N_Delta,0) in catalog order -> member offsets; also the emit work lists */
+__global__ void __launch_bounds__(1024) k_offsets(const int32_t *__restrict__ out_n, int nh,
+                                                  unsigned long long *__restrict__ out_off,
+                                                  unsigned long long *__restrict__ total, int32_t emit_small_max,
+                                                  int32_t *small_list, uint32_t *small_n, int32_t *big_list,
+                                                  uint32_t *big_n)
+{
+    __shared__ unsigned long long ws[32];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0ull;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int b0 = 0; b0 < nh; b0 += 1024) {
+        int i = b0 + threadIdx.x;
+        int32_t n = (i < nh) ? out_n[i] : 0;
+        unsigned long long v = n > 0 ? (unsigned long long)n : 0ull, x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += t;
+        }
+        if (lane == 31) ws[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            unsigned long long y = ws[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, y, o);
+                if (lane >= o) y += t;
+            }
+            ws[lane] = y;
+        }
+        __syncthreads();
+        unsigned long long incl = x + (w ? ws[w - 1] : 0ull) + carry;
+        if (i < nh) {
+            out_off[i] = incl - v;
+            if (n > 0) {
+                if (n <= emit_small_max) small_list[atomicAdd(small_n, 1u)] = i;
+                else big_list[atomicAdd(big_n, 1u)] = i;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out_off[nh] = carry; *total = carry; }
+}
+
+/* the running-mass table, built on the device so that build -> query needs no host round trip */
+__global__ void k_mass_table(const uint32_t *__restrict__ massmm, so_mass_table *mt, unsigned long long kmax)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    if (massmm[0] != massmm[1]) { mt->n = -1; mt->m = 0.0f; return; }     /* unequal masses */
+    if (so_mass_table_build(mt, __uint_as_float(massmm[0]), kmax)) { mt->n = -2; }
 }
 
 /* sogpu_ball_gather: one warp per row of cells, lanes stride over the row's particles */
@@ -976,34 +1208,54 @@ __global__ void __launch_bounds__(256) k_ball_gather(const __grid_constant__ Gri
 /* ============================================================================================
  * host side
  * ============================================================================================ */
+enum {
+    KID_CELL_COUNT = 0, KID_SCAN, KID_SCATTER, KID_MASS_TABLE, KID_CLASSIFY, KID_QUERY_WARP,
+    KID_QUERY_BLOCK, KID_OFFSETS, KID_EMIT_WARP, KID_EMIT_BLOCK, KID_BALL_GATHER, KID_COARSE_HIST,
+    KID_COARSE_SCAN, KID_PARTITION, KID_FINE_COUNT, KID_FINE_SCATTER, KID_N
+};
+static const char *const g_kernel_names[KID_N] = {
+    "k_cell_count", "k_scan(3 launches)", "k_scatter", "k_mass_table", "k_classify", "k_so_query<32>",
+    "k_so_query<256>", "k_offsets", "k_so_emit<32>", "k_so_emit<256>", "k_ball_gather", "k_coarse_hist",
+    "k_coarse_scan", "k_partition", "k_fine_count", "k_fine_scatter"};
+
+struct ProfRec { int kid; cudaEvent_t a, b; };
+
 struct sogpu {
     int device;
     cudaStream_t own_stream, stream;
     float ppc;                       /* target particles per cell */
+    int pack_threads;
 
     int64_t n;
     float period[3], center[3];
     const float4 *d_in;              /* unsorted particles (owned or borrowed) */
     float4 *d_in_owned;
+    int64_t d_in_cap;
     float4 *d_sorted;
     int32_t *d_orig;
+    int64_t grid_n_cap;
     uint32_t *d_ce;
     uint32_t *d_bsum;
     uint32_t *d_massmm;
+    uint32_t *d_coarse;              /* PART_BMAX bucket cursors */
+    float4 *d_tmp4;                  /* partitioned particles / keys / original indices */
+    uint32_t *d_tmpk;
+    int32_t *d_tmpi;
+    int64_t tmp_cap;
+    int two_level;                   /* -1 auto, 0 direct counting sort, 1 partition first */
     int64_t ncell;
     int nc, lb;
     bool built;
-    int equal_mass;
+    int mass_state;                  /* -1 unknown (not fetched yet), 0 unequal, 1 equal */
     float mass;
     GridDev g;
-    so_mass_table mt;
     so_mass_table *d_mt;
 
     /* query buffers */
     int32_t cap_h;
     float *d_centers, *d_rgtp;
-    int32_t *d_small, *d_big;
-    uint32_t *d_counters;            /* [0] small_n [1] big_n [2] work_small [3] work_big [4] overflow */
+    int32_t *d_small, *d_big, *d_esmall, *d_ebig;
+    uint32_t *d_counters;   /* 0 small_n 1 big_n 2 work_small 3 work_big 4 flags 5 esmall_n 6 ebig_n 7 work_es 8 work_eb */
     int32_t *d_out_n;
     float *d_out_m;
     unsigned long long *d_out_key, *d_out_off;
@@ -1012,7 +1264,8 @@ struct sogpu {
     float *d_md2;
     unsigned long long member_cap;
     int32_t last_h;
-    bool have_members;
+    bool have_result;
+    bool want_d2;
 
     /* pinned host staging */
     void *h_pin;
@@ -1020,10 +1273,40 @@ struct sogpu {
     int32_t *h_members;
     float *h_md2;
     size_t h_members_cap;
-    std::vector<int64_t> h_off;
+
+    /* profiling */
+    bool prof_on;
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[KID_N];
+    int64_t prof_launches[KID_N];
 
     sogpu_stats_t stats;
     int sm_count;
+};
+
+static cudaEvent_t prof_event(sogpu *h)
+{
+    cudaEvent_t e = nullptr;
+    if (!h->prof_pool.empty()) { e = h->prof_pool.back(); h->prof_pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {   /* brackets one (group of) kernel launch(es) with events when profiling is on */
+    sogpu *h; ProfRec r; bool on;
+    ProfScope(sogpu *h_, int kid) : h(h_), on(h_->prof_on)
+    {
+        h->stats.last_kernel_launches += (kid == KID_SCAN) ? 3 : 1;
+        if (!on) return;
+        r.kid = kid; r.a = prof_event(h); r.b = prof_event(h);
+        cudaEventRecord(r.a, h->stream);
+    }
+    ~ProfScope()
+    {
+        if (!on) return;
+        cudaEventRecord(r.b, h->stream);
+        h->prof_pending.push_back(r);
+    }
 };
 
 static int ensure_pinned(sogpu *h, size_t bytes)
@@ -1057,6 +1340,9 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     if (!h) return set_err(SOGPU_ERR_NOMEM, "out of host memory");
     h->device = device;
     h->ppc = 2.0f;
+    h->pack_threads = 8;
+    h->mass_state = -1;
+    h->two_level = -1;
     h->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return set_err(SOGPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
@@ -1064,6 +1350,10 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     e = cudaFuncSetAttribute(k_so_query<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<256>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_so_query<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<32>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_so_emit<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<256>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_so_emit<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<32>());
     if (e != cudaSuccess) {
         cudaStreamDestroy(h->own_stream); delete h;
         return set_err(SOGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -1079,14 +1369,16 @@ static void free_grid(sogpu *h)
     cudaFree(h->d_orig); h->d_orig = nullptr;
     cudaFree(h->d_ce); h->d_ce = nullptr;
     cudaFree(h->d_bsum); h->d_bsum = nullptr;
+    h->grid_n_cap = 0; h->nc = 0;
     h->built = false;
 }
 
 static void free_query(sogpu *h)
 {
     cudaFree(h->d_centers); cudaFree(h->d_rgtp); cudaFree(h->d_small); cudaFree(h->d_big);
+    cudaFree(h->d_esmall); cudaFree(h->d_ebig);
     cudaFree(h->d_out_n); cudaFree(h->d_out_m); cudaFree(h->d_out_key); cudaFree(h->d_out_off);
-    h->d_centers = h->d_rgtp = nullptr; h->d_small = h->d_big = nullptr;
+    h->d_centers = h->d_rgtp = nullptr; h->d_small = h->d_big = h->d_esmall = h->d_ebig = nullptr;
     h->d_out_n = nullptr; h->d_out_m = nullptr; h->d_out_key = h->d_out_off = nullptr;
     h->cap_h = 0;
 }
@@ -1100,6 +1392,8 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     free_query(h);
     cudaFree(h->d_in_owned);
     cudaFree(h->d_massmm);
+    cudaFree(h->d_coarse);
+    cudaFree(h->d_tmp4); cudaFree(h->d_tmpk); cudaFree(h->d_tmpi);
     cudaFree(h->d_mt);
     cudaFree(h->d_counters);
     cudaFree(h->d_u64);
@@ -1108,6 +1402,8 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->h_members) cudaFreeHost(h->h_members);
     if (h->h_md2) cudaFreeHost(h->h_md2);
+    for (auto &r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : h->prof_pool) cudaEventDestroy(e);
     cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -1116,6 +1412,13 @@ extern "C" int sogpu_set_stream(sogpu_t *h, void *s)
 {
     if (!h) return set_err(SOGPU_ERR_ARG, "NULL handle");
     h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_set_build_mode(sogpu_t *h, int mode)
+{
+    if (!h || mode < -1 || mode > 1) return set_err(SOGPU_ERR_ARG, "bad build mode");
+    h->two_level = mode;
     return SOGPU_OK;
 }
 
@@ -1133,10 +1436,11 @@ static int set_common(sogpu *h, int64_t n, const float period[3], const float ce
         if (!(period[k] > 0.0f) || !(period[k] < INFINITY))
             return set_err(SOGPU_ERR_ARG, "period[%d] must be positive (the reference is periodic only, smooth2.c:69)", k);
     CU(cudaSetDevice(h->device));
-    free_grid(h);
     h->n = n;
     for (int k = 0; k < 3; ++k) { h->period[k] = period[k]; h->center[k] = center ? center[k] : 0.0f; }
-    h->have_members = false;
+    h->built = false;
+    h->have_result = false;
+    h->mass_state = -1;
     return SOGPU_OK;
 }
 
@@ -1146,24 +1450,26 @@ extern "C" int sogpu_set_particles_device(sogpu_t *h, const void *d_xyzm, int64_
     if (!h || !d_xyzm || !period) return set_err(SOGPU_ERR_ARG, "sogpu_set_particles_device: NULL argument");
     int rc = set_common(h, n, period, center);
     if (rc) return rc;
-    if (h->d_in_owned) { cudaFree(h->d_in_owned); h->d_in_owned = nullptr; }
     h->d_in = (const float4 *)d_xyzm;
     return SOGPU_OK;
 }
 
-extern "C" int sogpu_set_particles_host(sogpu_t *h, const void *pos, size_t pos_stride, const void *mass,
-                                        size_t mass_stride, int64_t n, const float period[3],
-                                        const float center[3])
+static void pack_range(float4 *dst, const char *pp, size_t ps, const char *mp, size_t ms, int64_t k)
 {
-    if (!h || !pos || !mass || !period) return set_err(SOGPU_ERR_ARG, "sogpu_set_particles_host: NULL argument");
-    int rc = set_common(h, n, period, center);
-    if (rc) return rc;
-    if (h->d_in_owned) { cudaFree(h->d_in_owned); h->d_in_owned = nullptr; }
-    CU(cudaMalloc(&h->d_in_owned, (size_t)n * sizeof(float4)));
-    h->d_in = h->d_in_owned;
-    /* pack to float4 through two pinned staging buffers so the copy overlaps the packing */
+    for (int64_t i = 0; i < k; ++i) {
+        const float *p = (const float *)(pp + (size_t)i * ps);
+        dst[i].x = p[0]; dst[i].y = p[1]; dst[i].z = p[2];
+        dst[i].w = *(const float *)(mp + (size_t)i * ms);
+    }
+}
+
+/* pack host particles to float4 {x,y,z,m} with a few host threads into two pinned staging buffers
+ * (the H2D copy of one chunk overlaps the packing of the next) and copy them to d_dst */
+static int upload_to(sogpu *h, float4 *d_dst, const void *pos, size_t pos_stride, const void *mass,
+                     size_t mass_stride, int64_t n)
+{
     const int64_t chunk = 1 << 22;
-    rc = ensure_pinned(h, 2 * (size_t)chunk * sizeof(float4));
+    int rc = ensure_pinned(h, 2 * (size_t)chunk * sizeof(float4));
     if (rc) return rc;
     float4 *stage[2] = {(float4 *)h->h_pin, (float4 *)h->h_pin + chunk};
     cudaEvent_t ev[2];
@@ -1178,18 +1484,51 @@ extern "C" int sogpu_set_particles_host(sogpu_t *h, const void *pos, size_t pos_
         float4 *s = stage[b];
         const char *pp = (const char *)pos + (size_t)i0 * pos_stride;
         const char *mp = (const char *)mass + (size_t)i0 * mass_stride;
-        for (int64_t i = 0; i < k; ++i) {
-            const float *p = (const float *)(pp + (size_t)i * pos_stride);
-            s[i].x = p[0]; s[i].y = p[1]; s[i].z = p[2];
-            s[i].w = *(const float *)(mp + (size_t)i * mass_stride);
+        int nt = (k >= (1 << 16)) ? h->pack_threads : 1;
+        if (nt <= 1) {
+            pack_range(s, pp, pos_stride, mp, mass_stride, k);
+        } else {
+            std::vector<std::thread> th;
+            int64_t per = (k + nt - 1) / nt;
+            for (int t = 0; t < nt; ++t) {
+                int64_t a0 = t * per, a1 = std::min(k, a0 + per);
+                if (a0 >= a1) break;
+                th.emplace_back(pack_range, s + a0, pp + (size_t)a0 * pos_stride, pos_stride,
+                                mp + (size_t)a0 * mass_stride, mass_stride, a1 - a0);
+            }
+            for (auto &t : th) t.join();
         }
-        e = cudaMemcpyAsync(h->d_in_owned + i0, s, (size_t)k * sizeof(float4), cudaMemcpyHostToDevice, h->stream);
+        e = cudaMemcpyAsync(d_dst + i0, s, (size_t)k * sizeof(float4), cudaMemcpyHostToDevice, h->stream);
         if (e == cudaSuccess) e = cudaEventRecord(ev[b], h->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
     if (e != cudaSuccess) return set_err(SOGPU_ERR_CUDA, "particle upload failed: %s", cudaGetErrorString(e));
     return SOGPU_OK;
+}
+
+extern "C" int sogpu_upload_particles(sogpu_t *h, const void *pos, size_t pos_stride, const void *mass,
+                                      size_t mass_stride, int64_t n, void *d_xyzm_dst)
+{
+    if (!h || !pos || !mass || !d_xyzm_dst || n <= 0) return set_err(SOGPU_ERR_ARG, "sogpu_upload_particles: bad argument");
+    CU(cudaSetDevice(h->device));
+    return upload_to(h, (float4 *)d_xyzm_dst, pos, pos_stride, mass, mass_stride, n);
+}
+
+extern "C" int sogpu_set_particles_host(sogpu_t *h, const void *pos, size_t pos_stride, const void *mass,
+                                        size_t mass_stride, int64_t n, const float period[3],
+                                        const float center[3])
+{
+    if (!h || !pos || !mass || !period) return set_err(SOGPU_ERR_ARG, "sogpu_set_particles_host: NULL argument");
+    int rc = set_common(h, n, period, center);
+    if (rc) return rc;
+    if (n > h->d_in_cap) {
+        cudaFree(h->d_in_owned); h->d_in_owned = nullptr; h->d_in_cap = 0;
+        CU(cudaMalloc(&h->d_in_owned, (size_t)n * sizeof(float4)));
+        h->d_in_cap = n;
+    }
+    h->d_in = h->d_in_owned;
+    return upload_to(h, h->d_in_owned, pos, pos_stride, mass, mass_stride, n);
 }
 
 static int pick_cells(int64_t n, float ppc, int *lb)
@@ -1203,6 +1542,7 @@ static int pick_cells(int64_t n, float ppc, int *lb)
     return 1 << l;
 }
 
+/* kdBuildTree replacement.  Fully asynchronous on the handle's stream (no host round trip). */
 extern "C" int sogpu_build_grid(sogpu_t *h)
 {
     if (!h || !h->d_in || h->n <= 0) return set_err(SOGPU_ERR_ARG, "sogpu_build_grid: no particles set");
@@ -1210,17 +1550,22 @@ extern "C" int sogpu_build_grid(sogpu_t *h)
     int lb;
     int nc = pick_cells(h->n, h->ppc, &lb);
     int64_t ncell = (int64_t)nc * nc * nc;
+    int64_t ntile = (ncell + SCAN_TILE - 1) / SCAN_TILE;
     if (!h->d_ce || h->nc != nc) {
-        free_grid(h);
+        cudaFree(h->d_ce); cudaFree(h->d_bsum);
+        h->d_ce = nullptr; h->d_bsum = nullptr;
         CU(cudaMalloc(&h->d_ce, (size_t)(ncell + 1) * sizeof(uint32_t)));
-        int64_t ntile = (ncell + SCAN_TILE - 1) / SCAN_TILE;
         CU(cudaMalloc(&h->d_bsum, (size_t)ntile * sizeof(uint32_t)));
     }
-    if (!h->d_sorted) {
+    if (h->n > h->grid_n_cap) {
+        cudaFree(h->d_sorted); cudaFree(h->d_orig);
+        h->d_sorted = nullptr; h->d_orig = nullptr; h->grid_n_cap = 0;
         CU(cudaMalloc(&h->d_sorted, (size_t)h->n * sizeof(float4)));
         CU(cudaMalloc(&h->d_orig, (size_t)h->n * sizeof(int32_t)));
+        h->grid_n_cap = h->n;
     }
     if (!h->d_massmm) CU(cudaMalloc(&h->d_massmm, 2 * sizeof(uint32_t)));
+    if (!h->d_mt) CU(cudaMalloc(&h->d_mt, sizeof(so_mass_table)));
     h->nc = nc; h->lb = lb; h->ncell = ncell;
 
     GridDev &g = h->g;
@@ -1231,8 +1576,7 @@ extern "C" int sogpu_build_grid(sogpu_t *h)
         double L = (double)h->period[k];
         g.L[k] = h->period[k];
         g.halfL[k] = 0.5f * h->period[k];
-        g.dg0[k] = (double)h->center[k] - 0.5 * L;
-        g.g0[k] = (float)g.dg0[k];
+        g.g0[k] = (float)((double)h->center[k] - 0.5 * L);
         g.dg0[k] = (double)g.g0[k];
         g.dh[k] = L / nc;
         g.invh[k] = (float)((double)nc / L);
@@ -1243,43 +1587,92 @@ extern "C" int sogpu_build_grid(sogpu_t *h)
     g.bmax_pruned = 0.5 * lmin - 2.0 * hmax;
 
     cudaStream_t s = h->stream;
-    const uint32_t mm_init[2] = {0xFFFFFFFFu, 0u};
+    h->stats.last_kernel_launches = 0;
     CU(cudaMemsetAsync(h->d_ce, 0, (size_t)(ncell + 1) * sizeof(uint32_t), s));
-    CU(cudaMemcpyAsync(h->d_massmm, mm_init, sizeof(mm_init), cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(h->d_massmm, 0xFF, sizeof(uint32_t), s));
+    CU(cudaMemsetAsync(h->d_massmm + 1, 0, sizeof(uint32_t), s));
     int grid = h->sm_count * 8;
     int64_t need = (h->n + 255) / 256;
     if (need < grid) grid = (int)need;
-    k_cell_count<<<grid, 256, 0, s>>>(h->d_in, h->n, g, h->d_ce, h->d_massmm);
-    int64_t ntile = (ncell + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_reduce<<<(unsigned)ntile, 256, 0, s>>>(h->d_ce + 1, ncell, h->d_bsum);
-    k_scan_bsums<<<1, 1024, 0, s>>>(h->d_bsum, ntile);
-    k_scan_apply<<<(unsigned)ntile, 256, 0, s>>>(h->d_ce + 1, ncell, h->d_bsum);
-    k_scatter<<<grid, 256, 0, s>>>(h->d_in, h->n, g, h->d_ce, h->d_sorted, h->d_orig);
-    CU(cudaGetLastError());
-    uint32_t mm[2];
-    CU(cudaMemcpyAsync(mm, h->d_massmm, sizeof(mm), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    h->equal_mass = (mm[0] == mm[1]);
-    memcpy(&h->mass, &mm[0], sizeof(float));
-    h->stats.last_kernel_launches = 5;
-    if (h->equal_mass) {
-        if (so_mass_table_build(&h->mt, h->mass, (uint64_t)h->n + 2))
-            return set_err(SOGPU_ERR_UNSUPPORTED, "cannot tabulate the running mass for m=%g", (double)h->mass);
-        if (!h->d_mt) CU(cudaMalloc(&h->d_mt, sizeof(so_mass_table)));
-        CU(cudaMemcpyAsync(h->d_mt, &h->mt, sizeof(so_mass_table), cudaMemcpyHostToDevice, s));
-        CU(cudaStreamSynchronize(s));
+    /* coarse digit = top cb bits of the cell key; buckets of ~64K particles */
+    int cb = 0;
+    while (cb < 8 && ((int64_t)65536 << cb) < h->n) ++cb;
+    if (cb > 3 * lb) cb = 3 * lb;
+    const bool two_level = h->two_level < 0 ? (cb >= 2) : (h->two_level != 0 && cb >= 1);
+    if (!two_level) {
+        { ProfScope p(h, KID_CELL_COUNT); k_cell_count<<<grid, 256, 0, s>>>(h->d_in, h->n, g, h->d_ce, h->d_massmm); }
+        {
+            ProfScope p(h, KID_SCAN);
+            k_scan_reduce<<<(unsigned)ntile, 256, 0, s>>>(h->d_ce + 1, ncell, h->d_bsum);
+            k_scan_bsums<<<1, 1024, 0, s>>>(h->d_bsum, ntile);
+            k_scan_apply<<<(unsigned)ntile, 256, 0, s>>>(h->d_ce + 1, ncell, h->d_bsum);
+        }
+        { ProfScope p(h, KID_SCATTER); k_scatter<<<grid, 256, 0, s>>>(h->d_in, h->n, g, h->d_ce, h->d_sorted, h->d_orig); }
+    } else {
+        if (!h->d_coarse) CU(cudaMalloc(&h->d_coarse, PART_BMAX * sizeof(uint32_t)));
+        if (h->n > h->tmp_cap) {
+            cudaFree(h->d_tmp4); cudaFree(h->d_tmpk); cudaFree(h->d_tmpi);
+            h->d_tmp4 = nullptr; h->d_tmpk = nullptr; h->d_tmpi = nullptr; h->tmp_cap = 0;
+            CU(cudaMalloc(&h->d_tmp4, (size_t)h->n * sizeof(float4)));
+            CU(cudaMalloc(&h->d_tmpk, (size_t)h->n * sizeof(uint32_t)));
+            CU(cudaMalloc(&h->d_tmpi, (size_t)h->n * sizeof(int32_t)));
+            h->tmp_cap = h->n;
+        }
+        const int kshift = 3 * lb - cb;
+        const size_t part_smem = (size_t)PART_T * (16 + 4 + 2 + 2 + 1);
+        static bool attr_done = false;
+        if (!attr_done) {
+            CU(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
+            attr_done = true;
+        }
+        CU(cudaMemsetAsync(h->d_coarse, 0, PART_BMAX * sizeof(uint32_t), s));
+        { ProfScope p(h, KID_COARSE_HIST); k_coarse_hist<<<grid, 256, 0, s>>>(h->d_in, h->n, g, kshift, h->d_coarse, h->d_massmm); }
+        { ProfScope p(h, KID_COARSE_SCAN); k_coarse_scan<<<1, 256, 0, s>>>(h->d_coarse); }
+        {
+            ProfScope p(h, KID_PARTITION);
+            int64_t tiles = (h->n + PART_T - 1) / PART_T;
+            int pg = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 2);
+            k_partition<<<pg, 256, part_smem, s>>>(h->d_in, h->n, g, kshift, h->d_coarse, h->d_tmp4, h->d_tmpk, h->d_tmpi);
+        }
+        { ProfScope p(h, KID_FINE_COUNT); k_fine_count<<<grid, 256, 0, s>>>(h->d_tmpk, h->n, h->d_ce); }
+        {
+            ProfScope p(h, KID_SCAN);
+            k_scan_reduce<<<(unsigned)ntile, 256, 0, s>>>(h->d_ce + 1, ncell, h->d_bsum);
+            k_scan_bsums<<<1, 1024, 0, s>>>(h->d_bsum, ntile);
+            k_scan_apply<<<(unsigned)ntile, 256, 0, s>>>(h->d_ce + 1, ncell, h->d_bsum);
+        }
+        {
+            ProfScope p(h, KID_FINE_SCATTER);
+            k_fine_scatter<<<grid, 256, 0, s>>>(h->d_tmp4, h->d_tmpk, h->d_tmpi, h->n, h->d_ce, h->d_sorted, h->d_orig);
+        }
     }
+    { ProfScope p(h, KID_MASS_TABLE); k_mass_table<<<1, 32, 0, s>>>(h->d_massmm, h->d_mt, (unsigned long long)h->n + 2ull); }
+    CU(cudaGetLastError());
     h->built = true;
+    h->have_result = false;
+    h->mass_state = -1;
     h->stats.n_particles = h->n;
     h->stats.cells_per_axis = nc;
-    h->stats.equal_mass = h->equal_mass;
+    return SOGPU_OK;
+}
+
+/* lazily learn (one small D2H) whether the particle masses were all equal */
+static int fetch_mass_state(sogpu *h)
+{
+    if (h->mass_state >= 0) return SOGPU_OK;
+    uint32_t mm[2];
+    CU(cudaMemcpyAsync(mm, h->d_massmm, sizeof(mm), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->mass_state = (mm[0] == mm[1]) ? 1 : 0;
+    memcpy(&h->mass, &mm[0], sizeof(float));
+    h->stats.equal_mass = h->mass_state;
     return SOGPU_OK;
 }
 
 static int ensure_query(sogpu *h, int32_t nh)
 {
     if (!h->d_counters) {
-        CU(cudaMalloc(&h->d_counters, 8 * sizeof(uint32_t)));
+        CU(cudaMalloc(&h->d_counters, 16 * sizeof(uint32_t)));
         CU(cudaMalloc(&h->d_u64, 4 * sizeof(unsigned long long)));
     }
     if (nh > h->cap_h) {
@@ -1289,13 +1682,17 @@ static int ensure_query(sogpu *h, int32_t nh)
         CU(cudaMalloc(&h->d_rgtp, (size_t)cap * sizeof(float)));
         CU(cudaMalloc(&h->d_small, (size_t)cap * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_big, (size_t)cap * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_esmall, (size_t)cap * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_ebig, (size_t)cap * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_out_n, (size_t)cap * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_out_m, (size_t)cap * sizeof(float)));
         CU(cudaMalloc(&h->d_out_key, (size_t)cap * sizeof(unsigned long long)));
-        CU(cudaMalloc(&h->d_out_off, (size_t)cap * sizeof(unsigned long long)));
+        CU(cudaMalloc(&h->d_out_off, ((size_t)cap + 1) * sizeof(unsigned long long)));
         h->cap_h = cap;
     }
-    if (!h->d_members) {
+    if (!h->d_members || h->member_cap < (unsigned long long)h->n) {
+        cudaFree(h->d_members); cudaFree(h->d_md2);
+        h->d_members = nullptr; h->d_md2 = nullptr;
         h->member_cap = (unsigned long long)std::max<int64_t>(h->n, 1 << 20);
         CU(cudaMalloc(&h->d_members, (size_t)h->member_cap * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_md2, (size_t)h->member_cap * sizeof(float)));
@@ -1303,70 +1700,80 @@ static int ensure_query(sogpu *h, int32_t nh)
     return SOGPU_OK;
 }
 
-/* enqueue the query for nh halos whose centers/rgtp are on the device */
+template <int NT, typename K>
+static void launch_persistent(sogpu *h, K kernel, const QueryArgs &a, int nh)
+{
+    int ctas = h->sm_count * 4;
+    int need = (nh + Cfg<NT>::GROUPS - 1) / Cfg<NT>::GROUPS;
+    if (need < ctas) ctas = std::max(need, 1);
+    kernel<<<ctas, NT * Cfg<NT>::GROUPS, query_smem_bytes<NT>(), h->stream>>>(a);
+}
+
+/* enqueue query + member emission for nh halos whose centers/rgtp are on the device */
 static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int32_t nh, float thr, int32_t nM)
 {
     if (!h->built) return set_err(SOGPU_ERR_ARG, "sogpu_so: call sogpu_build_grid first");
-    if (!h->equal_mass)
-        return set_err(SOGPU_ERR_UNSUPPORTED, "particles have unequal masses: the exact sequential-mass path "
-                                              "for mixed masses is not implemented yet");
     if (nM < 2) return set_err(SOGPU_ERR_ARG, "nMembers must be >= 2 (the reference reads nnList[-1] otherwise, kd2.c:791)");
     if (nh <= 0) return set_err(SOGPU_ERR_ARG, "no halos");
+    if (!(thr > 0.0f)) return set_err(SOGPU_ERR_ARG, "density threshold must be positive");
     int rc = ensure_query(h, nh);
     if (rc) return rc;
     cudaStream_t s = h->stream;
-    CU(cudaMemsetAsync(h->d_counters, 0, 8 * sizeof(uint32_t), s));
+    h->stats.last_kernel_launches = 0;
+    CU(cudaMemsetAsync(h->d_counters, 0, 16 * sizeof(uint32_t), s));
     CU(cudaMemsetAsync(h->d_u64, 0, 4 * sizeof(unsigned long long), s));
 
-    /* expected particles in the final ball: halo of radius R ~ 1.25 rgtp at density thr, ball 1.2 R */
-    double per_r3 = 1.3 * (double)thr * SO_C43PI * 1.25 * 1.25 * 1.25 / (double)h->mass;
     const float small_max = 1024.0f;
-    k_classify<<<(nh + 255) / 256, 256, 0, s>>>(d_rgtp, nh, (float)per_r3, small_max, h->d_small,
-                                                h->d_counters + 0, h->d_big, h->d_counters + 1);
+    {
+        ProfScope p(h, KID_CLASSIFY);
+        k_classify<<<(nh + 255) / 256, 256, 0, s>>>(d_rgtp, nh, thr, h->d_mt, small_max, h->d_small,
+                                                    h->d_counters + 0, h->d_big, h->d_counters + 1);
+    }
     QueryArgs a;
     a.g = h->g;
     a.centers = d_centers; a.rgtp = d_rgtp;
     a.thr = thr; a.nM = nM;
     a.out_n = h->d_out_n; a.out_m = h->d_out_m; a.out_key = h->d_out_key; a.out_off = h->d_out_off;
-    a.members = h->d_members; a.md2 = h->d_md2;
-    a.member_total = h->d_u64 + 0; a.member_cap = h->member_cap;
+    a.members = h->d_members; a.md2 = h->want_d2 ? h->d_md2 : nullptr;
+    a.member_cap = h->member_cap;
     a.evals = h->d_u64 + 1;
-    a.overflow = h->d_counters + 4;
+    a.flags = h->d_counters + 4;
     a.mt = h->d_mt;
     a.defer_list = h->d_big; a.defer_n = h->d_counters + 1;
 
     /* warp-per-halo kernel over the small list; halos it cannot finish are appended to the big list */
     a.list = h->d_small; a.list_n = h->d_counters + 0; a.work_counter = h->d_counters + 2;
-    {
-        int ctas = h->sm_count * 4;
-        int need = (nh + Cfg<32>::GROUPS - 1) / Cfg<32>::GROUPS;
-        if (need < ctas) ctas = std::max(need, 1);
-        k_so_query<32><<<ctas, 32 * Cfg<32>::GROUPS, query_smem_bytes<32>(), s>>>(a);
-    }
+    { ProfScope p(h, KID_QUERY_WARP); launch_persistent<32>(h, k_so_query<32>, a, nh); }
     /* block-per-halo kernel over the big list (+ deferred) */
     a.list = h->d_big; a.list_n = h->d_counters + 1; a.work_counter = h->d_counters + 3;
+    { ProfScope p(h, KID_QUERY_BLOCK); launch_persistent<256>(h, k_so_query<256>, a, nh); }
+    /* member offsets in catalog order, then the member lists */
     {
-        int ctas = h->sm_count * 4;
-        if (nh < ctas) ctas = nh;
-        k_so_query<256><<<ctas, 256, query_smem_bytes<256>(), s>>>(a);
+        ProfScope p(h, KID_OFFSETS);
+        k_offsets<<<1, 1024, 0, s>>>(h->d_out_n, nh, h->d_out_off, h->d_u64 + 0, 2048, h->d_esmall,
+                                     h->d_counters + 5, h->d_ebig, h->d_counters + 6);
     }
+    a.list = h->d_esmall; a.list_n = h->d_counters + 5; a.work_counter = h->d_counters + 7;
+    { ProfScope p(h, KID_EMIT_WARP); launch_persistent<32>(h, k_so_emit<32>, a, nh); }
+    a.list = h->d_ebig; a.list_n = h->d_counters + 6; a.work_counter = h->d_counters + 8;
+    { ProfScope p(h, KID_EMIT_BLOCK); launch_persistent<256>(h, k_so_emit<256>, a, nh); }
     CU(cudaGetLastError());
-    h->stats.last_kernel_launches = 3;
     h->last_h = nh;
-    h->have_members = true;
+    h->have_result = true;
     return SOGPU_OK;
 }
 
 static int fetch_stats(sogpu *h)
 {
     unsigned long long u[4];
-    uint32_t c[8];
+    uint32_t c[16];
     CU(cudaMemcpyAsync(u, h->d_u64, sizeof(u), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->stats.last_members = (int64_t)u[0];
     h->stats.last_evals_first = (int64_t)u[1];
     h->stats.last_evals = (int64_t)(u[1] + u[2]);
+    h->stats.last_deferred = (int32_t)(c[1] + c[0]) - h->last_h;   /* halos listed twice = deferred */
     if (c[4] & 1u) return set_err(SOGPU_ERR_NOMEM, "member buffer overflow (%llu > %llu)", u[0], h->member_cap);
     if (c[4] & 2u) return set_err(SOGPU_ERR_UNSUPPORTED, "internal: member emission count mismatch");
     return SOGPU_OK;
@@ -1394,21 +1801,20 @@ extern "C" int sogpu_so(sogpu_t *h, const float *centers, const float *rgtp, int
     if (rc) return rc;
     size_t bytes_in = (size_t)nh * 4 * sizeof(float);
     size_t bytes_out = (size_t)nh * (sizeof(int32_t) + sizeof(float));
-    rc = ensure_pinned(h, std::max(bytes_in, bytes_out));
+    rc = ensure_pinned(h, bytes_in + bytes_out);
     if (rc) return rc;
     float *pc = (float *)h->h_pin, *pr = pc + (size_t)3 * nh;
+    int32_t *pn = (int32_t *)(pr + nh);
+    float *pm = (float *)(pn + nh);
     memcpy(pc, centers, (size_t)nh * 3 * sizeof(float));
     memcpy(pr, rgtp, (size_t)nh * sizeof(float));
     CU(cudaMemcpyAsync(h->d_centers, pc, (size_t)nh * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_rgtp, pr, (size_t)nh * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     rc = run_query(h, h->d_centers, h->d_rgtp, nh, thr, nM);
     if (rc) return rc;
-    CU(cudaStreamSynchronize(h->stream));   /* staging buffer is reused for the results */
-    int32_t *pn = (int32_t *)h->h_pin;
-    float *pm = (float *)(pn + nh);
     CU(cudaMemcpyAsync(pn, h->d_out_n, (size_t)nh * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(pm, h->d_out_m, (size_t)nh * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    rc = fetch_stats(h);
+    rc = fetch_stats(h);   /* synchronises the stream */
     if (rc) return rc;
     for (int32_t i = 0; i < nh; ++i) {
         int32_t n = pn[i];
@@ -1418,7 +1824,11 @@ extern "C" int sogpu_so(sogpu_t *h, const float *centers, const float *rgtp, int
             rvir[i] = so_rdelta_host(pm[i], thr);                         /* kd2.c:817-820 */
         } else if (n == -1 || n == -2 || n == -3) {
             ndelta[i] = 0;
-            mvir[i] = rvir[i] = (float)n;
+            mvir[i] = rvir[i] = (float)n;                                 /* kd2.c:774-776,793-795,837-838 */
+        } else if (n == CODE_UNEQUAL_MASS) {
+            h->mass_state = 0; h->stats.equal_mass = 0;
+            return set_err(SOGPU_ERR_UNSUPPORTED, "particles have unequal masses: the exact sequential-mass "
+                                                  "path for mixed masses is not implemented yet");
         } else {
             return set_err(SOGPU_ERR_UNSUPPORTED, "halo %d: unsupported particle configuration (code %d)", i, n);
         }
@@ -1426,61 +1836,77 @@ extern "C" int sogpu_so(sogpu_t *h, const float *centers, const float *rgtp, int
     return SOGPU_OK;
 }
 
-extern "C" int sogpu_members(sogpu_t *h, int64_t *offsets, const int32_t **members, const float **d2)
+/* convert the packed N_Delta/code array of sogpu_so_device into rvir/mvir/ndelta on the host */
+extern "C" int sogpu_finish_host(const int32_t *code_or_n, const float *m, int32_t nh, float thr, float *rvir,
+                                 float *mvir, int32_t *ndelta)
+{
+    if (!code_or_n || !m || !rvir || !mvir || !ndelta) return set_err(SOGPU_ERR_ARG, "sogpu_finish_host: NULL argument");
+    for (int32_t i = 0; i < nh; ++i) {
+        int32_t n = code_or_n[i];
+        if (n > 0) { ndelta[i] = n; mvir[i] = m[i]; rvir[i] = so_rdelta_host(m[i], thr); }
+        else if (n == -1 || n == -2 || n == -3) { ndelta[i] = 0; mvir[i] = rvir[i] = (float)n; }
+        else return set_err(SOGPU_ERR_UNSUPPORTED, "halo %d: code %d", i, n);
+    }
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_members(sogpu_t *h, int64_t *offsets, const int32_t **members, const float **d2, int sorted)
 {
     if (!h || !offsets || !members) return set_err(SOGPU_ERR_ARG, "sogpu_members: NULL argument");
-    if (!h->have_members) return set_err(SOGPU_ERR_ARG, "sogpu_members: no sogpu_so result available");
+    if (!h->have_result) return set_err(SOGPU_ERR_ARG, "sogpu_members: no sogpu_so result available");
+    if ((sorted || d2) && !h->want_d2)
+        return set_err(SOGPU_ERR_ARG, "sogpu_members: call sogpu_keep_member_d2(h,1) before sogpu_so to get r^2 / sorted lists");
     CU(cudaSetDevice(h->device));
     const int32_t nh = h->last_h;
     int rc = fetch_stats(h);
     if (rc) return rc;
     const size_t tot = (size_t)h->stats.last_members;
-    std::vector<int32_t> on(nh);
-    std::vector<unsigned long long> ooff(nh);
-    CU(cudaMemcpy(on.data(), h->d_out_n, (size_t)nh * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(ooff.data(), h->d_out_off, (size_t)nh * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     if (tot + 1 > h->h_members_cap) {
         if (h->h_members) cudaFreeHost(h->h_members);
         if (h->h_md2) cudaFreeHost(h->h_md2);
         h->h_members = nullptr; h->h_md2 = nullptr; h->h_members_cap = 0;
         size_t cap = std::max<size_t>(tot + 1, 1 << 16);
-        CU(cudaMallocHost((void **)&h->h_members, 2 * cap * sizeof(int32_t)));
-        CU(cudaMallocHost((void **)&h->h_md2, 2 * cap * sizeof(float)));
+        CU(cudaMallocHost((void **)&h->h_members, cap * sizeof(int32_t)));
+        CU(cudaMallocHost((void **)&h->h_md2, cap * sizeof(float)));
         h->h_members_cap = cap;
     }
-    /* raw (device order) in the upper half, final (catalog order, sorted) in the lower half */
-    int32_t *raw_i = h->h_members + h->h_members_cap;
-    float *raw_d = h->h_md2 + h->h_members_cap;
+    static_assert(sizeof(unsigned long long) == sizeof(int64_t), "offset type");
+    CU(cudaMemcpyAsync(offsets, h->d_out_off, ((size_t)nh + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     if (tot) {
-        CU(cudaMemcpy(raw_i, h->d_members, tot * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(raw_d, h->d_md2, tot * sizeof(float), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpyAsync(h->h_members, h->d_members, tot * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        if (h->want_d2)
+            CU(cudaMemcpyAsync(h->h_md2, h->d_md2, tot * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     }
-    std::vector<std::pair<uint64_t, uint32_t>> tmp;
-    int64_t run = 0;
-    for (int32_t i = 0; i < nh; ++i) {
-        offsets[i] = run;
-        int32_t n = on[i] > 0 ? on[i] : 0;
-        if (n) {
-            const int32_t *si = raw_i + ooff[i];
-            const float *sd = raw_d + ooff[i];
-            tmp.resize(n);
-            for (int32_t k = 0; k < n; ++k) {
+    CU(cudaStreamSynchronize(h->stream));
+    if (sorted && tot) {
+        /* ascending (fDist2, index): the order kdTagParticles walks the list (kd2.c:670,781) */
+        std::vector<std::pair<uint64_t, float>> tmp;
+        for (int32_t i = 0; i < nh; ++i) {
+            int64_t a0 = offsets[i], n = offsets[i + 1] - a0;
+            if (n <= 1) continue;
+            tmp.resize((size_t)n);
+            for (int64_t k = 0; k < n; ++k) {
                 uint32_t bits;
-                memcpy(&bits, &sd[k], 4);
-                tmp[k].first = ((uint64_t)bits << 32) | (uint32_t)si[k];
-                tmp[k].second = (uint32_t)k;
+                memcpy(&bits, &h->h_md2[a0 + k], 4);
+                tmp[k].first = ((uint64_t)bits << 32) | (uint32_t)h->h_members[a0 + k];
+                tmp[k].second = h->h_md2[a0 + k];
             }
             std::sort(tmp.begin(), tmp.end());
-            for (int32_t k = 0; k < n; ++k) {
-                h->h_members[run + k] = si[tmp[k].second];
-                h->h_md2[run + k] = sd[tmp[k].second];
+            for (int64_t k = 0; k < n; ++k) {
+                h->h_members[a0 + k] = (int32_t)(uint32_t)tmp[k].first;
+                h->h_md2[a0 + k] = tmp[k].second;
             }
         }
-        run += n;
     }
-    offsets[nh] = run;
     *members = h->h_members;
     if (d2) *d2 = h->h_md2;
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_keep_member_d2(sogpu_t *h, int on)
+{
+    if (!h) return set_err(SOGPU_ERR_ARG, "NULL handle");
+    h->want_d2 = on != 0;
     return SOGPU_OK;
 }
 
@@ -1494,14 +1920,18 @@ extern "C" int sogpu_ball_gather(sogpu_t *h, const float center[3], float ball2,
     int rc = ensure_query(h, 1);
     if (rc) return rc;
     cudaStream_t s = h->stream;
+    h->stats.last_kernel_launches = 0;
     CU(cudaMemsetAsync(h->d_u64 + 3, 0, sizeof(unsigned long long), s));
-    k_ball_gather<<<h->sm_count * 2, 256, 0, s>>>(h->g, center[0], center[1], center[2], ball2, h->d_members,
-                                                 h->d_md2, h->d_u64 + 3, h->member_cap);
+    {
+        ProfScope p(h, KID_BALL_GATHER);
+        k_ball_gather<<<h->sm_count * 2, 256, 0, s>>>(h->g, center[0], center[1], center[2], ball2, h->d_members,
+                                                     h->d_md2, h->d_u64 + 3, h->member_cap);
+    }
     CU(cudaGetLastError());
     unsigned long long cnt = 0;
     CU(cudaMemcpyAsync(&cnt, h->d_u64 + 3, sizeof(cnt), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    h->have_members = false;
+    h->have_result = false;
     *n = (int64_t)cnt;
     if (cnt > h->member_cap) return set_err(SOGPU_ERR_NOMEM, "ball holds %llu particles, buffer %llu", cnt, h->member_cap);
     if (cnt && (idx || d2) && cap > 0) {
@@ -1529,16 +1959,50 @@ extern "C" int sogpu_ball_gather(sogpu_t *h, const float center[3], float ball2,
 extern "C" int sogpu_get_stats(sogpu_t *h, sogpu_stats_t *out)
 {
     if (!h || !out) return set_err(SOGPU_ERR_ARG, "sogpu_get_stats: NULL argument");
-    if (h->have_members) {
-        CU(cudaSetDevice(h->device));
+    CU(cudaSetDevice(h->device));
+    if (h->built) {
+        int rc = fetch_mass_state(h);
+        if (rc) return rc;
+    }
+    if (h->have_result) {
         int rc = fetch_stats(h);
         if (rc) return rc;
-        uint32_t c[8];
-        CU(cudaMemcpy(c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
-        h->stats.last_deferred = 0;
-        (void)c;
     }
     *out = h->stats;
+    return SOGPU_OK;
+}
+
+/* ---- profiling: CUDA-event time per kernel, on the stream the kernels run on ------------------ */
+
+extern "C" int sogpu_profile_enable(sogpu_t *h, int on)
+{
+    if (!h) return set_err(SOGPU_ERR_ARG, "NULL handle");
+    h->prof_on = on != 0;
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_profile_kernels(void) { return KID_N; }
+
+extern "C" const char *sogpu_profile_name(int kid) { return (kid >= 0 && kid < KID_N) ? g_kernel_names[kid] : ""; }
+
+extern "C" int sogpu_profile_read(sogpu_t *h, double *ms, int64_t *launches, int nk, int reset)
+{
+    if (!h || !ms || !launches) return set_err(SOGPU_ERR_ARG, "sogpu_profile_read: NULL argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    for (auto &r : h->prof_pending) {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
+            h->prof_ms[r.kid] += (double)t;
+            h->prof_launches[r.kid] += (r.kid == KID_SCAN) ? 3 : 1;
+        }
+        h->prof_pool.push_back(r.a);
+        h->prof_pool.push_back(r.b);
+    }
+    h->prof_pending.clear();
+    for (int k = 0; k < nk && k < KID_N; ++k) { ms[k] = h->prof_ms[k]; launches[k] = h->prof_launches[k]; }
+    if (reset)
+        for (int k = 0; k < KID_N; ++k) { h->prof_ms[k] = 0.0; h->prof_launches[k] = 0; }
     return SOGPU_OK;
 }
 

@@ -18,8 +18,9 @@ def run_gpu(pos, mass, centers, rgtp, thr, n_members=8, period=(1.0, 1.0, 1.0), 
         g.set_cell_occupancy(ppc)
     g.set_particles(pos, mass, period, center)
     g.build_grid()
+    g.keep_member_d2(True)
     r = g.so(centers, rgtp, thr, n_members)
-    r["member_offset"], r["members"], r["members_d2"] = g.members(want_d2=True)
+    r["member_offset"], r["members"], r["members_d2"] = g.members(want_d2=True, sorted=True)
     r["stats"] = g.stats()
     g.close()
     return r
@@ -138,6 +139,26 @@ def test_cell_size_does_not_change_results():
         assert np.array_equal(r["members"], base["members"])
 
 
+def test_build_strategies_agree():
+    """Single counting sort vs coarse-partition-first build: identical results."""
+    s = synth.make_snapshot(80 ** 3, 60, seed=42, nmax=8000)
+    out = []
+    for mode in (0, 1):
+        g = api.SoGpu()
+        g.set_build_mode(mode)
+        g.set_particles(s.pos, s.mass)
+        g.build_grid()
+        g.keep_member_d2(True)
+        r = g.so(s.centers, s.rgtp, 200.0)
+        r["off"], r["mem"] = g.members(sorted=True)
+        out.append(r)
+        g.close()
+    assert_so_equal(out[1], out[0]["rvir"], out[0]["mvir"], out[0]["ndelta"])
+    assert np.array_equal(out[0]["mem"], out[1]["mem"])
+    ref = po.Oracle(s.pos, s.mass).so(s.centers, s.rgtp, np.float32(200.0), 8)
+    assert np.array_equal(out[1]["mem"], ref["members"])
+
+
 def test_records_layout_and_tiny_inputs():
     """AoS input with stride (tipsy dark records) and N smaller than the reference's nSmooth."""
     from so_b200 import tipsy
@@ -146,8 +167,9 @@ def test_records_layout_and_tiny_inputs():
     g = api.SoGpu()
     g.set_particles_records(d)
     g.build_grid()
+    g.keep_member_d2(True)
     r = g.so(s.centers, s.rgtp, 200.0)
-    off, mem = g.members()
+    off, mem = g.members(sorted=True)
     ref = po.Oracle(s.pos, s.mass).so(s.centers, s.rgtp, np.float32(200.0), 8)
     assert_so_equal(r, ref["rvir"], ref["mvir"], ref["ndelta"])
     assert np.array_equal(mem, ref["members"])

@@ -13,9 +13,10 @@ def compare(s, thr=200.0, nmem=8, label=""):
     t1 = time.time()
     g.build_grid()
     t2 = time.time()
+    g.keep_member_d2(True)
     r = g.so(s.centers, s.rgtp, thr, nmem)
     t3 = time.time()
-    off, mem = g.members()
+    off, mem = g.members(sorted=True)
     t4 = time.time()
     st = g.stats()
     print("[%s] N=%d H=%d upload %.3fs build %.3fs so %.3fs members %.3fs stats %s" %
