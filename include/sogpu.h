@@ -123,6 +123,11 @@ int sogpu_keep_member_d2(sogpu_t *h, int on);
 int sogpu_ball_gather(sogpu_t *h, const float center[3], float ball2, int32_t *idx, float *d2,
                       int64_t cap, int64_t *n);
 
+/* Batched form: nh balls (centers nh*3, ball2 nh; host pointers).  The lists are then fetched with
+ * sogpu_members() exactly like SO member lists (offsets, indices, r^2; sorted on request).  This
+ * is the 2*Rvir gather of kdVcirc (kd2.c:511-514) for all halos in one pass. */
+int sogpu_ball_gather_batch(sogpu_t *h, const float *centers, const float *ball2, int32_t nh);
+
 /* ---- introspection --------------------------------------------------------------------------- */
 
 typedef struct {

@@ -26,7 +26,7 @@ SYMBOLS = [
     "sogpu_get_stats", "sogpu_mass_prefix", "sogpu_ball_schedule", "sogpu_rdelta",
     "sogpu_finish_host", "sogpu_keep_member_d2", "sogpu_profile_enable", "sogpu_profile_kernels",
     "sogpu_profile_name", "sogpu_profile_read", "sogpu_upload_particles",
-    "sogpu_set_build_mode",
+    "sogpu_set_build_mode", "sogpu_ball_gather_batch",
 ]
 
 
@@ -81,6 +81,8 @@ def lib():
     L.sogpu_profile_name.argtypes = [C.c_int]
     L.sogpu_profile_read.argtypes = [vp, C.POINTER(C.c_double), i64p, C.c_int, C.c_int]
     L.sogpu_ball_gather.argtypes = [vp, fp, C.c_float, i32p, fp, C.c_int64, i64p]
+    L.sogpu_ball_gather_batch.argtypes = [vp, fp, fp, C.c_int32]
+    L.sogpu_ball_gather_batch.restype = C.c_int
     L.sogpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.sogpu_mass_prefix.argtypes = [C.c_float, C.c_int64, i64p, C.c_int64, fp]
     L.sogpu_ball_schedule.restype = C.c_int
@@ -295,6 +297,14 @@ class SoGpu:
                                        idx.ctypes.data_as(C.POINTER(C.c_int32)), _fp(d2), cap, C.byref(n)))
         k = min(cap, n.value)
         return idx[:k], d2[:k], n.value
+
+    def ball_gather_batch(self, centers, ball2, sorted=True):
+        """All particles with fDist2 <= ball2[i] around centers[i]: (offsets, indices, d2)."""
+        centers = np.ascontiguousarray(centers, np.float32)
+        ball2 = np.ascontiguousarray(ball2, np.float32)
+        _check(lib().sogpu_ball_gather_batch(self._h, _fp(centers), _fp(ball2), len(ball2)))
+        self._last_h = len(ball2)
+        return self.members(want_d2=True, sorted=sorted)
 
     def stats(self):
         s = Stats()

@@ -1178,6 +1178,58 @@ __global__ void __launch_bounds__(1024) k_offsets(const int32_t *__restrict__ ou
     if (threadIdx.x == 0) { out_off[nh] = carry; *total = carry; }
 }
 
+/* batched smBallGather, phase 1: count the particles with fDist2 <= ball2[h] (one warp per ball) */
+struct CountF {
+    const GridDev *g;
+    Center c;
+    uint32_t hi_bits;
+    uint32_t n;
+    __device__ __forceinline__ void operator()(uint32_t, const float4 &q)
+    {
+        if (__float_as_uint(dist2(c, q, *g)) <= hi_bits) ++n;
+    }
+};
+
+__global__ void __launch_bounds__(256) k_ball_count(const __grid_constant__ QueryArgs a, const float *ball2)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const size_t mt_bytes = (sizeof(MassTableS) + 15) & ~(size_t)15;
+    const int grp = threadIdx.x / 32, tid = threadIdx.x % 32;
+    GroupSmem<32> &sm = *reinterpret_cast<GroupSmem<32> *>(
+        smem_raw + mt_bytes + (size_t)grp * ((sizeof(GroupSmem<32>) + 15) & ~(size_t)15));
+    const uint32_t nlist = *a.list_n;
+    uint32_t ev = 0;
+    for (;;) {
+        const uint32_t h = next_item<32>(a.work_counter, sm, tid);
+        if (h >= nlist) break;
+        const float b2 = ball2[h];
+        uint32_t n = 0;
+        if (b2 >= 0.0f && b2 < INFINITY) {
+            CountF f;
+            f.g = &a.g; f.c.x = a.centers[3 * h]; f.c.y = a.centers[3 * h + 1]; f.c.z = a.centers[3 * h + 2];
+            f.hi_bits = __float_as_uint(b2); f.n = 0;
+            BallGeom B = make_geom(a.g, f.c, sqrt((double)b2) * (1.0 + 1.0e-6));
+            for_each_in_ball<32>(a.g, sm, tid, B, f, ev);
+            n = __reduce_add_sync(0xFFFFFFFFu, f.n);
+        }
+        if (tid == 0) {
+            a.out_n[h] = (int32_t)n;
+            /* key just above every (r^2 <= ball2, index): the emit kernel's "< key_j" keeps them all */
+            a.out_key[h] = ((unsigned long long)(__float_as_uint(b2) + 1u)) << 32;
+        }
+    }
+    ev = __reduce_add_sync(0xFFFFFFFFu, ev);
+    if ((threadIdx.x & 31) == 0 && ev) atomicAdd(&a.evals[1], (unsigned long long)ev);
+}
+
+/* identity work list 0..n-1 */
+__global__ void k_iota(int32_t *list, uint32_t *list_n, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) list[i] = i;
+    if (i == 0) *list_n = (uint32_t)n;
+}
+
 /* the running-mass table, built on the device so that build -> query needs no host round trip */
 __global__ void k_mass_table(const uint32_t *__restrict__ massmm, so_mass_table *mt, unsigned long long kmax)
 {
@@ -1354,6 +1406,8 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
         e = cudaFuncSetAttribute(k_so_emit<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<256>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_so_emit<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<32>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_ball_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<32>());
     if (e != cudaSuccess) {
         cudaStreamDestroy(h->own_stream); delete h;
         return set_err(SOGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -1700,13 +1754,13 @@ static int ensure_query(sogpu *h, int32_t nh)
     return SOGPU_OK;
 }
 
-template <int NT, typename K>
-static void launch_persistent(sogpu *h, K kernel, const QueryArgs &a, int nh)
+template <int NT, typename K, typename... Extra>
+static void launch_persistent(sogpu *h, K kernel, const QueryArgs &a, int nh, Extra... extra)
 {
     int ctas = h->sm_count * 4;
     int need = (nh + Cfg<NT>::GROUPS - 1) / Cfg<NT>::GROUPS;
     if (need < ctas) ctas = std::max(need, 1);
-    kernel<<<ctas, NT * Cfg<NT>::GROUPS, query_smem_bytes<NT>(), h->stream>>>(a);
+    kernel<<<ctas, NT * Cfg<NT>::GROUPS, query_smem_bytes<NT>(), h->stream>>>(a, extra...);
 }
 
 /* enqueue query + member emission for nh halos whose centers/rgtp are on the device */
@@ -1953,6 +2007,64 @@ extern "C" int sogpu_ball_gather(sogpu_t *h, const float center[3], float ball2,
             if (d2) d2[k] = td[tmp[k].second];
         }
     }
+    return SOGPU_OK;
+}
+
+/* Batched smBallGather (smooth2.c:58-114): for each of nh balls all particles with
+ * fDist2 <= ball2[i], as CSR lists fetched with sogpu_members (d2 kept, sorted on request). */
+extern "C" int sogpu_ball_gather_batch(sogpu_t *h, const float *centers, const float *ball2, int32_t nh)
+{
+    if (!h || !centers || !ball2 || nh <= 0) return set_err(SOGPU_ERR_ARG, "sogpu_ball_gather_batch: bad argument");
+    if (!h->built) return set_err(SOGPU_ERR_ARG, "sogpu_ball_gather_batch: call sogpu_build_grid first");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_query(h, nh);
+    if (rc) return rc;
+    rc = ensure_pinned(h, (size_t)nh * 4 * sizeof(float));
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    float *pc = (float *)h->h_pin, *pb = pc + (size_t)3 * nh;
+    memcpy(pc, centers, (size_t)nh * 3 * sizeof(float));
+    memcpy(pb, ball2, (size_t)nh * sizeof(float));
+    CU(cudaMemcpyAsync(h->d_centers, pc, (size_t)nh * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->d_rgtp, pb, (size_t)nh * sizeof(float), cudaMemcpyHostToDevice, s));
+    h->stats.last_kernel_launches = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CU(cudaMemsetAsync(h->d_counters, 0, 16 * sizeof(uint32_t), s));
+        CU(cudaMemsetAsync(h->d_u64, 0, 4 * sizeof(unsigned long long), s));
+        QueryArgs a;
+        memset(&a, 0, sizeof(a));
+        a.g = h->g;
+        a.centers = h->d_centers; a.rgtp = h->d_rgtp;
+        a.out_n = h->d_out_n; a.out_m = h->d_out_m; a.out_key = h->d_out_key; a.out_off = h->d_out_off;
+        a.members = h->d_members; a.md2 = h->d_md2; a.member_cap = h->member_cap;
+        a.evals = h->d_u64 + 1; a.flags = h->d_counters + 4; a.mt = h->d_mt;
+        a.list = h->d_small; a.list_n = h->d_counters + 0; a.work_counter = h->d_counters + 2;
+        k_iota<<<(nh + 255) / 256, 256, 0, s>>>(h->d_small, h->d_counters + 0, nh);
+        { ProfScope p(h, KID_BALL_GATHER); launch_persistent<32>(h, k_ball_count, a, nh, h->d_rgtp); }
+        {
+            ProfScope p(h, KID_OFFSETS);
+            k_offsets<<<1, 1024, 0, s>>>(h->d_out_n, nh, h->d_out_off, h->d_u64 + 0, 2048, h->d_esmall,
+                                         h->d_counters + 5, h->d_ebig, h->d_counters + 6);
+        }
+        a.list = h->d_esmall; a.list_n = h->d_counters + 5; a.work_counter = h->d_counters + 7;
+        { ProfScope p(h, KID_EMIT_WARP); launch_persistent<32>(h, k_so_emit<32>, a, nh); }
+        a.list = h->d_ebig; a.list_n = h->d_counters + 6; a.work_counter = h->d_counters + 8;
+        { ProfScope p(h, KID_EMIT_BLOCK); launch_persistent<256>(h, k_so_emit<256>, a, nh); }
+        CU(cudaGetLastError());
+        unsigned long long tot = 0;
+        CU(cudaMemcpyAsync(&tot, h->d_u64, sizeof(tot), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (tot <= h->member_cap) break;
+        if (attempt == 1) return set_err(SOGPU_ERR_NOMEM, "ball lists need %llu entries", tot);
+        cudaFree(h->d_members); cudaFree(h->d_md2);
+        h->d_members = nullptr; h->d_md2 = nullptr;
+        h->member_cap = tot + tot / 8;
+        CU(cudaMalloc(&h->d_members, (size_t)h->member_cap * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_md2, (size_t)h->member_cap * sizeof(float)));
+    }
+    h->last_h = nh;
+    h->have_result = true;
+    h->want_d2 = true;
     return SOGPU_OK;
 }
 

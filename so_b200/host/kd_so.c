@@ -1,0 +1,396 @@
+/* kd_so.c — the hot-path calls of the drop-in `so`, routed to the GPU through include/sogpu.h.
+ *
+ *   kdBuildTree  (kd2.c:1096-1185)  -> sogpu_set_particles_host + sogpu_build_grid
+ *   kdSO         (kd2.c:864-895)    -> sogpu_so + sogpu_members, then on the host, in the
+ *                                      reference's processing order (kdSortMass/indexx,
+ *                                      kd2.c:843-861): kdTagParticles / kdZeroGroup bookkeeping
+ *                                      (kd2.c:617-720), _VcmParticles (kd2.c:595-609) and the
+ *                                      kdVcirc / kdMassProfile post-processing (kd2.c:437-586) over
+ *                                      GPU-gathered, r^2-sorted 2*Rvir lists (sogpu_ball_gather_batch).
+ *
+ * The conflict pass is order dependent (a later, more massive halo may subsume or slurp an earlier
+ * one) and touches O(sum N_Delta) items, so it stays sequential on the host; the reference's
+ * O(N) sweep per zeroed group (kd2.c:636-641) and O(H) search per conflicting particle
+ * (kd2.c:647-660) are replaced by the member lists and an index -> slot map.
+ */
+#include "kd.h"
+
+#include <assert.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/resource.h>
+
+static void die_gpu(const char *what)
+{
+    fprintf(stderr, "ERROR in %s: %s\n", what, sogpu_last_error());
+    exit(1);
+}
+
+void kdTime(KD kd, int *puSecond, int *puMicro)
+{
+    struct rusage ru;                                     /* kd2.c:46-59: user CPU time deltas */
+    getrusage(RUSAGE_SELF, &ru);
+    *puMicro = (int)ru.ru_utime.tv_usec - kd->uMicro;
+    *puSecond = (int)ru.ru_utime.tv_sec - kd->uSecond;
+    if (*puMicro < 0) {
+        *puMicro += 1000000;
+        *puSecond -= 1;
+    }
+    kd->uSecond = (int)ru.ru_utime.tv_sec;
+    kd->uMicro = (int)ru.ru_utime.tv_usec;
+}
+
+int kdInit(KD *pkd, int nBucket, float *fPeriod, float *fCenter, int bOutDiag, int nMembers, int bPeriodic,
+           int bDark, int bGas, int bStar, int bMark, int bPot)
+{
+    KD kd = (KD)calloc(1, sizeof(struct kdContext));
+    int j;
+    (void)bOutDiag;
+    assert(kd != NULL);
+    kd->nBucket = nBucket;
+    for (j = 0; j < 3; ++j) {
+        kd->fPeriod[j] = fPeriod[j];
+        kd->fCenter[j] = fCenter[j];
+    }
+    kd->G = 1.0f;
+    kd->nMembers = nMembers;
+    kd->bPeriodic = bPeriodic;
+    kd->bDark = bDark; kd->bGas = bGas; kd->bStar = bStar; kd->bMark = bMark; kd->bPot = bPot;
+    kd->iDevice = -1;
+    *pkd = kd;
+    return 1;
+}
+
+void kdSetUniverse(KD kd, float G, float Omega0, float Lambda, float H0, float z, float fMassUnit, float fMpcUnit)
+{
+    (void)Omega0; (void)Lambda; (void)H0;                 /* stored in a CSM the reference never reads again */
+    kd->G = G;
+    kd->z = z;
+    kd->fMassUnit = fMassUnit;
+    kd->fMpcUnit = fMpcUnit;
+}
+
+static double wall(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+int kdBuildTree(KD kd)
+{
+    double t0 = wall();
+    if (kd->nParticles == 0) return 1;
+    if (!kd->gpu && sogpu_create(&kd->gpu, kd->iDevice)) die_gpu("kdBuildTree (sogpu_create)");
+    if (sogpu_set_particles_host(kd->gpu, kd->p.r, 3 * sizeof(float), kd->p.fMass, sizeof(float), kd->nParticles,
+                                 kd->fPeriod, kd->fCenter))
+        die_gpu("kdBuildTree (sogpu_set_particles_host)");
+    if (sogpu_build_grid(kd->gpu)) die_gpu("kdBuildTree (sogpu_build_grid)");
+    kd->dBuildSeconds = wall() - t0;
+    return 1;
+}
+
+/* ---- indexx: Numerical-Recipes style index quicksort, ascending, 1-based (nr.c:91-151).  The
+ * permutation it yields for EQUAL keys is algorithm specific and defines the order in which such
+ * halos are processed, so the same algorithm (median of three, insertion sort below 7) is used. */
+void indexx(int n, float arr[], int indx[])
+{
+    enum { SMALL = 7, DEPTH = 64 };
+    int stack[DEPTH + 2], top = 0, lo = 1, hi = n, i, j, k, t, pivot_i;
+    float pivot;
+#define EXCH(a, b) do { t = (a); (a) = (b); (b) = t; } while (0)
+    for (j = 1; j <= n; ++j) indx[j] = j;
+    for (;;) {
+        if (hi - lo < SMALL) {
+            for (j = lo + 1; j <= hi; ++j) {
+                pivot_i = indx[j];
+                pivot = arr[pivot_i];
+                for (i = j - 1; i >= 1; --i) {
+                    if (arr[indx[i]] <= pivot) break;
+                    indx[i + 1] = indx[i];
+                }
+                indx[i + 1] = pivot_i;
+            }
+            if (top == 0) break;
+            hi = stack[top--];
+            lo = stack[top--];
+        } else {
+            k = (lo + hi) >> 1;
+            EXCH(indx[k], indx[lo + 1]);
+            if (arr[indx[lo + 1]] > arr[indx[hi]]) EXCH(indx[lo + 1], indx[hi]);
+            if (arr[indx[lo]] > arr[indx[hi]]) EXCH(indx[lo], indx[hi]);
+            if (arr[indx[lo + 1]] > arr[indx[lo]]) EXCH(indx[lo + 1], indx[lo]);
+            i = lo + 1;
+            j = hi;
+            pivot_i = indx[lo];
+            pivot = arr[pivot_i];
+            for (;;) {
+                do ++i; while (arr[indx[i]] < pivot);
+                do --j; while (arr[indx[j]] > pivot);
+                if (j < i) break;
+                EXCH(indx[i], indx[j]);
+            }
+            indx[lo] = indx[j];
+            indx[j] = pivot_i;
+            top += 2;
+            if (top > DEPTH) { fprintf(stderr, "indexx: stack too small\n"); exit(1); }
+            if (hi - i + 1 >= j - lo) { stack[top] = hi; stack[top - 1] = i; hi = j - 1; }
+            else { stack[top] = j - 1; stack[top - 1] = lo; lo = i; }
+        }
+    }
+#undef EXCH
+}
+
+/* ---- conflict bookkeeping -------------------------------------------------------------------- */
+
+typedef struct {
+    const int64_t *off;       /* member list of group slot g: mem[off[g] .. off[g+1]) */
+    const int32_t *mem;
+    int *slot_of_index;       /* catalog index (1-based) -> slot in kd->grps, -1 if absent */
+} TAGCTX;
+
+/* kdZeroGroup (kd2.c:617-643): every particle still tagged by `small` is untagged and counted */
+static void zero_group(KD kd, const TAGCTX *c, int small, int big)
+{
+    GRPNODE *gs = &kd->grps[small];
+    int64_t k;
+    if (gs->fMvir < 0.0f) {
+        fprintf(stderr, "\nERROR in kdZeroGroup:\nZeroed group mass is already negtive!\n");
+        fprintf(stderr, "  OldGrp: %d  NewGrp: %d  fMvir: %g  Rvir: %g\n", gs->index, kd->grps[big].index,
+                gs->fMvir, gs->fRvir);
+        exit(1);
+    }
+    gs->fRvir = (float)(-10.0 * kd->grps[big].index);
+    gs->fMvir = -gs->fMvir;
+    for (k = c->off[small]; k < c->off[small + 1]; ++k) {
+        int32_t p = c->mem[k];
+        if (kd->p.iGrp[p] == gs->index) {
+            kd->p.iGrp[p] = 0;
+            ++kd->p.nSubsumed[p];
+        }
+    }
+}
+
+/* kdTagParticles (kd2.c:663-720) for group slot `big`, members in ascending (r^2, index) order */
+static void tag_particles(KD kd, const TAGCTX *c, int big)
+{
+    GRPNODE *gb = &kd->grps[big];
+    int64_t k;
+    for (k = c->off[big]; k < c->off[big + 1]; ++k) {
+        int32_t p = c->mem[k];
+        int tag = kd->p.iGrp[p];
+        if (tag == 0) {
+            kd->p.iGrp[p] = gb->index;
+        } else {
+            int small = c->slot_of_index[tag];
+            GRPNODE *gs = &kd->grps[small];
+            float dx = gb->pos[0] - gs->pos[0], dy = gb->pos[1] - gs->pos[1], dz = gb->pos[2] - gs->pos[2];
+            float r2 = dx * dx + dy * dy + dz * dz;       /* plain, non-periodic (kd2.c:677-680) */
+            if (r2 <= gb->fRvir * gb->fRvir) {            /* B's centre inside A: A subsumes B */
+                zero_group(kd, c, small, big);
+                ++kd->iGroupsRemoved;
+                kd->p.iGrp[p] = gb->index;
+            } else if (r2 <= gs->fRvir * gs->fRvir) {     /* A's centre inside B: A is slurped */
+                zero_group(kd, c, big, small);
+                ++kd->iGroupsSlurped;
+                return;                                   /* kd2.c:671: nothing after the slurp */
+            } else {
+                ++kd->p.nIgnored[p];
+            }
+        }
+    }
+}
+
+/* _VcmParticles (kd2.c:595-609): fp32 sums in list order */
+static void vcm_particles(KD kd, const TAGCTX *c, int g, float mass)
+{
+    float v[3] = {0.0f, 0.0f, 0.0f};
+    int64_t k;
+    int l;
+    for (k = c->off[g]; k < c->off[g + 1]; ++k) {
+        int32_t p = c->mem[k];
+        for (l = 0; l < 3; ++l) v[l] += kd->p.fMass[p] * kd->p.v[3 * p + l];
+    }
+    for (l = 0; l < 3; ++l) kd->grps[g].vcm[l] = v[l] / mass;
+}
+
+/* ---- kdVcirc / kdMassProfile (kd2.c:437-586) over one r^2-sorted list -------------------------- */
+
+static void mass_profile(KD kd, GRPNODE *g, float rvir, const int32_t *idx, const float *d2, int64_t n, int ptype)
+{
+    float *out = ptype == DARK ? g->fDark : ptype == GAS ? g->fGas : ptype == STAR ? g->fStar : g->fMark;
+    float fmin = 2.0 / NMASSPROFILE, f, mass = 0.0f;
+    int64_t j = 0;
+    int i;
+    for (f = fmin, i = 0; i < NMASSPROFILE - 1; ++i, f += fmin) {
+        float r = f * rvir, r2 = r * r;
+        while (j < n && d2[j] < r2) {
+            int take = ptype == MARK ? kd->bMarkList[idx[j]] : (kdParticleType(kd, idx[j]) == ptype);
+            if (take) mass += kd->p.fMass[idx[j]];
+            ++j;
+        }
+        out[i] = mass;
+    }
+    for (; j < n; ++j) {
+        int take = ptype == MARK ? kd->bMarkList[idx[j]] : (kdParticleType(kd, idx[j]) == ptype);
+        if (take) mass += kd->p.fMass[idx[j]];
+    }
+    out[NMASSPROFILE - 1] = mass;
+}
+
+static void vcirc(KD kd, GRPNODE *g, float rvir, float mvir, const int32_t *idx, const float *d2, int64_t n)
+{
+    float fmin = 2.0 / NVCIRC, f, mass = 0.0f, fBall = 2. * rvir, m, r, vm, rm, vc;
+    int64_t j = 0;
+    int i;
+    for (f = fmin, i = 0; i < NVCIRC - 1; ++i, f += fmin) {          /* kd2.c:517-526 */
+        float r2;
+        r = f * rvir;
+        r2 = r * r;
+        while (j < n && d2[j] < r2) mass += kd->p.fMass[idx[j++]];
+        g->fVcirc[i] = sqrt(kd->G * mass / r);
+    }
+    for (; j < n; ++j) mass += kd->p.fMass[idx[j]];
+    g->fVcirc[NVCIRC - 1] = sqrt(kd->G * mass / fBall);
+    for (f = 0.25, i = 0; i < 2; ++i, f += 0.25) {                    /* kd2.c:537-546 */
+        m = f * mvir;
+        j = 0;
+        mass = kd->p.fMass[idx[0]];
+        while (mass < m && j + 1 < n) {
+            ++j;
+            mass += kd->p.fMass[idx[j]];
+        }
+        g->fRmass[i] = sqrt(d2[j]);
+    }
+    mass = 0.0f;                                                      /* kd2.c:551-569 */
+    for (j = 0; j < kd->nMembers && j < n; ++j) mass += kd->p.fMass[idx[j]];
+    rm = sqrt(d2[(kd->nMembers <= n ? kd->nMembers : n) - 1]);
+    vm = sqrt(kd->G * mass / rm);
+    for (j = kd->nMembers; j < n; ++j) {
+        mass += kd->p.fMass[idx[j]];
+        r = sqrt(d2[j]);
+        vc = sqrt(kd->G * mass / r);
+        if (vc > vm) {
+            vm = vc;
+            rm = r;
+        }
+    }
+    g->fRmax = rm;
+    g->fVmax = vm;
+    if (kd->bDark) mass_profile(kd, g, rvir, idx, d2, n, DARK);
+    if (kd->bGas) mass_profile(kd, g, rvir, idx, d2, n, GAS);
+    if (kd->bStar) mass_profile(kd, g, rvir, idx, d2, n, STAR);
+    if (kd->bMark) mass_profile(kd, g, rvir, idx, d2, n, MARK);
+}
+
+/* ---- kdSO ----------------------------------------------------------------------------------- */
+
+void kdSO(KD kd, float rhovir, int nSmooth)
+{
+    const int h = kd->nGrps;
+    float *centers, *rgtp, *rvir, *mvir, *masses;
+    int32_t *ndelta, *mem;
+    int64_t *off;
+    int *order, *slot_of_index, *do_vcirc;
+    const int32_t *lib_mem;
+    const float *lib_d2;
+    sogpu_stats_t st;
+    TAGCTX c;
+    double t0 = wall();
+    int i, it;
+    (void)nSmooth;                 /* sized the reference's neighbour list (smInit); nothing to size here */
+    if (h == 0) return;
+    if (kd->bPot) {
+        fprintf(stderr, "ERROR: -pot (centre on the minimum-potential particle, kd2.c:749-761) is not "
+                        "implemented in the GPU build; use -stat.\n");
+        exit(1);
+    }
+    centers = (float *)malloc((size_t)h * 3 * sizeof(float));
+    rgtp = (float *)malloc((size_t)h * sizeof(float));
+    rvir = (float *)malloc((size_t)h * sizeof(float));
+    mvir = (float *)malloc((size_t)h * sizeof(float));
+    masses = (float *)malloc(((size_t)h + 1) * sizeof(float));       /* 1-based for indexx */
+    ndelta = (int32_t *)malloc((size_t)h * sizeof(int32_t));
+    off = (int64_t *)malloc(((size_t)h + 1) * sizeof(int64_t));
+    order = (int *)malloc(((size_t)h + 1) * sizeof(int));            /* 1-based for indexx */
+    do_vcirc = (int *)calloc((size_t)h, sizeof(int));
+    slot_of_index = (int *)malloc(((size_t)kd->nInGTP + 2) * sizeof(int));
+    assert(centers && rgtp && rvir && mvir && masses && ndelta && off && order && do_vcirc && slot_of_index);
+    for (i = 0; i <= kd->nInGTP + 1; ++i) slot_of_index[i] = -1;
+    for (i = 0; i < h; ++i) {
+        memcpy(centers + 3 * i, kd->grps[i].pos, 3 * sizeof(float));
+        rgtp[i] = kd->grps[i].fRgtp;
+        masses[i + 1] = kd->grps[i].fGTPMass;
+        slot_of_index[kd->grps[i].index] = i;
+    }
+
+    /* the hot path: R_Delta, M_Delta, N_Delta and the member lists of every group */
+    if (sogpu_keep_member_d2(kd->gpu, 1)) die_gpu("kdSO");
+    if (sogpu_so(kd->gpu, centers, rgtp, h, rhovir, kd->nMembers, rvir, mvir, ndelta)) die_gpu("kdSO (sogpu_so)");
+    if (sogpu_members(kd->gpu, off, &lib_mem, &lib_d2, 1)) die_gpu("kdSO (sogpu_members)");
+    mem = (int32_t *)malloc((size_t)(off[h] > 0 ? off[h] : 1) * sizeof(int32_t));
+    assert(mem != NULL);
+    memcpy(mem, lib_mem, (size_t)off[h] * sizeof(int32_t));
+    if (sogpu_get_stats(kd->gpu, &st) == 0) {
+        kd->nEvals = st.last_evals;
+        kd->nMembersTotal = st.last_members;
+    }
+
+    /* sequential replay in ascending catalog mass (kd2.c:873-879) */
+    c.off = off; c.mem = mem; c.slot_of_index = slot_of_index;
+    indexx(h, masses, order);
+    for (it = 1; it <= h; ++it) {
+        int g = order[it] - 1;
+        GRPNODE *grp = &kd->grps[g];
+        grp->fRvir = rvir[g];                              /* kd2.c:819-820 or the error code */
+        grp->fMvir = mvir[g];
+        if (rvir[g] > 0.0f) {
+            tag_particles(kd, &c, g);                      /* kd2.c:823 */
+            vcm_particles(kd, &c, g, mvir[g]);             /* kd2.c:826 */
+            if (grp->fRvir > 0.0f) do_vcirc[g] = 1;        /* kd2.c:884: not slurped */
+        }
+    }
+
+    /* kdVcirc for every group that was valid when the reference would have called it */
+    {
+        int nv = 0, k;
+        int *slots = (int *)malloc((size_t)h * sizeof(int));
+        float *vc = (float *)malloc((size_t)h * 3 * sizeof(float));
+        float *vb = (float *)malloc((size_t)h * sizeof(float));
+        int64_t *voff = (int64_t *)malloc(((size_t)h + 1) * sizeof(int64_t));
+        assert(slots && vc && vb && voff);
+        for (i = 0; i < h; ++i)
+            if (do_vcirc[i]) {
+                float fBall = 2. * rvir[i];                /* kd2.c:511-512 */
+                memcpy(vc + 3 * nv, kd->grps[i].pos, 3 * sizeof(float));
+                vb[nv] = fBall * fBall;
+                slots[nv++] = i;
+            }
+        if (nv) {
+            const int32_t *vi;
+            const float *vd;
+            if (sogpu_ball_gather_batch(kd->gpu, vc, vb, nv)) die_gpu("kdSO (sogpu_ball_gather_batch)");
+            if (sogpu_members(kd->gpu, voff, &vi, &vd, 1)) die_gpu("kdSO (2 Rvir lists)");
+            for (k = 0; k < nv; ++k) {
+                int g = slots[k];
+                vcirc(kd, &kd->grps[g], rvir[g], mvir[g], vi + voff[k], vd + voff[k], voff[k + 1] - voff[k]);
+            }
+        }
+        free(slots); free(vc); free(vb); free(voff);
+    }
+    kd->dSOSeconds = wall() - t0;
+    free(centers); free(rgtp); free(rvir); free(mvir); free(masses); free(ndelta); free(off); free(order);
+    free(do_vcirc); free(slot_of_index); free(mem);
+}
+
+void kdFinish(KD kd)
+{
+    if (!kd) return;
+    if (kd->gpu) sogpu_destroy(kd->gpu);
+    free(kd->p.r); free(kd->p.v); free(kd->p.fMass); free(kd->p.fPhi);
+    free(kd->p.iGrp); free(kd->p.nSubsumed); free(kd->p.nIgnored);
+    free(kd->grps);
+    free(kd->bMarkList);
+    free(kd);
+}

@@ -81,7 +81,9 @@ def run_case(name, case, tmp):
         off[i + 1] = off[i] + ndelta[i]
     # fThreshold exactly as so.c:319,480: (float)atof(delta) then *= fOmega (float)
     thr = np.float32(np.float32(case["delta"]) * np.float32(s.omega0))
+    rows_full = np.array(rows, dtype=np.float64)          # all 15 columns of every .sovcirc row
     rows = np.array([row[:3] for row in rows], dtype=np.float64)
+    sogtp_bytes = np.frombuffer(open(out + ".sogtp", "rb").read(), np.uint8)
     np.savez_compressed(
         os.path.join(HERE, name + ".npz"),
         gen=repr(case["gen"]), pos_sha1=hashlib.sha1(s.pos.tobytes()).hexdigest(), mass=s.mass,
@@ -89,7 +91,7 @@ def run_case(name, case, tmp):
         delta=np.float64(case["delta"]),
         rvir=star["eps"].astype(np.float32), mvir_sogtp=star["mass"].astype(np.float32),
         vcm=star["vel"].astype(np.float32),
-        sovcirc_idx_m_r=rows, ndelta=ndelta, member_offset=off,
+        sovcirc_idx_m_r=rows, sovcirc_rows=rows_full, sogtp_bytes=sogtp_bytes, ndelta=ndelta, member_offset=off,
         members=np.concatenate(mem) if mem else np.zeros(0, np.int32),
         members_d2=np.concatenate(md2) if md2 else np.zeros(0, np.float32),
         igrp=igrp.astype(np.int32), groups_removed=np.int32(removed), groups_slurped=np.int32(slurped),

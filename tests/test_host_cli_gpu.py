@@ -1,0 +1,107 @@
+"""The drop-in `so` program (so_b200/host/so: host C + C-ABI + CUDA) against the reference
+program's own output files: .sogtp bytes, .sogrp text, .sovcirc rows."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from so_b200 import synth, tipsy
+from tests.util import load_golden
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "so_b200", "host", "so")
+
+
+def run_so(tmp, s, centers, rgtp, gmass, extra):
+    snap, gtp, out = (os.path.join(tmp, n) for n in ("s.tipsy", "h.gtp", "ours"))
+    tipsy.write_tipsy(snap, s.time, dark=tipsy.dark_from_arrays(s.pos, s.mass))
+    tipsy.write_gtp(gtp, s.time, centers, rgtp, gmass)
+    assert os.path.exists(SO), "build the host program: make -C so_b200/host"
+    with open(snap, "rb") as fin:
+        r = subprocess.run([SO, "-i", gtp, "-o", out] + list(extra), stdin=fin, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return snap, gtp, out, r.stderr
+
+
+def compare_rows(ours, ref_rows):
+    """ours: parsed rows; ref_rows: array.  Error / subsumed rows: only index, Mvir, Rvir are defined
+    in the reference (the rest is uninitialised heap there)."""
+    assert len(ours) == len(ref_rows)
+    for a, b in zip(ours, ref_rows):
+        a = np.array(a)
+        if b[2] in (-1.0, -2.0, -3.0):
+            assert np.array_equal(a[:3], b[:3])
+        else:
+            assert np.array_equal(a, b), (a, b)
+
+
+@pytest.mark.parametrize("name", ["basic", "conflict", "errors", "members4", "omega03"])
+def test_cli_matches_golden_reference_files(tmp_path, name):
+    s, g = load_golden(name)
+    extra = ["-delta", repr(float(g["delta"])), "-grp", "-gtp", "-O", repr(float(g["omega0"]))]
+    if int(g["n_members"]) != 8:
+        extra += ["-m", str(int(g["n_members"]))]
+    _, _, out, err = run_so(str(tmp_path), s, g["centers"], g["rgtp"], g["gtp_mass"], extra)
+    assert np.array_equal(tipsy.read_sogrp(out + ".sogrp"), g["igrp"])
+    hdr, rows = tipsy.parse_sovcirc(out + ".sovcirc")
+    compare_rows(rows, g["sovcirc_rows"])
+    assert any("Groups subsumed into larger groups (cumulative):  %d" % int(g["groups_removed"]) in l for l in hdr)
+    assert any("Groups 'slurped' into larger groups (cumulative): %d" % int(g["groups_slurped"]) in l for l in hdr)
+    ours = np.frombuffer(open(out + ".sogtp", "rb").read(), np.uint8)
+    ref = g["sogtp_bytes"]
+    assert len(ours) == len(ref)
+    assert np.array_equal(ours[:28], ref[:28])                       # 28..31: uninitialised pad in the reference
+    a = ours[32:].view(np.float32).reshape(-1, 11)
+    b = ref[32:].view(np.float32).reshape(-1, 11)
+    okrow = b[:, 9] > 0                                              # eps = Rvir > 0: fully defined rows
+    assert a[:, [0, 1, 2, 3, 8, 9]].tobytes() == b[:, [0, 1, 2, 3, 8, 9]].tobytes()   # mass, pos, tform, eps
+    np.testing.assert_allclose(a[okrow, 4:7], b[okrow, 4:7], rtol=1e-6, atol=0)       # vcm (tolerance: SURVEY a16)
+    assert "SO CPU Time:" in err
+
+
+@pytest.mark.skipif(not po.ref_available("so_ref"), reason="reference binary not built")
+@pytest.mark.parametrize("std", [False, True])
+def test_cli_matches_reference_binary_live(tmp_path, std):
+    """Fresh seed, reference run side by side (native and -std XDR files, -list, -M, -subsumed/-ignored)."""
+    s = synth.make_snapshot(40 ** 3, 30, seed=77, nmax=4000, overlap_pairs=5)
+    snap, gtp = str(tmp_path / "s.tipsy"), str(tmp_path / "h.gtp")
+    rng = np.random.default_rng(1)
+    vel = rng.normal(size=(s.n, 3)).astype(np.float32)
+    tipsy.write_tipsy(snap, s.time, dark=tipsy.dark_from_arrays(s.pos, s.mass, vel=vel), standard=std)
+    tipsy.write_gtp(gtp, s.time, s.centers, s.rgtp, s.gtp_mass, standard=std)
+    lst = str(tmp_path / "list.txt")
+    keep = np.arange(1, s.h + 1)[::-1][:25]                          # a subset, in descending id order
+    np.savetxt(lst, np.sort(keep), fmt="%d")
+    flags = ["-delta", "200", "-grp", "-gtp", "-subsumed", "-ignored", "-list", lst, "-M", "1e-7", "-all"]
+    if std:
+        flags.append("-std")
+    outs = {}
+    for who, exe in (("ref", os.path.join(po.REF_DIR, "so_ref")), ("ours", SO)):
+        out = str(tmp_path / who)
+        with open(snap, "rb") as fin:
+            r = subprocess.run([exe, "-i", gtp, "-o", out] + flags, stdin=fin, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[who] = out
+    for ext in (".sogrp", ".sosub", ".soign"):
+        assert open(outs["ours"] + ext).read() == open(outs["ref"] + ext).read(), ext
+    _, ra = tipsy.parse_sovcirc(outs["ours"] + ".sovcirc")
+    _, rb = tipsy.parse_sovcirc(outs["ref"] + ".sovcirc")
+    compare_rows(ra, np.array(rb))
+    _, pa = tipsy.parse_sovcirc(outs["ours"] + ".sodark")
+    _, pb = tipsy.parse_sovcirc(outs["ref"] + ".sodark")
+    for a, b in zip(pa, pb):
+        if rb[pb.index(b)][2] > 0:
+            assert a == b
+    a = np.frombuffer(open(outs["ours"] + ".sogtp", "rb").read(), np.uint8)
+    b = np.frombuffer(open(outs["ref"] + ".sogtp", "rb").read(), np.uint8)
+    assert len(a) == len(b) and np.array_equal(a[:28], b[:28])
+    dt = ">f4" if std else "<f4"
+    fa = a[32:].view(dt).reshape(-1, 11).astype(np.float32)
+    fb = b[32:].view(dt).reshape(-1, 11).astype(np.float32)
+    assert fa[:, [0, 1, 2, 3, 8, 9]].tobytes() == fb[:, [0, 1, 2, 3, 8, 9]].tobytes()
+    okrow = fb[:, 9] > 0
+    np.testing.assert_allclose(fa[okrow, 4:7], fb[okrow, 4:7], rtol=2e-5, atol=1e-7)
