@@ -301,18 +301,32 @@ def run_ours(args):
     res_m = d_out_m[:h_mine].cpu().numpy()
 
     # ---- e2e: host buffers in, host results out, every step ----------------------------------
+    e2e_parts = {"upload_ms": 0.0, "build_so_ms": 0.0, "members_ms": 0.0}
+
     def step_e2e():
+        ta = time.perf_counter()
         upload_and_replicate()
+        tb = time.perf_counter()
         g.build_grid()
+        out = None
         if h_mine:
             r = g.so(centers[mine], rgtp[mine], thr, NMEM)
+            tc = time.perf_counter()
             off, mem = g.members(copy=False)
-            return r, off, mem
-        return None
+            out = (r, off, mem)
+        else:
+            tc = time.perf_counter()
+        td = time.perf_counter()
+        e2e_parts["upload_ms"] += (tb - ta) * 1e3
+        e2e_parts["build_so_ms"] += (tc - tb) * 1e3
+        e2e_parts["members_ms"] += (td - tc) * 1e3
+        return out
 
     for _ in range(2):
         step_e2e()
     barrier()
+    for k in e2e_parts:
+        e2e_parts[k] = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
         out = step_e2e()
@@ -324,7 +338,7 @@ def run_ours(args):
     e2e_s = float(t.item())
     clocks = sampler.stop()
     n_members_mine = int(out[1][-1]) if out else 0
-    h2d = (16 * n if rank == 0 else 0) + 16 * h_mine
+    h2d = (12 * n if rank == 0 else 0) + 16 * h_mine   # xyz triplets (+1 shared mass), centres + rgtp
     d2h = 8 * h_mine + 8 * (h_mine + 1) + 4 * n_members_mine
     io = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -386,7 +400,8 @@ def run_ours(args):
         "evals_per_s": evals_total / (ms_step * 1e-3), "evals_per_step": evals_total,
         "members_per_step": members_total, "halos_resolved_rank0": ok,
         "e2e": {"value": h_total / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
-                "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item())},
+                "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
+                "rank0_breakdown_ms": {k: v / args.steps for k, v in e2e_parts.items()}},
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
         "gpu_launches": launches, "clocks": clocks,
     }
@@ -396,6 +411,35 @@ def run_ours(args):
     return 0
 
 
-if __name__ == "__main__":
+def main():
     a = parse()
-    sys.exit(run_reference(a) if a.impl == "reference" else run_ours(a))
+    # exactly ONE line on stdout: anything a library prints there (e.g. NCCL's version banner)
+    # is diverted to stderr while the benchmark runs
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    buf = []
+    import builtins
+    real_print = builtins.print
+
+    def capture(*args, **kw):
+        if kw.get("file") in (None, sys.stdout):
+            buf.append(" ".join(str(x) for x in args))
+        else:
+            real_print(*args, **kw)
+    builtins.print = capture
+    try:
+        rc = run_reference(a) if a.impl == "reference" else run_ours(a)
+    finally:
+        builtins.print = real_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in buf:
+        print(line)
+    sys.stdout.flush()
+    return rc
+
+
+if __name__ == "__main__":
+    sys.exit(main())

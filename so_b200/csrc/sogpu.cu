@@ -395,6 +395,17 @@ __global__ void __launch_bounds__(256) k_fine_scatter(const float4 *__restrict__
     }
 }
 
+/* K1 (pack): raw host layout -> float4 {x,y,z,m} on the device (xyz triplets + one shared mass) */
+__global__ void __launch_bounds__(256) k_expand_xyz(const float *__restrict__ xyz, float m, float4 *__restrict__ dst,
+                                                    int64_t n)
+{
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float *p = xyz + 3 * i;
+        dst[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), m);
+    }
+}
+
 /* ============================================================================================
  * group (warp or block) primitives
  * ============================================================================================ */
@@ -1289,6 +1300,7 @@ struct sogpu {
     uint32_t *d_ce;
     uint32_t *d_bsum;
     uint32_t *d_massmm;
+    float *d_raw;                    /* staging of raw xyz triplets (pinned-host fast path) */
     uint32_t *d_coarse;              /* PART_BMAX bucket cursors */
     float4 *d_tmp4;                  /* partitioned particles / keys / original indices */
     uint32_t *d_tmpk;
@@ -1446,6 +1458,7 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     free_query(h);
     cudaFree(h->d_in_owned);
     cudaFree(h->d_massmm);
+    cudaFree(h->d_raw);
     cudaFree(h->d_coarse);
     cudaFree(h->d_tmp4); cudaFree(h->d_tmpk); cudaFree(h->d_tmpi);
     cudaFree(h->d_mt);
@@ -1522,6 +1535,30 @@ static void pack_range(float4 *dst, const char *pp, size_t ps, const char *mp, s
 static int upload_to(sogpu *h, float4 *d_dst, const void *pos, size_t pos_stride, const void *mass,
                      size_t mass_stride, int64_t n)
 {
+    /* fast paths for page-locked caller memory: DMA straight from it, unpack on the device */
+    cudaPointerAttributes pa;
+    bool pinned = cudaPointerGetAttributes(&pa, pos) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned && pos_stride == sizeof(float4) && mass_stride == sizeof(float4) &&
+        (const char *)mass == (const char *)pos + 3 * sizeof(float)) {
+        CU(cudaMemcpyAsync(d_dst, pos, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return SOGPU_OK;
+    }
+    if (pinned && pos_stride == 3 * sizeof(float) && mass_stride == 0) {
+        const int64_t rchunk = 1 << 23;   /* 96 MB of xyz per piece */
+        if (!h->d_raw) CU(cudaMalloc(&h->d_raw, (size_t)rchunk * 3 * sizeof(float)));
+        const float m = *(const float *)mass;
+        for (int64_t i0 = 0; i0 < n; i0 += rchunk) {
+            int64_t k = std::min(rchunk, n - i0);
+            CU(cudaMemcpyAsync(h->d_raw, (const float *)pos + 3 * i0, (size_t)k * 3 * sizeof(float),
+                               cudaMemcpyHostToDevice, h->stream));
+            k_expand_xyz<<<h->sm_count * 8, 256, 0, h->stream>>>(h->d_raw, m, d_dst + i0, k);
+        }
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));
+        return SOGPU_OK;
+    }
     const int64_t chunk = 1 << 22;
     int rc = ensure_pinned(h, 2 * (size_t)chunk * sizeof(float4));
     if (rc) return rc;

@@ -176,6 +176,30 @@ def test_records_layout_and_tiny_inputs():
     g.close()
 
 
+def test_pinned_host_memory_fast_paths():
+    """Page-locked caller memory is DMA'd directly (xyz triplets / float4) and unpacked on the GPU."""
+    import torch
+    s = synth.make_snapshot(30 ** 3, 10, seed=43, nmax=1500)
+    ref = po.Oracle(s.pos, s.mass).so(s.centers, s.rgtp, np.float32(200.0), 8)
+    pin3 = torch.from_numpy(s.pos).pin_memory()
+    xyzm = np.concatenate([s.pos, np.full((s.n, 1), s.mass, np.float32)], axis=1)
+    pin4 = torch.from_numpy(xyzm).pin_memory()
+    for which in ("xyz", "xyzm"):
+        g = api.SoGpu()
+        if which == "xyz":
+            g.set_particles(pin3.numpy(), s.mass)
+        else:
+            a = pin4.numpy()
+            g.set_particles(a[:, :3], a[:, 3])
+        g.build_grid()
+        g.keep_member_d2(True)
+        r = g.so(s.centers, s.rgtp, 200.0)
+        off, mem = g.members(sorted=True)
+        assert_so_equal(r, ref["rvir"], ref["mvir"], ref["ndelta"])
+        assert np.array_equal(mem, ref["members"])
+        g.close()
+
+
 def test_ball_gather_matches_oracle_ball():
     """smBallGather + qsort replacement (smooth2.c:58-114, kd2.c:781)."""
     s = synth.make_snapshot(40 ** 3, 10, seed=39, nmax=4000)
