@@ -180,12 +180,9 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-ALG_BYTES = {  # algorithmic bytes per unit of each kernel
-    "k_cell_count": ("particle", 16.0), "k_scatter": ("particle", 36.0),
-    "k_scan(3 launches)": ("cell", 12.0), "k_so_query<32>": ("eval", 16.0),
-    "k_so_query<256>": ("eval", 16.0), "k_so_emit<32>": ("member", 20.0), "k_so_emit<256>": ("member", 20.0),
-    "k_coarse_hist": ("particle", 16.0), "k_partition": ("particle", 40.0), "k_fine_count": ("particle", 4.0),
-    "k_fine_scatter": ("particle", 44.0),
+ALG_BYTES = {  # algorithmic bytes per unit for the kernels whose unit count is only known after the run
+    "k_so_query<32>": ("eval", 16.0), "k_so_query<256>": ("eval", 16.0),
+    "k_so_emit<32>": ("member", 20.0), "k_so_emit<256>": ("member", 20.0),
 }
 
 
@@ -359,15 +356,20 @@ def run_ours(args):
              "eval": float(st["last_evals"]), "member": float(st["last_members"])}
     total_ms = sum(v[0] for v in prof.values())
     kernels = {}
-    for kname, (kms, launches) in prof.items():
+    for kname, (kms, launches, kbytes) in prof.items():
         if launches == 0:
             continue
         per = kms / args.steps
         ent = {"ms_per_step": per, "share": kms / total_ms if total_ms else 0.0,
                "launches_per_step": launches / args.steps}
-        if kname in ALG_BYTES:
+        if kbytes > 0:                      # grid build: bytes known at launch (library-side table)
+            ent["alg_bytes"] = kbytes / args.steps
+        elif kname in ALG_BYTES:            # query / emit: 16 B per r^2 evaluation, 20 B per member
             unit, b = ALG_BYTES[kname]
             ent["alg_bytes"] = b * units[unit]
+            if unit == "eval":
+                ent["note"] = "evaluations are shared between the warp and the block kernel"
+        if "alg_bytes" in ent:
             ent["gbs"] = ent["alg_bytes"] / (per * 1e-3) / 1e9 if per > 0 else 0.0
         kernels[kname] = ent
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
@@ -376,6 +378,13 @@ def run_ours(args):
                 "frac": (dk.get("gbs") or 0.0) / peak, "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_launch": dk.get("alg_bytes"), "share_of_step": dk["share"]}
     launches = int(round(sum(v[1] for v in prof.values()) / args.steps))
+    # the two query kernels share one evaluation counter: split it by their time share
+    qk = [k for k in ("k_so_query<32>", "k_so_query<256>") if k in kernels]
+    if len(qk) == 2:
+        tq = sum(kernels[k]["ms_per_step"] for k in qk)
+        for k in qk:
+            kernels[k]["gbs"] = 16.0 * units["eval"] / (tq * 1e-3) / 1e9
+            kernels[k]["alg_bytes"] = 16.0 * units["eval"] * kernels[k]["ms_per_step"] / tq
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

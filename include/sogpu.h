@@ -50,8 +50,8 @@ const char *sogpu_last_error(void);
 /* All work of this handle is enqueued on `cuda_stream` (a cudaStream_t cast to void*;
  * NULL = the handle's own stream).  Lets a caller time the kernels with its own events. */
 int sogpu_set_stream(sogpu_t *h, void *cuda_stream);
-/* Tuning knob: grid build strategy. -1 auto (default), 0 single counting sort, 1 coarse MSD
- * partition first (keeps the scatter inside an L2-resident window; wins for N >~ 10^5). */
+/* Tuning knob: grid build strategy. -1 auto (default: MSD partition levels, then a shared-memory
+ * bucket sort); 0 = no partition levels (one bucket holds everything; slow path for N > 3072). */
 int sogpu_set_build_mode(sogpu_t *h, int mode);
 /* Tuning knob: target mean particles per grid cell (default 2.0). */
 int sogpu_set_cell_occupancy(sogpu_t *h, float particles_per_cell);
@@ -150,6 +150,8 @@ const char *sogpu_profile_name(int kernel_id);
 /* Accumulated milliseconds and launch counts per kernel slot since the last reset
  * (synchronises the stream). */
 int sogpu_profile_read(sogpu_t *h, double *ms, int64_t *launches, int n_slots, int reset);
+/* Algorithmic bytes per slot for the kernels whose traffic is known at launch (grid build). */
+int sogpu_profile_bytes(sogpu_t *h, double *bytes, int n_slots, int reset);
 
 /* ---- host-side helpers of the exact-arithmetic contract (no GPU needed; unit-tested) -------- */
 

@@ -27,6 +27,7 @@ SYMBOLS = [
     "sogpu_finish_host", "sogpu_keep_member_d2", "sogpu_profile_enable", "sogpu_profile_kernels",
     "sogpu_profile_name", "sogpu_profile_read", "sogpu_upload_particles",
     "sogpu_set_build_mode", "sogpu_ball_gather_batch",
+    "sogpu_profile_bytes",
 ]
 
 
@@ -80,6 +81,8 @@ def lib():
     L.sogpu_profile_name.restype = C.c_char_p
     L.sogpu_profile_name.argtypes = [C.c_int]
     L.sogpu_profile_read.argtypes = [vp, C.POINTER(C.c_double), i64p, C.c_int, C.c_int]
+    L.sogpu_profile_bytes.argtypes = [vp, C.POINTER(C.c_double), C.c_int, C.c_int]
+    L.sogpu_profile_bytes.restype = C.c_int
     L.sogpu_ball_gather.argtypes = [vp, fp, C.c_float, i32p, fp, C.c_int64, i64p]
     L.sogpu_ball_gather_batch.argtypes = [vp, fp, fp, C.c_int32]
     L.sogpu_ball_gather_batch.restype = C.c_int
@@ -282,8 +285,10 @@ class SoGpu:
         nk = lib().sogpu_profile_kernels()
         ms = (C.c_double * nk)()
         ln = (C.c_int64 * nk)()
+        by = (C.c_double * nk)()
         _check(lib().sogpu_profile_read(self._h, ms, ln, nk, 1 if reset else 0))
-        return {lib().sogpu_profile_name(k).decode(): (ms[k], ln[k]) for k in range(nk)}
+        _check(lib().sogpu_profile_bytes(self._h, by, nk, 1 if reset else 0))
+        return {lib().sogpu_profile_name(k).decode(): (ms[k], ln[k], by[k]) for k in range(nk)}
 
     def ball_gather(self, center, ball2, cap=None):
         c = np.asarray(center, np.float32).copy()

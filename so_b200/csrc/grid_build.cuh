@@ -1,0 +1,364 @@
+/* grid_build.cuh — kdBuildTree replacement (kd2.c:1096-1185): particles -> periodic cell grid.
+ *
+ * The reference permutes its 60-byte PINIT records with a recursive quickselect (kdSelectInit,
+ * kd2.c:1013-1041) until every kd bucket holds <= 16 particles.  Here the particles are sorted by
+ * cell key — (zorder2(iy,iz) << lb) | ix — with an MSD radix scheme whose every global store is a
+ * coalesced run, because scattered 16-byte stores are bound by L2 transaction rate, not by HBM:
+ *
+ *   level l = 0..L-1 :  k_lvl_hist       digit histogram per parent bucket (smem atomics)
+ *                       k_scan_*         exclusive scan -> child bucket starts
+ *                       k_lvl_partition  tile-wise counting sort by digit in shared memory, one
+ *                                        global atomic per (tile, child), run writes
+ *   final            :  k_bucket_sort    one CTA per final bucket (~1 K particles, <= 4096 cells):
+ *                                        counting sort by cell entirely in shared memory, coalesced
+ *                                        copy out, writes the bucket's slice of the cell table
+ *
+ * Payload is one float4 per particle: {x, y, z, original index (as int bits)}; masses stay in the
+ * caller's array (all equal on the fast path; gathered by index on the general path).
+ * Algorithmic bytes per particle: level 0: 16 (hist) + 36 (partition, key written unless last);
+ * further levels 4 + 36; final 16 + 16; total 124 B for two levels.
+ */
+#pragma once
+
+#define SCAN_TILE 2048   /* 256 threads x 8 */
+
+__global__ void __launch_bounds__(256) k_scan_reduce(const uint32_t *__restrict__ a, int64_t n,
+                                                     uint32_t *__restrict__ bsum)
+{
+    __shared__ uint32_t ws[8];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    uint32_t s = 0;
+    for (int k = 0; k < 8; ++k) {
+        int64_t i = base + k * 256 + threadIdx.x;
+        if (i < n) s += a[i];
+    }
+    s = __reduce_add_sync(0xFFFFFFFFu, s);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int k = 0; k < 8; ++k) t += ws[k];
+        bsum[blockIdx.x] = t;
+    }
+}
+
+/* exclusive scan of bsum[0..nb) by one block */
+__global__ void __launch_bounds__(1024) k_scan_bsums(uint32_t *__restrict__ bsum, int64_t nb)
+{
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int64_t b0 = 0; b0 < nb; b0 += 1024) {
+        int64_t i = b0 + threadIdx.x;
+        uint32_t v = (i < nb) ? bsum[i] : 0u, x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += t;
+        }
+        if (lane == 31) ws[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t y = ws[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, y, o);
+                if (lane >= o) y += t;
+            }
+            ws[lane] = y;
+        }
+        __syncthreads();
+        uint32_t incl = x + (w ? ws[w - 1] : 0u) + carry;
+        if (i < nb) bsum[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = incl;
+        __syncthreads();
+    }
+}
+
+/* exclusive scan of each tile plus its block offset: out[i] = sum a[0..i); out may alias a.
+ * If `copy` is given it receives the same values (the atomic cursors of the partition pass). */
+__global__ void __launch_bounds__(256) k_scan_apply(const uint32_t *a, int64_t n, const uint32_t *__restrict__ bsum,
+                                                    uint32_t *out, uint32_t *copy, uint32_t total_slot_value)
+{
+    __shared__ uint32_t ws[8];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * 8;
+    uint32_t v[8], s = 0;
+    for (int k = 0; k < 8; ++k) {
+        v[k] = (base + k < n) ? a[base + k] : 0u;
+        s += v[k];
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t x = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += t;
+    }
+    if (lane == 31) ws[w] = x;
+    __syncthreads();
+    uint32_t off = bsum[blockIdx.x];
+    for (int k = 0; k < w; ++k) off += ws[k];
+    uint32_t run = off + x - s;
+    for (int k = 0; k < 8; ++k) {
+        if (base + k < n) {
+            out[base + k] = run;
+            if (copy) copy[base + k] = run;
+        }
+        run += v[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = total_slot_value;   /* sentinel: array end */
+}
+
+/* ---- level kernels ---------------------------------------------------------------------------- */
+
+#define LVL_T 4096           /* particles per tile */
+#define LVL_CMAX 512         /* children per parent (digit of up to 9 bits) */
+
+struct LevelDesc {
+    int shift;               /* digit  = (key >> shift) & (C-1)                     */
+    int db;                  /* log2 C                                              */
+    int pshift;              /* parent = key >> pshift   (pshift >= 32: parent 0)   */
+    uint32_t n_parents;
+};
+
+/* last parent p with pstart[p] <= pos (empty parents share their start with the next one) */
+__device__ __forceinline__ uint32_t find_parent(const uint32_t *__restrict__ pstart, uint32_t n_parents, uint32_t pos)
+{
+    uint32_t lo = 0, hi = n_parents - 1;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (__ldg(pstart + mid) <= pos) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+/* digit histogram of every parent bucket; level 0 computes keys from positions (and mass min/max) */
+template <bool FIRST>
+__global__ void __launch_bounds__(256) k_lvl_hist(const float4 *__restrict__ in4, const uint32_t *__restrict__ inkey,
+                                                  int64_t n, GridDev g, LevelDesc lv,
+                                                  const uint32_t *__restrict__ pstart, uint32_t *__restrict__ counts,
+                                                  uint32_t *__restrict__ mass_minmax)
+{
+    __shared__ uint32_t sh[LVL_CMAX];
+    const int C = 1 << lv.db;
+    const uint32_t cmask = (uint32_t)C - 1u;
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    const int64_t ntiles = (n + LVL_T - 1) / LVL_T;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint32_t pos = (uint32_t)(tile * LVL_T);
+        const uint32_t tend = (uint32_t)min((int64_t)n, tile * LVL_T + LVL_T);
+        while (pos < tend) {
+            uint32_t p = FIRST ? 0u : find_parent(pstart, lv.n_parents, pos);
+            uint32_t send = FIRST ? tend : min(tend, __ldg(pstart + p + 1));
+            for (int c = threadIdx.x; c < C; c += 256) sh[c] = 0u;
+            __syncthreads();
+            for (uint32_t i = pos + threadIdx.x; i < send; i += 256) {
+                uint32_t key;
+                if (FIRST) {
+                    float4 q = ld_stream(in4 + i);
+                    key = cell_key(q, g);
+                    uint32_t mo = (q.w >= 0.0f) ? __float_as_uint(q.w) : 0xFFFFFFFEu;
+                    if (!(q.w >= 0.0f)) mn = 0u;     /* negative / NaN mass: treated as "unequal" */
+                    mn = min(mn, mo);
+                    mx = max(mx, mo);
+                } else {
+                    key = __ldg(inkey + i);
+                }
+                atomicAdd(&sh[(key >> lv.shift) & cmask], 1u);
+            }
+            __syncthreads();
+            for (int c = threadIdx.x; c < C; c += 256)
+                if (sh[c]) atomicAdd(&counts[(size_t)p * C + c], sh[c]);
+            __syncthreads();
+            pos = send;
+        }
+    }
+    if (FIRST) {
+        mn = __reduce_min_sync(0xFFFFFFFFu, mn);
+        mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&mass_minmax[0], mn);
+            atomicMax(&mass_minmax[1], mx);
+        }
+    }
+}
+
+/* tile-wise counting sort by digit, staged through shared memory so that each child bucket
+ * receives one contiguous run per tile segment */
+template <bool FIRST, bool WRITE_KEY>
+__global__ void __launch_bounds__(256) k_lvl_partition(const float4 *__restrict__ in4, const uint32_t *__restrict__ inkey,
+                                                       int64_t n, GridDev g, LevelDesc lv,
+                                                       const uint32_t *__restrict__ pstart, uint32_t *__restrict__ cursor,
+                                                       float4 *__restrict__ out4, uint32_t *__restrict__ outkey)
+{
+    extern __shared__ __align__(16) unsigned char raw[];
+    float4 *s4 = reinterpret_cast<float4 *>(raw);
+    uint32_t *sk = reinterpret_cast<uint32_t *>(s4 + LVL_T);
+    uint16_t *sd = reinterpret_cast<uint16_t *>(sk + LVL_T);
+    uint16_t *sr = sd + LVL_T;
+    uint16_t *perm = sr + LVL_T;
+    __shared__ uint32_t scnt[LVL_CMAX], soff[LVL_CMAX], sbase[LVL_CMAX], ws[8];
+    const int C = 1 << lv.db;
+    const uint32_t cmask = (uint32_t)C - 1u;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int64_t ntiles = (n + LVL_T - 1) / LVL_T;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint32_t pos = (uint32_t)(tile * LVL_T);
+        const uint32_t tend = (uint32_t)min((int64_t)n, tile * LVL_T + LVL_T);
+        while (pos < tend) {
+            const uint32_t p = FIRST ? 0u : find_parent(pstart, lv.n_parents, pos);
+            const uint32_t send = FIRST ? tend : min(tend, __ldg(pstart + p + 1));
+            const int cnt = (int)(send - pos);
+            for (int c = t; c < C; c += 256) scnt[c] = 0u;
+            __syncthreads();
+#pragma unroll 4
+            for (int i = t; i < cnt; i += 256) {
+                float4 q = ld_stream(in4 + pos + i);
+                uint32_t key;
+                if (FIRST) {
+                    key = cell_key(q, g);
+                    q.w = __int_as_float((int)(pos + i));      /* payload: original index */
+                } else {
+                    key = __ldg(inkey + pos + i);
+                }
+                uint32_t d = (key >> lv.shift) & cmask;
+                s4[i] = q;
+                sk[i] = key;
+                sd[i] = (uint16_t)d;
+                sr[i] = (uint16_t)atomicAdd(&scnt[d], 1u);
+            }
+            __syncthreads();
+            {   /* exclusive scan of the C counts (C <= 512: two per thread) + run reservation */
+                uint32_t c0 = (2 * t < C) ? scnt[2 * t] : 0u, c1 = (2 * t + 1 < C) ? scnt[2 * t + 1] : 0u;
+                uint32_t x = c0 + c1;
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t u = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                    if (lane >= o) x += u;
+                }
+                if (lane == 31) ws[w] = x;
+                __syncthreads();
+                uint32_t off = 0;
+                for (int k = 0; k < w; ++k) off += ws[k];
+                uint32_t e0 = off + x - c0 - c1;
+                if (2 * t < C) {
+                    soff[2 * t] = e0;
+                    sbase[2 * t] = c0 ? atomicAdd(&cursor[(size_t)p * C + 2 * t], c0) : 0u;
+                }
+                if (2 * t + 1 < C) {
+                    soff[2 * t + 1] = e0 + c0;
+                    sbase[2 * t + 1] = c1 ? atomicAdd(&cursor[(size_t)p * C + 2 * t + 1], c1) : 0u;
+                }
+            }
+            __syncthreads();
+            for (int i = t; i < cnt; i += 256) perm[soff[sd[i]] + sr[i]] = (uint16_t)i;
+            __syncthreads();
+            for (int slot = t; slot < cnt; slot += 256) {
+                int i = perm[slot];
+                uint32_t d = sd[i];
+                uint32_t dst = sbase[d] + ((uint32_t)slot - soff[d]);
+                out4[dst] = s4[i];
+                if (WRITE_KEY) outkey[dst] = sk[i];
+            }
+            __syncthreads();
+            pos = send;
+        }
+    }
+}
+
+/* ---- final: one CTA per bucket, counting sort by cell in shared memory ---------------------------- */
+
+#define BKT_CAP 3072         /* particles staged in shared memory; larger buckets take the slow path */
+#define BKT_CELLS 4096       /* cells per final bucket (<=)                                          */
+#define BKT_THREADS 256
+
+__global__ void __launch_bounds__(BKT_THREADS) k_bucket_sort(const float4 *__restrict__ in4, GridDev g, int cell_bits,
+                                                             uint32_t n_buckets, const uint32_t *__restrict__ bstart,
+                                                             float4 *__restrict__ sorted, uint32_t *__restrict__ ce,
+                                                             int first_pass_input_is_raw)
+{
+    extern __shared__ __align__(16) unsigned char raw[];
+    float4 *s4 = reinterpret_cast<float4 *>(raw);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(s4 + BKT_CAP);
+    uint16_t *sc = reinterpret_cast<uint16_t *>(cnt + BKT_CELLS);
+    uint16_t *sr = sc + BKT_CAP;
+    uint16_t *perm = sr + BKT_CAP;
+    __shared__ uint32_t ws[BKT_THREADS / 32];
+    const int ncells = 1 << cell_bits;
+    const uint32_t cmask = (uint32_t)ncells - 1u;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int per = (ncells + BKT_THREADS - 1) / BKT_THREADS;      /* cells per thread in the scan */
+    for (uint32_t b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+        const uint32_t b0 = __ldg(bstart + b), b1 = __ldg(bstart + b + 1);
+        const uint32_t nb = b1 - b0;
+        const bool staged = nb <= BKT_CAP;
+        for (int c = t; c < ncells; c += BKT_THREADS) cnt[c] = 0u;
+        __syncthreads();
+        /* count (and stage): all loads of a staged bucket are issued before the first use */
+        if (staged) {
+            constexpr int IT = BKT_CAP / BKT_THREADS;
+            float4 q[IT];
+#pragma unroll
+            for (int k = 0; k < IT; ++k) {
+                uint32_t i = t + k * BKT_THREADS;
+                if (i < nb) q[k] = ld_stream(in4 + b0 + i);
+            }
+#pragma unroll
+            for (int k = 0; k < IT; ++k) {
+                uint32_t i = t + k * BKT_THREADS;
+                if (i < nb) {
+                    if (first_pass_input_is_raw) q[k].w = __int_as_float((int)(b0 + i));
+                    uint32_t c = cell_key(q[k], g) & cmask;
+                    s4[i] = q[k];
+                    sc[i] = (uint16_t)c;
+                    sr[i] = (uint16_t)atomicAdd(&cnt[c], 1u);
+                }
+            }
+        } else {
+            for (uint32_t i = t; i < nb; i += BKT_THREADS) {
+                float4 q = ld_stream(in4 + b0 + i);
+                atomicAdd(&cnt[cell_key(q, g) & cmask], 1u);
+            }
+        }
+        __syncthreads();
+        /* exclusive scan of the cell counts (in place) and the bucket's slice of the cell table */
+        {
+            uint32_t s = 0;
+            const int c0 = t * per;
+            for (int k = 0; k < per; ++k) if (c0 + k < ncells) s += cnt[c0 + k];
+            uint32_t x = s;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t u = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                if (lane >= o) x += u;
+            }
+            if (lane == 31) ws[w] = x;
+            __syncthreads();
+            uint32_t off = 0;
+            for (int k = 0; k < w; ++k) off += ws[k];
+            uint32_t run = off + x - s;
+            for (int k = 0; k < per; ++k)
+                if (c0 + k < ncells) {
+                    uint32_t v = cnt[c0 + k];
+                    cnt[c0 + k] = run;
+                    ce[((size_t)b << cell_bits) + c0 + k] = b0 + run;
+                    run += v;
+                }
+        }
+        __syncthreads();
+        if (staged) {
+            for (uint32_t i = t; i < nb; i += BKT_THREADS) perm[cnt[sc[i]] + sr[i]] = (uint16_t)i;
+            __syncthreads();
+            for (uint32_t slot = t; slot < nb; slot += BKT_THREADS) sorted[b0 + slot] = s4[perm[slot]];
+        } else {
+            /* oversized bucket (a dense halo core): second read, ranks from shared-memory cursors,
+             * scattered stores inside the bucket's range */
+            for (uint32_t i = t; i < nb; i += BKT_THREADS) {
+                float4 q = ld_stream(in4 + b0 + i);
+                if (first_pass_input_is_raw) q.w = __int_as_float((int)(b0 + i));
+                uint32_t c = cell_key(q, g) & cmask;
+                uint32_t dst = atomicAdd(&cnt[c], 1u);
+                sorted[b0 + dst] = q;
+            }
+        }
+        __syncthreads();
+    }
+}

@@ -76,9 +76,8 @@ extern "C" const char *sogpu_last_error(void) { return g_err; }
  * device-side grid description
  * ============================================================================================ */
 struct GridDev {
-    const float4 *sorted;     /* particles {x,y,z,m} in cell order                         */
+    const float4 *sorted;     /* particles in cell order: {x, y, z, original index as int bits} */
     const uint32_t *ce;       /* ce[c] = first sorted slot of cell c, ce[ncell] = N          */
-    const int32_t *orig;      /* original (file) index of each sorted slot                   */
     int nc, lb;               /* cells per axis (power of two), log2                         */
     float g0[3], invh[3];     /* cell coordinate = floor((x - g0) * invh) & (nc-1)           */
     float L[3], halfL[3];
@@ -116,7 +115,7 @@ __device__ __forceinline__ uint32_t cell_key(const float4 &p, const GridDev &g)
 __device__ __forceinline__ float4 ld_stream(const float4 *p)
 {
     float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                  : "l"(p));
     return r;
@@ -125,274 +124,11 @@ __device__ __forceinline__ float4 ld_stream(const float4 *p)
 /* ============================================================================================
  * grid build kernels (kdBuildTree replacement)
  * ============================================================================================ */
-__device__ __forceinline__ uint32_t f2ord(float f) { return __float_as_uint(f); } /* f >= 0 */
+#include "grid_build.cuh"
 
-/* count particles per cell into ce[key+1]; also min/max of mass (as ordered uints) */
-__global__ void __launch_bounds__(256) k_cell_count(const float4 *__restrict__ in, int64_t n,
-                                                    GridDev g, uint32_t *__restrict__ ce,
-                                                    uint32_t *__restrict__ mass_minmax)
+__global__ void k_store_u32(uint32_t *p, uint32_t v0, uint32_t *q, uint32_t v1)
 {
-    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float4 p = ld_stream(in + i);
-        atomicAdd(&ce[cell_key(p, g) + 1], 1u);
-        uint32_t mo = (p.w >= 0.0f) ? f2ord(p.w) : 0xFFFFFFFEu;   /* negative/NaN mass => "unequal" */
-        if (!(p.w >= 0.0f)) { mn = 0u; }
-        mn = min(mn, mo);
-        mx = max(mx, mo);
-    }
-    mn = __reduce_min_sync(0xFFFFFFFFu, mn);
-    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
-    if ((threadIdx.x & 31) == 0) {
-        atomicMin(&mass_minmax[0], mn);
-        atomicMax(&mass_minmax[1], mx);
-    }
-}
-
-#define SCAN_TILE 2048   /* 256 threads x 8 */
-
-__global__ void __launch_bounds__(256) k_scan_reduce(const uint32_t *__restrict__ a, int64_t n,
-                                                     uint32_t *__restrict__ bsum)
-{
-    __shared__ uint32_t ws[8];
-    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
-    uint32_t s = 0;
-    for (int k = 0; k < 8; ++k) {
-        int64_t i = base + k * 256 + threadIdx.x;
-        if (i < n) s += a[i];
-    }
-    s = __reduce_add_sync(0xFFFFFFFFu, s);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int k = 0; k < 8; ++k) t += ws[k];
-        bsum[blockIdx.x] = t;
-    }
-}
-
-/* exclusive scan of bsum[0..nb) by one block */
-__global__ void __launch_bounds__(1024) k_scan_bsums(uint32_t *__restrict__ bsum, int64_t nb)
-{
-    __shared__ uint32_t ws[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int64_t b0 = 0; b0 < nb; b0 += 1024) {
-        int64_t i = b0 + threadIdx.x;
-        uint32_t v = (i < nb) ? bsum[i] : 0u, x = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= o) x += t;
-        }
-        if (lane == 31) ws[w] = x;
-        __syncthreads();
-        if (w == 0) {
-            uint32_t y = ws[lane];
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, y, o);
-                if (lane >= o) y += t;
-            }
-            ws[lane] = y;
-        }
-        __syncthreads();
-        uint32_t incl = x + (w ? ws[w - 1] : 0u) + carry;
-        if (i < nb) bsum[i] = incl - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = incl;
-        __syncthreads();
-    }
-}
-
-/* in-place exclusive scan of each tile plus its block offset */
-__global__ void __launch_bounds__(256) k_scan_apply(uint32_t *__restrict__ a, int64_t n,
-                                                    const uint32_t *__restrict__ bsum)
-{
-    __shared__ uint32_t ws[8];
-    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * 8;
-    uint32_t v[8], s = 0;
-    for (int k = 0; k < 8; ++k) {
-        v[k] = (base + k < n) ? a[base + k] : 0u;
-        s += v[k];
-    }
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t x = s;
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o);
-        if (lane >= o) x += t;
-    }
-    if (lane == 31) ws[w] = x;
-    __syncthreads();
-    uint32_t off = bsum[blockIdx.x];
-    for (int k = 0; k < w; ++k) off += ws[k];
-    uint32_t run = off + x - s;
-    for (int k = 0; k < 8; ++k) {
-        if (base + k < n) a[base + k] = run;
-        run += v[k];
-    }
-}
-
-/* place every particle in its cell: ce[key+1] is the cell's fill cursor, ends as the cell's end */
-__global__ void __launch_bounds__(256) k_scatter(const float4 *__restrict__ in, int64_t n, GridDev g,
-                                                 uint32_t *__restrict__ ce,
-                                                 float4 *__restrict__ sorted,
-                                                 int32_t *__restrict__ orig)
-{
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float4 p = ld_stream(in + i);
-        uint32_t pos = atomicAdd(&ce[cell_key(p, g) + 1], 1u);
-        sorted[pos] = p;
-        orig[pos] = (int32_t)i;
-    }
-}
-
-/* ---- two-level build for large N: MSD partition into coarse buckets (coalesced, staged through
- * shared memory), then the counting sort runs bucket by bucket so that its random accesses (cell
- * counters, scattered 16-byte stores) stay inside an L2-resident window ---------------------- */
-#define PART_T 4096          /* particles per tile (256 threads x 16)                          */
-#define PART_BMAX 256        /* coarse buckets (one per thread of the partition CTA)            */
-
-/* coarse histogram (shared-memory atomics, one global atomic per bucket per CTA) + mass min/max */
-__global__ void __launch_bounds__(256) k_coarse_hist(const float4 *__restrict__ in, int64_t n, GridDev g,
-                                                     int kshift, uint32_t *__restrict__ ghist,
-                                                     uint32_t *__restrict__ mass_minmax)
-{
-    __shared__ uint32_t sh[PART_BMAX];
-    sh[threadIdx.x] = 0u;
-    __syncthreads();
-    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float4 p = ld_stream(in + i);
-        atomicAdd(&sh[cell_key(p, g) >> kshift], 1u);
-        uint32_t mo = (p.w >= 0.0f) ? f2ord(p.w) : 0xFFFFFFFEu;
-        if (!(p.w >= 0.0f)) mn = 0u;
-        mn = min(mn, mo);
-        mx = max(mx, mo);
-    }
-    __syncthreads();
-    if (sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
-    mn = __reduce_min_sync(0xFFFFFFFFu, mn);
-    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
-    if ((threadIdx.x & 31) == 0) {
-        atomicMin(&mass_minmax[0], mn);
-        atomicMax(&mass_minmax[1], mx);
-    }
-}
-
-/* exclusive scan of the <=256 coarse counts into the bucket cursors (in place) */
-__global__ void __launch_bounds__(256) k_coarse_scan(uint32_t *__restrict__ ghist)
-{
-    __shared__ uint32_t ws[8];
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t v = ghist[threadIdx.x], x = v;
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o);
-        if (lane >= o) x += t;
-    }
-    if (lane == 31) ws[w] = x;
-    __syncthreads();
-    uint32_t off = 0;
-    for (int k = 0; k < w; ++k) off += ws[k];
-    ghist[threadIdx.x] = off + x - v;
-}
-
-/* tile-wise stable-enough partition: every tile is counting-sorted by coarse bucket in shared
- * memory, claims a run in each bucket with one atomic, and writes runs (coalesced) */
-__global__ void __launch_bounds__(256) k_partition(const float4 *__restrict__ in, int64_t n, GridDev g,
-                                                   int kshift, uint32_t *__restrict__ gcursor,
-                                                   float4 *__restrict__ tmp4, uint32_t *__restrict__ tmpk,
-                                                   int32_t *__restrict__ tmpi)
-{
-    extern __shared__ __align__(16) unsigned char raw[];
-    float4 *s4 = reinterpret_cast<float4 *>(raw);
-    uint32_t *sk = reinterpret_cast<uint32_t *>(s4 + PART_T);
-    uint16_t *sr = reinterpret_cast<uint16_t *>(sk + PART_T);
-    uint16_t *perm = sr + PART_T;
-    uint8_t *sd = reinterpret_cast<uint8_t *>(perm + PART_T);
-    __shared__ uint32_t scnt[PART_BMAX], soff[PART_BMAX], sbase[PART_BMAX], ws[8];
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const int64_t ntiles = (n + PART_T - 1) / PART_T;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t base = tile * PART_T;
-        const int cnt = (int)min((int64_t)PART_T, n - base);
-        scnt[t] = 0u;
-        __syncthreads();
-#pragma unroll 4
-        for (int k = 0; k < PART_T / 256; ++k) {
-            int i = k * 256 + t;
-            if (i < cnt) {
-                float4 p = ld_stream(in + base + i);
-                uint32_t key = cell_key(p, g);
-                uint32_t d = key >> kshift;
-                s4[i] = p;
-                sk[i] = key;
-                sd[i] = (uint8_t)d;
-                sr[i] = (uint16_t)atomicAdd(&scnt[d], 1u);
-            }
-        }
-        __syncthreads();
-        {
-            uint32_t c = scnt[t], x = c;
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t u = __shfl_up_sync(0xFFFFFFFFu, x, o);
-                if (lane >= o) x += u;
-            }
-            if (lane == 31) ws[w] = x;
-            __syncthreads();
-            uint32_t off = 0;
-            for (int k = 0; k < w; ++k) off += ws[k];
-            soff[t] = off + x - c;
-            sbase[t] = c ? atomicAdd(&gcursor[t], c) : 0u;
-        }
-        __syncthreads();
-        for (int i = t; i < cnt; i += 256) perm[soff[sd[i]] + sr[i]] = (uint16_t)i;
-        __syncthreads();
-        for (int slot = t; slot < cnt; slot += 256) {
-            int i = perm[slot];
-            uint32_t d = sd[i];
-            uint32_t dst = sbase[d] + ((uint32_t)slot - soff[d]);
-            tmp4[dst] = s4[i];
-            tmpk[dst] = sk[i];
-            tmpi[dst] = (int32_t)(base + i);
-        }
-        __syncthreads();
-    }
-}
-
-/* fine cell counts from the partitioned keys: neighbouring threads hit neighbouring counters */
-__global__ void __launch_bounds__(256) k_fine_count(const uint32_t *__restrict__ tmpk, int64_t n,
-                                                    uint32_t *__restrict__ ce)
-{
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        atomicAdd(&ce[__ldg(tmpk + i) + 1], 1u);
-}
-
-/* final placement, bucket by bucket: reads are streaming, writes stay in the bucket's window */
-__global__ void __launch_bounds__(256) k_fine_scatter(const float4 *__restrict__ tmp4,
-                                                      const uint32_t *__restrict__ tmpk,
-                                                      const int32_t *__restrict__ tmpi, int64_t n,
-                                                      uint32_t *__restrict__ ce, float4 *__restrict__ sorted,
-                                                      int32_t *__restrict__ orig)
-{
-    /* CTAs walk the array in order (chunk per CTA per round) so the active window is a few buckets */
-    const int64_t chunk = 256 * 8;
-    for (int64_t c0 = (int64_t)blockIdx.x * chunk; c0 < n; c0 += (int64_t)gridDim.x * chunk) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            int64_t i = c0 + k * 256 + threadIdx.x;
-            if (i < n) {
-                float4 p = ld_stream(tmp4 + i);
-                uint32_t pos = atomicAdd(&ce[__ldg(tmpk + i) + 1], 1u);
-                sorted[pos] = p;
-                orig[pos] = __ldg(tmpi + i);
-            }
-        }
-    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) { *p = v0; if (q) *q = v1; }
 }
 
 /* K1 (pack): raw host layout -> float4 {x,y,z,m} on the device (xyz triplets + one shared mass) */
@@ -623,13 +359,29 @@ __device__ __forceinline__ void for_each_in_ball(const GridDev &g, GroupSmem<NT>
                 if (sm.seg_pre[mid] > i) hi = mid; else lo = mid + 1;
             }
             int s = lo;
-            for (; i < total; i += NT) {
-                while (sm.seg_pre[s] <= i) ++s;
-                uint32_t beg = s ? sm.seg_pre[s - 1] : 0u;
-                uint32_t p = sm.seg_start[s] + (i - beg);
-                float4 q = __ldg(g.sorted + p);
-                f(p, q);
-                ++evals;
+            const int U = 4;                    /* independent loads in flight per thread */
+            for (; i < total; i += NT * U) {
+                uint32_t pp[U];
+                float4 qq[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    uint32_t iu = i + (uint32_t)u * NT;
+                    pp[u] = 0xFFFFFFFFu;
+                    if (iu < total) {
+                        while (sm.seg_pre[s] <= iu) ++s;
+                        uint32_t beg = s ? sm.seg_pre[s - 1] : 0u;
+                        pp[u] = sm.seg_start[s] + (iu - beg);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (pp[u] != 0xFFFFFFFFu) qq[u] = __ldg(g.sorted + pp[u]);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (pp[u] != 0xFFFFFFFFu) {
+                        f(pp[u], qq[u]);
+                        ++evals;
+                    }
             }
         }
         gsync<NT>();
@@ -666,7 +418,7 @@ template <int CAP> struct CollectF {   /* append (r^2 bits, original index) of t
         if (bits >= lo_bits && bits <= hi_bits) {
             uint32_t pos = atomicAdd(cnt, 1u);
             if (pos < (uint32_t)CAP)
-                wkey[pos] = ((unsigned long long)bits << 32) | (uint32_t)__ldg(g->orig + p);
+                wkey[pos] = ((unsigned long long)bits << 32) | __float_as_uint(q.w);
         }
     }
 };
@@ -685,7 +437,7 @@ struct EmitF {          /* members: (r^2 bits, index) < key_j */
         uint32_t bits = __float_as_uint(d2);
         uint32_t bj = (uint32_t)(key_j >> 32);
         if (bits <= bj) {
-            int32_t oi = __ldg(g->orig + p);
+            int32_t oi = __float_as_int(q.w);
             if (bits < bj || (uint32_t)oi < (uint32_t)key_j) {
                 uint32_t pos = atomicAdd(cnt, 1u);
                 if (pos < limit) {
@@ -711,7 +463,7 @@ struct GatherF {        /* sogpu_ball_gather: everything with r^2 <= ball2 */
         if (__float_as_uint(d2) <= hi_bits) {
             unsigned long long pos = atomicAdd(cnt, 1ull);
             if (pos < cap) {
-                idx[pos] = __ldg(g->orig + p);
+                idx[pos] = __float_as_int(q.w);
                 d2o[pos] = d2;
             }
         }
@@ -1272,14 +1024,12 @@ __global__ void __launch_bounds__(256) k_ball_gather(const __grid_constant__ Gri
  * host side
  * ============================================================================================ */
 enum {
-    KID_CELL_COUNT = 0, KID_SCAN, KID_SCATTER, KID_MASS_TABLE, KID_CLASSIFY, KID_QUERY_WARP,
-    KID_QUERY_BLOCK, KID_OFFSETS, KID_EMIT_WARP, KID_EMIT_BLOCK, KID_BALL_GATHER, KID_COARSE_HIST,
-    KID_COARSE_SCAN, KID_PARTITION, KID_FINE_COUNT, KID_FINE_SCATTER, KID_N
+    KID_LVL_HIST = 0, KID_LVL_SCAN, KID_LVL_PARTITION, KID_BUCKET_SORT, KID_MASS_TABLE, KID_CLASSIFY,
+    KID_QUERY_WARP, KID_QUERY_BLOCK, KID_OFFSETS, KID_EMIT_WARP, KID_EMIT_BLOCK, KID_BALL_GATHER, KID_N
 };
 static const char *const g_kernel_names[KID_N] = {
-    "k_cell_count", "k_scan(3 launches)", "k_scatter", "k_mass_table", "k_classify", "k_so_query<32>",
-    "k_so_query<256>", "k_offsets", "k_so_emit<32>", "k_so_emit<256>", "k_ball_gather", "k_coarse_hist",
-    "k_coarse_scan", "k_partition", "k_fine_count", "k_fine_scatter"};
+    "k_lvl_hist", "k_scan(3 launches)", "k_lvl_partition", "k_bucket_sort", "k_mass_table", "k_classify",
+    "k_so_query<32>", "k_so_query<256>", "k_offsets", "k_so_emit<32>", "k_so_emit<256>", "k_ball_gather"};
 
 struct ProfRec { int kid; cudaEvent_t a, b; };
 
@@ -1295,18 +1045,19 @@ struct sogpu {
     float4 *d_in_owned;
     int64_t d_in_cap;
     float4 *d_sorted;
-    int32_t *d_orig;
     int64_t grid_n_cap;
     uint32_t *d_ce;
     uint32_t *d_bsum;
     uint32_t *d_massmm;
     float *d_raw;                    /* staging of raw xyz triplets (pinned-host fast path) */
-    uint32_t *d_coarse;              /* PART_BMAX bucket cursors */
-    float4 *d_tmp4;                  /* partitioned particles / keys / original indices */
-    uint32_t *d_tmpk;
-    int32_t *d_tmpi;
+    float4 *d_tmp4;                  /* ping-pong payload buffer of the partition levels */
+    uint32_t *d_key[2];              /* ping-pong cell keys between levels */
     int64_t tmp_cap;
-    int two_level;                   /* -1 auto, 0 direct counting sort, 1 partition first */
+    uint32_t *d_lvl_start[4];        /* child-bucket starts per level (+ sentinel) */
+    uint32_t *d_lvl_cursor[4];       /* counts, then the atomic cursors of the partition */
+    size_t lvl_cap[4];
+    int two_level;                   /* -1 auto; 0: no partition levels (bucket sort only if it fits) */
+    double prof_bytes[32];
     int64_t ncell;
     int nc, lb;
     bool built;
@@ -1358,10 +1109,11 @@ static cudaEvent_t prof_event(sogpu *h)
 }
 struct ProfScope {   /* brackets one (group of) kernel launch(es) with events when profiling is on */
     sogpu *h; ProfRec r; bool on;
-    ProfScope(sogpu *h_, int kid) : h(h_), on(h_->prof_on)
+    ProfScope(sogpu *h_, int kid, double alg_bytes = 0.0) : h(h_), on(h_->prof_on)
     {
-        h->stats.last_kernel_launches += (kid == KID_SCAN) ? 3 : 1;
+        h->stats.last_kernel_launches += (kid == KID_LVL_SCAN) ? 3 : 1;
         if (!on) return;
+        h->prof_bytes[kid] += alg_bytes;
         r.kid = kid; r.a = prof_event(h); r.b = prof_event(h);
         cudaEventRecord(r.a, h->stream);
     }
@@ -1432,7 +1184,6 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
 static void free_grid(sogpu *h)
 {
     cudaFree(h->d_sorted); h->d_sorted = nullptr;
-    cudaFree(h->d_orig); h->d_orig = nullptr;
     cudaFree(h->d_ce); h->d_ce = nullptr;
     cudaFree(h->d_bsum); h->d_bsum = nullptr;
     h->grid_n_cap = 0; h->nc = 0;
@@ -1459,8 +1210,8 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     cudaFree(h->d_in_owned);
     cudaFree(h->d_massmm);
     cudaFree(h->d_raw);
-    cudaFree(h->d_coarse);
-    cudaFree(h->d_tmp4); cudaFree(h->d_tmpk); cudaFree(h->d_tmpi);
+    cudaFree(h->d_tmp4); cudaFree(h->d_key[0]); cudaFree(h->d_key[1]);
+    for (int l = 0; l < 4; ++l) { cudaFree(h->d_lvl_start[l]); cudaFree(h->d_lvl_cursor[l]); }
     cudaFree(h->d_mt);
     cudaFree(h->d_counters);
     cudaFree(h->d_u64);
@@ -1639,104 +1390,148 @@ extern "C" int sogpu_build_grid(sogpu_t *h)
     if (!h || !h->d_in || h->n <= 0) return set_err(SOGPU_ERR_ARG, "sogpu_build_grid: no particles set");
     CU(cudaSetDevice(h->device));
     int lb;
-    int nc = pick_cells(h->n, h->ppc, &lb);
-    int64_t ncell = (int64_t)nc * nc * nc;
-    int64_t ntile = (ncell + SCAN_TILE - 1) / SCAN_TILE;
+    const int nc = pick_cells(h->n, h->ppc, &lb);
+    const int64_t ncell = (int64_t)nc * nc * nc;
+    const int keybits = 3 * lb;
+    /* final buckets: ~1024 particles on average and at most BKT_CELLS cells each */
+    int cbt = 0;
+    while (((int64_t)1024 << cbt) < h->n) ++cbt;
+    if (h->two_level == 0) cbt = 0;
+    if (cbt < keybits - 12) cbt = keybits - 12;
+    if (cbt > keybits) cbt = keybits;
+    const int cell_bits = keybits - cbt;
+    const int L = (cbt + 7) / 8;                       /* partition levels, digits of <= 8 bits */
+    if (L > 4) return set_err(SOGPU_ERR_UNSUPPORTED, "too many partition levels");
     if (!h->d_ce || h->nc != nc) {
-        cudaFree(h->d_ce); cudaFree(h->d_bsum);
-        h->d_ce = nullptr; h->d_bsum = nullptr;
+        cudaFree(h->d_ce); h->d_ce = nullptr;
         CU(cudaMalloc(&h->d_ce, (size_t)(ncell + 1) * sizeof(uint32_t)));
-        CU(cudaMalloc(&h->d_bsum, (size_t)ntile * sizeof(uint32_t)));
     }
+    if (!h->d_bsum) CU(cudaMalloc(&h->d_bsum, 4096 * sizeof(uint32_t)));
     if (h->n > h->grid_n_cap) {
-        cudaFree(h->d_sorted); cudaFree(h->d_orig);
-        h->d_sorted = nullptr; h->d_orig = nullptr; h->grid_n_cap = 0;
+        cudaFree(h->d_sorted);
+        h->d_sorted = nullptr; h->grid_n_cap = 0;
         CU(cudaMalloc(&h->d_sorted, (size_t)h->n * sizeof(float4)));
-        CU(cudaMalloc(&h->d_orig, (size_t)h->n * sizeof(int32_t)));
         h->grid_n_cap = h->n;
+    }
+    if (L > 0 && h->n > h->tmp_cap) {
+        cudaFree(h->d_tmp4); cudaFree(h->d_key[0]); cudaFree(h->d_key[1]);
+        h->d_tmp4 = nullptr; h->d_key[0] = h->d_key[1] = nullptr; h->tmp_cap = 0;
+        CU(cudaMalloc(&h->d_tmp4, (size_t)h->n * sizeof(float4)));
+        CU(cudaMalloc(&h->d_key[0], (size_t)h->n * sizeof(uint32_t)));
+        CU(cudaMalloc(&h->d_key[1], (size_t)h->n * sizeof(uint32_t)));
+        h->tmp_cap = h->n;
     }
     if (!h->d_massmm) CU(cudaMalloc(&h->d_massmm, 2 * sizeof(uint32_t)));
     if (!h->d_mt) CU(cudaMalloc(&h->d_mt, sizeof(so_mass_table)));
     h->nc = nc; h->lb = lb; h->ncell = ncell;
 
     GridDev &g = h->g;
-    g.sorted = h->d_sorted; g.ce = h->d_ce; g.orig = h->d_orig;
+    g.sorted = h->d_sorted; g.ce = h->d_ce;
     g.nc = nc; g.lb = lb;
     double hmax = 0.0, lmin = 1e300;
     for (int k = 0; k < 3; ++k) {
-        double L = (double)h->period[k];
+        double Lk = (double)h->period[k];
         g.L[k] = h->period[k];
         g.halfL[k] = 0.5f * h->period[k];
-        g.g0[k] = (float)((double)h->center[k] - 0.5 * L);
+        g.g0[k] = (float)((double)h->center[k] - 0.5 * Lk);
         g.dg0[k] = (double)g.g0[k];
-        g.dh[k] = L / nc;
-        g.invh[k] = (float)((double)nc / L);
+        g.dh[k] = Lk / nc;
+        g.invh[k] = (float)((double)nc / Lk);
         g.dinvh[k] = (double)g.invh[k];
         hmax = std::max(hmax, g.dh[k]);
-        lmin = std::min(lmin, L);
+        lmin = std::min(lmin, Lk);
     }
     g.bmax_pruned = 0.5 * lmin - 2.0 * hmax;
 
     cudaStream_t s = h->stream;
+    const double N = (double)h->n;
     h->stats.last_kernel_launches = 0;
-    CU(cudaMemsetAsync(h->d_ce, 0, (size_t)(ncell + 1) * sizeof(uint32_t), s));
     CU(cudaMemsetAsync(h->d_massmm, 0xFF, sizeof(uint32_t), s));
     CU(cudaMemsetAsync(h->d_massmm + 1, 0, sizeof(uint32_t), s));
-    int grid = h->sm_count * 8;
-    int64_t need = (h->n + 255) / 256;
-    if (need < grid) grid = (int)need;
-    /* coarse digit = top cb bits of the cell key; buckets of ~64K particles */
-    int cb = 0;
-    while (cb < 8 && ((int64_t)65536 << cb) < h->n) ++cb;
-    if (cb > 3 * lb) cb = 3 * lb;
-    const bool two_level = h->two_level < 0 ? (cb >= 2) : (h->two_level != 0 && cb >= 1);
-    if (!two_level) {
-        { ProfScope p(h, KID_CELL_COUNT); k_cell_count<<<grid, 256, 0, s>>>(h->d_in, h->n, g, h->d_ce, h->d_massmm); }
-        {
-            ProfScope p(h, KID_SCAN);
-            k_scan_reduce<<<(unsigned)ntile, 256, 0, s>>>(h->d_ce + 1, ncell, h->d_bsum);
-            k_scan_bsums<<<1, 1024, 0, s>>>(h->d_bsum, ntile);
-            k_scan_apply<<<(unsigned)ntile, 256, 0, s>>>(h->d_ce + 1, ncell, h->d_bsum);
-        }
-        { ProfScope p(h, KID_SCATTER); k_scatter<<<grid, 256, 0, s>>>(h->d_in, h->n, g, h->d_ce, h->d_sorted, h->d_orig); }
-    } else {
-        if (!h->d_coarse) CU(cudaMalloc(&h->d_coarse, PART_BMAX * sizeof(uint32_t)));
-        if (h->n > h->tmp_cap) {
-            cudaFree(h->d_tmp4); cudaFree(h->d_tmpk); cudaFree(h->d_tmpi);
-            h->d_tmp4 = nullptr; h->d_tmpk = nullptr; h->d_tmpi = nullptr; h->tmp_cap = 0;
-            CU(cudaMalloc(&h->d_tmp4, (size_t)h->n * sizeof(float4)));
-            CU(cudaMalloc(&h->d_tmpk, (size_t)h->n * sizeof(uint32_t)));
-            CU(cudaMalloc(&h->d_tmpi, (size_t)h->n * sizeof(int32_t)));
-            h->tmp_cap = h->n;
-        }
-        const int kshift = 3 * lb - cb;
-        const size_t part_smem = (size_t)PART_T * (16 + 4 + 2 + 2 + 1);
-        static bool attr_done = false;
-        if (!attr_done) {
-            CU(cudaFuncSetAttribute(k_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
-            attr_done = true;
-        }
-        CU(cudaMemsetAsync(h->d_coarse, 0, PART_BMAX * sizeof(uint32_t), s));
-        { ProfScope p(h, KID_COARSE_HIST); k_coarse_hist<<<grid, 256, 0, s>>>(h->d_in, h->n, g, kshift, h->d_coarse, h->d_massmm); }
-        { ProfScope p(h, KID_COARSE_SCAN); k_coarse_scan<<<1, 256, 0, s>>>(h->d_coarse); }
-        {
-            ProfScope p(h, KID_PARTITION);
-            int64_t tiles = (h->n + PART_T - 1) / PART_T;
-            int pg = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 2);
-            k_partition<<<pg, 256, part_smem, s>>>(h->d_in, h->n, g, kshift, h->d_coarse, h->d_tmp4, h->d_tmpk, h->d_tmpi);
-        }
-        { ProfScope p(h, KID_FINE_COUNT); k_fine_count<<<grid, 256, 0, s>>>(h->d_tmpk, h->n, h->d_ce); }
-        {
-            ProfScope p(h, KID_SCAN);
-            k_scan_reduce<<<(unsigned)ntile, 256, 0, s>>>(h->d_ce + 1, ncell, h->d_bsum);
-            k_scan_bsums<<<1, 1024, 0, s>>>(h->d_bsum, ntile);
-            k_scan_apply<<<(unsigned)ntile, 256, 0, s>>>(h->d_ce + 1, ncell, h->d_bsum);
-        }
-        {
-            ProfScope p(h, KID_FINE_SCATTER);
-            k_fine_scatter<<<grid, 256, 0, s>>>(h->d_tmp4, h->d_tmpk, h->d_tmpi, h->n, h->d_ce, h->d_sorted, h->d_orig);
+
+    /* digit widths: cbt split as evenly as possible over L levels, most significant first */
+    int db[4] = {0, 0, 0, 0}, bits_done = 0;
+    for (int l = 0; l < L; ++l) db[l] = cbt / L + (l < cbt % L ? 1 : 0);
+    for (int l = 0, done = 0; l < std::max(L, 1); ++l) {
+        done += db[l];
+        size_t need = ((size_t)1 << done) + 1;
+        if (need > h->lvl_cap[l]) {
+            cudaFree(h->d_lvl_start[l]); cudaFree(h->d_lvl_cursor[l]);
+            h->d_lvl_start[l] = h->d_lvl_cursor[l] = nullptr; h->lvl_cap[l] = 0;
+            CU(cudaMalloc(&h->d_lvl_start[l], need * sizeof(uint32_t)));
+            CU(cudaMalloc(&h->d_lvl_cursor[l], need * sizeof(uint32_t)));
+            h->lvl_cap[l] = need;
         }
     }
+    static bool attr_done = false;
+    const size_t part_smem = (size_t)LVL_T * (16 + 4 + 2 + 2 + 2);
+    const size_t bkt_smem = (size_t)BKT_CAP * (16 + 2 + 2 + 2) + (size_t)BKT_CELLS * 4;
+    if (!attr_done) {
+        CU(cudaFuncSetAttribute(k_lvl_partition<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
+        CU(cudaFuncSetAttribute(k_lvl_partition<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
+        CU(cudaFuncSetAttribute(k_lvl_partition<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
+        CU(cudaFuncSetAttribute(k_lvl_partition<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
+        CU(cudaFuncSetAttribute(k_bucket_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bkt_smem));
+        attr_done = true;
+    }
+    const int64_t tiles = (h->n + LVL_T - 1) / LVL_T;
+    const int hist_grid = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 8);
+    const int part_grid = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 2);
+
+    const float4 *src = h->d_in;
+    const uint32_t *src_key = nullptr;
+    if (L == 0) {
+        /* tiny input: one bucket = the whole array; the histogram launch only finds mass min/max */
+        LevelDesc lv; lv.shift = 0; lv.db = 0; lv.pshift = 32; lv.n_parents = 1;
+        CU(cudaMemsetAsync(h->d_lvl_cursor[0], 0, 2 * sizeof(uint32_t), s));
+        { ProfScope p(h, KID_LVL_HIST, 16.0 * N);
+          k_lvl_hist<true><<<hist_grid, 256, 0, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[0], h->d_massmm); }
+        k_store_u32<<<1, 32, 0, s>>>(h->d_lvl_start[0], 0u, h->d_lvl_start[0] + 1, (uint32_t)h->n);
+    }
+    for (int l = 0; l < L; ++l) {
+        LevelDesc lv;
+        lv.db = db[l];
+        lv.shift = keybits - bits_done - db[l];
+        lv.pshift = bits_done ? keybits - bits_done : 32;
+        lv.n_parents = 1u << bits_done;
+        const size_t M = (size_t)1 << (bits_done + db[l]);
+        const bool last = (l == L - 1);
+        float4 *dst = ((L - 1 - l) % 2 == 0) ? h->d_tmp4 : h->d_sorted;
+        uint32_t *dst_key = h->d_key[l & 1];
+        const uint32_t *pstart = l ? h->d_lvl_start[l - 1] : nullptr;
+        CU(cudaMemsetAsync(h->d_lvl_cursor[l], 0, M * sizeof(uint32_t), s));
+        {
+            ProfScope p(h, KID_LVL_HIST, (l ? 4.0 : 16.0) * N);
+            if (l == 0) k_lvl_hist<true><<<hist_grid, 256, 0, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], h->d_massmm);
+            else k_lvl_hist<false><<<hist_grid, 256, 0, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], h->d_massmm);
+        }
+        {
+            ProfScope p(h, KID_LVL_SCAN, 12.0 * (double)M);
+            int64_t nt = ((int64_t)M + SCAN_TILE - 1) / SCAN_TILE;
+            k_scan_reduce<<<(unsigned)nt, 256, 0, s>>>(h->d_lvl_cursor[l], (int64_t)M, h->d_bsum);
+            k_scan_bsums<<<1, 1024, 0, s>>>(h->d_bsum, nt);
+            k_scan_apply<<<(unsigned)nt, 256, 0, s>>>(h->d_lvl_cursor[l], (int64_t)M, h->d_bsum, h->d_lvl_start[l],
+                                                     h->d_lvl_cursor[l], (uint32_t)h->n);
+        }
+        {
+            ProfScope p(h, KID_LVL_PARTITION, ((l ? 20.0 : 16.0) + 16.0 + (last ? 0.0 : 4.0)) * N);
+            if (l == 0 && !last) k_lvl_partition<true, true><<<part_grid, 256, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key);
+            else if (l == 0) k_lvl_partition<true, false><<<part_grid, 256, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key);
+            else if (!last) k_lvl_partition<false, true><<<part_grid, 256, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key);
+            else k_lvl_partition<false, false><<<part_grid, 256, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key);
+        }
+        src = dst;
+        src_key = dst_key;
+        bits_done += db[l];
+    }
+    {
+        const uint32_t nb = 1u << cbt;
+        const uint32_t *bstart = h->d_lvl_start[L ? L - 1 : 0];
+        int grid = (int)std::min<int64_t>((int64_t)nb, (int64_t)h->sm_count * 16);
+        ProfScope p(h, KID_BUCKET_SORT, 32.0 * N + 4.0 * (double)ncell);
+        k_bucket_sort<<<grid, BKT_THREADS, bkt_smem, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, L == 0 ? 1 : 0);
+    }
+    k_store_u32<<<1, 32, 0, s>>>(h->d_ce + ncell, (uint32_t)h->n, nullptr, 0u);
     { ProfScope p(h, KID_MASS_TABLE); k_mass_table<<<1, 32, 0, s>>>(h->d_massmm, h->d_mt, (unsigned long long)h->n + 2ull); }
     CU(cudaGetLastError());
     h->built = true;
@@ -2143,7 +1938,7 @@ extern "C" int sogpu_profile_read(sogpu_t *h, double *ms, int64_t *launches, int
         float t = 0.0f;
         if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
             h->prof_ms[r.kid] += (double)t;
-            h->prof_launches[r.kid] += (r.kid == KID_SCAN) ? 3 : 1;
+            h->prof_launches[r.kid] += (r.kid == KID_LVL_SCAN) ? 3 : 1;
         }
         h->prof_pool.push_back(r.a);
         h->prof_pool.push_back(r.b);
@@ -2152,6 +1947,18 @@ extern "C" int sogpu_profile_read(sogpu_t *h, double *ms, int64_t *launches, int
     for (int k = 0; k < nk && k < KID_N; ++k) { ms[k] = h->prof_ms[k]; launches[k] = h->prof_launches[k]; }
     if (reset)
         for (int k = 0; k < KID_N; ++k) { h->prof_ms[k] = 0.0; h->prof_launches[k] = 0; }
+    return SOGPU_OK;
+}
+
+/* Algorithmic bytes accumulated per kernel slot since the last sogpu_profile_read(reset=1) for the
+ * kernels whose traffic is known at launch time (the grid build); 0 for the query kernels, whose
+ * bytes are 16 B x r^2 evaluations (sogpu_get_stats). */
+extern "C" int sogpu_profile_bytes(sogpu_t *h, double *bytes, int nk, int reset)
+{
+    if (!h || !bytes) return set_err(SOGPU_ERR_ARG, "sogpu_profile_bytes: NULL argument");
+    for (int k = 0; k < nk && k < KID_N; ++k) bytes[k] = h->prof_bytes[k];
+    if (reset)
+        for (int k = 0; k < KID_N; ++k) h->prof_bytes[k] = 0.0;
     return SOGPU_OK;
 }
 
