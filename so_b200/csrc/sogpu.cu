@@ -20,6 +20,7 @@
 #include "so_math.h"
 
 #include <cuda_runtime.h>
+#include <cub/device/device_segmented_sort.cuh>
 
 #include <algorithm>
 #include <climits>
@@ -1021,6 +1022,248 @@ __global__ void __launch_bounds__(256) k_ball_gather(const __grid_constant__ Gri
 }
 
 /* ============================================================================================
+ * general path: particles of unequal mass (gas + dark + star snapshots)
+ *
+ * The enclosed mass is a sequential fp32 sum in sorted order (kd2.c:787,807), so with unequal masses
+ * nothing short of the fully sorted list reproduces it.  Per ball of the schedule and per halo:
+ * count -> emit (key, mass) -> segmented sort (CUB) -> the reference's scan, literally, by one warp
+ * (serial fp32 adds replicated on all lanes, density tests spread over the lanes).
+ * ============================================================================================ */
+struct GenState {            /* per halo, carried from ball to ball (kdRvir's locals) */
+    float ball;              /* fBall of the last gathered ball                               */
+    float mass;              /* running mass (kd2.c:744,787,807)                              */
+    uint32_t jlast;          /* kd2.c:743,797,832                                             */
+};
+
+struct GenArgs {
+    GridDev g;
+    const float4 *in;        /* original particle array: mass of particle i = in[i].w          */
+    const float *centers, *rgtp;
+    GenState *st;
+    const int32_t *list; const uint32_t *list_n; uint32_t *work;      /* halos of this round  */
+    int32_t *round_list; uint32_t *round_n;   /* (count) halos that need emit+sort+scan        */
+    unsigned long long *seg_n;                /* particles in the ball, per round slot          */
+    const unsigned long long *seg_begin;
+    unsigned long long *keys; float *mass;    /* scratch segments                                */
+    int32_t *next_list; uint32_t *next_n;     /* (scan) halos that need a bigger ball            */
+    float thr; int nM;
+    int32_t *out_n; float *out_m; unsigned long long *out_key;
+    unsigned long long *evals;
+};
+
+struct EmitPairF {
+    const GridDev *g; const float4 *in;
+    Center c; uint32_t hi_bits;
+    unsigned long long *keys; float *mass; uint32_t *cnt; uint32_t limit;
+    __device__ __forceinline__ void operator()(uint32_t, const float4 &q)
+    {
+        uint32_t bits = __float_as_uint(dist2(c, q, *g));
+        if (bits <= hi_bits) {
+            uint32_t pos = atomicAdd(cnt, 1u);
+            if (pos < limit) {
+                uint32_t idx = __float_as_uint(q.w);
+                keys[pos] = ((unsigned long long)bits << 32) | idx;
+                mass[pos] = __ldg(&in[idx].w);
+            }
+        }
+    }
+};
+
+/* advance every active halo to its next ball and count the particles in it (kd2.c:766-778) */
+__global__ void __launch_bounds__(256) k_gen_count(const __grid_constant__ GenArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const size_t mt_bytes = (sizeof(MassTableS) + 15) & ~(size_t)15;
+    GroupSmem<256> &sm = *reinterpret_cast<GroupSmem<256> *>(smem_raw + mt_bytes);
+    const int tid = threadIdx.x;
+    const uint32_t nlist = *a.list_n;
+    uint32_t ev = 0;
+    const float root = so_root_period(a.g.L[0], a.g.L[1], a.g.L[2]);
+    for (;;) {
+        const uint32_t item = next_item<256>(a.work, sm, tid);
+        if (item >= nlist) break;
+        const int h = a.list[item];
+        GenState st = a.st[h];
+        if (!((double)st.ball < 0.25 * (double)root) || !(st.ball > 0.0f)) {     /* kd2.c:766, 837-839 */
+            if (tid == 0) { a.out_n[h] = -3; a.out_m[h] = -3.0f; a.out_key[h] = 0ull; }
+            continue;
+        }
+        st.ball = so_next_ball(st.ball);
+        const float ball2 = __fmul_rn(st.ball, st.ball);
+        CountF f;
+        f.g = &a.g; f.c.x = a.centers[3 * h]; f.c.y = a.centers[3 * h + 1]; f.c.z = a.centers[3 * h + 2];
+        f.hi_bits = __float_as_uint(ball2); f.n = 0;
+        BallGeom B = make_geom(a.g, f.c, sqrt((double)ball2) * (1.0 + 1.0e-6));
+        for_each_in_ball<256>(a.g, sm, tid, B, f, ev);
+        const uint32_t n = gsum<256>(f.n, sm.tmp, tid);
+        if (tid == 0) {
+            a.st[h].ball = st.ball;
+            if (st.jlast == 0 && n < (uint32_t)a.nM) {                            /* kd2.c:772-778 */
+                a.out_n[h] = -1; a.out_m[h] = -1.0f; a.out_key[h] = 0ull;
+            } else {
+                uint32_t slot = atomicAdd(a.round_n, 1u);
+                a.round_list[slot] = h;
+                a.seg_n[slot] = n;
+            }
+        }
+    }
+    ev = __reduce_add_sync(0xFFFFFFFFu, ev);
+    if ((threadIdx.x & 31) == 0 && ev) atomicAdd(&a.evals[1], (unsigned long long)ev);
+}
+
+/* exclusive scan of the per-slot counts of slots [s0, s1) (one block) */
+__global__ void __launch_bounds__(1024) k_gen_offsets(const unsigned long long *__restrict__ seg_n, uint32_t s0,
+                                                      uint32_t s1, unsigned long long *__restrict__ seg_begin,
+                                                      unsigned long long *__restrict__ seg_end)
+{
+    __shared__ unsigned long long ws[32];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0ull;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (uint32_t b0 = s0; b0 < s1; b0 += 1024) {
+        uint32_t i = b0 + threadIdx.x;
+        unsigned long long v = (i < s1) ? seg_n[i] : 0ull, x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += t;
+        }
+        if (lane == 31) ws[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            unsigned long long y = ws[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, y, o);
+                if (lane >= o) y += t;
+            }
+            ws[lane] = y;
+        }
+        __syncthreads();
+        unsigned long long incl = x + (w ? ws[w - 1] : 0ull) + carry;
+        if (i < s1) { seg_begin[i] = incl - v; seg_end[i] = incl; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = incl;
+        __syncthreads();
+    }
+}
+
+/* write (key, mass) of every particle of the ball into the halo's scratch segment */
+__global__ void __launch_bounds__(256) k_gen_emit(const __grid_constant__ GenArgs a, uint32_t s0, uint32_t s1)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const size_t mt_bytes = (sizeof(MassTableS) + 15) & ~(size_t)15;
+    GroupSmem<256> &sm = *reinterpret_cast<GroupSmem<256> *>(smem_raw + mt_bytes);
+    const int tid = threadIdx.x;
+    uint32_t ev = 0;
+    for (uint32_t slot = s0 + blockIdx.x; slot < s1; slot += gridDim.x) {
+        const int h = a.round_list[slot];
+        const float ball = a.st[h].ball;
+        const float ball2 = __fmul_rn(ball, ball);
+        if (tid == 0) sm.cnt = 0u;
+        __syncthreads();
+        EmitPairF f;
+        f.g = &a.g; f.in = a.in;
+        f.c.x = a.centers[3 * h]; f.c.y = a.centers[3 * h + 1]; f.c.z = a.centers[3 * h + 2];
+        f.hi_bits = __float_as_uint(ball2);
+        f.keys = a.keys + a.seg_begin[slot]; f.mass = a.mass + a.seg_begin[slot];
+        f.cnt = &sm.cnt; f.limit = (uint32_t)a.seg_n[slot];
+        BallGeom B = make_geom(a.g, f.c, sqrt((double)ball2) * (1.0 + 1.0e-6));
+        for_each_in_ball<256>(a.g, sm, tid, B, f, ev);
+        __syncthreads();
+    }
+    ev = __reduce_add_sync(0xFFFFFFFFu, ev);
+    if ((threadIdx.x & 31) == 0 && ev) atomicAdd(&a.evals[1], (unsigned long long)ev);
+}
+
+/* kdRvir's scan over the sorted ball (kd2.c:785-832), one warp per halo */
+__global__ void __launch_bounds__(256) k_gen_scan(const __grid_constant__ GenArgs a, uint32_t s0, uint32_t s1,
+                                                  const unsigned long long *__restrict__ keys,
+                                                  const float *__restrict__ mass)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t slot = s0 + wid; slot < s1; slot += nw) {
+        const int h = a.round_list[slot];
+        const unsigned long long *K = keys + a.seg_begin[slot];
+        const float *M = mass + a.seg_begin[slot];
+        const uint32_t n = (uint32_t)a.seg_n[slot];
+        GenState st = a.st[h];
+        float run = st.mass;
+        uint32_t j = st.jlast;
+        bool done = false;
+        if (j == 0) {                                                  /* first ball: kd2.c:785-798 */
+            for (int k = 0; k < a.nM - 1; ++k) run = __fadd_rn(run, M[k]);
+            j = (uint32_t)(a.nM - 1);
+            float d2a = __uint_as_float((uint32_t)(K[j - 1] >> 32)), d2b = __uint_as_float((uint32_t)(K[j] >> 32));
+            if (so_rho_below(run, d2a, a.thr) && so_rho_below(__fadd_rn(run, M[j]), d2b, a.thr)) {
+                if (lane == 0) { a.out_n[h] = -2; a.out_m[h] = -2.0f; a.out_key[h] = 0ull; }
+                done = true;
+            }
+        }
+        /* main loop, kd2.c:804-831: for (j = jlast; j < n-1; j++) { mass += m[j]; test j and j+1 } */
+        while (!done && j + 1 < n) {
+            /* this chunk handles j0 = j .. j0+31 (as far as j+1 < n); lane t owns element j0+t */
+            const uint32_t j0 = j;
+            const uint32_t e = j0 + lane;
+            const float m_l = (e < n) ? M[e] : 0.0f;
+            const unsigned long long k_l = (e < n) ? K[e] : 0ull;
+            /* serial running sum, replicated on every lane: S_t = mass after adding element j0+t */
+            float S = run, mine = 0.0f;
+            for (int t = 0; t < 32; ++t) {
+                float mt_ = __shfl_sync(0xFFFFFFFFu, m_l, t);
+                S = __fadd_rn(S, mt_);
+                if (t == lane) mine = S;
+            }
+            /* below(e) = rho(S_e, d2_e) < thr ; valid where e < n */
+            bool below = (e < n) && so_rho_below(mine, __uint_as_float((uint32_t)(k_l >> 32)), a.thr);
+            unsigned bal = __ballot_sync(0xFFFFFFFFu, below);
+            /* pair (e, e+1) needs e+1 < n; lane 31's partner is the next chunk's lane 0: handle by
+             * limiting this chunk to 31 pairs and re-starting the next chunk at j0+31 */
+            unsigned pairs = bal & (bal >> 1);
+            unsigned valid = 0u;
+            {
+                uint32_t last_pair = n - 2u - j0;                     /* largest t with (j0+t)+1 < n */
+                valid = last_pair >= 30u ? 0x7FFFFFFFu : ((2u << last_pair) - 1u);
+            }
+            pairs &= valid;
+            if (pairs) {
+                int t = __ffs(pairs) - 1;                              /* first firing j = j0 + t */
+                float Sj = __shfl_sync(0xFFFFFFFFu, mine, t);
+                float mj = __shfl_sync(0xFFFFFFFFu, m_l, t);
+                unsigned long long kj = __shfl_sync(0xFFFFFFFFu, k_l, t);
+                if (lane == 0) {
+                    a.out_n[h] = (int32_t)(j0 + t);                    /* kd2.c:823 */
+                    a.out_m[h] = __fsub_rn(Sj, mj);                    /* kd2.c:816 */
+                    a.out_key[h] = kj;
+                }
+                done = true;
+                break;
+            }
+            /* no hit among pairs t = 0..30: continue at element j0+31 with the mass before it */
+            uint32_t adv = min(31u, n - 1u - j0);
+            run = __shfl_sync(0xFFFFFFFFu, mine, (int)adv - 1);        /* mass after element j0+adv-1 */
+            j = j0 + adv;
+        }
+        if (!done && lane == 0) {
+            /* kd2.c:832: jlast = j (= n-1); mass holds elements 0..n-2 */
+            a.st[h].jlast = j;
+            a.st[h].mass = run;
+            a.next_list[atomicAdd(a.next_n, 1u)] = h;
+        }
+    }
+}
+
+__global__ void k_gen_init(GenState *st, const float *rgtp, int32_t *list, uint32_t *list_n, int nh)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nh) {
+        st[i].ball = rgtp[i]; st[i].mass = 0.0f; st[i].jlast = 0u;     /* kd2.c:743-745 */
+        list[i] = i;
+    }
+    if (i == 0) *list_n = (uint32_t)nh;
+}
+
+/* ============================================================================================
  * host side
  * ============================================================================================ */
 enum {
@@ -1081,6 +1324,17 @@ struct sogpu {
     int32_t last_h;
     bool have_result;
     bool want_d2;
+
+    /* general (unequal-mass) path */
+    GenState *d_gen_state;
+    int32_t *d_gen_list[2], *d_gen_round;
+    unsigned long long *d_seg_n, *d_seg_begin, *d_seg_end;
+    unsigned long long *d_gkeys[2];
+    float *d_gmass[2];
+    size_t gen_cap;                  /* entries of the (key, mass) scratch */
+    void *d_cub_tmp;
+    size_t cub_tmp_bytes;
+    int32_t gen_cap_h;
 
     /* pinned host staging */
     void *h_pin;
@@ -1172,6 +1426,10 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
         e = cudaFuncSetAttribute(k_so_emit<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<32>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_ball_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<32>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_gen_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<256>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_gen_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<256>());
     if (e != cudaSuccess) {
         cudaStreamDestroy(h->own_stream); delete h;
         return set_err(SOGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -1217,6 +1475,10 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     cudaFree(h->d_u64);
     cudaFree(h->d_members);
     cudaFree(h->d_md2);
+    cudaFree(h->d_gen_state); cudaFree(h->d_gen_list[0]); cudaFree(h->d_gen_list[1]); cudaFree(h->d_gen_round);
+    cudaFree(h->d_seg_n); cudaFree(h->d_seg_begin); cudaFree(h->d_seg_end);
+    cudaFree(h->d_gkeys[0]); cudaFree(h->d_gkeys[1]); cudaFree(h->d_gmass[0]); cudaFree(h->d_gmass[1]);
+    cudaFree(h->d_cub_tmp);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->h_members) cudaFreeHost(h->h_members);
     if (h->h_md2) cudaFreeHost(h->h_md2);
@@ -1649,6 +1911,138 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
     return SOGPU_OK;
 }
 
+/* ---- general path driver: rounds over the ball schedule, batches bounded by the scratch size ---- */
+static int gen_scratch(sogpu *h, size_t entries)
+{
+    if (entries <= h->gen_cap) return SOGPU_OK;
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(h->d_gkeys[k]); cudaFree(h->d_gmass[k]);
+        h->d_gkeys[k] = nullptr; h->d_gmass[k] = nullptr;
+    }
+    h->gen_cap = 0;
+    for (int k = 0; k < 2; ++k) {
+        CU(cudaMalloc(&h->d_gkeys[k], entries * sizeof(unsigned long long)));
+        CU(cudaMalloc(&h->d_gmass[k], entries * sizeof(float)));
+    }
+    h->gen_cap = entries;
+    return SOGPU_OK;
+}
+
+static int run_query_general(sogpu *h, const float *d_centers, const float *d_rgtp, int32_t nh, float thr, int32_t nM)
+{
+    cudaStream_t s = h->stream;
+    if (nh > h->gen_cap_h) {
+        cudaFree(h->d_gen_state); cudaFree(h->d_gen_list[0]); cudaFree(h->d_gen_list[1]); cudaFree(h->d_gen_round);
+        cudaFree(h->d_seg_n); cudaFree(h->d_seg_begin); cudaFree(h->d_seg_end);
+        h->gen_cap_h = 0;
+        CU(cudaMalloc(&h->d_gen_state, (size_t)nh * sizeof(GenState)));
+        CU(cudaMalloc(&h->d_gen_list[0], (size_t)nh * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_gen_list[1], (size_t)nh * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_gen_round, (size_t)nh * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_seg_n, (size_t)nh * sizeof(unsigned long long)));
+        CU(cudaMalloc(&h->d_seg_begin, (size_t)nh * sizeof(unsigned long long)));
+        CU(cudaMalloc(&h->d_seg_end, (size_t)nh * sizeof(unsigned long long)));
+        h->gen_cap_h = nh;
+    }
+    /* scratch budget per batch: at least one full-box ball must fit */
+    const size_t budget = (size_t)std::max<int64_t>(h->n, (int64_t)1 << 22);
+    int rc = gen_scratch(h, budget);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(h->d_counters, 0, 16 * sizeof(uint32_t), s));
+    CU(cudaMemsetAsync(h->d_u64, 0, 4 * sizeof(unsigned long long), s));
+    /* counters: [9] list_n(cur) [10] work [11] round_n [12] next_n */
+    k_gen_init<<<(nh + 255) / 256, 256, 0, s>>>(h->d_gen_state, d_rgtp, h->d_gen_list[0], h->d_counters + 9, nh);
+    GenArgs a;
+    memset(&a, 0, sizeof(a));
+    a.g = h->g; a.in = h->d_in; a.centers = d_centers; a.rgtp = d_rgtp; a.st = h->d_gen_state;
+    a.round_list = h->d_gen_round; a.round_n = h->d_counters + 11;
+    a.seg_n = h->d_seg_n; a.seg_begin = h->d_seg_begin;
+    a.thr = thr; a.nM = nM;
+    a.out_n = h->d_out_n; a.out_m = h->d_out_m; a.out_key = h->d_out_key;
+    a.evals = h->d_u64 + 1;
+    std::vector<unsigned long long> seg_n;
+    int cur = 0;
+    uint32_t n_active = (uint32_t)nh;
+    const size_t smem = query_smem_bytes<256>();
+    for (int round = 0; n_active > 0 && round < 4096; ++round) {
+        a.list = h->d_gen_list[cur]; a.list_n = h->d_counters + 9; a.work = h->d_counters + 10;
+        a.next_list = h->d_gen_list[cur ^ 1]; a.next_n = h->d_counters + 12;
+        CU(cudaMemsetAsync(h->d_counters + 10, 0, 3 * sizeof(uint32_t), s));      /* work, round_n, next_n */
+        {
+            ProfScope p(h, KID_QUERY_BLOCK);
+            int ctas = (int)std::min<uint32_t>(n_active, (uint32_t)h->sm_count * 4);
+            k_gen_count<<<ctas, 256, smem, s>>>(a);
+        }
+        uint32_t n_round = 0;
+        CU(cudaMemcpyAsync(&n_round, h->d_counters + 11, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        if (n_round) {
+            seg_n.resize(n_round);
+            CU(cudaMemcpy(seg_n.data(), h->d_seg_n, (size_t)n_round * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            uint32_t s0 = 0;
+            while (s0 < n_round) {
+                size_t tot = 0;
+                uint32_t s1 = s0;
+                while (s1 < n_round && (s1 == s0 || tot + seg_n[s1] <= h->gen_cap)) tot += seg_n[s1++];
+                rc = gen_scratch(h, tot);                     /* a single ball larger than the budget */
+                if (rc) return rc;
+                a.keys = h->d_gkeys[0]; a.mass = h->d_gmass[0];
+                k_gen_offsets<<<1, 1024, 0, s>>>(h->d_seg_n, s0, s1, h->d_seg_begin, h->d_seg_end);
+                {
+                    ProfScope p(h, KID_EMIT_BLOCK);
+                    int ctas = (int)std::min<uint32_t>(s1 - s0, (uint32_t)h->sm_count * 4);
+                    k_gen_emit<<<ctas, 256, smem, s>>>(a, s0, s1);
+                }
+                size_t need = 0;
+                cub::DeviceSegmentedSort::SortPairs(nullptr, need, h->d_gkeys[0], h->d_gkeys[1], h->d_gmass[0],
+                                                    h->d_gmass[1], (int64_t)tot, (int64_t)(s1 - s0), h->d_seg_begin + s0,
+                                                    h->d_seg_end + s0, s);
+                if (need > h->cub_tmp_bytes) {
+                    cudaFree(h->d_cub_tmp); h->d_cub_tmp = nullptr; h->cub_tmp_bytes = 0;
+                    CU(cudaMalloc(&h->d_cub_tmp, need));
+                    h->cub_tmp_bytes = need;
+                }
+                CU(cub::DeviceSegmentedSort::SortPairs(h->d_cub_tmp, need, h->d_gkeys[0], h->d_gkeys[1], h->d_gmass[0],
+                                                       h->d_gmass[1], (int64_t)tot, (int64_t)(s1 - s0),
+                                                       h->d_seg_begin + s0, h->d_seg_end + s0, s));
+                {
+                    ProfScope p(h, KID_QUERY_WARP);
+                    int warps = (int)(s1 - s0);
+                    int ctas = std::min((warps + 7) / 8, h->sm_count * 8);
+                    k_gen_scan<<<ctas, 256, 0, s>>>(a, s0, s1, h->d_gkeys[1], h->d_gmass[1]);
+                }
+                s0 = s1;
+            }
+        }
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(&n_active, h->d_counters + 12, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        CU(cudaMemcpyAsync(h->d_counters + 9, &n_active, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));
+        cur ^= 1;
+    }
+    /* member offsets + lists exactly as on the equal-mass path */
+    QueryArgs q;
+    memset(&q, 0, sizeof(q));
+    q.g = h->g; q.centers = d_centers; q.rgtp = d_rgtp; q.thr = thr; q.nM = nM;
+    q.out_n = h->d_out_n; q.out_m = h->d_out_m; q.out_key = h->d_out_key; q.out_off = h->d_out_off;
+    q.members = h->d_members; q.md2 = h->want_d2 ? h->d_md2 : nullptr; q.member_cap = h->member_cap;
+    q.evals = h->d_u64 + 1; q.flags = h->d_counters + 4; q.mt = h->d_mt;
+    {
+        ProfScope p(h, KID_OFFSETS);
+        k_offsets<<<1, 1024, 0, s>>>(h->d_out_n, nh, h->d_out_off, h->d_u64 + 0, 2048, h->d_esmall,
+                                     h->d_counters + 5, h->d_ebig, h->d_counters + 6);
+    }
+    q.list = h->d_esmall; q.list_n = h->d_counters + 5; q.work_counter = h->d_counters + 7;
+    { ProfScope p(h, KID_EMIT_WARP); launch_persistent<32>(h, k_so_emit<32>, q, nh); }
+    q.list = h->d_ebig; q.list_n = h->d_counters + 6; q.work_counter = h->d_counters + 8;
+    { ProfScope p(h, KID_EMIT_BLOCK); launch_persistent<256>(h, k_so_emit<256>, q, nh); }
+    CU(cudaGetLastError());
+    h->last_h = nh;
+    h->have_result = true;
+    return SOGPU_OK;
+}
+
 static int fetch_stats(sogpu *h)
 {
     unsigned long long u[4];
@@ -1702,6 +2096,16 @@ extern "C" int sogpu_so(sogpu_t *h, const float *centers, const float *rgtp, int
     CU(cudaMemcpyAsync(pm, h->d_out_m, (size_t)nh * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     rc = fetch_stats(h);   /* synchronises the stream */
     if (rc) return rc;
+    if (pn[0] == CODE_UNEQUAL_MASS) {
+        /* mixed particle masses: the rank-only mass table does not apply; run the general path */
+        h->mass_state = 0; h->stats.equal_mass = 0;
+        rc = run_query_general(h, h->d_centers, h->d_rgtp, nh, thr, nM);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(pn, h->d_out_n, (size_t)nh * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(pm, h->d_out_m, (size_t)nh * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        rc = fetch_stats(h);
+        if (rc) return rc;
+    }
     for (int32_t i = 0; i < nh; ++i) {
         int32_t n = pn[i];
         if (n > 0) {
@@ -1711,10 +2115,6 @@ extern "C" int sogpu_so(sogpu_t *h, const float *centers, const float *rgtp, int
         } else if (n == -1 || n == -2 || n == -3) {
             ndelta[i] = 0;
             mvir[i] = rvir[i] = (float)n;                                 /* kd2.c:774-776,793-795,837-838 */
-        } else if (n == CODE_UNEQUAL_MASS) {
-            h->mass_state = 0; h->stats.equal_mass = 0;
-            return set_err(SOGPU_ERR_UNSUPPORTED, "particles have unequal masses: the exact sequential-mass "
-                                                  "path for mixed masses is not implemented yet");
         } else {
             return set_err(SOGPU_ERR_UNSUPPORTED, "halo %d: unsupported particle configuration (code %d)", i, n);
         }
@@ -1731,6 +2131,9 @@ extern "C" int sogpu_finish_host(const int32_t *code_or_n, const float *m, int32
         int32_t n = code_or_n[i];
         if (n > 0) { ndelta[i] = n; mvir[i] = m[i]; rvir[i] = so_rdelta_host(m[i], thr); }
         else if (n == -1 || n == -2 || n == -3) { ndelta[i] = 0; mvir[i] = rvir[i] = (float)n; }
+        else if (n == CODE_UNEQUAL_MASS)
+            return set_err(SOGPU_ERR_UNSUPPORTED, "particles have unequal masses: use sogpu_so (host entry point), "
+                                                  "which switches to the general sequential-mass path");
         else return set_err(SOGPU_ERR_UNSUPPORTED, "halo %d: code %d", i, n);
     }
     return SOGPU_OK;

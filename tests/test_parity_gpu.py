@@ -220,16 +220,32 @@ def test_ball_gather_matches_oracle_ball():
     g.close()
 
 
-def test_unequal_masses_are_rejected_loudly():
-    s = synth.make_snapshot(5000, 3, seed=40, nmax=300)
+def test_unequal_masses_general_path():
+    """Mixed particle masses: the enclosed mass is the SEQUENTIAL fp32 sum in sorted order, so the
+    library switches to the full-sort path; results must still be bit-exact."""
+    s = synth.make_snapshot(40 ** 3, 24, seed=40, nmax=6000)
+    rng = np.random.default_rng(11)
     m = np.full(s.n, s.mass, np.float32)
-    m[::7] *= np.float32(3.0)
+    sel = rng.random(s.n)
+    m[sel < 0.3] *= np.float32(0.37)          # "gas"
+    m[sel > 0.9] *= np.float32(2.9)           # "stars"
+    vc = (rng.random((6, 3)) - 0.5).astype(np.float32)          # -1 / -2 cases
+    centers = np.concatenate([s.centers, vc])
+    rgtp = np.concatenate([s.rgtp, np.full(3, 0.01, np.float32), np.full(3, 0.06, np.float32)])
     g = api.SoGpu()
     g.set_particles(s.pos, m)
     g.build_grid()
+    g.keep_member_d2(True)
+    r = g.so(centers, rgtp, 150.0)
+    off, mem = g.members(sorted=True)
     assert g.stats()["equal_mass"] == 0
-    with pytest.raises(api.SoGpuError):
-        g.so(s.centers, s.rgtp, 200.0)
+    ref = po.Oracle(s.pos, m).so(centers, rgtp, np.float32(150.0), 8)
+    assert_so_equal(r, ref["rvir"], ref["mvir"], ref["ndelta"])
+    assert np.array_equal(off, ref["member_offset"]) and np.array_equal(mem, ref["members"])
+    assert (ref["rvir"] > 0).sum() >= 20 and (ref["rvir"] < 0).sum() >= 3
+    # never-reached threshold on the general path: -3 for everything
+    r3 = g.so(s.centers[:3], s.rgtp[:3], 0.01)
+    assert (r3["rvir"] == -3.0).all()
     g.close()
 
 
