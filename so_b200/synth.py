@@ -174,6 +174,6 @@ def config(idx: int, scale: float = 1.0) -> Snapshot:
     if idx == 4:  # 5a of SURVEY §8d: 512^3, 64 x 1e6 + 436 x 3e4
         n = int(512 ** 3 * scale)
         sizes = np.concatenate([np.full(64, 1.0e6 * scale), np.full(436, 3.0e4 * scale)])
-        return make_snapshot(n, 500, seed=1004, sizes=np.maximum(sizes, 20), nmax=1e6,
+        return make_snapshot(n, 500, seed=1004, sizes=np.maximum(sizes, 20), nmax=1e6, trunc=1.3,
                              name="cfg4_512^3_clusterheavy")
     raise ValueError(idx)
