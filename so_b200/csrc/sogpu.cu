@@ -48,6 +48,9 @@ template <> struct Cfg<32> {   /* warp per halo */
 template <> struct Cfg<256> {  /* block per halo */
     static const int CAP = 4096, WTARGET = 1024, NLEV = 4, GROUPS = 1;
 };
+template <> struct Cfg<1024> { /* one full-SM block per halo: cluster-size halos (>= ~10^5 particles) */
+    static const int CAP = 4096, WTARGET = 2048, NLEV = 4, GROUPS = 1;
+};
 
 /* ============================================================================================
  * error handling
@@ -497,18 +500,20 @@ __device__ __forceinline__ uint32_t bin_hi(const Level &lv, int b)
 /* counts -> exclusive prefix in place; hist[NB] = total.  Returns the total. */
 template <int NT> __device__ __forceinline__ uint32_t scan_hist(uint32_t *hist, uint32_t *tmp, int tid)
 {
-    const int BPT = NB / NT;
+    const int BPT = (NB + NT - 1) / NT;        /* bins per thread (threads beyond NB/BPT idle) */
     uint32_t v[BPT], s = 0;
 #pragma unroll
     for (int k = 0; k < BPT; ++k) {
-        v[k] = hist[tid * BPT + k];
+        int b = tid * BPT + k;
+        v[k] = (b < NB) ? hist[b] : 0u;
         s += v[k];
     }
     uint32_t incl = gscan_incl<NT>(s, tmp, tid);
     uint32_t run = incl - s;
 #pragma unroll
     for (int k = 0; k < BPT; ++k) {
-        hist[tid * BPT + k] = run;
+        int b = tid * BPT + k;
+        if (b < NB) hist[b] = run;
         run += v[k];
     }
     if (tid == NT - 1) hist[NB] = incl;
@@ -884,8 +889,8 @@ template <int NT> static size_t query_smem_bytes()
  * a halo of radius R ~ 1.25 rgtp at mean density thr holds thr*(4pi/3)R^3/m particles, the final
  * ball (1.2 R) about 1.3x that */
 __global__ void k_classify(const float *__restrict__ rgtp, int nh, float thr, const so_mass_table *mt,
-                           float small_max, int32_t *small_list, uint32_t *small_n, int32_t *big_list,
-                           uint32_t *big_n)
+                           float small_max, float huge_min, int32_t *small_list, uint32_t *small_n,
+                           int32_t *big_list, uint32_t *big_n, int32_t *huge_list, uint32_t *huge_n)
 {
     int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= nh) return;
@@ -893,7 +898,8 @@ __global__ void k_classify(const float *__restrict__ rgtp, int nh, float thr, co
     float m = mt->n > 0 ? mt->m : 1.0f;
     float est = 1.3f * thr * 4.18879f * r * r * r / m;
     if (!(est > small_max)) small_list[atomicAdd(small_n, 1u)] = h;
-    else big_list[atomicAdd(big_n, 1u)] = h;
+    else if (!(est > huge_min)) big_list[atomicAdd(big_n, 1u)] = h;
+    else huge_list[atomicAdd(huge_n, 1u)] = h;
 }
 
 /* exclusive scan of max(N_Delta,0) in catalog order -> member offsets; also the emit work lists */
@@ -901,7 +907,8 @@ __global__ void __launch_bounds__(1024) k_offsets(const int32_t *__restrict__ ou
                                                   unsigned long long *__restrict__ out_off,
                                                   unsigned long long *__restrict__ total, int32_t emit_small_max,
                                                   int32_t *small_list, uint32_t *small_n, int32_t *big_list,
-                                                  uint32_t *big_n)
+                                                  uint32_t *big_n, int32_t emit_huge_min = 0x7FFFFFFF,
+                                                  int32_t *huge_list = nullptr, uint32_t *huge_n = nullptr)
 {
     __shared__ unsigned long long ws[32];
     __shared__ unsigned long long carry;
@@ -932,7 +939,8 @@ __global__ void __launch_bounds__(1024) k_offsets(const int32_t *__restrict__ ou
             out_off[i] = incl - v;
             if (n > 0) {
                 if (n <= emit_small_max) small_list[atomicAdd(small_n, 1u)] = i;
-                else big_list[atomicAdd(big_n, 1u)] = i;
+                else if (n < emit_huge_min || !huge_list) big_list[atomicAdd(big_n, 1u)] = i;
+                else huge_list[atomicAdd(huge_n, 1u)] = i;
             }
         }
         __syncthreads();
@@ -1268,11 +1276,13 @@ __global__ void k_gen_init(GenState *st, const float *rgtp, int32_t *list, uint3
  * ============================================================================================ */
 enum {
     KID_LVL_HIST = 0, KID_LVL_SCAN, KID_LVL_PARTITION, KID_BUCKET_SORT, KID_MASS_TABLE, KID_CLASSIFY,
-    KID_QUERY_WARP, KID_QUERY_BLOCK, KID_OFFSETS, KID_EMIT_WARP, KID_EMIT_BLOCK, KID_BALL_GATHER, KID_N
+    KID_QUERY_WARP, KID_QUERY_BLOCK, KID_OFFSETS, KID_EMIT_WARP, KID_EMIT_BLOCK, KID_BALL_GATHER,
+    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_N
 };
 static const char *const g_kernel_names[KID_N] = {
     "k_lvl_hist", "k_scan(3 launches)", "k_lvl_partition", "k_bucket_sort", "k_mass_table", "k_classify",
-    "k_so_query<32>", "k_so_query<256>", "k_offsets", "k_so_emit<32>", "k_so_emit<256>", "k_ball_gather"};
+    "k_so_query<32>", "k_so_query<256>", "k_offsets", "k_so_emit<32>", "k_so_emit<256>", "k_ball_gather",
+    "k_so_query<1024>", "k_so_emit<1024>"};
 
 struct ProfRec { int kid; cudaEvent_t a, b; };
 
@@ -1312,7 +1322,7 @@ struct sogpu {
     /* query buffers */
     int32_t cap_h;
     float *d_centers, *d_rgtp;
-    int32_t *d_small, *d_big, *d_esmall, *d_ebig;
+    int32_t *d_small, *d_big, *d_esmall, *d_ebig, *d_huge, *d_ehuge;
     uint32_t *d_counters;   /* 0 small_n 1 big_n 2 work_small 3 work_big 4 flags 5 esmall_n 6 ebig_n 7 work_es 8 work_eb */
     int32_t *d_out_n;
     float *d_out_m;
@@ -1419,6 +1429,10 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     h->stream = h->own_stream;
     e = cudaFuncSetAttribute(k_so_query<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<256>());
     if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_so_query<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<1024>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_so_emit<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<1024>());
+    if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_so_query<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<32>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_so_emit<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<256>());
@@ -1451,9 +1465,10 @@ static void free_grid(sogpu *h)
 static void free_query(sogpu *h)
 {
     cudaFree(h->d_centers); cudaFree(h->d_rgtp); cudaFree(h->d_small); cudaFree(h->d_big);
-    cudaFree(h->d_esmall); cudaFree(h->d_ebig);
+    cudaFree(h->d_esmall); cudaFree(h->d_ebig); cudaFree(h->d_huge); cudaFree(h->d_ehuge);
     cudaFree(h->d_out_n); cudaFree(h->d_out_m); cudaFree(h->d_out_key); cudaFree(h->d_out_off);
     h->d_centers = h->d_rgtp = nullptr; h->d_small = h->d_big = h->d_esmall = h->d_ebig = nullptr;
+    h->d_huge = h->d_ehuge = nullptr;
     h->d_out_n = nullptr; h->d_out_m = nullptr; h->d_out_key = h->d_out_off = nullptr;
     h->cap_h = 0;
 }
@@ -1820,7 +1835,7 @@ static int fetch_mass_state(sogpu *h)
 static int ensure_query(sogpu *h, int32_t nh)
 {
     if (!h->d_counters) {
-        CU(cudaMalloc(&h->d_counters, 16 * sizeof(uint32_t)));
+        CU(cudaMalloc(&h->d_counters, 24 * sizeof(uint32_t)));
         CU(cudaMalloc(&h->d_u64, 4 * sizeof(unsigned long long)));
     }
     if (nh > h->cap_h) {
@@ -1832,6 +1847,8 @@ static int ensure_query(sogpu *h, int32_t nh)
         CU(cudaMalloc(&h->d_big, (size_t)cap * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_esmall, (size_t)cap * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_ebig, (size_t)cap * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_huge, (size_t)cap * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_ehuge, (size_t)cap * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_out_n, (size_t)cap * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_out_m, (size_t)cap * sizeof(float)));
         CU(cudaMalloc(&h->d_out_key, (size_t)cap * sizeof(unsigned long long)));
@@ -1868,14 +1885,17 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
     if (rc) return rc;
     cudaStream_t s = h->stream;
     h->stats.last_kernel_launches = 0;
-    CU(cudaMemsetAsync(h->d_counters, 0, 16 * sizeof(uint32_t), s));
+    CU(cudaMemsetAsync(h->d_counters, 0, 24 * sizeof(uint32_t), s));
     CU(cudaMemsetAsync(h->d_u64, 0, 4 * sizeof(unsigned long long), s));
 
-    const float small_max = 1024.0f;
+    /* counters: 0 small_n 1 big_n 2 work_small 3 work_big 4 flags 5 esmall_n 6 ebig_n 7 work_es 8 work_eb
+     *           13 huge_n 14 work_huge 15 ehuge_n 16 work_ehuge   (9-12: general path) */
+    const float small_max = 1024.0f, huge_min = 131072.0f;
     {
         ProfScope p(h, KID_CLASSIFY);
-        k_classify<<<(nh + 255) / 256, 256, 0, s>>>(d_rgtp, nh, thr, h->d_mt, small_max, h->d_small,
-                                                    h->d_counters + 0, h->d_big, h->d_counters + 1);
+        k_classify<<<(nh + 255) / 256, 256, 0, s>>>(d_rgtp, nh, thr, h->d_mt, small_max, huge_min, h->d_small,
+                                                    h->d_counters + 0, h->d_big, h->d_counters + 1, h->d_huge,
+                                                    h->d_counters + 13);
     }
     QueryArgs a;
     a.g = h->g;
@@ -1889,6 +1909,9 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
     a.mt = h->d_mt;
     a.defer_list = h->d_big; a.defer_n = h->d_counters + 1;
 
+    /* cluster-size halos first (longest jobs): one 1024-thread CTA each */
+    a.list = h->d_huge; a.list_n = h->d_counters + 13; a.work_counter = h->d_counters + 14;
+    { ProfScope p(h, KID_QUERY_HUGE); launch_persistent<1024>(h, k_so_query<1024>, a, std::min(nh, h->sm_count)); }
     /* warp-per-halo kernel over the small list; halos it cannot finish are appended to the big list */
     a.list = h->d_small; a.list_n = h->d_counters + 0; a.work_counter = h->d_counters + 2;
     { ProfScope p(h, KID_QUERY_WARP); launch_persistent<32>(h, k_so_query<32>, a, nh); }
@@ -1899,8 +1922,11 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
     {
         ProfScope p(h, KID_OFFSETS);
         k_offsets<<<1, 1024, 0, s>>>(h->d_out_n, nh, h->d_out_off, h->d_u64 + 0, 2048, h->d_esmall,
-                                     h->d_counters + 5, h->d_ebig, h->d_counters + 6);
+                                     h->d_counters + 5, h->d_ebig, h->d_counters + 6, 131072, h->d_ehuge,
+                                     h->d_counters + 15);
     }
+    a.list = h->d_ehuge; a.list_n = h->d_counters + 15; a.work_counter = h->d_counters + 16;
+    { ProfScope p(h, KID_EMIT_HUGE); launch_persistent<1024>(h, k_so_emit<1024>, a, std::min(nh, h->sm_count)); }
     a.list = h->d_esmall; a.list_n = h->d_counters + 5; a.work_counter = h->d_counters + 7;
     { ProfScope p(h, KID_EMIT_WARP); launch_persistent<32>(h, k_so_emit<32>, a, nh); }
     a.list = h->d_ebig; a.list_n = h->d_counters + 6; a.work_counter = h->d_counters + 8;
@@ -1948,7 +1974,7 @@ static int run_query_general(sogpu *h, const float *d_centers, const float *d_rg
     const size_t budget = (size_t)std::max<int64_t>(h->n, (int64_t)1 << 22);
     int rc = gen_scratch(h, budget);
     if (rc) return rc;
-    CU(cudaMemsetAsync(h->d_counters, 0, 16 * sizeof(uint32_t), s));
+    CU(cudaMemsetAsync(h->d_counters, 0, 24 * sizeof(uint32_t), s));
     CU(cudaMemsetAsync(h->d_u64, 0, 4 * sizeof(unsigned long long), s));
     /* counters: [9] list_n(cur) [10] work [11] round_n [12] next_n */
     k_gen_init<<<(nh + 255) / 256, 256, 0, s>>>(h->d_gen_state, d_rgtp, h->d_gen_list[0], h->d_counters + 9, nh);
@@ -2046,14 +2072,14 @@ static int run_query_general(sogpu *h, const float *d_centers, const float *d_rg
 static int fetch_stats(sogpu *h)
 {
     unsigned long long u[4];
-    uint32_t c[16];
+    uint32_t c[24];
     CU(cudaMemcpyAsync(u, h->d_u64, sizeof(u), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(c, h->d_counters, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->stats.last_members = (int64_t)u[0];
     h->stats.last_evals_first = (int64_t)u[1];
     h->stats.last_evals = (int64_t)(u[1] + u[2]);
-    h->stats.last_deferred = (int32_t)(c[1] + c[0]) - h->last_h;   /* halos listed twice = deferred */
+    h->stats.last_deferred = (int32_t)(c[1] + c[0] + c[13]) - h->last_h;   /* halos listed twice = deferred */
     if (c[4] & 1u) return set_err(SOGPU_ERR_NOMEM, "member buffer overflow (%llu > %llu)", u[0], h->member_cap);
     if (c[4] & 2u) return set_err(SOGPU_ERR_UNSUPPORTED, "internal: member emission count mismatch");
     return SOGPU_OK;
@@ -2264,7 +2290,7 @@ extern "C" int sogpu_ball_gather_batch(sogpu_t *h, const float *centers, const f
     CU(cudaMemcpyAsync(h->d_rgtp, pb, (size_t)nh * sizeof(float), cudaMemcpyHostToDevice, s));
     h->stats.last_kernel_launches = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        CU(cudaMemsetAsync(h->d_counters, 0, 16 * sizeof(uint32_t), s));
+        CU(cudaMemsetAsync(h->d_counters, 0, 24 * sizeof(uint32_t), s));
         CU(cudaMemsetAsync(h->d_u64, 0, 4 * sizeof(unsigned long long), s));
         QueryArgs a;
         memset(&a, 0, sizeof(a));
