@@ -132,6 +132,33 @@ __device__ __forceinline__ uint32_t find_parent(const uint32_t *__restrict__ pst
     return lo;
 }
 
+/* block-wide version: NT threads probe NT candidate parents per step (one or two dependent loads
+ * instead of log2(n_parents)); result broadcast through shared memory.  All threads must call. */
+template <int NT>
+__device__ __forceinline__ uint32_t find_parent_block(const uint32_t *__restrict__ pstart, uint32_t n_parents,
+                                                      uint32_t pos, uint32_t *sh_res)
+{
+    uint32_t lo = 0, hi = n_parents;            /* answer in [lo, hi) */
+    while (hi - lo > 1) {
+        uint32_t span = hi - lo, step = (span + NT - 1) / NT;
+        uint32_t cand = lo + threadIdx.x * step;
+        /* thread owns [cand, cand+step): the answer p satisfies pstart[p] <= pos, and is the LAST such p */
+        bool mine = false;
+        if (cand < hi) {
+            uint32_t nxt = cand + step < hi ? cand + step : hi;
+            bool ge = __ldg(pstart + cand) <= pos;
+            bool nx = (nxt < n_parents) ? (__ldg(pstart + nxt) <= pos) : false;
+            mine = ge && !nx;
+        }
+        __syncthreads();
+        if (mine) { sh_res[0] = cand; sh_res[1] = cand + step < hi ? cand + step : hi; }
+        __syncthreads();
+        lo = sh_res[0]; hi = sh_res[1];
+    }
+    __syncthreads();
+    return lo;
+}
+
 /* digit histogram of every parent bucket; level 0 computes keys from positions (and mass min/max) */
 template <bool FIRST>
 __global__ void __launch_bounds__(256) k_lvl_hist(const float4 *__restrict__ in4, const uint32_t *__restrict__ inkey,
@@ -140,6 +167,7 @@ __global__ void __launch_bounds__(256) k_lvl_hist(const float4 *__restrict__ in4
                                                   uint32_t *__restrict__ mass_minmax)
 {
     __shared__ uint32_t sh[LVL_CMAX];
+    __shared__ uint32_t sres[2];
     const int C = 1 << lv.db;
     const uint32_t cmask = (uint32_t)C - 1u;
     uint32_t mn = 0xFFFFFFFFu, mx = 0u;
@@ -148,7 +176,7 @@ __global__ void __launch_bounds__(256) k_lvl_hist(const float4 *__restrict__ in4
         uint32_t pos = (uint32_t)(tile * LVL_T);
         const uint32_t tend = (uint32_t)min((int64_t)n, tile * LVL_T + LVL_T);
         while (pos < tend) {
-            uint32_t p = FIRST ? 0u : find_parent(pstart, lv.n_parents, pos);
+            uint32_t p = FIRST ? 0u : find_parent_block<256>(pstart, lv.n_parents, pos, sres);
             uint32_t send = FIRST ? tend : min(tend, __ldg(pstart + p + 1));
             for (int c = threadIdx.x; c < C; c += 256) sh[c] = 0u;
             __syncthreads();
@@ -185,11 +213,15 @@ __global__ void __launch_bounds__(256) k_lvl_hist(const float4 *__restrict__ in4
 
 /* tile-wise counting sort by digit, staged through shared memory so that each child bucket
  * receives one contiguous run per tile segment */
+#define LVL_THREADS 512
 template <bool FIRST, bool WRITE_KEY>
-__global__ void __launch_bounds__(256) k_lvl_partition(const float4 *__restrict__ in4, const uint32_t *__restrict__ inkey,
-                                                       int64_t n, GridDev g, LevelDesc lv,
-                                                       const uint32_t *__restrict__ pstart, uint32_t *__restrict__ cursor,
-                                                       float4 *__restrict__ out4, uint32_t *__restrict__ outkey)
+__global__ void __launch_bounds__(LVL_THREADS, 2) k_lvl_partition(const float4 *__restrict__ in4,
+                                                                  const uint32_t *__restrict__ inkey, int64_t n,
+                                                                  GridDev g, LevelDesc lv,
+                                                                  const uint32_t *__restrict__ pstart,
+                                                                  uint32_t *__restrict__ cursor,
+                                                                  float4 *__restrict__ out4,
+                                                                  uint32_t *__restrict__ outkey)
 {
     extern __shared__ __align__(16) unsigned char raw[];
     float4 *s4 = reinterpret_cast<float4 *>(raw);
@@ -197,7 +229,7 @@ __global__ void __launch_bounds__(256) k_lvl_partition(const float4 *__restrict_
     uint16_t *sd = reinterpret_cast<uint16_t *>(sk + LVL_T);
     uint16_t *sr = sd + LVL_T;
     uint16_t *perm = sr + LVL_T;
-    __shared__ uint32_t scnt[LVL_CMAX], soff[LVL_CMAX], sbase[LVL_CMAX], ws[8];
+    __shared__ uint32_t scnt[LVL_CMAX], soff[LVL_CMAX], sbase[LVL_CMAX], ws[LVL_THREADS / 32], sres[2];
     const int C = 1 << lv.db;
     const uint32_t cmask = (uint32_t)C - 1u;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -206,31 +238,43 @@ __global__ void __launch_bounds__(256) k_lvl_partition(const float4 *__restrict_
         uint32_t pos = (uint32_t)(tile * LVL_T);
         const uint32_t tend = (uint32_t)min((int64_t)n, tile * LVL_T + LVL_T);
         while (pos < tend) {
-            const uint32_t p = FIRST ? 0u : find_parent(pstart, lv.n_parents, pos);
+            const uint32_t p = FIRST ? 0u : find_parent_block<LVL_THREADS>(pstart, lv.n_parents, pos, sres);
             const uint32_t send = FIRST ? tend : min(tend, __ldg(pstart + p + 1));
             const int cnt = (int)(send - pos);
-            for (int c = t; c < C; c += 256) scnt[c] = 0u;
+            if (t < C) scnt[t] = 0u;
             __syncthreads();
-#pragma unroll 4
-            for (int i = t; i < cnt; i += 256) {
-                float4 q = ld_stream(in4 + pos + i);
-                uint32_t key;
-                if (FIRST) {
-                    key = cell_key(q, g);
-                    q.w = __int_as_float((int)(pos + i));      /* payload: original index */
-                } else {
-                    key = __ldg(inkey + pos + i);
+            {   /* all loads of the tile segment are issued before the first shared-memory atomic */
+                constexpr int IT = LVL_T / LVL_THREADS;
+                float4 q[IT];
+                uint32_t key[IT];
+#pragma unroll
+                for (int k = 0; k < IT; ++k) {
+                    int i = t + k * LVL_THREADS;
+                    if (i < cnt) {
+                        q[k] = ld_stream(in4 + pos + i);
+                        if (!FIRST) key[k] = __ldg(inkey + pos + i);
+                    }
                 }
-                uint32_t d = (key >> lv.shift) & cmask;
-                s4[i] = q;
-                sk[i] = key;
-                sd[i] = (uint16_t)d;
-                sr[i] = (uint16_t)atomicAdd(&scnt[d], 1u);
+#pragma unroll
+                for (int k = 0; k < IT; ++k) {
+                    int i = t + k * LVL_THREADS;
+                    if (i < cnt) {
+                        if (FIRST) {
+                            key[k] = cell_key(q[k], g);
+                            q[k].w = __int_as_float((int)(pos + i));      /* payload: original index */
+                        }
+                        uint32_t d = (key[k] >> lv.shift) & cmask;
+                        s4[i] = q[k];
+                        sk[i] = key[k];
+                        sd[i] = (uint16_t)d;
+                        sr[i] = (uint16_t)atomicAdd(&scnt[d], 1u);
+                    }
+                }
             }
             __syncthreads();
-            {   /* exclusive scan of the C counts (C <= 512: two per thread) + run reservation */
-                uint32_t c0 = (2 * t < C) ? scnt[2 * t] : 0u, c1 = (2 * t + 1 < C) ? scnt[2 * t + 1] : 0u;
-                uint32_t x = c0 + c1;
+            {   /* exclusive scan of the C counts (C <= 512: one per thread) + run reservation */
+                uint32_t c0 = (t < C) ? scnt[t] : 0u;
+                uint32_t x = c0;
                 for (int o = 1; o < 32; o <<= 1) {
                     uint32_t u = __shfl_up_sync(0xFFFFFFFFu, x, o);
                     if (lane >= o) x += u;
@@ -239,20 +283,15 @@ __global__ void __launch_bounds__(256) k_lvl_partition(const float4 *__restrict_
                 __syncthreads();
                 uint32_t off = 0;
                 for (int k = 0; k < w; ++k) off += ws[k];
-                uint32_t e0 = off + x - c0 - c1;
-                if (2 * t < C) {
-                    soff[2 * t] = e0;
-                    sbase[2 * t] = c0 ? atomicAdd(&cursor[(size_t)p * C + 2 * t], c0) : 0u;
-                }
-                if (2 * t + 1 < C) {
-                    soff[2 * t + 1] = e0 + c0;
-                    sbase[2 * t + 1] = c1 ? atomicAdd(&cursor[(size_t)p * C + 2 * t + 1], c1) : 0u;
+                if (t < C) {
+                    soff[t] = off + x - c0;
+                    sbase[t] = c0 ? atomicAdd(&cursor[(size_t)p * C + t], c0) : 0u;
                 }
             }
             __syncthreads();
-            for (int i = t; i < cnt; i += 256) perm[soff[sd[i]] + sr[i]] = (uint16_t)i;
+            for (int i = t; i < cnt; i += LVL_THREADS) perm[soff[sd[i]] + sr[i]] = (uint16_t)i;
             __syncthreads();
-            for (int slot = t; slot < cnt; slot += 256) {
+            for (int slot = t; slot < cnt; slot += LVL_THREADS) {
                 int i = perm[slot];
                 uint32_t d = sd[i];
                 uint32_t dst = sbase[d] + ((uint32_t)slot - soff[d]);
@@ -269,9 +308,9 @@ __global__ void __launch_bounds__(256) k_lvl_partition(const float4 *__restrict_
 
 #define BKT_CAP 3072         /* particles staged in shared memory; larger buckets take the slow path */
 #define BKT_CELLS 4096       /* cells per final bucket (<=)                                          */
-#define BKT_THREADS 256
+#define BKT_THREADS 512
 
-__global__ void __launch_bounds__(BKT_THREADS) k_bucket_sort(const float4 *__restrict__ in4, GridDev g, int cell_bits,
+__global__ void __launch_bounds__(BKT_THREADS, 2) k_bucket_sort(const float4 *__restrict__ in4, GridDev g, int cell_bits,
                                                              uint32_t n_buckets, const uint32_t *__restrict__ bstart,
                                                              float4 *__restrict__ sorted, uint32_t *__restrict__ ce,
                                                              int first_pass_input_is_raw)

@@ -1289,6 +1289,9 @@ struct ProfRec { int kid; cudaEvent_t a, b; };
 struct sogpu {
     int device;
     cudaStream_t own_stream, stream;
+    cudaStream_t aux[2];             /* side streams: the three halo-size classes run concurrently */
+    cudaStream_t launch_stream;      /* where ProfScope / launch_persistent currently enqueue */
+    cudaEvent_t ev_fork, ev_join[2];
     float ppc;                       /* target particles per cell */
     int pack_threads;
 
@@ -1322,7 +1325,7 @@ struct sogpu {
     /* query buffers */
     int32_t cap_h;
     float *d_centers, *d_rgtp;
-    int32_t *d_small, *d_big, *d_esmall, *d_ebig, *d_huge, *d_ehuge;
+    int32_t *d_small, *d_big, *d_esmall, *d_ebig, *d_huge, *d_ehuge, *d_defer;
     uint32_t *d_counters;   /* 0 small_n 1 big_n 2 work_small 3 work_big 4 flags 5 esmall_n 6 ebig_n 7 work_es 8 work_eb */
     int32_t *d_out_n;
     float *d_out_m;
@@ -1379,12 +1382,12 @@ struct ProfScope {   /* brackets one (group of) kernel launch(es) with events wh
         if (!on) return;
         h->prof_bytes[kid] += alg_bytes;
         r.kid = kid; r.a = prof_event(h); r.b = prof_event(h);
-        cudaEventRecord(r.a, h->stream);
+        cudaEventRecord(r.a, h->launch_stream);
     }
     ~ProfScope()
     {
         if (!on) return;
-        cudaEventRecord(r.b, h->stream);
+        cudaEventRecord(r.b, h->launch_stream);
         h->prof_pending.push_back(r);
     }
 };
@@ -1426,8 +1429,14 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     h->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return set_err(SOGPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
-    h->stream = h->own_stream;
-    e = cudaFuncSetAttribute(k_so_query<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<256>());
+    h->stream = h->launch_stream = h->own_stream;
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        e = cudaStreamCreateWithFlags(&h->aux[k], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_so_query<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<256>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_so_query<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<1024>());
     if (e == cudaSuccess)
@@ -1465,10 +1474,10 @@ static void free_grid(sogpu *h)
 static void free_query(sogpu *h)
 {
     cudaFree(h->d_centers); cudaFree(h->d_rgtp); cudaFree(h->d_small); cudaFree(h->d_big);
-    cudaFree(h->d_esmall); cudaFree(h->d_ebig); cudaFree(h->d_huge); cudaFree(h->d_ehuge);
+    cudaFree(h->d_esmall); cudaFree(h->d_ebig); cudaFree(h->d_huge); cudaFree(h->d_ehuge); cudaFree(h->d_defer);
     cudaFree(h->d_out_n); cudaFree(h->d_out_m); cudaFree(h->d_out_key); cudaFree(h->d_out_off);
     h->d_centers = h->d_rgtp = nullptr; h->d_small = h->d_big = h->d_esmall = h->d_ebig = nullptr;
-    h->d_huge = h->d_ehuge = nullptr;
+    h->d_huge = h->d_ehuge = h->d_defer = nullptr;
     h->d_out_n = nullptr; h->d_out_m = nullptr; h->d_out_key = h->d_out_off = nullptr;
     h->cap_h = 0;
 }
@@ -1499,6 +1508,11 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     if (h->h_md2) cudaFreeHost(h->h_md2);
     for (auto &r : h->prof_pending) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : h->prof_pool) cudaEventDestroy(e);
+    for (int k = 0; k < 2; ++k) {
+        if (h->aux[k]) cudaStreamDestroy(h->aux[k]);
+        if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -1506,7 +1520,7 @@ extern "C" void sogpu_destroy(sogpu_t *h)
 extern "C" int sogpu_set_stream(sogpu_t *h, void *s)
 {
     if (!h) return set_err(SOGPU_ERR_ARG, "NULL handle");
-    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    h->stream = h->launch_stream = s ? (cudaStream_t)s : h->own_stream;
     return SOGPU_OK;
 }
 
@@ -1792,10 +1806,10 @@ extern "C" int sogpu_build_grid(sogpu_t *h)
         }
         {
             ProfScope p(h, KID_LVL_PARTITION, ((l ? 20.0 : 16.0) + 16.0 + (last ? 0.0 : 4.0)) * N);
-            if (l == 0 && !last) k_lvl_partition<true, true><<<part_grid, 256, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key);
-            else if (l == 0) k_lvl_partition<true, false><<<part_grid, 256, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key);
-            else if (!last) k_lvl_partition<false, true><<<part_grid, 256, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key);
-            else k_lvl_partition<false, false><<<part_grid, 256, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key);
+            if (l == 0 && !last) k_lvl_partition<true, true><<<part_grid, LVL_THREADS, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key);
+            else if (l == 0) k_lvl_partition<true, false><<<part_grid, LVL_THREADS, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key);
+            else if (!last) k_lvl_partition<false, true><<<part_grid, LVL_THREADS, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key);
+            else k_lvl_partition<false, false><<<part_grid, LVL_THREADS, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key);
         }
         src = dst;
         src_key = dst_key;
@@ -1849,6 +1863,7 @@ static int ensure_query(sogpu *h, int32_t nh)
         CU(cudaMalloc(&h->d_ebig, (size_t)cap * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_huge, (size_t)cap * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_ehuge, (size_t)cap * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_defer, (size_t)cap * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_out_n, (size_t)cap * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_out_m, (size_t)cap * sizeof(float)));
         CU(cudaMalloc(&h->d_out_key, (size_t)cap * sizeof(unsigned long long)));
@@ -1871,7 +1886,7 @@ static void launch_persistent(sogpu *h, K kernel, const QueryArgs &a, int nh, Ex
     int ctas = h->sm_count * 4;
     int need = (nh + Cfg<NT>::GROUPS - 1) / Cfg<NT>::GROUPS;
     if (need < ctas) ctas = std::max(need, 1);
-    kernel<<<ctas, NT * Cfg<NT>::GROUPS, query_smem_bytes<NT>(), h->stream>>>(a, extra...);
+    kernel<<<ctas, NT * Cfg<NT>::GROUPS, query_smem_bytes<NT>(), h->launch_stream>>>(a, extra...);
 }
 
 /* enqueue query + member emission for nh halos whose centers/rgtp are on the device */
@@ -1890,7 +1905,7 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
 
     /* counters: 0 small_n 1 big_n 2 work_small 3 work_big 4 flags 5 esmall_n 6 ebig_n 7 work_es 8 work_eb
      *           13 huge_n 14 work_huge 15 ehuge_n 16 work_ehuge   (9-12: general path) */
-    const float small_max = 1024.0f, huge_min = 131072.0f;
+    const float small_max = 1024.0f, huge_min = 16384.0f;
     {
         ProfScope p(h, KID_CLASSIFY);
         k_classify<<<(nh + 255) / 256, 256, 0, s>>>(d_rgtp, nh, thr, h->d_mt, small_max, huge_min, h->d_small,
@@ -1907,30 +1922,53 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
     a.evals = h->d_u64 + 1;
     a.flags = h->d_counters + 4;
     a.mt = h->d_mt;
-    a.defer_list = h->d_big; a.defer_n = h->d_counters + 1;
+    a.defer_list = h->d_defer; a.defer_n = h->d_counters + 17;
 
-    /* cluster-size halos first (longest jobs): one 1024-thread CTA each */
+    /* the three size classes are independent: run them concurrently (main + two side streams) */
+    CU(cudaEventRecord(h->ev_fork, s));
+    CU(cudaStreamWaitEvent(h->aux[0], h->ev_fork, 0));
+    CU(cudaStreamWaitEvent(h->aux[1], h->ev_fork, 0));
+    /* cluster-size halos: one 1024-thread CTA each */
+    h->launch_stream = h->aux[0];
     a.list = h->d_huge; a.list_n = h->d_counters + 13; a.work_counter = h->d_counters + 14;
     { ProfScope p(h, KID_QUERY_HUGE); launch_persistent<1024>(h, k_so_query<1024>, a, std::min(nh, h->sm_count)); }
-    /* warp-per-halo kernel over the small list; halos it cannot finish are appended to the big list */
-    a.list = h->d_small; a.list_n = h->d_counters + 0; a.work_counter = h->d_counters + 2;
-    { ProfScope p(h, KID_QUERY_WARP); launch_persistent<32>(h, k_so_query<32>, a, nh); }
-    /* block-per-halo kernel over the big list (+ deferred) */
+    CU(cudaEventRecord(h->ev_join[0], h->aux[0]));
+    /* mid-size halos: one 256-thread CTA each */
+    h->launch_stream = h->aux[1];
     a.list = h->d_big; a.list_n = h->d_counters + 1; a.work_counter = h->d_counters + 3;
     { ProfScope p(h, KID_QUERY_BLOCK); launch_persistent<256>(h, k_so_query<256>, a, nh); }
-    /* member offsets in catalog order, then the member lists */
+    CU(cudaEventRecord(h->ev_join[1], h->aux[1]));
+    /* small halos: one warp each; the few it cannot finish go to a CTA kernel right behind it */
+    h->launch_stream = s;
+    a.list = h->d_small; a.list_n = h->d_counters + 0; a.work_counter = h->d_counters + 2;
+    { ProfScope p(h, KID_QUERY_WARP); launch_persistent<32>(h, k_so_query<32>, a, nh); }
+    a.list = h->d_defer; a.list_n = h->d_counters + 17; a.work_counter = h->d_counters + 18;
+    { ProfScope p(h, KID_QUERY_BLOCK); launch_persistent<256>(h, k_so_query<256>, a, 64); }
+    CU(cudaStreamWaitEvent(s, h->ev_join[0], 0));
+    CU(cudaStreamWaitEvent(s, h->ev_join[1], 0));
+    /* member offsets in catalog order, then the member lists (again three classes side by side) */
     {
         ProfScope p(h, KID_OFFSETS);
         k_offsets<<<1, 1024, 0, s>>>(h->d_out_n, nh, h->d_out_off, h->d_u64 + 0, 2048, h->d_esmall,
                                      h->d_counters + 5, h->d_ebig, h->d_counters + 6, 131072, h->d_ehuge,
                                      h->d_counters + 15);
     }
+    CU(cudaEventRecord(h->ev_fork, s));
+    CU(cudaStreamWaitEvent(h->aux[0], h->ev_fork, 0));
+    CU(cudaStreamWaitEvent(h->aux[1], h->ev_fork, 0));
+    h->launch_stream = h->aux[0];
     a.list = h->d_ehuge; a.list_n = h->d_counters + 15; a.work_counter = h->d_counters + 16;
     { ProfScope p(h, KID_EMIT_HUGE); launch_persistent<1024>(h, k_so_emit<1024>, a, std::min(nh, h->sm_count)); }
-    a.list = h->d_esmall; a.list_n = h->d_counters + 5; a.work_counter = h->d_counters + 7;
-    { ProfScope p(h, KID_EMIT_WARP); launch_persistent<32>(h, k_so_emit<32>, a, nh); }
+    CU(cudaEventRecord(h->ev_join[0], h->aux[0]));
+    h->launch_stream = h->aux[1];
     a.list = h->d_ebig; a.list_n = h->d_counters + 6; a.work_counter = h->d_counters + 8;
     { ProfScope p(h, KID_EMIT_BLOCK); launch_persistent<256>(h, k_so_emit<256>, a, nh); }
+    CU(cudaEventRecord(h->ev_join[1], h->aux[1]));
+    h->launch_stream = s;
+    a.list = h->d_esmall; a.list_n = h->d_counters + 5; a.work_counter = h->d_counters + 7;
+    { ProfScope p(h, KID_EMIT_WARP); launch_persistent<32>(h, k_so_emit<32>, a, nh); }
+    CU(cudaStreamWaitEvent(s, h->ev_join[0], 0));
+    CU(cudaStreamWaitEvent(s, h->ev_join[1], 0));
     CU(cudaGetLastError());
     h->last_h = nh;
     h->have_result = true;
@@ -2079,7 +2117,7 @@ static int fetch_stats(sogpu *h)
     h->stats.last_members = (int64_t)u[0];
     h->stats.last_evals_first = (int64_t)u[1];
     h->stats.last_evals = (int64_t)(u[1] + u[2]);
-    h->stats.last_deferred = (int32_t)(c[1] + c[0] + c[13]) - h->last_h;   /* halos listed twice = deferred */
+    h->stats.last_deferred = (int32_t)c[17];
     if (c[4] & 1u) return set_err(SOGPU_ERR_NOMEM, "member buffer overflow (%llu > %llu)", u[0], h->member_cap);
     if (c[4] & 2u) return set_err(SOGPU_ERR_UNSUPPORTED, "internal: member emission count mismatch");
     return SOGPU_OK;
