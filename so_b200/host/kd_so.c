@@ -302,9 +302,32 @@ void kdSO(KD kd, float rhovir, int nSmooth)
     (void)nSmooth;                 /* sized the reference's neighbour list (smInit); nothing to size here */
     if (h == 0) return;
     if (kd->bPot) {
-        fprintf(stderr, "ERROR: -pot (centre on the minimum-potential particle, kd2.c:749-761) is not "
-                        "implemented in the GPU build; use -stat.\n");
-        exit(1);
+        /* -pot (kd2.c:749-761): re-centre every group on the particle of lowest potential inside
+         * its .gtp radius.  One batched GPU gather of the fRgtp balls; the arg-min runs on the host
+         * over lists in ascending (r^2, index) order (the reference scans kd-tree walk order; only
+         * exactly equal potentials could be resolved differently). */
+        float *pc = (float *)malloc((size_t)h * 3 * sizeof(float));
+        float *pb = (float *)malloc((size_t)h * sizeof(float));
+        int64_t *poff = (int64_t *)malloc(((size_t)h + 1) * sizeof(int64_t));
+        const int32_t *pi;
+        const float *pd;
+        int64_t k;
+        assert(pc && pb && poff);
+        for (i = 0; i < h; ++i) {
+            memcpy(pc + 3 * i, kd->grps[i].pos, 3 * sizeof(float));
+            pb[i] = kd->grps[i].fRgtp * kd->grps[i].fRgtp;                 /* kd2.c:750 */
+        }
+        if (sogpu_ball_gather_batch(kd->gpu, pc, pb, h)) die_gpu("kdSO (-pot gather)");
+        if (sogpu_members(kd->gpu, poff, &pi, &pd, 1)) die_gpu("kdSO (-pot lists)");
+        for (i = 0; i < h; ++i) {
+            if (poff[i + 1] > poff[i]) {
+                int32_t best = pi[poff[i]];
+                for (k = poff[i] + 1; k < poff[i + 1]; ++k)
+                    if (kd->p.fPhi[pi[k]] < kd->p.fPhi[best]) best = pi[k];
+                memcpy(kd->grps[i].pos, kd->p.r + 3 * (size_t)best, 3 * sizeof(float));   /* kd2.c:760 */
+            }
+        }
+        free(pc); free(pb); free(poff);
     }
     centers = (float *)malloc((size_t)h * 3 * sizeof(float));
     rgtp = (float *)malloc((size_t)h * sizeof(float));
@@ -319,7 +342,7 @@ void kdSO(KD kd, float rhovir, int nSmooth)
     assert(centers && rgtp && rvir && mvir && masses && ndelta && off && order && do_vcirc && slot_of_index);
     for (i = 0; i <= kd->nInGTP + 1; ++i) slot_of_index[i] = -1;
     for (i = 0; i < h; ++i) {
-        memcpy(centers + 3 * i, kd->grps[i].pos, 3 * sizeof(float));
+        memcpy(centers + 3 * i, kd->grps[i].pos, 3 * sizeof(float));   /* (after -pot re-centring) */
         rgtp[i] = kd->grps[i].fRgtp;
         masses[i + 1] = kd->grps[i].fGTPMass;
         slot_of_index[kd->grps[i].index] = i;

@@ -157,3 +157,35 @@ def test_cli_gas_dark_star_snapshot_live(tmp_path):
         for a, b, good in zip(pa, pb, ok):
             if good:
                 np.testing.assert_allclose(a, b, rtol=2e-5, err_msg=ext)
+
+
+@pytest.mark.skipif(not po.ref_available("so_ref"), reason="reference binary not built")
+def test_cli_pot_recentring_live(tmp_path):
+    """-pot: centre each group on its minimum-potential particle (kd2.c:749-761)."""
+    s = synth.make_snapshot(36 ** 3, 20, seed=79, nmax=3000)
+    rng = np.random.default_rng(3)
+    # potential: deepest at the true halo centres (unique minimum per group) + noise
+    phi = rng.normal(size=s.n).astype(np.float32)
+    for c, r in zip(s.centers, s.r200):
+        d = s.pos - c
+        d -= np.rint(d)
+        phi -= (5.0 / (1.0 + (np.sqrt((d * d).sum(1)) / (0.2 * r)) ** 2)).astype(np.float32)
+    snap, gtp = str(tmp_path / "s.tipsy"), str(tmp_path / "h.gtp")
+    tipsy.write_tipsy(snap, s.time, dark=tipsy.dark_from_arrays(s.pos, s.mass, phi=phi))
+    tipsy.write_gtp(gtp, s.time, s.centers, s.rgtp, s.gtp_mass)
+    flags = ["-delta", "200", "-grp", "-gtp", "-pot"]
+    outs = {}
+    for who, exe in (("ref", os.path.join(po.REF_DIR, "so_ref")), ("ours", SO)):
+        out = str(tmp_path / who)
+        with open(snap, "rb") as fin:
+            r = subprocess.run([exe, "-i", gtp, "-o", out] + flags, stdin=fin, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[who] = out
+    assert open(outs["ours"] + ".sogrp").read() == open(outs["ref"] + ".sogrp").read()
+    _, ra = tipsy.parse_sovcirc(outs["ours"] + ".sovcirc")
+    _, rb = tipsy.parse_sovcirc(outs["ref"] + ".sovcirc")
+    compare_rows(ra, np.array(rb))
+    a = np.frombuffer(open(outs["ours"] + ".sogtp", "rb").read(), np.uint8)[32:].view(np.float32).reshape(-1, 11)
+    b = np.frombuffer(open(outs["ref"] + ".sogtp", "rb").read(), np.uint8)[32:].view(np.float32).reshape(-1, 11)
+    assert a[:, [0, 1, 2, 3, 8, 9]].tobytes() == b[:, [0, 1, 2, 3, 8, 9]].tobytes()     # incl. the new centres
+    assert not np.array_equal(a[:, 1:4], s.centers)                                    # centres did move
