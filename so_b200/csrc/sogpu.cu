@@ -1261,14 +1261,23 @@ __global__ void __launch_bounds__(256) k_gen_scan(const __grid_constant__ GenArg
     }
 }
 
-__global__ void k_gen_init(GenState *st, const float *rgtp, int32_t *list, uint32_t *list_n, int nh)
+__global__ void k_gen_init(GenState *st, const float *rgtp, int32_t *list, uint32_t *list_n, int n,
+                           const int32_t *subset)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nh) {
-        st[i].ball = rgtp[i]; st[i].mass = 0.0f; st[i].jlast = 0u;     /* kd2.c:743-745 */
-        list[i] = i;
+    if (i < n) {
+        int h = subset ? subset[i] : i;
+        st[h].ball = rgtp[h]; st[h].mass = 0.0f; st[h].jlast = 0u;     /* kd2.c:743-745 */
+        list[i] = h;
     }
-    if (i == 0) *list_n = (uint32_t)nh;
+    if (i == 0) *list_n = (uint32_t)n;
+}
+
+/* halos whose result is `code`, as a compact list */
+__global__ void k_select_code(const int32_t *out_n, int nh, int32_t code, int32_t *list, uint32_t *list_n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nh && out_n[i] == code) list[atomicAdd(list_n, 1u)] = i;
 }
 
 /* ============================================================================================
@@ -1337,6 +1346,7 @@ struct sogpu {
     int32_t last_h;
     bool have_result;
     bool want_d2;
+    bool member_overflow;
 
     /* general (unequal-mass) path */
     GenState *d_gen_state;
@@ -1992,7 +2002,11 @@ static int gen_scratch(sogpu *h, size_t entries)
     return SOGPU_OK;
 }
 
-static int run_query_general(sogpu *h, const float *d_centers, const float *d_rgtp, int32_t nh, float thr, int32_t nM)
+static int emit_members(sogpu *h, const float *d_centers, const float *d_rgtp, int32_t nh, float thr, int32_t nM);
+
+/* subset == nullptr: all nh halos; else the n_subset halo ids in the device array `subset` */
+static int run_query_general(sogpu *h, const float *d_centers, const float *d_rgtp, int32_t nh, float thr, int32_t nM,
+                             const int32_t *subset = nullptr, uint32_t n_subset = 0)
 {
     cudaStream_t s = h->stream;
     if (nh > h->gen_cap_h) {
@@ -2012,10 +2026,14 @@ static int run_query_general(sogpu *h, const float *d_centers, const float *d_rg
     const size_t budget = (size_t)std::max<int64_t>(h->n, (int64_t)1 << 22);
     int rc = gen_scratch(h, budget);
     if (rc) return rc;
-    CU(cudaMemsetAsync(h->d_counters, 0, 24 * sizeof(uint32_t), s));
-    CU(cudaMemsetAsync(h->d_u64, 0, 4 * sizeof(unsigned long long), s));
+    if (!subset) {
+        CU(cudaMemsetAsync(h->d_counters, 0, 24 * sizeof(uint32_t), s));
+        CU(cudaMemsetAsync(h->d_u64, 0, 4 * sizeof(unsigned long long), s));
+    }
     /* counters: [9] list_n(cur) [10] work [11] round_n [12] next_n */
-    k_gen_init<<<(nh + 255) / 256, 256, 0, s>>>(h->d_gen_state, d_rgtp, h->d_gen_list[0], h->d_counters + 9, nh);
+    const int n_init = subset ? (int)n_subset : nh;
+    k_gen_init<<<(n_init + 255) / 256, 256, 0, s>>>(h->d_gen_state, d_rgtp, h->d_gen_list[0], h->d_counters + 9,
+                                                    n_init, subset);
     GenArgs a;
     memset(&a, 0, sizeof(a));
     a.g = h->g; a.in = h->d_in; a.centers = d_centers; a.rgtp = d_rgtp; a.st = h->d_gen_state;
@@ -2026,7 +2044,7 @@ static int run_query_general(sogpu *h, const float *d_centers, const float *d_rg
     a.evals = h->d_u64 + 1;
     std::vector<unsigned long long> seg_n;
     int cur = 0;
-    uint32_t n_active = (uint32_t)nh;
+    uint32_t n_active = (uint32_t)n_init;
     const size_t smem = query_smem_bytes<256>();
     for (int round = 0; n_active > 0 && round < 4096; ++round) {
         a.list = h->d_gen_list[cur]; a.list_n = h->d_counters + 9; a.work = h->d_counters + 10;
@@ -2085,18 +2103,30 @@ static int run_query_general(sogpu *h, const float *d_centers, const float *d_rg
         CU(cudaStreamSynchronize(s));
         cur ^= 1;
     }
-    /* member offsets + lists exactly as on the equal-mass path */
+    return emit_members(h, d_centers, d_rgtp, nh, thr, nM);
+}
+
+/* member offsets in catalog order + the CSR member lists, from out_n / out_key of all nh halos */
+static int emit_members(sogpu *h, const float *d_centers, const float *d_rgtp, int32_t nh, float thr, int32_t nM)
+{
+    cudaStream_t s = h->stream;
     QueryArgs q;
     memset(&q, 0, sizeof(q));
     q.g = h->g; q.centers = d_centers; q.rgtp = d_rgtp; q.thr = thr; q.nM = nM;
     q.out_n = h->d_out_n; q.out_m = h->d_out_m; q.out_key = h->d_out_key; q.out_off = h->d_out_off;
     q.members = h->d_members; q.md2 = h->want_d2 ? h->d_md2 : nullptr; q.member_cap = h->member_cap;
     q.evals = h->d_u64 + 1; q.flags = h->d_counters + 4; q.mt = h->d_mt;
+    CU(cudaMemsetAsync(h->d_counters + 4, 0, 5 * sizeof(uint32_t), s));     /* flags, emit lists + work */
+    CU(cudaMemsetAsync(h->d_counters + 15, 0, 2 * sizeof(uint32_t), s));
+    CU(cudaMemsetAsync(h->d_u64, 0, sizeof(unsigned long long), s));
     {
         ProfScope p(h, KID_OFFSETS);
         k_offsets<<<1, 1024, 0, s>>>(h->d_out_n, nh, h->d_out_off, h->d_u64 + 0, 2048, h->d_esmall,
-                                     h->d_counters + 5, h->d_ebig, h->d_counters + 6);
+                                     h->d_counters + 5, h->d_ebig, h->d_counters + 6, 131072, h->d_ehuge,
+                                     h->d_counters + 15);
     }
+    q.list = h->d_ehuge; q.list_n = h->d_counters + 15; q.work_counter = h->d_counters + 16;
+    { ProfScope p(h, KID_EMIT_HUGE); launch_persistent<1024>(h, k_so_emit<1024>, q, std::min(nh, h->sm_count)); }
     q.list = h->d_esmall; q.list_n = h->d_counters + 5; q.work_counter = h->d_counters + 7;
     { ProfScope p(h, KID_EMIT_WARP); launch_persistent<32>(h, k_so_emit<32>, q, nh); }
     q.list = h->d_ebig; q.list_n = h->d_counters + 6; q.work_counter = h->d_counters + 8;
@@ -2118,9 +2148,26 @@ static int fetch_stats(sogpu *h)
     h->stats.last_evals_first = (int64_t)u[1];
     h->stats.last_evals = (int64_t)(u[1] + u[2]);
     h->stats.last_deferred = (int32_t)c[17];
-    if (c[4] & 1u) return set_err(SOGPU_ERR_NOMEM, "member buffer overflow (%llu > %llu)", u[0], h->member_cap);
+    h->member_overflow = (c[4] & 1u) != 0;
+    if (h->member_overflow)
+        return set_err(SOGPU_ERR_NOMEM, "member buffer overflow (%llu > %llu)", u[0], h->member_cap);
     if (c[4] & 2u) return set_err(SOGPU_ERR_UNSUPPORTED, "internal: member emission count mismatch");
     return SOGPU_OK;
+}
+
+/* the member lists did not fit: grow the buffers to the (now known) total and emit again */
+static int grow_members_and_reemit(sogpu *h, const float *d_centers, const float *d_rgtp, int32_t nh, float thr,
+                                   int32_t nM)
+{
+    unsigned long long need = (unsigned long long)h->stats.last_members;
+    cudaFree(h->d_members); cudaFree(h->d_md2);
+    h->d_members = nullptr; h->d_md2 = nullptr;
+    h->member_cap = need + need / 16 + 1024;
+    CU(cudaMalloc(&h->d_members, (size_t)h->member_cap * sizeof(int32_t)));
+    CU(cudaMalloc(&h->d_md2, (size_t)h->member_cap * sizeof(float)));
+    int rc = emit_members(h, d_centers, d_rgtp, nh, thr, nM);
+    if (rc) return rc;
+    return fetch_stats(h);
 }
 
 extern "C" int sogpu_so_device(sogpu_t *h, const void *d_centers, const void *d_rgtp, int32_t nh, float thr,
@@ -2159,6 +2206,7 @@ extern "C" int sogpu_so(sogpu_t *h, const float *centers, const float *rgtp, int
     CU(cudaMemcpyAsync(pn, h->d_out_n, (size_t)nh * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(pm, h->d_out_m, (size_t)nh * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     rc = fetch_stats(h);   /* synchronises the stream */
+    if (rc && h->member_overflow) rc = grow_members_and_reemit(h, h->d_centers, h->d_rgtp, nh, thr, nM);
     if (rc) return rc;
     if (pn[0] == CODE_UNEQUAL_MASS) {
         /* mixed particle masses: the rank-only mass table does not apply; run the general path */
@@ -2168,7 +2216,25 @@ extern "C" int sogpu_so(sogpu_t *h, const float *centers, const float *rgtp, int
         CU(cudaMemcpyAsync(pn, h->d_out_n, (size_t)nh * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaMemcpyAsync(pm, h->d_out_m, (size_t)nh * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         rc = fetch_stats(h);
+        if (rc && h->member_overflow) rc = grow_members_and_reemit(h, h->d_centers, h->d_rgtp, nh, thr, nM);
         if (rc) return rc;
+    } else {
+        /* degenerate particle configurations the histogram levels cannot split (thousands of
+         * particles at one identical r^2): those halos go through the general full-sort path */
+        int32_t n_bad = 0;
+        for (int32_t i = 0; i < nh; ++i) n_bad += (pn[i] == CODE_UNSUPPORTED);
+        if (n_bad) {
+            CU(cudaMemsetAsync(h->d_counters + 19, 0, sizeof(uint32_t), h->stream));
+            k_select_code<<<(nh + 255) / 256, 256, 0, h->stream>>>(h->d_out_n, nh, CODE_UNSUPPORTED, h->d_defer,
+                                                                   h->d_counters + 19);
+            rc = run_query_general(h, h->d_centers, h->d_rgtp, nh, thr, nM, h->d_defer, (uint32_t)n_bad);
+            if (rc) return rc;
+            CU(cudaMemcpyAsync(pn, h->d_out_n, (size_t)nh * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaMemcpyAsync(pm, h->d_out_m, (size_t)nh * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+            rc = fetch_stats(h);
+            if (rc && h->member_overflow) rc = grow_members_and_reemit(h, h->d_centers, h->d_rgtp, nh, thr, nM);
+            if (rc) return rc;
+        }
     }
     for (int32_t i = 0; i < nh; ++i) {
         int32_t n = pn[i];

@@ -249,6 +249,31 @@ def test_unequal_masses_general_path():
     g.close()
 
 
+def test_thousands_of_particles_at_identical_radius():
+    """More coincident particles than any histogram level can split: those halos are re-run through
+    the general full-sort path instead of failing."""
+    s = synth.make_snapshot(32 ** 3, 6, seed=44, nmax=2500)
+    pos = s.pos.copy()
+    rng = np.random.default_rng(4)
+    bg = rng.choice(s.n, 12000, replace=False)
+    pos[bg[:6000]] = s.centers[0]                                    # r^2 = 0 for 6000 particles of halo 0
+    off = np.array([0.3, -0.2, 0.1], np.float32) * np.float32(s.rgtp[1])
+    pos[bg[6000:]] = s.centers[1] + off                              # one identical r^2 > 0 around halo 1
+    r, ref = check_against_oracle(pos, s.mass, s.centers, s.rgtp, 200.0)
+    assert ref["ndelta"][0] > 6000 or ref["rvir"][0] < 0
+    assert r["stats"]["equal_mass"] == 1
+
+
+def test_member_buffer_grows_when_halos_overlap_heavily():
+    """Sum of N_Delta far above N (the same big halo listed hundreds of times)."""
+    s = synth.make_snapshot(40 ** 3, 3, seed=45, sizes=[6000, 3000, 500], nmax=1e4)
+    reps = 300
+    centers = np.repeat(s.centers[:1], reps, axis=0)
+    rgtp = np.repeat(s.rgtp[:1], reps)
+    r, ref = check_against_oracle(s.pos, s.mass, centers, rgtp, 200.0)
+    assert int(ref["member_offset"][-1]) > (1 << 20) > s.n
+
+
 def test_bad_arguments_return_errors():
     g = api.SoGpu()
     with pytest.raises(api.SoGpuError):
