@@ -293,9 +293,41 @@ def run_ours(args):
         dist.all_reduce(evals, op=dist.ReduceOp.SUM)
     evals_total, members_total = float(evals[0].item()), float(evals[1].item())
 
-    # parity spot check of what was just timed (rank 0, a few halos, against the oracle)
     res_n = d_out_n[:h_mine].cpu().numpy()
     res_m = d_out_m[:h_mine].cpu().numpy()
+
+    # ---- extra: the focused build (grid only where this rank's halos can look) -------------------
+    FOCUS_BALLS = 4
+
+    def step_focused():
+        if h_mine:
+            g.build_grid_for_device(d_centers.data_ptr(), d_rgtp.data_ptr(), h_mine, FOCUS_BALLS)
+            g.so_device(d_centers.data_ptr(), d_rgtp.data_ptr(), h_mine, thr, NMEM,
+                        d_out_n.data_ptr(), d_out_m.data_ptr())
+        else:
+            g.build_grid()
+
+    for _ in range(3):
+        step_focused()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(args.steps):
+        step_focused()
+    f1.record(stream)
+    barrier()
+    tf = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+    ms_focused = float(tf.item()) / args.steps
+    foc_n = d_out_n[:h_mine].cpu().numpy()
+    foc_m = d_out_m[:h_mine].cpu().numpy()
+    foc_in = foc_n != -103            # halos whose balls stayed inside the focused region
+    foc_same = bool(np.array_equal(foc_n[foc_in], res_n[foc_in]) and
+                    foc_m[foc_in].tobytes() == res_m[foc_in].tobytes())
+    foc_outgrown = int((~foc_in).sum())
+    foc_kept = g.stats()["n_in_grid"]
+    foc_prof = {k: round(v[0] / (args.steps + 3), 4) for k, v in g.profile_read(reset=True).items() if v[1]}
 
     # ---- e2e: host buffers in, host results out, every step ----------------------------------
     e2e_parts = {"upload_ms": 0.0, "build_so_ms": 0.0, "members_ms": 0.0}
@@ -406,6 +438,12 @@ def run_ours(args):
                    "l2": "inputs (%.0f MB float4 particles) exceed the 126 MB L2; no flush between steps"
                          % (16 * n / 1e6),
                    "parallelism": "halos sharded by LPT over %d rank(s), particles replicated" % world},
+        "focused_build": {"note": "same step with sogpu_build_grid_for (grid only where the halos can look, "
+                                  "%d schedule balls); results of the halos inside the focus identical to the full build: %s; "
+                                  "sogpu_so() re-solves outgrown halos on a full grid by itself" % (FOCUS_BALLS, foc_same),
+                          "value": h_total / (ms_focused * 1e-3), "unit": UNIT, "ms_per_step": ms_focused,
+                          "particles_sorted_rank0": int(foc_kept), "halos_outgrown_rank0": foc_outgrown,
+                          "kernel_ms_per_step": foc_prof},
         "evals_per_s": evals_total / (ms_step * 1e-3), "evals_per_step": evals_total,
         "members_per_step": members_total, "halos_resolved_rank0": ok,
         "e2e": {"value": h_total / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,

@@ -81,6 +81,18 @@ int sogpu_set_particles_device(sogpu_t *h, const void *d_xyzm, int64_t n, const 
  * periodic uniform grid: sorted float4 array + original-index array + cell-end table. */
 int sogpu_build_grid(sogpu_t *h);
 
+/* Focused variant: build the grid only where these nh halos can ever look — the cubes of half-width
+ * b_k = rgtp * 1.2^n_balls (the radius of the n_balls-th ball of kdRvir's schedule) around the
+ * centres, at a resolution of 2^min(lb,8) coarse cells per axis.  Particles elsewhere are not
+ * sorted at all.  sogpu_so() on such a grid returns exactly the results of a full grid: every ball
+ * is checked against the kept region on the device, and if a halo needs a bigger ball than
+ * planned (or an arbitrary ball gather is requested) the library rebuilds the full grid and solves
+ * again.  sogpu_so_device() reports such halos with code -103 instead (asynchronous, no retry). */
+int sogpu_build_grid_for(sogpu_t *h, const float *centers, const float *rgtp, int32_t nh,
+                         int32_t n_balls);
+int sogpu_build_grid_for_device(sogpu_t *h, const void *d_centers, const void *d_rgtp, int32_t nh,
+                                int32_t n_balls);
+
 /* ---- kdSO / kdRvir replacement (kd2.c:864-895, 723-840), without tagging ------------------- */
 
 /* For each of the nh halos (any order; halos are independent):
@@ -139,6 +151,7 @@ typedef struct {
     int64_t last_members;        /* sum of N_Delta of the last call                           */
     int32_t last_kernel_launches;/* kernels launched by the last build or so call             */
     int32_t last_deferred;       /* halos the warp kernel handed to the block kernel          */
+    int64_t n_in_grid;           /* particles the last build sorted (< n_particles if focused) */
 } sogpu_stats_t;
 int sogpu_get_stats(sogpu_t *h, sogpu_stats_t *out);
 

@@ -27,7 +27,7 @@ SYMBOLS = [
     "sogpu_finish_host", "sogpu_keep_member_d2", "sogpu_profile_enable", "sogpu_profile_kernels",
     "sogpu_profile_name", "sogpu_profile_read", "sogpu_upload_particles",
     "sogpu_set_build_mode", "sogpu_ball_gather_batch",
-    "sogpu_profile_bytes",
+    "sogpu_profile_bytes", "sogpu_build_grid_for", "sogpu_build_grid_for_device",
 ]
 
 
@@ -38,7 +38,7 @@ class SoGpuError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("n_particles", C.c_int64), ("cells_per_axis", C.c_int32), ("equal_mass", C.c_int32),
                 ("last_evals", C.c_int64), ("last_evals_first", C.c_int64), ("last_members", C.c_int64),
-                ("last_kernel_launches", C.c_int32), ("last_deferred", C.c_int32)]
+                ("last_kernel_launches", C.c_int32), ("last_deferred", C.c_int32), ("n_in_grid", C.c_int64)]
 
 
 _lib = None
@@ -70,6 +70,10 @@ def lib():
     L.sogpu_upload_particles.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_int64, vp]
     L.sogpu_upload_particles.restype = C.c_int
     L.sogpu_build_grid.argtypes = [vp]
+    L.sogpu_build_grid_for.argtypes = [vp, fp, fp, C.c_int32, C.c_int32]
+    L.sogpu_build_grid_for.restype = C.c_int
+    L.sogpu_build_grid_for_device.argtypes = [vp, vp, vp, C.c_int32, C.c_int32]
+    L.sogpu_build_grid_for_device.restype = C.c_int
     L.sogpu_so.argtypes = [vp, fp, fp, C.c_int32, C.c_float, C.c_int32, fp, fp, i32p]
     L.sogpu_so_device.argtypes = [vp, vp, vp, C.c_int32, C.c_float, C.c_int32, vp, vp]
     L.sogpu_members.argtypes = [vp, i64p, C.POINTER(i32p), C.POINTER(fp), C.c_int]
@@ -226,6 +230,16 @@ class SoGpu:
 
     def build_grid(self):
         _check(lib().sogpu_build_grid(self._h))
+
+    def build_grid_for(self, centers, rgtp, n_balls=3):
+        """Focused build: keep only what these halos can reach within n_balls schedule steps."""
+        centers = np.ascontiguousarray(centers, np.float32)
+        rgtp = np.ascontiguousarray(rgtp, np.float32)
+        _check(lib().sogpu_build_grid_for(self._h, _fp(centers), _fp(rgtp), len(rgtp), int(n_balls)))
+
+    def build_grid_for_device(self, d_centers, d_rgtp, nh, n_balls=3):
+        _check(lib().sogpu_build_grid_for_device(self._h, C.c_void_p(int(d_centers)), C.c_void_p(int(d_rgtp)),
+                                                 int(nh), int(n_balls)))
 
     def so(self, centers, rgtp, thr, n_members=8):
         centers = np.ascontiguousarray(centers, np.float32)

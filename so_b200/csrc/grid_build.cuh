@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(1024) k_scan_bsums(uint32_t *__restrict__ bsum
 /* exclusive scan of each tile plus its block offset: out[i] = sum a[0..i); out may alias a.
  * If `copy` is given it receives the same values (the atomic cursors of the partition pass). */
 __global__ void __launch_bounds__(256) k_scan_apply(const uint32_t *a, int64_t n, const uint32_t *__restrict__ bsum,
-                                                    uint32_t *out, uint32_t *copy, uint32_t total_slot_value)
+                                                    uint32_t *out, uint32_t *copy)
 {
     __shared__ uint32_t ws[8];
     int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * 8;
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) k_scan_apply(const uint32_t *a, int64_t n
         }
         run += v[k];
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = total_slot_value;   /* sentinel: array end */
+    if (base <= n - 1 && n - 1 < base + 8) out[n] = run;   /* sentinel: total (= particles kept) */
 }
 
 /* ---- level kernels ---------------------------------------------------------------------------- */
@@ -164,10 +164,12 @@ template <bool FIRST>
 __global__ void __launch_bounds__(256) k_lvl_hist(const float4 *__restrict__ in4, const uint32_t *__restrict__ inkey,
                                                   int64_t n, GridDev g, LevelDesc lv,
                                                   const uint32_t *__restrict__ pstart, uint32_t *__restrict__ counts,
-                                                  uint32_t *__restrict__ mass_minmax)
+                                                  uint32_t *__restrict__ mass_minmax,
+                                                  const uint32_t *__restrict__ n_dev)
 {
     __shared__ uint32_t sh[LVL_CMAX];
     __shared__ uint32_t sres[2];
+    if (n_dev) n = (int64_t)__ldg(n_dev);        /* focused build: particles kept by level 0 */
     const int C = 1 << lv.db;
     const uint32_t cmask = (uint32_t)C - 1u;
     uint32_t mn = 0xFFFFFFFFu, mx = 0u;
@@ -182,9 +184,10 @@ __global__ void __launch_bounds__(256) k_lvl_hist(const float4 *__restrict__ in4
             __syncthreads();
             for (uint32_t i = pos + threadIdx.x; i < send; i += 256) {
                 uint32_t key;
+                bool kept = true;
                 if (FIRST) {
                     float4 q = ld_stream(in4 + i);
-                    key = cell_key(q, g);
+                    key = cell_key_kept(q, g, kept);
                     uint32_t mo = (q.w >= 0.0f) ? __float_as_uint(q.w) : 0xFFFFFFFEu;
                     if (!(q.w >= 0.0f)) mn = 0u;     /* negative / NaN mass: treated as "unequal" */
                     mn = min(mn, mo);
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(256) k_lvl_hist(const float4 *__restrict__ in4
                 } else {
                     key = __ldg(inkey + i);
                 }
-                atomicAdd(&sh[(key >> lv.shift) & cmask], 1u);
+                if (kept) atomicAdd(&sh[(key >> lv.shift) & cmask], 1u);
             }
             __syncthreads();
             for (int c = threadIdx.x; c < C; c += 256)
@@ -221,15 +224,17 @@ __global__ void __launch_bounds__(LVL_THREADS, 2) k_lvl_partition(const float4 *
                                                                   const uint32_t *__restrict__ pstart,
                                                                   uint32_t *__restrict__ cursor,
                                                                   float4 *__restrict__ out4,
-                                                                  uint32_t *__restrict__ outkey)
+                                                                  uint32_t *__restrict__ outkey,
+                                                                  const uint32_t *__restrict__ n_dev)
 {
+    if (n_dev) n = (int64_t)__ldg(n_dev);
     extern __shared__ __align__(16) unsigned char raw[];
     float4 *s4 = reinterpret_cast<float4 *>(raw);
     uint32_t *sk = reinterpret_cast<uint32_t *>(s4 + LVL_T);
     uint16_t *sd = reinterpret_cast<uint16_t *>(sk + LVL_T);
     uint16_t *sr = sd + LVL_T;
     uint16_t *perm = sr + LVL_T;
-    __shared__ uint32_t scnt[LVL_CMAX], soff[LVL_CMAX], sbase[LVL_CMAX], ws[LVL_THREADS / 32], sres[2];
+    __shared__ uint32_t scnt[LVL_CMAX], soff[LVL_CMAX], sbase[LVL_CMAX], ws[LVL_THREADS / 32], sres[2], stot;
     const int C = 1 << lv.db;
     const uint32_t cmask = (uint32_t)C - 1u;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -259,15 +264,20 @@ __global__ void __launch_bounds__(LVL_THREADS, 2) k_lvl_partition(const float4 *
                 for (int k = 0; k < IT; ++k) {
                     int i = t + k * LVL_THREADS;
                     if (i < cnt) {
+                        bool kept = true;
                         if (FIRST) {
-                            key[k] = cell_key(q[k], g);
+                            key[k] = cell_key_kept(q[k], g, kept);
                             q[k].w = __int_as_float((int)(pos + i));      /* payload: original index */
                         }
-                        uint32_t d = (key[k] >> lv.shift) & cmask;
-                        s4[i] = q[k];
-                        sk[i] = key[k];
-                        sd[i] = (uint16_t)d;
-                        sr[i] = (uint16_t)atomicAdd(&scnt[d], 1u);
+                        if (kept) {
+                            uint32_t d = (key[k] >> lv.shift) & cmask;
+                            s4[i] = q[k];
+                            sk[i] = key[k];
+                            sd[i] = (uint16_t)d;
+                            sr[i] = (uint16_t)atomicAdd(&scnt[d], 1u);
+                        } else {
+                            sd[i] = 0xFFFFu;                              /* outside the focused region */
+                        }
                     }
                 }
             }
@@ -286,12 +296,15 @@ __global__ void __launch_bounds__(LVL_THREADS, 2) k_lvl_partition(const float4 *
                 if (t < C) {
                     soff[t] = off + x - c0;
                     sbase[t] = c0 ? atomicAdd(&cursor[(size_t)p * C + t], c0) : 0u;
+                    if (t == C - 1) stot = off + x;
                 }
             }
             __syncthreads();
-            for (int i = t; i < cnt; i += LVL_THREADS) perm[soff[sd[i]] + sr[i]] = (uint16_t)i;
+            for (int i = t; i < cnt; i += LVL_THREADS)
+                if (sd[i] != 0xFFFFu) perm[soff[sd[i]] + sr[i]] = (uint16_t)i;
             __syncthreads();
-            for (int slot = t; slot < cnt; slot += LVL_THREADS) {
+            const int kept_cnt = (int)stot;
+            for (int slot = t; slot < kept_cnt; slot += LVL_THREADS) {
                 int i = perm[slot];
                 uint32_t d = sd[i];
                 uint32_t dst = sbase[d] + ((uint32_t)slot - soff[d]);
@@ -330,6 +343,10 @@ __global__ void __launch_bounds__(BKT_THREADS, 2) k_bucket_sort(const float4 *__
         const uint32_t b0 = __ldg(bstart + b), b1 = __ldg(bstart + b + 1);
         const uint32_t nb = b1 - b0;
         const bool staged = nb <= BKT_CAP;
+        if (nb == 0) {                   /* empty bucket (focused builds): only its cell-table slice */
+            for (int c = t; c < ncells; c += BKT_THREADS) ce[((size_t)b << cell_bits) + c] = b0;
+            continue;
+        }
         for (int c = t; c < ncells; c += BKT_THREADS) cnt[c] = 0u;
         __syncthreads();
         /* count (and stage): all loads of a staged bucket are issued before the first use */

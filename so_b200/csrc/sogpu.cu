@@ -40,6 +40,7 @@
 #define CELL_MARGIN 2.0e-3  /* slack, in cells, of every cell-range computation              */
 #define CODE_UNSUPPORTED (-100)
 #define CODE_DEFER (-101)
+#define CODE_NEED_FULL (-103)   /* focused grid does not cover this halo's ball */
 
 template <int NT> struct Cfg;
 template <> struct Cfg<32> {   /* warp per halo */
@@ -87,6 +88,8 @@ struct GridDev {
     float L[3], halfL[3];
     double dg0[3], dinvh[3], dh[3];
     double bmax_pruned;       /* balls at least this large visit every cell                  */
+    const uint32_t *mask;     /* focused build: bit per coarse cell that was kept (NULL = all) */
+    int mb, ms;               /* mask cells per axis = 2^mb; fine cell coordinate >> ms        */
 };
 
 __device__ __forceinline__ uint32_t spread10(uint32_t x)
@@ -116,6 +119,22 @@ __device__ __forceinline__ uint32_t cell_key(const float4 &p, const GridDev &g)
     return (row_key(iy, iz) << g.lb) | ix;
 }
 
+__device__ __forceinline__ bool mask_bit(const GridDev &g, uint32_t mx, uint32_t my, uint32_t mz)
+{
+    uint32_t bit = (mz << (2 * g.mb)) | (my << g.mb) | mx;
+    return (__ldg(g.mask + (bit >> 5)) >> (bit & 31)) & 1u;
+}
+/* cell key + whether the particle's coarse cell belongs to the focused region */
+__device__ __forceinline__ uint32_t cell_key_kept(const float4 &p, const GridDev &g, bool &kept)
+{
+    int mask = g.nc - 1;
+    uint32_t ix = cell_coord(p.x, g.g0[0], g.invh[0], mask);
+    uint32_t iy = cell_coord(p.y, g.g0[1], g.invh[1], mask);
+    uint32_t iz = cell_coord(p.z, g.g0[2], g.invh[2], mask);
+    kept = !g.mask || mask_bit(g, ix >> g.ms, iy >> g.ms, iz >> g.ms);
+    return (row_key(iy, iz) << g.lb) | ix;
+}
+
 __device__ __forceinline__ float4 ld_stream(const float4 *p)
 {
     float4 r;
@@ -129,6 +148,11 @@ __device__ __forceinline__ float4 ld_stream(const float4 *p)
  * grid build kernels (kdBuildTree replacement)
  * ============================================================================================ */
 #include "grid_build.cuh"
+
+__global__ void k_copy_u32(uint32_t *dst, const uint32_t *src)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) *dst = *src;
+}
 
 __global__ void k_store_u32(uint32_t *p, uint32_t v0, uint32_t *q, uint32_t v1)
 {
@@ -559,6 +583,66 @@ template <int NT> __device__ __forceinline__ void bitonic_sort(unsigned long lon
 }
 
 /* ============================================================================================
+ * focused grid: only the coarse cells some halo can ever look at are kept by the build
+ * ============================================================================================ */
+/* conservative range of mask cells [m0, m0+cnt) per axis touched by the cube of half-width b */
+__device__ __forceinline__ void mask_range(const GridDev &g, int axis, double c, double b, int &m0, int &cnt)
+{
+    const int nm = 1 << g.mb;
+    if (!(b < g.bmax_pruned)) { m0 = 0; cnt = nm; return; }
+    int lo = (int)floor((c - b - g.dg0[axis]) * g.dinvh[axis] - CELL_MARGIN) - 1;
+    int hi = (int)floor((c + b - g.dg0[axis]) * g.dinvh[axis] + CELL_MARGIN) + 1;
+    int mlo = lo >> g.ms, mhi = hi >> g.ms;          /* arithmetic shifts: floor division */
+    cnt = min(mhi - mlo + 1, nm);
+    m0 = mlo;
+}
+
+template <int NT>
+__device__ __forceinline__ bool ball_covered(const GridDev &g, GroupSmem<NT> &sm, int tid, const Center &c, double b)
+{
+    if (!g.mask) return true;
+    int x0, nx, y0, ny, z0, nz;
+    mask_range(g, 0, c.x, b, x0, nx);
+    mask_range(g, 1, c.y, b, y0, ny);
+    mask_range(g, 2, c.z, b, z0, nz);
+    const int nm1 = (1 << g.mb) - 1, tot = nx * ny * nz;
+    int ok = 1;
+    for (int i = tid; i < tot && ok; i += NT) {
+        int ix = i % nx, iy = (i / nx) % ny, iz = i / (nx * ny);
+        ok = mask_bit(g, (uint32_t)((x0 + ix) & nm1), (uint32_t)((y0 + iy) & nm1), (uint32_t)((z0 + iz) & nm1));
+    }
+    return gmin<NT>(ok, sm.tmp, tid) != 0;
+}
+
+/* one warp per halo marks the cube it can reach after n_balls steps of the ball schedule */
+__global__ void __launch_bounds__(256) k_mark_mask(GridDev g, const float *__restrict__ centers,
+                                                   const float *__restrict__ rgtp, int nh, int n_balls,
+                                                   uint32_t *__restrict__ mask)
+{
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const float root = so_root_period(g.L[0], g.L[1], g.L[2]);
+    const int nm1 = (1 << g.mb) - 1;
+    for (int h = wid; h < nh; h += nw) {
+        float ball = rgtp[h];
+        for (int k = 0; k < n_balls && (double)ball < 0.25 * (double)root; ++k) ball = so_next_ball(ball);
+        const float ball2 = __fmul_rn(ball, ball);
+        const double b = sqrt((double)ball2) * (1.0 + 1.0e-6);
+        int x0, nx, y0, ny, z0, nz;
+        mask_range(g, 0, centers[3 * h + 0], b, x0, nx);
+        mask_range(g, 1, centers[3 * h + 1], b, y0, ny);
+        mask_range(g, 2, centers[3 * h + 2], b, z0, nz);
+        const int tot = nx * ny * nz;
+        for (int i = lane; i < tot; i += 32) {
+            int ix = i % nx, iy = (i / nx) % ny, iz = i / (nx * ny);
+            uint32_t bit = ((uint32_t)((z0 + iz) & nm1) << (2 * g.mb)) | ((uint32_t)((y0 + iy) & nm1) << g.mb) |
+                           (uint32_t)((x0 + ix) & nm1);
+            atomicOr(&mask[bit >> 5], 1u << (bit & 31));
+        }
+    }
+}
+
+/* ============================================================================================
  * one halo: kdRvir (kd2.c:723-840)
  * ============================================================================================ */
 struct HaloResult {
@@ -596,6 +680,10 @@ __device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &s
         }
         for (int b = tid; b <= NB; b += NT) sm.hist[0][b] = 0u;
         gsync<NT>();
+        if (!ball_covered<NT>(g, sm, tid, c, sqrt((double)ball2) * (1.0 + 1.0e-6))) {
+            res.n = CODE_NEED_FULL; res.m = 0.0f;      /* focused grid too small for this ball */
+            return;
+        }
         BallGeom B = make_geom(g, c, sqrt((double)ball2) * (1.0 + 1.0e-6));
         {
             HistF f;
@@ -1286,12 +1374,12 @@ __global__ void k_select_code(const int32_t *out_n, int nh, int32_t code, int32_
 enum {
     KID_LVL_HIST = 0, KID_LVL_SCAN, KID_LVL_PARTITION, KID_BUCKET_SORT, KID_MASS_TABLE, KID_CLASSIFY,
     KID_QUERY_WARP, KID_QUERY_BLOCK, KID_OFFSETS, KID_EMIT_WARP, KID_EMIT_BLOCK, KID_BALL_GATHER,
-    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_N
+    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_N
 };
 static const char *const g_kernel_names[KID_N] = {
     "k_lvl_hist", "k_scan(3 launches)", "k_lvl_partition", "k_bucket_sort", "k_mass_table", "k_classify",
     "k_so_query<32>", "k_so_query<256>", "k_offsets", "k_so_emit<32>", "k_so_emit<256>", "k_ball_gather",
-    "k_so_query<1024>", "k_so_emit<1024>"};
+    "k_so_query<1024>", "k_so_emit<1024>", "k_mark_mask"};
 
 struct ProfRec { int kid; cudaEvent_t a, b; };
 
@@ -1322,6 +1410,9 @@ struct sogpu {
     uint32_t *d_lvl_cursor[4];       /* counts, then the atomic cursors of the partition */
     size_t lvl_cap[4];
     int two_level;                   /* -1 auto; 0: no partition levels (bucket sort only if it fits) */
+    uint32_t *d_mask;                /* focused build: 2^(3*mb) bits */
+    bool focused;                    /* the current grid holds only the focused region */
+    int focus_balls;
     double prof_bytes[32];
     int64_t ncell;
     int nc, lb;
@@ -1502,6 +1593,7 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     cudaFree(h->d_in_owned);
     cudaFree(h->d_massmm);
     cudaFree(h->d_raw);
+    cudaFree(h->d_mask);
     cudaFree(h->d_tmp4); cudaFree(h->d_key[0]); cudaFree(h->d_key[1]);
     for (int l = 0; l < 4; ++l) { cudaFree(h->d_lvl_start[l]); cudaFree(h->d_lvl_cursor[l]); }
     cudaFree(h->d_mt);
@@ -1685,8 +1777,10 @@ static int pick_cells(int64_t n, float ppc, int *lb)
     return 1 << l;
 }
 
-/* kdBuildTree replacement.  Fully asynchronous on the handle's stream (no host round trip). */
-extern "C" int sogpu_build_grid(sogpu_t *h)
+/* kdBuildTree replacement.  Fully asynchronous on the handle's stream (no host round trip).
+ * focus_nh > 0: only the region the focus_nh halos in d_centers/d_rgtp can reach within
+ * focus_balls steps of the ball schedule is kept (sogpu_build_grid_for). */
+static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
 {
     if (!h || !h->d_in || h->n <= 0) return set_err(SOGPU_ERR_ARG, "sogpu_build_grid: no particles set");
     CU(cudaSetDevice(h->device));
@@ -1743,9 +1837,28 @@ extern "C" int sogpu_build_grid(sogpu_t *h)
         lmin = std::min(lmin, Lk);
     }
     g.bmax_pruned = 0.5 * lmin - 2.0 * hmax;
+    g.mask = nullptr; g.mb = 0; g.ms = 0;
 
     cudaStream_t s = h->stream;
     const double N = (double)h->n;
+    h->focused = false;
+    if (focus_nh > 0 && L > 0) {
+        const int mb = std::min(lb, 8);
+        const size_t words = ((size_t)1 << (3 * mb)) / 32 + 1;
+        if (!h->d_mask) CU(cudaMalloc(&h->d_mask, (((size_t)1 << 24) / 32 + 1) * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(h->d_mask, 0, words * sizeof(uint32_t), s));
+        g.mb = mb; g.ms = lb - mb;
+        GridDev gm = g;
+        gm.mask = h->d_mask;
+        {
+            ProfScope p(h, KID_MARK_MASK);
+            k_mark_mask<<<std::min((focus_nh + 7) / 8, h->sm_count * 8), 256, 0, s>>>(gm, h->d_centers, h->d_rgtp,
+                                                                                      focus_nh, focus_balls, h->d_mask);
+        }
+        g.mask = h->d_mask;
+        h->focused = true;
+        h->focus_balls = focus_balls;
+    }
     h->stats.last_kernel_launches = 0;
     CU(cudaMemsetAsync(h->d_massmm, 0xFF, sizeof(uint32_t), s));
     CU(cudaMemsetAsync(h->d_massmm + 1, 0, sizeof(uint32_t), s));
@@ -1786,7 +1899,7 @@ extern "C" int sogpu_build_grid(sogpu_t *h)
         LevelDesc lv; lv.shift = 0; lv.db = 0; lv.pshift = 32; lv.n_parents = 1;
         CU(cudaMemsetAsync(h->d_lvl_cursor[0], 0, 2 * sizeof(uint32_t), s));
         { ProfScope p(h, KID_LVL_HIST, 16.0 * N);
-          k_lvl_hist<true><<<hist_grid, 256, 0, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[0], h->d_massmm); }
+          k_lvl_hist<true><<<hist_grid, 256, 0, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[0], h->d_massmm, nullptr); }
         k_store_u32<<<1, 32, 0, s>>>(h->d_lvl_start[0], 0u, h->d_lvl_start[0] + 1, (uint32_t)h->n);
     }
     for (int l = 0; l < L; ++l) {
@@ -1800,11 +1913,13 @@ extern "C" int sogpu_build_grid(sogpu_t *h)
         float4 *dst = ((L - 1 - l) % 2 == 0) ? h->d_tmp4 : h->d_sorted;
         uint32_t *dst_key = h->d_key[l & 1];
         const uint32_t *pstart = l ? h->d_lvl_start[l - 1] : nullptr;
+        /* particles that survive level 0 (== N unless the build is focused): sentinel of its scan */
+        const uint32_t *n_dev = (l && h->focused) ? h->d_lvl_start[0] + ((size_t)1 << db[0]) : nullptr;
         CU(cudaMemsetAsync(h->d_lvl_cursor[l], 0, M * sizeof(uint32_t), s));
         {
             ProfScope p(h, KID_LVL_HIST, (l ? 4.0 : 16.0) * N);
-            if (l == 0) k_lvl_hist<true><<<hist_grid, 256, 0, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], h->d_massmm);
-            else k_lvl_hist<false><<<hist_grid, 256, 0, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], h->d_massmm);
+            if (l == 0) k_lvl_hist<true><<<hist_grid, 256, 0, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], h->d_massmm, nullptr);
+            else k_lvl_hist<false><<<hist_grid, 256, 0, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], h->d_massmm, n_dev);
         }
         {
             ProfScope p(h, KID_LVL_SCAN, 12.0 * (double)M);
@@ -1812,14 +1927,14 @@ extern "C" int sogpu_build_grid(sogpu_t *h)
             k_scan_reduce<<<(unsigned)nt, 256, 0, s>>>(h->d_lvl_cursor[l], (int64_t)M, h->d_bsum);
             k_scan_bsums<<<1, 1024, 0, s>>>(h->d_bsum, nt);
             k_scan_apply<<<(unsigned)nt, 256, 0, s>>>(h->d_lvl_cursor[l], (int64_t)M, h->d_bsum, h->d_lvl_start[l],
-                                                     h->d_lvl_cursor[l], (uint32_t)h->n);
+                                                     h->d_lvl_cursor[l]);
         }
         {
             ProfScope p(h, KID_LVL_PARTITION, ((l ? 20.0 : 16.0) + 16.0 + (last ? 0.0 : 4.0)) * N);
-            if (l == 0 && !last) k_lvl_partition<true, true><<<part_grid, LVL_THREADS, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key);
-            else if (l == 0) k_lvl_partition<true, false><<<part_grid, LVL_THREADS, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key);
-            else if (!last) k_lvl_partition<false, true><<<part_grid, LVL_THREADS, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key);
-            else k_lvl_partition<false, false><<<part_grid, LVL_THREADS, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key);
+            if (l == 0 && !last) k_lvl_partition<true, true><<<part_grid, LVL_THREADS, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, nullptr);
+            else if (l == 0) k_lvl_partition<true, false><<<part_grid, LVL_THREADS, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, nullptr);
+            else if (!last) k_lvl_partition<false, true><<<part_grid, LVL_THREADS, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key, n_dev);
+            else k_lvl_partition<false, false><<<part_grid, LVL_THREADS, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key, n_dev);
         }
         src = dst;
         src_key = dst_key;
@@ -1832,7 +1947,8 @@ extern "C" int sogpu_build_grid(sogpu_t *h)
         ProfScope p(h, KID_BUCKET_SORT, 32.0 * N + 4.0 * (double)ncell);
         k_bucket_sort<<<grid, BKT_THREADS, bkt_smem, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, L == 0 ? 1 : 0);
     }
-    k_store_u32<<<1, 32, 0, s>>>(h->d_ce + ncell, (uint32_t)h->n, nullptr, 0u);
+    if (h->focused) k_copy_u32<<<1, 32, 0, s>>>(h->d_ce + ncell, h->d_lvl_start[0] + ((size_t)1 << db[0]));
+    else k_store_u32<<<1, 32, 0, s>>>(h->d_ce + ncell, (uint32_t)h->n, nullptr, 0u);
     { ProfScope p(h, KID_MASS_TABLE); k_mass_table<<<1, 32, 0, s>>>(h->d_massmm, h->d_mt, (unsigned long long)h->n + 2ull); }
     CU(cudaGetLastError());
     h->built = true;
@@ -1841,6 +1957,44 @@ extern "C" int sogpu_build_grid(sogpu_t *h)
     h->stats.n_particles = h->n;
     h->stats.cells_per_axis = nc;
     return SOGPU_OK;
+}
+
+extern "C" int sogpu_build_grid(sogpu_t *h) { return build_grid_impl(h, 0, 0); }
+
+static int ensure_query(sogpu *h, int32_t nh);
+
+extern "C" int sogpu_build_grid_for(sogpu_t *h, const float *centers, const float *rgtp, int32_t nh, int32_t n_balls)
+{
+    if (!h || !centers || !rgtp || nh <= 0 || n_balls < 1)
+        return set_err(SOGPU_ERR_ARG, "sogpu_build_grid_for: bad argument");
+    if (!h->d_in || h->n <= 0) return set_err(SOGPU_ERR_ARG, "sogpu_build_grid_for: no particles set");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_query(h, nh);
+    if (rc) return rc;
+    rc = ensure_pinned(h, (size_t)nh * 4 * sizeof(float));
+    if (rc) return rc;
+    float *pc = (float *)h->h_pin, *pr = pc + (size_t)3 * nh;
+    memcpy(pc, centers, (size_t)nh * 3 * sizeof(float));
+    memcpy(pr, rgtp, (size_t)nh * sizeof(float));
+    CU(cudaMemcpyAsync(h->d_centers, pc, (size_t)nh * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_rgtp, pr, (size_t)nh * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    return build_grid_impl(h, nh, n_balls);
+}
+
+/* same, with the halo list already on the device (asynchronous) */
+extern "C" int sogpu_build_grid_for_device(sogpu_t *h, const void *d_centers, const void *d_rgtp, int32_t nh,
+                                           int32_t n_balls)
+{
+    if (!h || !d_centers || !d_rgtp || nh <= 0 || n_balls < 1)
+        return set_err(SOGPU_ERR_ARG, "sogpu_build_grid_for_device: bad argument");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_query(h, nh);
+    if (rc) return rc;
+    if (d_centers != h->d_centers)
+        CU(cudaMemcpyAsync(h->d_centers, d_centers, (size_t)nh * 3 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    if (d_rgtp != h->d_rgtp)
+        CU(cudaMemcpyAsync(h->d_rgtp, d_rgtp, (size_t)nh * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    return build_grid_impl(h, nh, n_balls);
 }
 
 /* lazily learn (one small D2H) whether the particle masses were all equal */
@@ -2208,6 +2362,23 @@ extern "C" int sogpu_so(sogpu_t *h, const float *centers, const float *rgtp, int
     rc = fetch_stats(h);   /* synchronises the stream */
     if (rc && h->member_overflow) rc = grow_members_and_reemit(h, h->d_centers, h->d_rgtp, nh, thr, nM);
     if (rc) return rc;
+    if (h->focused) {
+        /* a focused grid (sogpu_build_grid_for) that some ball outgrew, or mixed masses: build the
+         * full grid and solve again — results never depend on how the grid was built */
+        bool redo = (pn[0] == CODE_UNEQUAL_MASS);
+        for (int32_t i = 0; i < nh && !redo; ++i) redo = (pn[i] == CODE_NEED_FULL);
+        if (redo) {
+            rc = build_grid_impl(h, 0, 0);
+            if (rc) return rc;
+            rc = run_query(h, h->d_centers, h->d_rgtp, nh, thr, nM);
+            if (rc) return rc;
+            CU(cudaMemcpyAsync(pn, h->d_out_n, (size_t)nh * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaMemcpyAsync(pm, h->d_out_m, (size_t)nh * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+            rc = fetch_stats(h);
+            if (rc && h->member_overflow) rc = grow_members_and_reemit(h, h->d_centers, h->d_rgtp, nh, thr, nM);
+            if (rc) return rc;
+        }
+    }
     if (pn[0] == CODE_UNEQUAL_MASS) {
         /* mixed particle masses: the rank-only mass table does not apply; run the general path */
         h->mass_state = 0; h->stats.equal_mass = 0;
@@ -2264,6 +2435,9 @@ extern "C" int sogpu_finish_host(const int32_t *code_or_n, const float *m, int32
         else if (n == CODE_UNEQUAL_MASS)
             return set_err(SOGPU_ERR_UNSUPPORTED, "particles have unequal masses: use sogpu_so (host entry point), "
                                                   "which switches to the general sequential-mass path");
+        else if (n == CODE_NEED_FULL)
+            return set_err(SOGPU_ERR_UNSUPPORTED, "halo %d outgrew the focused grid (sogpu_build_grid_for): rebuild "
+                                                  "with sogpu_build_grid, or use sogpu_so which does it itself", i);
         else return set_err(SOGPU_ERR_UNSUPPORTED, "halo %d: code %d", i, n);
     }
     return SOGPU_OK;
@@ -2336,6 +2510,7 @@ extern "C" int sogpu_ball_gather(sogpu_t *h, const float center[3], float ball2,
     if (!h->built) return set_err(SOGPU_ERR_ARG, "sogpu_ball_gather: call sogpu_build_grid first");
     if (!(ball2 >= 0.0f) || !(ball2 < INFINITY)) return set_err(SOGPU_ERR_ARG, "bad ball2");
     CU(cudaSetDevice(h->device));
+    if (h->focused) { int rf = build_grid_impl(h, 0, 0); if (rf) return rf; }
     int rc = ensure_query(h, 1);
     if (rc) return rc;
     cudaStream_t s = h->stream;
@@ -2382,6 +2557,7 @@ extern "C" int sogpu_ball_gather_batch(sogpu_t *h, const float *centers, const f
     if (!h || !centers || !ball2 || nh <= 0) return set_err(SOGPU_ERR_ARG, "sogpu_ball_gather_batch: bad argument");
     if (!h->built) return set_err(SOGPU_ERR_ARG, "sogpu_ball_gather_batch: call sogpu_build_grid first");
     CU(cudaSetDevice(h->device));
+    if (h->focused) { int rf = build_grid_impl(h, 0, 0); if (rf) return rf; }   /* arbitrary balls need every particle */
     int rc = ensure_query(h, nh);
     if (rc) return rc;
     rc = ensure_pinned(h, (size_t)nh * 4 * sizeof(float));
@@ -2440,6 +2616,10 @@ extern "C" int sogpu_get_stats(sogpu_t *h, sogpu_stats_t *out)
     if (h->built) {
         int rc = fetch_mass_state(h);
         if (rc) return rc;
+        uint32_t kept = 0;
+        CU(cudaMemcpyAsync(&kept, h->d_ce + h->ncell, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->stats.n_in_grid = (int64_t)kept;
     }
     if (h->have_result) {
         int rc = fetch_stats(h);

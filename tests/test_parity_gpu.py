@@ -159,6 +159,42 @@ def test_build_strategies_agree():
     assert np.array_equal(out[1]["mem"], ref["members"])
 
 
+@pytest.mark.parametrize("n_balls", [1, 2, 4])
+def test_focused_build_gives_identical_results(n_balls):
+    """sogpu_build_grid_for: only the neighbourhood of the halos is sorted; results are those of the
+    full grid, including halos that outgrow the planned reach (library falls back by itself)."""
+    s = synth.make_snapshot(64 ** 3, 120, seed=46, nmax=8000)
+    rng = np.random.default_rng(5)
+    vc = (rng.random((6, 3)) - 0.5).astype(np.float32)                 # void centres: -1 / -2
+    centers = np.concatenate([s.centers, vc])
+    rgtp = np.concatenate([s.rgtp, np.full(3, 0.004, np.float32), np.full(3, 0.03, np.float32)])
+    ref = po.Oracle(s.pos, s.mass).so(centers, rgtp, np.float32(200.0), 8)
+    g = api.SoGpu()
+    g.set_particles(s.pos, s.mass)
+    g.build_grid_for(centers, rgtp, n_balls)
+    g.keep_member_d2(True)
+    r = g.so(centers, rgtp, 200.0)
+    off, mem = g.members(sorted=True)
+    assert_so_equal(r, ref["rvir"], ref["mvir"], ref["ndelta"])
+    assert np.array_equal(mem, ref["members"])
+    # a ball gather on a focused grid silently rebuilds the full grid
+    idx, d2, n = g.ball_gather((0.0, 0.0, 0.0), np.float32(0.01))
+    oi, od = po.Oracle(s.pos, s.mass).ball((0.0, 0.0, 0.0), np.float32(0.01))
+    assert n == len(oi) and np.array_equal(idx, oi)
+    g.close()
+
+
+def test_focused_build_threshold_never_reached():
+    """Every halo outgrows any focus (-3 after the whole schedule): fallback to the full grid."""
+    s = synth.make_snapshot(24 ** 3, 4, seed=36, nmax=600)
+    g = api.SoGpu()
+    g.set_particles(s.pos, s.mass)
+    g.build_grid_for(s.centers, s.rgtp, 2)
+    r = g.so(s.centers, s.rgtp, 0.5)
+    assert (r["rvir"] == -3.0).all()
+    g.close()
+
+
 def test_records_layout_and_tiny_inputs():
     """AoS input with stride (tipsy dark records) and N smaller than the reference's nSmooth."""
     from so_b200 import tipsy
