@@ -51,7 +51,9 @@ const char *sogpu_last_error(void);
  * NULL = the handle's own stream).  Lets a caller time the kernels with its own events. */
 int sogpu_set_stream(sogpu_t *h, void *cuda_stream);
 /* Tuning knob: grid build strategy. -1 auto (default: MSD partition levels, then a shared-memory
- * bucket sort); 0 = no partition levels (one bucket holds everything; slow path for N > 3072). */
+ * bucket sort, both storing from registers straight to the final slot); 0 = no partition levels
+ * (one bucket holds everything; slow path for N > 3072); 2 = the staged variant of the same
+ * levels (each tile is first sorted in shared memory, then copied out in coalesced runs). */
 int sogpu_set_build_mode(sogpu_t *h, int mode);
 /* Tuning knob: target mean particles per grid cell (default 2.0). */
 int sogpu_set_cell_occupancy(sogpu_t *h, float particles_per_cell);

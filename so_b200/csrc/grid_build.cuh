@@ -418,3 +418,221 @@ __global__ void __launch_bounds__(BKT_THREADS, 2) k_bucket_sort(const float4 *__
         __syncthreads();
     }
 }
+
+/* ---- register-resident tile variants (default) --------------------------------------------------
+ * Same scheme as k_lvl_partition / k_bucket_sort, with about half the shared-memory operations per
+ * particle: a thread keeps its particles in registers while the tile's digit counts are scanned,
+ * then writes each particle ONCE to its sorted position in shared memory (the staged kernels write
+ * it unsorted and permute through an index array).  Smaller tiles (2048) and 45 KB of shared memory
+ * per CTA let three CTAs share an SM, so one CTA's load phase overlaps the others' shuffle phases.
+ * (A variant that stored from registers straight to global memory — no staging at all — was
+ * measured 1.4x SLOWER: 16-byte stores to 128 different runs per warp are partial-sector writes
+ * and are bound by L2 transaction rate, see profiles/.) */
+#define RT_NT 256
+#define RT_IT 8
+#define RT_T (RT_NT * RT_IT)          /* 2048 particles per tile */
+#define RT_SMEM (RT_T * (16 + 4 + 2))
+
+template <bool FIRST, bool WRITE_KEY>
+__global__ void __launch_bounds__(RT_NT, 3) k_lvl_partition_rt(const float4 *__restrict__ in4,
+                                                               const uint32_t *__restrict__ inkey, int64_t n,
+                                                               GridDev g, LevelDesc lv,
+                                                               const uint32_t *__restrict__ pstart,
+                                                               uint32_t *__restrict__ cursor,
+                                                               float4 *__restrict__ out4,
+                                                               uint32_t *__restrict__ outkey,
+                                                               const uint32_t *__restrict__ n_dev)
+{
+    if (n_dev) n = (int64_t)__ldg(n_dev);
+    extern __shared__ __align__(16) unsigned char raw[];      /* RT_SMEM bytes */
+    float4 *s4 = reinterpret_cast<float4 *>(raw);
+    uint32_t *sk = reinterpret_cast<uint32_t *>(s4 + RT_T);
+    uint16_t *sd = reinterpret_cast<uint16_t *>(sk + RT_T);
+    __shared__ uint32_t scnt[LVL_CMAX], soff[LVL_CMAX], sbase[LVL_CMAX], ws[RT_NT / 32], sres[2], stot;
+    const int C = 1 << lv.db;
+    const uint32_t cmask = (uint32_t)C - 1u;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    constexpr int CPT = LVL_CMAX / RT_NT;                     /* counts per thread in the scan */
+    for (int c = t; c < LVL_CMAX; c += RT_NT) scnt[c] = 0u;
+    __syncthreads();
+    const int64_t ntiles = (n + RT_T - 1) / RT_T;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint32_t pos = (uint32_t)(tile * RT_T);
+        const uint32_t tend = (uint32_t)min((int64_t)n, tile * RT_T + RT_T);
+        while (pos < tend) {
+            const uint32_t p = FIRST ? 0u : find_parent_block<RT_NT>(pstart, lv.n_parents, pos, sres);
+            const uint32_t send = FIRST ? tend : min(tend, __ldg(pstart + p + 1));
+            const int cnt = (int)(send - pos);
+            float4 q[RT_IT];
+            uint32_t key[RT_IT], dr[RT_IT];
+#pragma unroll
+            for (int k = 0; k < RT_IT; ++k) {
+                int i = t + k * RT_NT;
+                if (i < cnt) {
+                    q[k] = ld_stream(in4 + pos + i);
+                    if (!FIRST) key[k] = __ldg(inkey + pos + i);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < RT_IT; ++k) {
+                int i = t + k * RT_NT;
+                dr[k] = 0xFFFFFFFFu;
+                if (i < cnt) {
+                    bool kept = true;
+                    if (FIRST) {
+                        key[k] = cell_key_kept(q[k], g, kept);
+                        q[k].w = __int_as_float((int)(pos + i));          /* payload: original index */
+                    }
+                    if (kept) {
+                        uint32_t d = (key[k] >> lv.shift) & cmask;
+                        dr[k] = (d << 16) | atomicAdd(&scnt[d], 1u);
+                    }
+                }
+            }
+            __syncthreads();
+            {   /* exclusive scan of the counts (CPT consecutive children per thread) + run reservation */
+                uint32_t c0[CPT], sum = 0;
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) {
+                    int c = t * CPT + k;
+                    c0[k] = scnt[c];
+                    scnt[c] = 0u;                                          /* ready for the next tile */
+                    sum += c0[k];
+                }
+                uint32_t x = sum;
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t u = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                    if (lane >= o) x += u;
+                }
+                if (lane == 31) ws[w] = x;
+                __syncthreads();
+                uint32_t off = 0;
+                for (int k = 0; k < w; ++k) off += ws[k];
+                uint32_t run = off + x - sum;
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) {
+                    int c = t * CPT + k;
+                    if (c < C) {
+                        soff[c] = run;
+                        sbase[c] = c0[k] ? atomicAdd(&cursor[(size_t)p * C + c], c0[k]) - run : 0u;
+                    }
+                    run += c0[k];
+                }
+                if (t == RT_NT - 1) stot = run;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < RT_IT; ++k) {
+                if (dr[k] != 0xFFFFFFFFu) {
+                    uint32_t d = dr[k] >> 16, slot = soff[d] + (dr[k] & 0xFFFFu);
+                    s4[slot] = q[k];
+                    if (WRITE_KEY) sk[slot] = key[k];
+                    sd[slot] = (uint16_t)d;
+                }
+            }
+            __syncthreads();
+            const int kept_cnt = (int)stot;
+            for (int slot = t; slot < kept_cnt; slot += RT_NT) {
+                uint32_t dst = sbase[sd[slot]] + (uint32_t)slot;           /* sbase holds (run base - soff) */
+                out4[dst] = s4[slot];
+                if (WRITE_KEY) outkey[dst] = sk[slot];
+            }
+            pos = send;
+        }
+    }
+}
+
+/* final pass: one CTA per bucket, 256 threads, up to BR_IT particles per thread kept in registers
+ * with their (cell, rank); larger buckets (dense halo cores) read their particles a second time
+ * (an L2 hit).  Stores go straight to the final slot: the bucket's whole output range (16-50 KB)
+ * is written by this CTA within a microsecond, so the 16-byte stores merge in L2.  Only the cell
+ * counts live in shared memory (16 KB), which leaves room for 4 CTAs per SM. */
+#define BR_NT 256
+#define BR_IT 8
+
+__global__ void __launch_bounds__(BR_NT, 4) k_bucket_sort_rt(const float4 *__restrict__ in4, GridDev g, int cell_bits,
+                                                             uint32_t n_buckets, const uint32_t *__restrict__ bstart,
+                                                             float4 *__restrict__ sorted, uint32_t *__restrict__ ce,
+                                                             int first_pass_input_is_raw)
+{
+    __shared__ uint32_t cnt[BKT_CELLS];
+    __shared__ uint32_t ws[BR_NT / 32];
+    const int ncells = 1 << cell_bits;
+    const uint32_t cmask = (uint32_t)ncells - 1u;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int per = (ncells + BR_NT - 1) / BR_NT;
+    for (uint32_t b = blockIdx.x; b < n_buckets; b += gridDim.x) {
+        const uint32_t b0 = __ldg(bstart + b), b1 = __ldg(bstart + b + 1);
+        const uint32_t nb = b1 - b0;
+        if (nb == 0) {
+            for (int c = t; c < ncells; c += BR_NT) ce[((size_t)b << cell_bits) + c] = b0;
+            continue;
+        }
+        const bool in_regs = nb <= (uint32_t)(BR_NT * BR_IT);
+        for (int c = t; c < ncells; c += BR_NT) cnt[c] = 0u;
+        __syncthreads();
+        float4 q[BR_IT];
+        uint32_t cr[BR_IT];
+        if (in_regs) {
+#pragma unroll
+            for (int k = 0; k < BR_IT; ++k) {
+                uint32_t i = t + k * BR_NT;
+                if (i < nb) q[k] = ld_stream(in4 + b0 + i);
+            }
+#pragma unroll
+            for (int k = 0; k < BR_IT; ++k) {
+                uint32_t i = t + k * BR_NT;
+                if (i < nb) {
+                    if (first_pass_input_is_raw) q[k].w = __int_as_float((int)(b0 + i));
+                    uint32_t c = cell_key(q[k], g) & cmask;
+                    cr[k] = (c << 16) | atomicAdd(&cnt[c], 1u);
+                }
+            }
+        } else {
+            for (uint32_t i = t; i < nb; i += BR_NT) {
+                float4 qq = __ldg(in4 + b0 + i);
+                atomicAdd(&cnt[cell_key(qq, g) & cmask], 1u);
+            }
+        }
+        __syncthreads();
+        {
+            uint32_t s = 0;
+            const int c0 = t * per;
+            for (int k = 0; k < per; ++k) if (c0 + k < ncells) s += cnt[c0 + k];
+            uint32_t x = s;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t u = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                if (lane >= o) x += u;
+            }
+            if (lane == 31) ws[w] = x;
+            __syncthreads();
+            uint32_t off = 0;
+            for (int k = 0; k < w; ++k) off += ws[k];
+            uint32_t run = off + x - s;
+            for (int k = 0; k < per; ++k)
+                if (c0 + k < ncells) {
+                    uint32_t v = cnt[c0 + k];
+                    cnt[c0 + k] = run;
+                    ce[((size_t)b << cell_bits) + c0 + k] = b0 + run;
+                    run += v;
+                }
+        }
+        __syncthreads();
+        if (in_regs) {
+#pragma unroll
+            for (int k = 0; k < BR_IT; ++k) {
+                uint32_t i = t + k * BR_NT;
+                if (i < nb) sorted[b0 + cnt[cr[k] >> 16] + (cr[k] & 0xFFFFu)] = q[k];
+            }
+        } else {
+            for (uint32_t i = t; i < nb; i += BR_NT) {
+                float4 qq = __ldg(in4 + b0 + i);
+                if (first_pass_input_is_raw) qq.w = __int_as_float((int)(b0 + i));
+                uint32_t c = cell_key(qq, g) & cmask;
+                uint32_t dst = atomicAdd(&cnt[c], 1u);
+                sorted[b0 + dst] = qq;
+            }
+        }
+        __syncthreads();
+    }
+}

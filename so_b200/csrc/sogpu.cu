@@ -1527,6 +1527,7 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     h->pack_threads = 8;
     h->mass_state = -1;
     h->two_level = -1;
+    if (const char *e = getenv("SOGPU_BUILD_MODE")) h->two_level = atoi(e);   /* A/B knob, see sogpu_set_build_mode */
     h->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return set_err(SOGPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
@@ -1628,7 +1629,7 @@ extern "C" int sogpu_set_stream(sogpu_t *h, void *s)
 
 extern "C" int sogpu_set_build_mode(sogpu_t *h, int mode)
 {
-    if (!h || mode < -1 || mode > 1) return set_err(SOGPU_ERR_ARG, "bad build mode");
+    if (!h || mode < -1 || mode > 2) return set_err(SOGPU_ERR_ARG, "bad build mode");
     h->two_level = mode;
     return SOGPU_OK;
 }
@@ -1886,6 +1887,10 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         CU(cudaFuncSetAttribute(k_lvl_partition<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
         CU(cudaFuncSetAttribute(k_lvl_partition<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
         CU(cudaFuncSetAttribute(k_bucket_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bkt_smem));
+        CU(cudaFuncSetAttribute(k_lvl_partition_rt<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM));
+        CU(cudaFuncSetAttribute(k_lvl_partition_rt<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM));
+        CU(cudaFuncSetAttribute(k_lvl_partition_rt<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM));
+        CU(cudaFuncSetAttribute(k_lvl_partition_rt<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM));
         attr_done = true;
     }
     const int64_t tiles = (h->n + LVL_T - 1) / LVL_T;
@@ -1931,10 +1936,18 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         }
         {
             ProfScope p(h, KID_LVL_PARTITION, ((l ? 20.0 : 16.0) + 16.0 + (last ? 0.0 : 4.0)) * N);
-            if (l == 0 && !last) k_lvl_partition<true, true><<<part_grid, LVL_THREADS, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, nullptr);
-            else if (l == 0) k_lvl_partition<true, false><<<part_grid, LVL_THREADS, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, nullptr);
-            else if (!last) k_lvl_partition<false, true><<<part_grid, LVL_THREADS, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key, n_dev);
-            else k_lvl_partition<false, false><<<part_grid, LVL_THREADS, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key, n_dev);
+            if (h->two_level == 2) {       /* staged variant (tile sorted in shared memory first) */
+                if (l == 0 && !last) k_lvl_partition<true, true><<<part_grid, LVL_THREADS, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, nullptr);
+                else if (l == 0) k_lvl_partition<true, false><<<part_grid, LVL_THREADS, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, nullptr);
+                else if (!last) k_lvl_partition<false, true><<<part_grid, LVL_THREADS, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key, n_dev);
+                else k_lvl_partition<false, false><<<part_grid, LVL_THREADS, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key, n_dev);
+            } else {
+                const int sg = (int)std::min<int64_t>((h->n + RT_T - 1) / RT_T, (int64_t)h->sm_count * 3);
+                if (l == 0 && !last) k_lvl_partition_rt<true, true><<<sg, RT_NT, RT_SMEM, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, nullptr);
+                else if (l == 0) k_lvl_partition_rt<true, false><<<sg, RT_NT, RT_SMEM, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, nullptr);
+                else if (!last) k_lvl_partition_rt<false, true><<<sg, RT_NT, RT_SMEM, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key, n_dev);
+                else k_lvl_partition_rt<false, false><<<sg, RT_NT, RT_SMEM, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key, n_dev);
+            }
         }
         src = dst;
         src_key = dst_key;
@@ -1945,7 +1958,10 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         const uint32_t *bstart = h->d_lvl_start[L ? L - 1 : 0];
         int grid = (int)std::min<int64_t>((int64_t)nb, (int64_t)h->sm_count * 16);
         ProfScope p(h, KID_BUCKET_SORT, 32.0 * N + 4.0 * (double)ncell);
-        k_bucket_sort<<<grid, BKT_THREADS, bkt_smem, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, L == 0 ? 1 : 0);
+        if (h->two_level == 2)
+            k_bucket_sort<<<grid, BKT_THREADS, bkt_smem, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, L == 0 ? 1 : 0);
+        else
+            k_bucket_sort_rt<<<grid, BR_NT, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, L == 0 ? 1 : 0);
     }
     if (h->focused) k_copy_u32<<<1, 32, 0, s>>>(h->d_ce + ncell, h->d_lvl_start[0] + ((size_t)1 << db[0]));
     else k_store_u32<<<1, 32, 0, s>>>(h->d_ce + ncell, (uint32_t)h->n, nullptr, 0u);

@@ -143,7 +143,7 @@ def test_build_strategies_agree():
     """Single counting sort vs coarse-partition-first build: identical results."""
     s = synth.make_snapshot(80 ** 3, 60, seed=42, nmax=8000)
     out = []
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         g = api.SoGpu()
         g.set_build_mode(mode)
         g.set_particles(s.pos, s.mass)
@@ -153,7 +153,9 @@ def test_build_strategies_agree():
         r["off"], r["mem"] = g.members(sorted=True)
         out.append(r)
         g.close()
-    assert_so_equal(out[1], out[0]["rvir"], out[0]["mvir"], out[0]["ndelta"])
+    for o in out[1:]:
+        assert_so_equal(o, out[0]["rvir"], out[0]["mvir"], out[0]["ndelta"])
+        assert np.array_equal(out[0]["mem"], o["mem"])
     assert np.array_equal(out[0]["mem"], out[1]["mem"])
     ref = po.Oracle(s.pos, s.mass).so(s.centers, s.rgtp, np.float32(200.0), 8)
     assert np.array_equal(out[1]["mem"], ref["members"])
