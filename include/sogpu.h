@@ -55,6 +55,11 @@ int sogpu_set_stream(sogpu_t *h, void *cuda_stream);
  * (one bucket holds everything; slow path for N > 3072); 2 = the staged variant of the same
  * levels (each tile is first sorted in shared memory, then copied out in coalesced runs). */
 int sogpu_set_build_mode(sogpu_t *h, int mode);
+/* Tuning knob: which ball of kdRvir's schedule b_k = rgtp * 1.2^k (kd2.c:745,765-768) is gathered
+ * first (default 2; 1 = gather every ball like the reference).  Results do not depend on it: a ball
+ * only examines what smaller balls have not, the -1 test always counts the schedule's first ball,
+ * and the schedule's last ball is never skipped. */
+int sogpu_set_first_ball(sogpu_t *h, int k);
 /* Tuning knob: target mean particles per grid cell (default 2.0). */
 int sogpu_set_cell_occupancy(sogpu_t *h, float particles_per_cell);
 

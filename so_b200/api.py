@@ -27,7 +27,7 @@ SYMBOLS = [
     "sogpu_finish_host", "sogpu_keep_member_d2", "sogpu_profile_enable", "sogpu_profile_kernels",
     "sogpu_profile_name", "sogpu_profile_read", "sogpu_upload_particles",
     "sogpu_set_build_mode", "sogpu_ball_gather_batch",
-    "sogpu_profile_bytes", "sogpu_build_grid_for", "sogpu_build_grid_for_device",
+    "sogpu_profile_bytes", "sogpu_build_grid_for", "sogpu_build_grid_for_device", "sogpu_set_first_ball",
 ]
 
 
@@ -63,6 +63,8 @@ def lib():
     L.sogpu_last_error.argtypes = []
     L.sogpu_set_stream.argtypes = [vp, vp]
     L.sogpu_set_cell_occupancy.argtypes = [vp, C.c_float]
+    L.sogpu_set_first_ball.argtypes = [vp, C.c_int]
+    L.sogpu_set_first_ball.restype = C.c_int
     L.sogpu_set_build_mode.argtypes = [vp, C.c_int]
     L.sogpu_set_build_mode.restype = C.c_int
     L.sogpu_set_particles_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_int64, fp, fp]
@@ -167,6 +169,10 @@ class SoGpu:
 
     def set_stream(self, stream):
         _check(lib().sogpu_set_stream(self._h, C.c_void_p(int(stream) if stream else 0)))
+
+    def set_first_ball(self, k):
+        """First ball of the reference's schedule that is gathered (results do not depend on it)."""
+        _check(lib().sogpu_set_first_ball(self._h, int(k)))
 
     def set_build_mode(self, mode):
         """-1 auto, 0 single counting sort, 1 coarse partition first."""

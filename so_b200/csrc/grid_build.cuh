@@ -555,21 +555,32 @@ __global__ void __launch_bounds__(BR_NT, 4) k_bucket_sort_rt(const float4 *__res
                                                              float4 *__restrict__ sorted, uint32_t *__restrict__ ce,
                                                              int first_pass_input_is_raw)
 {
-    __shared__ uint32_t cnt[BKT_CELLS];
+    __shared__ __align__(16) uint32_t cnt[BKT_CELLS];
     __shared__ uint32_t ws[BR_NT / 32];
     const int ncells = 1 << cell_bits;
-    const uint32_t cmask = (uint32_t)ncells - 1u;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    /* scan layout: thread t owns the `per` consecutive cells starting at t*per; with >= 1024 cells
+     * per bucket (every build large enough to matter) `per` is a multiple of 4 and the counts are
+     * moved as uint4 */
     const int per = (ncells + BR_NT - 1) / BR_NT;
+    const bool vec = (ncells >= 4 * BR_NT);
+    uint4 *cnt4 = reinterpret_cast<uint4 *>(cnt);
+    uint32_t nx0 = 0, nx1 = 0;
+    if (blockIdx.x < n_buckets) { nx0 = __ldg(bstart + blockIdx.x); nx1 = __ldg(bstart + blockIdx.x + 1); }
     for (uint32_t b = blockIdx.x; b < n_buckets; b += gridDim.x) {
-        const uint32_t b0 = __ldg(bstart + b), b1 = __ldg(bstart + b + 1);
+        const uint32_t b0 = nx0, b1 = nx1;
         const uint32_t nb = b1 - b0;
-        if (nb == 0) {
-            for (int c = t; c < ncells; c += BR_NT) ce[((size_t)b << cell_bits) + c] = b0;
+        if (b + gridDim.x < n_buckets) {                                  /* bounds of the next bucket, early */
+            nx0 = __ldg(bstart + b + gridDim.x); nx1 = __ldg(bstart + b + gridDim.x + 1);
+        }
+        uint32_t *ceb = ce + ((size_t)b << cell_bits);
+        if (nb == 0) {                   /* empty bucket (focused builds): only its cell-table slice */
+            for (int c = t; c < ncells; c += BR_NT) ceb[c] = b0;
             continue;
         }
         const bool in_regs = nb <= (uint32_t)(BR_NT * BR_IT);
-        for (int c = t; c < ncells; c += BR_NT) cnt[c] = 0u;
+        if (vec) for (int c = t; c < ncells / 4; c += BR_NT) cnt4[c] = make_uint4(0u, 0u, 0u, 0u);
+        else for (int c = t; c < ncells; c += BR_NT) cnt[c] = 0u;
         __syncthreads();
         float4 q[BR_IT];
         uint32_t cr[BR_IT];
@@ -581,21 +592,50 @@ __global__ void __launch_bounds__(BR_NT, 4) k_bucket_sort_rt(const float4 *__res
             }
 #pragma unroll
             for (int k = 0; k < BR_IT; ++k) {
+                if ((uint32_t)(k * BR_NT) >= nb) break;                   /* uniform: nothing left for anyone */
                 uint32_t i = t + k * BR_NT;
                 if (i < nb) {
                     if (first_pass_input_is_raw) q[k].w = __int_as_float((int)(b0 + i));
-                    uint32_t c = cell_key(q[k], g) & cmask;
+                    uint32_t c = cell_key_low(q[k], g, cell_bits);
                     cr[k] = (c << 16) | atomicAdd(&cnt[c], 1u);
                 }
             }
         } else {
             for (uint32_t i = t; i < nb; i += BR_NT) {
                 float4 qq = __ldg(in4 + b0 + i);
-                atomicAdd(&cnt[cell_key(qq, g) & cmask], 1u);
+                atomicAdd(&cnt[cell_key_low(qq, g, cell_bits)], 1u);
             }
         }
         __syncthreads();
-        {
+        /* exclusive scan of the cell counts (in place) and the bucket's slice of the cell table */
+        if (vec) {
+            const int G = per / 4;
+            uint32_t s = 0;
+            for (int k = 0; k < G; ++k) {
+                uint4 v = cnt4[t * G + k];
+                s += v.x + v.y + v.z + v.w;
+            }
+            uint32_t x = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t u = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                if (lane >= o) x += u;
+            }
+            if (lane == 31) ws[w] = x;
+            __syncthreads();
+            uint32_t off = 0;
+#pragma unroll
+            for (int k = 0; k < BR_NT / 32; ++k) off += (k < w) ? ws[k] : 0u;
+            uint32_t run = off + x - s;
+            uint4 *ce4 = reinterpret_cast<uint4 *>(ceb);                  /* (b << cell_bits) is a multiple of 1024 */
+            for (int k = 0; k < G; ++k) {
+                uint4 v = cnt4[t * G + k], e;
+                e.x = run; e.y = e.x + v.x; e.z = e.y + v.y; e.w = e.z + v.z;
+                run = e.w + v.w;
+                cnt4[t * G + k] = e;
+                ce4[t * G + k] = make_uint4(b0 + e.x, b0 + e.y, b0 + e.z, b0 + e.w);
+            }
+        } else {
             uint32_t s = 0;
             const int c0 = t * per;
             for (int k = 0; k < per; ++k) if (c0 + k < ncells) s += cnt[c0 + k];
@@ -613,7 +653,7 @@ __global__ void __launch_bounds__(BR_NT, 4) k_bucket_sort_rt(const float4 *__res
                 if (c0 + k < ncells) {
                     uint32_t v = cnt[c0 + k];
                     cnt[c0 + k] = run;
-                    ce[((size_t)b << cell_bits) + c0 + k] = b0 + run;
+                    ceb[c0 + k] = b0 + run;
                     run += v;
                 }
         }
@@ -621,14 +661,16 @@ __global__ void __launch_bounds__(BR_NT, 4) k_bucket_sort_rt(const float4 *__res
         if (in_regs) {
 #pragma unroll
             for (int k = 0; k < BR_IT; ++k) {
+                if ((uint32_t)(k * BR_NT) >= nb) break;
                 uint32_t i = t + k * BR_NT;
                 if (i < nb) sorted[b0 + cnt[cr[k] >> 16] + (cr[k] & 0xFFFFu)] = q[k];
             }
         } else {
+            /* oversized bucket (a dense halo core): second read (L2), ranks from the shared cursors */
             for (uint32_t i = t; i < nb; i += BR_NT) {
                 float4 qq = __ldg(in4 + b0 + i);
                 if (first_pass_input_is_raw) qq.w = __int_as_float((int)(b0 + i));
-                uint32_t c = cell_key(qq, g) & cmask;
+                uint32_t c = cell_key_low(qq, g, cell_bits);
                 uint32_t dst = atomicAdd(&cnt[c], 1u);
                 sorted[b0 + dst] = qq;
             }

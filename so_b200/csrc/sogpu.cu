@@ -84,6 +84,7 @@ struct GridDev {
     const float4 *sorted;     /* particles in cell order: {x, y, z, original index as int bits} */
     const uint32_t *ce;       /* ce[c] = first sorted slot of cell c, ce[ncell] = N          */
     int nc, lb;               /* cells per axis (power of two), log2                         */
+    int tb;                   /* rows are ordered in tiles of 2^tb x 2^tb (iy, iz)           */
     float g0[3], invh[3];     /* cell coordinate = floor((x - g0) * invh) & (nc-1)           */
     float L[3], halfL[3];
     double dg0[3], dinvh[3], dh[3];
@@ -92,18 +93,13 @@ struct GridDev {
     int mb, ms;               /* mask cells per axis = 2^mb; fine cell coordinate >> ms        */
 };
 
-__device__ __forceinline__ uint32_t spread10(uint32_t x)
+/* rows of cells (fixed iy, iz) are contiguous along x; rows are ordered in 8x8 tiles of (iy, iz),
+ * tiles row-major: a ball's rows fall into a handful of contiguous stretches of the sorted array, and
+ * the key costs a few shifts (a Morton interleave of iy, iz gave the same locality for 3x the ALU work) */
+__device__ __forceinline__ uint32_t row_key(uint32_t iy, uint32_t iz, int lb, int tb)
 {
-    x &= 0x3ffu;
-    x = (x | (x << 8)) & 0x00ff00ffu;
-    x = (x | (x << 4)) & 0x0f0f0f0fu;
-    x = (x | (x << 2)) & 0x33333333u;
-    x = (x | (x << 1)) & 0x55555555u;
-    return x;
-}
-__device__ __forceinline__ uint32_t row_key(uint32_t iy, uint32_t iz)
-{
-    return spread10(iy) | (spread10(iz) << 1);
+    const uint32_t m = (1u << tb) - 1u;
+    return ((((iz >> tb) << (lb - tb)) | (iy >> tb)) << (2 * tb)) | ((iz & m) << tb) | (iy & m);
 }
 __device__ __forceinline__ uint32_t cell_coord(float x, float g0, float invh, int mask)
 {
@@ -116,7 +112,23 @@ __device__ __forceinline__ uint32_t cell_key(const float4 &p, const GridDev &g)
     uint32_t ix = cell_coord(p.x, g.g0[0], g.invh[0], mask);
     uint32_t iy = cell_coord(p.y, g.g0[1], g.invh[1], mask);
     uint32_t iz = cell_coord(p.z, g.g0[2], g.invh[2], mask);
-    return (row_key(iy, iz) << g.lb) | ix;
+    return (row_key(iy, iz, g.lb, g.tb) << g.lb) | ix;
+}
+
+/* the low `bits` bits of cell_key (the cell inside a final bucket): often x alone decides them */
+__device__ __forceinline__ uint32_t cell_key_low(const float4 &p, const GridDev &g, int bits)
+{
+    const int mask = g.nc - 1;
+    const uint32_t cm = (1u << bits) - 1u;
+    uint32_t ix = cell_coord(p.x, g.g0[0], g.invh[0], mask);
+    if (bits <= g.lb) return ix & cm;
+    uint32_t iy = cell_coord(p.y, g.g0[1], g.invh[1], mask);
+    uint32_t iz = cell_coord(p.z, g.g0[2], g.invh[2], mask);
+    if (bits <= g.lb + 2 * g.tb) {
+        const uint32_t m = (1u << g.tb) - 1u;
+        return (((((iz & m) << g.tb) | (iy & m)) << g.lb) | ix) & cm;
+    }
+    return ((row_key(iy, iz, g.lb, g.tb) << g.lb) | ix) & cm;
 }
 
 __device__ __forceinline__ bool mask_bit(const GridDev &g, uint32_t mx, uint32_t my, uint32_t mz)
@@ -132,7 +144,7 @@ __device__ __forceinline__ uint32_t cell_key_kept(const float4 &p, const GridDev
     uint32_t iy = cell_coord(p.y, g.g0[1], g.invh[1], mask);
     uint32_t iz = cell_coord(p.z, g.g0[2], g.invh[2], mask);
     kept = !g.mask || mask_bit(g, ix >> g.ms, iy >> g.ms, iz >> g.ms);
-    return (row_key(iy, iz) << g.lb) | ix;
+    return (row_key(iy, iz, g.lb, g.tb) << g.lb) | ix;
 }
 
 __device__ __forceinline__ float4 ld_stream(const float4 *p)
@@ -352,7 +364,7 @@ __device__ __forceinline__ void row_segments(const GridDev &g, const BallGeom &B
         nx = min(xhi - xlo + 1, g.nc);
         xa = xlo & mask;
     }
-    uint32_t rowbase = row_key((uint32_t)(iyu & mask), (uint32_t)(izu & mask)) << g.lb;
+    uint32_t rowbase = row_key((uint32_t)(iyu & mask), (uint32_t)(izu & mask), g.lb, g.tb) << g.lb;
     int n0 = min(nx, g.nc - xa);
     uint32_t a = __ldg(g.ce + rowbase + xa), e = __ldg(g.ce + rowbase + xa + n0);
     s0 = a; l0 = e - a;
@@ -424,12 +436,14 @@ struct HistF {          /* count particles with bits(r^2) in [lo,hi] into level 
     Center c;
     uint32_t lo_bits, hi_bits, shift, base;
     uint32_t *hist;
+    uint32_t first_bits, n_first;   /* side count: particles inside the FIRST ball of the schedule */
     __device__ __forceinline__ void operator()(uint32_t, const float4 &q)
     {
         uint32_t bits = __float_as_uint(dist2(c, q, *g));
         if (bits >= lo_bits && bits <= hi_bits) {   /* NaN (> 0x7f800000) never passes: hi is finite */
             uint32_t hb = bits >> shift;
             atomicAdd(&hist[hb > base ? hb - base : 0u], 1u);
+            n_first += (bits <= first_bits);
         }
     }
 };
@@ -653,7 +667,7 @@ struct HaloResult {
 
 template <int NT>
 __device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &sm, int tid,
-                        Center c, float rgtp, float thr, int nM, HaloResult &res,
+                        Center c, float rgtp, float thr, int nM, int first_ball, HaloResult &res,
                         uint32_t &ev_hist, uint32_t &ev_other)
 {
     typedef Cfg<NT> CF;
@@ -661,10 +675,20 @@ __device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &s
     float ball = rgtp;                                                   /* kd2.c:745 */
     uint32_t n_prev = 0;
     int kball = 0;
+    /* The reference gathers ball after ball of its schedule b_k = 1.2 b_(k-1) until a pair fires
+     * inside one (kd2.c:765-836).  Which ball that is does not change the answer: ball k examines
+     * exactly the pairs (j, j+1) with j+1 inside it that smaller balls have not examined, so the
+     * result is the first firing pair of the sorted list, found in the first ball that holds it.
+     * Any SUBSET of the schedule that ends with the same last ball therefore gives the same result
+     * (and the same -3), provided the -1 test still counts the FIRST ball (done on the side below).
+     * `steps` = how many schedule steps to advance before the next gather. */
+    int steps = first_ball;
     res.n = -3; res.m = -3.0f; res.key_j = 0ull;                         /* kd2.c:837-838 */
 
     while ((double)ball < 0.25 * (double)root) {                         /* kd2.c:766 */
         ball = so_next_ball(ball);                                       /* kd2.c:767 */
+        const float ball_k1 = ball;                                      /* (kball == 0: the schedule's first ball) */
+        for (int sk = 1; sk < steps && (double)ball < 0.25 * (double)root; ++sk) ball = so_next_ball(ball);
         const float ball2 = __fmul_rn(ball, ball);                       /* kd2.c:768 */
         if (!(ball2 < INFINITY) || !(ball > 0.0f)) break;
         const uint32_t ball_bits = __float_as_uint(ball2);
@@ -685,17 +709,23 @@ __device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &s
             return;
         }
         BallGeom B = make_geom(g, c, sqrt((double)ball2) * (1.0 + 1.0e-6));
+        uint32_t n_first;
         {
             HistF f;
             f.g = &g; f.c = c; f.lo_bits = 0u; f.hi_bits = ball_bits;
             f.shift = SHIFT0; f.base = lev[0].base; f.hist = sm.hist[0];
+            f.first_bits = __float_as_uint(__fmul_rn(ball_k1, ball_k1)); f.n_first = 0u;
             for_each_in_ball<NT>(g, sm, tid, B, f, ev_hist);
+            n_first = f.n_first;
         }
         const uint32_t n = scan_hist<NT>(sm.hist[0], sm.tmp, tid);       /* nParticles, kd2.c:769 */
 
-        if (kball == 0 && n < (uint32_t)nM) {                            /* kd2.c:772-778 */
-            res.n = -1; res.m = -1.0f;
-            return;
+        if (kball == 0) {                                                /* kd2.c:772-778 */
+            if (ball != ball_k1) n_first = gsum<NT>(n_first, sm.tmp, tid); else n_first = n;
+            if (n_first < (uint32_t)nM) {
+                res.n = -1; res.m = -1.0f;
+                return;
+            }
         }
         /* pairs (j, j+1) already examined in smaller balls: j <= n_prev-2 (kd2.c:804,832) */
         const uint32_t jmin = (kball == 0) ? (uint32_t)(nM - 2) : n_prev - 1u;
@@ -760,6 +790,7 @@ __device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &s
                     HistF f;
                     f.g = &g; f.c = c; f.lo_bits = nl.lo_bits; f.hi_bits = nl.hi_bits;
                     f.shift = nl.shift; f.base = nl.base; f.hist = sm.hist[L];
+                    f.first_bits = 0u; f.n_first = 0u;
                     for_each_in_ball<NT>(g, sm, tid, B2, f, ev_other);
                     scan_hist<NT>(sm.hist[L], sm.tmp, tid);
                     continue;
@@ -833,6 +864,14 @@ __device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &s
         }
         n_prev = n;                                                      /* kd2.c:832 */
         ++kball;
+        /* nothing fired: jump towards the radius where an isothermal profile (mean density ~ r^-2)
+         * through the density at this ball's edge would cross the threshold */
+        steps = 1;
+        if (n > 0u) {
+            const float b = sqrtf(ball2);
+            const float ratio = mt_eval(mt, n) / (4.18879f * b * b * b * thr);
+            if (ratio > 1.0f) steps = min(8, max(1, (int)rintf(0.5f * __log2f(ratio) * 3.8018f)));   /* / log2(1.2) */
+        }
     }
 }
 
@@ -852,6 +891,7 @@ struct QueryArgs {
     uint32_t *defer_n;
     float thr;
     int nM;
+    int first_ball;            /* schedule index (1-based) of the first ball gathered */
     int32_t *out_n;            /* N_Delta or a negative code */
     float *out_m;              /* M_Delta */
     unsigned long long *out_key;   /* (r^2 bits, index) of sorted element j */
@@ -905,7 +945,7 @@ __global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS) k_so_query(const __grid_c
         } else {
             Center c;
             c.x = a.centers[3 * h + 0]; c.y = a.centers[3 * h + 1]; c.z = a.centers[3 * h + 2];
-            so_halo<NT>(a.g, mt, sm, tid, c, a.rgtp[h], a.thr, a.nM, res, ev_hist, ev_other);
+            so_halo<NT>(a.g, mt, sm, tid, c, a.rgtp[h], a.thr, a.nM, a.first_ball, res, ev_hist, ev_other);
             gsync<NT>();
         }
         if (res.n == CODE_DEFER) {
@@ -1409,6 +1449,7 @@ struct sogpu {
     uint32_t *d_lvl_start[4];        /* child-bucket starts per level (+ sentinel) */
     uint32_t *d_lvl_cursor[4];       /* counts, then the atomic cursors of the partition */
     size_t lvl_cap[4];
+    int first_ball;                  /* first ball of the schedule that is gathered (1 = as the reference) */
     int two_level;                   /* -1 auto; 0: no partition levels (bucket sort only if it fits) */
     uint32_t *d_mask;                /* focused build: 2^(3*mb) bits */
     bool focused;                    /* the current grid holds only the focused region */
@@ -1527,6 +1568,8 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     h->pack_threads = 8;
     h->mass_state = -1;
     h->two_level = -1;
+    h->first_ball = 2;
+    if (const char *e = getenv("SOGPU_FIRST_BALL")) h->first_ball = std::max(1, atoi(e));
     if (const char *e = getenv("SOGPU_BUILD_MODE")) h->two_level = atoi(e);   /* A/B knob, see sogpu_set_build_mode */
     h->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
@@ -1631,6 +1674,13 @@ extern "C" int sogpu_set_build_mode(sogpu_t *h, int mode)
 {
     if (!h || mode < -1 || mode > 2) return set_err(SOGPU_ERR_ARG, "bad build mode");
     h->two_level = mode;
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_set_first_ball(sogpu_t *h, int k)
+{
+    if (!h || k < 1 || k > 64) return set_err(SOGPU_ERR_ARG, "bad first ball");
+    h->first_ball = k;
     return SOGPU_OK;
 }
 
@@ -1823,7 +1873,7 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
 
     GridDev &g = h->g;
     g.sorted = h->d_sorted; g.ce = h->d_ce;
-    g.nc = nc; g.lb = lb;
+    g.nc = nc; g.lb = lb; g.tb = std::min(lb, 3);
     double hmax = 0.0, lmin = 1e300;
     for (int k = 0; k < 3; ++k) {
         double Lk = (double)h->period[k];
@@ -2095,7 +2145,7 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
     QueryArgs a;
     a.g = h->g;
     a.centers = d_centers; a.rgtp = d_rgtp;
-    a.thr = thr; a.nM = nM;
+    a.thr = thr; a.nM = nM; a.first_ball = h->first_ball;
     a.out_n = h->d_out_n; a.out_m = h->d_out_m; a.out_key = h->d_out_key; a.out_off = h->d_out_off;
     a.members = h->d_members; a.md2 = h->want_d2 ? h->d_md2 : nullptr;
     a.member_cap = h->member_cap;

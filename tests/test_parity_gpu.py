@@ -12,10 +12,12 @@ pytestmark = pytest.mark.gpu
 
 
 def run_gpu(pos, mass, centers, rgtp, thr, n_members=8, period=(1.0, 1.0, 1.0), center=(0.0, 0.0, 0.0),
-            ppc=None):
+            ppc=None, first_ball=None):
     g = api.SoGpu()
     if ppc:
         g.set_cell_occupancy(ppc)
+    if first_ball:
+        g.set_first_ball(first_ball)
     g.set_particles(pos, mass, period, center)
     g.build_grid()
     g.keep_member_d2(True)
@@ -122,6 +124,22 @@ def test_nmembers_and_error_codes(nmem):
     rgtp = np.concatenate([s.rgtp, vr])
     r, ref = check_against_oracle(s.pos, s.mass, centers, rgtp, 200.0, n_members=nmem)
     assert set(np.unique(ref["rvir"][ref["rvir"] < 0])) <= {-1.0, -2.0, -3.0}
+
+
+@pytest.mark.parametrize("first_ball", [1, 2, 3, 7, 40])
+def test_ball_schedule_subset_gives_the_reference_results(first_ball):
+    """The library gathers a subset of kdRvir's ball schedule (kd2.c:765-768): starting at any ball, and
+    jumping ahead, must reproduce what the reference finds walking every ball, including the -1 test on
+    the schedule's FIRST ball, the -2 test and -3 at the schedule's LAST ball."""
+    s = synth.make_snapshot(40 ** 3, 30, seed=51, nmax=3000)
+    rng = np.random.default_rng(9)
+    vc = (rng.random((16, 3)) - 0.5).astype(np.float32)
+    vr = np.concatenate([np.full(6, 0.004), np.full(5, 0.02), np.full(5, 0.08)]).astype(np.float32)
+    centers = np.concatenate([s.centers, vc, s.centers[:8]])
+    rgtp = np.concatenate([s.rgtp, vr, s.rgtp[:8] * np.float32(0.3)])     # small first guesses: many steps
+    for thr in (200.0, 20.0, 0.7):
+        r, ref = check_against_oracle(s.pos, s.mass, centers, rgtp, thr, first_ball=first_ball)
+    assert (ref["rvir"] == -3.0).any()
 
 
 def test_threshold_never_reached_gives_minus3():
