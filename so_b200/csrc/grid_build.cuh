@@ -109,6 +109,66 @@ __global__ void __launch_bounds__(256) k_scan_apply(const uint32_t *a, int64_t n
     if (base <= n - 1 && n - 1 < base + 8) out[n] = run;   /* sentinel: total (= particles kept) */
 }
 
+/* the same exclusive scan by ONE block (bucket tables up to a few 10^5 entries: one launch instead of
+ * three): out[i] = sum a[0..i), copy[i] likewise, out[n] = total.  out may alias a. */
+#define SCAN1_PER 16
+__global__ void __launch_bounds__(1024) k_scan_one(const uint32_t *a, int64_t n, uint32_t *out, uint32_t *copy)
+{
+    __shared__ uint32_t ws[32];
+    __shared__ uint32_t carry_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) carry_s = 0u;
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < n; c0 += 1024 * SCAN1_PER) {
+        const int64_t base = c0 + (int64_t)t * SCAN1_PER;
+        uint32_t v[SCAN1_PER], s = 0;
+        if (base + SCAN1_PER <= n) {                       /* 64 contiguous bytes per thread */
+            const uint4 *a4 = reinterpret_cast<const uint4 *>(a + base);
+#pragma unroll
+            for (int k = 0; k < SCAN1_PER / 4; ++k) {
+                uint4 x4 = a4[k];
+                v[4 * k] = x4.x; v[4 * k + 1] = x4.y; v[4 * k + 2] = x4.z; v[4 * k + 3] = x4.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN1_PER; ++k) v[k] = (base + k < n) ? a[base + k] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < SCAN1_PER; ++k) s += v[k];
+        uint32_t x = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t u = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += u;
+        }
+        if (lane == 31) ws[w] = x;
+        __syncthreads();
+        if (w == 0) {
+            uint32_t y = ws[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t u = __shfl_up_sync(0xFFFFFFFFu, y, o);
+                if (lane >= o) y += u;
+            }
+            ws[lane] = y;
+        }
+        __syncthreads();
+        uint32_t run = carry_s + (w ? ws[w - 1] : 0u) + x - s;
+#pragma unroll
+        for (int k = 0; k < SCAN1_PER; ++k) {
+            if (base + k < n) {
+                out[base + k] = run;
+                if (copy) copy[base + k] = run;
+            }
+            run += v[k];
+        }
+        __syncthreads();
+        if (t == 1023) carry_s = run;
+        __syncthreads();
+    }
+    if (t == 0) out[n] = carry_s;
+}
+
 /* ---- level kernels ---------------------------------------------------------------------------- */
 
 #define LVL_T 4096           /* particles per tile */
@@ -182,20 +242,31 @@ __global__ void __launch_bounds__(256) k_lvl_hist(const float4 *__restrict__ in4
             uint32_t send = FIRST ? tend : min(tend, __ldg(pstart + p + 1));
             for (int c = threadIdx.x; c < C; c += 256) sh[c] = 0u;
             __syncthreads();
-            for (uint32_t i = pos + threadIdx.x; i < send; i += 256) {
-                uint32_t key;
-                bool kept = true;
-                if (FIRST) {
+            if (FIRST) {
+                for (uint32_t i = pos + threadIdx.x; i < send; i += 256) {
+                    bool kept = true;
                     float4 q = ld_stream(in4 + i);
-                    key = cell_key_kept(q, g, kept);
+                    uint32_t key = cell_key_kept(q, g, kept);
                     uint32_t mo = (q.w >= 0.0f) ? __float_as_uint(q.w) : 0xFFFFFFFEu;
                     if (!(q.w >= 0.0f)) mn = 0u;     /* negative / NaN mass: treated as "unequal" */
                     mn = min(mn, mo);
                     mx = max(mx, mo);
-                } else {
-                    key = __ldg(inkey + i);
+                    if (kept) atomicAdd(&sh[(key >> lv.shift) & cmask], 1u);
                 }
-                if (kept) atomicAdd(&sh[(key >> lv.shift) & cmask], 1u);
+            } else {
+                /* keys only: 16 per thread, all loads in flight before the first shared-memory atomic */
+                constexpr int KPT = LVL_T / 256;
+                uint32_t key[KPT];
+#pragma unroll
+                for (int k = 0; k < KPT; ++k) {
+                    uint32_t i = pos + threadIdx.x + k * 256;
+                    if (i < send) key[k] = __ldg(inkey + i);
+                }
+#pragma unroll
+                for (int k = 0; k < KPT; ++k) {
+                    uint32_t i = pos + threadIdx.x + k * 256;
+                    if (i < send) atomicAdd(&sh[(key[k] >> lv.shift) & cmask], 1u);
+                }
             }
             __syncthreads();
             for (int c = threadIdx.x; c < C; c += 256)

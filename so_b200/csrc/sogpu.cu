@@ -1013,6 +1013,18 @@ template <int NT> static size_t query_smem_bytes()
     return mt_bytes + g_bytes * Cfg<NT>::GROUPS;
 }
 
+/* append `item` to list[*n ..) for the lanes with pred set: one atomic per warp */
+__device__ __forceinline__ void warp_append(bool pred, int32_t item, int32_t *list, uint32_t *n)
+{
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, pred);
+    if (!m) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(n, (uint32_t)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = item;
+}
+
 /* split the halos into the warp-kernel list and the block-kernel list by expected ball size:
  * a halo of radius R ~ 1.25 rgtp at mean density thr holds thr*(4pi/3)R^3/m particles, the final
  * ball (1.2 R) about 1.3x that */
@@ -1020,17 +1032,44 @@ __global__ void k_classify(const float *__restrict__ rgtp, int nh, float thr, co
                            float small_max, float huge_min, int32_t *small_list, uint32_t *small_n,
                            int32_t *big_list, uint32_t *big_n, int32_t *huge_list, uint32_t *huge_n)
 {
-    int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= nh) return;
-    float r = 1.25f * rgtp[h];
+    int h = blockIdx.x * blockDim.x + threadIdx.x;          /* blockDim is a multiple of 32: whole warps stay */
+    const bool in = h < nh;
+    float r = 1.25f * (in ? rgtp[h] : 0.0f);
     float m = mt->n > 0 ? mt->m : 1.0f;
     float est = 1.3f * thr * 4.18879f * r * r * r / m;
-    if (!(est > small_max)) small_list[atomicAdd(small_n, 1u)] = h;
-    else if (!(est > huge_min)) big_list[atomicAdd(big_n, 1u)] = h;
-    else huge_list[atomicAdd(huge_n, 1u)] = h;
+    const bool sm = !(est > small_max), bg = !sm && !(est > huge_min);
+    warp_append(in && sm, h, small_list, small_n);
+    warp_append(in && bg, h, big_list, big_n);
+    warp_append(in && !sm && !bg, h, huge_list, huge_n);
 }
 
-/* exclusive scan of max(N_Delta,0) in catalog order -> member offsets; also the emit work lists */
+/* exclusive scan of max(N_Delta,0) in catalog order -> member offsets; also the emit work lists.
+ * One block; every thread owns OFF_PER consecutive halos per round, the three list cursors are
+ * scanned together with the offsets (packed 3 x 16 bit), so the lists need no atomics. */
+#define OFF_PER 8
+template <typename T> __device__ __forceinline__ T block_scan_incl_1024(T v, T *ws, int lane, int w)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) ws[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        T y = ws[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T t = __shfl_up_sync(0xFFFFFFFFu, y, o);
+            if (lane >= o) y += t;
+        }
+        ws[lane] = y;
+    }
+    __syncthreads();
+    if (w) v += ws[w - 1];
+    return v;
+}
+
 __global__ void __launch_bounds__(1024) k_offsets(const int32_t *__restrict__ out_n, int nh,
                                                   unsigned long long *__restrict__ out_off,
                                                   unsigned long long *__restrict__ total, int32_t emit_small_max,
@@ -1038,44 +1077,60 @@ __global__ void __launch_bounds__(1024) k_offsets(const int32_t *__restrict__ ou
                                                   uint32_t *big_n, int32_t emit_huge_min = 0x7FFFFFFF,
                                                   int32_t *huge_list = nullptr, uint32_t *huge_n = nullptr)
 {
-    __shared__ unsigned long long ws[32];
+    __shared__ unsigned long long ws[32], ws2[32];
     __shared__ unsigned long long carry;
-    if (threadIdx.x == 0) carry = 0ull;
+    __shared__ uint32_t carry_c[3];                /* entries already in the small / big / huge list */
+    if (threadIdx.x == 0) { carry = 0ull; carry_c[0] = carry_c[1] = carry_c[2] = 0u; }
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int b0 = 0; b0 < nh; b0 += 1024) {
-        int i = b0 + threadIdx.x;
-        int32_t n = (i < nh) ? out_n[i] : 0;
-        unsigned long long v = n > 0 ? (unsigned long long)n : 0ull, x = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= o) x += t;
-        }
-        if (lane == 31) ws[w] = x;
-        __syncthreads();
-        if (w == 0) {
-            unsigned long long y = ws[lane];
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, y, o);
-                if (lane >= o) y += t;
-            }
-            ws[lane] = y;
-        }
-        __syncthreads();
-        unsigned long long incl = x + (w ? ws[w - 1] : 0ull) + carry;
-        if (i < nh) {
-            out_off[i] = incl - v;
-            if (n > 0) {
-                if (n <= emit_small_max) small_list[atomicAdd(small_n, 1u)] = i;
-                else if (n < emit_huge_min || !huge_list) big_list[atomicAdd(big_n, 1u)] = i;
-                else huge_list[atomicAdd(huge_n, 1u)] = i;
+    for (int b0 = 0; b0 < nh; b0 += 1024 * OFF_PER) {
+        const int i0 = b0 + threadIdx.x * OFF_PER;
+        int32_t n[OFF_PER];
+        unsigned long long v = 0ull, cls = 0ull;
+#pragma unroll
+        for (int k = 0; k < OFF_PER; ++k) {
+            n[k] = (i0 + k < nh) ? out_n[i0 + k] : 0;
+            if (n[k] > 0) {
+                v += (unsigned long long)n[k];
+                const bool sm = n[k] <= emit_small_max, bg = !sm && (n[k] < emit_huge_min || !huge_list);
+                cls += sm ? 1ull : bg ? (1ull << 16) : (1ull << 32);
             }
         }
+        const unsigned long long incl = block_scan_incl_1024(v, ws, lane, w);
+        const unsigned long long cincl = block_scan_incl_1024(cls, ws2, lane, w);
+        unsigned long long run = carry + incl - v;
+        const unsigned long long cex = cincl - cls;          /* per round at most 8192 per list: 3 x 16 bits */
+        uint32_t ps = carry_c[0] + (uint32_t)(cex & 0xFFFFull);
+        uint32_t pb = carry_c[1] + (uint32_t)((cex >> 16) & 0xFFFFull);
+        uint32_t ph = carry_c[2] + (uint32_t)((cex >> 32) & 0xFFFFull);
+#pragma unroll
+        for (int k = 0; k < OFF_PER; ++k) {
+            if (i0 + k < nh) {
+                out_off[i0 + k] = run;
+                if (n[k] > 0) {
+                    run += (unsigned long long)n[k];
+                    const bool sm = n[k] <= emit_small_max, bg = !sm && (n[k] < emit_huge_min || !huge_list);
+                    if (sm) small_list[ps++] = i0 + k;
+                    else if (bg) big_list[pb++] = i0 + k;
+                    else huge_list[ph++] = i0 + k;
+                }
+            }
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) carry = incl;
+        if (threadIdx.x == 1023) {
+            carry += incl;
+            carry_c[0] += (uint32_t)(cincl & 0xFFFFull);
+            carry_c[1] += (uint32_t)((cincl >> 16) & 0xFFFFull);
+            carry_c[2] += (uint32_t)((cincl >> 32) & 0xFFFFull);
+        }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { out_off[nh] = carry; *total = carry; }
+    if (threadIdx.x == 0) {
+        out_off[nh] = carry; *total = carry;
+        *small_n = carry_c[0];
+        *big_n = carry_c[1];
+        if (huge_n) *huge_n = carry_c[2];
+    }
 }
 
 /* batched smBallGather, phase 1: count the particles with fDist2 <= ball2[h] (one warp per ball) */
@@ -1417,11 +1472,11 @@ enum {
     KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_N
 };
 static const char *const g_kernel_names[KID_N] = {
-    "k_lvl_hist", "k_scan(3 launches)", "k_lvl_partition", "k_bucket_sort", "k_mass_table", "k_classify",
+    "k_lvl_hist", "k_scan", "k_lvl_partition", "k_bucket_sort", "k_mass_table", "k_classify",
     "k_so_query<32>", "k_so_query<256>", "k_offsets", "k_so_emit<32>", "k_so_emit<256>", "k_ball_gather",
     "k_so_query<1024>", "k_so_emit<1024>", "k_mark_mask"};
 
-struct ProfRec { int kid; cudaEvent_t a, b; };
+struct ProfRec { int kid, launches; cudaEvent_t a, b; };
 
 struct sogpu {
     int device;
@@ -1449,6 +1504,8 @@ struct sogpu {
     uint32_t *d_lvl_start[4];        /* child-bucket starts per level (+ sentinel) */
     uint32_t *d_lvl_cursor[4];       /* counts, then the atomic cursors of the partition */
     size_t lvl_cap[4];
+    float cls_small_max, cls_huge_min;   /* expected ball population: warp / 256-thread CTA / 1024-thread CTA */
+    int emit_small_max, emit_huge_min;   /* same split for the member emission, by N_Delta */
     int first_ball;                  /* first ball of the schedule that is gathered (1 = as the reference) */
     int two_level;                   /* -1 auto; 0: no partition levels (bucket sort only if it fits) */
     uint32_t *d_mask;                /* focused build: 2^(3*mb) bits */
@@ -1518,12 +1575,12 @@ static cudaEvent_t prof_event(sogpu *h)
 }
 struct ProfScope {   /* brackets one (group of) kernel launch(es) with events when profiling is on */
     sogpu *h; ProfRec r; bool on;
-    ProfScope(sogpu *h_, int kid, double alg_bytes = 0.0) : h(h_), on(h_->prof_on)
+    ProfScope(sogpu *h_, int kid, double alg_bytes = 0.0, int launches = 1) : h(h_), on(h_->prof_on)
     {
-        h->stats.last_kernel_launches += (kid == KID_LVL_SCAN) ? 3 : 1;
+        h->stats.last_kernel_launches += launches;
         if (!on) return;
         h->prof_bytes[kid] += alg_bytes;
-        r.kid = kid; r.a = prof_event(h); r.b = prof_event(h);
+        r.kid = kid; r.launches = launches; r.a = prof_event(h); r.b = prof_event(h);
         cudaEventRecord(r.a, h->launch_stream);
     }
     ~ProfScope()
@@ -1569,6 +1626,12 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     h->mass_state = -1;
     h->two_level = -1;
     h->first_ball = 2;
+    h->cls_small_max = 1024.0f; h->cls_huge_min = 4096.0f;
+    h->emit_small_max = 2048; h->emit_huge_min = 4096;
+    if (const char *e = getenv("SOGPU_SMALL_MAX")) h->cls_small_max = (float)atof(e);
+    if (const char *e = getenv("SOGPU_HUGE_MIN")) h->cls_huge_min = (float)atof(e);
+    if (const char *e = getenv("SOGPU_EMIT_SMALL_MAX")) h->emit_small_max = atoi(e);
+    if (const char *e = getenv("SOGPU_EMIT_HUGE_MIN")) h->emit_huge_min = atoi(e);
     if (const char *e = getenv("SOGPU_FIRST_BALL")) h->first_ball = std::max(1, atoi(e));
     if (const char *e = getenv("SOGPU_BUILD_MODE")) h->two_level = atoi(e);   /* A/B knob, see sogpu_set_build_mode */
     h->sm_count = prop.multiProcessorCount;
@@ -1828,6 +1891,20 @@ static int pick_cells(int64_t n, float ppc, int *lb)
     return 1 << l;
 }
 
+/* the running-mass table needs only the mass min/max of the level-0 histogram pass: a one-thread
+ * kernel on a side stream, overlapped with the partition passes, joined at the end of the build */
+static int launch_mass_table(sogpu *h)
+{
+    CU(cudaEventRecord(h->ev_fork, h->stream));
+    CU(cudaStreamWaitEvent(h->aux[0], h->ev_fork, 0));
+    cudaStream_t keep = h->launch_stream;
+    h->launch_stream = h->aux[0];
+    { ProfScope p(h, KID_MASS_TABLE); k_mass_table<<<1, 32, 0, h->aux[0]>>>(h->d_massmm, h->d_mt, (unsigned long long)h->n + 2ull); }
+    h->launch_stream = keep;
+    CU(cudaEventRecord(h->ev_join[0], h->aux[0]));
+    return SOGPU_OK;
+}
+
 /* kdBuildTree replacement.  Fully asynchronous on the handle's stream (no host round trip).
  * focus_nh > 0: only the region the focus_nh halos in d_centers/d_rgtp can reach within
  * focus_balls steps of the ball schedule is kept (sogpu_build_grid_for). */
@@ -1955,6 +2032,7 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         CU(cudaMemsetAsync(h->d_lvl_cursor[0], 0, 2 * sizeof(uint32_t), s));
         { ProfScope p(h, KID_LVL_HIST, 16.0 * N);
           k_lvl_hist<true><<<hist_grid, 256, 0, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[0], h->d_massmm, nullptr); }
+        { int rc = launch_mass_table(h); if (rc) return rc; }
         k_store_u32<<<1, 32, 0, s>>>(h->d_lvl_start[0], 0u, h->d_lvl_start[0] + 1, (uint32_t)h->n);
     }
     for (int l = 0; l < L; ++l) {
@@ -1976,13 +2054,18 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
             if (l == 0) k_lvl_hist<true><<<hist_grid, 256, 0, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], h->d_massmm, nullptr);
             else k_lvl_hist<false><<<hist_grid, 256, 0, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], h->d_massmm, n_dev);
         }
+        if (l == 0) { int rc = launch_mass_table(h); if (rc) return rc; }
         {
-            ProfScope p(h, KID_LVL_SCAN, 12.0 * (double)M);
-            int64_t nt = ((int64_t)M + SCAN_TILE - 1) / SCAN_TILE;
-            k_scan_reduce<<<(unsigned)nt, 256, 0, s>>>(h->d_lvl_cursor[l], (int64_t)M, h->d_bsum);
-            k_scan_bsums<<<1, 1024, 0, s>>>(h->d_bsum, nt);
-            k_scan_apply<<<(unsigned)nt, 256, 0, s>>>(h->d_lvl_cursor[l], (int64_t)M, h->d_bsum, h->d_lvl_start[l],
-                                                     h->d_lvl_cursor[l]);
+            ProfScope p(h, KID_LVL_SCAN, 12.0 * (double)M, M <= ((size_t)1 << 18) ? 1 : 3);
+            if (M <= ((size_t)1 << 18)) {
+                k_scan_one<<<1, 1024, 0, s>>>(h->d_lvl_cursor[l], (int64_t)M, h->d_lvl_start[l], h->d_lvl_cursor[l]);
+            } else {
+                int64_t nt = ((int64_t)M + SCAN_TILE - 1) / SCAN_TILE;
+                k_scan_reduce<<<(unsigned)nt, 256, 0, s>>>(h->d_lvl_cursor[l], (int64_t)M, h->d_bsum);
+                k_scan_bsums<<<1, 1024, 0, s>>>(h->d_bsum, nt);
+                k_scan_apply<<<(unsigned)nt, 256, 0, s>>>(h->d_lvl_cursor[l], (int64_t)M, h->d_bsum, h->d_lvl_start[l],
+                                                         h->d_lvl_cursor[l]);
+            }
         }
         {
             ProfScope p(h, KID_LVL_PARTITION, ((l ? 20.0 : 16.0) + 16.0 + (last ? 0.0 : 4.0)) * N);
@@ -2015,7 +2098,7 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
     }
     if (h->focused) k_copy_u32<<<1, 32, 0, s>>>(h->d_ce + ncell, h->d_lvl_start[0] + ((size_t)1 << db[0]));
     else k_store_u32<<<1, 32, 0, s>>>(h->d_ce + ncell, (uint32_t)h->n, nullptr, 0u);
-    { ProfScope p(h, KID_MASS_TABLE); k_mass_table<<<1, 32, 0, s>>>(h->d_massmm, h->d_mt, (unsigned long long)h->n + 2ull); }
+    CU(cudaStreamWaitEvent(s, h->ev_join[0], 0));         /* the mass table (side stream) */
     CU(cudaGetLastError());
     h->built = true;
     h->have_result = false;
@@ -2135,7 +2218,7 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
 
     /* counters: 0 small_n 1 big_n 2 work_small 3 work_big 4 flags 5 esmall_n 6 ebig_n 7 work_es 8 work_eb
      *           13 huge_n 14 work_huge 15 ehuge_n 16 work_ehuge   (9-12: general path) */
-    const float small_max = 1024.0f, huge_min = 16384.0f;
+    const float small_max = h->cls_small_max, huge_min = h->cls_huge_min;
     {
         ProfScope p(h, KID_CLASSIFY);
         k_classify<<<(nh + 255) / 256, 256, 0, s>>>(d_rgtp, nh, thr, h->d_mt, small_max, huge_min, h->d_small,
@@ -2179,8 +2262,8 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
     /* member offsets in catalog order, then the member lists (again three classes side by side) */
     {
         ProfScope p(h, KID_OFFSETS);
-        k_offsets<<<1, 1024, 0, s>>>(h->d_out_n, nh, h->d_out_off, h->d_u64 + 0, 2048, h->d_esmall,
-                                     h->d_counters + 5, h->d_ebig, h->d_counters + 6, 131072, h->d_ehuge,
+        k_offsets<<<1, 1024, 0, s>>>(h->d_out_n, nh, h->d_out_off, h->d_u64 + 0, h->emit_small_max, h->d_esmall,
+                                     h->d_counters + 5, h->d_ebig, h->d_counters + 6, h->emit_huge_min, h->d_ehuge,
                                      h->d_counters + 15);
     }
     CU(cudaEventRecord(h->ev_fork, s));
@@ -2717,7 +2800,7 @@ extern "C" int sogpu_profile_read(sogpu_t *h, double *ms, int64_t *launches, int
         float t = 0.0f;
         if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) {
             h->prof_ms[r.kid] += (double)t;
-            h->prof_launches[r.kid] += (r.kid == KID_LVL_SCAN) ? 3 : 1;
+            h->prof_launches[r.kid] += r.launches;
         }
         h->prof_pool.push_back(r.a);
         h->prof_pool.push_back(r.b);
