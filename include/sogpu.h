@@ -147,6 +147,23 @@ int sogpu_ball_gather(sogpu_t *h, const float center[3], float ball2, int32_t *i
  * is the 2*Rvir gather of kdVcirc (kd2.c:511-514) for all halos in one pass. */
 int sogpu_ball_gather_batch(sogpu_t *h, const float *centers, const float *ball2, int32_t nh);
 
+/* ---- kdVcirc + kdMassProfile replacement (kd2.c:498-586, 458-496) ---------------------------- */
+
+/* For each of the nh groups (centre, fRvir > 0, fMvir): gathers the ball of radius 2*fRvir
+ * (kd2.c:511-514), sorts it by fDist2 and returns, exactly as the reference computes them in fp32:
+ *   vcirc[8*i .. +8)   Vc = sqrt(G M(<r)/r) at r = 0.25, 0.5 .. 1.75 Rvir, and over the whole ball at 2 Rvir
+ *   rmass[2*i .. +2)   radius of the particle at which the cumulative mass reaches Mvir/4, Mvir/2
+ *   rmax[i], vmax[i]   first maximum of Vc over the sorted list from particle nMembers on
+ *   profile[16*i..+16) cumulative mass of ALL particles inside r = 0.125 .. 1.875 Rvir, and in the whole
+ *                      ball (may be NULL): the -dark/-gas/-star profile of a single-species snapshot
+ * G is kdSetUniverse's constant (so.c: G = 1).  The sorted 2*Rvir lists stay available through
+ * sogpu_members().  Equal particle masses only: returns SOGPU_ERR_UNSUPPORTED for a mixed-mass
+ * snapshot (per-species sums then depend on which particle sits at which rank; the host program
+ * walks the sorted lists itself in that case). */
+int sogpu_vcirc(sogpu_t *h, const float *centers, const float *rvir, const float *mvir, int32_t nh,
+                float G, int32_t nMembers, float *vcirc, float *rmass, float *rmax, float *vmax,
+                float *profile);
+
 /* ---- introspection --------------------------------------------------------------------------- */
 
 typedef struct {

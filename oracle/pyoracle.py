@@ -68,6 +68,9 @@ def lib():
         L.so_oracle_tag.restype = C.c_int
         L.so_oracle_tag.argtypes = [C.c_void_p, C.c_int, i32p, fp, fp, fp, fp, C.POINTER(i64), i32p,
                                     fp, i64, i32p, i32p, i32p, fp, i32p]
+        L.so_oracle_vcirc.restype = C.c_int
+        L.so_oracle_vcirc.argtypes = [C.c_void_p, fp, C.c_float, C.c_float, C.c_float, C.c_int, fp, fp, fp, fp, fp,
+                                      C.POINTER(C.c_ubyte), C.c_int]
         _lib = L
     return _lib
 
@@ -145,6 +148,30 @@ class Oracle:
         idx = np.ctypeslib.as_array(lib().so_oracle_ball_index(self._h), (max(n, 1),))[:n].copy()
         d2 = np.ctypeslib.as_array(lib().so_oracle_ball_d2(self._h), (max(n, 1),))[:n].copy()
         return idx, d2
+
+    def vcirc(self, centers, rvir, mvir, G=1.0, n_members=8, ptype_of=None, ptype_mask=0xFF):
+        """kdVcirc + kdMassProfile (kd2.c:498-586, 458-496) for every group with rvir > 0."""
+        centers = np.ascontiguousarray(centers, np.float32).reshape(-1, 3)
+        h = len(centers)
+        out = {"vcirc": np.zeros((h, 8), np.float32), "rmass": np.zeros((h, 2), np.float32),
+               "rmax": np.zeros(h, np.float32), "vmax": np.zeros(h, np.float32),
+               "profile": np.zeros((h, 16), np.float32)}
+        pt = None
+        if ptype_of is not None:
+            ptype_of = np.ascontiguousarray(ptype_of, np.uint8)
+            pt = ptype_of.ctypes.data_as(C.POINTER(C.c_ubyte))
+        for i in range(h):
+            if not rvir[i] > 0:
+                continue
+            rm, vm = C.c_float(), C.c_float()
+            rc = lib().so_oracle_vcirc(self._h, _fp(centers[i]), C.c_float(rvir[i]), C.c_float(mvir[i]), C.c_float(G),
+                                       int(n_members), _fp(out["vcirc"][i]), _fp(out["rmass"][i]),
+                                       C.cast(C.byref(rm), C.POINTER(C.c_float)), C.cast(C.byref(vm), C.POINTER(C.c_float)),
+                                       _fp(out["profile"][i]), pt, int(ptype_mask))
+            if rc:
+                raise RuntimeError("so_oracle_vcirc failed")
+            out["rmax"][i], out["vmax"][i] = rm.value, vm.value
+        return out
 
     def rvir(self, c, rgtp, thr, n_members=8):
         c = np.asarray(c, np.float32)

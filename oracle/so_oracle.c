@@ -433,3 +433,80 @@ int so_oracle_tag(const so_oracle_t *o, int h, const int32_t *index, const float
     free(order);
     return 0;
 }
+
+/* ---- kdVcirc / kdMassProfile, kd2.c:498-586 and 458-496 ------------------------------------------ */
+
+int so_oracle_vcirc(so_oracle_t *o, const float c[3], float rvir, float mvir, float G, int n_members,
+                    float *vcirc, float *rmass, float *rmax, float *vmax, float *profile,
+                    const unsigned char *ptype_of, int ptype_mask)
+{
+    int i;
+    int64_t j, n;
+    float fBall, fBall2, mass, m, r, r2, vm, rm, vc, fmin, f;
+    fmin = 2.0 / 8;                                                       /* kd2.c:507 (NVCIRC = 8) */
+    fBall = 2. * rvir;                                                    /* kd2.c:511 */
+    fBall2 = fBall * fBall;
+    n = so_oracle_ball(o, c, fBall2);                                     /* kd2.c:513-514 */
+    if (n <= 0) return -1;
+    j = 0;
+    mass = 0.0;
+    for (f = fmin, i = 0; i < 8 - 1; ++i, f += fmin) {                    /* kd2.c:517-526 */
+        r = f * rvir;
+        r2 = r * r;
+        while (j < n && o->list[j].d2 < r2) {
+            mass += mass_of(o, o->list[j].idx);
+            ++j;
+        }
+        vcirc[i] = sqrt(G * mass / r);
+    }
+    while (j < n) {                                                       /* kd2.c:528-531 */
+        mass += mass_of(o, o->list[j].idx);
+        ++j;
+    }
+    vcirc[8 - 1] = sqrt(G * mass / fBall);
+    for (f = 0.25, i = 0; i < 2; ++i, f += 0.25) {                        /* kd2.c:537-546 */
+        m = f * mvir;
+        j = 0;
+        mass = mass_of(o, o->list[0].idx);
+        while (mass < m && j + 1 < n) {
+            ++j;
+            mass += mass_of(o, o->list[j].idx);
+        }
+        rmass[i] = sqrt(o->list[j].d2);
+    }
+    mass = 0.;                                                            /* kd2.c:551-569 */
+    for (j = 0; j < n_members && j < n; ++j) mass += mass_of(o, o->list[j].idx);
+    rm = sqrt(o->list[(n_members <= n ? n_members : n) - 1].d2);
+    vm = sqrt(G * mass / rm);
+    for (j = n_members; j < n; ++j) {
+        mass += mass_of(o, o->list[j].idx);
+        r = sqrt(o->list[j].d2);
+        vc = sqrt(G * mass / r);
+        if (vc > vm) {
+            vm = vc;
+            rm = r;
+        }
+    }
+    *rmax = rm;
+    *vmax = vm;
+    if (profile) {                                                        /* kd2.c:458-496 */
+        fmin = 2.0 / 16;
+        j = 0;
+        mass = 0.0;
+        for (f = fmin, i = 0; i < 16 - 1; ++i, f += fmin) {
+            r = f * rvir;
+            r2 = r * r;
+            while (j < n && o->list[j].d2 < r2) {
+                if (!ptype_of || (ptype_of[o->list[j].idx] & ptype_mask)) mass += mass_of(o, o->list[j].idx);
+                ++j;
+            }
+            profile[i] = mass;
+        }
+        while (j < n) {
+            if (!ptype_of || (ptype_of[o->list[j].idx] & ptype_mask)) mass += mass_of(o, o->list[j].idx);
+            ++j;
+        }
+        profile[16 - 1] = mass;
+    }
+    return 0;
+}

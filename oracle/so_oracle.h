@@ -59,6 +59,15 @@ int so_oracle_so(so_oracle_t *o, const float *centers, const float *rgtp, int h,
                  int32_t **members, int64_t *nevals);
 void so_oracle_free(void *p);
 
+/* kdVcirc (kd2.c:498-586) + kdMassProfile (kd2.c:458-496) for one group with fRvir > 0: gathers and
+ * sorts the 2*Rvir ball, then walks it exactly like the reference (sequential fp32 sums).
+ * vcirc[8], rmass[2], *rmax, *vmax; profile[16] (may be NULL) = kdMassProfile of the particles whose
+ * type flag ptype_of[i] & ptype_mask is non-zero (ptype_of NULL: every particle counts).
+ * The reference's unguarded while(mass < m) (kd2.c:540) is bounded by the list length here. */
+int so_oracle_vcirc(so_oracle_t *o, const float c[3], float rvir, float mvir, float G, int n_members,
+                    float *vcirc, float *rmass, float *rmax, float *vmax, float *profile,
+                    const unsigned char *ptype_of, int ptype_mask);
+
 /* indexx (nr.c:91-151): ascending argsort, indx values are 1-based like the reference. */
 void so_oracle_indexx(int n, const float *arr, int32_t *indx);
 

@@ -27,7 +27,7 @@ SYMBOLS = [
     "sogpu_finish_host", "sogpu_keep_member_d2", "sogpu_profile_enable", "sogpu_profile_kernels",
     "sogpu_profile_name", "sogpu_profile_read", "sogpu_upload_particles",
     "sogpu_set_build_mode", "sogpu_ball_gather_batch",
-    "sogpu_profile_bytes", "sogpu_build_grid_for", "sogpu_build_grid_for_device", "sogpu_set_first_ball",
+    "sogpu_profile_bytes", "sogpu_build_grid_for", "sogpu_build_grid_for_device", "sogpu_set_first_ball", "sogpu_vcirc",
 ]
 
 
@@ -63,6 +63,8 @@ def lib():
     L.sogpu_last_error.argtypes = []
     L.sogpu_set_stream.argtypes = [vp, vp]
     L.sogpu_set_cell_occupancy.argtypes = [vp, C.c_float]
+    L.sogpu_vcirc.argtypes = [vp, fp, fp, fp, C.c_int32, C.c_float, C.c_int32, fp, fp, fp, fp, fp]
+    L.sogpu_vcirc.restype = C.c_int
     L.sogpu_set_first_ball.argtypes = [vp, C.c_int]
     L.sogpu_set_first_ball.restype = C.c_int
     L.sogpu_set_build_mode.argtypes = [vp, C.c_int]
@@ -330,6 +332,21 @@ class SoGpu:
         _check(lib().sogpu_ball_gather_batch(self._h, _fp(centers), _fp(ball2), len(ball2)))
         self._last_h = len(ball2)
         return self.members(want_d2=True, sorted=sorted)
+
+    def vcirc(self, centers, rvir, mvir, G=1.0, n_members=8, profile=True):
+        """kdVcirc / kdMassProfile (kd2.c:498-586) for groups with rvir > 0, on the device."""
+        centers = np.ascontiguousarray(centers, np.float32).reshape(-1, 3)
+        rvir = np.ascontiguousarray(rvir, np.float32)
+        mvir = np.ascontiguousarray(mvir, np.float32)
+        h = len(rvir)
+        out = {"vcirc": np.zeros((h, 8), np.float32), "rmass": np.zeros((h, 2), np.float32),
+               "rmax": np.zeros(h, np.float32), "vmax": np.zeros(h, np.float32),
+               "profile": np.zeros((h, 16), np.float32) if profile else None}
+        _check(lib().sogpu_vcirc(self._h, _fp(centers), _fp(rvir), _fp(mvir), h, C.c_float(G), int(n_members),
+                                 _fp(out["vcirc"]), _fp(out["rmass"]), _fp(out["rmax"]), _fp(out["vmax"]),
+                                 _fp(out["profile"]) if profile else None))
+        self._last_h = h
+        return out
 
     def stats(self):
         s = Stats()

@@ -1464,17 +1464,152 @@ __global__ void k_select_code(const int32_t *out_n, int nh, int32_t code, int32_
 }
 
 /* ============================================================================================
+ * kdVcirc + kdMassProfile (kd2.c:498-586, 458-496) over the r^2-sorted 2*Rvir lists, equal masses:
+ * the reference's cumulative fp32 mass after k particles is S[k] (mass table), so every quantity
+ * is a rank query on the sorted r^2 list.  One 256-thread CTA per group.
+ * ============================================================================================ */
+#define SO_NVCIRC 8          /* kd2.h:9  */
+#define SO_NMASSPROFILE 16   /* kd2.h:11 */
+
+struct VcircArgs {
+    const float *d2;                      /* sorted r^2 of all lists, CSR */
+    const unsigned long long *off;        /* nh + 1 */
+    const float *rvir, *mvir;
+    const so_mass_table *mt;
+    float G;
+    int nM, nh;
+    float *vcirc, *rmass, *rmax, *vmax, *profile;   /* 8, 2, 1, 1, 16 per group (profile may be NULL) */
+};
+
+__device__ __forceinline__ uint32_t lower_bound_f(const float *__restrict__ a, uint32_t n, float x)
+{
+    uint32_t lo = 0, hi = n;                       /* first j with !(a[j] < x): the reference's while (d2[j] < r2) */
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) k_vcirc(const __grid_constant__ VcircArgs a)
+{
+    __shared__ MassTableS mt;
+    __shared__ float s_v[8];
+    __shared__ uint32_t s_j[8];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int mtn = a.mt->n;
+    if (t == 0) { mt.n = mtn; mt.m = a.mt->m; }
+    for (int i = t; i <= mtn; i += 256) mt.k0[i] = a.mt->k0[i];
+    for (int i = t; i < mtn; i += 256) { mt.s0[i] = a.mt->s0[i]; mt.inc[i] = a.mt->inc[i]; }
+    __syncthreads();
+    for (int h = blockIdx.x; h < a.nh; h += gridDim.x) {
+        const unsigned long long o = a.off[h];
+        const uint32_t n = (uint32_t)(a.off[h + 1] - o);
+        const float *d2 = a.d2 + o;
+        const float rvir = a.rvir[h], mvir = a.mvir[h];
+        if (n == 0) {                              /* cannot happen for a resolved group (N_Delta >= nMembers) */
+            if (t < SO_NVCIRC) a.vcirc[(size_t)h * SO_NVCIRC + t] = 0.0f;
+            if (t < 2) a.rmass[(size_t)h * 2 + t] = 0.0f;
+            if (t == 0) { a.rmax[h] = 0.0f; a.vmax[h] = 0.0f; }
+            if (a.profile && t < SO_NMASSPROFILE) a.profile[(size_t)h * SO_NMASSPROFILE + t] = 0.0f;
+            continue;
+        }
+        if (t < SO_NVCIRC) {                       /* kd2.c:517-531 */
+            const float fmin = (float)(2.0 / SO_NVCIRC);
+            float f = fmin;
+            for (int i = 0; i < t; ++i) f = __fadd_rn(f, fmin);
+            float v;
+            if (t < SO_NVCIRC - 1) {
+                const float r = __fmul_rn(f, rvir), r2 = __fmul_rn(r, r);
+                const float mass = mt_eval(mt, lower_bound_f(d2, n, r2));
+                v = __fsqrt_rn(__fdiv_rn(__fmul_rn(a.G, mass), r));
+            } else {
+                const float fBall = 2.0f * rvir;
+                v = __fsqrt_rn(__fdiv_rn(__fmul_rn(a.G, mt_eval(mt, n)), fBall));
+            }
+            a.vcirc[(size_t)h * SO_NVCIRC + t] = v;
+        } else if (t >= 32 && t < 32 + 2) {        /* kd2.c:537-546: radii holding 1/4 and 1/2 of Mvir */
+            const int i = t - 32;
+            const float f = i ? 0.5f : 0.25f, m = __fmul_rn(f, mvir);
+            uint32_t lo = 0, hi = n - 1;           /* first j with S[j+1] >= m, at most n-1 */
+            while (lo < hi) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (mt_eval(mt, mid + 1u) < m) lo = mid + 1; else hi = mid;
+            }
+            a.rmass[(size_t)h * 2 + i] = __fsqrt_rn(__ldg(d2 + lo));
+        } else if (a.profile && t >= 64 && t < 64 + SO_NMASSPROFILE) {   /* kd2.c:458-496, every particle counted */
+            const int i = t - 64;
+            const float fmin = (float)(2.0 / SO_NMASSPROFILE);
+            float f = fmin;
+            for (int k = 0; k < i; ++k) f = __fadd_rn(f, fmin);
+            float mass;
+            if (i < SO_NMASSPROFILE - 1) {
+                const float r = __fmul_rn(f, rvir), r2 = __fmul_rn(r, r);
+                mass = mt_eval(mt, lower_bound_f(d2, n, r2));
+            } else {
+                mass = mt_eval(mt, n);
+            }
+            a.profile[(size_t)h * SO_NMASSPROFILE + i] = mass;
+        }
+        /* kd2.c:551-569: maximum of Vc over the list from the nMembers-th particle on, first maximum wins */
+        const uint32_t j0 = ((uint32_t)a.nM <= n ? (uint32_t)a.nM : n) - 1u;
+        float best = -1.0f;
+        uint32_t bj = 0xFFFFFFFFu;
+        for (uint32_t j = j0 + (uint32_t)t; j < n; j += 256u) {
+            const float r = __fsqrt_rn(__ldg(d2 + j));
+            const float vc = __fsqrt_rn(__fdiv_rn(__fmul_rn(a.G, mt_eval(mt, j + 1u)), r));
+            if (vc > best) { best = vc; bj = j; }          /* ascending j per thread: keeps the first */
+        }
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+            float ov = __shfl_down_sync(0xFFFFFFFFu, best, o2);
+            uint32_t oj = __shfl_down_sync(0xFFFFFFFFu, bj, o2);
+            if (ov > best || (ov == best && oj < bj)) { best = ov; bj = oj; }
+        }
+        if (lane == 0) { s_v[w] = best; s_j[w] = bj; }
+        __syncthreads();
+        if (t == 0) {
+            for (int k = 1; k < 8; ++k)
+                if (s_v[k] > best || (s_v[k] == best && s_j[k] < bj)) { best = s_v[k]; bj = s_j[k]; }
+            a.vmax[h] = best;
+            a.rmax[h] = __fsqrt_rn(__ldg(d2 + bj));
+        }
+        __syncthreads();
+    }
+}
+
+/* member lists -> sortable keys and back: ascending (fDist2 bits, original index) is the order the
+ * reference's qsort(CmpList) + stable merge gives for distinct r^2 (kd2.c:425-435,781) */
+__global__ void __launch_bounds__(256) k_member_keys(const int32_t *__restrict__ idx, const float *__restrict__ d2,
+                                                     unsigned long long n, unsigned long long *__restrict__ keys)
+{
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        keys[i] = ((unsigned long long)__float_as_uint(d2[i]) << 32) | (uint32_t)idx[i];
+}
+__global__ void __launch_bounds__(256) k_member_unkeys(const unsigned long long *__restrict__ keys, unsigned long long n,
+                                                       int32_t *__restrict__ idx, float *__restrict__ d2)
+{
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        unsigned long long k = keys[i];
+        idx[i] = (int32_t)(uint32_t)k;
+        d2[i] = __uint_as_float((uint32_t)(k >> 32));
+    }
+}
+
+/* ============================================================================================
  * host side
  * ============================================================================================ */
 enum {
     KID_LVL_HIST = 0, KID_LVL_SCAN, KID_LVL_PARTITION, KID_BUCKET_SORT, KID_MASS_TABLE, KID_CLASSIFY,
     KID_QUERY_WARP, KID_QUERY_BLOCK, KID_OFFSETS, KID_EMIT_WARP, KID_EMIT_BLOCK, KID_BALL_GATHER,
-    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_N
+    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_VCIRC, KID_N
 };
 static const char *const g_kernel_names[KID_N] = {
     "k_lvl_hist", "k_scan", "k_lvl_partition", "k_bucket_sort", "k_mass_table", "k_classify",
     "k_so_query<32>", "k_so_query<256>", "k_offsets", "k_so_emit<32>", "k_so_emit<256>", "k_ball_gather",
-    "k_so_query<1024>", "k_so_emit<1024>", "k_mark_mask"};
+    "k_so_query<1024>", "k_so_emit<1024>", "k_mark_mask", "k_vcirc"};
 
 struct ProfRec { int kid, launches; cudaEvent_t a, b; };
 
@@ -1536,6 +1671,9 @@ struct sogpu {
     bool have_result;
     bool want_d2;
     bool member_overflow;
+    float *d_vc;                     /* sogpu_vcirc: per-group inputs and outputs */
+    size_t vc_cap;
+    bool members_sorted;             /* the device member lists are already in (r^2, index) order */
 
     /* general (unequal-mass) path */
     GenState *d_gen_state;
@@ -1704,6 +1842,7 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     cudaFree(h->d_tmp4); cudaFree(h->d_key[0]); cudaFree(h->d_key[1]);
     for (int l = 0; l < 4; ++l) { cudaFree(h->d_lvl_start[l]); cudaFree(h->d_lvl_cursor[l]); }
     cudaFree(h->d_mt);
+    cudaFree(h->d_vc);
     cudaFree(h->d_counters);
     cudaFree(h->d_u64);
     cudaFree(h->d_members);
@@ -2285,6 +2424,7 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
     CU(cudaGetLastError());
     h->last_h = nh;
     h->have_result = true;
+    h->members_sorted = false;
     return SOGPU_OK;
 }
 
@@ -2437,6 +2577,7 @@ static int emit_members(sogpu *h, const float *d_centers, const float *d_rgtp, i
     CU(cudaGetLastError());
     h->last_h = nh;
     h->have_result = true;
+    h->members_sorted = false;
     return SOGPU_OK;
 }
 
@@ -2592,6 +2733,30 @@ extern "C" int sogpu_finish_host(const int32_t *code_or_n, const float *m, int32
     return SOGPU_OK;
 }
 
+/* sort every member list of the last result by (r^2, index) on the device (segmented sort) */
+static int sort_members_device(sogpu *h, int32_t nh, size_t tot)
+{
+    if (tot == 0) return SOGPU_OK;
+    int rc = gen_scratch(h, tot);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    const int grid = (int)std::min<size_t>((tot + 255) / 256, (size_t)h->sm_count * 16);
+    k_member_keys<<<grid, 256, 0, s>>>(h->d_members, h->d_md2, tot, h->d_gkeys[0]);
+    size_t need = 0;
+    cub::DeviceSegmentedSort::SortKeys(nullptr, need, h->d_gkeys[0], h->d_gkeys[1], (int64_t)tot, (int64_t)nh,
+                                       h->d_out_off, h->d_out_off + 1, s);
+    if (need > h->cub_tmp_bytes) {
+        cudaFree(h->d_cub_tmp); h->d_cub_tmp = nullptr; h->cub_tmp_bytes = 0;
+        CU(cudaMalloc(&h->d_cub_tmp, need));
+        h->cub_tmp_bytes = need;
+    }
+    CU(cub::DeviceSegmentedSort::SortKeys(h->d_cub_tmp, need, h->d_gkeys[0], h->d_gkeys[1], (int64_t)tot, (int64_t)nh,
+                                          h->d_out_off, h->d_out_off + 1, s));
+    k_member_unkeys<<<grid, 256, 0, s>>>(h->d_gkeys[1], tot, h->d_members, h->d_md2);
+    CU(cudaGetLastError());
+    return SOGPU_OK;
+}
+
 extern "C" int sogpu_members(sogpu_t *h, int64_t *offsets, const int32_t **members, const float **d2, int sorted)
 {
     if (!h || !offsets || !members) return set_err(SOGPU_ERR_ARG, "sogpu_members: NULL argument");
@@ -2603,6 +2768,9 @@ extern "C" int sogpu_members(sogpu_t *h, int64_t *offsets, const int32_t **membe
     int rc = fetch_stats(h);
     if (rc) return rc;
     const size_t tot = (size_t)h->stats.last_members;
+    const bool dbg = getenv("SOGPU_DEBUG_TIMING") != nullptr;
+    auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    double t0 = now();
     if (tot + 1 > h->h_members_cap) {
         if (h->h_members) cudaFreeHost(h->h_members);
         if (h->h_md2) cudaFreeHost(h->h_md2);
@@ -2613,6 +2781,14 @@ extern "C" int sogpu_members(sogpu_t *h, int64_t *offsets, const int32_t **membe
         h->h_members_cap = cap;
     }
     static_assert(sizeof(unsigned long long) == sizeof(int64_t), "offset type");
+    if (dbg) { fprintf(stderr, "    [members] pinned alloc %.3f ms (tot %zu)\n", now() - t0, tot); t0 = now(); }
+    if (sorted && tot && !h->members_sorted) {
+        /* ascending (fDist2, index): the order kdTagParticles walks the list (kd2.c:670,781) */
+        rc = sort_members_device(h, nh, tot);
+        if (rc) return rc;
+        h->members_sorted = true;
+        if (dbg) { cudaStreamSynchronize(h->stream); fprintf(stderr, "    [members] device sort %.3f ms\n", now() - t0); t0 = now(); }
+    }
     CU(cudaMemcpyAsync(offsets, h->d_out_off, ((size_t)nh + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     if (tot) {
         CU(cudaMemcpyAsync(h->h_members, h->d_members, tot * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -2620,26 +2796,7 @@ extern "C" int sogpu_members(sogpu_t *h, int64_t *offsets, const int32_t **membe
             CU(cudaMemcpyAsync(h->h_md2, h->d_md2, tot * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     }
     CU(cudaStreamSynchronize(h->stream));
-    if (sorted && tot) {
-        /* ascending (fDist2, index): the order kdTagParticles walks the list (kd2.c:670,781) */
-        std::vector<std::pair<uint64_t, float>> tmp;
-        for (int32_t i = 0; i < nh; ++i) {
-            int64_t a0 = offsets[i], n = offsets[i + 1] - a0;
-            if (n <= 1) continue;
-            tmp.resize((size_t)n);
-            for (int64_t k = 0; k < n; ++k) {
-                uint32_t bits;
-                memcpy(&bits, &h->h_md2[a0 + k], 4);
-                tmp[k].first = ((uint64_t)bits << 32) | (uint32_t)h->h_members[a0 + k];
-                tmp[k].second = h->h_md2[a0 + k];
-            }
-            std::sort(tmp.begin(), tmp.end());
-            for (int64_t k = 0; k < n; ++k) {
-                h->h_members[a0 + k] = (int32_t)(uint32_t)tmp[k].first;
-                h->h_md2[a0 + k] = tmp[k].second;
-            }
-        }
-    }
+    if (dbg) fprintf(stderr, "    [members] D2H %.3f ms\n", now() - t0);
     *members = h->h_members;
     if (d2) *d2 = h->h_md2;
     return SOGPU_OK;
@@ -2754,7 +2911,71 @@ extern "C" int sogpu_ball_gather_batch(sogpu_t *h, const float *centers, const f
     }
     h->last_h = nh;
     h->have_result = true;
+    h->members_sorted = false;
     h->want_d2 = true;
+    return SOGPU_OK;
+}
+
+/* kdVcirc / kdMassProfile for nh groups (kd2.c:498-586): gather the 2*Rvir balls, sort every list by
+ * (r^2, index) on the device, evaluate the circular-velocity curve, R(M/4), R(M/2), (Rmax, Vmax) and the
+ * all-particle mass profile per group.  Equal particle masses only (SOGPU_ERR_UNSUPPORTED otherwise:
+ * with mixed masses the cumulative fp32 mass depends on which particle sits at which rank). */
+extern "C" int sogpu_vcirc(sogpu_t *h, const float *centers, const float *rvir, const float *mvir, int32_t nh, float G,
+                           int32_t nMembers, float *vcirc, float *rmass, float *rmax, float *vmax, float *profile)
+{
+    if (!h || !centers || !rvir || !mvir || !vcirc || !rmass || !rmax || !vmax || nh <= 0 || nMembers < 1)
+        return set_err(SOGPU_ERR_ARG, "sogpu_vcirc: bad argument");
+    if (!h->built) return set_err(SOGPU_ERR_ARG, "sogpu_vcirc: call sogpu_build_grid first");
+    CU(cudaSetDevice(h->device));
+    int rc = fetch_mass_state(h);
+    if (rc) return rc;
+    if (h->mass_state != 1) return set_err(SOGPU_ERR_UNSUPPORTED, "sogpu_vcirc: particles have unequal masses");
+    std::vector<float> ball2((size_t)nh);
+    for (int32_t i = 0; i < nh; ++i) {
+        float fBall = (float)(2. * rvir[i]);                              /* kd2.c:511-512 */
+        ball2[i] = fBall * fBall;
+    }
+    rc = sogpu_ball_gather_batch(h, centers, ball2.data(), nh);
+    if (rc) return rc;
+    rc = fetch_stats(h);
+    if (rc) return rc;
+    const size_t tot = (size_t)h->stats.last_members;
+    rc = sort_members_device(h, nh, tot);
+    if (rc) return rc;
+    h->members_sorted = true;
+    /* per-group inputs and outputs share one device block: rvir, mvir | vcirc 8, rmass 2, rmax, vmax, profile 16 */
+    const size_t per = 2 + SO_NVCIRC + 2 + 1 + 1 + SO_NMASSPROFILE;
+    if ((size_t)nh * per > h->vc_cap) {
+        cudaFree(h->d_vc); h->d_vc = nullptr; h->vc_cap = 0;
+        CU(cudaMalloc(&h->d_vc, (size_t)nh * per * sizeof(float)));
+        h->vc_cap = (size_t)nh * per;
+    }
+    rc = ensure_pinned(h, (size_t)nh * per * sizeof(float));
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    float *pin = (float *)h->h_pin;
+    memcpy(pin, rvir, (size_t)nh * sizeof(float));
+    memcpy(pin + nh, mvir, (size_t)nh * sizeof(float));
+    CU(cudaMemcpyAsync(h->d_vc, pin, (size_t)nh * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    VcircArgs a;
+    a.d2 = h->d_md2; a.off = h->d_out_off; a.rvir = h->d_vc; a.mvir = h->d_vc + nh; a.mt = h->d_mt;
+    a.G = G; a.nM = nMembers; a.nh = nh;
+    a.vcirc = h->d_vc + (size_t)2 * nh;
+    a.rmass = a.vcirc + (size_t)SO_NVCIRC * nh;
+    a.rmax = a.rmass + (size_t)2 * nh;
+    a.vmax = a.rmax + nh;
+    a.profile = profile ? a.vmax + nh : nullptr;
+    { ProfScope p(h, KID_VCIRC); k_vcirc<<<std::min(nh, h->sm_count * 16), 256, 0, s>>>(a); }
+    CU(cudaGetLastError());
+    const size_t n_out = (size_t)nh * (per - 2);
+    CU(cudaMemcpyAsync(pin + (size_t)2 * nh, h->d_vc + (size_t)2 * nh, n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const float *o = pin + (size_t)2 * nh;
+    memcpy(vcirc, o, (size_t)SO_NVCIRC * nh * sizeof(float)); o += (size_t)SO_NVCIRC * nh;
+    memcpy(rmass, o, (size_t)2 * nh * sizeof(float)); o += (size_t)2 * nh;
+    memcpy(rmax, o, (size_t)nh * sizeof(float)); o += nh;
+    memcpy(vmax, o, (size_t)nh * sizeof(float)); o += nh;
+    if (profile) memcpy(profile, o, (size_t)SO_NMASSPROFILE * nh * sizeof(float));
     return SOGPU_OK;
 }
 

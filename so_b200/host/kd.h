@@ -97,6 +97,8 @@ void kdSO(KD, float rhovir, int nSmooth);
 void kdWriteProfile(KD, char *achOutFileBase, time_t, FILE *, int ptype);
 void kdWriteOut(KD, FILE *);
 int kdBuildTree(KD);
+void kdStartGpu(KD);                             /* optional: create the CUDA context on a thread, early */
+void kdPhase(const char *name, double *t);       /* SO_TIMING=1: phase wall-clock on stderr */
 void kdFinish(KD);
 void kdWriteConflict(KD, char *achOutFileBase, int iOpt);
 void kdOutStats(KD, FILE *);

@@ -315,17 +315,39 @@ void kdWriteOut(KD kd, FILE *fpOutFile)
     }
 }
 
+/* one integer per line (kd2.c:1256-1258, 1231-1239): formatted by hand into a 1 MB buffer — at 10^7..10^9
+ * particles fprintf("%d\n") per line costs more than the whole GPU run */
+static void write_int_lines(FILE *fp, int first, const int32_t *a, int64_t n)
+{
+    enum { CAP = 1 << 20 };
+    char *buf = (char *)malloc(CAP + 16);
+    size_t len = 0;
+    int64_t i;
+    assert(buf != NULL);
+    for (i = -1; i < n; ++i) {
+        int64_t v = i < 0 ? first : a[i];
+        char tmp[16];
+        int k = 0;
+        uint64_t u = v < 0 ? (uint64_t)(-v) : (uint64_t)v;
+        if (v < 0) buf[len++] = '-';
+        do { tmp[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+        while (k) buf[len++] = tmp[--k];
+        buf[len++] = '\n';
+        if (len >= CAP) { fwrite(buf, 1, len, fp); len = 0; }
+    }
+    if (len) fwrite(buf, 1, len, fp);
+    free(buf);
+}
+
 void kdWriteConflict(KD kd, char *achOutFileBase, int iOpt)
 {
     char name[256];
     const int32_t *a = iOpt == KD_SUBSUMED ? kd->p.nSubsumed : kd->p.nIgnored;
     FILE *fp;
-    int i;
     snprintf(name, sizeof(name), "%s.%s", achOutFileBase, iOpt == KD_SUBSUMED ? "sosub" : "soign");
     fp = fopen(name, "w");
     assert(fp != NULL);
-    fprintf(fp, "%d\n", kd->nParticles);                  /* kd2.c:1231-1239; we keep file order */
-    for (i = 0; i < kd->nParticles; ++i) fprintf(fp, "%d\n", a[i]);
+    write_int_lines(fp, kd->nParticles, a, kd->nParticles);   /* kd2.c:1231-1239; we keep file order */
     fclose(fp);
 }
 
@@ -333,12 +355,10 @@ void kdWriteArray(KD kd, char *achOutFileBase)
 {
     char name[256];
     FILE *fp;
-    int i;
     snprintf(name, sizeof(name), "%s.sogrp", achOutFileBase);
     fp = fopen(name, "w");
     assert(fp != NULL);
-    fprintf(fp, "%d\n", kd->nParticles);                  /* kd2.c:1256-1258 */
-    for (i = 0; i < kd->nParticles; ++i) fprintf(fp, "%d\n", kd->p.iGrp[i]);
+    write_int_lines(fp, kd->nParticles, kd->p.iGrp, kd->nParticles);   /* kd2.c:1256-1258 */
     fclose(fp);
 }
 

@@ -17,6 +17,7 @@
 
 #include <assert.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/resource.h>
@@ -71,6 +72,21 @@ void kdSetUniverse(KD kd, float G, float Omega0, float Lambda, float H0, float z
     kd->fMpcUnit = fMpcUnit;
 }
 
+/* SO_TIMING=1: wall-clock of every phase on stderr */
+void kdPhase(const char *name, double *t);
+#define phase kdPhase
+void kdPhase(const char *name, double *t)
+{
+    static int on = -1;
+    struct timespec ts;
+    double now;
+    if (on < 0) on = getenv("SO_TIMING") != NULL;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    now = ts.tv_sec + 1e-9 * ts.tv_nsec;
+    if (on && name) fprintf(stderr, "  [timing] %-28s %9.3f ms\n", name, 1e3 * (now - *t));
+    *t = now;
+}
+
 static double wall(void)
 {
     struct timespec ts;
@@ -78,15 +94,55 @@ static double wall(void)
     return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
+/* Creating the CUDA context takes ~0.6 s and does not depend on the input, so main() may start it on a
+ * thread before the snapshot is read (SO_EARLY_GPU=1) and kdBuildTree joins it.  Off by default:
+ * measured on the B200 host the driver's address-space setup and the reader's page faults fight
+ * over the process's mmap lock and the context then takes 2.5-3.8 s instead of 0.6 s. */
+static pthread_t g_gpu_thread;
+static int g_gpu_thread_on = 0, g_gpu_thread_rc = 0;
+static char g_gpu_thread_err[512];
+
+static void *gpu_create_thread(void *arg)
+{
+    KD kd = (KD)arg;
+    g_gpu_thread_rc = sogpu_create(&kd->gpu, kd->iDevice);
+    if (g_gpu_thread_rc) snprintf(g_gpu_thread_err, sizeof(g_gpu_thread_err), "%s", sogpu_last_error());
+    return NULL;
+}
+
+void kdStartGpu(KD kd)
+{
+    if (kd->gpu || g_gpu_thread_on || !getenv("SO_EARLY_GPU")) return;
+    if (pthread_create(&g_gpu_thread, NULL, gpu_create_thread, kd) == 0) g_gpu_thread_on = 1;
+}
+
+static void join_gpu(KD kd)
+{
+    if (g_gpu_thread_on) {
+        pthread_join(g_gpu_thread, NULL);
+        g_gpu_thread_on = 0;
+        if (g_gpu_thread_rc) {
+            fprintf(stderr, "ERROR in kdBuildTree (sogpu_create): %s\n", g_gpu_thread_err);
+            exit(1);
+        }
+    }
+    if (!kd->gpu && sogpu_create(&kd->gpu, kd->iDevice)) die_gpu("kdBuildTree (sogpu_create)");
+}
+
 int kdBuildTree(KD kd)
 {
     double t0 = wall();
+    double tp;
     if (kd->nParticles == 0) return 1;
-    if (!kd->gpu && sogpu_create(&kd->gpu, kd->iDevice)) die_gpu("kdBuildTree (sogpu_create)");
+    phase(NULL, &tp);
+    join_gpu(kd);
+    phase("wait for the CUDA context", &tp);
     if (sogpu_set_particles_host(kd->gpu, kd->p.r, 3 * sizeof(float), kd->p.fMass, sizeof(float), kd->nParticles,
                                  kd->fPeriod, kd->fCenter))
         die_gpu("kdBuildTree (sogpu_set_particles_host)");
+    phase("upload particles", &tp);
     if (sogpu_build_grid(kd->gpu)) die_gpu("kdBuildTree (sogpu_build_grid)");
+    phase("build grid (enqueue)", &tp);
     kd->dBuildSeconds = wall() - t0;
     return 1;
 }
@@ -297,9 +353,10 @@ void kdSO(KD kd, float rhovir, int nSmooth)
     const float *lib_d2;
     sogpu_stats_t st;
     TAGCTX c;
-    double t0 = wall();
-    int i, it;
-    (void)nSmooth;                 /* sized the reference's neighbour list (smInit); nothing to size here */
+    double t0 = wall(), tp;
+    int i, it, equal_mass = 0;
+    (void)nSmooth;
+    phase(NULL, &tp);                 /* sized the reference's neighbour list (smInit); nothing to size here */
     if (h == 0) return;
     if (kd->bPot) {
         /* -pot (kd2.c:749-761): re-centre every group on the particle of lowest potential inside
@@ -350,14 +407,18 @@ void kdSO(KD kd, float rhovir, int nSmooth)
 
     /* the hot path: R_Delta, M_Delta, N_Delta and the member lists of every group */
     if (sogpu_keep_member_d2(kd->gpu, 1)) die_gpu("kdSO");
+    phase("kdSO setup", &tp);
     if (sogpu_so(kd->gpu, centers, rgtp, h, rhovir, kd->nMembers, rvir, mvir, ndelta)) die_gpu("kdSO (sogpu_so)");
+    phase("sogpu_so (build+query)", &tp);
     if (sogpu_members(kd->gpu, off, &lib_mem, &lib_d2, 1)) die_gpu("kdSO (sogpu_members)");
+    phase("member lists (sorted)", &tp);
     mem = (int32_t *)malloc((size_t)(off[h] > 0 ? off[h] : 1) * sizeof(int32_t));
     assert(mem != NULL);
     memcpy(mem, lib_mem, (size_t)off[h] * sizeof(int32_t));
     if (sogpu_get_stats(kd->gpu, &st) == 0) {
         kd->nEvals = st.last_evals;
         kd->nMembersTotal = st.last_members;
+        equal_mass = st.equal_mass;
     }
 
     /* sequential replay in ascending catalog mass (kd2.c:873-879) */
@@ -375,6 +436,7 @@ void kdSO(KD kd, float rhovir, int nSmooth)
         }
     }
 
+    phase("tagging replay + vcm", &tp);
     /* kdVcirc for every group that was valid when the reference would have called it */
     {
         int nv = 0, k;
@@ -391,17 +453,51 @@ void kdSO(KD kd, float rhovir, int nSmooth)
                 slots[nv++] = i;
             }
         if (nv) {
-            const int32_t *vi;
-            const float *vd;
-            if (sogpu_ball_gather_batch(kd->gpu, vc, vb, nv)) die_gpu("kdSO (sogpu_ball_gather_batch)");
-            if (sogpu_members(kd->gpu, voff, &vi, &vd, 1)) die_gpu("kdSO (2 Rvir lists)");
-            for (k = 0; k < nv; ++k) {
-                int g = slots[k];
-                vcirc(kd, &kd->grps[g], rvir[g], mvir[g], vi + voff[k], vd + voff[k], voff[k + 1] - voff[k]);
+            /* equal-mass, single-species snapshot (the usual dark-matter run): the whole of kdVcirc and
+             * kdMassProfile is rank queries on the sorted lists and runs on the device (sogpu_vcirc);
+             * otherwise the per-species fp32 sums need the particle at every rank: host walk below */
+            const int one_species = kd->nDark == kd->nParticles || kd->nGas == kd->nParticles ||
+                                    kd->nStar == kd->nParticles;
+            const int want_prof = kd->bDark || kd->bGas || kd->bStar;
+            if (equal_mass == 1 && !kd->bMark && (one_species || !want_prof) && !getenv("SO_HOST_VCIRC")) {
+                float *vr = (float *)malloc((size_t)nv * 2 * sizeof(float)), *vm = vr + nv;
+                float *o_vc = (float *)malloc((size_t)nv * (NVCIRC + 2 + 1 + 1 + NMASSPROFILE) * sizeof(float));
+                float *o_rm = o_vc + (size_t)nv * NVCIRC, *o_rx = o_rm + (size_t)nv * 2, *o_vx = o_rx + nv;
+                float *o_pr = o_vx + nv;
+                assert(vr && o_vc);
+                for (k = 0; k < nv; ++k) { vr[k] = rvir[slots[k]]; vm[k] = mvir[slots[k]]; }
+                if (sogpu_vcirc(kd->gpu, vc, vr, vm, nv, kd->G, kd->nMembers, o_vc, o_rm, o_rx, o_vx,
+                                want_prof ? o_pr : NULL))
+                    die_gpu("kdSO (sogpu_vcirc)");
+                phase("kdVcirc on the device", &tp);
+                for (k = 0; k < nv; ++k) {
+                    GRPNODE *g = &kd->grps[slots[k]];
+                    memcpy(g->fVcirc, o_vc + (size_t)k * NVCIRC, NVCIRC * sizeof(float));
+                    memcpy(g->fRmass, o_rm + (size_t)k * 2, 2 * sizeof(float));
+                    g->fRmax = o_rx[k];
+                    g->fVmax = o_vx[k];
+                    /* a species that is absent keeps a zero profile (mass never incremented, kd2.c:470-480) */
+                    if (kd->bDark && kd->nDark) memcpy(g->fDark, o_pr + (size_t)k * NMASSPROFILE, NMASSPROFILE * sizeof(float));
+                    if (kd->bGas && kd->nGas) memcpy(g->fGas, o_pr + (size_t)k * NMASSPROFILE, NMASSPROFILE * sizeof(float));
+                    if (kd->bStar && kd->nStar) memcpy(g->fStar, o_pr + (size_t)k * NMASSPROFILE, NMASSPROFILE * sizeof(float));
+                }
+                free(vr); free(o_vc);
+            } else {
+                const int32_t *vi;
+                const float *vd;
+                if (sogpu_ball_gather_batch(kd->gpu, vc, vb, nv)) die_gpu("kdSO (sogpu_ball_gather_batch)");
+                phase("2 Rvir ball gather", &tp);
+                if (sogpu_members(kd->gpu, voff, &vi, &vd, 1)) die_gpu("kdSO (2 Rvir lists)");
+                phase("2 Rvir lists (sorted)", &tp);
+                for (k = 0; k < nv; ++k) {
+                    int g = slots[k];
+                    vcirc(kd, &kd->grps[g], rvir[g], mvir[g], vi + voff[k], vd + voff[k], voff[k + 1] - voff[k]);
+                }
             }
         }
         free(slots); free(vc); free(vb); free(voff);
     }
+    phase("kdVcirc / kdMassProfile", &tp);
     kd->dSOSeconds = wall() - t0;
     free(centers); free(rgtp); free(rvir); free(mvir); free(masses); free(ndelta); free(off); free(order);
     free(do_vcirc); free(slot_of_index); free(mem);

@@ -82,6 +82,7 @@ int main(int argc, char **argv)
     char *achBenchJson = NULL;
     char achDefOutBase[] = "so", achLongWord[256];
     time_t timeRun;
+    double tPhase;
     FILE *fpOutFile;
 
     fprintf(stderr, "SO Release 1.7: Jeff Gardner, May 2003\n");
@@ -129,7 +130,10 @@ int main(int argc, char **argv)
 
     kdInit(&kd, nBucket, fPeriod, fCenter, 0, nMembers, bPeriodic, bDark, bGas, bStar, bMark, bPot);
     kd->iDevice = iDevice;
+    kdStartGpu(kd);                                   /* CUDA context creation overlaps the snapshot read */
+    kdPhase(NULL, &tPhase);
     i = kdReadTipsy(kd, stdin, bStandard);
+    kdPhase("read TIPSY snapshot", &tPhase);
     fprintf(stderr, "Read %d particles from TIPSY file.\n", i);
     if (bMark) {
         i = kdReadMark(kd, achMarkFile);
@@ -174,6 +178,7 @@ int main(int argc, char **argv)
     kdTime(kd, &sec, &usec);
     kdSO(kd, fThreshold, nSmooth);
     kdTime(kd, &sec, &usec);
+    kdPhase(NULL, &tPhase);
 
     kdOutStats(kd, fpOutFile);
     if (bDark) kdWriteProfile(kd, achOutFileBase, timeRun, fpOutFile, DARK);
@@ -186,6 +191,7 @@ int main(int argc, char **argv)
     if (bGtp) kdWriteGTP(kd, achOutFileBase, bStandard);
     if (bSubsumed) kdWriteConflict(kd, achOutFileBase, KD_SUBSUMED);
     if (bIgnored) kdWriteConflict(kd, achOutFileBase, KD_IGNORED);
+    kdPhase("write output files", &tPhase);
 
     fprintf(stderr, "SO CPU Time:");
     fprintf(stderr, "   %d.%06d\n\n", sec, usec);

@@ -58,6 +58,23 @@ def test_oracle_tagging_matches_sogrp(name):
     np.testing.assert_allclose(t["mvir"], rows[:, 1], rtol=6e-6)   # %g = 6 significant digits
 
 
+@pytest.mark.parametrize("name", ["basic", "conflict", "omega03", "members4"])
+def test_oracle_vcirc_matches_sovcirc_rows(name):
+    """kdVcirc restatement (kd2.c:498-586) against the reference's .sovcirc text: columns R(M/4), R(M/2),
+    R(Vc_max), Vc_max and the eight Vc values, printed by the reference with %g (6 significant digits),
+    so the pin is to %g resolution: our value formatted the same way must give the same number."""
+    s, g = load_golden(name)
+    rows = g["sovcirc_rows"]
+    ok = rows[:, 2] > 0                                   # Rvir column: valid, not subsumed / slurped
+    o = po.Oracle(s.pos, s.mass)
+    v = o.vcirc(g["centers"], np.where(ok, g["rvir"], 0).astype(np.float32), g["mvir_sogtp"], 1.0,
+                int(g["n_members"]))
+    ours = np.concatenate([v["rmass"], v["rmax"][:, None], v["vmax"][:, None], v["vcirc"]], axis=1)
+    fmt = np.array([[float("%g" % x) for x in r] for r in ours[ok]])
+    assert ok.sum() > 0
+    assert np.array_equal(fmt, rows[ok, 3:15])
+
+
 def test_rho_enclosed_expression():
     """kd2.c:588-593 restated: fp32 -> fp64 sqrt/mul/div -> fp32."""
     rng = np.random.default_rng(0)

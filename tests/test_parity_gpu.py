@@ -276,6 +276,46 @@ def test_ball_gather_matches_oracle_ball():
     g.close()
 
 
+@pytest.mark.parametrize("nmem", [8, 3])
+def test_vcirc_and_mass_profile_match_oracle(nmem):
+    """sogpu_vcirc (kdVcirc + kdMassProfile, kd2.c:498-586): bit-exact against the oracle's literal walk of
+    the sorted 2*Rvir lists, including a group on the periodic boundary and Omega0 = 0.3 (a particle mass
+    that is not a power of two, so the sequential fp32 mass sum matters)."""
+    for seed, omega0 in ((61, 1.0), (62, 0.3)):
+        s = synth.make_snapshot(48 ** 3, 40, seed=seed, nmax=6000, omega0=omega0)
+        centers = s.centers.copy()
+        centers[0] = (0.4995, -0.4995, 0.1)
+        thr = np.float32(np.float32(200.0) * np.float32(omega0))
+        o = po.Oracle(s.pos, s.mass)
+        ref = o.so(centers, s.rgtp, thr, nmem)
+        ok = ref["rvir"] > 0
+        assert ok.sum() > 20
+        want = o.vcirc(centers[ok], ref["rvir"][ok], ref["mvir"][ok], 1.0, nmem)
+        g = api.SoGpu()
+        g.set_particles(s.pos, s.mass)
+        g.build_grid()
+        got = g.vcirc(centers[ok], ref["rvir"][ok], ref["mvir"][ok], 1.0, nmem)
+        for k in ("vcirc", "rmass", "rmax", "vmax", "profile"):
+            assert got[k].tobytes() == want[k].tobytes(), k
+        # the sorted 2 Rvir lists stay available
+        off, mem, d2 = g.members(want_d2=True, sorted=True)
+        oi, od = o.ball(centers[ok][3], np.float32(np.float32(2.0 * ref["rvir"][ok][3]) ** 2))
+        assert np.array_equal(mem[off[3]:off[4]], oi) and d2[off[3]:off[4]].tobytes() == od.tobytes()
+        g.close()
+
+
+def test_vcirc_refuses_mixed_masses():
+    s = synth.make_snapshot(20 ** 3, 4, seed=63, nmax=500)
+    mass = np.full(s.n, s.mass, np.float32)
+    mass[::7] *= np.float32(3.0)
+    g = api.SoGpu()
+    g.set_particles(s.pos, mass)
+    g.build_grid()
+    with pytest.raises(api.SoGpuError):
+        g.vcirc(s.centers, np.full(s.h, 0.02, np.float32), np.full(s.h, 1e-4, np.float32))
+    g.close()
+
+
 def test_unequal_masses_general_path():
     """Mixed particle masses: the enclosed mass is the SEQUENTIAL fp32 sum in sorted order, so the
     library switches to the full-sort path; results must still be bit-exact."""
