@@ -164,6 +164,17 @@ int sogpu_vcirc(sogpu_t *h, const float *centers, const float *rvir, const float
                 float G, int32_t nMembers, float *vcirc, float *rmass, float *rmax, float *vmax,
                 float *profile);
 
+/* ---- kdTagParticles, order-independent part (kd2.c:663-720) ---------------------------------- */
+
+/* Over the member lists of the last sogpu_so() call (nh groups, same order): a group that shares no
+ * particle with any other group tags its members with its catalog id index[i] whatever the processing
+ * order; groups that do share particles are reported in in_conflict[i] = 1 and their particles are
+ * left untagged (0), for the caller to replay kdTagParticles over THOSE groups only, in kdSortMass
+ * order (subsume / slurp / ignore depend on the order; a conflict-free group can never be met by
+ * that replay).  igrp (host, N ints, may be NULL) receives the per-particle tags (PINIT.iGrp). */
+int sogpu_tag_members(sogpu_t *h, const int32_t *index, int32_t nh, unsigned char *in_conflict,
+                      int32_t *igrp);
+
 /* ---- introspection --------------------------------------------------------------------------- */
 
 typedef struct {

@@ -27,7 +27,7 @@ SYMBOLS = [
     "sogpu_finish_host", "sogpu_keep_member_d2", "sogpu_profile_enable", "sogpu_profile_kernels",
     "sogpu_profile_name", "sogpu_profile_read", "sogpu_upload_particles",
     "sogpu_set_build_mode", "sogpu_ball_gather_batch",
-    "sogpu_profile_bytes", "sogpu_build_grid_for", "sogpu_build_grid_for_device", "sogpu_set_first_ball", "sogpu_vcirc",
+    "sogpu_profile_bytes", "sogpu_build_grid_for", "sogpu_build_grid_for_device", "sogpu_set_first_ball", "sogpu_vcirc", "sogpu_tag_members",
 ]
 
 
@@ -65,6 +65,8 @@ def lib():
     L.sogpu_set_cell_occupancy.argtypes = [vp, C.c_float]
     L.sogpu_vcirc.argtypes = [vp, fp, fp, fp, C.c_int32, C.c_float, C.c_int32, fp, fp, fp, fp, fp]
     L.sogpu_vcirc.restype = C.c_int
+    L.sogpu_tag_members.argtypes = [vp, i32p, C.c_int32, C.POINTER(C.c_ubyte), i32p]
+    L.sogpu_tag_members.restype = C.c_int
     L.sogpu_set_first_ball.argtypes = [vp, C.c_int]
     L.sogpu_set_first_ball.restype = C.c_int
     L.sogpu_set_build_mode.argtypes = [vp, C.c_int]
@@ -347,6 +349,16 @@ class SoGpu:
                                  _fp(out["profile"]) if profile else None))
         self._last_h = h
         return out
+
+    def tag_members(self, index, n_particles=None):
+        """Order-independent part of kdTagParticles: (in_conflict[nh], igrp[N]) for the last so() call."""
+        index = np.ascontiguousarray(index, np.int32)
+        dirty = np.zeros(len(index), np.uint8)
+        igrp = np.zeros(int(n_particles), np.int32) if n_particles else None
+        _check(lib().sogpu_tag_members(self._h, index.ctypes.data_as(C.POINTER(C.c_int32)), len(index),
+                                       dirty.ctypes.data_as(C.POINTER(C.c_ubyte)),
+                                       igrp.ctypes.data_as(C.POINTER(C.c_int32)) if igrp is not None else None))
+        return dirty.astype(bool), igrp
 
     def stats(self):
         s = Stats()

@@ -1578,6 +1578,46 @@ __global__ void __launch_bounds__(256) k_vcirc(const __grid_constant__ VcircArgs
     }
 }
 
+/* ============================================================================================
+ * kdTagParticles, the part that needs no ordering (kd2.c:663-720): a group none of whose members
+ * belongs to another group simply tags its members, whatever the processing order.  Pass 1 lets
+ * every member claim its particle with a compare-and-swap; a failed claim marks both groups
+ * involved as "in conflict".  Pass 2 writes the catalog index for conflict-free groups and
+ * releases the claims of the others, which the caller replays sequentially (subsume / slurp /
+ * ignore are order dependent).  A conflict-free group can never be touched by that replay: nobody
+ * else owns or meets one of its particles.
+ * ============================================================================================ */
+__global__ void __launch_bounds__(256) k_tag_claim(const unsigned long long *__restrict__ off, const int32_t *__restrict__ mem,
+                                                   int nh, int32_t *tag, unsigned char *dirty)
+{
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int h = wid; h < nh; h += nw) {
+        const unsigned long long a = off[h], b = off[h + 1];
+        for (unsigned long long k = a + lane; k < b; k += 32) {
+            const int32_t old = atomicCAS(&tag[mem[k]], 0, h + 1);
+            if (old != 0 && old != h + 1) { dirty[h] = 1; dirty[old - 1] = 1; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_tag_settle(const unsigned long long *__restrict__ off, const int32_t *__restrict__ mem,
+                                                    const int32_t *__restrict__ index, int nh, int32_t *tag,
+                                                    const unsigned char *__restrict__ dirty)
+{
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int h = wid; h < nh; h += nw) {
+        const unsigned long long a = off[h], b = off[h + 1];
+        if (!dirty[h]) {
+            const int32_t id = index[h];
+            for (unsigned long long k = a + lane; k < b; k += 32) tag[mem[k]] = id;
+        } else {
+            for (unsigned long long k = a + lane; k < b; k += 32) atomicCAS(&tag[mem[k]], h + 1, 0);
+        }
+    }
+}
+
 /* member lists -> sortable keys and back: ascending (fDist2 bits, original index) is the order the
  * reference's qsort(CmpList) + stable merge gives for distinct r^2 (kd2.c:425-435,781) */
 __global__ void __launch_bounds__(256) k_member_keys(const int32_t *__restrict__ idx, const float *__restrict__ d2,
@@ -1604,12 +1644,12 @@ __global__ void __launch_bounds__(256) k_member_unkeys(const unsigned long long 
 enum {
     KID_LVL_HIST = 0, KID_LVL_SCAN, KID_LVL_PARTITION, KID_BUCKET_SORT, KID_MASS_TABLE, KID_CLASSIFY,
     KID_QUERY_WARP, KID_QUERY_BLOCK, KID_OFFSETS, KID_EMIT_WARP, KID_EMIT_BLOCK, KID_BALL_GATHER,
-    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_VCIRC, KID_N
+    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_VCIRC, KID_TAG, KID_N
 };
 static const char *const g_kernel_names[KID_N] = {
     "k_lvl_hist", "k_scan", "k_lvl_partition", "k_bucket_sort", "k_mass_table", "k_classify",
     "k_so_query<32>", "k_so_query<256>", "k_offsets", "k_so_emit<32>", "k_so_emit<256>", "k_ball_gather",
-    "k_so_query<1024>", "k_so_emit<1024>", "k_mark_mask", "k_vcirc"};
+    "k_so_query<1024>", "k_so_emit<1024>", "k_mark_mask", "k_vcirc", "k_tag_claim+settle"};
 
 struct ProfRec { int kid, launches; cudaEvent_t a, b; };
 
@@ -1671,6 +1711,10 @@ struct sogpu {
     bool have_result;
     bool want_d2;
     bool member_overflow;
+    int32_t *d_tag, *d_tag_index;    /* sogpu_tag_members: owner per particle, catalog ids */
+    unsigned char *d_dirty;
+    int64_t tag_cap;
+    int32_t tagh_cap;
     float *d_vc;                     /* sogpu_vcirc: per-group inputs and outputs */
     size_t vc_cap;
     bool members_sorted;             /* the device member lists are already in (r^2, index) order */
@@ -1843,6 +1887,7 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     for (int l = 0; l < 4; ++l) { cudaFree(h->d_lvl_start[l]); cudaFree(h->d_lvl_cursor[l]); }
     cudaFree(h->d_mt);
     cudaFree(h->d_vc);
+    cudaFree(h->d_tag); cudaFree(h->d_tag_index); cudaFree(h->d_dirty);
     cudaFree(h->d_counters);
     cudaFree(h->d_u64);
     cudaFree(h->d_members);
@@ -2976,6 +3021,49 @@ extern "C" int sogpu_vcirc(sogpu_t *h, const float *centers, const float *rvir, 
     memcpy(rmax, o, (size_t)nh * sizeof(float)); o += nh;
     memcpy(vmax, o, (size_t)nh * sizeof(float)); o += nh;
     if (profile) memcpy(profile, o, (size_t)SO_NMASSPROFILE * nh * sizeof(float));
+    return SOGPU_OK;
+}
+
+/* Conflict detection + tagging of the conflict-free groups of the last sogpu_so() result (see k_tag_claim). */
+extern "C" int sogpu_tag_members(sogpu_t *h, const int32_t *index, int32_t nh, unsigned char *in_conflict,
+                                 int32_t *igrp)
+{
+    if (!h || !index || !in_conflict || nh <= 0) return set_err(SOGPU_ERR_ARG, "sogpu_tag_members: bad argument");
+    if (!h->have_result || h->last_h != nh)
+        return set_err(SOGPU_ERR_ARG, "sogpu_tag_members: needs the member lists of a sogpu_so() call over the same %d groups", nh);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    if (h->n > h->tag_cap) {
+        cudaFree(h->d_tag); h->d_tag = nullptr; h->tag_cap = 0;
+        CU(cudaMalloc(&h->d_tag, (size_t)h->n * sizeof(int32_t)));
+        h->tag_cap = h->n;
+    }
+    if (nh > h->tagh_cap) {
+        cudaFree(h->d_tag_index); cudaFree(h->d_dirty);
+        h->d_tag_index = nullptr; h->d_dirty = nullptr; h->tagh_cap = 0;
+        CU(cudaMalloc(&h->d_tag_index, (size_t)nh * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_dirty, (size_t)nh));
+        h->tagh_cap = nh;
+    }
+    int rc = ensure_pinned(h, (size_t)nh * (sizeof(int32_t) + 1));
+    if (rc) return rc;
+    int32_t *pi = (int32_t *)h->h_pin;
+    unsigned char *pd = (unsigned char *)(pi + nh);
+    memcpy(pi, index, (size_t)nh * sizeof(int32_t));
+    CU(cudaMemcpyAsync(h->d_tag_index, pi, (size_t)nh * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(h->d_tag, 0, (size_t)h->n * sizeof(int32_t), s));
+    CU(cudaMemsetAsync(h->d_dirty, 0, (size_t)nh, s));
+    const int grid = std::min((nh + 7) / 8, h->sm_count * 16);
+    {
+        ProfScope p(h, KID_TAG, 0.0, 2);
+        k_tag_claim<<<grid, 256, 0, s>>>(h->d_out_off, h->d_members, nh, h->d_tag, h->d_dirty);
+        k_tag_settle<<<grid, 256, 0, s>>>(h->d_out_off, h->d_members, h->d_tag_index, nh, h->d_tag, h->d_dirty);
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(pd, h->d_dirty, (size_t)nh, cudaMemcpyDeviceToHost, s));
+    if (igrp) CU(cudaMemcpyAsync(igrp, h->d_tag, (size_t)h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    memcpy(in_conflict, pd, (size_t)nh);
     return SOGPU_OK;
 }
 

@@ -79,6 +79,9 @@ typedef struct kdContext {
     int uSecond, uMicro;
     sogpu_t *gpu;
     int iDevice;
+    int bSkipGrpArray;     /* main() sets these when nothing will print the per-particle tags (.sogrp) ... */
+    int bSkipVcm;          /* ... or the centre-of-mass velocities (.sogtp)                                  */
+    int nGrpsInConflict;   /* groups that shared particles and went through the sequential replay           */
     /* filled by kdSO for reporting (--bench-json) */
     double dBuildSeconds, dSOSeconds;
     long long nEvals, nMembersTotal;

@@ -349,6 +349,7 @@ void kdSO(KD kd, float rhovir, int nSmooth)
     int32_t *ndelta, *mem;
     int64_t *off;
     int *order, *slot_of_index, *do_vcirc;
+    unsigned char *in_conflict;
     const int32_t *lib_mem;
     const float *lib_d2;
     sogpu_stats_t st;
@@ -395,8 +396,9 @@ void kdSO(KD kd, float rhovir, int nSmooth)
     off = (int64_t *)malloc(((size_t)h + 1) * sizeof(int64_t));
     order = (int *)malloc(((size_t)h + 1) * sizeof(int));            /* 1-based for indexx */
     do_vcirc = (int *)calloc((size_t)h, sizeof(int));
+    in_conflict = (unsigned char *)calloc((size_t)h, 1);
     slot_of_index = (int *)malloc(((size_t)kd->nInGTP + 2) * sizeof(int));
-    assert(centers && rgtp && rvir && mvir && masses && ndelta && off && order && do_vcirc && slot_of_index);
+    assert(centers && rgtp && rvir && mvir && masses && ndelta && off && order && do_vcirc && slot_of_index && in_conflict);
     for (i = 0; i <= kd->nInGTP + 1; ++i) slot_of_index[i] = -1;
     for (i = 0; i < h; ++i) {
         memcpy(centers + 3 * i, kd->grps[i].pos, 3 * sizeof(float));   /* (after -pot re-centring) */
@@ -421,7 +423,20 @@ void kdSO(KD kd, float rhovir, int nSmooth)
         equal_mass = st.equal_mass;
     }
 
-    /* sequential replay in ascending catalog mass (kd2.c:873-879) */
+    /* kdTagParticles (kd2.c:663-720).  Groups that share no particle with another group are tagged on
+     * the device, whatever the order; the others come back flagged and are replayed here, in
+     * ascending catalog mass like the reference (kd2.c:873-879): subsume / slurp / ignore depend on
+     * the order, and a conflict-free group can never be met by that replay. */
+    {
+        int32_t *ids = (int32_t *)malloc((size_t)h * sizeof(int32_t));
+        assert(ids != NULL);
+        for (i = 0; i < h; ++i) ids[i] = kd->grps[i].index;
+        if (sogpu_tag_members(kd->gpu, ids, h, in_conflict, kd->bSkipGrpArray ? NULL : kd->p.iGrp))
+            die_gpu("kdSO (sogpu_tag_members)");
+        free(ids);
+        for (i = 0; i < h; ++i) kd->nGrpsInConflict += in_conflict[i];
+    }
+    phase("tagging on the device", &tp);
     c.off = off; c.mem = mem; c.slot_of_index = slot_of_index;
     indexx(h, masses, order);
     for (it = 1; it <= h; ++it) {
@@ -430,13 +445,13 @@ void kdSO(KD kd, float rhovir, int nSmooth)
         grp->fRvir = rvir[g];                              /* kd2.c:819-820 or the error code */
         grp->fMvir = mvir[g];
         if (rvir[g] > 0.0f) {
-            tag_particles(kd, &c, g);                      /* kd2.c:823 */
-            vcm_particles(kd, &c, g, mvir[g]);             /* kd2.c:826 */
+            if (in_conflict[g]) tag_particles(kd, &c, g);  /* kd2.c:823 */
+            if (!kd->bSkipVcm) vcm_particles(kd, &c, g, mvir[g]);   /* kd2.c:826 (only .sogtp prints it) */
             if (grp->fRvir > 0.0f) do_vcirc[g] = 1;        /* kd2.c:884: not slurped */
         }
     }
 
-    phase("tagging replay + vcm", &tp);
+    phase("conflict replay + vcm", &tp);
     /* kdVcirc for every group that was valid when the reference would have called it */
     {
         int nv = 0, k;
@@ -500,7 +515,7 @@ void kdSO(KD kd, float rhovir, int nSmooth)
     phase("kdVcirc / kdMassProfile", &tp);
     kd->dSOSeconds = wall() - t0;
     free(centers); free(rgtp); free(rvir); free(mvir); free(masses); free(ndelta); free(off); free(order);
-    free(do_vcirc); free(slot_of_index); free(mem);
+    free(do_vcirc); free(slot_of_index); free(mem); free(in_conflict);
 }
 
 void kdFinish(KD kd)

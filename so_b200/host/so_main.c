@@ -130,6 +130,8 @@ int main(int argc, char **argv)
 
     kdInit(&kd, nBucket, fPeriod, fCenter, 0, nMembers, bPeriodic, bDark, bGas, bStar, bMark, bPot);
     kd->iDevice = iDevice;
+    kd->bSkipGrpArray = !bGrp;                        /* PINIT.iGrp of conflict-free groups is only read by kdWriteArray */
+    kd->bSkipVcm = !bGtp;                             /* GRPNODE.vcm is only read by kdWriteGTP */
     kdStartGpu(kd);                                   /* CUDA context creation overlaps the snapshot read */
     kdPhase(NULL, &tPhase);
     i = kdReadTipsy(kd, stdin, bStandard);

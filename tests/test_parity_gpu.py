@@ -316,6 +316,45 @@ def test_vcirc_refuses_mixed_masses():
     g.close()
 
 
+@pytest.mark.parametrize("name", ["conflict", "basic"])
+def test_device_tagging_of_conflict_free_groups(name):
+    """sogpu_tag_members against the sequential kdTagParticles replay of the oracle (kd2.c:663-720): every
+    particle the device tags carries the tag the full replay ends with, every group the replay subsumes,
+    slurps or lets ignore particles is flagged, and flagged groups leave their particles untagged."""
+    s, g = load_golden(name)
+    h = len(g["rgtp"])
+    ids = np.arange(1, h + 1, dtype=np.int32)
+    o = po.Oracle(s.pos, s.mass)
+    ref = o.so(g["centers"], g["rgtp"], g["thr"], int(g["n_members"]))
+    t = o.tag(ids, g["centers"], g["gtp_mass"], ref["rvir"].copy(), ref["mvir"].copy(), ref["member_offset"],
+              ref["members"])
+    gpu = api.SoGpu()
+    gpu.set_particles(s.pos, s.mass)
+    gpu.build_grid()
+    gpu.so(g["centers"], g["rgtp"], g["thr"], int(g["n_members"]))
+    dirty, igrp = gpu.tag_members(ids, s.n)
+    gpu.close()
+    off, mem = ref["member_offset"], ref["members"]
+    owners = np.zeros(s.n, np.int32)
+    np.add.at(owners, mem, 1)
+    for i in range(h):
+        seg = mem[off[i]:off[i + 1]]
+        shares = bool((owners[seg] > 1).any())
+        assert dirty[i] == shares, i
+        if not shares:
+            assert (igrp[seg] == ids[i]).all() and (t["igrp"][seg] == ids[i]).all()
+        else:
+            assert not (igrp[seg] == ids[i]).any()
+    tagged = igrp != 0
+    assert np.array_equal(igrp[tagged], t["igrp"][tagged])
+    changed = t["rvir"] != ref["rvir"]                     # subsumed or slurped by the replay
+    assert dirty[changed].all()
+    if name == "conflict":
+        assert dirty.any() and changed.any()
+    else:
+        assert not dirty.any() and np.array_equal(igrp, t["igrp"])
+
+
 def test_unequal_masses_general_path():
     """Mixed particle masses: the enclosed mass is the SEQUENTIAL fp32 sum in sorted order, so the
     library switches to the full-sort path; results must still be bit-exact."""
