@@ -73,6 +73,21 @@ int sogpu_set_cell_occupancy(sogpu_t *h, float particles_per_cell);
 int sogpu_set_particles_host(sogpu_t *h, const void *pos, size_t pos_stride, const void *mass,
                              size_t mass_stride, int64_t n, const float period[3],
                              const float center[3]);
+/* Streaming ingest of RAW TIPSY records, as read from the file: `count` records of `floats_per_record`
+ * 4-byte floats with the mass first and x, y, z next (gas 12, dark 9, star 11 floats, tipsydefs.h:6-37);
+ * big_endian = 1 for -std (XDR) files: the byte swap of xdr_float (kd2.c:369,385,401) then happens on the
+ * device.  Particle numbering follows the order of the calls (gas, dark, star: kd2.c:135-141).
+ *   sogpu_ingest_begin(h, N, period, center); { read a chunk; sogpu_ingest_records(...); }*; sogpu_ingest_end(h)
+ * With a page-locked buffer (sogpu_host_alloc) the copy is an asynchronous DMA that overlaps the
+ * caller's next read; such a buffer may be refilled once the NEXT sogpu_ingest_records / _end call has
+ * returned, i.e. the caller alternates two buffers.  Pageable buffers work too (synchronous copy). */
+void *sogpu_host_alloc(size_t bytes);
+void sogpu_host_free(void *p);
+int sogpu_ingest_begin(sogpu_t *h, int64_t n_total, const float period[3], const float center[3]);
+int sogpu_ingest_records(sogpu_t *h, const void *records, int64_t count, int32_t floats_per_record,
+                         int32_t big_endian);
+int sogpu_ingest_end(sogpu_t *h);
+
 /* Pack + copy host particles (same layout rules) into a CALLER-owned device float4 array, without
  * touching the handle's particle state: used when the array is then replicated to other GPUs
  * (NCCL broadcast) and handed to each handle with sogpu_set_particles_device. */

@@ -27,7 +27,8 @@ SYMBOLS = [
     "sogpu_finish_host", "sogpu_keep_member_d2", "sogpu_profile_enable", "sogpu_profile_kernels",
     "sogpu_profile_name", "sogpu_profile_read", "sogpu_upload_particles",
     "sogpu_set_build_mode", "sogpu_ball_gather_batch",
-    "sogpu_profile_bytes", "sogpu_build_grid_for", "sogpu_build_grid_for_device", "sogpu_set_first_ball", "sogpu_vcirc", "sogpu_tag_members",
+    "sogpu_profile_bytes", "sogpu_build_grid_for", "sogpu_build_grid_for_device", "sogpu_set_first_ball", "sogpu_vcirc", "sogpu_tag_members", "sogpu_host_alloc", "sogpu_host_free", "sogpu_ingest_begin",
+    "sogpu_ingest_records", "sogpu_ingest_end",
 ]
 
 
@@ -67,6 +68,15 @@ def lib():
     L.sogpu_vcirc.restype = C.c_int
     L.sogpu_tag_members.argtypes = [vp, i32p, C.c_int32, C.POINTER(C.c_ubyte), i32p]
     L.sogpu_tag_members.restype = C.c_int
+    L.sogpu_ingest_begin.argtypes = [vp, C.c_int64, fp, fp]
+    L.sogpu_ingest_begin.restype = C.c_int
+    L.sogpu_ingest_records.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32]
+    L.sogpu_ingest_records.restype = C.c_int
+    L.sogpu_ingest_end.argtypes = [vp]
+    L.sogpu_ingest_end.restype = C.c_int
+    L.sogpu_host_alloc.argtypes = [C.c_size_t]
+    L.sogpu_host_alloc.restype = C.c_void_p
+    L.sogpu_host_free.argtypes = [vp]
     L.sogpu_set_first_ball.argtypes = [vp, C.c_int]
     L.sogpu_set_first_ball.restype = C.c_int
     L.sogpu_set_build_mode.argtypes = [vp, C.c_int]
@@ -349,6 +359,21 @@ class SoGpu:
                                  _fp(out["profile"]) if profile else None))
         self._last_h = h
         return out
+
+    def ingest_records(self, blocks, period=(1.0, 1.0, 1.0), center=(0.0, 0.0, 0.0), big_endian=False, chunk=1 << 16):
+        """Raw TIPSY record blocks [(float32 array (n, floats_per_record)), ...] in file order -> device."""
+        n = sum(len(b) for b in blocks)
+        per = (C.c_float * 3)(*period)
+        cen = (C.c_float * 3)(*center)
+        _check(lib().sogpu_ingest_begin(self._h, n, per, cen))
+        for b in blocks:
+            b = np.ascontiguousarray(b)
+            for i0 in range(0, len(b), chunk):
+                part = np.ascontiguousarray(b[i0:i0 + chunk])
+                _check(lib().sogpu_ingest_records(self._h, C.c_void_p(part.ctypes.data), len(part), b.shape[1],
+                                                  1 if big_endian else 0))
+        _check(lib().sogpu_ingest_end(self._h))
+        self.n = n
 
     def tag_members(self, index, n_particles=None):
         """Order-independent part of kdTagParticles: (in_conflict[nh], igrp[N]) for the last so() call."""

@@ -182,6 +182,21 @@ __global__ void __launch_bounds__(256) k_expand_xyz(const float *__restrict__ xy
     }
 }
 
+/* K1 (ingest): raw TIPSY records -> float4 {x,y,z,m}.  A record is `nf` 4-byte floats, mass first, then
+ * x, y, z (gas 12, dark 9, star 11 floats: tipsydefs.h:6-37); `swap` = the file is XDR / big-endian
+ * (-std, kd2.c:32-44,369,385,401), the byte swap happens here instead of in xdr_float. */
+__global__ void __launch_bounds__(256) k_ingest_records(const uint32_t *__restrict__ raw, int64_t count, int nf, int swap,
+                                                        float4 *__restrict__ dst)
+{
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const uint32_t *r = raw + i * nf;
+        uint32_t m = __ldg(r), x = __ldg(r + 1), y = __ldg(r + 2), z = __ldg(r + 3);
+        if (swap) { m = __byte_perm(m, 0, 0x0123); x = __byte_perm(x, 0, 0x0123); y = __byte_perm(y, 0, 0x0123); z = __byte_perm(z, 0, 0x0123); }
+        dst[i] = make_float4(__uint_as_float(x), __uint_as_float(y), __uint_as_float(z), __uint_as_float(m));
+    }
+}
+
 /* ============================================================================================
  * group (warp or block) primitives
  * ============================================================================================ */
@@ -1673,6 +1688,12 @@ struct sogpu {
     uint32_t *d_bsum;
     uint32_t *d_massmm;
     float *d_raw;                    /* staging of raw xyz triplets (pinned-host fast path) */
+    void *d_ingest[2];               /* streaming ingest: raw record chunks */
+    size_t ingest_cap[2];
+    cudaEvent_t ingest_ev[2];
+    int64_t ingest_done;
+    int ingest_slot;
+    bool ingest_prev_ev_valid;
     float4 *d_tmp4;                  /* ping-pong payload buffer of the partition levels */
     uint32_t *d_key[2];              /* ping-pong cell keys between levels */
     int64_t tmp_cap;
@@ -1771,6 +1792,14 @@ struct ProfScope {   /* brackets one (group of) kernel launch(es) with events wh
         cudaEventRecord(r.b, h->launch_stream);
         h->prof_pending.push_back(r);
     }
+};
+
+/* SOGPU_DEBUG_TIMING=1: wall-clock marks inside the longer host-side entry points (stderr) */
+struct DbgTimer {
+    bool on; double t0; cudaStream_t s;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    explicit DbgTimer(cudaStream_t s_) : on(getenv("SOGPU_DEBUG_TIMING") != nullptr), t0(0), s(s_) { if (on) t0 = now(); }
+    void mark(const char *what) { if (!on) return; cudaStreamSynchronize(s); double t = now(); fprintf(stderr, "    [sogpu] %-28s %9.3f ms\n", what, t - t0); t0 = t; }
 };
 
 static int ensure_pinned(sogpu *h, size_t bytes)
@@ -1882,6 +1911,8 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     cudaFree(h->d_in_owned);
     cudaFree(h->d_massmm);
     cudaFree(h->d_raw);
+    cudaFree(h->d_ingest[0]); cudaFree(h->d_ingest[1]);
+    for (int k = 0; k < 2; ++k) if (h->ingest_ev[k]) cudaEventDestroy(h->ingest_ev[k]);
     cudaFree(h->d_mask);
     cudaFree(h->d_tmp4); cudaFree(h->d_key[0]); cudaFree(h->d_key[1]);
     for (int l = 0; l < 4; ++l) { cudaFree(h->d_lvl_start[l]); cudaFree(h->d_lvl_cursor[l]); }
@@ -2062,6 +2093,87 @@ extern "C" int sogpu_set_particles_host(sogpu_t *h, const void *pos, size_t pos_
     }
     h->d_in = h->d_in_owned;
     return upload_to(h, h->d_in_owned, pos, pos_stride, mass, mass_stride, n);
+}
+
+/* ---- streaming ingest of raw TIPSY records (replaces the PINIT fill of kdReadTipsy, kd2.c:352-416) ---- */
+
+extern "C" void *sogpu_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+extern "C" void sogpu_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" int sogpu_ingest_begin(sogpu_t *h, int64_t n_total, const float period[3], const float center[3])
+{
+    if (!h || !period) return set_err(SOGPU_ERR_ARG, "sogpu_ingest_begin: NULL argument");
+    int rc = set_common(h, n_total, period, center);
+    if (rc) return rc;
+    if (n_total > h->d_in_cap) {
+        cudaFree(h->d_in_owned); h->d_in_owned = nullptr; h->d_in_cap = 0;
+        CU(cudaMalloc(&h->d_in_owned, (size_t)n_total * sizeof(float4)));
+        h->d_in_cap = n_total;
+    }
+    h->d_in = nullptr;                     /* set by sogpu_ingest_end */
+    h->ingest_done = 0;
+    h->ingest_slot = 0;
+    h->ingest_prev_ev_valid = false;
+    for (int k = 0; k < 2; ++k)
+        if (!h->ingest_ev[k]) CU(cudaEventCreateWithFlags(&h->ingest_ev[k], cudaEventDisableTiming));
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_ingest_records(sogpu_t *h, const void *records, int64_t count, int32_t floats_per_record,
+                                    int32_t big_endian)
+{
+    if (!h || !records || count < 0 || floats_per_record < 4)
+        return set_err(SOGPU_ERR_ARG, "sogpu_ingest_records: bad argument");
+    if (count == 0) return SOGPU_OK;
+    if (h->ingest_done + count > h->n) return set_err(SOGPU_ERR_ARG, "sogpu_ingest_records: more records than announced");
+    CU(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)count * (size_t)floats_per_record * sizeof(float);
+    const int slot = h->ingest_slot;
+    /* the previous chunk (other slot) is on the device and unpacked: its host buffer is free again, and so
+     * is this slot's device staging (used two chunks ago, finished before the previous one in stream order) */
+    if (h->ingest_prev_ev_valid) CU(cudaEventSynchronize(h->ingest_ev[slot ^ 1]));
+    if (bytes > h->ingest_cap[slot]) {
+        cudaFree(h->d_ingest[slot]); h->d_ingest[slot] = nullptr; h->ingest_cap[slot] = 0;
+        CU(cudaMalloc(&h->d_ingest[slot], bytes));
+        h->ingest_cap[slot] = bytes;
+    }
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, records) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    cudaStream_t s = h->stream;
+    /* page-locked source: asynchronous DMA; pageable source: the call returns when the driver has staged
+     * the data (the caller's buffer is free again), the copy itself stays ordered before the unpack kernel */
+    (void)pinned;
+    CU(cudaMemcpyAsync(h->d_ingest[slot], records, bytes, cudaMemcpyHostToDevice, s));
+    const int grid = (int)std::min<int64_t>((count + 255) / 256, (int64_t)h->sm_count * 8);
+    k_ingest_records<<<grid, 256, 0, s>>>((const uint32_t *)h->d_ingest[slot], count, floats_per_record, big_endian ? 1 : 0,
+                                          h->d_in_owned + h->ingest_done);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(h->ingest_ev[slot], s));
+    h->ingest_prev_ev_valid = true;
+    h->ingest_done += count;
+    h->ingest_slot = slot ^ 1;
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_ingest_end(sogpu_t *h)
+{
+    if (!h) return set_err(SOGPU_ERR_ARG, "NULL handle");
+    if (h->ingest_done != h->n)
+        return set_err(SOGPU_ERR_ARG, "sogpu_ingest_end: %lld of %lld records received", (long long)h->ingest_done, (long long)h->n);
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    h->d_in = h->d_in_owned;
+    return SOGPU_OK;
 }
 
 static int pick_cells(int64_t n, float ppc, int *lb)
@@ -2946,6 +3058,7 @@ extern "C" int sogpu_ball_gather_batch(sogpu_t *h, const float *centers, const f
         unsigned long long tot = 0;
         CU(cudaMemcpyAsync(&tot, h->d_u64, sizeof(tot), cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
+        if (getenv("SOGPU_DEBUG_TIMING")) fprintf(stderr, "    [sogpu] ball batch attempt %d: %llu entries (cap %llu)\n", attempt, tot, h->member_cap);
         if (tot <= h->member_cap) break;
         if (attempt == 1) return set_err(SOGPU_ERR_NOMEM, "ball lists need %llu entries", tot);
         cudaFree(h->d_members); cudaFree(h->d_md2);
@@ -2980,14 +3093,17 @@ extern "C" int sogpu_vcirc(sogpu_t *h, const float *centers, const float *rvir, 
         float fBall = (float)(2. * rvir[i]);                              /* kd2.c:511-512 */
         ball2[i] = fBall * fBall;
     }
+    DbgTimer dt(h->stream);
     rc = sogpu_ball_gather_batch(h, centers, ball2.data(), nh);
     if (rc) return rc;
+    dt.mark("vcirc: ball gather batch");
     rc = fetch_stats(h);
     if (rc) return rc;
     const size_t tot = (size_t)h->stats.last_members;
     rc = sort_members_device(h, nh, tot);
     if (rc) return rc;
     h->members_sorted = true;
+    dt.mark("vcirc: segmented sort");
     /* per-group inputs and outputs share one device block: rvir, mvir | vcirc 8, rmass 2, rmax, vmax, profile 16 */
     const size_t per = 2 + SO_NVCIRC + 2 + 1 + 1 + SO_NMASSPROFILE;
     if ((size_t)nh * per > h->vc_cap) {
@@ -3010,8 +3126,10 @@ extern "C" int sogpu_vcirc(sogpu_t *h, const float *centers, const float *rvir, 
     a.rmax = a.rmass + (size_t)2 * nh;
     a.vmax = a.rmax + nh;
     a.profile = profile ? a.vmax + nh : nullptr;
+    dt.mark("vcirc: buffers + upload");
     { ProfScope p(h, KID_VCIRC); k_vcirc<<<std::min(nh, h->sm_count * 16), 256, 0, s>>>(a); }
     CU(cudaGetLastError());
+    dt.mark("vcirc: k_vcirc");
     const size_t n_out = (size_t)nh * (per - 2);
     CU(cudaMemcpyAsync(pin + (size_t)2 * nh, h->d_vc + (size_t)2 * nh, n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));

@@ -79,6 +79,7 @@ typedef struct kdContext {
     int uSecond, uMicro;
     sogpu_t *gpu;
     int iDevice;
+    int bIngested;         /* kdReadTipsy streamed the particles to the device already */
     int bSkipGrpArray;     /* main() sets these when nothing will print the per-particle tags (.sogrp) ... */
     int bSkipVcm;          /* ... or the centre-of-mass velocities (.sogtp)                                  */
     int nGrpsInConflict;   /* groups that shared particles and went through the sequential replay           */
@@ -100,7 +101,7 @@ void kdSO(KD, float rhovir, int nSmooth);
 void kdWriteProfile(KD, char *achOutFileBase, time_t, FILE *, int ptype);
 void kdWriteOut(KD, FILE *);
 int kdBuildTree(KD);
-void kdStartGpu(KD);                             /* optional: create the CUDA context on a thread, early */
+sogpu_t *kdGpu(KD);                              /* the device handle, created on first use */
 void kdPhase(const char *name, double *t);       /* SO_TIMING=1: phase wall-clock on stderr */
 void kdFinish(KD);
 void kdWriteConflict(KD, char *achOutFileBase, int iOpt);

@@ -89,40 +89,91 @@ static void write_header(FILE *fp, int bStandard, const tipsy_header *h)
     fwrite(b, 1, 32, fp);
 }
 
-/* read `count` records of `nf` floats; field offsets (in floats): mass 0, pos 1..3, vel 4..6, phi last */
-static void read_species(KD kd, FILE *fp, int bStandard, int first, int count, int nf)
+/* Read `count` records of `nf` floats (field offsets in floats: mass 0, pos 1..3, vel 4..6, phi last) and
+ * stream them RAW to the device: chunks are read into two page-locked buffers used alternately, each is
+ * handed to sogpu_ingest_records (asynchronous DMA + unpack / XDR byte swap on the GPU, f3 of SURVEY §8)
+ * while the next one is being read.  The host keeps only what its own passes need: the mass, the
+ * velocity if .sogtp is written, the potential and the position for -pot. */
+#define READ_CHUNK (1 << 20)
+
+static float load_f32(const float *p, int swap)
 {
-    const int chunk = 1 << 16;
-    float *buf = (float *)malloc((size_t)chunk * nf * sizeof(float));
+    uint32_t u;
+    float f;
+    memcpy(&u, p, 4);
+    if (swap) u = bswap32(u);
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+static double g_t_fread, g_t_ingest, g_t_extract;
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static void read_species(KD kd, FILE *fp, int bStandard, int first, int count, int nf, float *buf[2], int *slot)
+{
     int done = 0;
-    assert(buf != NULL);
     while (done < count) {
-        int k = count - done < chunk ? count - done : chunk, i;
-        size_t got = fread(buf, sizeof(float) * nf, (size_t)k, fp);
+        int k = count - done < READ_CHUNK ? count - done : READ_CHUNK, i;
+        float *b = buf[*slot];
+        double t0 = now_s(), t1, t2;
+        size_t got = fread(b, sizeof(float) * nf, (size_t)k, fp);
+        t1 = now_s();
         if ((int)got != k) {
             fprintf(stderr, "ERROR: TIPSY file ends after %d of %d particles\n", first + done + (int)got, kd->nParticles);
             exit(1);
         }
-        if (bStandard) swap_floats(buf, (size_t)k * nf);
-        for (i = 0; i < k; ++i) {
-            const float *rec = buf + (size_t)i * nf;
-            int p = first + done + i, j;
-            kd->p.fMass[p] = rec[0];
-            for (j = 0; j < 3; ++j) {
-                kd->p.r[3 * p + j] = rec[1 + j];
-                kd->p.v[3 * p + j] = rec[4 + j];
-            }
-            kd->p.fPhi[p] = rec[nf - 1];
+        if (sogpu_ingest_records(kd->gpu, b, k, nf, bStandard)) {
+            fprintf(stderr, "ERROR in kdReadTipsy (sogpu_ingest_records): %s\n", sogpu_last_error());
+            exit(1);
         }
+        t2 = now_s();
+        {   /* host copies of the fields the host passes still read (branches hoisted out of the loops) */
+            const int p0 = first + done;
+            float *m = kd->p.fMass + p0;
+            if (!bStandard) {
+                for (i = 0; i < k; ++i) m[i] = b[(size_t)i * nf];
+                if (kd->p.v) {
+                    float *v = kd->p.v + 3 * (size_t)p0;
+                    for (i = 0; i < k; ++i) memcpy(v + 3 * (size_t)i, b + (size_t)i * nf + 4, 3 * sizeof(float));
+                }
+                if (kd->p.r) {
+                    float *r = kd->p.r + 3 * (size_t)p0, *phi = kd->p.fPhi + p0;
+                    for (i = 0; i < k; ++i) {
+                        memcpy(r + 3 * (size_t)i, b + (size_t)i * nf + 1, 3 * sizeof(float));
+                        phi[i] = b[(size_t)i * nf + nf - 1];
+                    }
+                }
+            } else {
+                for (i = 0; i < k; ++i) {
+                    const float *rec = b + (size_t)i * nf;
+                    int p = p0 + i, j;
+                    m[i] = load_f32(rec, 1);
+                    if (kd->p.v) for (j = 0; j < 3; ++j) kd->p.v[3 * (size_t)p + j] = load_f32(rec + 4 + j, 1);
+                    if (kd->p.r) {
+                        for (j = 0; j < 3; ++j) kd->p.r[3 * (size_t)p + j] = load_f32(rec + 1 + j, 1);
+                        kd->p.fPhi[p] = load_f32(rec + nf - 1, 1);
+                    }
+                }
+            }
+        }
+        g_t_fread += t1 - t0; g_t_ingest += t2 - t1; g_t_extract += now_s() - t2;
         done += k;
+        *slot ^= 1;
     }
-    free(buf);
 }
 
 int kdReadTipsy(KD kd, FILE *fp, int bStandard)
 {
     tipsy_header h;
     size_t n;
+    float *buf[2];
+    int slot = 0;
+    double tp;
     if (!read_header(fp, bStandard, &h)) {
         fprintf(stderr, "ERROR: cannot read TIPSY header\n");
         exit(1);
@@ -131,19 +182,43 @@ int kdReadTipsy(KD kd, FILE *fp, int bStandard)
     kd->fTime = (float)h.time;
     kd->nParticles = kd->nDark + kd->nGas + kd->nStar;
     n = (size_t)(kd->nParticles > 0 ? kd->nParticles : 1);
-    kd->p.r = (float *)malloc(n * 3 * sizeof(float));
-    kd->p.v = (float *)malloc(n * 3 * sizeof(float));
     kd->p.fMass = (float *)malloc(n * sizeof(float));
-    kd->p.fPhi = (float *)malloc(n * sizeof(float));
+    kd->p.v = kd->bSkipVcm ? NULL : (float *)malloc(n * 3 * sizeof(float));   /* only _VcmParticles reads it */
+    kd->p.r = kd->bPot ? (float *)malloc(n * 3 * sizeof(float)) : NULL;       /* only -pot reads these two  */
+    kd->p.fPhi = kd->bPot ? (float *)malloc(n * sizeof(float)) : NULL;
     kd->p.iGrp = (int32_t *)calloc(n, sizeof(int32_t));
     kd->p.nSubsumed = (int32_t *)calloc(n, sizeof(int32_t));
     kd->p.nIgnored = (int32_t *)calloc(n, sizeof(int32_t));
-    assert(kd->p.r && kd->p.v && kd->p.fMass && kd->p.fPhi && kd->p.iGrp && kd->p.nSubsumed && kd->p.nIgnored);
+    assert(kd->p.fMass && kd->p.iGrp && kd->p.nSubsumed && kd->p.nIgnored);
+    assert((kd->p.v || kd->bSkipVcm) && (!kd->bPot || (kd->p.r && kd->p.fPhi)));
     fprintf(stderr, "nDark:%d nGas:%d nStar:%d\n", kd->nDark, kd->nGas, kd->nStar);
+    if (kd->nParticles == 0) return 0;
+    kdGpu(kd);                                                      /* the records go straight to the device */
+    kdPhase(NULL, &tp);
+    if (sogpu_ingest_begin(kd->gpu, kd->nParticles, kd->fPeriod, kd->fCenter)) {
+        fprintf(stderr, "ERROR in kdReadTipsy (sogpu_ingest_begin): %s\n", sogpu_last_error());
+        exit(1);
+    }
+    buf[0] = (float *)sogpu_host_alloc((size_t)READ_CHUNK * 12 * sizeof(float));
+    buf[1] = (float *)sogpu_host_alloc((size_t)READ_CHUNK * 12 * sizeof(float));
+    assert(buf[0] && buf[1]);
+    kdPhase("  ingest_begin + pinned buffers", &tp);
     /* file order: gas, dark, star (kdParticleType, kd2.c:135-141) */
-    read_species(kd, fp, bStandard, 0, kd->nGas, 12);
-    read_species(kd, fp, bStandard, kd->nGas, kd->nDark, 9);
-    read_species(kd, fp, bStandard, kd->nGas + kd->nDark, kd->nStar, 11);
+    read_species(kd, fp, bStandard, 0, kd->nGas, 12, buf, &slot);
+    read_species(kd, fp, bStandard, kd->nGas, kd->nDark, 9, buf, &slot);
+    read_species(kd, fp, bStandard, kd->nGas + kd->nDark, kd->nStar, 11, buf, &slot);
+    if (sogpu_ingest_end(kd->gpu)) {
+        fprintf(stderr, "ERROR in kdReadTipsy (sogpu_ingest_end): %s\n", sogpu_last_error());
+        exit(1);
+    }
+    kdPhase("  read + stream chunks", &tp);
+    sogpu_host_free(buf[0]);
+    sogpu_host_free(buf[1]);
+    kdPhase("  free pinned buffers", &tp);
+    kd->bIngested = 1;
+    if (getenv("SO_TIMING"))
+        fprintf(stderr, "  [timing]   of which fread %.1f ms, sogpu_ingest_records %.1f ms, host field copies %.1f ms\n",
+                1e3 * g_t_fread, 1e3 * g_t_ingest, 1e3 * g_t_extract);
     return kd->nParticles;
 }
 

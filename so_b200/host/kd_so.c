@@ -1,23 +1,24 @@
 /* kd_so.c — the hot-path calls of the drop-in `so`, routed to the GPU through include/sogpu.h.
  *
- *   kdBuildTree  (kd2.c:1096-1185)  -> sogpu_set_particles_host + sogpu_build_grid
- *   kdSO         (kd2.c:864-895)    -> sogpu_so + sogpu_members, then on the host, in the
- *                                      reference's processing order (kdSortMass/indexx,
- *                                      kd2.c:843-861): kdTagParticles / kdZeroGroup bookkeeping
- *                                      (kd2.c:617-720), _VcmParticles (kd2.c:595-609) and the
- *                                      kdVcirc / kdMassProfile post-processing (kd2.c:437-586) over
- *                                      GPU-gathered, r^2-sorted 2*Rvir lists (sogpu_ball_gather_batch).
- *
- * The conflict pass is order dependent (a later, more massive halo may subsume or slurp an earlier
- * one) and touches O(sum N_Delta) items, so it stays sequential on the host; the reference's
- * O(N) sweep per zeroed group (kd2.c:636-641) and O(H) search per conflicting particle
- * (kd2.c:647-660) are replaced by the member lists and an index -> slot map.
+ *   kdBuildTree  (kd2.c:1096-1185)  -> sogpu_build_grid (the particles are already on the device:
+ *                                      kdReadTipsy streams the raw records there, kd_io.c)
+ *   kdSO         (kd2.c:864-895)    -> sogpu_so + sogpu_members (sorted on the device), then
+ *       kdTagParticles (kd2.c:663-720)  sogpu_tag_members: groups that share no particle are tagged on the
+ *                                      device; the others are replayed here in the reference's processing
+ *                                      order (kdSortMass/indexx, kd2.c:843-861) with kdZeroGroup's
+ *                                      bookkeeping (kd2.c:617-643): subsume / slurp / ignore are order
+ *                                      dependent.  The reference's O(N) sweep per zeroed group and O(H)
+ *                                      search per conflicting particle (kd2.c:636-660) are replaced by the
+ *                                      member lists and an index -> slot map.
+ *       _VcmParticles (kd2.c:595-609)   host, only when .sogtp is written
+ *       kdVcirc / kdMassProfile (kd2.c:437-586)  sogpu_vcirc on the device for equal-mass single-species
+ *                                      snapshots; host walk over GPU-gathered, device-sorted 2*Rvir lists
+ *                                      otherwise (per-species fp32 sums need the particle at each rank)
  */
 #include "kd.h"
 
 #include <assert.h>
 #include <math.h>
-#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/resource.h>
@@ -94,39 +95,16 @@ static double wall(void)
     return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
-/* Creating the CUDA context takes ~0.6 s and does not depend on the input, so main() may start it on a
- * thread before the snapshot is read (SO_EARLY_GPU=1) and kdBuildTree joins it.  Off by default:
- * measured on the B200 host the driver's address-space setup and the reader's page faults fight
- * over the process's mmap lock and the context then takes 2.5-3.8 s instead of 0.6 s. */
-static pthread_t g_gpu_thread;
-static int g_gpu_thread_on = 0, g_gpu_thread_rc = 0;
-static char g_gpu_thread_err[512];
-
-static void *gpu_create_thread(void *arg)
+/* the device handle, created on first use (CUDA context creation: 0.6 s and more, once per process) */
+sogpu_t *kdGpu(KD kd)
 {
-    KD kd = (KD)arg;
-    g_gpu_thread_rc = sogpu_create(&kd->gpu, kd->iDevice);
-    if (g_gpu_thread_rc) snprintf(g_gpu_thread_err, sizeof(g_gpu_thread_err), "%s", sogpu_last_error());
-    return NULL;
-}
-
-void kdStartGpu(KD kd)
-{
-    if (kd->gpu || g_gpu_thread_on || !getenv("SO_EARLY_GPU")) return;
-    if (pthread_create(&g_gpu_thread, NULL, gpu_create_thread, kd) == 0) g_gpu_thread_on = 1;
-}
-
-static void join_gpu(KD kd)
-{
-    if (g_gpu_thread_on) {
-        pthread_join(g_gpu_thread, NULL);
-        g_gpu_thread_on = 0;
-        if (g_gpu_thread_rc) {
-            fprintf(stderr, "ERROR in kdBuildTree (sogpu_create): %s\n", g_gpu_thread_err);
-            exit(1);
-        }
+    if (!kd->gpu) {
+        double tp;
+        kdPhase(NULL, &tp);
+        if (sogpu_create(&kd->gpu, kd->iDevice)) die_gpu("sogpu_create");
+        kdPhase("CUDA context", &tp);
     }
-    if (!kd->gpu && sogpu_create(&kd->gpu, kd->iDevice)) die_gpu("kdBuildTree (sogpu_create)");
+    return kd->gpu;
 }
 
 int kdBuildTree(KD kd)
@@ -135,12 +113,16 @@ int kdBuildTree(KD kd)
     double tp;
     if (kd->nParticles == 0) return 1;
     phase(NULL, &tp);
-    join_gpu(kd);
-    phase("wait for the CUDA context", &tp);
-    if (sogpu_set_particles_host(kd->gpu, kd->p.r, 3 * sizeof(float), kd->p.fMass, sizeof(float), kd->nParticles,
-                                 kd->fPeriod, kd->fCenter))
-        die_gpu("kdBuildTree (sogpu_set_particles_host)");
-    phase("upload particles", &tp);
+    if (!kd->bIngested) {
+        /* particles that did not come through kdReadTipsy's streaming ingest */
+        kdGpu(kd);
+        phase(NULL, &tp);
+        if (!kd->p.r) { fprintf(stderr, "ERROR in kdBuildTree: no particle positions\n"); exit(1); }
+        if (sogpu_set_particles_host(kd->gpu, kd->p.r, 3 * sizeof(float), kd->p.fMass, sizeof(float), kd->nParticles,
+                                     kd->fPeriod, kd->fCenter))
+            die_gpu("kdBuildTree (sogpu_set_particles_host)");
+        phase("upload particles", &tp);
+    }
     if (sogpu_build_grid(kd->gpu)) die_gpu("kdBuildTree (sogpu_build_grid)");
     phase("build grid (enqueue)", &tp);
     kd->dBuildSeconds = wall() - t0;

@@ -132,10 +132,10 @@ int main(int argc, char **argv)
     kd->iDevice = iDevice;
     kd->bSkipGrpArray = !bGrp;                        /* PINIT.iGrp of conflict-free groups is only read by kdWriteArray */
     kd->bSkipVcm = !bGtp;                             /* GRPNODE.vcm is only read by kdWriteGTP */
-    kdStartGpu(kd);                                   /* CUDA context creation overlaps the snapshot read */
+    kdGpu(kd);                                        /* the snapshot is streamed to the device as it is read */
     kdPhase(NULL, &tPhase);
     i = kdReadTipsy(kd, stdin, bStandard);
-    kdPhase("read TIPSY snapshot", &tPhase);
+    kdPhase("read TIPSY snapshot -> device", &tPhase);
     fprintf(stderr, "Read %d particles from TIPSY file.\n", i);
     if (bMark) {
         i = kdReadMark(kd, achMarkFile);

@@ -232,6 +232,33 @@ def test_records_layout_and_tiny_inputs():
     g.close()
 
 
+@pytest.mark.parametrize("big_endian", [False, True])
+def test_streaming_ingest_of_raw_tipsy_records(big_endian):
+    """sogpu_ingest_records: raw gas / dark / star records (12 / 9 / 11 floats, mass first, then x y z;
+    XDR byte order for -std files) unpacked on the device give the results of the packed upload."""
+    s = synth.make_snapshot(40 ** 3, 25, seed=71, nmax=3000)
+    n = s.n
+    ng, nd = n // 5, n // 2
+    cuts = [(0, ng, 12), (ng, ng + nd, 9), (ng + nd, n, 11)]
+    rng = np.random.default_rng(3)
+    blocks = []
+    for a, b, nf in cuts:
+        rec = rng.random((b - a, nf)).astype(np.float32)          # junk in the fields the path ignores
+        rec[:, 0] = s.mass
+        rec[:, 1:4] = s.pos[a:b]
+        blocks.append(rec.astype(">f4").view(np.float32) if big_endian else rec)
+    ref = run_gpu(s.pos, s.mass, s.centers, s.rgtp, 200.0)
+    g = api.SoGpu()
+    g.ingest_records(blocks, big_endian=big_endian, chunk=7777)
+    g.build_grid()
+    g.keep_member_d2(True)
+    r = g.so(s.centers, s.rgtp, 200.0)
+    off, mem = g.members(sorted=True)
+    g.close()
+    assert_so_equal(r, ref["rvir"], ref["mvir"], ref["ndelta"])
+    assert np.array_equal(mem, ref["members"]) and np.array_equal(off, ref["member_offset"])
+
+
 def test_pinned_host_memory_fast_paths():
     """Page-locked caller memory is DMA'd directly (xyz triplets / float4) and unpacked on the GPU."""
     import torch

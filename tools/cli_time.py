@@ -42,7 +42,7 @@ def main():
         assert r.returncode == 0, r.stderr[-3000:]
         res[name] = dt
         print("== %s: %.3f s wall" % (name, dt))
-        print("\n".join(l for l in r.stderr.splitlines() if "timing" in l or "CPU Time" in l or l.strip().startswith("SO")))
+        print("\n".join(l for l in r.stderr.splitlines() if "timing" in l or "[sogpu]" in l or "[members]" in l or "CPU Time" in l or l.strip().startswith("SO")))
     if "ref" in res:
         a, b = tipsy.read_sogrp(os.path.join(tmp, "ours.sogrp")), tipsy.read_sogrp(os.path.join(tmp, "ref.sogrp"))
         print(".sogrp identical:", bool(np.array_equal(a, b)))
