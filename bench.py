@@ -420,9 +420,21 @@ def run_ours(args):
         kernels[kname] = ent
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     dk = kernels[dom]
+    lps = max(dk["launches_per_step"], 1.0)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": dk.get("gbs"), "peak": peak, "unit": "GB/s",
                 "frac": (dk.get("gbs") or 0.0) / peak, "traffic": None, "peak_source": peak_src,
-                "alg_bytes_per_launch": dk.get("alg_bytes"), "share_of_step": dk["share"]}
+                "alg_bytes_per_launch": (dk.get("alg_bytes") or 0.0) / lps, "launches_per_step": lps,
+                "avg_launch_ms": dk["ms_per_step"] / lps, "share_of_step": dk["share"],
+                "timed": "live CUDA events on the launching stream, second pass over the same K steps"}
+    # DRAM traffic per launch of that kernel from the committed `ncu --set full` capture (same workload only)
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and args.scale == 1.0:
+        tj = json.load(open(tpath))
+        if tj.get("workload", "") and name.startswith(tj["workload"]):
+            hit = [v["dram_bytes_per_launch"] for k, v in tj["kernels"].items() if k.startswith(dom)]
+            if hit:
+                roofline["traffic"] = sum(hit) / len(hit)
+                roofline["traffic_source"] = tj.get("source")
     launches = int(round(sum(v[1] for v in prof.values()) / args.steps))
     # the two query kernels share one evaluation counter: split it by their time share
     qk = [k for k in ("k_so_query<32>", "k_so_query<256>") if k in kernels]

@@ -190,6 +190,39 @@ int sogpu_vcirc(sogpu_t *h, const float *centers, const float *rvir, const float
 int sogpu_tag_members(sogpu_t *h, const int32_t *index, int32_t nh, unsigned char *in_conflict,
                       int32_t *igrp);
 
+/* ---- several GPUs: domain runs ----------------------------------------- */
+
+/* Every rank (one process per GPU) holds a SLICE of the snapshot and a spatially compact share of the
+ * halos.  Its focus mask marks the coarse cells (2^min(lb,8) per axis, lb from n_total) its halos can
+ * reach within n_balls steps of the ball schedule; the masks of all ranks are exchanged (they are a few
+ * MB), then every rank routes each of its particles to every rank whose mask holds the particle's cell:
+ *   sogpu_domain_mask_words   size of one mask in 32-bit words
+ *   sogpu_domain_mask         this rank's mask -> d_mask (device)
+ *   sogpu_domain_route_count  counts[r] = particles of this slice that rank r needs (host array)
+ *   sogpu_domain_route_scatter  writes {x, y, z, global index} records of 16 bytes to dst[r] + dst_offset[r]
+ *                             (device pointers: local buffers for an NCCL all-to-all, or the receivers'
+ *                             own buffers mapped with sogpu_peer_open — the kernel then stores over NVLink)
+ *   sogpu_set_particles_device_indexed  hands the received records to the grid build; all particles have
+ *                             mass `mass`; n_total keeps the cell size identical on every rank
+ * followed by sogpu_build_grid_for[_device] with the same halos and n_balls (balls that leave the mask
+ * are reported with code -103 by sogpu_so_device and must be re-run with a larger n_balls) and sogpu_so*.
+ * Member indices are the global ones.  d_slice is float4 {x,y,z,m}; masks are n_ranks consecutive masks. */
+int sogpu_domain_mask_words(sogpu_t *h, int64_t n_total, int64_t *words);
+int sogpu_domain_mask(sogpu_t *h, int64_t n_total, const float period[3], const float center[3],
+                      const float *centers, const float *rgtp, int32_t nh, int32_t n_balls, void *d_mask);
+int sogpu_domain_route_count(sogpu_t *h, int64_t n_total, const void *d_slice, int64_t n_slice,
+                             const void *d_masks, int32_t n_ranks, int64_t *counts);
+int sogpu_domain_route_scatter(sogpu_t *h, int64_t n_total, const void *d_slice, int64_t n_slice,
+                               int64_t index_base, const void *d_masks, int32_t n_ranks,
+                               void *const *dst, const int64_t *dst_offset);
+int sogpu_set_particles_device_indexed(sogpu_t *h, const void *d_xyzi, int64_t n_local, int64_t n_total,
+                                       float mass, const float period[3], const float center[3]);
+/* receive buffers another process of the node can map (cudaIpc*): handle64 is 64 opaque bytes */
+int sogpu_peer_alloc(sogpu_t *h, size_t bytes, void **ptr, void *handle64);
+int sogpu_peer_open(sogpu_t *h, const void *handle64, void **ptr);
+int sogpu_peer_close(sogpu_t *h, void *ptr);
+int sogpu_peer_free(sogpu_t *h, void *ptr);
+
 /* ---- introspection --------------------------------------------------------------------------- */
 
 typedef struct {

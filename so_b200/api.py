@@ -28,7 +28,9 @@ SYMBOLS = [
     "sogpu_profile_name", "sogpu_profile_read", "sogpu_upload_particles",
     "sogpu_set_build_mode", "sogpu_ball_gather_batch",
     "sogpu_profile_bytes", "sogpu_build_grid_for", "sogpu_build_grid_for_device", "sogpu_set_first_ball", "sogpu_vcirc", "sogpu_tag_members", "sogpu_host_alloc", "sogpu_host_free", "sogpu_ingest_begin",
-    "sogpu_ingest_records", "sogpu_ingest_end",
+    "sogpu_ingest_records", "sogpu_ingest_end", "sogpu_domain_mask_words", "sogpu_domain_mask",
+    "sogpu_domain_route_count", "sogpu_domain_route_scatter", "sogpu_set_particles_device_indexed",
+    "sogpu_peer_alloc", "sogpu_peer_open", "sogpu_peer_close", "sogpu_peer_free",
 ]
 
 
@@ -77,6 +79,20 @@ def lib():
     L.sogpu_host_alloc.argtypes = [C.c_size_t]
     L.sogpu_host_alloc.restype = C.c_void_p
     L.sogpu_host_free.argtypes = [vp]
+    L.sogpu_domain_mask_words.argtypes = [vp, C.c_int64, i64p]
+    L.sogpu_domain_mask.argtypes = [vp, C.c_int64, fp, fp, fp, fp, C.c_int32, C.c_int32, vp]
+    L.sogpu_domain_route_count.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, C.c_int32, i64p]
+    L.sogpu_domain_route_scatter.argtypes = [vp, C.c_int64, vp, C.c_int64, C.c_int64, vp, C.c_int32,
+                                             C.POINTER(C.c_void_p), i64p]
+    L.sogpu_set_particles_device_indexed.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_float, fp, fp]
+    L.sogpu_peer_alloc.argtypes = [vp, C.c_size_t, C.POINTER(C.c_void_p), vp]
+    L.sogpu_peer_open.argtypes = [vp, vp, C.POINTER(C.c_void_p)]
+    L.sogpu_peer_close.argtypes = [vp, vp]
+    L.sogpu_peer_free.argtypes = [vp, vp]
+    for f in (L.sogpu_domain_mask_words, L.sogpu_domain_mask, L.sogpu_domain_route_count, L.sogpu_domain_route_scatter,
+              L.sogpu_set_particles_device_indexed, L.sogpu_peer_alloc, L.sogpu_peer_open, L.sogpu_peer_close,
+              L.sogpu_peer_free):
+        f.restype = C.c_int
     L.sogpu_set_first_ball.argtypes = [vp, C.c_int]
     L.sogpu_set_first_ball.restype = C.c_int
     L.sogpu_set_build_mode.argtypes = [vp, C.c_int]
@@ -374,6 +390,59 @@ class SoGpu:
                                                   1 if big_endian else 0))
         _check(lib().sogpu_ingest_end(self._h))
         self.n = n
+
+    # ---- domain runs (several GPUs) -------------------------------------------------------------
+    def domain_mask_words(self, n_total):
+        w = C.c_int64()
+        _check(lib().sogpu_domain_mask_words(self._h, int(n_total), C.byref(w)))
+        return int(w.value)
+
+    def domain_mask(self, n_total, centers, rgtp, n_balls, d_mask, period=(1.0, 1.0, 1.0), center=(0.0, 0.0, 0.0)):
+        centers = np.ascontiguousarray(centers, np.float32).reshape(-1, 3)
+        rgtp = np.ascontiguousarray(rgtp, np.float32)
+        per, cen = (C.c_float * 3)(*period), (C.c_float * 3)(*center)
+        _check(lib().sogpu_domain_mask(self._h, int(n_total), per, cen, _fp(centers) if len(rgtp) else None,
+                                       _fp(rgtp) if len(rgtp) else None, len(rgtp), int(n_balls), C.c_void_p(int(d_mask))))
+
+    def domain_route_count(self, n_total, d_slice, n_slice, d_masks, n_ranks):
+        counts = np.zeros(n_ranks, np.int64)
+        _check(lib().sogpu_domain_route_count(self._h, int(n_total), C.c_void_p(int(d_slice)), int(n_slice),
+                                              C.c_void_p(int(d_masks)), int(n_ranks),
+                                              counts.ctypes.data_as(C.POINTER(C.c_int64))))
+        return counts
+
+    def domain_route_scatter(self, n_total, d_slice, n_slice, index_base, d_masks, dst_ptrs, dst_offsets):
+        n_ranks = len(dst_ptrs)
+        ptrs = (C.c_void_p * n_ranks)(*[int(p) for p in dst_ptrs])
+        offs = np.ascontiguousarray(dst_offsets, np.int64)
+        _check(lib().sogpu_domain_route_scatter(self._h, int(n_total), C.c_void_p(int(d_slice)), int(n_slice),
+                                                int(index_base), C.c_void_p(int(d_masks)), n_ranks, ptrs,
+                                                offs.ctypes.data_as(C.POINTER(C.c_int64))))
+
+    def set_particles_device_indexed(self, d_xyzi, n_local, n_total, mass, period=(1.0, 1.0, 1.0), center=(0.0, 0.0, 0.0)):
+        per, cen = (C.c_float * 3)(*period), (C.c_float * 3)(*center)
+        _check(lib().sogpu_set_particles_device_indexed(self._h, C.c_void_p(int(d_xyzi)), int(n_local), int(n_total),
+                                                        C.c_float(float(mass)), per, cen))
+        self.n = int(n_local)
+
+    def peer_alloc(self, nbytes):
+        """(device pointer, 64-byte handle another process of the node can open)"""
+        p = C.c_void_p()
+        hbuf = (C.c_ubyte * 64)()
+        _check(lib().sogpu_peer_alloc(self._h, int(nbytes), C.byref(p), hbuf))
+        return int(p.value), bytes(hbuf)
+
+    def peer_open(self, handle):
+        p = C.c_void_p()
+        hbuf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        _check(lib().sogpu_peer_open(self._h, hbuf, C.byref(p)))
+        return int(p.value)
+
+    def peer_close(self, ptr):
+        _check(lib().sogpu_peer_close(self._h, C.c_void_p(int(ptr))))
+
+    def peer_free(self, ptr):
+        _check(lib().sogpu_peer_free(self._h, C.c_void_p(int(ptr))))
 
     def tag_members(self, index, n_particles=None):
         """Order-independent part of kdTagParticles: (in_conflict[nh], igrp[N]) for the last so() call."""

@@ -247,10 +247,12 @@ __global__ void __launch_bounds__(256) k_lvl_hist(const float4 *__restrict__ in4
                     bool kept = true;
                     float4 q = ld_stream(in4 + i);
                     uint32_t key = cell_key_kept(q, g, kept);
-                    uint32_t mo = (q.w >= 0.0f) ? __float_as_uint(q.w) : 0xFFFFFFFEu;
-                    if (!(q.w >= 0.0f)) mn = 0u;     /* negative / NaN mass: treated as "unequal" */
-                    mn = min(mn, mo);
-                    mx = max(mx, mo);
+                    if (!g.indexed) {                /* (.w of indexed input is the particle's global index) */
+                        uint32_t mo = (q.w >= 0.0f) ? __float_as_uint(q.w) : 0xFFFFFFFEu;
+                        if (!(q.w >= 0.0f)) mn = 0u; /* negative / NaN mass: treated as "unequal" */
+                        mn = min(mn, mo);
+                        mx = max(mx, mo);
+                    }
                     if (kept) atomicAdd(&sh[(key >> lv.shift) & cmask], 1u);
                 }
             } else {
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(256) k_lvl_hist(const float4 *__restrict__ in4
             pos = send;
         }
     }
-    if (FIRST) {
+    if (FIRST && !g.indexed) {
         mn = __reduce_min_sync(0xFFFFFFFFu, mn);
         mx = __reduce_max_sync(0xFFFFFFFFu, mx);
         if ((threadIdx.x & 31) == 0) {
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(LVL_THREADS, 2) k_lvl_partition(const float4 *
                         bool kept = true;
                         if (FIRST) {
                             key[k] = cell_key_kept(q[k], g, kept);
-                            q[k].w = __int_as_float((int)(pos + i));      /* payload: original index */
+                            if (!g.indexed) q[k].w = __int_as_float((int)(pos + i));      /* payload: original index */
                         }
                         if (kept) {
                             uint32_t d = (key[k] >> lv.shift) & cmask;
@@ -552,7 +554,7 @@ __global__ void __launch_bounds__(RT_NT, 3) k_lvl_partition_rt(const float4 *__r
                     bool kept = true;
                     if (FIRST) {
                         key[k] = cell_key_kept(q[k], g, kept);
-                        q[k].w = __int_as_float((int)(pos + i));          /* payload: original index */
+                        if (!g.indexed) q[k].w = __int_as_float((int)(pos + i));      /* payload: original index */
                     }
                     if (kept) {
                         uint32_t d = (key[k] >> lv.shift) & cmask;

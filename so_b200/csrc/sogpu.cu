@@ -85,6 +85,7 @@ struct GridDev {
     const uint32_t *ce;       /* ce[c] = first sorted slot of cell c, ce[ncell] = N          */
     int nc, lb;               /* cells per axis (power of two), log2                         */
     int tb;                   /* rows are ordered in tiles of 2^tb x 2^tb (iy, iz)           */
+    int indexed;              /* input .w already holds the particle's (global) index, not its mass */
     float g0[3], invh[3];     /* cell coordinate = floor((x - g0) * invh) & (nc-1)           */
     float L[3], halfL[3];
     double dg0[3], dinvh[3], dh[3];
@@ -1594,6 +1595,78 @@ __global__ void __launch_bounds__(256) k_vcirc(const __grid_constant__ VcircArgs
 }
 
 /* ============================================================================================
+ * domain runs (several GPUs): every rank holds a SLICE of the snapshot and a
+ * spatially compact share of the halos.  A rank's "focus mask" marks the coarse cells its halos can
+ * reach; a particle is routed to every rank whose mask holds its coarse cell (none: nobody needs it).
+ * k_route_count / k_route_scatter are the exchange step: the scatter writes {x, y, z, global index}
+ * records straight into the receivers' buffers (peer pointers over NVLink, or local staging
+ * buffers for an NCCL all-to-all), one warp-aggregated reservation per (warp, destination).
+ * ============================================================================================ */
+#define ROUTE_MAXR 16
+
+struct RouteArgs {
+    GridDev g;                              /* geometry + mb/ms of the masks (mask pointer unused) */
+    const float4 *slice;                    /* this rank's particles {x,y,z,m} */
+    int64_t n;
+    uint32_t index_base;                    /* global index of slice[0] */
+    const uint32_t *masks;                  /* R masks, mask_words each */
+    uint32_t mask_words;
+    int R;
+    unsigned long long *counts;             /* R counters (count pass) / running cursors (scatter pass) */
+    float4 *dst[ROUTE_MAXR];                /* receive buffers (scatter pass) */
+    unsigned long long dst_off[ROUTE_MAXR]; /* where this rank's records start in each */
+};
+
+__device__ __forceinline__ uint32_t coarse_bit(const float4 &p, const GridDev &g)
+{
+    const int mask = g.nc - 1;
+    uint32_t ix = cell_coord(p.x, g.g0[0], g.invh[0], mask) >> g.ms;
+    uint32_t iy = cell_coord(p.y, g.g0[1], g.invh[1], mask) >> g.ms;
+    uint32_t iz = cell_coord(p.z, g.g0[2], g.invh[2], mask) >> g.ms;
+    return (iz << (2 * g.mb)) | (iy << g.mb) | ix;
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_route(const __grid_constant__ RouteArgs a)
+{
+    __shared__ unsigned long long scount[ROUTE_MAXR];
+    if (threadIdx.x < ROUTE_MAXR) scount[threadIdx.x] = 0ull;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nround = (a.n + stride - 1) / stride;
+    for (int64_t it = 0; it < nround; ++it) {               /* whole warps stay together for the ballots */
+        const int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const bool in = i < a.n;
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t bit = 0;
+        if (in) {
+            q = ld_stream(a.slice + i);
+            bit = coarse_bit(q, a.g);
+            q.w = __uint_as_float(a.index_base + (uint32_t)i);
+        }
+        for (int d = 0; d < a.R; ++d) {
+            const bool want = in && ((__ldg(a.masks + (size_t)d * a.mask_words + (bit >> 5)) >> (bit & 31)) & 1u);
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
+            if (!m) continue;
+            if (!SCATTER) {
+                if (lane == 0) atomicAdd(&scount[d], (unsigned long long)__popc(m));
+            } else {
+                const int leader = __ffs(m) - 1;
+                unsigned long long base = 0ull;
+                if (lane == leader) base = atomicAdd(&a.counts[d], (unsigned long long)__popc(m));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (want) a.dst[d][a.dst_off[d] + base + (unsigned long long)__popc(m & ((1u << lane) - 1u))] = q;
+            }
+        }
+    }
+    if (!SCATTER) {
+        __syncthreads();
+        if (threadIdx.x < a.R && scount[threadIdx.x]) atomicAdd(&a.counts[threadIdx.x], scount[threadIdx.x]);
+    }
+}
+
+/* ============================================================================================
  * kdTagParticles, the part that needs no ordering (kd2.c:663-720): a group none of whose members
  * belongs to another group simply tags its members, whatever the processing order.  Pass 1 lets
  * every member claim its particle with a compare-and-swap; a failed claim marks both groups
@@ -1659,12 +1732,12 @@ __global__ void __launch_bounds__(256) k_member_unkeys(const unsigned long long 
 enum {
     KID_LVL_HIST = 0, KID_LVL_SCAN, KID_LVL_PARTITION, KID_BUCKET_SORT, KID_MASS_TABLE, KID_CLASSIFY,
     KID_QUERY_WARP, KID_QUERY_BLOCK, KID_OFFSETS, KID_EMIT_WARP, KID_EMIT_BLOCK, KID_BALL_GATHER,
-    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_VCIRC, KID_TAG, KID_N
+    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_VCIRC, KID_TAG, KID_ROUTE, KID_N
 };
 static const char *const g_kernel_names[KID_N] = {
     "k_lvl_hist", "k_scan", "k_lvl_partition", "k_bucket_sort", "k_mass_table", "k_classify",
     "k_so_query<32>", "k_so_query<256>", "k_offsets", "k_so_emit<32>", "k_so_emit<256>", "k_ball_gather",
-    "k_so_query<1024>", "k_so_emit<1024>", "k_mark_mask", "k_vcirc", "k_tag_claim+settle"};
+    "k_so_query<1024>", "k_so_emit<1024>", "k_mark_mask", "k_vcirc", "k_tag_claim+settle", "k_route"};
 
 struct ProfRec { int kid, launches; cudaEvent_t a, b; };
 
@@ -1702,6 +1775,9 @@ struct sogpu {
     size_t lvl_cap[4];
     float cls_small_max, cls_huge_min;   /* expected ball population: warp / 256-thread CTA / 1024-thread CTA */
     int emit_small_max, emit_huge_min;   /* same split for the member emission, by N_Delta */
+    bool indexed;                    /* d_in is {x,y,z,global index} of one rank's share (domain runs) */
+    float indexed_mass;
+    int64_t n_total;                 /* particles of the whole snapshot (grid resolution of a domain run) */
     int first_ball;                  /* first ball of the schedule that is gathered (1 = as the reference) */
     int two_level;                   /* -1 auto; 0: no partition levels (bucket sort only if it fits) */
     uint32_t *d_mask;                /* focused build: 2^(3*mb) bits */
@@ -1732,6 +1808,7 @@ struct sogpu {
     bool have_result;
     bool want_d2;
     bool member_overflow;
+    unsigned long long *d_route;     /* domain runs: per-destination counters */
     int32_t *d_tag, *d_tag_index;    /* sogpu_tag_members: owner per particle, catalog ids */
     unsigned char *d_dirty;
     int64_t tag_cap;
@@ -1918,6 +1995,7 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     for (int l = 0; l < 4; ++l) { cudaFree(h->d_lvl_start[l]); cudaFree(h->d_lvl_cursor[l]); }
     cudaFree(h->d_mt);
     cudaFree(h->d_vc);
+    cudaFree(h->d_route);
     cudaFree(h->d_tag); cudaFree(h->d_tag_index); cudaFree(h->d_dirty);
     cudaFree(h->d_counters);
     cudaFree(h->d_u64);
@@ -1981,6 +2059,8 @@ static int set_common(sogpu *h, int64_t n, const float period[3], const float ce
     h->built = false;
     h->have_result = false;
     h->mass_state = -1;
+    h->indexed = false;
+    h->n_total = n;
     return SOGPU_OK;
 }
 
@@ -2209,7 +2289,7 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
     if (!h || !h->d_in || h->n <= 0) return set_err(SOGPU_ERR_ARG, "sogpu_build_grid: no particles set");
     CU(cudaSetDevice(h->device));
     int lb;
-    const int nc = pick_cells(h->n, h->ppc, &lb);
+    const int nc = pick_cells(h->indexed ? h->n_total : h->n, h->ppc, &lb);   /* one resolution for every rank of a domain run */
     const int64_t ncell = (int64_t)nc * nc * nc;
     const int keybits = 3 * lb;
     /* final buckets: ~1024 particles on average and at most BKT_CELLS cells each */
@@ -2262,11 +2342,12 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
     }
     g.bmax_pruned = 0.5 * lmin - 2.0 * hmax;
     g.mask = nullptr; g.mb = 0; g.ms = 0;
+    g.indexed = h->indexed ? 1 : 0;
 
     cudaStream_t s = h->stream;
     const double N = (double)h->n;
     h->focused = false;
-    if (focus_nh > 0 && L > 0) {
+    if (focus_nh > 0) {   /* (L == 0, tiny inputs: nothing is filtered, but the mask still guards the balls) */
         const int mb = std::min(lb, 8);
         const size_t words = ((size_t)1 << (3 * mb)) / 32 + 1;
         if (!h->d_mask) CU(cudaMalloc(&h->d_mask, (((size_t)1 << 24) / 32 + 1) * sizeof(uint32_t)));
@@ -2284,8 +2365,14 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         h->focus_balls = focus_balls;
     }
     h->stats.last_kernel_launches = 0;
-    CU(cudaMemsetAsync(h->d_massmm, 0xFF, sizeof(uint32_t), s));
-    CU(cudaMemsetAsync(h->d_massmm + 1, 0, sizeof(uint32_t), s));
+    if (h->indexed) {                      /* the (single) particle mass came with sogpu_set_particles_device_indexed */
+        uint32_t mb32;
+        memcpy(&mb32, &h->indexed_mass, sizeof(mb32));
+        k_store_u32<<<1, 32, 0, s>>>(h->d_massmm, mb32, h->d_massmm + 1, mb32);
+    } else {
+        CU(cudaMemsetAsync(h->d_massmm, 0xFF, sizeof(uint32_t), s));
+        CU(cudaMemsetAsync(h->d_massmm + 1, 0, sizeof(uint32_t), s));
+    }
 
     /* digit widths: cbt split as evenly as possible over L levels, most significant first */
     int db[4] = {0, 0, 0, 0}, bits_done = 0;
@@ -2388,9 +2475,9 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         int grid = (int)std::min<int64_t>((int64_t)nb, (int64_t)h->sm_count * 16);
         ProfScope p(h, KID_BUCKET_SORT, 32.0 * N + 4.0 * (double)ncell);
         if (h->two_level == 2)
-            k_bucket_sort<<<grid, BKT_THREADS, bkt_smem, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, L == 0 ? 1 : 0);
+            k_bucket_sort<<<grid, BKT_THREADS, bkt_smem, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, (L == 0 && !g.indexed) ? 1 : 0);
         else
-            k_bucket_sort_rt<<<grid, BR_NT, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, L == 0 ? 1 : 0);
+            k_bucket_sort_rt<<<grid, BR_NT, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, (L == 0 && !g.indexed) ? 1 : 0);
     }
     if (h->focused) k_copy_u32<<<1, 32, 0, s>>>(h->d_ce + ncell, h->d_lvl_start[0] + ((size_t)1 << db[0]));
     else k_store_u32<<<1, 32, 0, s>>>(h->d_ce + ncell, (uint32_t)h->n, nullptr, 0u);
@@ -2841,6 +2928,9 @@ extern "C" int sogpu_so(sogpu_t *h, const float *centers, const float *rgtp, int
          * particles at one identical r^2): those halos go through the general full-sort path */
         int32_t n_bad = 0;
         for (int32_t i = 0; i < nh; ++i) n_bad += (pn[i] == CODE_UNSUPPORTED);
+        if (n_bad && h->indexed)
+            return set_err(SOGPU_ERR_UNSUPPORTED, "%d halo(s) need the general full-sort path, which reads particle masses "
+                                                  "by index and is not available on one rank's share of a domain run", n_bad);
         if (n_bad) {
             CU(cudaMemsetAsync(h->d_counters + 19, 0, sizeof(uint32_t), h->stream));
             k_select_code<<<(nh + 255) / 256, 256, 0, h->stream>>>(h->d_out_n, nh, CODE_UNSUPPORTED, h->d_defer,
@@ -3182,6 +3272,191 @@ extern "C" int sogpu_tag_members(sogpu_t *h, const int32_t *index, int32_t nh, u
     if (igrp) CU(cudaMemcpyAsync(igrp, h->d_tag, (size_t)h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     memcpy(in_conflict, pd, (size_t)nh);
+    return SOGPU_OK;
+}
+
+/* ---- domain runs: geometry, focus masks, routing (see k_route) ------------------------------------ */
+
+/* geometry of the cell grid and of the coarse mask for a snapshot of n_total particles */
+static void domain_geometry(sogpu *h, int64_t n_total, GridDev &g)
+{
+    int lb;
+    const int nc = pick_cells(n_total, h->ppc, &lb);
+    memset(&g, 0, sizeof(g));
+    g.nc = nc; g.lb = lb; g.tb = std::min(lb, 3);
+    double hmax = 0.0, lmin = 1e300;
+    for (int k = 0; k < 3; ++k) {
+        double Lk = (double)h->period[k];
+        g.L[k] = h->period[k];
+        g.halfL[k] = 0.5f * h->period[k];
+        g.g0[k] = (float)((double)h->center[k] - 0.5 * Lk);
+        g.dg0[k] = (double)g.g0[k];
+        g.dh[k] = Lk / nc;
+        g.invh[k] = (float)((double)nc / Lk);
+        g.dinvh[k] = (double)g.invh[k];
+        hmax = std::max(hmax, g.dh[k]);
+        lmin = std::min(lmin, Lk);
+    }
+    g.bmax_pruned = 0.5 * lmin - 2.0 * hmax;
+    g.mb = std::min(lb, 8); g.ms = lb - g.mb;
+}
+
+extern "C" int sogpu_domain_mask_words(sogpu_t *h, int64_t n_total, int64_t *words)
+{
+    if (!h || !words || n_total <= 0) return set_err(SOGPU_ERR_ARG, "sogpu_domain_mask_words: bad argument");
+    int lb;
+    pick_cells(n_total, h->ppc, &lb);
+    *words = (int64_t)(((size_t)1 << (3 * std::min(lb, 8))) / 32 + 1);
+    return SOGPU_OK;
+}
+
+/* the coarse cells the nh halos can reach within n_balls steps of the ball schedule -> d_mask (device) */
+extern "C" int sogpu_domain_mask(sogpu_t *h, int64_t n_total, const float period[3], const float center[3],
+                                 const float *centers, const float *rgtp, int32_t nh, int32_t n_balls, void *d_mask)
+{
+    if (!h || !period || !d_mask || nh < 0 || n_balls < 1 || n_total <= 0 || (nh > 0 && (!centers || !rgtp)))
+        return set_err(SOGPU_ERR_ARG, "sogpu_domain_mask: bad argument");
+    CU(cudaSetDevice(h->device));
+    for (int k = 0; k < 3; ++k) { h->period[k] = period[k]; h->center[k] = center ? center[k] : 0.0f; }
+    GridDev g;
+    domain_geometry(h, n_total, g);
+    int64_t words;
+    sogpu_domain_mask_words(h, n_total, &words);
+    cudaStream_t s = h->stream;
+    CU(cudaMemsetAsync(d_mask, 0, (size_t)words * sizeof(uint32_t), s));
+    if (nh == 0) return SOGPU_OK;
+    int rc = ensure_query(h, nh);
+    if (rc) return rc;
+    rc = ensure_pinned(h, (size_t)nh * 4 * sizeof(float));
+    if (rc) return rc;
+    float *pc = (float *)h->h_pin, *pr = pc + (size_t)3 * nh;
+    memcpy(pc, centers, (size_t)nh * 3 * sizeof(float));
+    memcpy(pr, rgtp, (size_t)nh * sizeof(float));
+    CU(cudaMemcpyAsync(h->d_centers, pc, (size_t)nh * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(h->d_rgtp, pr, (size_t)nh * sizeof(float), cudaMemcpyHostToDevice, s));
+    g.mask = (const uint32_t *)d_mask;
+    { ProfScope p(h, KID_MARK_MASK);
+      k_mark_mask<<<std::min((nh + 7) / 8, h->sm_count * 8), 256, 0, s>>>(g, h->d_centers, h->d_rgtp, nh, n_balls, (uint32_t *)d_mask); }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));            /* the pinned staging is reused by the next call */
+    return SOGPU_OK;
+}
+
+static int route_args(sogpu *h, RouteArgs &a, int64_t n_total, const void *d_slice, int64_t n_slice, int64_t index_base,
+                      const void *d_masks, int32_t n_ranks)
+{
+    if (!h || !d_slice || !d_masks || n_slice < 0 || n_ranks < 1 || n_ranks > ROUTE_MAXR || index_base < 0 ||
+        index_base + n_slice > 0x7FFFFFF0LL)
+        return set_err(SOGPU_ERR_ARG, "sogpu_domain_route: bad argument (at most %d ranks)", ROUTE_MAXR);
+    memset(&a, 0, sizeof(a));
+    domain_geometry(h, n_total, a.g);
+    int64_t words;
+    sogpu_domain_mask_words(h, n_total, &words);
+    a.slice = (const float4 *)d_slice; a.n = n_slice; a.index_base = (uint32_t)index_base;
+    a.masks = (const uint32_t *)d_masks; a.mask_words = (uint32_t)words; a.R = n_ranks;
+    if (!h->d_route) CU(cudaMalloc(&h->d_route, ROUTE_MAXR * sizeof(unsigned long long)));
+    a.counts = h->d_route;
+    return SOGPU_OK;
+}
+
+/* how many of this rank's particles each rank needs: counts[n_ranks] (host) */
+extern "C" int sogpu_domain_route_count(sogpu_t *h, int64_t n_total, const void *d_slice, int64_t n_slice,
+                                        const void *d_masks, int32_t n_ranks, int64_t *counts)
+{
+    if (!counts) return set_err(SOGPU_ERR_ARG, "sogpu_domain_route_count: NULL counts");
+    RouteArgs a;
+    int rc = route_args(h, a, n_total, d_slice, n_slice, 0, d_masks, n_ranks);
+    if (rc) return rc;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    CU(cudaMemsetAsync(h->d_route, 0, ROUTE_MAXR * sizeof(unsigned long long), s));
+    if (n_slice > 0) {
+        ProfScope p(h, KID_ROUTE, 16.0 * (double)n_slice);
+        k_route<false><<<(int)std::min<int64_t>((n_slice + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, s>>>(a);
+    }
+    CU(cudaGetLastError());
+    unsigned long long c[ROUTE_MAXR];
+    CU(cudaMemcpyAsync(c, h->d_route, sizeof(c), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (int d = 0; d < n_ranks; ++d) counts[d] = (int64_t)c[d];
+    return SOGPU_OK;
+}
+
+/* write this rank's particles into the receive buffers: dst[d] (device pointers, possibly peer memory
+ * opened with sogpu_peer_open), starting at record dst_offset[d].  Asynchronous on the handle's stream. */
+extern "C" int sogpu_domain_route_scatter(sogpu_t *h, int64_t n_total, const void *d_slice, int64_t n_slice,
+                                          int64_t index_base, const void *d_masks, int32_t n_ranks,
+                                          void *const *dst, const int64_t *dst_offset)
+{
+    if (!dst || !dst_offset) return set_err(SOGPU_ERR_ARG, "sogpu_domain_route_scatter: NULL destination");
+    RouteArgs a;
+    int rc = route_args(h, a, n_total, d_slice, n_slice, index_base, d_masks, n_ranks);
+    if (rc) return rc;
+    for (int d = 0; d < n_ranks; ++d) { a.dst[d] = (float4 *)dst[d]; a.dst_off[d] = (unsigned long long)dst_offset[d]; }
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    CU(cudaMemsetAsync(h->d_route, 0, ROUTE_MAXR * sizeof(unsigned long long), s));
+    if (n_slice > 0) {
+        ProfScope p(h, KID_ROUTE, 16.0 * (double)n_slice);
+        k_route<true><<<(int)std::min<int64_t>((n_slice + 255) / 256, (int64_t)h->sm_count * 8), 256, 0, s>>>(a);
+    }
+    CU(cudaGetLastError());
+    return SOGPU_OK;
+}
+
+/* one rank's share of a domain run: {x, y, z, global index} records (what sogpu_domain_route_scatter
+ * writes), all of mass `mass`; n_total fixes the grid resolution so that every rank uses the same cells */
+extern "C" int sogpu_set_particles_device_indexed(sogpu_t *h, const void *d_xyzi, int64_t n_local, int64_t n_total,
+                                                  float mass, const float period[3], const float center[3])
+{
+    if (!h || !d_xyzi || !period || n_total < n_local || !(mass > 0.0f))
+        return set_err(SOGPU_ERR_ARG, "sogpu_set_particles_device_indexed: bad argument");
+    int rc = set_common(h, n_local, period, center);
+    if (rc) return rc;
+    h->d_in = (const float4 *)d_xyzi;
+    h->indexed = true;
+    h->indexed_mass = mass;
+    h->n_total = n_total;
+    return SOGPU_OK;
+}
+
+/* device memory another process of the same node can map (cudaIpc): the receive buffers of the exchange */
+extern "C" int sogpu_peer_alloc(sogpu_t *h, size_t bytes, void **ptr, void *handle64)
+{
+    if (!h || !ptr || !handle64) return set_err(SOGPU_ERR_ARG, "sogpu_peer_alloc: NULL argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMalloc(ptr, bytes ? bytes : 256));
+    cudaIpcMemHandle_t ih;
+    cudaError_t e = cudaIpcGetMemHandle(&ih, *ptr);
+    if (e != cudaSuccess) { cudaFree(*ptr); *ptr = nullptr; return set_err(SOGPU_ERR_CUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); }
+    static_assert(sizeof(ih) == 64, "ipc handle size");
+    memcpy(handle64, &ih, 64);
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_peer_open(sogpu_t *h, const void *handle64, void **ptr)
+{
+    if (!h || !ptr || !handle64) return set_err(SOGPU_ERR_ARG, "sogpu_peer_open: NULL argument");
+    CU(cudaSetDevice(h->device));
+    cudaIpcMemHandle_t ih;
+    memcpy(&ih, handle64, 64);
+    CU(cudaIpcOpenMemHandle(ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_peer_close(sogpu_t *h, void *ptr)
+{
+    if (!h || !ptr) return set_err(SOGPU_ERR_ARG, "sogpu_peer_close: NULL argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaIpcCloseMemHandle(ptr));
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_peer_free(sogpu_t *h, void *ptr)
+{
+    if (!h) return set_err(SOGPU_ERR_ARG, "NULL handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaFree(ptr));
     return SOGPU_OK;
 }
 

@@ -112,3 +112,128 @@ def distributed_so(compute, centers, rgtp, n_particles, volume, group=None, devi
     merged["rank_of"] = rank_of
     merged["load"] = load
     return merged
+
+
+# ---------------------------------------------------------------------------------------------
+# domain runs: every rank holds a slice of the snapshot and a compact share of the halos
+# ---------------------------------------------------------------------------------------------
+
+def spatial_assign(centers, cost, n_ranks, period=1.0, cells=64):
+    """Spatially compact, cost-balanced halo shares: halos are ordered along a tiled (8x8x8 blocks of
+    coarse cells, blocks row-major) curve through the box and cut into n_ranks consecutive pieces of
+    equal estimated cost.  Compact shares keep the focus masks of the ranks nearly disjoint, so that
+    few particles are sent to more than one rank.  Returns rank[h] and the load per rank."""
+    centers = np.asarray(centers, np.float64).reshape(-1, 3)
+    cost = np.asarray(cost, np.float64)
+    h = len(cost)
+    rank = np.zeros(h, np.int32)
+    load = np.zeros(n_ranks, np.float64)
+    if h == 0 or n_ranks <= 1:
+        load[0] = cost.sum()
+        return rank, load
+    c = np.floor(((centers / period) % 1.0) * cells).astype(np.int64) % cells
+    hi, lo = c >> 3, c & 7
+    nb = max(cells >> 3, 1)
+    key = (((hi[:, 2] * nb + hi[:, 1]) * nb + hi[:, 0]) << 9) | (lo[:, 2] << 6) | (lo[:, 1] << 3) | lo[:, 0]
+    order = np.lexsort((np.arange(h), key))
+    csum = np.cumsum(cost[order])
+    total = csum[-1]
+    # halo k goes to the piece that holds the midpoint of its cost interval
+    mid = csum - 0.5 * cost[order]
+    r = np.minimum((mid / total * n_ranks).astype(np.int64), n_ranks - 1)
+    rank[order] = r.astype(np.int32)
+    np.add.at(load, rank, cost)
+    return rank, load
+
+
+def slice_bounds(n, n_ranks):
+    """[start, end) of every rank's slice of the particle array."""
+    b = [(n * r) // n_ranks for r in range(n_ranks + 1)]
+    return [(b[r], b[r + 1]) for r in range(n_ranks)]
+
+
+def exchange_plan(count_matrix):
+    """count_matrix[src][dst] = particles src sends to dst.  Returns (recv_total[dst],
+    recv_offset[src][dst] = where src's records start in dst's receive buffer)."""
+    cm = np.asarray(count_matrix, np.int64)
+    off = np.zeros_like(cm)
+    off[1:, :] = np.cumsum(cm, axis=0)[:-1, :]
+    return cm.sum(axis=0), off
+
+
+class VirtualDomainRun:
+    """The domain run with all `n_ranks` ranks living in THIS process on one device (tests, and the
+    reference implementation of the protocol): slices, masks, routing, per-rank builds and solves,
+    results merged in catalog order.  `DomainRun` below is the same protocol over torch.distributed."""
+
+    def __init__(self, n_ranks, n_balls=4):
+        self.R = int(n_ranks)
+        self.n_balls = int(n_balls)
+
+    def run(self, pos, mass, centers, rgtp, thr, n_members=8, period=(1.0, 1.0, 1.0)):
+        import torch
+        from so_b200 import api
+        R = self.R
+        n = len(pos)
+        dev = torch.device("cuda")
+        xyzm = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        xyzm[:, :3] = torch.from_numpy(np.ascontiguousarray(pos, np.float32)).to(dev)
+        xyzm[:, 3] = float(mass)
+        rank_of, _ = spatial_assign(centers, halo_cost(rgtp, n, float(np.prod(period))), R, period[0])
+        gs = [api.SoGpu() for _ in range(R)]
+        words = gs[0].domain_mask_words(n)
+        out = {"rvir": np.zeros(len(rgtp), np.float32), "mvir": np.zeros(len(rgtp), np.float32),
+               "ndelta": np.zeros(len(rgtp), np.int32), "members": [None] * len(rgtp), "sent": 0, "rounds": 0}
+        todo = [shard_indices(rank_of, r) for r in range(R)]
+        n_balls = self.n_balls
+        while any(len(t) for t in todo):
+            out["rounds"] += 1
+            masks = torch.zeros((R, words), dtype=torch.int32, device=dev)
+            for r in range(R):
+                gs[r].domain_mask(n, centers[todo[r]], rgtp[todo[r]], n_balls, masks[r].data_ptr(), period)
+            torch.cuda.synchronize()
+            bounds = slice_bounds(n, R)
+            cm = np.zeros((R, R), np.int64)
+            for s in range(R):
+                a, b = bounds[s]
+                cm[s] = gs[s].domain_route_count(n, xyzm[a:].data_ptr(), b - a, masks.data_ptr(), R)
+            recv_total, recv_off = exchange_plan(cm)
+            recv = [torch.empty((max(int(t), 1), 4), dtype=torch.float32, device=dev) for t in recv_total]
+            for s in range(R):
+                a, b = bounds[s]
+                gs[s].domain_route_scatter(n, xyzm[a:].data_ptr(), b - a, a, masks.data_ptr(),
+                                           [t.data_ptr() for t in recv], recv_off[s])
+            torch.cuda.synchronize()
+            out["sent"] += int(recv_total.sum())
+            nxt = [np.zeros(0, np.int64)] * R
+            for r in range(R):
+                mine = todo[r]
+                if not len(mine):
+                    continue
+                g = gs[r]
+                if recv_total[r] == 0:                       # nothing within reach: -1 for every halo (kd2.c:772-778)
+                    out["rvir"][mine] = -1.0
+                    out["mvir"][mine] = -1.0
+                    continue
+                g.set_particles_device_indexed(recv[r].data_ptr(), int(recv_total[r]), n, mass, period)
+                g.build_grid_for(centers[mine], rgtp[mine], n_balls)
+                d_c = torch.from_numpy(np.ascontiguousarray(centers[mine])).to(dev)
+                d_r = torch.from_numpy(np.ascontiguousarray(rgtp[mine])).to(dev)
+                d_n = torch.empty(len(mine), dtype=torch.int32, device=dev)
+                d_m = torch.empty(len(mine), dtype=torch.float32, device=dev)
+                g.so_device(d_c.data_ptr(), d_r.data_ptr(), len(mine), thr, n_members, d_n.data_ptr(), d_m.data_ptr())
+                torch.cuda.synchronize()
+                code = d_n.cpu().numpy()
+                done = code != -103
+                fin = g.finish_host(np.where(done, code, -1).astype(np.int32), d_m.cpu().numpy(), thr)
+                off, mem = g.members(copy=True)
+                for k in np.nonzero(done)[0]:
+                    i = mine[k]
+                    out["rvir"][i], out["mvir"][i], out["ndelta"][i] = fin["rvir"][k], fin["mvir"][k], fin["ndelta"][k]
+                    out["members"][i] = mem[off[k]:off[k + 1]].copy()
+                nxt[r] = mine[~done]                          # balls that left the mask: again, further out
+            todo = nxt
+            n_balls += 4
+        for g in gs:
+            g.close()
+        return out

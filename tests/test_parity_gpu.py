@@ -482,3 +482,26 @@ def test_config1_full_size_properties():
     assert r["rvir"][pick].tobytes() == ref["rvir"].tobytes()
     for n, i in enumerate(pick):
         assert np.array_equal(mem[off[i]:off[i + 1]], ref["members"][ref["member_offset"][n]:ref["member_offset"][n + 1]])
+
+
+@pytest.mark.parametrize("n_ranks,n_balls", [(1, 4), (2, 1), (4, 2), (8, 4)])
+def test_domain_run_matches_single_grid(n_ranks, n_balls):
+    """Domain run (SURVEY 8e): slices of the snapshot, focus masks, routing of {x,y,z,global index}
+    records, one grid per rank over what it received — all ranks simulated on this one device.  Results
+    (incl. -1/-2/-3 codes, halos on the periodic boundary, halos whose balls outgrow the first masks and
+    are re-run with larger ones) are those of the single full grid, member indices global."""
+    from so_b200 import parallel
+    s = synth.make_snapshot(64 ** 3, 150, seed=81, nmax=6000)
+    rng = np.random.default_rng(11)
+    vc = (rng.random((10, 3)) - 0.5).astype(np.float32)
+    centers = np.concatenate([s.centers, vc, np.array([[0.4999, 0.4999, -0.4999]], np.float32)])
+    rgtp = np.concatenate([s.rgtp, np.full(5, 0.004, np.float32), np.full(5, 0.03, np.float32), [np.float32(0.01)]])
+    ref = run_gpu(s.pos, s.mass, centers, rgtp, 200.0)
+    out = parallel.VirtualDomainRun(n_ranks, n_balls).run(s.pos, s.mass, centers, rgtp, np.float32(200.0))
+    assert_so_equal(out, ref["rvir"], ref["mvir"], ref["ndelta"])
+    for i in range(len(rgtp)):
+        a = ref["members"][ref["member_offset"][i]:ref["member_offset"][i + 1]]
+        b = out["members"][i] if out["members"][i] is not None else np.zeros(0, np.int32)
+        assert np.array_equal(np.sort(a), np.sort(b)), i
+    if n_ranks > 1:
+        assert out["sent"] < n_ranks * s.n        # far from "everything to everyone"
