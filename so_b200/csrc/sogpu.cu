@@ -1609,8 +1609,8 @@ struct RouteArgs {
     const float4 *slice;                    /* this rank's particles {x,y,z,m} */
     int64_t n;
     uint32_t index_base;                    /* global index of slice[0] */
-    const uint32_t *masks;                  /* R masks, mask_words each */
-    uint32_t mask_words;
+    const unsigned short *table;            /* set of destination ranks per coarse cell (k_route_table) */
+    const uint32_t *any;                    /* bit per coarse cell: some rank wants it */
     int R;
     unsigned long long *counts;             /* R counters (count pass) / running cursors (scatter pass) */
     float4 *dst[ROUTE_MAXR];                /* receive buffers (scatter pass) */
@@ -1626,38 +1626,96 @@ __device__ __forceinline__ uint32_t coarse_bit(const float4 &p, const GridDev &g
     return (iz << (2 * g.mb)) | (iy << g.mb) | ix;
 }
 
+/* masks of all ranks -> one 16-bit set of destination ranks per coarse cell (one lookup per particle) */
+__global__ void __launch_bounds__(256) k_route_table(const uint32_t *__restrict__ masks, uint32_t mask_words, int R,
+                                                     uint32_t n_cells, unsigned short *__restrict__ table,
+                                                     uint32_t *__restrict__ any)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;          /* one 32-cell word per thread */
+    if (w >= mask_words) return;
+    uint32_t m[ROUTE_MAXR], u = 0u;
+    for (int d = 0; d < R; ++d) { m[d] = __ldg(masks + (size_t)d * mask_words + w); u |= m[d]; }
+    any[w] = u;                        /* union of the masks: 2 MB, stays in L1/L2; most particles stop here */
+    if (!u) return;
+    for (int b = 0; b < 32; ++b) {
+        const uint32_t cell = w * 32u + (uint32_t)b;
+        if (cell >= n_cells) break;
+        uint32_t set = 0;
+        for (int d = 0; d < R; ++d) set |= ((m[d] >> b) & 1u) << d;
+        table[cell] = (unsigned short)set;
+    }
+}
+
+#define ROUTE_U 4       /* particles per thread per round: independent loads in flight */
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_route(const __grid_constant__ RouteArgs a)
 {
-    __shared__ unsigned long long scount[ROUTE_MAXR];
+    __shared__ unsigned long long scount[ROUTE_MAXR];          /* count pass: CTA totals             */
+    __shared__ uint32_t wcnt[8][ROUTE_MAXR];                   /* scatter pass: records per (warp, destination) of a round */
+    __shared__ unsigned long long wbase[8][ROUTE_MAXR];        /* ... and where each warp's run starts */
     if (threadIdx.x < ROUTE_MAXR) scount[threadIdx.x] = 0ull;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t nround = (a.n + stride - 1) / stride;
-    for (int64_t it = 0; it < nround; ++it) {               /* whole warps stay together for the ballots */
-        const int64_t i = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        const bool in = i < a.n;
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t bit = 0;
-        if (in) {
-            q = ld_stream(a.slice + i);
-            bit = coarse_bit(q, a.g);
-            q.w = __uint_as_float(a.index_base + (uint32_t)i);
+    const int64_t nround = (a.n + stride * ROUTE_U - 1) / (stride * ROUTE_U);
+    for (int64_t it = 0; it < nround; ++it) {               /* every thread runs every round (ballots, barriers) */
+        const int64_t i0 = it * stride * ROUTE_U + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        float4 q[ROUTE_U];
+        uint32_t set[ROUTE_U];
+#pragma unroll
+        for (int u = 0; u < ROUTE_U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < a.n) q[u] = ld_stream(a.slice + i);
         }
-        for (int d = 0; d < a.R; ++d) {
-            const bool want = in && ((__ldg(a.masks + (size_t)d * a.mask_words + (bit >> 5)) >> (bit & 31)) & 1u);
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
-            if (!m) continue;
-            if (!SCATTER) {
-                if (lane == 0) atomicAdd(&scount[d], (unsigned long long)__popc(m));
-            } else {
-                const int leader = __ffs(m) - 1;
-                unsigned long long base = 0ull;
-                if (lane == leader) base = atomicAdd(&a.counts[d], (unsigned long long)__popc(m));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (want) a.dst[d][a.dst_off[d] + base + (unsigned long long)__popc(m & ((1u << lane) - 1u))] = q;
+#pragma unroll
+        for (int u = 0; u < ROUTE_U; ++u) {
+            const int64_t i = i0 + u * stride;
+            set[u] = 0u;
+            if (i < a.n) {
+                const uint32_t bit = coarse_bit(q[u], a.g);
+                if ((__ldg(a.any + (bit >> 5)) >> (bit & 31)) & 1u) set[u] = __ldg(a.table + bit);
+                q[u].w = __uint_as_float(a.index_base + (uint32_t)i);
             }
+        }
+        if (!SCATTER) {
+            for (int d = 0; d < a.R; ++d) {
+                uint32_t c = 0;
+#pragma unroll
+                for (int u = 0; u < ROUTE_U; ++u) c += __popc(__ballot_sync(0xFFFFFFFFu, (set[u] >> d) & 1u));
+                if (lane == 0 && c) atomicAdd(&scount[d], (unsigned long long)c);
+            }
+        } else {
+            /* one reservation per (CTA, round, destination): the warps' runs follow each other, inside a warp
+             * the records are ordered by (u, lane) — runs of up to 128 contiguous records per warp */
+            for (int d = 0; d < a.R; ++d) {
+                uint32_t c = 0;
+#pragma unroll
+                for (int u = 0; u < ROUTE_U; ++u) c += __popc(__ballot_sync(0xFFFFFFFFu, (set[u] >> d) & 1u));
+                if (lane == 0) wcnt[w][d] = c;
+            }
+            __syncthreads();
+            if (threadIdx.x < a.R) {
+                const int d = threadIdx.x;
+                uint32_t tot = 0;
+                for (int k = 0; k < 8; ++k) tot += wcnt[k][d];
+                unsigned long long base = tot ? atomicAdd(&a.counts[d], (unsigned long long)tot) : 0ull;
+                base += a.dst_off[d];
+                for (int k = 0; k < 8; ++k) { wbase[k][d] = base; base += wcnt[k][d]; }
+            }
+            __syncthreads();
+            for (int d = 0; d < a.R; ++d) {
+                if (!wcnt[w][d]) continue;
+                unsigned long long pos = wbase[w][d];
+#pragma unroll
+                for (int u = 0; u < ROUTE_U; ++u) {
+                    const bool want = (set[u] >> d) & 1u;
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
+                    if (want) a.dst[d][pos + (unsigned long long)__popc(m & lt)] = q[u];
+                    pos += (unsigned long long)__popc(m);
+                }
+            }
+            __syncthreads();                                /* wcnt / wbase are reused by the next round */
         }
     }
     if (!SCATTER) {
@@ -1809,6 +1867,8 @@ struct sogpu {
     bool want_d2;
     bool member_overflow;
     unsigned long long *d_route;     /* domain runs: per-destination counters */
+    unsigned short *d_route_table;   /* destination ranks per coarse cell */
+    uint32_t *d_route_any;
     int32_t *d_tag, *d_tag_index;    /* sogpu_tag_members: owner per particle, catalog ids */
     unsigned char *d_dirty;
     int64_t tag_cap;
@@ -1995,7 +2055,7 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     for (int l = 0; l < 4; ++l) { cudaFree(h->d_lvl_start[l]); cudaFree(h->d_lvl_cursor[l]); }
     cudaFree(h->d_mt);
     cudaFree(h->d_vc);
-    cudaFree(h->d_route);
+    cudaFree(h->d_route); cudaFree(h->d_route_table); cudaFree(h->d_route_any);
     cudaFree(h->d_tag); cudaFree(h->d_tag_index); cudaFree(h->d_dirty);
     cudaFree(h->d_counters);
     cudaFree(h->d_u64);
@@ -3343,7 +3403,7 @@ extern "C" int sogpu_domain_mask(sogpu_t *h, int64_t n_total, const float period
 }
 
 static int route_args(sogpu *h, RouteArgs &a, int64_t n_total, const void *d_slice, int64_t n_slice, int64_t index_base,
-                      const void *d_masks, int32_t n_ranks)
+                      const void *d_masks, int32_t n_ranks, bool build_table)
 {
     if (!h || !d_slice || !d_masks || n_slice < 0 || n_ranks < 1 || n_ranks > ROUTE_MAXR || index_base < 0 ||
         index_base + n_slice > 0x7FFFFFF0LL)
@@ -3353,7 +3413,17 @@ static int route_args(sogpu *h, RouteArgs &a, int64_t n_total, const void *d_sli
     int64_t words;
     sogpu_domain_mask_words(h, n_total, &words);
     a.slice = (const float4 *)d_slice; a.n = n_slice; a.index_base = (uint32_t)index_base;
-    a.masks = (const uint32_t *)d_masks; a.mask_words = (uint32_t)words; a.R = n_ranks;
+    a.R = n_ranks;
+    const uint32_t n_cells = 1u << (3 * a.g.mb);
+    if (!h->d_route_table) {
+        CU(cudaMalloc(&h->d_route_table, ((size_t)1 << 24) * sizeof(unsigned short)));
+        CU(cudaMalloc(&h->d_route_any, (((size_t)1 << 24) / 32 + 1) * sizeof(uint32_t)));
+    }
+    if (build_table)
+        k_route_table<<<(unsigned)((words + 255) / 256), 256, 0, h->stream>>>((const uint32_t *)d_masks, (uint32_t)words, n_ranks,
+                                                                            n_cells, h->d_route_table, h->d_route_any);
+    a.table = h->d_route_table;
+    a.any = h->d_route_any;
     if (!h->d_route) CU(cudaMalloc(&h->d_route, ROUTE_MAXR * sizeof(unsigned long long)));
     a.counts = h->d_route;
     return SOGPU_OK;
@@ -3365,7 +3435,7 @@ extern "C" int sogpu_domain_route_count(sogpu_t *h, int64_t n_total, const void 
 {
     if (!counts) return set_err(SOGPU_ERR_ARG, "sogpu_domain_route_count: NULL counts");
     RouteArgs a;
-    int rc = route_args(h, a, n_total, d_slice, n_slice, 0, d_masks, n_ranks);
+    int rc = route_args(h, a, n_total, d_slice, n_slice, 0, d_masks, n_ranks, true);
     if (rc) return rc;
     CU(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
@@ -3390,7 +3460,7 @@ extern "C" int sogpu_domain_route_scatter(sogpu_t *h, int64_t n_total, const voi
 {
     if (!dst || !dst_offset) return set_err(SOGPU_ERR_ARG, "sogpu_domain_route_scatter: NULL destination");
     RouteArgs a;
-    int rc = route_args(h, a, n_total, d_slice, n_slice, index_base, d_masks, n_ranks);
+    int rc = route_args(h, a, n_total, d_slice, n_slice, index_base, d_masks, n_ranks, true);
     if (rc) return rc;
     for (int d = 0; d < n_ranks; ++d) { a.dst[d] = (float4 *)dst[d]; a.dst_off[d] = (unsigned long long)dst_offset[d]; }
     CU(cudaSetDevice(h->device));

@@ -237,3 +237,142 @@ class VirtualDomainRun:
         for g in gs:
             g.close()
         return out
+
+
+class DomainRun:
+    """One rank of a domain run over torch.distributed (one process per GPU, NCCL).
+
+    Every rank holds the slice [a, b) of the particle array (device, float4 {x,y,z,m}) and the full halo
+    catalog.  step(): masks of all ranks (all_gather, a few MB) -> per-destination counts of my slice
+    -> count matrix (all_gather, R ints) -> scatter of {x,y,z,global index} records
+        transport "p2p":  straight into the receivers' buffers, mapped once with cudaIpc: the routing
+                          kernel's stores travel over NVLink, no staging copy, no collective for the data;
+        transport "nccl": into a local staging buffer, then all_to_all_single
+    -> barrier -> grid over what arrived (same cell size on every rank) -> SO solve of my halos.
+    Halos whose balls leave the mask (code -103) are re-run with more schedule balls in the mask."""
+
+    def __init__(self, gpu, n_total, mass, period=(1.0, 1.0, 1.0), transport="p2p", n_balls=4, group=None):
+        import torch
+        import torch.distributed as dist
+        self.g, self.n_total, self.mass, self.period = gpu, int(n_total), float(mass), tuple(period)
+        self.transport, self.n_balls, self.group = transport, int(n_balls), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.words = gpu.domain_mask_words(n_total)
+        self.masks = torch.zeros((self.world, self.words), dtype=torch.int32, device=self.dev)
+        self.my_mask = torch.zeros(self.words, dtype=torch.int32, device=self.dev)
+        self.recv_cap = 0
+        self.recv_ptr = 0                 # my receive buffer (peer-shareable allocation)
+        self.peer_ptrs = []               # everyone's receive buffer as seen from this process
+        self.send = None
+        self.stats = {}
+
+    # -- receive buffers: allocated through the library so that other processes can map them ---------
+    def _ensure_recv(self, need):
+        import torch
+        import torch.distributed as dist
+        # `need` is the largest receive count over ALL ranks (every rank knows the whole count matrix),
+        # so every rank takes the same decision here without talking to the others
+        if need <= self.recv_cap:
+            return
+        self.close_buffers()
+        cap = int(need * 1.1) + 1024
+        self.recv_ptr, handle = self.g.peer_alloc(cap * 16)
+        self.recv_cap = cap
+        if self.transport == "p2p" and self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle, group=self.group)
+            self.peer_ptrs = [self.recv_ptr if r == self.rank else self.g.peer_open(handles[r]) for r in range(self.world)]
+        else:
+            self.peer_ptrs = [self.recv_ptr]
+
+    def close_buffers(self):
+        import torch
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+        for r, p in enumerate(self.peer_ptrs):
+            if r != self.rank and self.transport == "p2p" and self.world > 1:
+                self.g.peer_close(p)
+        self.peer_ptrs = []
+        if self.recv_ptr:
+            self.g.peer_free(self.recv_ptr)
+        self.recv_ptr, self.recv_cap = 0, 0
+
+    def exchange(self, d_slice, n_slice, index_base, centers_mine, rgtp_mine, n_balls):
+        """Masks -> counts -> records in place.  Returns the number of records this rank received."""
+        import torch
+        import torch.distributed as dist
+        g, R, me = self.g, self.world, self.rank
+        g.domain_mask(self.n_total, centers_mine, rgtp_mine, n_balls, self.my_mask.data_ptr(), self.period)
+        if R > 1:
+            dist.all_gather_into_tensor(self.masks.view(-1), self.my_mask, group=self.group)
+        else:
+            self.masks[0].copy_(self.my_mask)
+        torch.cuda.current_stream().synchronize()
+        counts = g.domain_route_count(self.n_total, d_slice, n_slice, self.masks.data_ptr(), R)
+        cm = torch.zeros((R, R), dtype=torch.int64, device=self.dev)
+        mine = torch.from_numpy(counts).to(self.dev)
+        if R > 1:
+            dist.all_gather_into_tensor(cm.view(-1), mine, group=self.group)
+        else:
+            cm[0] = mine
+        cm = cm.cpu().numpy()
+        recv_total, recv_off = exchange_plan(cm)
+        self._ensure_recv(int(recv_total.max()))
+        if self.transport == "p2p" or R == 1:
+            g.domain_route_scatter(self.n_total, d_slice, n_slice, index_base, self.masks.data_ptr(),
+                                   self.peer_ptrs if R > 1 else [self.recv_ptr], recv_off[me])
+            torch.cuda.current_stream().synchronize()       # my stores are out
+            if R > 1:
+                dist.barrier(group=self.group)              # ... and so are everybody else's
+        else:
+            tot = int(cm[me].sum())
+            if self.send is None or self.send.shape[0] < tot:
+                self.send = torch.empty((int(tot * 1.1) + 1024, 4), dtype=torch.float32, device=self.dev)
+            seg = np.concatenate([[0], np.cumsum(cm[me])[:-1]])
+            g.domain_route_scatter(self.n_total, d_slice, n_slice, index_base, self.masks.data_ptr(),
+                                   [self.send.data_ptr()] * R, seg)
+            torch.cuda.current_stream().synchronize()
+            recv = _as_tensor(self.recv_ptr, int(recv_total[me]), self.dev)
+            dist.all_to_all_single(recv, self.send[:tot], output_split_sizes=[int(x) for x in cm[:, me]],
+                                   input_split_sizes=[int(x) for x in cm[me]], group=self.group)
+            torch.cuda.current_stream().synchronize()
+        self.stats = {"sent": int(cm[me].sum()), "received": int(recv_total[me]), "count_matrix": cm}
+        return int(recv_total[me])
+
+    def solve(self, n_recv, d_centers, d_rgtp, nh, thr, n_members, n_balls, d_out_n, d_out_m):
+        """Grid over the received records + SO solve of my halos (asynchronous)."""
+        g = self.g
+        if nh == 0:
+            return
+        if n_recv == 0:
+            import torch
+            _as_tensor_i32(d_out_n, nh, self.dev).fill_(-1)
+            return
+        g.set_particles_device_indexed(self.recv_ptr, n_recv, self.n_total, self.mass, self.period)
+        g.build_grid_for_device(d_centers, d_rgtp, nh, n_balls)
+        g.so_device(d_centers, d_rgtp, nh, thr, n_members, d_out_n, d_out_m)
+
+
+def _as_tensor(ptr, n_records, dev):
+    """A torch view of `n_records` 16-byte records at a raw device pointer (no ownership)."""
+    import torch
+
+    class _Arr:
+        pass
+    a = _Arr()
+    a.__cuda_array_interface__ = {"shape": (max(n_records, 1), 4), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(a, device=dev)[:n_records]
+
+
+def _as_tensor_i32(ptr, n, dev):
+    import torch
+
+    class _Arr:
+        pass
+    a = _Arr()
+    a.__cuda_array_interface__ = {"shape": (max(n, 1),), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(a, device=dev)[:n]
