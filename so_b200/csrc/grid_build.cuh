@@ -648,6 +648,18 @@ __global__ void __launch_bounds__(BR_NT, 4) k_bucket_sort_rt(const float4 *__res
         }
         uint32_t *ceb = ce + ((size_t)b << cell_bits);
         if (nb == 0) {                   /* empty bucket (focused builds): only its cell-table slice */
+            if (g.mask) {
+                /* ... and not even that when none of its cells lies in a coarse cell of the focus mask:
+                 * the queries check every ball against the mask, so they read cell-table entries of
+                 * marked cells and the entry right behind one, which is either in a bucket with a marked
+                 * cell (written in full) or the FIRST entry of the next bucket (written here) */
+                bool any = false;
+                for (int c = t; c < ncells && !any; c += BR_NT) any = cell_in_mask(g, ((uint32_t)b << cell_bits) | (uint32_t)c);
+                if (!__syncthreads_or(any)) {
+                    if (t == 0) ceb[0] = b0;
+                    continue;
+                }
+            }
             for (int c = t; c < ncells; c += BR_NT) ceb[c] = b0;
             continue;
         }

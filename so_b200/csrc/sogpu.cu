@@ -92,6 +92,7 @@ struct GridDev {
     double bmax_pruned;       /* balls at least this large visit every cell                  */
     const uint32_t *mask;     /* focused build: bit per coarse cell that was kept (NULL = all) */
     int mb, ms;               /* mask cells per axis = 2^mb; fine cell coordinate >> ms        */
+    double mask_rmin;         /* smallest half-width a halo marks in the mask                  */
 };
 
 /* rows of cells (fixed iy, iz) are contiguous along x; rows are ordered in 8x8 tiles of (iy, iz),
@@ -146,6 +147,16 @@ __device__ __forceinline__ uint32_t cell_key_kept(const float4 &p, const GridDev
     uint32_t iz = cell_coord(p.z, g.g0[2], g.invh[2], mask);
     kept = !g.mask || mask_bit(g, ix >> g.ms, iy >> g.ms, iz >> g.ms);
     return (row_key(iy, iz, g.lb, g.tb) << g.lb) | ix;
+}
+
+/* is the cell with this key inside a coarse cell of the focus mask?  (inverse of row_key) */
+__device__ __forceinline__ bool cell_in_mask(const GridDev &g, uint32_t key)
+{
+    const uint32_t ix = key & (uint32_t)(g.nc - 1), rk = key >> g.lb;
+    const uint32_t m = (1u << g.tb) - 1u, lo = rk & ((1u << (2 * g.tb)) - 1u), hi = rk >> (2 * g.tb);
+    const uint32_t iy = ((hi & ((1u << (g.lb - g.tb)) - 1u)) << g.tb) | (lo & m);
+    const uint32_t iz = ((hi >> (g.lb - g.tb)) << g.tb) | (lo >> g.tb);
+    return mask_bit(g, ix >> g.ms, iy >> g.ms, iz >> g.ms);
 }
 
 __device__ __forceinline__ float4 ld_stream(const float4 *p)
@@ -657,7 +668,9 @@ __global__ void __launch_bounds__(256) k_mark_mask(GridDev g, const float *__res
         float ball = rgtp[h];
         for (int k = 0; k < n_balls && (double)ball < 0.25 * (double)root; ++k) ball = so_next_ball(ball);
         const float ball2 = __fmul_rn(ball, ball);
-        const double b = sqrt((double)ball2) * (1.0 + 1.0e-6);
+        /* small halos: at least mask_rmin around the centre (a fraction of a coarse cell costs next to
+         * nothing and keeps poorly estimated small groups inside their mask) */
+        const double b = fmax(sqrt((double)ball2) * (1.0 + 1.0e-6), g.mask_rmin);
         int x0, nx, y0, ny, z0, nz;
         mask_range(g, 0, centers[3 * h + 0], b, x0, nx);
         mask_range(g, 1, centers[3 * h + 1], b, y0, ny);
@@ -1678,17 +1691,25 @@ __global__ void __launch_bounds__(256) k_route(const __grid_constant__ RouteArgs
                 q[u].w = __uint_as_float(a.index_base + (uint32_t)i);
             }
         }
+        uint32_t wset = 0u;                                 /* destinations some lane of this warp has */
+#pragma unroll
+        for (int u = 0; u < ROUTE_U; ++u) wset |= set[u];
+        wset = __reduce_or_sync(0xFFFFFFFFu, wset);
         if (!SCATTER) {
-            for (int d = 0; d < a.R; ++d) {
+            for (uint32_t rem = wset; rem; rem &= rem - 1u) {
+                const int d = __ffs(rem) - 1;
                 uint32_t c = 0;
 #pragma unroll
                 for (int u = 0; u < ROUTE_U; ++u) c += __popc(__ballot_sync(0xFFFFFFFFu, (set[u] >> d) & 1u));
-                if (lane == 0 && c) atomicAdd(&scount[d], (unsigned long long)c);
+                if (lane == 0) atomicAdd(&scount[d], (unsigned long long)c);
             }
         } else {
             /* one reservation per (CTA, round, destination): the warps' runs follow each other, inside a warp
              * the records are ordered by (u, lane) — runs of up to 128 contiguous records per warp */
-            for (int d = 0; d < a.R; ++d) {
+            if (lane < a.R) wcnt[w][lane] = 0u;
+            __syncwarp();
+            for (uint32_t rem = wset; rem; rem &= rem - 1u) {
+                const int d = __ffs(rem) - 1;
                 uint32_t c = 0;
 #pragma unroll
                 for (int u = 0; u < ROUTE_U; ++u) c += __popc(__ballot_sync(0xFFFFFFFFu, (set[u] >> d) & 1u));
@@ -1704,8 +1725,8 @@ __global__ void __launch_bounds__(256) k_route(const __grid_constant__ RouteArgs
                 for (int k = 0; k < 8; ++k) { wbase[k][d] = base; base += wcnt[k][d]; }
             }
             __syncthreads();
-            for (int d = 0; d < a.R; ++d) {
-                if (!wcnt[w][d]) continue;
+            for (uint32_t rem = wset; rem; rem &= rem - 1u) {
+                const int d = __ffs(rem) - 1;
                 unsigned long long pos = wbase[w][d];
 #pragma unroll
                 for (int u = 0; u < ROUTE_U; ++u) {
@@ -1833,6 +1854,7 @@ struct sogpu {
     size_t lvl_cap[4];
     float cls_small_max, cls_huge_min;   /* expected ball population: warp / 256-thread CTA / 1024-thread CTA */
     int emit_small_max, emit_huge_min;   /* same split for the member emission, by N_Delta */
+    double mask_rmin_cells;          /* focus masks: minimum half-width per halo, in coarse cells */
     bool indexed;                    /* d_in is {x,y,z,global index} of one rank's share (domain runs) */
     float indexed_mass;
     int64_t n_total;                 /* particles of the whole snapshot (grid resolution of a domain run) */
@@ -1974,6 +1996,8 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     h->mass_state = -1;
     h->two_level = -1;
     h->first_ball = 2;
+    h->mask_rmin_cells = 0.75;
+    if (const char *e = getenv("SOGPU_MASK_RMIN")) h->mask_rmin_cells = atof(e);
     h->cls_small_max = 1024.0f; h->cls_huge_min = 4096.0f;
     h->emit_small_max = 2048; h->emit_huge_min = 4096;
     if (const char *e = getenv("SOGPU_SMALL_MAX")) h->cls_small_max = (float)atof(e);
@@ -2413,6 +2437,7 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         if (!h->d_mask) CU(cudaMalloc(&h->d_mask, (((size_t)1 << 24) / 32 + 1) * sizeof(uint32_t)));
         CU(cudaMemsetAsync(h->d_mask, 0, words * sizeof(uint32_t), s));
         g.mb = mb; g.ms = lb - mb;
+        g.mask_rmin = h->mask_rmin_cells * hmax * (double)(1 << g.ms);
         GridDev gm = g;
         gm.mask = h->d_mask;
         {
@@ -2961,6 +2986,9 @@ extern "C" int sogpu_so(sogpu_t *h, const float *centers, const float *rgtp, int
          * full grid and solve again — results never depend on how the grid was built */
         bool redo = (pn[0] == CODE_UNEQUAL_MASS);
         for (int32_t i = 0; i < nh && !redo; ++i) redo = (pn[i] == CODE_NEED_FULL);
+        if (redo && h->indexed)
+            return set_err(SOGPU_ERR_UNSUPPORTED, "a halo outgrew the focus mask of this rank's share: route again with a "
+                                                  "larger n_balls (sogpu_so_device reports such halos with code -103)");
         if (redo) {
             rc = build_grid_impl(h, 0, 0);
             if (rc) return rc;
@@ -3123,6 +3151,7 @@ extern "C" int sogpu_ball_gather(sogpu_t *h, const float center[3], float ball2,
     if (!h->built) return set_err(SOGPU_ERR_ARG, "sogpu_ball_gather: call sogpu_build_grid first");
     if (!(ball2 >= 0.0f) || !(ball2 < INFINITY)) return set_err(SOGPU_ERR_ARG, "bad ball2");
     CU(cudaSetDevice(h->device));
+    if (h->indexed) return set_err(SOGPU_ERR_UNSUPPORTED, "sogpu_ball_gather: not available on one rank's share of a domain run");
     if (h->focused) { int rf = build_grid_impl(h, 0, 0); if (rf) return rf; }
     int rc = ensure_query(h, 1);
     if (rc) return rc;
@@ -3170,6 +3199,7 @@ extern "C" int sogpu_ball_gather_batch(sogpu_t *h, const float *centers, const f
     if (!h || !centers || !ball2 || nh <= 0) return set_err(SOGPU_ERR_ARG, "sogpu_ball_gather_batch: bad argument");
     if (!h->built) return set_err(SOGPU_ERR_ARG, "sogpu_ball_gather_batch: call sogpu_build_grid first");
     CU(cudaSetDevice(h->device));
+    if (h->indexed) return set_err(SOGPU_ERR_UNSUPPORTED, "sogpu_ball_gather_batch: not available on one rank's share of a domain run");
     if (h->focused) { int rf = build_grid_impl(h, 0, 0); if (rf) return rf; }   /* arbitrary balls need every particle */
     int rc = ensure_query(h, nh);
     if (rc) return rc;
@@ -3359,6 +3389,7 @@ static void domain_geometry(sogpu *h, int64_t n_total, GridDev &g)
     }
     g.bmax_pruned = 0.5 * lmin - 2.0 * hmax;
     g.mb = std::min(lb, 8); g.ms = lb - g.mb;
+    g.mask_rmin = h->mask_rmin_cells * hmax * (double)(1 << g.ms);
 }
 
 extern "C" int sogpu_domain_mask_words(sogpu_t *h, int64_t n_total, int64_t *words)

@@ -262,6 +262,7 @@ class DomainRun:
         self.words = gpu.domain_mask_words(n_total)
         self.masks = torch.zeros((self.world, self.words), dtype=torch.int32, device=self.dev)
         self.my_mask = torch.zeros(self.words, dtype=torch.int32, device=self.dev)
+        self._token = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.recv_cap = 0
         self.recv_ptr = 0                 # my receive buffer (peer-shareable allocation)
         self.peer_ptrs = []               # everyone's receive buffer as seen from this process
@@ -311,7 +312,6 @@ class DomainRun:
             dist.all_gather_into_tensor(self.masks.view(-1), self.my_mask, group=self.group)
         else:
             self.masks[0].copy_(self.my_mask)
-        torch.cuda.current_stream().synchronize()
         counts = g.domain_route_count(self.n_total, d_slice, n_slice, self.masks.data_ptr(), R)
         cm = torch.zeros((R, R), dtype=torch.int64, device=self.dev)
         mine = torch.from_numpy(counts).to(self.dev)
@@ -325,9 +325,10 @@ class DomainRun:
         if self.transport == "p2p" or R == 1:
             g.domain_route_scatter(self.n_total, d_slice, n_slice, index_base, self.masks.data_ptr(),
                                    self.peer_ptrs if R > 1 else [self.recv_ptr], recv_off[me])
-            torch.cuda.current_stream().synchronize()       # my stores are out
             if R > 1:
-                dist.barrier(group=self.group)              # ... and so are everybody else's
+                # stream-ordered barrier: my grid build (same stream) starts after every rank's routing
+                # kernel has finished, i.e. after all stores into my buffer have been performed
+                dist.all_reduce(self._token, group=self.group)
         else:
             tot = int(cm[me].sum())
             if self.send is None or self.send.shape[0] < tot:
