@@ -623,10 +623,48 @@ __global__ void __launch_bounds__(RT_NT, 3) k_lvl_partition_rt(const float4 *__r
 #define BR_NT 256
 #define BR_IT 8
 
+/* focused builds: most final buckets are empty and lie outside the focus mask.  One thread per bucket
+ * settles those (their cell-table slice is never read except its first entry, see k_bucket_sort_rt) and
+ * lists the others for the sort kernel, which then iterates over live buckets only. */
+__global__ void __launch_bounds__(256) k_bucket_live(GridDev g, int cell_bits, uint32_t n_buckets,
+                                                     const uint32_t *__restrict__ bstart, uint32_t *__restrict__ ce,
+                                                     uint32_t *__restrict__ live, uint32_t *__restrict__ live_n)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    bool is_live = false;
+    if (b < n_buckets) {
+        const uint32_t b0 = __ldg(bstart + b), b1 = __ldg(bstart + b + 1);
+        is_live = b1 > b0;
+        if (!is_live) {
+            /* a stretch of one row of cells: its coarse cells are consecutive mask bits */
+            const uint32_t key0 = b << cell_bits;
+            const uint32_t nbits = max(1u, (1u << cell_bits) >> g.ms);
+            const uint32_t bit0 = cell_mask_bit(g, key0);                 /* ... starting here, tested a word at a time */
+            for (uint32_t k = bit0; k < bit0 + nbits && !is_live;) {
+                const uint32_t wbit = k & 31u, take = min(32u - wbit, bit0 + nbits - k);
+                const uint32_t word = __ldg(g.mask + (k >> 5)) >> wbit;
+                is_live = (take == 32u ? word : (word & ((1u << take) - 1u))) != 0u;
+                k += take;
+            }
+            if (!is_live) ce[(size_t)b << cell_bits] = b0;
+        }
+    }
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_live);
+    if (m) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(live_n, (uint32_t)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (is_live) live[base + __popc(m & ((1u << lane) - 1u))] = b;
+    }
+}
+
 __global__ void __launch_bounds__(BR_NT, 4) k_bucket_sort_rt(const float4 *__restrict__ in4, GridDev g, int cell_bits,
                                                              uint32_t n_buckets, const uint32_t *__restrict__ bstart,
                                                              float4 *__restrict__ sorted, uint32_t *__restrict__ ce,
-                                                             int first_pass_input_is_raw)
+                                                             int first_pass_input_is_raw,
+                                                             const uint32_t *__restrict__ live,
+                                                             const uint32_t *__restrict__ live_n)
 {
     __shared__ __align__(16) uint32_t cnt[BKT_CELLS];
     __shared__ uint32_t ws[BR_NT / 32];
@@ -638,28 +676,21 @@ __global__ void __launch_bounds__(BR_NT, 4) k_bucket_sort_rt(const float4 *__res
     const int per = (ncells + BR_NT - 1) / BR_NT;
     const bool vec = (ncells >= 4 * BR_NT);
     uint4 *cnt4 = reinterpret_cast<uint4 *>(cnt);
-    uint32_t nx0 = 0, nx1 = 0;
-    if (blockIdx.x < n_buckets) { nx0 = __ldg(bstart + blockIdx.x); nx1 = __ldg(bstart + blockIdx.x + 1); }
-    for (uint32_t b = blockIdx.x; b < n_buckets; b += gridDim.x) {
-        const uint32_t b0 = nx0, b1 = nx1;
+    if (live) n_buckets = __ldg(live_n);                 /* iterate over the live buckets only (k_bucket_live) */
+    uint32_t nxb = 0, nx0 = 0, nx1 = 0;
+    if (blockIdx.x < n_buckets) {
+        nxb = live ? __ldg(live + blockIdx.x) : blockIdx.x;
+        nx0 = __ldg(bstart + nxb); nx1 = __ldg(bstart + nxb + 1);
+    }
+    for (uint32_t bi = blockIdx.x; bi < n_buckets; bi += gridDim.x) {
+        const uint32_t b = nxb, b0 = nx0, b1 = nx1;
         const uint32_t nb = b1 - b0;
-        if (b + gridDim.x < n_buckets) {                                  /* bounds of the next bucket, early */
-            nx0 = __ldg(bstart + b + gridDim.x); nx1 = __ldg(bstart + b + gridDim.x + 1);
+        if (bi + gridDim.x < n_buckets) {                                 /* bounds of the next bucket, early */
+            nxb = live ? __ldg(live + bi + gridDim.x) : bi + gridDim.x;
+            nx0 = __ldg(bstart + nxb); nx1 = __ldg(bstart + nxb + 1);
         }
         uint32_t *ceb = ce + ((size_t)b << cell_bits);
         if (nb == 0) {                   /* empty bucket (focused builds): only its cell-table slice */
-            if (g.mask) {
-                /* ... and not even that when none of its cells lies in a coarse cell of the focus mask:
-                 * the queries check every ball against the mask, so they read cell-table entries of
-                 * marked cells and the entry right behind one, which is either in a bucket with a marked
-                 * cell (written in full) or the FIRST entry of the next bucket (written here) */
-                bool any = false;
-                for (int c = t; c < ncells && !any; c += BR_NT) any = cell_in_mask(g, ((uint32_t)b << cell_bits) | (uint32_t)c);
-                if (!__syncthreads_or(any)) {
-                    if (t == 0) ceb[0] = b0;
-                    continue;
-                }
-            }
             for (int c = t; c < ncells; c += BR_NT) ceb[c] = b0;
             continue;
         }

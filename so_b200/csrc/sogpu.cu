@@ -149,7 +149,15 @@ __device__ __forceinline__ uint32_t cell_key_kept(const float4 &p, const GridDev
     return (row_key(iy, iz, g.lb, g.tb) << g.lb) | ix;
 }
 
-/* is the cell with this key inside a coarse cell of the focus mask?  (inverse of row_key) */
+/* mask bit of the coarse cell that holds the cell with this key (inverse of row_key) */
+__device__ __forceinline__ uint32_t cell_mask_bit(const GridDev &g, uint32_t key)
+{
+    const uint32_t ix = key & (uint32_t)(g.nc - 1), rk = key >> g.lb;
+    const uint32_t m = (1u << g.tb) - 1u, lo = rk & ((1u << (2 * g.tb)) - 1u), hi = rk >> (2 * g.tb);
+    const uint32_t iy = ((hi & ((1u << (g.lb - g.tb)) - 1u)) << g.tb) | (lo & m);
+    const uint32_t iz = ((hi >> (g.lb - g.tb)) << g.tb) | (lo >> g.tb);
+    return ((iz >> g.ms) << (2 * g.mb)) | ((iy >> g.ms) << g.mb) | (ix >> g.ms);
+}
 __device__ __forceinline__ bool cell_in_mask(const GridDev &g, uint32_t key)
 {
     const uint32_t ix = key & (uint32_t)(g.nc - 1), rk = key >> g.lb;
@@ -1888,6 +1896,8 @@ struct sogpu {
     bool have_result;
     bool want_d2;
     bool member_overflow;
+    uint32_t *d_live;                /* focused builds: list of live final buckets (+ its length) */
+    size_t live_cap;
     unsigned long long *d_route;     /* domain runs: per-destination counters */
     unsigned short *d_route_table;   /* destination ranks per coarse cell */
     uint32_t *d_route_any;
@@ -2080,6 +2090,7 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     cudaFree(h->d_mt);
     cudaFree(h->d_vc);
     cudaFree(h->d_route); cudaFree(h->d_route_table); cudaFree(h->d_route_any);
+    cudaFree(h->d_live);
     cudaFree(h->d_tag); cudaFree(h->d_tag_index); cudaFree(h->d_dirty);
     cudaFree(h->d_counters);
     cudaFree(h->d_u64);
@@ -2562,7 +2573,22 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         if (h->two_level == 2)
             k_bucket_sort<<<grid, BKT_THREADS, bkt_smem, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, (L == 0 && !g.indexed) ? 1 : 0);
         else
-            k_bucket_sort_rt<<<grid, BR_NT, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, (L == 0 && !g.indexed) ? 1 : 0);
+        {
+            const uint32_t *live = nullptr, *live_n = nullptr;
+            if (g.mask && cell_bits <= lb && nb >= 4096u) {
+                /* focused build with many final buckets: settle the empty ones outside the mask first */
+                if ((size_t)nb + 1 > h->live_cap) {
+                    cudaFree(h->d_live); h->d_live = nullptr; h->live_cap = 0;
+                    CU(cudaMalloc(&h->d_live, ((size_t)nb + 1) * sizeof(uint32_t)));
+                    h->live_cap = (size_t)nb + 1;
+                }
+                CU(cudaMemsetAsync(h->d_live + nb, 0, sizeof(uint32_t), s));
+                k_bucket_live<<<(nb + 255) / 256, 256, 0, s>>>(g, cell_bits, nb, bstart, h->d_ce, h->d_live, h->d_live + nb);
+                live = h->d_live; live_n = h->d_live + nb;
+            }
+            k_bucket_sort_rt<<<grid, BR_NT, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce,
+                                                    (L == 0 && !g.indexed) ? 1 : 0, live, live_n);
+        }
     }
     if (h->focused) k_copy_u32<<<1, 32, 0, s>>>(h->d_ce + ncell, h->d_lvl_start[0] + ((size_t)1 << db[0]));
     else k_store_u32<<<1, 32, 0, s>>>(h->d_ce + ncell, (uint32_t)h->n, nullptr, 0u);

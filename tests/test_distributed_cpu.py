@@ -86,3 +86,39 @@ def test_lpt_assignment_is_balanced_and_deterministic():
 def test_halo_cost_scales_with_radius_cubed():
     c = parallel.halo_cost(np.array([0.01, 0.02]), 1e6, 1.0)
     assert np.isclose((c[1] - 64) / (c[0] - 64), 8.0)
+
+
+def test_spatial_assignment_is_balanced_and_compact():
+    """Domain runs: halos are cut into spatially compact, cost-balanced shares (so_b200.parallel.spatial_assign)."""
+    rng = np.random.default_rng(3)
+    c = (rng.random((20000, 3)) - 0.5).astype(np.float32)
+    cost = 10.0 ** rng.uniform(1, 4, 20000)
+    for r in (1, 2, 3, 8):
+        rank, load = parallel.spatial_assign(c, cost, r)
+        assert rank.min() == 0 and rank.max() == r - 1
+        np.testing.assert_allclose(load.sum(), cost.sum())
+        assert load.max() / load.mean() < 1.05
+        again, _ = parallel.spatial_assign(c, cost, r)
+        assert np.array_equal(rank, again)                  # deterministic: every rank computes the same split
+    # compactness: a share occupies far fewer coarse blocks than a random share of the same size would
+    rank, _ = parallel.spatial_assign(c, cost, 8)
+    blocks = (np.floor((c + 0.5) * 8).astype(int) % 8) @ np.array([1, 8, 64])
+    mine = len(np.unique(blocks[rank == 3]))
+    rand = len(np.unique(blocks[rng.permutation(len(c))[: (rank == 3).sum()]]))
+    assert mine < 0.4 * rand
+
+
+def test_exchange_plan_offsets():
+    cm = np.array([[5, 0, 2], [1, 7, 0], [0, 3, 4]])
+    total, off = parallel.exchange_plan(cm)
+    assert total.tolist() == [6, 10, 6]
+    assert off.tolist() == [[0, 0, 0], [5, 0, 2], [6, 7, 2]]
+    # every destination's buffer is tiled exactly by the sources' ranges
+    for d in range(3):
+        spans = sorted((off[s, d], off[s, d] + cm[s, d]) for s in range(3))
+        pos = 0
+        for a, b in spans:
+            assert a == pos
+            pos = b
+        assert pos == total[d]
+    assert parallel.slice_bounds(10, 3) == [(0, 3), (3, 6), (6, 10)]
