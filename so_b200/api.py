@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsogpu.so")
+LIB_PATH = os.environ.get("SOGPU_LIB") or os.path.join(HERE, "libsogpu.so")   # SOGPU_LIB: A/B builds of the library
 
 SYMBOLS = [
     "sogpu_create", "sogpu_destroy", "sogpu_last_error", "sogpu_set_stream",

@@ -42,15 +42,18 @@
 #define CODE_DEFER (-101)
 #define CODE_NEED_FULL (-103)   /* focused grid does not cover this halo's ball */
 
+#ifndef Q32_MINB
+#define Q32_MINB 1      /* resident CTAs per SM the warp-per-halo kernel is compiled for */
+#endif
 template <int NT> struct Cfg;
 template <> struct Cfg<32> {   /* warp per halo */
-    static const int CAP = 256, WTARGET = 128, NLEV = 1, GROUPS = 8;
+    static const int CAP = 256, WTARGET = 128, NLEV = 1, GROUPS = 8, MINB = Q32_MINB;
 };
 template <> struct Cfg<256> {  /* block per halo */
-    static const int CAP = 4096, WTARGET = 1024, NLEV = 4, GROUPS = 1;
+    static const int CAP = 4096, WTARGET = 1024, NLEV = 4, GROUPS = 1, MINB = 1;
 };
 template <> struct Cfg<1024> { /* one full-SM block per halo: cluster-size halos (>= ~10^5 particles) */
-    static const int CAP = 4096, WTARGET = 2048, NLEV = 4, GROUPS = 1;
+    static const int CAP = 4096, WTARGET = 2048, NLEV = 4, GROUPS = 1, MINB = 1;
 };
 
 /* ============================================================================================
@@ -952,7 +955,7 @@ __device__ __forceinline__ uint32_t next_item(uint32_t *counter, GroupSmem<NT> &
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS) k_so_query(const __grid_constant__ QueryArgs a)
+__global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS, Cfg<NT>::MINB) k_so_query(const __grid_constant__ QueryArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MassTableS &mt = *reinterpret_cast<MassTableS *>(smem_raw);
