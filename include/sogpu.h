@@ -60,6 +60,10 @@ int sogpu_set_build_mode(sogpu_t *h, int mode);
  * only examines what smaller balls have not, the -1 test always counts the schedule's first ball,
  * and the schedule's last ball is never skipped. */
 int sogpu_set_first_ball(sogpu_t *h, int k);
+/* Tuning knob: the 1024-thread class (cluster-size halos) stages its particles through TMA bulk copies
+ * (cp.async.bulk + mbarrier ring in shared memory) instead of per-thread float4 loads.  Default off
+ * (slower on B200 for this access pattern); results are identical. */
+int sogpu_set_tma_staging(sogpu_t *h, int on);
 /* Tuning knob: target mean particles per grid cell (default 2.0). */
 int sogpu_set_cell_occupancy(sogpu_t *h, float particles_per_cell);
 

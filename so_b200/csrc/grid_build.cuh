@@ -620,7 +620,10 @@ __global__ void __launch_bounds__(RT_NT, 3) k_lvl_partition_rt(const float4 *__r
  * (an L2 hit).  Stores go straight to the final slot: the bucket's whole output range (16-50 KB)
  * is written by this CTA within a microsecond, so the 16-byte stores merge in L2.  Only the cell
  * counts live in shared memory (16 KB), which leaves room for 4 CTAs per SM. */
+#ifndef BR_NT
 #define BR_NT 256
+#define BR_MINB 4
+#endif
 #define BR_IT 8
 
 /* focused builds: most final buckets are empty and lie outside the focus mask.  One thread per bucket
@@ -659,7 +662,7 @@ __global__ void __launch_bounds__(256) k_bucket_live(GridDev g, int cell_bits, u
     }
 }
 
-__global__ void __launch_bounds__(BR_NT, 4) k_bucket_sort_rt(const float4 *__restrict__ in4, GridDev g, int cell_bits,
+__global__ void __launch_bounds__(BR_NT, BR_MINB) k_bucket_sort_rt(const float4 *__restrict__ in4, GridDev g, int cell_bits,
                                                              uint32_t n_buckets, const uint32_t *__restrict__ bstart,
                                                              float4 *__restrict__ sorted, uint32_t *__restrict__ ce,
                                                              int first_pass_input_is_raw,

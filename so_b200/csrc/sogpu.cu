@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstddef>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -42,6 +43,9 @@
 #define CODE_DEFER (-101)
 #define CODE_NEED_FULL (-103)   /* focused grid does not cover this halo's ball */
 
+#ifndef BKT_AVG
+#define BKT_AVG 1024   /* mean particles per final bucket */
+#endif
 #ifndef Q32_MINB
 #define Q32_MINB 1      /* resident CTAs per SM the warp-per-halo kernel is compiled for */
 #endif
@@ -89,6 +93,7 @@ struct GridDev {
     int nc, lb;               /* cells per axis (power of two), log2                         */
     int tb;                   /* rows are ordered in tiles of 2^tb x 2^tb (iy, iz)           */
     int indexed;              /* input .w already holds the particle's (global) index, not its mass */
+    int use_tma;              /* 1024-thread class: stage the particles through TMA bulk copies */
     float g0[3], invh[3];     /* cell coordinate = floor((x - g0) * invh) & (nc-1)           */
     float L[3], halfL[3];
     double dg0[3], dinvh[3], dh[3];
@@ -305,6 +310,23 @@ struct MassTableS {   /* CTA-shared copy of the mass table */
     float inc[SO_MT_MAX];
 };
 
+/* Staging of the 1024-thread class (cluster-size halos): the particles of a ball are pulled into shared
+ * memory by TMA bulk copies (cp.async.bulk, one per row segment piece, completion on an mbarrier) through
+ * a ring of TMA_STAGES tiles (full / empty mbarriers, no block-wide barrier per tile), instead of
+ * per-thread loads.  Selectable (sogpu_set_tma_staging) and OFF by default: measured on B200 with 64
+ * halos of 10^6 particles the plain coalesced float4 loads (4 in flight per thread, 64 KB per SM) already
+ * pull 2.7 TB/s over the 64 busy SMs and finish the solve in 2.5 ms; the TMA ring needs 3.3 ms
+ * (profiles/r1b_build_experiments.md). */
+#define TMA_TILE 2048
+#define TMA_STAGES 4
+template <int NT> struct TmaStage { };
+template <> struct TmaStage<1024> {
+    float4 tile[TMA_STAGES][TMA_TILE];          /* 4 x 32 KB: three tiles in flight while one is read */
+    unsigned long long full[TMA_STAGES];        /* producer: expect_tx + the copies' complete_tx     */
+    unsigned long long empty[TMA_STAGES];       /* consumers: one arrival per warp after reading     */
+    uint32_t tiles_done;                        /* tiles staged so far by this CTA: stage and phase of the next */
+};
+
 template <int NT> struct GroupSmem {
     unsigned long long wkey[Cfg<NT>::CAP];      /* window: (r^2 bits << 32) | original index   */
     uint32_t hist[Cfg<NT>::NLEV][NB + 1];       /* per level: counts, then exclusive prefix    */
@@ -314,6 +336,7 @@ template <int NT> struct GroupSmem {
     uint32_t cnt;                               /* append cursor                               */
     uint32_t bcast[4];
     uint8_t wflag[Cfg<NT>::CAP];                /* below-threshold flag per window element     */
+    alignas(128) TmaStage<NT> tma;              /* LAST: only allocated when TMA staging is on (query_smem_bytes) */
 };
 
 __device__ __forceinline__ float mt_eval(const MassTableS &mt, uint32_t k)
@@ -412,6 +435,49 @@ __device__ __forceinline__ void row_segments(const GridDev &g, const BallGeom &B
     }
 }
 
+/* ---- TMA bulk copy + mbarrier (PTX ISA 8.0, sm_90+) ---------------------------------------------- */
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+template <int NT> __device__ __forceinline__ void tma_stage_init(GroupSmem<NT> &sm, int tid, int use_tma)
+{
+    if constexpr (NT == 1024) {
+        if (!use_tma) return;                   /* the stage memory is not even allocated then */
+        if (tid == 0) {
+            for (int k = 0; k < TMA_STAGES; ++k) {
+                mbar_init(&sm.tma.full[k], 1u);
+                mbar_init(&sm.tma.empty[k], (uint32_t)(NT / 32));      /* one arrival per warp */
+            }
+            sm.tma.tiles_done = 0u;
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+}
+
 /* Visit every particle stored in a cell that overlaps the ball: f(slot, particle).
  * All NT threads of the group must call this together. */
 template <int NT, typename F>
@@ -429,6 +495,55 @@ __device__ __forceinline__ void for_each_in_ball(const GridDev &g, GroupSmem<NT>
         sm.seg_pre[2 * tid + 1] = incl;
         gsync<NT>();
         uint32_t total = sm.seg_pre[2 * NT - 1];
+        if (NT == 1024 && g.use_tma) if constexpr (NT == 1024) {
+            /* TMA path: tile k = flat range [k*TMA_TILE, (k+1)*TMA_TILE) of the concatenated row segments,
+             * fetched by warp 0 (one bulk copy per piece of a segment, lanes in parallel) TMA_STAGES-1 tiles
+             * ahead of the tile the block reads.  Tiles are numbered J = 0, 1, 2 ... over the CTA's lifetime:
+             * stage J % STAGES, full-barrier phase (J / STAGES) & 1; a stage is refilled once all warps
+             * have arrived on its empty barrier for tile J - STAGES. */
+            const int lane = tid & 31, w = tid >> 5;
+            const uint32_t J0 = sm.tma.tiles_done;
+            const uint32_t ntile = (total + TMA_TILE - 1) / TMA_TILE;
+            auto issue = [&](uint32_t k) {
+                const uint32_t J = J0 + k, st = J % TMA_STAGES, t0 = k * TMA_TILE, t1 = min(total, t0 + TMA_TILE);
+                if (J >= TMA_STAGES) mbar_wait(&sm.tma.empty[st], ((J / TMA_STAGES) - 1u) & 1u);
+                if (lane == 0) mbar_expect_tx(&sm.tma.full[st], (t1 - t0) * (uint32_t)sizeof(float4));
+                __syncwarp();
+                int lo = 0, hi = 2 * NT - 1;                  /* first segment whose inclusive prefix > t0 */
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (sm.seg_pre[mid] > t0) hi = mid; else lo = mid + 1;
+                }
+                for (int sgm = lo + lane; sgm < 2 * NT; sgm += 32) {
+                    const uint32_t beg = sgm ? sm.seg_pre[sgm - 1] : 0u, end = sm.seg_pre[sgm];
+                    if (beg >= t1) break;
+                    const uint32_t a = max(beg, t0), b = min(end, t1);
+                    if (b > a)
+                        tma_bulk_g2s(&sm.tma.tile[st][a - t0], g.sorted + sm.seg_start[sgm] + (a - beg),
+                                     (b - a) * (uint32_t)sizeof(float4), &sm.tma.full[st]);
+                }
+            };
+            if (w == 0)
+                for (uint32_t k = 0; k < ntile && k < TMA_STAGES - 1; ++k) issue(k);
+            for (uint32_t k = 0; k < ntile; ++k) {
+                if (w == 0 && k + TMA_STAGES - 1 < ntile) issue(k + TMA_STAGES - 1);
+                const uint32_t J = J0 + k, st = J % TMA_STAGES;
+                mbar_wait(&sm.tma.full[st], (J / TMA_STAGES) & 1u);
+                const uint32_t cnt = min((uint32_t)TMA_TILE, total - k * TMA_TILE);
+                for (uint32_t i = tid; i < cnt; i += NT) {
+                    const float4 q = sm.tma.tile[st][i];
+                    f(0u, q);
+                    ++evals;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   /* my reads come before the next bulk write */
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.tma.empty[st]);
+            }
+            gsync<NT>();
+            if (tid == 0) sm.tma.tiles_done = J0 + ntile;
+            gsync<NT>();
+            continue;
+        }
         uint32_t i = tid;
         if (i < total) {
             int lo = 0, hi = 2 * NT - 1;
@@ -973,6 +1088,7 @@ __global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS, Cfg<NT>::MINB) k_so_query
     }
     __syncthreads();
 
+    tma_stage_init<NT>(sm, tid, a.g.use_tma);
     const uint32_t nlist = *a.list_n;
     uint32_t ev_hist = 0, ev_other = 0;
     for (;;) {
@@ -1015,6 +1131,7 @@ __global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS) k_so_emit(const __grid_co
     const int grp = threadIdx.x / NT, tid = threadIdx.x % NT;
     GroupSmem<NT> &sm = *reinterpret_cast<GroupSmem<NT> *>(
         smem_raw + mt_bytes + (size_t)grp * ((sizeof(GroupSmem<NT>) + 15) & ~(size_t)15));
+    tma_stage_init<NT>(sm, tid, a.g.use_tma);
     const uint32_t nlist = *a.list_n;
     uint32_t ev = 0;
     for (;;) {
@@ -1046,10 +1163,11 @@ __global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS) k_so_emit(const __grid_co
     if ((threadIdx.x & 31) == 0 && ev) atomicAdd(&a.evals[1], (unsigned long long)ev);
 }
 
-template <int NT> static size_t query_smem_bytes()
+template <int NT> static size_t query_smem_bytes(bool with_tma = true)
 {
     size_t mt_bytes = (sizeof(MassTableS) + 15) & ~(size_t)15;
     size_t g_bytes = (sizeof(GroupSmem<NT>) + 15) & ~(size_t)15;
+    if (NT == 1024 && !with_tma) g_bytes = offsetof(GroupSmem<NT>, tma);      /* GROUPS == 1: nothing behind it */
     return mt_bytes + g_bytes * Cfg<NT>::GROUPS;
 }
 
@@ -1865,6 +1983,7 @@ struct sogpu {
     size_t lvl_cap[4];
     float cls_small_max, cls_huge_min;   /* expected ball population: warp / 256-thread CTA / 1024-thread CTA */
     int emit_small_max, emit_huge_min;   /* same split for the member emission, by N_Delta */
+    bool use_tma;                    /* sogpu_set_tma_staging */
     double mask_rmin_cells;          /* focus masks: minimum half-width per halo, in coarse cells */
     bool indexed;                    /* d_in is {x,y,z,global index} of one rank's share (domain runs) */
     float indexed_mass;
@@ -2010,6 +2129,7 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     h->two_level = -1;
     h->first_ball = 2;
     h->mask_rmin_cells = 0.75;
+    if (const char *e = getenv("SOGPU_TMA")) h->use_tma = atoi(e) != 0;
     if (const char *e = getenv("SOGPU_MASK_RMIN")) h->mask_rmin_cells = atof(e);
     h->cls_small_max = 1024.0f; h->cls_huge_min = 4096.0f;
     h->emit_small_max = 2048; h->emit_huge_min = 4096;
@@ -2135,6 +2255,14 @@ extern "C" int sogpu_set_first_ball(sogpu_t *h, int k)
 {
     if (!h || k < 1 || k > 64) return set_err(SOGPU_ERR_ARG, "bad first ball");
     h->first_ball = k;
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_set_tma_staging(sogpu_t *h, int on)
+{
+    if (!h) return set_err(SOGPU_ERR_ARG, "NULL handle");
+    h->use_tma = on != 0;
+    h->g.use_tma = h->use_tma ? 1 : 0;
     return SOGPU_OK;
 }
 
@@ -2392,7 +2520,7 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
     const int keybits = 3 * lb;
     /* final buckets: ~1024 particles on average and at most BKT_CELLS cells each */
     int cbt = 0;
-    while (((int64_t)1024 << cbt) < h->n) ++cbt;
+    while (((int64_t)BKT_AVG << cbt) < h->n) ++cbt;
     if (h->two_level == 0) cbt = 0;
     if (cbt < keybits - 12) cbt = keybits - 12;
     if (cbt > keybits) cbt = keybits;
@@ -2441,6 +2569,7 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
     g.bmax_pruned = 0.5 * lmin - 2.0 * hmax;
     g.mask = nullptr; g.mb = 0; g.ms = 0;
     g.indexed = h->indexed ? 1 : 0;
+    g.use_tma = h->use_tma ? 1 : 0;
 
     cudaStream_t s = h->stream;
     const double N = (double)h->n;
@@ -2696,7 +2825,7 @@ static void launch_persistent(sogpu *h, K kernel, const QueryArgs &a, int nh, Ex
     int ctas = h->sm_count * 4;
     int need = (nh + Cfg<NT>::GROUPS - 1) / Cfg<NT>::GROUPS;
     if (need < ctas) ctas = std::max(need, 1);
-    kernel<<<ctas, NT * Cfg<NT>::GROUPS, query_smem_bytes<NT>(), h->launch_stream>>>(a, extra...);
+    kernel<<<ctas, NT * Cfg<NT>::GROUPS, query_smem_bytes<NT>(h->use_tma), h->launch_stream>>>(a, extra...);
 }
 
 /* enqueue query + member emission for nh halos whose centers/rgtp are on the device */

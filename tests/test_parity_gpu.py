@@ -12,8 +12,10 @@ pytestmark = pytest.mark.gpu
 
 
 def run_gpu(pos, mass, centers, rgtp, thr, n_members=8, period=(1.0, 1.0, 1.0), center=(0.0, 0.0, 0.0),
-            ppc=None, first_ball=None):
+            ppc=None, first_ball=None, tma=False):
     g = api.SoGpu()
+    if tma:
+        g.set_tma_staging(True)
     if ppc:
         g.set_cell_occupancy(ppc)
     if first_ball:
@@ -77,9 +79,15 @@ def test_non_power_of_two_mass_sequential_sum():
     assert ref["ndelta"].max() > 30000
 
 
-def test_large_halos_use_block_kernel_and_refinement():
+@pytest.mark.parametrize("tma", [False, True])
+def test_large_halos_use_block_kernel_and_refinement(tma):
+    """Cluster-size halos: the 1024-thread class with per-thread loads, and with the TMA bulk-copy ring
+    (sogpu_set_tma_staging), incl. a halo on the periodic boundary (row segments that wrap)."""
     s = synth.make_snapshot(128 ** 3, 6, seed=32, sizes=[400000, 150000, 60000, 20000, 3000, 100], nmax=1e6)
-    r, ref = check_against_oracle(s.pos, s.mass, s.centers, s.rgtp, 200.0)
+    shift = np.array([0.4999 - s.centers[0, 0], -0.4999 - s.centers[0, 1], 0.0], np.float64)
+    pos = synth._wrap(s.pos.astype(np.float64) + shift).astype(np.float32)
+    centers = synth._wrap(s.centers.astype(np.float64) + shift).astype(np.float32)
+    r, ref = check_against_oracle(pos, s.mass, centers, s.rgtp, 200.0, tma=tma)
     assert ref["ndelta"].max() > 300000
 
 
