@@ -627,8 +627,10 @@ __global__ void __launch_bounds__(RT_NT, 3) k_lvl_partition_rt(const float4 *__r
 #define BR_IT 8
 
 /* focused builds: most final buckets are empty and lie outside the focus mask.  One thread per bucket
- * settles those (their cell-table slice is never read except its first entry, see k_bucket_sort_rt) and
- * lists the others for the sort kernel, which then iterates over live buckets only. */
+ * settles those and lists the others for the sort kernel, which then iterates over live buckets only.
+ * A settled bucket's cell-table slice is never read except its first entry: the queries check every ball
+ * against the mask, so they read entries of marked cells and the entry right behind one, which lies in a
+ * bucket with a marked cell (live: written in full) or is the first entry of the next bucket. */
 __global__ void __launch_bounds__(256) k_bucket_live(GridDev g, int cell_bits, uint32_t n_buckets,
                                                      const uint32_t *__restrict__ bstart, uint32_t *__restrict__ ce,
                                                      uint32_t *__restrict__ live, uint32_t *__restrict__ live_n)
@@ -639,15 +641,19 @@ __global__ void __launch_bounds__(256) k_bucket_live(GridDev g, int cell_bits, u
         const uint32_t b0 = __ldg(bstart + b), b1 = __ldg(bstart + b + 1);
         is_live = b1 > b0;
         if (!is_live) {
-            /* a stretch of one row of cells: its coarse cells are consecutive mask bits */
-            const uint32_t key0 = b << cell_bits;
-            const uint32_t nbits = max(1u, (1u << cell_bits) >> g.ms);
-            const uint32_t bit0 = cell_mask_bit(g, key0);                 /* ... starting here, tested a word at a time */
-            for (uint32_t k = bit0; k < bit0 + nbits && !is_live;) {
-                const uint32_t wbit = k & 31u, take = min(32u - wbit, bit0 + nbits - k);
-                const uint32_t word = __ldg(g.mask + (k >> 5)) >> wbit;
-                is_live = (take == 32u ? word : (word & ((1u << take) - 1u))) != 0u;
-                k += take;
+            /* the bucket is a stretch of one row of cells, or a few whole rows: per row its coarse cells
+             * are consecutive mask bits, tested a word at a time */
+            const uint32_t ncell_b = 1u << cell_bits;
+            const uint32_t per_row = min(ncell_b, (uint32_t)g.nc), nrow = ncell_b / per_row;
+            const uint32_t nbits = max(1u, per_row >> g.ms);
+            for (uint32_t r = 0; r < nrow && !is_live; ++r) {
+                const uint32_t bit0 = cell_mask_bit(g, (b << cell_bits) + r * per_row);
+                for (uint32_t k = bit0; k < bit0 + nbits && !is_live;) {
+                    const uint32_t wbit = k & 31u, take = min(32u - wbit, bit0 + nbits - k);
+                    const uint32_t word = __ldg(g.mask + (k >> 5)) >> wbit;
+                    is_live = (take == 32u ? word : (word & ((1u << take) - 1u))) != 0u;
+                    k += take;
+                }
             }
             if (!is_live) ce[(size_t)b << cell_bits] = b0;
         }

@@ -2707,7 +2707,7 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         else
         {
             const uint32_t *live = nullptr, *live_n = nullptr;
-            if (g.mask && cell_bits <= lb && nb >= 4096u) {
+            if (g.mask && nb >= 4096u) {
                 /* focused build with many final buckets: settle the empty ones outside the mask first */
                 if ((size_t)nb + 1 > h->live_cap) {
                     cudaFree(h->d_live); h->d_live = nullptr; h->live_cap = 0;
