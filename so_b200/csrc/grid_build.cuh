@@ -110,8 +110,11 @@ __global__ void __launch_bounds__(256) k_scan_apply(const uint32_t *a, int64_t n
 }
 
 /* the same exclusive scan by ONE block (bucket tables up to a few 10^5 entries: one launch instead of
- * three): out[i] = sum a[0..i), copy[i] likewise, out[n] = total.  out may alias a. */
-#define SCAN1_PER 16
+ * three): out[i] = sum a[0..i), copy[i] likewise, out[n] = total.  out may alias a.  Four consecutive
+ * entries per thread, moved as uint4: the loads AND the stores of a warp are 512 contiguous bytes
+ * (measured, tools/micro/scan_microbench.cu, 16384 entries: 6.2 us; 16 entries per thread with scalar
+ * stores at a 64-byte stride between lanes: 24.6 us — partial-sector writes again). */
+#define SCAN1_PER 4
 __global__ void __launch_bounds__(1024) k_scan_one(const uint32_t *a, int64_t n, uint32_t *out, uint32_t *copy)
 {
     __shared__ uint32_t ws[32];
@@ -121,20 +124,16 @@ __global__ void __launch_bounds__(1024) k_scan_one(const uint32_t *a, int64_t n,
     __syncthreads();
     for (int64_t c0 = 0; c0 < n; c0 += 1024 * SCAN1_PER) {
         const int64_t base = c0 + (int64_t)t * SCAN1_PER;
-        uint32_t v[SCAN1_PER], s = 0;
-        if (base + SCAN1_PER <= n) {                       /* 64 contiguous bytes per thread */
-            const uint4 *a4 = reinterpret_cast<const uint4 *>(a + base);
-#pragma unroll
-            for (int k = 0; k < SCAN1_PER / 4; ++k) {
-                uint4 x4 = a4[k];
-                v[4 * k] = x4.x; v[4 * k + 1] = x4.y; v[4 * k + 2] = x4.z; v[4 * k + 3] = x4.w;
-            }
+        const bool whole = base + SCAN1_PER <= n;             /* (a, out, copy are 16-byte aligned allocations) */
+        uint32_t v[SCAN1_PER];
+        if (whole) {
+            const uint4 x4 = *reinterpret_cast<const uint4 *>(a + base);
+            v[0] = x4.x; v[1] = x4.y; v[2] = x4.z; v[3] = x4.w;
         } else {
 #pragma unroll
             for (int k = 0; k < SCAN1_PER; ++k) v[k] = (base + k < n) ? a[base + k] : 0u;
         }
-#pragma unroll
-        for (int k = 0; k < SCAN1_PER; ++k) s += v[k];
+        const uint32_t s = v[0] + v[1] + v[2] + v[3];
         uint32_t x = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -153,14 +152,21 @@ __global__ void __launch_bounds__(1024) k_scan_one(const uint32_t *a, int64_t n,
             ws[lane] = y;
         }
         __syncthreads();
-        uint32_t run = carry_s + (w ? ws[w - 1] : 0u) + x - s;
+        uint4 e;
+        e.x = carry_s + (w ? ws[w - 1] : 0u) + x - s;
+        e.y = e.x + v[0]; e.z = e.y + v[1]; e.w = e.z + v[2];
+        const uint32_t run = e.w + v[3];
+        if (whole) {
+            *reinterpret_cast<uint4 *>(out + base) = e;
+            if (copy) *reinterpret_cast<uint4 *>(copy + base) = e;
+        } else {
+            const uint32_t ee[4] = {e.x, e.y, e.z, e.w};
 #pragma unroll
-        for (int k = 0; k < SCAN1_PER; ++k) {
-            if (base + k < n) {
-                out[base + k] = run;
-                if (copy) copy[base + k] = run;
-            }
-            run += v[k];
+            for (int k = 0; k < SCAN1_PER; ++k)
+                if (base + k < n) {
+                    out[base + k] = ee[k];
+                    if (copy) copy[base + k] = ee[k];
+                }
         }
         __syncthreads();
         if (t == 1023) carry_s = run;

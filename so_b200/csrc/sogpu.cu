@@ -1204,7 +1204,7 @@ __global__ void k_classify(const float *__restrict__ rgtp, int nh, float thr, co
 /* exclusive scan of max(N_Delta,0) in catalog order -> member offsets; also the emit work lists.
  * One block; every thread owns OFF_PER consecutive halos per round, the three list cursors are
  * scanned together with the offsets (packed 3 x 16 bit), so the lists need no atomics. */
-#define OFF_PER 8
+#define OFF_PER 4
 template <typename T> __device__ __forceinline__ T block_scan_incl_1024(T v, T *ws, int lane, int w)
 {
 #pragma unroll
@@ -1236,6 +1236,7 @@ __global__ void __launch_bounds__(1024) k_offsets(const int32_t *__restrict__ ou
                                                   int32_t *huge_list = nullptr, uint32_t *huge_n = nullptr)
 {
     __shared__ unsigned long long ws[32], ws2[32];
+    __shared__ unsigned long long stage[1024 * OFF_PER];   /* offsets of a round, written out coalesced */
     __shared__ unsigned long long carry;
     __shared__ uint32_t carry_c[3];                /* entries already in the small / big / huge list */
     if (threadIdx.x == 0) { carry = 0ull; carry_c[0] = carry_c[1] = carry_c[2] = 0u; }
@@ -1245,9 +1246,15 @@ __global__ void __launch_bounds__(1024) k_offsets(const int32_t *__restrict__ ou
         const int i0 = b0 + threadIdx.x * OFF_PER;
         int32_t n[OFF_PER];
         unsigned long long v = 0ull, cls = 0ull;
+        if (i0 + OFF_PER <= nh) {                            /* 16 contiguous bytes per thread */
+            const int4 n4 = *reinterpret_cast<const int4 *>(out_n + i0);
+            n[0] = n4.x; n[1] = n4.y; n[2] = n4.z; n[3] = n4.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < OFF_PER; ++k) n[k] = (i0 + k < nh) ? out_n[i0 + k] : 0;
+        }
 #pragma unroll
         for (int k = 0; k < OFF_PER; ++k) {
-            n[k] = (i0 + k < nh) ? out_n[i0 + k] : 0;
             if (n[k] > 0) {
                 v += (unsigned long long)n[k];
                 const bool sm = n[k] <= emit_small_max, bg = !sm && (n[k] < emit_huge_min || !huge_list);
@@ -1257,14 +1264,14 @@ __global__ void __launch_bounds__(1024) k_offsets(const int32_t *__restrict__ ou
         const unsigned long long incl = block_scan_incl_1024(v, ws, lane, w);
         const unsigned long long cincl = block_scan_incl_1024(cls, ws2, lane, w);
         unsigned long long run = carry + incl - v;
-        const unsigned long long cex = cincl - cls;          /* per round at most 8192 per list: 3 x 16 bits */
+        const unsigned long long cex = cincl - cls;          /* per round at most 4096 per list: 3 x 16 bits */
         uint32_t ps = carry_c[0] + (uint32_t)(cex & 0xFFFFull);
         uint32_t pb = carry_c[1] + (uint32_t)((cex >> 16) & 0xFFFFull);
         uint32_t ph = carry_c[2] + (uint32_t)((cex >> 32) & 0xFFFFull);
 #pragma unroll
         for (int k = 0; k < OFF_PER; ++k) {
+            stage[threadIdx.x * OFF_PER + k] = run;
             if (i0 + k < nh) {
-                out_off[i0 + k] = run;
                 if (n[k] > 0) {
                     run += (unsigned long long)n[k];
                     const bool sm = n[k] <= emit_small_max, bg = !sm && (n[k] < emit_huge_min || !huge_list);
@@ -1275,6 +1282,7 @@ __global__ void __launch_bounds__(1024) k_offsets(const int32_t *__restrict__ ou
             }
         }
         __syncthreads();
+        for (int k = threadIdx.x; k < 1024 * OFF_PER && b0 + k < nh; k += 1024) out_off[b0 + k] = stage[k];
         if (threadIdx.x == 1023) {
             carry += incl;
             carry_c[0] += (uint32_t)(cincl & 0xFFFFull);
