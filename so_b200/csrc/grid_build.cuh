@@ -20,17 +20,19 @@
  */
 #pragma once
 
-#define SCAN_TILE 2048   /* 256 threads x 8 */
+#define SCAN_TILE 1024   /* 256 threads x 4 consecutive entries, moved as uint4 */
 
 __global__ void __launch_bounds__(256) k_scan_reduce(const uint32_t *__restrict__ a, int64_t n,
                                                      uint32_t *__restrict__ bsum)
 {
     __shared__ uint32_t ws[8];
-    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * 4;
     uint32_t s = 0;
-    for (int k = 0; k < 8; ++k) {
-        int64_t i = base + k * 256 + threadIdx.x;
-        if (i < n) s += a[i];
+    if (base + 4 <= n) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(a + base);
+        s = v.x + v.y + v.z + v.w;
+    } else {
+        for (int k = 0; k < 4; ++k) if (base + k < n) s += a[base + k];
     }
     s = __reduce_add_sync(0xFFFFFFFFu, s);
     if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
@@ -82,14 +84,19 @@ __global__ void __launch_bounds__(256) k_scan_apply(const uint32_t *a, int64_t n
                                                     uint32_t *out, uint32_t *copy)
 {
     __shared__ uint32_t ws[8];
-    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * 8;
-    uint32_t v[8], s = 0;
-    for (int k = 0; k < 8; ++k) {
-        v[k] = (base + k < n) ? a[base + k] : 0u;
-        s += v[k];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * 4;
+    const bool whole = base + 4 <= n;
+    uint32_t v[4];
+    if (whole) {
+        const uint4 x4 = *reinterpret_cast<const uint4 *>(a + base);
+        v[0] = x4.x; v[1] = x4.y; v[2] = x4.z; v[3] = x4.w;
+    } else {
+        for (int k = 0; k < 4; ++k) v[k] = (base + k < n) ? a[base + k] : 0u;
     }
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t s = v[0] + v[1] + v[2] + v[3];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t x = s;
+#pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o);
         if (lane >= o) x += t;
@@ -98,15 +105,21 @@ __global__ void __launch_bounds__(256) k_scan_apply(const uint32_t *a, int64_t n
     __syncthreads();
     uint32_t off = bsum[blockIdx.x];
     for (int k = 0; k < w; ++k) off += ws[k];
-    uint32_t run = off + x - s;
-    for (int k = 0; k < 8; ++k) {
-        if (base + k < n) {
-            out[base + k] = run;
-            if (copy) copy[base + k] = run;
-        }
-        run += v[k];
+    uint4 e;
+    e.x = off + x - s; e.y = e.x + v[0]; e.z = e.y + v[1]; e.w = e.z + v[2];
+    const uint32_t run = e.w + v[3];
+    if (whole) {
+        *reinterpret_cast<uint4 *>(out + base) = e;
+        if (copy) *reinterpret_cast<uint4 *>(copy + base) = e;
+    } else {
+        const uint32_t ee[4] = {e.x, e.y, e.z, e.w};
+        for (int k = 0; k < 4; ++k)
+            if (base + k < n) {
+                out[base + k] = ee[k];
+                if (copy) copy[base + k] = ee[k];
+            }
     }
-    if (base <= n - 1 && n - 1 < base + 8) out[n] = run;   /* sentinel: total (= particles kept) */
+    if (base <= n - 1 && n - 1 < base + 4) out[n] = run;   /* sentinel: total (= particles kept) */
 }
 
 /* the same exclusive scan by ONE block (bucket tables up to a few 10^5 entries: one launch instead of

@@ -1991,6 +1991,7 @@ struct sogpu {
     size_t lvl_cap[4];
     float cls_small_max, cls_huge_min;   /* expected ball population: warp / 256-thread CTA / 1024-thread CTA */
     int emit_small_max, emit_huge_min;   /* same split for the member emission, by N_Delta */
+    size_t scan1_max;                /* bucket tables up to this many entries are scanned by one block */
     bool use_tma;                    /* sogpu_set_tma_staging */
     double mask_rmin_cells;          /* focus masks: minimum half-width per halo, in coarse cells */
     bool indexed;                    /* d_in is {x,y,z,global index} of one rank's share (domain runs) */
@@ -2137,6 +2138,8 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     h->two_level = -1;
     h->first_ball = 2;
     h->mask_rmin_cells = 0.75;
+    h->scan1_max = (size_t)1 << 18;
+    if (const char *e = getenv("SOGPU_SCAN1_MAX")) h->scan1_max = (size_t)atoll(e);
     if (const char *e = getenv("SOGPU_TMA")) h->use_tma = atoi(e) != 0;
     if (const char *e = getenv("SOGPU_MASK_RMIN")) h->mask_rmin_cells = atof(e);
     h->cls_small_max = 1024.0f; h->cls_huge_min = 4096.0f;
@@ -2675,8 +2678,8 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         }
         if (l == 0) { int rc = launch_mass_table(h); if (rc) return rc; }
         {
-            ProfScope p(h, KID_LVL_SCAN, 12.0 * (double)M, M <= ((size_t)1 << 18) ? 1 : 3);
-            if (M <= ((size_t)1 << 18)) {
+            ProfScope p(h, KID_LVL_SCAN, 12.0 * (double)M, M <= h->scan1_max ? 1 : 3);
+            if (M <= h->scan1_max) {
                 k_scan_one<<<1, 1024, 0, s>>>(h->d_lvl_cursor[l], (int64_t)M, h->d_lvl_start[l], h->d_lvl_cursor[l]);
             } else {
                 int64_t nt = ((int64_t)M + SCAN_TILE - 1) / SCAN_TILE;

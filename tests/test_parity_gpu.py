@@ -165,6 +165,17 @@ def test_cell_size_does_not_change_results():
         assert np.array_equal(r["members"], base["members"])
 
 
+def test_multi_block_table_scan(monkeypatch):
+    """Bucket tables above 2^18 entries (1024^3-size builds) are scanned by three kernels instead of one
+    block: forced here on a small snapshot (SOGPU_SCAN1_MAX=0)."""
+    s = synth.make_snapshot(64 ** 3, 80, seed=43, nmax=6000)
+    base = run_gpu(s.pos, s.mass, s.centers, s.rgtp, 200.0)
+    monkeypatch.setenv("SOGPU_SCAN1_MAX", "0")
+    r = run_gpu(s.pos, s.mass, s.centers, s.rgtp, 200.0)
+    assert_so_equal(r, base["rvir"], base["mvir"], base["ndelta"])
+    assert np.array_equal(r["members"], base["members"])
+
+
 def test_build_strategies_agree():
     """Single counting sort vs coarse-partition-first build: identical results."""
     s = synth.make_snapshot(80 ** 3, 60, seed=42, nmax=8000)
