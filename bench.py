@@ -472,6 +472,8 @@ def run_ours(args):
                           "kernel_ms_per_step": foc_prof},
         "evals_per_s": evals_total / (ms_step * 1e-3), "evals_per_step": evals_total,
         "members_per_step": members_total, "halos_resolved_rank0": ok,
+        # work inflation: r^2 evaluations over the minimum sum(N_Delta + 1)
+        "evals_over_min": evals_total / max(members_total + h_total, 1.0),
         "e2e": {"value": h_total / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
                 "rank0_breakdown_ms": {k: v / args.steps for k, v in e2e_parts.items()}},
