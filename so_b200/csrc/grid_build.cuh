@@ -262,17 +262,30 @@ __global__ void __launch_bounds__(256) k_lvl_hist(const float4 *__restrict__ in4
             for (int c = threadIdx.x; c < C; c += 256) sh[c] = 0u;
             __syncthreads();
             if (FIRST) {
-                for (uint32_t i = pos + threadIdx.x; i < send; i += 256) {
-                    bool kept = true;
-                    float4 q = ld_stream(in4 + i);
-                    uint32_t key = cell_key_kept(q, g, kept);
-                    if (!g.indexed) {                /* (.w of indexed input is the particle's global index) */
-                        uint32_t mo = (q.w >= 0.0f) ? __float_as_uint(q.w) : 0xFFFFFFFEu;
-                        if (!(q.w >= 0.0f)) mn = 0u; /* negative / NaN mass: treated as "unequal" */
-                        mn = min(mn, mo);
-                        mx = max(mx, mo);
+                /* 8 particles per thread at a time: all loads in flight before the first shared-memory atomic */
+                constexpr int PPT = 8;
+                for (uint32_t i0 = pos + threadIdx.x; i0 < send; i0 += 256 * PPT) {
+                    float4 q[PPT];
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k) {
+                        uint32_t i = i0 + k * 256;
+                        if (i < send) q[k] = ld_stream(in4 + i);
                     }
-                    if (kept) atomicAdd(&sh[(key >> lv.shift) & cmask], 1u);
+#pragma unroll
+                    for (int k = 0; k < PPT; ++k) {
+                        uint32_t i = i0 + k * 256;
+                        if (i < send) {
+                            bool kept = true;
+                            uint32_t key = cell_key_kept(q[k], g, kept);
+                            if (!g.indexed) {        /* (.w of indexed input is the particle's global index) */
+                                uint32_t mo = (q[k].w >= 0.0f) ? __float_as_uint(q[k].w) : 0xFFFFFFFEu;
+                                if (!(q[k].w >= 0.0f)) mn = 0u; /* negative / NaN mass: treated as "unequal" */
+                                mn = min(mn, mo);
+                                mx = max(mx, mo);
+                            }
+                            if (kept) atomicAdd(&sh[(key >> lv.shift) & cmask], 1u);
+                        }
+                    }
                 }
             } else {
                 /* keys only: 16 per thread, all loads in flight before the first shared-memory atomic */
