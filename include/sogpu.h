@@ -241,6 +241,9 @@ typedef struct {
     int64_t n_in_grid;           /* particles the last build sorted (< n_particles if focused) */
 } sogpu_stats_t;
 int sogpu_get_stats(sogpu_t *h, sogpu_stats_t *out);
+/* Debug (process started with SOGPU_DEBUG_TIMELINE=1): device clock in ns of the first CTA start and the
+ * last CTA end of the last call's 1024-thread, 256-thread, warp and deferred query kernels (8 values used). */
+int sogpu_debug_timeline(sogpu_t *h, uint64_t *out16);
 
 /* ---- per-kernel timing (CUDA events on the handle's stream) ------------------------------------ */
 

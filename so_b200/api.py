@@ -27,7 +27,7 @@ SYMBOLS = [
     "sogpu_finish_host", "sogpu_keep_member_d2", "sogpu_profile_enable", "sogpu_profile_kernels",
     "sogpu_profile_name", "sogpu_profile_read", "sogpu_upload_particles",
     "sogpu_set_build_mode", "sogpu_ball_gather_batch",
-    "sogpu_profile_bytes", "sogpu_build_grid_for", "sogpu_build_grid_for_device", "sogpu_set_first_ball", "sogpu_set_tma_staging", "sogpu_vcirc", "sogpu_tag_members", "sogpu_host_alloc", "sogpu_host_free", "sogpu_ingest_begin",
+    "sogpu_profile_bytes", "sogpu_build_grid_for", "sogpu_build_grid_for_device", "sogpu_set_first_ball", "sogpu_set_tma_staging", "sogpu_debug_timeline", "sogpu_vcirc", "sogpu_tag_members", "sogpu_host_alloc", "sogpu_host_free", "sogpu_ingest_begin",
     "sogpu_ingest_records", "sogpu_ingest_end", "sogpu_domain_mask_words", "sogpu_domain_mask",
     "sogpu_domain_route_count", "sogpu_domain_route_scatter", "sogpu_set_particles_device_indexed",
     "sogpu_peer_alloc", "sogpu_peer_open", "sogpu_peer_close", "sogpu_peer_free",
@@ -93,6 +93,8 @@ def lib():
               L.sogpu_set_particles_device_indexed, L.sogpu_peer_alloc, L.sogpu_peer_open, L.sogpu_peer_close,
               L.sogpu_peer_free):
         f.restype = C.c_int
+    L.sogpu_debug_timeline.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.sogpu_debug_timeline.restype = C.c_int
     L.sogpu_set_tma_staging.argtypes = [vp, C.c_int]
     L.sogpu_set_tma_staging.restype = C.c_int
     L.sogpu_set_first_ball.argtypes = [vp, C.c_int]
@@ -201,6 +203,11 @@ class SoGpu:
 
     def set_stream(self, stream):
         _check(lib().sogpu_set_stream(self._h, C.c_void_p(int(stream) if stream else 0)))
+
+    def debug_timeline(self):
+        out = (C.c_uint64 * 16)()
+        _check(lib().sogpu_debug_timeline(self._h, out))
+        return list(out)
 
     def set_tma_staging(self, on=True):
         """1024-thread class: TMA bulk-copy staging instead of per-thread loads (results identical)."""

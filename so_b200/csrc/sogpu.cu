@@ -47,14 +47,16 @@
 #define BKT_AVG 1024   /* mean particles per final bucket */
 #endif
 #ifndef Q32_MINB
-#define Q32_MINB 1      /* resident CTAs per SM the warp-per-halo kernel is compiled for */
+#define Q32_MINB 3      /* resident CTAs per SM the warp-per-halo kernel is compiled for: 80 registers, so that one
+                         * of its CTAs fits next to a 256-thread-class CTA (<= 128 registers) on an SM — at 118 + 130
+                         * registers the two excluded each other by 0.1 % of the register file */
 #endif
 template <int NT> struct Cfg;
 template <> struct Cfg<32> {   /* warp per halo */
     static const int CAP = 256, WTARGET = 128, NLEV = 1, GROUPS = 8, MINB = Q32_MINB;
 };
 template <> struct Cfg<256> {  /* block per halo */
-    static const int CAP = 4096, WTARGET = 1024, NLEV = 4, GROUPS = 1, MINB = 1;
+    static const int CAP = 4096, WTARGET = 1024, NLEV = 4, GROUPS = 1, MINB = 2;
 };
 template <> struct Cfg<1024> { /* one full-SM block per halo: cluster-size halos (>= ~10^5 particles) */
     static const int CAP = 4096, WTARGET = 2048, NLEV = 4, GROUPS = 1, MINB = 1;
@@ -1057,7 +1059,16 @@ struct QueryArgs {
     unsigned long long *evals;     /* [0] histogram pass, [1] other passes */
     uint32_t *flags;               /* bit0 member buffer too small, bit1 emit count mismatch */
     const so_mass_table *mt;
+    unsigned long long *timeline;  /* debug (SOGPU_DEBUG_TIMELINE): [2*slot] first CTA start, [2*slot+1] last CTA end, in ns */
+    int tl_slot;
 };
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 template <int NT>
 __device__ __forceinline__ uint32_t next_item(uint32_t *counter, GroupSmem<NT> &sm, int tid)
@@ -1089,6 +1100,7 @@ __global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS, Cfg<NT>::MINB) k_so_query
     __syncthreads();
 
     tma_stage_init<NT>(sm, tid, a.g.use_tma);
+    if (a.timeline && threadIdx.x == 0) atomicMin(&a.timeline[2 * a.tl_slot], global_ns());
     const uint32_t nlist = *a.list_n;
     uint32_t ev_hist = 0, ev_other = 0;
     for (;;) {
@@ -1114,6 +1126,7 @@ __global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS, Cfg<NT>::MINB) k_so_query
             a.out_key[h] = res.key_j;
         }
     }
+    if (a.timeline && threadIdx.x == 0) atomicMax(&a.timeline[2 * a.tl_slot + 1], global_ns());
     ev_hist = __reduce_add_sync(0xFFFFFFFFu, ev_hist);
     ev_other = __reduce_add_sync(0xFFFFFFFFu, ev_other);
     if ((threadIdx.x & 31) == 0) {
@@ -1991,6 +2004,8 @@ struct sogpu {
     size_t lvl_cap[4];
     float cls_small_max, cls_huge_min;   /* expected ball population: warp / 256-thread CTA / 1024-thread CTA */
     int emit_small_max, emit_huge_min;   /* same split for the member emission, by N_Delta */
+    int qgrid32, qgrid256;           /* persistent CTAs per SM of the warp / 256-thread halo kernels */
+    int qorder;                      /* launch order of the classes behind the 1024-thread one (tuning) */
     size_t scan1_max;                /* bucket tables up to this many entries are scanned by one block */
     bool use_tma;                    /* sogpu_set_tma_staging */
     double mask_rmin_cells;          /* focus masks: minimum half-width per halo, in coarse cells */
@@ -2027,6 +2042,7 @@ struct sogpu {
     bool have_result;
     bool want_d2;
     bool member_overflow;
+    unsigned long long *d_timeline;  /* SOGPU_DEBUG_TIMELINE */
     uint32_t *d_live;                /* focused builds: list of live final buckets (+ its length) */
     size_t live_cap;
     unsigned long long *d_route;     /* domain runs: per-destination counters */
@@ -2139,6 +2155,10 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     h->first_ball = 2;
     h->mask_rmin_cells = 0.75;
     h->scan1_max = (size_t)1 << 18;
+    h->qgrid32 = 4; h->qgrid256 = 1; h->qorder = 0;    /* (measured: pending CTAs of the 256-thread class hold back the warp class) */
+    if (const char *e = getenv("SOGPU_QGRID32")) h->qgrid32 = std::max(1, atoi(e));
+    if (const char *e = getenv("SOGPU_QGRID256")) h->qgrid256 = std::max(1, atoi(e));
+    if (const char *e = getenv("SOGPU_QORDER")) h->qorder = atoi(e);
     if (const char *e = getenv("SOGPU_SCAN1_MAX")) h->scan1_max = (size_t)atoll(e);
     if (const char *e = getenv("SOGPU_TMA")) h->use_tma = atoi(e) != 0;
     if (const char *e = getenv("SOGPU_MASK_RMIN")) h->mask_rmin_cells = atof(e);
@@ -2154,8 +2174,11 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     cudaError_t e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return set_err(SOGPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     h->stream = h->launch_stream = h->own_stream;
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
-        e = cudaStreamCreateWithFlags(&h->aux[k], cudaStreamNonBlocking);
+        /* aux[0] (256-thread class) is served before aux[1] (warp class) when both have CTAs pending */
+        e = cudaStreamCreateWithPriority(&h->aux[k], cudaStreamNonBlocking, k == 0 ? prio_greatest : prio_least);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
@@ -2177,6 +2200,17 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
         e = cudaFuncSetAttribute(k_gen_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<256>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_gen_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<256>());
+    /* The three halo classes must be able to SHARE an SM.  An SM's L1 / shared-memory split is fixed while
+     * it has resident CTAs, so kernels that ask for different splits exclude each other until it drains
+     * (measured with %globaltimer: whichever class started first kept the others out for 70-120 us).
+     * Every query / emit kernel therefore asks for the same (maximum shared memory) carve-out. */
+    {
+        const void *fns[] = {(const void *)k_so_query<32>, (const void *)k_so_query<256>, (const void *)k_so_query<1024>,
+                             (const void *)k_so_emit<32>, (const void *)k_so_emit<256>, (const void *)k_so_emit<1024>};
+        for (const void *f : fns)
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
     if (e != cudaSuccess) {
         cudaStreamDestroy(h->own_stream); delete h;
         return set_err(SOGPU_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -2224,7 +2258,7 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     cudaFree(h->d_mt);
     cudaFree(h->d_vc);
     cudaFree(h->d_route); cudaFree(h->d_route_table); cudaFree(h->d_route_any);
-    cudaFree(h->d_live);
+    cudaFree(h->d_live); cudaFree(h->d_timeline);
     cudaFree(h->d_tag); cudaFree(h->d_tag_index); cudaFree(h->d_dirty);
     cudaFree(h->d_counters);
     cudaFree(h->d_u64);
@@ -2833,7 +2867,7 @@ static int ensure_query(sogpu *h, int32_t nh)
 template <int NT, typename K, typename... Extra>
 static void launch_persistent(sogpu *h, K kernel, const QueryArgs &a, int nh, Extra... extra)
 {
-    int ctas = h->sm_count * 4;
+    int ctas = h->sm_count * (NT == 32 ? h->qgrid32 : NT == 256 ? h->qgrid256 : 1);
     int need = (nh + Cfg<NT>::GROUPS - 1) / Cfg<NT>::GROUPS;
     if (need < ctas) ctas = std::max(need, 1);
     kernel<<<ctas, NT * Cfg<NT>::GROUPS, query_smem_bytes<NT>(h->use_tma), h->launch_stream>>>(a, extra...);
@@ -2873,27 +2907,43 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
     a.flags = h->d_counters + 4;
     a.mt = h->d_mt;
     a.defer_list = h->d_defer; a.defer_n = h->d_counters + 17;
+    a.timeline = nullptr; a.tl_slot = 0;
+    if (getenv("SOGPU_DEBUG_TIMELINE")) {       /* debug: when did each class really start / end on the device */
+        if (!h->d_timeline) CU(cudaMalloc(&h->d_timeline, 16 * sizeof(unsigned long long)));
+        unsigned long long init[16];
+        for (int k = 0; k < 8; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
+        CU(cudaMemcpyAsync(h->d_timeline, init, sizeof(init), cudaMemcpyHostToDevice, s));
+        a.timeline = h->d_timeline;
+    }
 
-    /* the three size classes are independent: run them concurrently (main + two side streams) */
+    /* The three size classes are independent and run concurrently.  ORDER MATTERS: a 1024-thread CTA needs a
+     * whole SM, so the cluster-size class goes first, on the main stream (no event wait in front of it):
+     * measured with %globaltimer, launched behind the warp kernel it started 121 us late because 592
+     * warp-kernel CTAs had filled every SM.  Its CTAs without work leave within microseconds; the 256-thread
+     * class (high-priority side stream) and the warp class (side stream) then fill the other SMs. */
     CU(cudaEventRecord(h->ev_fork, s));
     CU(cudaStreamWaitEvent(h->aux[0], h->ev_fork, 0));
     CU(cudaStreamWaitEvent(h->aux[1], h->ev_fork, 0));
-    /* cluster-size halos: one 1024-thread CTA each */
-    h->launch_stream = h->aux[0];
-    a.list = h->d_huge; a.list_n = h->d_counters + 13; a.work_counter = h->d_counters + 14;
-    { ProfScope p(h, KID_QUERY_HUGE); launch_persistent<1024>(h, k_so_query<1024>, a, std::min(nh, h->sm_count)); }
-    CU(cudaEventRecord(h->ev_join[0], h->aux[0]));
-    /* mid-size halos: one 256-thread CTA each */
-    h->launch_stream = h->aux[1];
-    a.list = h->d_big; a.list_n = h->d_counters + 1; a.work_counter = h->d_counters + 3;
-    { ProfScope p(h, KID_QUERY_BLOCK); launch_persistent<256>(h, k_so_query<256>, a, nh); }
-    CU(cudaEventRecord(h->ev_join[1], h->aux[1]));
-    /* small halos: one warp each; the few it cannot finish go to a CTA kernel right behind it */
     h->launch_stream = s;
-    a.list = h->d_small; a.list_n = h->d_counters + 0; a.work_counter = h->d_counters + 2;
-    { ProfScope p(h, KID_QUERY_WARP); launch_persistent<32>(h, k_so_query<32>, a, nh); }
-    a.list = h->d_defer; a.list_n = h->d_counters + 17; a.work_counter = h->d_counters + 18;
-    { ProfScope p(h, KID_QUERY_BLOCK); launch_persistent<256>(h, k_so_query<256>, a, 64); }
+    a.list = h->d_huge; a.list_n = h->d_counters + 13; a.work_counter = h->d_counters + 14; a.tl_slot = 0;
+    { ProfScope p(h, KID_QUERY_HUGE); launch_persistent<1024>(h, k_so_query<1024>, a, std::min(nh, h->sm_count)); }
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool big_now = (pass == 0) == (h->qorder == 0);
+        if (big_now) {      /* mid-size halos: one 256-thread CTA each */
+            h->launch_stream = h->aux[0];
+            a.list = h->d_big; a.list_n = h->d_counters + 1; a.work_counter = h->d_counters + 3; a.tl_slot = 1;
+            { ProfScope p(h, KID_QUERY_BLOCK); launch_persistent<256>(h, k_so_query<256>, a, nh); }
+            CU(cudaEventRecord(h->ev_join[0], h->aux[0]));
+        } else {            /* small halos: one warp each; the few it cannot finish go to a CTA kernel right behind it */
+            h->launch_stream = h->aux[1];
+            a.list = h->d_small; a.list_n = h->d_counters + 0; a.work_counter = h->d_counters + 2; a.tl_slot = 2;
+            { ProfScope p(h, KID_QUERY_WARP); launch_persistent<32>(h, k_so_query<32>, a, nh); }
+            a.list = h->d_defer; a.list_n = h->d_counters + 17; a.work_counter = h->d_counters + 18; a.tl_slot = 3;
+            { ProfScope p(h, KID_QUERY_BLOCK); launch_persistent<256>(h, k_so_query<256>, a, 64); }
+            CU(cudaEventRecord(h->ev_join[1], h->aux[1]));
+        }
+    }
+    h->launch_stream = s;
     CU(cudaStreamWaitEvent(s, h->ev_join[0], 0));
     CU(cudaStreamWaitEvent(s, h->ev_join[1], 0));
     /* member offsets in catalog order, then the member lists (again three classes side by side) */
@@ -2906,17 +2956,18 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
     CU(cudaEventRecord(h->ev_fork, s));
     CU(cudaStreamWaitEvent(h->aux[0], h->ev_fork, 0));
     CU(cudaStreamWaitEvent(h->aux[1], h->ev_fork, 0));
-    h->launch_stream = h->aux[0];
+    h->launch_stream = s;                                  /* (same order as the solve: whole-SM CTAs first) */
     a.list = h->d_ehuge; a.list_n = h->d_counters + 15; a.work_counter = h->d_counters + 16;
     { ProfScope p(h, KID_EMIT_HUGE); launch_persistent<1024>(h, k_so_emit<1024>, a, std::min(nh, h->sm_count)); }
-    CU(cudaEventRecord(h->ev_join[0], h->aux[0]));
-    h->launch_stream = h->aux[1];
+    h->launch_stream = h->aux[0];
     a.list = h->d_ebig; a.list_n = h->d_counters + 6; a.work_counter = h->d_counters + 8;
     { ProfScope p(h, KID_EMIT_BLOCK); launch_persistent<256>(h, k_so_emit<256>, a, nh); }
-    CU(cudaEventRecord(h->ev_join[1], h->aux[1]));
-    h->launch_stream = s;
+    CU(cudaEventRecord(h->ev_join[0], h->aux[0]));
+    h->launch_stream = h->aux[1];
     a.list = h->d_esmall; a.list_n = h->d_counters + 5; a.work_counter = h->d_counters + 7;
     { ProfScope p(h, KID_EMIT_WARP); launch_persistent<32>(h, k_so_emit<32>, a, nh); }
+    CU(cudaEventRecord(h->ev_join[1], h->aux[1]));
+    h->launch_stream = s;
     CU(cudaStreamWaitEvent(s, h->ev_join[0], 0));
     CU(cudaStreamWaitEvent(s, h->ev_join[1], 0));
     CU(cudaGetLastError());
@@ -3727,6 +3778,16 @@ extern "C" int sogpu_peer_free(sogpu_t *h, void *ptr)
     if (!h) return set_err(SOGPU_ERR_ARG, "NULL handle");
     CU(cudaSetDevice(h->device));
     CU(cudaFree(ptr));
+    return SOGPU_OK;
+}
+
+/* debug: device clock (ns) of the first CTA start / last CTA end of the huge, big, small, deferred query kernels */
+extern "C" int sogpu_debug_timeline(sogpu_t *h, uint64_t *out16)
+{
+    if (!h || !out16 || !h->d_timeline) return set_err(SOGPU_ERR_ARG, "sogpu_debug_timeline: run with SOGPU_DEBUG_TIMELINE=1");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(out16, h->d_timeline, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return SOGPU_OK;
 }
 
