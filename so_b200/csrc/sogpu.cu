@@ -2042,6 +2042,7 @@ struct sogpu {
     bool have_result;
     bool want_d2;
     bool member_overflow;
+    bool build_attr_done;
     unsigned long long *d_timeline;  /* SOGPU_DEBUG_TIMELINE */
     uint32_t *d_live;                /* focused builds: list of live final buckets (+ its length) */
     size_t live_cap;
@@ -2661,7 +2662,8 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
             h->lvl_cap[l] = need;
         }
     }
-    static bool attr_done = false;
+    /* function attributes belong to the device's context: once per handle, not once per process */
+    bool &attr_done = h->build_attr_done;
     const size_t part_smem = (size_t)LVL_T * (16 + 4 + 2 + 2 + 2);
     const size_t bkt_smem = (size_t)BKT_CAP * (16 + 2 + 2 + 2) + (size_t)BKT_CELLS * 4;
     if (!attr_done) {
