@@ -85,6 +85,9 @@ int sogpu_set_particles_host(sogpu_t *h, const void *pos, size_t pos_stride, con
  * With a page-locked buffer (sogpu_host_alloc) the copy is an asynchronous DMA that overlaps the
  * caller's next read; such a buffer may be refilled once the NEXT sogpu_ingest_records / _end call has
  * returned, i.e. the caller alternates two buffers.  Pageable buffers work too (synchronous copy). */
+/* sogpu_ingest_keep_velocities(h, 1) before sogpu_ingest_begin: fields 4..6 of every record (vx, vy, vz) are
+ * kept on the device as well, for sogpu_vcm. */
+int sogpu_ingest_keep_velocities(sogpu_t *h, int on);
 void *sogpu_host_alloc(size_t bytes);
 void sogpu_host_free(void *p);
 int sogpu_ingest_begin(sogpu_t *h, int64_t n_total, const float period[3], const float center[3]);
@@ -182,6 +185,14 @@ int sogpu_ball_gather_batch(sogpu_t *h, const float *centers, const float *ball2
 int sogpu_vcirc(sogpu_t *h, const float *centers, const float *rvir, const float *mvir, int32_t nh,
                 float G, int32_t nMembers, float *vcirc, float *rmass, float *rmax, float *vmax,
                 float *profile);
+
+/* ---- _VcmParticles replacement (kd2.c:595-609) -------------------------------------------------- */
+
+/* Centre-of-mass velocity of every group of the last sogpu_so() call (same nh, sogpu_keep_member_d2 on):
+ * vcm[3*i+l] = (sum over the members of group i, in ascending (fDist2, index) order, of fl(m * v[l])) / mvir[i],
+ * the reference's sequential fp32 sum; zeros where mvir[i] <= 0.  Needs the velocities on the device
+ * (streaming ingest with sogpu_ingest_keep_velocities). */
+int sogpu_vcm(sogpu_t *h, const float *mvir, int32_t nh, float *vcm);
 
 /* ---- kdTagParticles, order-independent part (kd2.c:663-720) ---------------------------------- */
 

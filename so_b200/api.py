@@ -27,7 +27,7 @@ SYMBOLS = [
     "sogpu_finish_host", "sogpu_keep_member_d2", "sogpu_profile_enable", "sogpu_profile_kernels",
     "sogpu_profile_name", "sogpu_profile_read", "sogpu_upload_particles",
     "sogpu_set_build_mode", "sogpu_ball_gather_batch",
-    "sogpu_profile_bytes", "sogpu_build_grid_for", "sogpu_build_grid_for_device", "sogpu_set_first_ball", "sogpu_set_tma_staging", "sogpu_debug_timeline", "sogpu_vcirc", "sogpu_tag_members", "sogpu_host_alloc", "sogpu_host_free", "sogpu_ingest_begin",
+    "sogpu_profile_bytes", "sogpu_build_grid_for", "sogpu_build_grid_for_device", "sogpu_set_first_ball", "sogpu_set_tma_staging", "sogpu_debug_timeline", "sogpu_vcirc", "sogpu_tag_members", "sogpu_vcm", "sogpu_ingest_keep_velocities", "sogpu_host_alloc", "sogpu_host_free", "sogpu_ingest_begin",
     "sogpu_ingest_records", "sogpu_ingest_end", "sogpu_domain_mask_words", "sogpu_domain_mask",
     "sogpu_domain_route_count", "sogpu_domain_route_scatter", "sogpu_set_particles_device_indexed",
     "sogpu_peer_alloc", "sogpu_peer_open", "sogpu_peer_close", "sogpu_peer_free",
@@ -70,6 +70,10 @@ def lib():
     L.sogpu_vcirc.restype = C.c_int
     L.sogpu_tag_members.argtypes = [vp, i32p, C.c_int32, C.POINTER(C.c_ubyte), i32p]
     L.sogpu_tag_members.restype = C.c_int
+    L.sogpu_vcm.argtypes = [vp, fp, C.c_int32, fp]
+    L.sogpu_vcm.restype = C.c_int
+    L.sogpu_ingest_keep_velocities.argtypes = [vp, C.c_int]
+    L.sogpu_ingest_keep_velocities.restype = C.c_int
     L.sogpu_ingest_begin.argtypes = [vp, C.c_int64, fp, fp]
     L.sogpu_ingest_begin.restype = C.c_int
     L.sogpu_ingest_records.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32]
@@ -389,8 +393,17 @@ class SoGpu:
         self._last_h = h
         return out
 
-    def ingest_records(self, blocks, period=(1.0, 1.0, 1.0), center=(0.0, 0.0, 0.0), big_endian=False, chunk=1 << 16):
+    def vcm(self, mvir):
+        """_VcmParticles of the last so() call (velocities kept by ingest_records(keep_velocities=True))."""
+        mvir = np.ascontiguousarray(mvir, np.float32)
+        out = np.zeros((len(mvir), 3), np.float32)
+        _check(lib().sogpu_vcm(self._h, _fp(mvir), len(mvir), _fp(out)))
+        return out
+
+    def ingest_records(self, blocks, period=(1.0, 1.0, 1.0), center=(0.0, 0.0, 0.0), big_endian=False, chunk=1 << 16,
+                       keep_velocities=False):
         """Raw TIPSY record blocks [(float32 array (n, floats_per_record)), ...] in file order -> device."""
+        _check(lib().sogpu_ingest_keep_velocities(self._h, 1 if keep_velocities else 0))
         n = sum(len(b) for b in blocks)
         per = (C.c_float * 3)(*period)
         cen = (C.c_float * 3)(*center)

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) k_expand_xyz(const float *__restrict__ xy
  * x, y, z (gas 12, dark 9, star 11 floats: tipsydefs.h:6-37); `swap` = the file is XDR / big-endian
  * (-std, kd2.c:32-44,369,385,401), the byte swap happens here instead of in xdr_float. */
 __global__ void __launch_bounds__(256) k_ingest_records(const uint32_t *__restrict__ raw, int64_t count, int nf, int swap,
-                                                        float4 *__restrict__ dst)
+                                                        float4 *__restrict__ dst, float4 *__restrict__ vel)
 {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
@@ -224,6 +224,11 @@ __global__ void __launch_bounds__(256) k_ingest_records(const uint32_t *__restri
         uint32_t m = __ldg(r), x = __ldg(r + 1), y = __ldg(r + 2), z = __ldg(r + 3);
         if (swap) { m = __byte_perm(m, 0, 0x0123); x = __byte_perm(x, 0, 0x0123); y = __byte_perm(y, 0, 0x0123); z = __byte_perm(z, 0, 0x0123); }
         dst[i] = make_float4(__uint_as_float(x), __uint_as_float(y), __uint_as_float(z), __uint_as_float(m));
+        if (vel) {                                           /* fields 4..6 of every record type: vx, vy, vz */
+            uint32_t vx = __ldg(r + 4), vy = __ldg(r + 5), vz = __ldg(r + 6);
+            if (swap) { vx = __byte_perm(vx, 0, 0x0123); vy = __byte_perm(vy, 0, 0x0123); vz = __byte_perm(vz, 0, 0x0123); }
+            vel[i] = make_float4(__uint_as_float(vx), __uint_as_float(vy), __uint_as_float(vz), 0.0f);
+        }
     }
 }
 
@@ -1935,6 +1940,41 @@ __global__ void __launch_bounds__(256) k_tag_settle(const unsigned long long *__
     }
 }
 
+/* _VcmParticles (kd2.c:595-609): vcm[l] = (sum over the members, in sorted order, of fl(m * v[l])) / Mvir,
+ * a sequential fp32 sum per group.  One thread per group walks its (r^2, index)-sorted member list; the
+ * loads of 8 members are issued together, the adds stay in list order. */
+__global__ void __launch_bounds__(128) k_vcm(const unsigned long long *__restrict__ off, const int32_t *__restrict__ mem,
+                                             const float4 *__restrict__ in, const float4 *__restrict__ vel,
+                                             const float *__restrict__ mvir, int nh, float *__restrict__ vcm)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nh) return;
+    const unsigned long long a = off[h], b = off[h + 1];
+    float vx = 0.0f, vy = 0.0f, vz = 0.0f;
+    for (unsigned long long k0 = a; k0 < b; k0 += 8) {
+        float4 v[8];
+        float m[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (k0 + u < b) {
+                const int32_t p = __ldg(mem + k0 + u);
+                v[u] = __ldg(vel + p);
+                m[u] = __ldg(&in[p].w);
+            }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (k0 + u < b) {
+                vx = __fadd_rn(vx, __fmul_rn(m[u], v[u].x));
+                vy = __fadd_rn(vy, __fmul_rn(m[u], v[u].y));
+                vz = __fadd_rn(vz, __fmul_rn(m[u], v[u].z));
+            }
+    }
+    const float mv = mvir[h];
+    vcm[3 * h + 0] = __fdiv_rn(vx, mv);
+    vcm[3 * h + 1] = __fdiv_rn(vy, mv);
+    vcm[3 * h + 2] = __fdiv_rn(vz, mv);
+}
+
 /* member lists -> sortable keys and back: ascending (fDist2 bits, original index) is the order the
  * reference's qsort(CmpList) + stable merge gives for distinct r^2 (kd2.c:425-435,781) */
 __global__ void __launch_bounds__(256) k_member_keys(const int32_t *__restrict__ idx, const float *__restrict__ d2,
@@ -1991,6 +2031,8 @@ struct sogpu {
     uint32_t *d_massmm;
     float *d_raw;                    /* staging of raw xyz triplets (pinned-host fast path) */
     void *d_ingest[2];               /* streaming ingest: raw record chunks */
+    float4 *d_vel;                   /* velocities {vx,vy,vz,0} in file order, when the ingest was asked to keep them */
+    bool ingest_want_vel;
     size_t ingest_cap[2];
     cudaEvent_t ingest_ev[2];
     int64_t ingest_done;
@@ -2251,7 +2293,7 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     cudaFree(h->d_in_owned);
     cudaFree(h->d_massmm);
     cudaFree(h->d_raw);
-    cudaFree(h->d_ingest[0]); cudaFree(h->d_ingest[1]);
+    cudaFree(h->d_ingest[0]); cudaFree(h->d_ingest[1]); cudaFree(h->d_vel);
     for (int k = 0; k < 2; ++k) if (h->ingest_ev[k]) cudaEventDestroy(h->ingest_ev[k]);
     cudaFree(h->d_mask);
     cudaFree(h->d_tmp4); cudaFree(h->d_key[0]); cudaFree(h->d_key[1]);
@@ -2472,6 +2514,8 @@ extern "C" int sogpu_ingest_begin(sogpu_t *h, int64_t n_total, const float perio
         h->d_in_cap = n_total;
     }
     h->d_in = nullptr;                     /* set by sogpu_ingest_end */
+    cudaFree(h->d_vel); h->d_vel = nullptr;
+    if (h->ingest_want_vel) CU(cudaMalloc(&h->d_vel, (size_t)n_total * sizeof(float4)));
     h->ingest_done = 0;
     h->ingest_slot = 0;
     h->ingest_prev_ev_valid = false;
@@ -2507,8 +2551,9 @@ extern "C" int sogpu_ingest_records(sogpu_t *h, const void *records, int64_t cou
     (void)pinned;
     CU(cudaMemcpyAsync(h->d_ingest[slot], records, bytes, cudaMemcpyHostToDevice, s));
     const int grid = (int)std::min<int64_t>((count + 255) / 256, (int64_t)h->sm_count * 8);
+    if (h->d_vel && floats_per_record < 7) return set_err(SOGPU_ERR_ARG, "sogpu_ingest_records: records without velocity fields");
     k_ingest_records<<<grid, 256, 0, s>>>((const uint32_t *)h->d_ingest[slot], count, floats_per_record, big_endian ? 1 : 0,
-                                          h->d_in_owned + h->ingest_done);
+                                          h->d_in_owned + h->ingest_done, h->d_vel ? h->d_vel + h->ingest_done : nullptr);
     CU(cudaGetLastError());
     CU(cudaEventRecord(h->ingest_ev[slot], s));
     h->ingest_prev_ev_valid = true;
@@ -3790,6 +3835,51 @@ extern "C" int sogpu_debug_timeline(sogpu_t *h, uint64_t *out16)
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaMemcpy(out16, h->d_timeline, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_ingest_keep_velocities(sogpu_t *h, int on)
+{
+    if (!h) return set_err(SOGPU_ERR_ARG, "NULL handle");
+    h->ingest_want_vel = on != 0;
+    return SOGPU_OK;
+}
+
+/* _VcmParticles for every group of the last sogpu_so() call whose mvir[i] > 0 (others: zeros). */
+extern "C" int sogpu_vcm(sogpu_t *h, const float *mvir, int32_t nh, float *vcm)
+{
+    if (!h || !mvir || !vcm || nh <= 0) return set_err(SOGPU_ERR_ARG, "sogpu_vcm: bad argument");
+    if (!h->have_result || h->last_h != nh) return set_err(SOGPU_ERR_ARG, "sogpu_vcm: needs the member lists of a sogpu_so() call over the same %d groups", nh);
+    if (!h->d_vel || h->d_in != h->d_in_owned || h->indexed)
+        return set_err(SOGPU_ERR_ARG, "sogpu_vcm: velocities are not on the device (sogpu_ingest_keep_velocities before sogpu_ingest_begin)");
+    if (!h->want_d2) return set_err(SOGPU_ERR_ARG, "sogpu_vcm: call sogpu_keep_member_d2(h,1) before sogpu_so (the sum runs in r^2 order)");
+    CU(cudaSetDevice(h->device));
+    int rc = fetch_stats(h);
+    if (rc) return rc;
+    const size_t tot = (size_t)h->stats.last_members;
+    if (!h->members_sorted) {
+        rc = sort_members_device(h, nh, tot);
+        if (rc) return rc;
+        h->members_sorted = true;
+    }
+    const size_t per = 4;
+    if ((size_t)nh * per > h->vc_cap) {
+        cudaFree(h->d_vc); h->d_vc = nullptr; h->vc_cap = 0;
+        CU(cudaMalloc(&h->d_vc, (size_t)nh * per * sizeof(float)));
+        h->vc_cap = (size_t)nh * per;
+    }
+    rc = ensure_pinned(h, (size_t)nh * per * sizeof(float));
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    float *pin = (float *)h->h_pin;
+    memcpy(pin, mvir, (size_t)nh * sizeof(float));
+    CU(cudaMemcpyAsync(h->d_vc, pin, (size_t)nh * sizeof(float), cudaMemcpyHostToDevice, s));
+    { ProfScope p(h, KID_VCIRC); k_vcm<<<(nh + 127) / 128, 128, 0, s>>>(h->d_out_off, h->d_members, h->d_in, h->d_vel, h->d_vc, nh, h->d_vc + nh); }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(pin + nh, h->d_vc + nh, (size_t)nh * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    for (int32_t i = 0; i < nh; ++i)
+        for (int l = 0; l < 3; ++l) vcm[3 * i + l] = mvir[i] > 0.0f ? pin[nh + 3 * (size_t)i + l] : 0.0f;
     return SOGPU_OK;
 }
 

@@ -183,19 +183,20 @@ int kdReadTipsy(KD kd, FILE *fp, int bStandard)
     kd->nParticles = kd->nDark + kd->nGas + kd->nStar;
     n = (size_t)(kd->nParticles > 0 ? kd->nParticles : 1);
     kd->p.fMass = (float *)malloc(n * sizeof(float));
-    kd->p.v = kd->bSkipVcm ? NULL : (float *)malloc(n * 3 * sizeof(float));   /* only _VcmParticles reads it */
+    kd->p.v = NULL;                                 /* velocities stay on the device (sogpu_vcm), see below */
     kd->p.r = kd->bPot ? (float *)malloc(n * 3 * sizeof(float)) : NULL;       /* only -pot reads these two  */
     kd->p.fPhi = kd->bPot ? (float *)malloc(n * sizeof(float)) : NULL;
     kd->p.iGrp = (int32_t *)calloc(n, sizeof(int32_t));
     kd->p.nSubsumed = (int32_t *)calloc(n, sizeof(int32_t));
     kd->p.nIgnored = (int32_t *)calloc(n, sizeof(int32_t));
     assert(kd->p.fMass && kd->p.iGrp && kd->p.nSubsumed && kd->p.nIgnored);
-    assert((kd->p.v || kd->bSkipVcm) && (!kd->bPot || (kd->p.r && kd->p.fPhi)));
+    assert(!kd->bPot || (kd->p.r && kd->p.fPhi));
     fprintf(stderr, "nDark:%d nGas:%d nStar:%d\n", kd->nDark, kd->nGas, kd->nStar);
     if (kd->nParticles == 0) return 0;
     kdGpu(kd);                                                      /* the records go straight to the device */
     kdPhase(NULL, &tp);
-    if (sogpu_ingest_begin(kd->gpu, kd->nParticles, kd->fPeriod, kd->fCenter)) {
+    if (sogpu_ingest_keep_velocities(kd->gpu, !kd->bSkipVcm) ||            /* _VcmParticles runs on the device */
+        sogpu_ingest_begin(kd->gpu, kd->nParticles, kd->fPeriod, kd->fCenter)) {
         fprintf(stderr, "ERROR in kdReadTipsy (sogpu_ingest_begin): %s\n", sogpu_last_error());
         exit(1);
     }

@@ -419,6 +419,17 @@ void kdSO(KD kd, float rhovir, int nSmooth)
         for (i = 0; i < h; ++i) kd->nGrpsInConflict += in_conflict[i];
     }
     phase("tagging on the device", &tp);
+    if (!kd->bSkipVcm && kd->p.v == NULL) {
+        /* _VcmParticles (kd2.c:595-609, 826) of every resolved group on the device: the same sequential fp32
+         * sum over the (r^2, index)-sorted members; the velocities were kept there by the ingest */
+        float *vcm = (float *)malloc((size_t)h * 3 * sizeof(float));
+        assert(vcm != NULL);
+        if (sogpu_vcm(kd->gpu, mvir, h, vcm)) die_gpu("kdSO (sogpu_vcm)");
+        for (i = 0; i < h; ++i)
+            if (rvir[i] > 0.0f) memcpy(kd->grps[i].vcm, vcm + 3 * (size_t)i, 3 * sizeof(float));
+        free(vcm);
+        phase("vcm on the device", &tp);
+    }
     c.off = off; c.mem = mem; c.slot_of_index = slot_of_index;
     indexx(h, masses, order);
     for (it = 1; it <= h; ++it) {
@@ -428,12 +439,12 @@ void kdSO(KD kd, float rhovir, int nSmooth)
         grp->fMvir = mvir[g];
         if (rvir[g] > 0.0f) {
             if (in_conflict[g]) tag_particles(kd, &c, g);  /* kd2.c:823 */
-            if (!kd->bSkipVcm) vcm_particles(kd, &c, g, mvir[g]);   /* kd2.c:826 (only .sogtp prints it) */
+            if (!kd->bSkipVcm && kd->p.v) vcm_particles(kd, &c, g, mvir[g]);   /* kd2.c:826; host copy of the velocities only */
             if (grp->fRvir > 0.0f) do_vcirc[g] = 1;        /* kd2.c:884: not slurped */
         }
     }
 
-    phase("conflict replay + vcm", &tp);
+    phase("conflict replay", &tp);
     /* kdVcirc for every group that was valid when the reference would have called it */
     {
         int nv = 0, k;

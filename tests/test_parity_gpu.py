@@ -278,6 +278,33 @@ def test_streaming_ingest_of_raw_tipsy_records(big_endian):
     assert np.array_equal(mem, ref["members"]) and np.array_equal(off, ref["member_offset"])
 
 
+def test_vcm_on_the_device_matches_oracle():
+    """sogpu_vcm (_VcmParticles, kd2.c:595-609): the sequential fp32 sum over the sorted members, bit-exact
+    against the oracle's replay (which is pinned to the reference's .sogtp velocities)."""
+    s = synth.make_snapshot(40 ** 3, 30, seed=72, nmax=4000)
+    rng = np.random.default_rng(5)
+    vel = rng.normal(size=(s.n, 3)).astype(np.float32)
+    rec = np.zeros((s.n, 9), np.float32)
+    rec[:, 0] = s.mass
+    rec[:, 1:4] = s.pos
+    rec[:, 4:7] = vel
+    o = po.Oracle(s.pos, s.mass)
+    ref = o.so(s.centers, s.rgtp, np.float32(200.0), 8)
+    t = o.tag(np.arange(1, s.h + 1), s.centers, s.gtp_mass, ref["rvir"], ref["mvir"], ref["member_offset"],
+              ref["members"], vel=vel)
+    g = api.SoGpu()
+    g.ingest_records([rec], keep_velocities=True, chunk=50000)
+    g.build_grid()
+    g.keep_member_d2(True)
+    r = g.so(s.centers, s.rgtp, 200.0)
+    vcm = g.vcm(r["mvir"])
+    g.close()
+    ok = ref["rvir"] > 0
+    assert ok.sum() > 20
+    assert vcm[ok].tobytes() == t["vcm"][ok].tobytes()
+    assert not vcm[~ok].any()
+
+
 def test_pinned_host_memory_fast_paths():
     """Page-locked caller memory is DMA'd directly (xyz triplets / float4) and unpacked on the GPU."""
     import torch
