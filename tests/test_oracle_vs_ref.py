@@ -50,3 +50,43 @@ def test_timed_driver_agrees_with_reference_main(tmp_path):
     b = open(str(tmp_path / "b.sogtp"), "rb").read()
     # bytes 28..31 are the uninitialised padding of `struct dump` (kd2.c:1272,1297)
     assert a[:28] == b[:28] and a[32:] == b[32:]
+
+
+@pytest.mark.skipif(not po.ref_available("so_ref"), reason="reference binary not built")
+def test_oracle_vcirc_and_species_profiles_against_reference_binary(tmp_path):
+    """kdVcirc + kdMassProfile restated in the oracle (so_oracle_vcirc, with the per-species mask) against a
+    live run of the reference on a gas + dark + star snapshot with three different particle masses:
+    .sovcirc columns and the .sodark/.sogas/.sostar rows, which the reference prints with %g."""
+    s = synth.make_snapshot(36 ** 3, 16, seed=79, nmax=3000)
+    ng, ns = s.n // 4, s.n // 10
+    nd = s.n - ng - ns
+    gas = np.zeros(ng, tipsy.GAS_DT)
+    gas["mass"], gas["pos"] = s.mass * np.float32(0.4), s.pos[:ng]
+    dark = tipsy.dark_from_arrays(s.pos[ng:ng + nd], s.mass)
+    star = np.zeros(ns, tipsy.STAR_DT)
+    star["mass"], star["pos"] = s.mass * np.float32(0.13), s.pos[ng + nd:]
+    snap, gtp, out = (str(tmp_path / n) for n in ("s.tipsy", "h.gtp", "o"))
+    tipsy.write_tipsy(snap, s.time, gas=gas, dark=dark, star=star)
+    tipsy.write_gtp(gtp, s.time, s.centers, s.rgtp, s.gtp_mass)
+    po.run_so_ref(snap, gtp, out, delta=120.0, extra=["-gtp", "-all"])
+    mass = np.concatenate([gas["mass"], dark["mass"], star["mass"]]).astype(np.float32)
+    ptype = np.concatenate([np.full(ng, 2), np.full(nd, 1), np.full(ns, 4)]).astype(np.uint8)   # GAS 2, DARK 1, STAR 4
+    o = po.Oracle(s.pos, mass)
+    res = o.so(s.centers, s.rgtp, np.float32(120.0), 8)
+    _, rows = tipsy.parse_sovcirc(out + ".sovcirc")
+    rows = np.array(rows)
+    ok = rows[:, 2] > 0
+    assert ok.sum() >= 12
+    # Mvir / Rvir of the general (mixed-mass) solver, then the Vcirc block
+    np.testing.assert_allclose(res["mvir"][ok], rows[ok, 1], rtol=6e-6)
+    np.testing.assert_allclose(res["rvir"][ok], rows[ok, 2], rtol=6e-6)
+    v = o.vcirc(s.centers, np.where(ok, res["rvir"], 0).astype(np.float32), res["mvir"], 1.0, 8)
+    ours = np.concatenate([v["rmass"], v["rmax"][:, None], v["vmax"][:, None], v["vcirc"]], axis=1)
+    np.testing.assert_allclose(ours[ok], rows[ok, 3:15], rtol=2e-5)      # %g; ties between unequal masses: SURVEY H3
+    for ext, bit in ((".sodark", 1), (".sogas", 2), (".sostar", 4)):
+        _, prow = tipsy.parse_sovcirc(out + ext)
+        prow = np.array(prow)
+        p = o.vcirc(s.centers, np.where(ok, res["rvir"], 0).astype(np.float32), res["mvir"], 1.0, 8,
+                    ptype_of=ptype, ptype_mask=bit)["profile"]
+        np.testing.assert_allclose(p[ok], prow[ok, 1:17], rtol=2e-5, err_msg=ext)
+        assert (p[ok, -1] > 0).all()
