@@ -46,6 +46,9 @@
 #ifndef BKT_AVG
 #define BKT_AVG 1024   /* mean particles per final bucket */
 #endif
+#ifndef Q256_MINB
+#define Q256_MINB 2     /* 256-thread class: <= 128 registers */
+#endif
 #ifndef Q32_MINB
 #define Q32_MINB 3      /* resident CTAs per SM the warp-per-halo kernel is compiled for: 80 registers, so that one
                          * of its CTAs fits next to a 256-thread-class CTA (<= 128 registers) on an SM — at 118 + 130
@@ -56,7 +59,7 @@ template <> struct Cfg<32> {   /* warp per halo */
     static const int CAP = 256, WTARGET = 128, NLEV = 1, GROUPS = 8, MINB = Q32_MINB;
 };
 template <> struct Cfg<256> {  /* block per halo */
-    static const int CAP = 4096, WTARGET = 1024, NLEV = 4, GROUPS = 1, MINB = 2;
+    static const int CAP = 4096, WTARGET = 1024, NLEV = 4, GROUPS = 1, MINB = Q256_MINB;
 };
 template <> struct Cfg<1024> { /* one full-SM block per halo: cluster-size halos (>= ~10^5 particles) */
     static const int CAP = 4096, WTARGET = 2048, NLEV = 4, GROUPS = 1, MINB = 1;
@@ -2221,7 +2224,8 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
         /* aux[0] (256-thread class) is served before aux[1] (warp class) when both have CTAs pending */
-        e = cudaStreamCreateWithPriority(&h->aux[k], cudaStreamNonBlocking, k == 0 ? prio_greatest : prio_least);
+        e = cudaStreamCreateWithPriority(&h->aux[k], cudaStreamNonBlocking,
+                                         (k == 0 && !getenv("SOGPU_NO_PRIO")) ? prio_greatest : prio_least);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
