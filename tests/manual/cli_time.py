@@ -1,16 +1,16 @@
 """Time the drop-in `so` program (so_b200/host/so) next to the reference binary on one BASELINE
 config, with the phase breakdown (SO_TIMING=1), and diff their output files.  Run under gpurun:
-    python tools/cli_time.py [config] [scale] [--no-ref]"""
+    python tests/manual/cli_time.py [config] [scale] [--no-ref]"""
 import os
 import subprocess
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from so_b200 import synth, tipsy
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 SO = os.path.join(ROOT, "so_b200", "host", "so")
 REF = os.path.join(ROOT, "oracle", "_ref", "so_ref")
 

@@ -1,6 +1,6 @@
 """Development check: CUDA path vs the oracle on scaled BASELINE configs (run under gpurun)."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from so_b200 import api, synth
 from oracle import pyoracle as po
