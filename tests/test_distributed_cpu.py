@@ -122,3 +122,84 @@ def test_exchange_plan_offsets():
             pos = b
         assert pos == total[d]
     assert parallel.slice_bounds(10, 3) == [(0, 3), (3, 6), (6, 10)]
+
+
+def _needed_by(pos, centers, reach):
+    """numpy stand-in for k_mark_mask + k_route: particle i is needed by a rank if it lies inside the periodic
+    cube of half-width reach[h] around one of the rank's halo centres."""
+    need = np.zeros(len(pos), bool)
+    for c, b in zip(centers, reach):
+        d = np.abs(pos - c)
+        d = np.minimum(d, 1.0 - d)
+        need |= (d <= b).all(axis=1)
+    return need
+
+
+def _domain_worker(rank, world, port, seed, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import pyoracle as po
+        s = synth.make_snapshot(24 ** 3, 40, seed=seed, nmax=1500)       # every rank can regenerate the catalog ...
+        a, b = parallel.slice_bounds(s.n, world)[rank]
+        my_pos = s.pos[a:b]                                               # ... but only holds ITS slice of the particles
+        rank_of, _ = parallel.spatial_assign(s.centers, parallel.halo_cost(s.rgtp, s.n, 1.0), world)
+        reach = np.maximum(s.rgtp.astype(np.float64) * 1.2 ** 8, 0.02)
+        # which of my particles does every rank need; count matrix by all_gather; offsets by exchange_plan
+        need = [_needed_by(my_pos, s.centers[rank_of == r], reach[rank_of == r]) for r in range(world)]
+        counts = torch.tensor([int(n.sum()) for n in need], dtype=torch.int64)
+        rows = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(rows, counts)
+        cm = torch.stack(rows).numpy()
+        recv_total, recv_off = parallel.exchange_plan(cm)
+        # records {x, y, z, global index} grouped by destination, then the all-to-all
+        send = np.concatenate([np.concatenate([my_pos[n], (a + np.nonzero(n)[0]).astype(np.float64)[:, None]], axis=1)
+                               for n in need]).astype(np.float64)
+        recv = torch.zeros((int(recv_total[rank]), 4), dtype=torch.float64)
+        dist.all_to_all_single(recv, torch.from_numpy(send), output_split_sizes=[int(x) for x in cm[:, rank]],
+                               input_split_sizes=[int(x) for x in cm[rank]])
+        recv = recv.numpy()
+        # what src sent sits at the planned offset of my buffer
+        for src in range(world):
+            seg = recv[recv_off[src, rank]:recv_off[src, rank] + cm[src, rank], 3].astype(np.int64)
+            sa, sb = parallel.slice_bounds(s.n, world)[src]
+            assert ((seg >= sa) & (seg < sb)).all()
+        gidx = recv[:, 3].astype(np.int64)
+        mine = parallel.shard_indices(rank_of, rank)
+        out = {"mine": mine}
+        if len(mine):
+            o = po.Oracle(recv[:, :3].astype(np.float32), s.mass)
+            res = o.so(s.centers[mine], s.rgtp[mine], np.float32(200.0), 8)
+            out.update(rvir=res["rvir"], mvir=res["mvir"], ndelta=res["ndelta"], member_offset=res["member_offset"],
+                       members=gidx[res["members"]].astype(np.int64))      # back to global particle indices
+        np.savez(os.path.join(out_dir, "dom%d.npz" % rank), **out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_domain_run_protocol_over_gloo(tmp_path, world):
+    """The domain-run protocol (slices, spatial halo shares, count matrix, planned offsets, all-to-all of
+    {x,y,z,global index} records, per-rank solve) with numpy in place of the device kernels and the oracle as
+    the per-rank solver: merged results = the single-rank oracle, member indices global."""
+    from oracle import pyoracle as po
+    seed = 600 + world
+    mp.spawn(_domain_worker, args=(world, _free_port(), seed, str(tmp_path)), nprocs=world, join=True)
+    s = synth.make_snapshot(24 ** 3, 40, seed=seed, nmax=1500)
+    ref = po.Oracle(s.pos, s.mass).so(s.centers, s.rgtp, np.float32(200.0), 8)
+    seen = np.zeros(s.h, bool)
+    for r in range(world):
+        z = np.load(str(tmp_path / ("dom%d.npz" % r)))
+        mine = z["mine"]
+        seen[mine] = True
+        if not len(mine):
+            continue
+        assert z["rvir"].tobytes() == ref["rvir"][mine].tobytes()
+        assert z["mvir"].tobytes() == ref["mvir"][mine].tobytes()
+        assert np.array_equal(z["ndelta"], ref["ndelta"][mine])
+        for k, i in enumerate(mine):
+            a = z["members"][z["member_offset"][k]:z["member_offset"][k + 1]]
+            b = ref["members"][ref["member_offset"][i]:ref["member_offset"][i + 1]]
+            assert np.array_equal(np.sort(a), np.sort(b))
+    assert seen.all()
