@@ -179,6 +179,7 @@ class VirtualDomainRun:
         xyzm = torch.empty((n, 4), dtype=torch.float32, device=dev)
         xyzm[:, :3] = torch.from_numpy(np.ascontiguousarray(pos, np.float32)).to(dev)
         xyzm[:, 3] = float(mass)
+        torch.cuda.synchronize()
         rank_of, _ = spatial_assign(centers, halo_cost(rgtp, n, float(np.prod(period))), R, period[0])
         gs = [api.SoGpu() for _ in range(R)]
         words = gs[0].domain_mask_words(n)
@@ -189,6 +190,7 @@ class VirtualDomainRun:
         while any(len(t) for t in todo):
             out["rounds"] += 1
             masks = torch.zeros((R, words), dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()            # (torch's stream is not the handles' stream)
             for r in range(R):
                 gs[r].domain_mask(n, centers[todo[r]], rgtp[todo[r]], n_balls, masks[r].data_ptr(), period)
             torch.cuda.synchronize()
@@ -221,6 +223,7 @@ class VirtualDomainRun:
                 d_r = torch.from_numpy(np.ascontiguousarray(rgtp[mine])).to(dev)
                 d_n = torch.empty(len(mine), dtype=torch.int32, device=dev)
                 d_m = torch.empty(len(mine), dtype=torch.float32, device=dev)
+                torch.cuda.synchronize()        # the uploads above ran on torch's stream
                 g.so_device(d_c.data_ptr(), d_r.data_ptr(), len(mine), thr, n_members, d_n.data_ptr(), d_m.data_ptr())
                 torch.cuda.synchronize()
                 code = d_n.cpu().numpy()
