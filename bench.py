@@ -1,19 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — halos/sec of the SO hot path (grid build + SO radius solve + member lists).
+"""bench.py — halos/sec of the SO hot path on ONE catalog over ONE snapshot (strong scaling).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU code (oracle/_ref)
 
-A "step" is one pass of the hot path over one batch of synthetic input:
-    kdBuildTree (sogpu_build_grid) + kdSO (sogpu_so_device) for every halo of the catalog.
-Workload at N=1: BASELINE.json configs[1] — 256^3 periodic snapshot (16.8 M particles), 10 000
-NFW halos, Delta = 200 rho_crit.  At N>1 (weak scaling) every rank holds the same snapshot
-(replicated by one NCCL broadcast) and the catalog grows to N x 10 000 centres, sharded across
-ranks by LPT on the estimated particle count; no data-path collective.
+Workload: BASELINE.json configs[3] — 1024^3 periodic snapshot (1.07 G particles), 100 000 NFW halo centres,
+Delta = 200 rho_crit (the configuration north_star's target is stated on; 73 of 180 GB on one GPU).
+A "step" is one pass of the hot path over that input:
+    kdBuildTree (so.c:515) + kdSO/kdRvir for every halo (so.c:540; R/M/N + member lists),
+run as a DOMAIN STEP (so_b200/csrc/domain_step.cuh): every rank holds 1/N of the particle array (as a parallel
+reader delivers it) and the whole catalog; per step each rank derives halo ownership and the destination table
+on its own device, routes its slice in one pass, pushes {x,y,z,index} records into the owners' buffers over
+NVLink peer memory, meets the others at a flag barrier, builds a grid over what arrived and solves its halos.
+At N = 1 the same code is the best single-GPU path (routing = compaction to the 5-20 % of the particles any
+halo can reach).  There is no collective in the timed region.
 
-`value`  = halos/s with inputs already in HBM, timed with CUDA events, max over ranks.
-`e2e`    = the same through the public API with HOST buffers: pack + H2D of the particles
-           (rank 0, then NCCL broadcast), H2D of the catalog, D2H of R/M/N and the member lists.
+`value`  = halos/s with the slices and the catalog already in HBM, CUDA events, max over ranks.
+`e2e`    = the same through the public API with HOST buffers: every rank's slice from its own page-locked
+           memory over its own PCIe link, catalog H2D, R/M/N (merged on rank 0's side by one small NCCL
+           reduction when N > 1) and the member lists D2H.
+`cfg1`   = (N = 1) the round-1 workload, BASELINE configs[1] (256^3 / 10 000 halos), for continuity.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -32,25 +38,28 @@ METRIC = "halos/sec"
 UNIT = "halos/s"
 THR = 200.0
 NMEM = 8
+N_BALLS = 4
+REF_SAMPLE = {3: 1.0 / 64.0, 2: 1.0 / 8.0, 4: 1.0 / 8.0, 1: 1.0, 0: 1.0}   # --impl reference: fraction of the workload per step
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=1, help="BASELINE.json configs index (default 1)")
+    ap.add_argument("--config", type=int, default=3, help="BASELINE.json configs index (default 3: 1024^3)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink N and H together (debug)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-scale", type=float, default=0.125,
-                    help="--impl reference: fraction of the workload timed per step")
+    ap.add_argument("--no-cfg1", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end steps (default min(steps, 10))")
+    ap.add_argument("--ref-scale", type=float, default=0.0,
+                    help="--impl reference: fraction of the workload timed per step (default: 1/64 of configs[3])")
     return ap.parse_args()
 
 
-def workload_name(s, h_total):
-    return "%s: %d particles, %d halo centres, Delta=200 rho_crit, z=0" % (s.name, s.n, h_total)
+def workload_name(name, n, h, omega0=1.0):
+    return "%s: %d particles, %d halo centres, Delta=200 rho_crit, z=0" % (name, n, h)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -118,8 +127,9 @@ def write_inputs(s, tmpdir):
     return snap, gtp
 
 
-def time_reference(s, steps, warmup, tmpdir):
-    """Returns (list of seconds per step (kdBuildTree + kdSO), kind, h)."""
+def time_reference(s, steps, warmup, tmpdir, full_kdso=False):
+    """Seconds per step of the reference's kdBuildTree + kdSO on snapshot s -> (list, kind).
+    The reference's kdSO includes kdVcirc, kdTagParticles and _VcmParticles per halo (kd2.c:823-826,884-885)."""
     from oracle import pyoracle as po
     if po.ref_available("so_ref_timed"):
         snap, gtp = write_inputs(s, tmpdir)
@@ -154,25 +164,35 @@ def run_reference(args):
     if rank != 0:
         return 0
     from so_b200 import synth
-    scale = args.scale * args.ref_scale
+    frac = args.ref_scale if args.ref_scale > 0 else REF_SAMPLE.get(args.config, 1.0)
+    scale = args.scale * frac
     s = synth.config(args.config, scale)
     with tmp_dir() as tmp:
         ts, kind = time_reference(s, args.steps, args.warmup, tmp)
     sec = float(np.mean(ts))
     value = s.h / sec
-    sample = ("%s scaled by %g (%d particles, %d halos) per step; kdBuildTree+kdSO of the reference, "
-              "single-threaded as shipped" % (s.name, scale, s.n, s.h))
-    full = synth.config  # noqa: F841
+    sample = ("%s scaled by %g (%d particles, %d halos) per step; kdBuildTree + kdSO of the reference (kdSO there "
+              "also runs kdVcirc, kdTagParticles and _VcmParticles per halo), single-threaded as shipped"
+              % (s.name, scale, s.n, s.h))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "BASELINE configs[%d] (%s)" % (args.config, s.name), "sample": sample,
-                   "delta": THR, "n_members": NMEM},
+                   "delta": THR, "n_members": NMEM,
+                   "note": "the reference needs ~70 GB and tens of minutes per step on the full 1024^3 configuration; "
+                           "its per-halo rate falls with N (kdBuildTree is N log N), so the sampled rate flatters it"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.config != 1 and not args.no_cfg1:
+        # the round-1 workload in full, so that one key of the two arms compares identical work
+        s1 = synth.config(1, args.scale)
+        with tmp_dir() as tmp:
+            t1, _ = time_reference(s1, min(args.steps, 3), 0, tmp)
+        line["cfg1"] = {"workload": workload_name(s1.name, s1.n, s1.h), "value": s1.h / float(np.mean(t1)), "unit": UNIT,
+                        "ms_per_step": float(np.mean(t1)) * 1e3, "steps": len(t1), "sample": "the full configuration"}
     print(json.dumps(line))
     return 0
 
@@ -180,10 +200,167 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-ALG_BYTES = {  # algorithmic bytes per unit for the kernels whose unit count is only known after the run
-    "k_so_query<32>": ("eval", 16.0), "k_so_query<256>": ("eval", 16.0),
-    "k_so_emit<32>": ("member", 20.0), "k_so_emit<256>": ("member", 20.0),
-}
+def peak_hbm():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback (of fallback)"
+
+
+def kernel_table(prof, steps, units):
+    """per-kernel ms / launches / algorithmic bytes per step from the library's event log"""
+    alg = {"k_so_query<32>": ("eval", 16.0), "k_so_query<256>": ("eval", 16.0), "k_so_query<1024>": ("eval", 16.0),
+           "k_so_emit<32>": ("member", 20.0), "k_so_emit<256>": ("member", 20.0), "k_so_emit<1024>": ("member", 20.0)}
+    total_ms = sum(v[0] for v in prof.values())
+    kernels = {}
+    for kname, (kms, launches, kbytes) in prof.items():
+        if launches == 0:
+            continue
+        per = kms / steps
+        ent = {"ms_per_step": per, "share": kms / total_ms if total_ms else 0.0, "launches_per_step": launches / steps}
+        if kbytes > 0:
+            ent["alg_bytes"] = kbytes / steps
+        if "alg_bytes" in ent and per > 0:
+            ent["gbs"] = ent["alg_bytes"] / (per * 1e-3) / 1e9
+        kernels[kname] = ent
+    # the query kernels run side by side and share one evaluation counter: their roofline is taken over the group
+    q = [k for k in kernels if k.startswith("k_so_query")]
+    if q and units.get("eval"):
+        tq = max(kernels[k]["ms_per_step"] for k in q)          # they overlap: the longest one bounds the phase
+        for k in q:
+            kernels[k]["note"] = "runs concurrently with the other size classes; evaluations are counted for the group"
+        kernels["gather(k_so_query*)"] = {"ms_per_step": tq, "alg_bytes": 16.0 * units["eval"],
+                                          "gbs": 16.0 * units["eval"] / (tq * 1e-3) / 1e9 if tq > 0 else 0.0,
+                                          "note": "16 B x r^2 evaluations over the longest of the concurrent query kernels"}
+    del alg
+    return kernels
+
+
+def roofline_entry(kernels, name, peak, peak_src, extra=None):
+    k = kernels.get(name)
+    if not k or not k.get("gbs"):
+        return None
+    lps = max(k.get("launches_per_step", 1.0), 1.0)
+    r = {"bound": "hbm", "kernel": name, "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": k["gbs"] / peak,
+         "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": k["alg_bytes"] / lps,
+         "launches_per_step": lps, "avg_launch_ms": k["ms_per_step"] / lps, "share_of_step": k.get("share"),
+         "timed": "live CUDA events on the launching stream, second pass over the same K steps"}
+    if extra:
+        r.update(extra)
+    return r
+
+
+def traffic_for(name, workload):
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tpath):
+        return None, None
+    tj = json.load(open(tpath))
+    for entry in (tj if isinstance(tj, list) else [tj]):
+        if entry.get("workload", "") and workload.startswith(entry["workload"]):
+            hit = [v["dram_bytes_per_launch"] for k, v in entry["kernels"].items() if k.startswith(name)]
+            if hit:
+                return sum(hit) / len(hit), entry.get("source")
+    return None, None
+
+
+def run_cfg1(torch, api, synth, dev, stream, args):
+    """The round-1 step on BASELINE configs[1] (full grid build + solve, and the domain step), one GPU."""
+    from so_b200 import parallel
+    s = synth.config(1, args.scale)
+    g = api.SoGpu(device=dev.index, stream=stream.cuda_stream)
+    xyzm = torch.empty((s.n, 4), dtype=torch.float32, device=dev)
+    pos_pin = torch.from_numpy(s.pos).pin_memory()
+    g.upload_particles(pos_pin.numpy(), s.mass, xyzm.data_ptr())
+    g.set_particles_device(xyzm.data_ptr(), s.n)
+    d_c = torch.from_numpy(s.centers).to(dev)
+    d_r = torch.from_numpy(s.rgtp).to(dev)
+    d_n = torch.empty(s.h, dtype=torch.int32, device=dev)
+    d_m = torch.empty(s.h, dtype=torch.float32, device=dev)
+    thr = np.float32(THR)
+    steps = max(args.steps, 5)
+
+    def timed(fn, k):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / k
+
+    def full():
+        g.build_grid()
+        g.so_device(d_c.data_ptr(), d_r.data_ptr(), s.h, thr, NMEM, d_n.data_ptr(), d_m.data_ptr())
+    ms_full = timed(full, steps)
+    n_full = d_n.cpu().numpy().copy()
+    st = g.stats()
+
+    def e2e():
+        g.upload_particles(pos_pin.numpy(), s.mass, xyzm.data_ptr())
+        g.set_particles_device(xyzm.data_ptr(), s.n)
+        g.build_grid()
+        r = g.so(s.centers, s.rgtp, thr, NMEM)
+        g.members(copy=False)
+        return r
+    for _ in range(2):
+        e2e()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) / steps * 1e3
+    # kdSO-equivalent step (what the reference's timed kdSO does): + tagging, vcm needs velocities (not in this
+    # synthetic input), kdVcirc on the device
+    r = g.so(s.centers, s.rgtp, thr, NMEM)
+
+    def full_kdso():
+        g.upload_particles(pos_pin.numpy(), s.mass, xyzm.data_ptr())
+        g.set_particles_device(xyzm.data_ptr(), s.n)
+        g.build_grid()
+        g.keep_member_d2(True)
+        rr = g.so(s.centers, s.rgtp, thr, NMEM)
+        g.members(sorted=True, copy=False)
+        g.tag_members(np.arange(1, s.h + 1, dtype=np.int32))
+        ok = rr["rvir"] > 0
+        g.vcirc(s.centers[ok], rr["rvir"][ok], rr["mvir"][ok], 1.0, NMEM, profile=False)
+        g.keep_member_d2(False)
+    kdso_ms = None
+    try:
+        for _ in range(2):
+            full_kdso()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            full_kdso()
+        torch.cuda.synchronize()
+        kdso_ms = (time.perf_counter() - t0) / 3 * 1e3
+    except Exception as e:    # reported, not fatal: this leg is an extra
+        kdso_ms = "failed: %s" % e
+    g.close()
+    # the same workload as a domain step on one GPU
+    g2 = api.SoGpu(device=dev.index, stream=stream.cuda_stream)
+    ds = parallel.DomainStep(g2, s.n, s.mass)
+    ds.step(d_c.data_ptr(), d_r.data_ptr(), s.h, N_BALLS, xyzm.data_ptr(), s.n, 0, thr, NMEM, d_n.data_ptr(), d_m.data_ptr())
+    res = ds.result()
+    ms_dom = timed(lambda: ds.step(d_c.data_ptr(), d_r.data_ptr(), s.h, N_BALLS, xyzm.data_ptr(), s.n, 0, thr, NMEM,
+                                   d_n.data_ptr(), d_m.data_ptr()), steps)
+    same = bool(np.array_equal(d_n.cpu().numpy(), n_full))
+    ds.close()
+    g2.close()
+    return {"workload": workload_name(s.name, s.n, s.h), "value": s.h / (min(ms_full, ms_dom) * 1e-3), "unit": UNIT,
+            "ms_per_step_full_grid": ms_full, "ms_per_step_domain_step": ms_dom,
+            "domain_step_same_n_delta_as_full_grid": same, "domain_step_flags": res["flags"],
+            "evals_per_step": st["last_evals"], "members_per_step": st["last_members"],
+            "e2e": {"value": s.h / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 12 * s.n + 16 * s.h, "d2h_bytes_per_step": 16 * s.h + 8 + 4 * st["last_members"]},
+            "e2e_full_kdso_equivalent": {"ms_per_step": kdso_ms,
+                                         "note": "upload + build + solve + sorted member lists + device tagging + kdVcirc: the work "
+                                                 "the reference's kdBuildTree + kdSO does (kd2.c:864-895), minus _VcmParticles "
+                                                 "(the synthetic input has no velocities)"}}
 
 
 def run_ours(args):
@@ -198,80 +375,104 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    os.environ.setdefault("TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING", "false")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    t_setup = time.time()
 
-    # ---- inputs (rank 0 generates; everything else is replicated / sharded from it) ----------
+    # ---- inputs: rank 0 generates; every rank receives ITS slice and the whole (small) catalog ----------
     if rank == 0:
         s = synth.config(args.config, args.scale)
-        n, h_base = s.n, s.h
-        reps = world if args.scaling == "weak" else 1
-        cen, rg = [s.centers], [s.rgtp]
-        for r in range(1, reps):   # extra catalog copies: same halos, re-estimated centres
-            rng = np.random.default_rng(7000 + r)
-            d = synth._unit_vectors(rng, s.h) * (rng.random(s.h) * 0.05 * s.r200)[:, None]
-            cen.append(synth._wrap(s.centers.astype(np.float64) + d))
-            rg.append(s.rgtp)
-        centers = np.concatenate(cen).astype(np.float32)
-        rgtp = np.concatenate(rg).astype(np.float32)
-        meta = [n, len(rgtp), float(s.mass), s.name]
+        meta = [s.n, s.h, float(s.mass), s.name, float(s.omega0)]
     else:
-        s, centers, rgtp, meta = None, None, None, [0, 0, 0.0, ""]
+        s, meta = None, [0, 0, 0.0, "", 1.0]
     if world > 1:
         dist.broadcast_object_list(meta, src=0)
-    n, h_total, mass, name = int(meta[0]), int(meta[1]), np.float32(meta[2]), meta[3]
-    cat = torch.empty((h_total, 4), dtype=torch.float32, device=dev)
+    n, h, mass, name, omega0 = int(meta[0]), int(meta[1]), np.float32(meta[2]), meta[3], float(meta[4])
+    thr = np.float32(np.float32(THR) * np.float32(omega0))
+    cat = torch.empty((h, 4), dtype=torch.float32, device=dev)
     if rank == 0:
-        cat.copy_(torch.from_numpy(np.concatenate([centers, rgtp[:, None]], axis=1)))
+        cat.copy_(torch.from_numpy(np.concatenate([s.centers, s.rgtp[:, None]], axis=1).astype(np.float32)))
     if world > 1:
         dist.broadcast(cat, src=0)
-    cat_h = cat.cpu().numpy()
-    centers, rgtp = np.ascontiguousarray(cat_h[:, :3]), np.ascontiguousarray(cat_h[:, 3])
-    rank_of, load = parallel.lpt_assign(parallel.halo_cost(rgtp, n, 1.0), world)
-    mine = parallel.shard_indices(rank_of, rank)
-    h_mine = len(mine)
+    cat_pin = torch.empty((h, 4), dtype=torch.float32).pin_memory()
+    cat_pin.copy_(cat)
+    d_centers = cat[:, :3].contiguous()
+    d_rgtp = cat[:, 3].contiguous()
+    cen_pin = d_centers.cpu().pin_memory()
+    rg_pin = d_rgtp.cpu().pin_memory()
 
-    # host-side particle buffer of the e2e leg (pinned), only rank 0 owns the snapshot
-    if rank == 0:
-        pos_pin = torch.from_numpy(s.pos).pin_memory()
-    xyzm = torch.empty((n, 4), dtype=torch.float32, device=dev)   # device-resident float4 particles
-    # a real (non-default) stream: the library launches on it and torch's events time it
+    bounds = parallel.slice_bounds(n, world)
+    a, b = bounds[rank]
+    n_slice = b - a
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
+    d_slice = torch.empty((n_slice, 4), dtype=torch.float32, device=dev)
+    chunk = 1 << 24
+    for r in range(world):
+        ra, rb = bounds[r]
+        for c0 in range(ra, rb, chunk):
+            c1 = min(rb, c0 + chunk)
+            if rank == 0:
+                t = torch.empty((c1 - c0, 4), dtype=torch.float32, device=dev)
+                t[:, :3] = torch.from_numpy(s.pos[c0:c1]).to(dev)
+                t[:, 3] = float(mass)
+                if r == 0:
+                    d_slice[c0 - ra:c1 - ra] = t
+                else:
+                    dist.send(t, dst=r)
+                del t
+            elif rank == r:
+                dist.recv(d_slice[c0 - ra:c1 - ra], src=0)
+    torch.cuda.synchronize()
+    if rank == 0:
+        s.pos = None                       # the slices live on the devices now
+    # page-locked host copy of the slice's positions: the input of the end-to-end leg
+    pos_pin = torch.empty((n_slice, 3), dtype=torch.float32).pin_memory()
+    for c0 in range(0, n_slice, chunk):
+        c1 = min(n_slice, c0 + chunk)
+        pos_pin[c0:c1].copy_(d_slice[c0:c1, :3])
+    torch.cuda.synchronize()
+    t_setup = time.time() - t_setup
+
     g = api.SoGpu(device=local, stream=stream.cuda_stream)
-    g.profile_enable(True)
-
-    def upload_and_replicate():
-        """e2e leg: rank 0 packs + copies the snapshot (pinned host memory) into its device buffer
-        through the C-ABI, then the array is replicated to the other GPUs by one NCCL broadcast."""
-        if rank == 0:
-            g.upload_particles(pos_pin.numpy(), mass, xyzm.data_ptr())
-        if world > 1:
-            dist.broadcast(xyzm, src=0)
-        g.set_particles_device(xyzm.data_ptr(), n)
-
-    upload_and_replicate()   # initial residency for the device-timed leg
-    d_centers = torch.from_numpy(np.ascontiguousarray(centers[mine])).to(dev)
-    d_rgtp = torch.from_numpy(np.ascontiguousarray(rgtp[mine])).to(dev)
-    d_out_n = torch.empty(max(h_mine, 1), dtype=torch.int32, device=dev)
-    d_out_m = torch.empty(max(h_mine, 1), dtype=torch.float32, device=dev)
-    thr = np.float32(THR)
+    ds = parallel.DomainStep(g, n, mass)
+    d_out_n = torch.empty(h, dtype=torch.int32, device=dev)
+    d_out_m = torch.empty(h, dtype=torch.float32, device=dev)
 
     def step_device():
-        g.build_grid()
-        if h_mine:
-            g.so_device(d_centers.data_ptr(), d_rgtp.data_ptr(), h_mine, thr, NMEM,
-                        d_out_n.data_ptr(), d_out_m.data_ptr())
+        ds.step(d_centers.data_ptr(), d_rgtp.data_ptr(), h, N_BALLS, d_slice.data_ptr(), n_slice, a, thr, NMEM,
+                d_out_n.data_ptr(), d_out_m.data_ptr())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(xs):
+        t = torch.tensor(xs, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+    def check_flags(res, what):
+        f = allmax(float(res["flags"]))
+        if f:
+            raise SystemExit("bench.py: domain step failed (%s): %s" % (what, parallel.flags_text(int(res["flags"])) or f))
+
+    # ---- device-resident leg ---------------------------------------------------------------------
     sampler = ClockSampler(local)
     g.profile_enable(False)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         step_device()
+        check_flags(ds.result(), "warm-up")          # (also teaches the library how many records to expect)
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -281,9 +482,14 @@ def run_ours(args):
         step_device()
     e1.record(stream)
     barrier()
-    ms = e0.elapsed_time(e1)
-    # the SAME K steps once more with the library's per-kernel CUDA events on (two event records
-    # per launch perturb the step by a few percent, so the headline above is timed without them)
+    ms_step = allmax(e0.elapsed_time(e1)) / args.steps
+    res = ds.result(h)
+    check_flags(res, "timed steps")
+    owner = res["owner"]
+    st = g.stats()
+    launches = st["last_kernel_launches"]
+    # the SAME K steps once more with the library's per-kernel CUDA events on (two event records per launch
+    # perturb the step by a few percent, so the headline above is timed without them)
     g.profile_enable(True)
     g.profile_read(reset=True)
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -295,192 +501,134 @@ def run_ours(args):
     barrier()
     ms_profiled = p0.elapsed_time(p1) / args.steps
     prof = g.profile_read(reset=True)
-    st = g.stats()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
-    evals = torch.tensor([float(st["last_evals"]), float(st["last_members"])], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(evals, op=dist.ReduceOp.SUM)
-    evals_total, members_total = float(evals[0].item()), float(evals[1].item())
-
-    res_n = d_out_n[:h_mine].cpu().numpy()
-    res_m = d_out_m[:h_mine].cpu().numpy()
-
-    # ---- extra: the focused build (grid only where this rank's halos can look) -------------------
-    FOCUS_BALLS = 4
-
-    def step_focused():
-        if h_mine:
-            g.build_grid_for_device(d_centers.data_ptr(), d_rgtp.data_ptr(), h_mine, FOCUS_BALLS)
-            g.so_device(d_centers.data_ptr(), d_rgtp.data_ptr(), h_mine, thr, NMEM,
-                        d_out_n.data_ptr(), d_out_m.data_ptr())
-        else:
-            g.build_grid()
-
-    g.profile_read(reset=True)
-    for _ in range(3):
-        step_focused()
-    barrier()
-    foc_prof = {k: round(v[0] / 3, 4) for k, v in g.profile_read(reset=True).items() if v[1]}
     g.profile_enable(False)
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(stream)
-    for _ in range(args.steps):
-        step_focused()
-    f1.record(stream)
-    barrier()
-    tf = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+    st = g.stats()
+    n_recv = ds.result()["n_recv"]
+    evals_total, members_total, recv_total, recv_max = allsum([float(st["last_evals"]), float(st["last_members"]),
+                                                               float(n_recv), 0.0])[:3] + [allmax(float(n_recv))]
+
+    # results of the whole catalog, merged: every halo is solved by exactly one rank
+    code = d_out_n.clone()
+    mm = torch.where(code == int(parallel.NOT_MINE), torch.full_like(d_out_m, -float("inf")), d_out_m)
     if world > 1:
-        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-    ms_focused = float(tf.item()) / args.steps
-    foc_n = d_out_n[:h_mine].cpu().numpy()
-    foc_m = d_out_m[:h_mine].cpu().numpy()
-    foc_in = foc_n != -103            # halos whose balls stayed inside the focused region
-    foc_same = bool(np.array_equal(foc_n[foc_in], res_n[foc_in]) and
-                    foc_m[foc_in].tobytes() == res_m[foc_in].tobytes())
-    foc_outgrown = int((~foc_in).sum())
-    foc_kept = g.stats()["n_in_grid"]
+        dist.all_reduce(code, op=dist.ReduceOp.MAX)
+        dist.all_reduce(mm, op=dist.ReduceOp.MAX)
+    res_n, res_m = code.cpu().numpy(), mm.cpu().numpy()
+    ok = res_n > 0
+    outgrown = int((res_n == -103).sum())
+    k = res_n[ok].astype(np.int64)
+    m_ok = bool(np.array_equal(res_m[ok], (api.mass_prefix(mass, k + 1) - mass).astype(np.float32)))
+    codes = {int(c): int((res_n == c).sum()) for c in np.unique(res_n[~ok])}
 
     # ---- e2e: host buffers in, host results out, every step ----------------------------------
-    e2e_parts = {"upload_ms": 0.0, "build_so_ms": 0.0, "members_ms": 0.0}
+    e2e_steps = args.e2e_steps or min(args.steps, 10)
+    out_pin = torch.empty((2, h), dtype=torch.float32).pin_memory()
 
     def step_e2e():
-        ta = time.perf_counter()
-        upload_and_replicate()
-        tb = time.perf_counter()
-        g.build_grid()
-        out = None
-        if h_mine:
-            r = g.so(centers[mine], rgtp[mine], thr, NMEM)
-            tc = time.perf_counter()
-            off, mem = g.members(copy=False)
-            out = (r, off, mem)
-        else:
-            tc = time.perf_counter()
-        td = time.perf_counter()
-        e2e_parts["upload_ms"] += (tb - ta) * 1e3
-        e2e_parts["build_so_ms"] += (tc - tb) * 1e3
-        e2e_parts["members_ms"] += (td - tc) * 1e3
-        return out
+        d_centers.copy_(cen_pin, non_blocking=True)
+        d_rgtp.copy_(rg_pin, non_blocking=True)
+        ds.step(d_centers.data_ptr(), d_rgtp.data_ptr(), h, N_BALLS, d_slice.data_ptr(), n_slice, a, thr, NMEM,
+                d_out_n.data_ptr(), d_out_m.data_ptr(), host_xyz=pos_pin.data_ptr())
+        c2 = d_out_n.clone()
+        m2 = torch.where(c2 == int(parallel.NOT_MINE), torch.full_like(d_out_m, -float("inf")), d_out_m)
+        if world > 1:
+            dist.all_reduce(c2, op=dist.ReduceOp.MAX)
+            dist.all_reduce(m2, op=dist.ReduceOp.MAX)
+        out_pin[0].copy_(c2.view(torch.float32), non_blocking=True)
+        out_pin[1].copy_(m2, non_blocking=True)
+        r = ds.result()                              # synchronises
+        off, mem = g.members(copy=False)             # member lists of this rank's halos (global indices)
+        return r, off
 
     for _ in range(2):
-        step_e2e()
+        r, off = step_e2e()
+        check_flags(r, "end-to-end warm-up")
     barrier()
-    for k in e2e_parts:
-        e2e_parts[k] = 0.0
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out = step_e2e()
+    for _ in range(e2e_steps):
+        r, off = step_e2e()
     barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_s = allmax((time.perf_counter() - t0) / e2e_steps)
+    check_flags(r, "end-to-end steps")
     clocks = sampler.stop()
-    n_members_mine = int(out[1][-1]) if out else 0
-    h2d = (12 * n if rank == 0 else 0) + 16 * h_mine   # xyz triplets (+1 shared mass), centres + rgtp
-    d2h = 8 * h_mine + 8 * (h_mine + 1) + 4 * n_members_mine
-    io = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(io, op=dist.ReduceOp.SUM)
+    n_members_mine = int(off[-1])
+    h2d, d2h = allsum([12.0 * n_slice + 16.0 * h, 8.0 * h + 8.0 * (h + 1) + 4.0 * n_members_mine])
+    halos_per_rank = allsum([float((owner == r_).sum()) if rank == 0 else 0.0 for r_ in range(world)])
 
+    ds.close()
+    g.close()
+    del d_slice, pos_pin
+    torch.cuda.empty_cache()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (rank 0's launches, live CUDA-event times) ----------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
-    else:
-        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    units = {"particle": float(n), "cell": float(st["cells_per_axis"]) ** 3,
-             "eval": float(st["last_evals"]), "member": float(st["last_members"])}
-    total_ms = sum(v[0] for v in prof.values())
-    kernels = {}
-    for kname, (kms, launches, kbytes) in prof.items():
-        if launches == 0:
-            continue
-        per = kms / args.steps
-        ent = {"ms_per_step": per, "share": kms / total_ms if total_ms else 0.0,
-               "launches_per_step": launches / args.steps}
-        if kbytes > 0:                      # grid build: bytes known at launch (library-side table)
-            ent["alg_bytes"] = kbytes / args.steps
-        elif kname in ALG_BYTES:            # query / emit: 16 B per r^2 evaluation, 20 B per member
-            unit, b = ALG_BYTES[kname]
-            ent["alg_bytes"] = b * units[unit]
-            if unit == "eval":
-                ent["note"] = "evaluations are shared between the warp and the block kernel"
-        if "alg_bytes" in ent:
-            ent["gbs"] = ent["alg_bytes"] / (per * 1e-3) / 1e9 if per > 0 else 0.0
-        kernels[kname] = ent
-    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
-    dk = kernels[dom]
-    lps = max(dk["launches_per_step"], 1.0)
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": dk.get("gbs"), "peak": peak, "unit": "GB/s",
-                "frac": (dk.get("gbs") or 0.0) / peak, "traffic": None, "peak_source": peak_src,
-                "alg_bytes_per_launch": (dk.get("alg_bytes") or 0.0) / lps, "launches_per_step": lps,
-                "avg_launch_ms": dk["ms_per_step"] / lps, "share_of_step": dk["share"],
-                "timed": "live CUDA events on the launching stream, second pass over the same K steps"}
-    # DRAM traffic per launch of that kernel from the committed `ncu --set full` capture (same workload only)
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath) and args.scale == 1.0:
-        tj = json.load(open(tpath))
-        if tj.get("workload", "") and name.startswith(tj["workload"]):
-            hit = [v["dram_bytes_per_launch"] for k, v in tj["kernels"].items() if k.startswith(dom)]
-            if hit:
-                roofline["traffic"] = sum(hit) / len(hit)
-                roofline["traffic_source"] = tj.get("source")
-    launches = int(round(sum(v[1] for v in prof.values()) / args.steps))
-    # the two query kernels share one evaluation counter: split it by their time share
-    qk = [k for k in ("k_so_query<32>", "k_so_query<256>") if k in kernels]
-    if len(qk) == 2:
-        tq = sum(kernels[k]["ms_per_step"] for k in qk)
-        for k in qk:
-            kernels[k]["gbs"] = 16.0 * units["eval"] / (tq * 1e-3) / 1e9
-            kernels[k]["alg_bytes"] = 16.0 * units["eval"] * kernels[k]["ms_per_step"] / tq
+    # ---- roofline entries (rank 0's launches, live CUDA-event times) -------------------------------
+    peak, peak_src = peak_hbm()
+    units = {"eval": float(st["last_evals"]), "member": float(st["last_members"])}
+    kernels = kernel_table(prof, args.steps, units)
+    timed_kernels = {k: v for k, v in kernels.items() if not k.startswith("gather(")}
+    dom = max(timed_kernels, key=lambda k_: timed_kernels[k_]["ms_per_step"])
+    wl = workload_name(name, n, h)
+    roofline = roofline_entry(kernels, dom, peak, peak_src) or {"bound": "hbm", "kernel": dom, "achieved": None, "peak": peak,
+                                                                 "unit": "GB/s", "frac": None, "traffic": None}
+    tr, tr_src = traffic_for(dom, name)
+    if tr is not None and args.scale == 1.0:
+        roofline["traffic"], roofline["traffic_source"] = tr, tr_src
+    e_min = members_total + h
+    roof_gather = roofline_entry(kernels, "gather(k_so_query*)", peak, peak_src,
+                                 {"evals": units["eval"], "evals_min": float(st["last_members"]) + float((owner == 0).sum()),
+                                  "note": "rank 0's halos; E_min = sum(N_Delta + 1)"})
+    build_names = [k_ for k_ in ("k_lvl_hist", "k_scan", "k_lvl_partition", "k_bucket_sort") if k_ in kernels]
+    t_build = sum(kernels[k_]["ms_per_step"] for k_ in build_names)
+    roof_build = None
+    if t_build > 0:
+        gbs = 36.0 * n_recv / (t_build * 1e-3) / 1e9
+        roof_build = {"bound": "hbm", "kernel": "+".join(build_names), "achieved": gbs, "peak": peak, "unit": "GB/s",
+                      "frac": gbs / peak, "alg_bytes": 36.0 * n_recv, "ms_per_step": t_build,
+                      "note": "SURVEY 8(d): 36 B per particle sorted for the whole build; particles = records this rank received"}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
+        frac = REF_SAMPLE.get(args.config, 1.0)
+        sb = synth.config(args.config, args.scale * frac)
         with tmp_dir() as tmp:
-            ts, kind = time_reference(s, 1, 0, tmp)
-        cpu_baseline = {"value": s.h / ts[0], "unit": UNIT, "cores": 1, "kind": kind,
-                        "sample": "the full workload once (%d particles, %d halos): kdBuildTree + kdSO of "
-                                  "the reference, %.1f s" % (s.n, s.h, ts[0])}
+            ts, kind = time_reference(sb, 1, 0, tmp)
+        cpu_baseline = {"value": sb.h / ts[0], "unit": UNIT, "cores": 1, "kind": kind,
+                        "sample": "%s scaled by %g (%d particles, %d halos) once: kdBuildTree + kdSO of the reference, "
+                                  "%.1f s, single-threaded as shipped" % (sb.name, args.scale * frac, sb.n, sb.h, ts[0])}
+    cfg1 = None
+    if world == 1 and not args.no_cfg1 and args.config != 1:
+        cfg1 = run_cfg1(torch, api, synth, dev, stream, args)
 
-    # sanity of the timed result: codes are valid and most halos resolved
-    ok = int((res_n > 0).sum())
     line = {
-        "metric": METRIC, "value": h_total / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(s, h_total), "baseline_config": args.config,
-                   "delta": THR, "n_members": NMEM, "cells_per_axis": st["cells_per_axis"],
-                   "halos_per_rank": [int((rank_of == r).sum()) for r in range(world)],
-                   "l2": "inputs (%.0f MB float4 particles) exceed the 126 MB L2; no flush between steps"
-                         % (16 * n / 1e6),
-                   "parallelism": "halos sharded by LPT over %d rank(s), particles replicated" % world},
-        "focused_build": {"note": "same step with sogpu_build_grid_for (grid only where the halos can look, "
-                                  "%d schedule balls); results of the halos inside the focus identical to the full build: %s; "
-                                  "sogpu_so() re-solves outgrown halos on a full grid by itself" % (FOCUS_BALLS, foc_same),
-                          "value": h_total / (ms_focused * 1e-3), "unit": UNIT, "ms_per_step": ms_focused,
-                          "particles_sorted_rank0": int(foc_kept), "halos_outgrown_rank0": foc_outgrown,
-                          "kernel_ms_per_step": foc_prof},
+        "metric": METRIC, "value": h / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl, "baseline_config": args.config, "delta": THR, "n_members": NMEM,
+                   "cells_per_axis": st["cells_per_axis"], "mask_balls": N_BALLS,
+                   "halos_per_rank": [int(x) for x in halos_per_rank],
+                   "l2": "inputs (%.1f GB of float4 particles per rank) exceed the 126 MB L2; no flush between steps"
+                         % (16 * n_slice / 1e9),
+                   "parallelism": "domain step over %d rank(s): particle slices, halos owned by spatially compact "
+                                  "cost-balanced shares, records pushed over NVLink peer memory, no collective" % world},
+        "records_received_total": recv_total, "records_received_max": recv_max, "received_fraction_of_N": recv_total / n,
         "evals_per_s": evals_total / (ms_step * 1e-3), "evals_per_step": evals_total,
-        "members_per_step": members_total, "halos_resolved_rank0": ok,
+        "members_per_step": members_total,
+        "check": {"halos_resolved": int(ok.sum()), "codes": codes, "outgrown_-103": outgrown,
+                  "m_delta_equals_mass_table_at_n_delta": m_ok},
         # work inflation: r^2 evaluations over the minimum sum(N_Delta + 1)
-        "evals_over_min": evals_total / max(members_total + h_total, 1.0),
-        "e2e": {"value": h_total / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
-                "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
-                "rank0_breakdown_ms": {k: v / args.steps for k, v in e2e_parts.items()}},
-        "roofline": roofline, "kernels": kernels, "ms_per_step_with_kernel_events": ms_profiled,
-        "cpu_baseline": cpu_baseline,
-        "gpu_launches": launches, "clocks": clocks,
+        "evals_over_min": evals_total / max(e_min, 1.0),
+        "e2e": {"value": h / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "roofline": roofline, "roofline_gather": roof_gather, "roofline_build": roof_build,
+        "kernels": kernels, "ms_per_step_with_kernel_events": ms_profiled,
+        "cpu_baseline": cpu_baseline, "cfg1": cfg1, "setup_s": t_setup,
+        "gpu_launches": int(launches), "clocks": clocks,
     }
+    if outgrown or not m_ok:
+        line["invalid"] = "results failed the built-in checks"
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

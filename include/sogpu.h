@@ -238,6 +238,48 @@ int sogpu_peer_open(sogpu_t *h, const void *handle64, void **ptr);
 int sogpu_peer_close(sogpu_t *h, void *ptr);
 int sogpu_peer_free(sogpu_t *h, void *ptr);
 
+/* ---- several GPUs: the domain STEP, stream-ordered from the slice to the results ---------------------
+ *
+ * The calls above keep the host in the loop (masks and counts are read back to size the buffers).  The step
+ * below does not: every rank derives the halo ownership and the destination table from the catalog on its own
+ * device (identical integer arithmetic everywhere, so nothing is exchanged), routes its slice in ONE pass into
+ * local staging runs, reserves its range in every receiver's buffer with one system-scope atomic on the
+ * receiver's cursor, copies the runs over NVLink, and meets the other ranks at a flag barrier in peer memory.
+ * The grid build then reads the number of records that arrived from the device.
+ *
+ *   sogpu_domain_open     buffers of this rank; handles192 = three 64-byte cudaIpc handles (receive buffer 0,
+ *                         receive buffer 1, control block) for the other processes of the node
+ *   sogpu_domain_connect  pointers to every rank's buffers as seen from THIS process (sogpu_peer_open of the
+ *                         handles, or the plain device pointers in a one-process run after sogpu_enable_peer_access)
+ *   per step, every rank, same arguments:
+ *     sogpu_domain_begin        whole catalog (device): ownership, destination table, own focus mask
+ *     sogpu_domain_route[_host] this rank's slice (or pieces of it), device float4 {x,y,z,m} / pinned host xyz
+ *     sogpu_domain_push         reservations + copies (+ barrier)
+ *     sogpu_domain_solve        grid over what arrived, SO solve of the owned halos; outputs cover the WHOLE
+ *                               catalog: N_Delta / code and M_Delta for owned halos, 0x80808080 elsewhere;
+ *                               code -103 = the halo's ball left the mask: step again with a larger n_balls
+ *     sogpu_domain_result       (synchronises) records received / sent, error flags, owner of every halo
+ * Member lists of the owned halos: sogpu_members (offsets over the whole catalog; indices are global). */
+typedef struct {
+    int32_t rank, n_ranks;
+    int64_t n_total;          /* particles of the whole snapshot (fixes the cell size on every rank) */
+    float mass;               /* the particle mass (domain steps are for equal-mass snapshots)       */
+    float period[3], center[3];
+    int64_t recv_cap;         /* records each receive buffer holds                                   */
+    int64_t stage_cap;        /* records one per-destination staging area holds (n_ranks > 1)        */
+} sogpu_domain_cfg_t;
+int sogpu_domain_open(sogpu_t *h, const sogpu_domain_cfg_t *cfg, void *handles192);
+int sogpu_domain_connect(sogpu_t *h, void *const *recv0, void *const *recv1, void *const *ctrl);
+int sogpu_domain_pointers(sogpu_t *h, void **recv0, void **recv1, void **ctrl);
+int sogpu_enable_peer_access(sogpu_t *h, int peer_device);
+int sogpu_domain_begin(sogpu_t *h, const void *d_centers, const void *d_rgtp, int32_t nh, int32_t n_balls);
+int sogpu_domain_route(sogpu_t *h, const void *d_chunk, int64_t n, int64_t index_base);
+int sogpu_domain_route_host(sogpu_t *h, const float *xyz_pinned, int64_t n, int64_t index_base, void *d_slice_dst);
+int sogpu_domain_push(sogpu_t *h, int barrier);
+int sogpu_domain_solve(sogpu_t *h, float rho_thr, int32_t n_members, void *d_out_n, void *d_out_m);
+int sogpu_domain_result(sogpu_t *h, int64_t *n_recv, int64_t *n_sent, uint32_t *flags, unsigned char *owner);
+int sogpu_domain_close(sogpu_t *h);
+
 /* ---- introspection --------------------------------------------------------------------------- */
 
 typedef struct {

@@ -31,11 +31,19 @@ SYMBOLS = [
     "sogpu_ingest_records", "sogpu_ingest_end", "sogpu_domain_mask_words", "sogpu_domain_mask",
     "sogpu_domain_route_count", "sogpu_domain_route_scatter", "sogpu_set_particles_device_indexed",
     "sogpu_peer_alloc", "sogpu_peer_open", "sogpu_peer_close", "sogpu_peer_free",
+    "sogpu_domain_open", "sogpu_domain_connect", "sogpu_enable_peer_access", "sogpu_domain_begin",
+    "sogpu_domain_route", "sogpu_domain_route_host", "sogpu_domain_push", "sogpu_domain_solve",
+    "sogpu_domain_result", "sogpu_domain_close", "sogpu_domain_pointers",
 ]
 
 
 class SoGpuError(RuntimeError):
     pass
+
+
+class DomainCfg(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("n_ranks", C.c_int32), ("n_total", C.c_int64), ("mass", C.c_float),
+                ("period", C.c_float * 3), ("center", C.c_float * 3), ("recv_cap", C.c_int64), ("stage_cap", C.c_int64)]
 
 
 class Stats(C.Structure):
@@ -96,6 +104,22 @@ def lib():
     for f in (L.sogpu_domain_mask_words, L.sogpu_domain_mask, L.sogpu_domain_route_count, L.sogpu_domain_route_scatter,
               L.sogpu_set_particles_device_indexed, L.sogpu_peer_alloc, L.sogpu_peer_open, L.sogpu_peer_close,
               L.sogpu_peer_free):
+        f.restype = C.c_int
+    L.sogpu_domain_open.argtypes = [vp, C.POINTER(DomainCfg), vp]
+    L.sogpu_domain_connect.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.sogpu_enable_peer_access.argtypes = [vp, C.c_int]
+    L.sogpu_domain_begin.argtypes = [vp, vp, vp, C.c_int32, C.c_int32]
+    L.sogpu_domain_route.argtypes = [vp, vp, C.c_int64, C.c_int64]
+    L.sogpu_domain_route_host.argtypes = [vp, vp, C.c_int64, C.c_int64, vp]
+    L.sogpu_domain_push.argtypes = [vp, C.c_int]
+    L.sogpu_domain_solve.argtypes = [vp, C.c_float, C.c_int32, vp, vp]
+    L.sogpu_domain_result.argtypes = [vp, i64p, i64p, C.POINTER(C.c_uint32), C.POINTER(C.c_ubyte)]
+    L.sogpu_domain_close.argtypes = [vp]
+    L.sogpu_domain_pointers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.sogpu_domain_pointers.restype = C.c_int
+    for f in (L.sogpu_domain_open, L.sogpu_domain_connect, L.sogpu_enable_peer_access, L.sogpu_domain_begin,
+              L.sogpu_domain_route, L.sogpu_domain_route_host, L.sogpu_domain_push, L.sogpu_domain_solve,
+              L.sogpu_domain_result, L.sogpu_domain_close):
         f.restype = C.c_int
     L.sogpu_debug_timeline.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.sogpu_debug_timeline.restype = C.c_int
@@ -469,6 +493,59 @@ class SoGpu:
 
     def peer_free(self, ptr):
         _check(lib().sogpu_peer_free(self._h, C.c_void_p(int(ptr))))
+
+    # ---- domain STEP: stream-ordered from the slice to the results -----------------------------------
+    def domain_open(self, rank, n_ranks, n_total, mass, recv_cap, stage_cap, period=(1.0, 1.0, 1.0), center=(0.0, 0.0, 0.0)):
+        """Allocates this rank's buffers; returns the three 64-byte handles (recv0, recv1, ctrl) other processes open."""
+        cfg = DomainCfg(int(rank), int(n_ranks), int(n_total), float(mass), (C.c_float * 3)(*period),
+                        (C.c_float * 3)(*center), int(recv_cap), int(stage_cap))
+        hb = (C.c_ubyte * 192)()
+        _check(lib().sogpu_domain_open(self._h, C.byref(cfg), hb))
+        raw = bytes(hb)
+        return [raw[0:64], raw[64:128], raw[128:192]]
+
+    def domain_pointers(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib().sogpu_domain_pointers(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return int(a.value), int(b.value), int(c.value)
+
+    def domain_connect(self, recv0, recv1, ctrl):
+        n = len(ctrl)
+        arr = lambda v: (C.c_void_p * n)(*[int(p) if p else None for p in v])
+        _check(lib().sogpu_domain_connect(self._h, arr(recv0), arr(recv1), arr(ctrl)))
+
+    def enable_peer_access(self, peer_device):
+        _check(lib().sogpu_enable_peer_access(self._h, int(peer_device)))
+
+    def domain_begin(self, d_centers, d_rgtp, nh, n_balls):
+        _check(lib().sogpu_domain_begin(self._h, C.c_void_p(int(d_centers)), C.c_void_p(int(d_rgtp)), int(nh), int(n_balls)))
+        self._last_h = int(nh)
+
+    def domain_route(self, d_chunk, n, index_base):
+        _check(lib().sogpu_domain_route(self._h, C.c_void_p(int(d_chunk)), int(n), int(index_base)))
+
+    def domain_route_host(self, xyz_pinned_ptr, n, index_base, d_slice_dst):
+        _check(lib().sogpu_domain_route_host(self._h, C.c_void_p(int(xyz_pinned_ptr)), int(n), int(index_base),
+                                             C.c_void_p(int(d_slice_dst))))
+
+    def domain_push(self, barrier=True):
+        _check(lib().sogpu_domain_push(self._h, 1 if barrier else 0))
+
+    def domain_solve(self, thr, n_members=8, d_out_n=0, d_out_m=0):
+        _check(lib().sogpu_domain_solve(self._h, C.c_float(float(thr)), int(n_members),
+                                        C.c_void_p(int(d_out_n)) if d_out_n else None,
+                                        C.c_void_p(int(d_out_m)) if d_out_m else None))
+
+    def domain_result(self, nh=0):
+        """Synchronises.  Returns dict(n_recv, n_sent, flags, owner[nh] or None)."""
+        nr, ns, fl = C.c_int64(), C.c_int64(), C.c_uint32()
+        owner = np.zeros(int(nh), np.uint8) if nh else None
+        _check(lib().sogpu_domain_result(self._h, C.byref(nr), C.byref(ns), C.byref(fl),
+                                         owner.ctypes.data_as(C.POINTER(C.c_ubyte)) if nh else None))
+        return {"n_recv": int(nr.value), "n_sent": int(ns.value), "flags": int(fl.value), "owner": owner}
+
+    def domain_close(self):
+        _check(lib().sogpu_domain_close(self._h))
 
     def tag_members(self, index, n_particles=None):
         """Order-independent part of kdTagParticles: (in_conflict[nh], igrp[N]) for the last so() call."""

@@ -1,0 +1,730 @@
+/* domain_step.cuh — one step of a DOMAIN RUN (several GPUs) without any host round trip.
+ *
+ * The path being scaled is so.c:515 (kdBuildTree) + so.c:540 (kdSO -> kdRvir, kd2.c:864-895, 723-840) over ONE
+ * snapshot and ONE catalog.  Every rank holds a slice of the particle array and the whole (small) catalog.
+ * All of the following is enqueued on the rank's stream; nothing is read back by the host before the results:
+ *
+ *   k_assign_hist/_scan/_owner  owner rank of every halo: halos ordered along a tiled curve through the box, cut
+ *                               into pieces of equal estimated cost.  Integer arithmetic on identical inputs, so
+ *                               every rank computes the same assignment without talking to the others.
+ *   k_mark_table                destination table: for every halo, its owner's bit is set in every coarse cell the
+ *                               halo can reach within n_balls steps of kdRvir's ball schedule (kd2.c:765-768).
+ *                               Again computed redundantly by every rank from the catalog: no mask exchange.
+ *   k_table_to_mask             this rank's own focus mask (what the grid build and the ball checks use)
+ *   k_route_stage               ONE pass over the slice: each particle is looked up in the table and appended, as a
+ *                               {x, y, z, global index} record, to a local staging run per destination (runs are
+ *                               reserved per (CTA, round, destination) with local atomics); the rank's own records
+ *                               go straight into its receive buffer.
+ *   k_push_reserve              one system-scope atomicAdd per destination on the RECEIVER's cursor (peer memory,
+ *                               NVLink) reserves the range this rank's records will occupy there
+ *   k_push_copy                 staging runs -> the receivers' buffers: large coalesced 16-byte stores over NVLink
+ *   k_dom_barrier               flag barrier through peer memory (release / acquire at system scope)
+ *   build (n read on the device) + SO solve of the halos this rank owns.
+ *
+ * Receive buffers and cursors are double-buffered by step parity: a rank that runs ahead writes into the other set.
+ */
+#pragma once
+
+#define DOM_ASSIGN_LOG 5
+#define DOM_ASSIGN_BINS (1 << (3 * DOM_ASSIGN_LOG))
+#define CODE_NOT_MINE ((int32_t)0x80808080)     /* cudaMemset pattern 0x80: halo solved by another rank */
+
+struct DomCtrl {                        /* lives in peer-shareable memory (sogpu_peer_alloc) */
+    unsigned long long cursor[2];       /* records reserved so far in recv[parity]            */
+    uint32_t flag[ROUTE_MAXR];          /* barrier: last epoch rank r has announced to me     */
+    uint32_t pad[12];
+};
+
+struct DomainState {
+    sogpu_domain_cfg_t cfg;
+    float4 *recv[2];
+    DomCtrl *ctrl;
+    float4 *stage;                      /* n_ranks x stage_cap records (unused slot: own rank) */
+    float4 *peer_recv[2][ROUTE_MAXR];
+    DomCtrl *peer_ctrl[ROUTE_MAXR];
+    bool connected;
+    unsigned long long *d_counts;       /* [0..R) staged, [R..2R) push base, [2R..3R) push count, [3R] received (clamped) */
+    uint32_t *d_flags;                  /* bit0 staging overflow, bit1 own receive overflow, bit2 peer receive overflow, bit3 barrier timeout */
+    uint32_t *d_nrecv32;
+    unsigned char *d_owner;
+    int32_t owner_cap;
+    unsigned short *d_table;            /* destination ranks per coarse cell (2^(3 mb) entries)                */
+    uint32_t *d_any, *d_super, *d_mymask; /* bit per coarse cell: somebody's / (64^3 pre-filter) / this rank's  */
+    bool marked;                        /* the tables hold the marks of the previous step's catalog            */
+    int marked_balls;
+    int32_t marked_nh;
+    unsigned long long *d_bins;         /* DOM_ASSIGN_BINS + 1 */
+    uint32_t epoch;
+    int parity, n_balls;
+    int32_t nh;
+    int64_t n_hint;
+    bool routed;
+};
+
+/* ---- ownership -------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t assign_bin(const float *c, const GridDev &g)
+{
+    uint32_t k[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double t = ((double)c[a] - g.dg0[a]) / (double)g.L[a];
+        t -= floor(t);
+        int ci = (int)(t * (double)(1 << DOM_ASSIGN_LOG));
+        k[a] = (uint32_t)min(max(ci, 0), (1 << DOM_ASSIGN_LOG) - 1);
+    }
+    /* 8x8x8 blocks of cells, blocks row-major, cells row-major inside a block */
+    const uint32_t nb = 1u << (DOM_ASSIGN_LOG - 3);
+    const uint32_t hx = k[0] >> 3, hy = k[1] >> 3, hz = k[2] >> 3, lx = k[0] & 7u, ly = k[1] & 7u, lz = k[2] & 7u;
+    return ((((hz * nb + hy) * nb + hx)) << 9) | (lz << 6) | (ly << 3) | lx;
+}
+/* estimated r^2 evaluations of one halo: the final ball (1.2 R, R ~ 1.25 rgtp) at 200 x the mean number density,
+ * plus a floor for the fixed per-halo work (so_b200/parallel.py: halo_cost) */
+__device__ __forceinline__ unsigned long long assign_cost(float rgtp, double nbar)
+{
+    const double r = 1.2 * 1.25 * (double)rgtp;
+    const double c = 200.0 * nbar * 4.18879020478639 * r * r * r * 0.6 + 64.0;
+    return c < 1.0e15 ? (unsigned long long)c : 1000000000000000ull;
+}
+
+__global__ void __launch_bounds__(256) k_assign_hist(GridDev g, const float *__restrict__ centers, const float *__restrict__ rgtp,
+                                                     int nh, double nbar, unsigned long long *__restrict__ bins)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nh) return;
+    atomicAdd(&bins[assign_bin(centers + 3 * (size_t)h, g)], assign_cost(rgtp[h], nbar));
+}
+
+/* exclusive scan of the DOM_ASSIGN_BINS costs by one block; bins[DOM_ASSIGN_BINS] = total */
+__global__ void __launch_bounds__(1024) k_assign_scan(unsigned long long *bins)
+{
+    constexpr int PER = DOM_ASSIGN_BINS / 1024;
+    __shared__ unsigned long long ws[32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    unsigned long long s = 0;
+    for (int k = 0; k < PER; ++k) s += bins[t * PER + k];
+    unsigned long long x = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += u;
+    }
+    if (lane == 31) ws[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        unsigned long long y = ws[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, y, o);
+            if (lane >= o) y += u;
+        }
+        ws[lane] = y;
+    }
+    __syncthreads();
+    unsigned long long run = x - s + (w ? ws[w - 1] : 0ull);
+    for (int k = 0; k < PER; ++k) { const unsigned long long v = bins[t * PER + k]; bins[t * PER + k] = run; run += v; }
+    if (t == 1023) bins[DOM_ASSIGN_BINS] = run;
+}
+
+__global__ void __launch_bounds__(256) k_assign_owner(GridDev g, const float *__restrict__ centers, int nh, int R,
+                                                      const unsigned long long *__restrict__ bins,
+                                                      unsigned char *__restrict__ owner)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nh) return;
+    const uint32_t b = assign_bin(centers + 3 * (size_t)h, g);
+    const unsigned long long lo = bins[b], hi = bins[b + 1], total = bins[DOM_ASSIGN_BINS];
+    const unsigned long long mid = lo + (hi - lo) / 2ull;
+    unsigned long long r = total ? (mid * (unsigned long long)R) / total : 0ull;
+    owner[h] = (unsigned char)(r < (unsigned long long)R ? r : (unsigned long long)(R - 1));
+}
+
+/* ---- destination table -------------------------------------------------------------------------------- */
+#define DOM_SUPER_LOG 6       /* 64^3-bit pre-filter: 32 KB, stays in every SM's L1 during the routing pass */
+
+/* run of `len` bits starting at bit `b0` of a bitmap: OR it in (or clear the words) — at most len/32 + 2 operations */
+__device__ __forceinline__ void bit_run(uint32_t *map, uint32_t b0, uint32_t len, int clear)
+{
+    uint32_t b = b0, end = b0 + len;
+    while (b < end) {
+        const uint32_t w = b >> 5, lo = b & 31u, take = min(32u - lo, end - b);
+        const uint32_t m = (take == 32u ? 0xFFFFFFFFu : ((1u << take) - 1u)) << lo;
+        if (clear) map[w] = 0u; else atomicOr(&map[w], m);      /* (result unused: a fire-and-forget RED) */
+        b += take;
+    }
+}
+
+/* One warp per halo: the cube it can reach after n_balls steps of the ball schedule (same rule as k_mark_mask).
+ * Sets the owner's bit in the destination table, the "somebody wants this cell" bitmap, its 64^3 pre-filter and
+ * (own halos) this rank's focus mask.  A lane takes a whole x-row of the cube: consecutive cells are consecutive
+ * bits / table entries, so a row is a handful of word-wide reductions with nothing to wait for.
+ * clear = 1 undoes exactly those marks: the tables are kept clean between steps by un-marking the previous
+ * catalog (a few million stores) instead of clearing hundreds of megabytes. */
+__global__ void __launch_bounds__(256) k_mark_table(GridDev g, const float *__restrict__ centers,
+                                                    const float *__restrict__ rgtp, int nh, int n_balls,
+                                                    const unsigned char *__restrict__ owner, int me,
+                                                    uint32_t *__restrict__ table32, uint32_t *__restrict__ any,
+                                                    uint32_t *__restrict__ super, uint32_t *__restrict__ mymask, int clear)
+{
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const float root = so_root_period(g.L[0], g.L[1], g.L[2]);
+    const int nm = 1 << g.mb, nm1 = nm - 1;
+    const int sb = min(g.mb, DOM_SUPER_LOG), ss = g.mb - sb;
+    for (int h = wid; h < nh; h += nw) {
+        float ball = rgtp[h];
+        for (int k = 0; k < n_balls && (double)ball < 0.25 * (double)root; ++k) ball = so_next_ball(ball);
+        const float ball2 = __fmul_rn(ball, ball);
+        const double b = fmax(sqrt((double)ball2) * (1.0 + 1.0e-6), g.mask_rmin);
+        int x0, nx, y0, ny, z0, nz;
+        mask_range(g, 0, centers[3 * h + 0], b, x0, nx);
+        mask_range(g, 1, centers[3 * h + 1], b, y0, ny);
+        mask_range(g, 2, centers[3 * h + 2], b, z0, nz);
+        const int own = owner[h];
+        const uint32_t ob = (1u << own) * 0x00010001u;             /* the owner's bit in both halves of a table word */
+        const int xa = x0 & nm1;                                   /* the row's x-range, split where it wraps */
+        const int n0 = min(nx, nm - xa), n1 = nx - n0;
+        for (int r = lane; r < ny * nz; r += 32) {
+            const uint32_t cy = (uint32_t)((y0 + r % ny) & nm1), cz = (uint32_t)((z0 + r / ny) & nm1);
+            const uint32_t row = (cz << (2 * g.mb)) | (cy << g.mb);
+            const uint32_t srow = ((cz >> ss) << (2 * sb)) | ((cy >> ss) << sb);
+            for (int piece = 0; piece < 2; ++piece) {
+                const int px = piece ? 0 : xa, pn = piece ? n1 : n0;
+                if (pn <= 0) continue;
+                bit_run(any, row + (uint32_t)px, (uint32_t)pn, clear);
+                if (own == me) bit_run(mymask, row + (uint32_t)px, (uint32_t)pn, clear);
+                bit_run(super, srow + ((uint32_t)px >> ss), (((uint32_t)(px + pn - 1)) >> ss) - ((uint32_t)px >> ss) + 1u, clear);
+                /* table: 16-bit entries, two per word */
+                uint32_t c = row + (uint32_t)px, e = c + (uint32_t)pn;
+                while (c < e) {
+                    const uint32_t w = c >> 1;
+                    uint32_t m = ob;
+                    if (c & 1u) m &= 0xFFFF0000u;
+                    if (((c | 1u) + 1u) > e) m &= 0x0000FFFFu;      /* the word's upper entry lies beyond the run */
+                    if (clear) table32[w] = 0u; else atomicOr(&table32[w], m);
+                    c = (c | 1u) + 1u;
+                }
+            }
+        }
+    }
+}
+
+/* ---- routing: one pass over the slice ------------------------------------------------------------------ */
+struct StageArgs {
+    GridDev g;
+    const float4 *slice;
+    int64_t n;
+    uint32_t index_base;
+    const unsigned short *table;
+    const uint32_t *any, *super;
+    int R;
+    float4 *dst[ROUTE_MAXR];                 /* staging area per destination; own rank: its receive buffer */
+    unsigned long long *cursor[ROUTE_MAXR];  /* records appended so far                                    */
+    unsigned long long cap[ROUTE_MAXR];
+    uint32_t flag_bit[ROUTE_MAXR];
+    uint32_t *flags;
+};
+
+__global__ void __launch_bounds__(256) k_route_stage(const __grid_constant__ StageArgs a)
+{
+    __shared__ uint32_t wcnt[8][ROUTE_MAXR];                   /* records per (warp, destination) of a round */
+    __shared__ unsigned long long wbase[8][ROUTE_MAXR];        /* ... and where each warp's run starts       */
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t nround = (a.n + stride * ROUTE_U - 1) / (stride * ROUTE_U);
+    for (int64_t it = 0; it < nround; ++it) {               /* every thread runs every round (ballots, barriers) */
+        const int64_t i0 = it * stride * ROUTE_U + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        float4 q[ROUTE_U];
+        uint32_t set[ROUTE_U];
+#pragma unroll
+        for (int u = 0; u < ROUTE_U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < a.n) q[u] = ld_stream(a.slice + i);
+        }
+#pragma unroll
+        for (int u = 0; u < ROUTE_U; ++u) {
+            const int64_t i = i0 + u * stride;
+            set[u] = 0u;
+            if (i < a.n) {
+                const int mask = a.g.nc - 1, mb = a.g.mb;
+                const uint32_t cx = cell_coord(q[u].x, a.g.g0[0], a.g.invh[0], mask) >> a.g.ms;
+                const uint32_t cy = cell_coord(q[u].y, a.g.g0[1], a.g.invh[1], mask) >> a.g.ms;
+                const uint32_t cz = cell_coord(q[u].z, a.g.g0[2], a.g.invh[2], mask) >> a.g.ms;
+                /* three lookups, cheapest first: 64^3 pre-filter (32 KB: L1), "somebody wants it" bitmap (L2),
+                 * destination set (only for the few particles that pass both) */
+                const int sb = min(mb, DOM_SUPER_LOG), ss = mb - sb;
+                const uint32_t sbit = ((cz >> ss) << (2 * sb)) | ((cy >> ss) << sb) | (cx >> ss);
+                if ((__ldg(a.super + (sbit >> 5)) >> (sbit & 31)) & 1u) {
+                    const uint32_t bit = (cz << (2 * mb)) | (cy << mb) | cx;
+                    if ((__ldg(a.any + (bit >> 5)) >> (bit & 31)) & 1u) set[u] = a.R > 1 ? __ldg(a.table + bit) : 1u;
+                }
+                q[u].w = __uint_as_float(a.index_base + (uint32_t)i);
+            }
+        }
+        uint32_t wset = 0u;                                 /* destinations some lane of this warp has */
+#pragma unroll
+        for (int u = 0; u < ROUTE_U; ++u) wset |= set[u];
+        wset = __reduce_or_sync(0xFFFFFFFFu, wset);
+        /* (whole CTA without a single record this round: nothing to reserve — the common case away from halos) */
+        if (!__syncthreads_or((int)wset)) continue;
+        if (lane < a.R) wcnt[w][lane] = 0u;
+        __syncwarp();
+        for (uint32_t rem = wset; rem; rem &= rem - 1u) {
+            const int d = __ffs(rem) - 1;
+            uint32_t c = 0;
+#pragma unroll
+            for (int u = 0; u < ROUTE_U; ++u) c += __popc(__ballot_sync(0xFFFFFFFFu, (set[u] >> d) & 1u));
+            if (lane == 0) wcnt[w][d] = c;
+        }
+        __syncthreads();
+        if (threadIdx.x < a.R) {
+            const int d = threadIdx.x;
+            uint32_t tot = 0;
+            for (int k = 0; k < 8; ++k) tot += wcnt[k][d];
+            unsigned long long base = tot ? atomicAdd(a.cursor[d], (unsigned long long)tot) : 0ull;
+            if (base + tot > a.cap[d]) {                    /* no room: drop the run, report (the host grows the buffers) */
+                if (tot) atomicOr(a.flags, a.flag_bit[d]);
+                base = ~0ull;
+            }
+            for (int k = 0; k < 8; ++k) {
+                wbase[k][d] = base;
+                if (base != ~0ull) base += wcnt[k][d];
+            }
+        }
+        __syncthreads();
+        for (uint32_t rem = wset; rem; rem &= rem - 1u) {
+            const int d = __ffs(rem) - 1;
+            unsigned long long pos = wbase[w][d];
+            const bool ok = pos != ~0ull;
+#pragma unroll
+            for (int u = 0; u < ROUTE_U; ++u) {
+                const bool want = (set[u] >> d) & 1u;
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
+                if (want && ok) a.dst[d][pos + (unsigned long long)__popc(m & lt)] = q[u];
+                pos += (unsigned long long)__popc(m);
+            }
+        }
+        __syncthreads();                                    /* wcnt / wbase are reused by the next round */
+    }
+}
+
+/* ---- push: staging runs -> the receivers' buffers over NVLink ---------------------------------------- */
+struct PushArgs {
+    int R, me, parity;
+    DomCtrl *peer_ctrl[ROUTE_MAXR];
+    float4 *peer_recv[ROUTE_MAXR];
+    const float4 *stage;
+    unsigned long long stage_cap, recv_cap;
+    unsigned long long *counts;             /* [0..R) staged, [R..2R) base at the receiver, [2R..3R) records to copy */
+    uint32_t *flags;
+};
+
+__global__ void k_push_reserve(const __grid_constant__ PushArgs a)
+{
+    const int d = threadIdx.x;
+    if (d >= a.R || d == a.me) return;
+    unsigned long long c = a.counts[d];
+    if (c > a.stage_cap) c = a.stage_cap;                     /* (staging overflow was flagged by k_route_stage) */
+    unsigned long long base = 0ull;
+    if (c) base = atomicAdd_system(&a.peer_ctrl[d]->cursor[a.parity], c);
+    if (base + c > a.recv_cap) { atomicOr(a.flags, 4u); c = 0ull; }   /* the receiver sees cursor > cap as well */
+    a.counts[a.R + d] = base;
+    a.counts[2 * a.R + d] = c;
+}
+
+__global__ void __launch_bounds__(256) k_push_copy(const __grid_constant__ PushArgs a)
+{
+    const int d = blockIdx.y;
+    if (d == a.me) return;
+    const unsigned long long n = a.counts[2 * a.R + d];
+    const float4 *__restrict__ src = a.stage + (size_t)d * a.stage_cap;
+    float4 *__restrict__ dst = a.peer_recv[d] + a.counts[a.R + d];
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3ull * stride < n; i += 4ull * stride) {
+        const float4 v0 = ld_stream(src + i), v1 = ld_stream(src + i + stride), v2 = ld_stream(src + i + 2ull * stride),
+                     v3 = ld_stream(src + i + 3ull * stride);
+        dst[i] = v0; dst[i + stride] = v1; dst[i + 2ull * stride] = v2; dst[i + 3ull * stride] = v3;
+    }
+    for (; i < n; i += stride) dst[i] = ld_stream(src + i);
+    __threadfence_system();
+}
+
+/* every rank announces `epoch` to every peer, then waits until every peer has announced it to this rank:
+ * all pushes of this step are then complete and visible.  Bounded wait: a missing peer raises flag bit 3
+ * instead of hanging the device. */
+__global__ void k_dom_barrier(const __grid_constant__ PushArgs a, DomCtrl *mine, uint32_t epoch, long long timeout_cycles)
+{
+    const int d = threadIdx.x;
+    if (d >= a.R || d == a.me) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&a.peer_ctrl[d]->flag[a.me]), "r"(epoch) : "memory");
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(&mine->flag[d]) : "memory");
+        if ((int32_t)(v - epoch) >= 0) break;
+        if (clock64() - t0 > timeout_cycles) { atomicOr(a.flags, 8u); break; }
+        __nanosleep(200);
+    }
+}
+
+/* received count of this step: clamped copy for the grid build (32 bit) and for the host (64 bit) */
+__global__ void k_dom_nrecv(const DomCtrl *mine, int parity, unsigned long long recv_cap, uint32_t *n32,
+                            unsigned long long *n64, uint32_t *flags)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    unsigned long long c = mine->cursor[parity];
+    *n64 = c;
+    if (c > recv_cap) { atomicOr(flags, 2u); c = 0ull; }      /* some run was dropped: nothing of this step is usable */
+    *n32 = (uint32_t)c;
+}
+
+/* ============================================================================================
+ * host side
+ * ============================================================================================ */
+static void dom_geometry(sogpu *h, GridDev &g)
+{
+    DomainState *D = h->dom;
+    for (int k = 0; k < 3; ++k) { h->period[k] = D->cfg.period[k]; h->center[k] = D->cfg.center[k]; }
+    domain_geometry(h, D->cfg.n_total, g);
+}
+
+extern "C" int sogpu_domain_open(sogpu_t *h, const sogpu_domain_cfg_t *cfg, void *handles192)
+{
+    if (!h || !cfg || !handles192) return set_err(SOGPU_ERR_ARG, "sogpu_domain_open: NULL argument");
+    if (cfg->n_ranks < 1 || cfg->n_ranks > ROUTE_MAXR || cfg->rank < 0 || cfg->rank >= cfg->n_ranks)
+        return set_err(SOGPU_ERR_ARG, "sogpu_domain_open: rank %d of %d (at most %d ranks)", cfg->rank, cfg->n_ranks, ROUTE_MAXR);
+    if (cfg->n_total <= 0 || cfg->n_total > 0x7FFFFFF0LL || cfg->recv_cap <= 0 || cfg->recv_cap > 0x7FFFFFF0LL ||
+        !(cfg->mass > 0.0f) || (cfg->n_ranks > 1 && cfg->stage_cap <= 0))
+        return set_err(SOGPU_ERR_ARG, "sogpu_domain_open: bad sizes");
+    if (h->dom) return set_err(SOGPU_ERR_ARG, "sogpu_domain_open: already open (sogpu_domain_close first)");
+    CU(cudaSetDevice(h->device));
+    DomainState *D = new (std::nothrow) DomainState();
+    if (!D) return set_err(SOGPU_ERR_NOMEM, "out of host memory");
+    memset(D, 0, sizeof(*D));
+    D->cfg = *cfg;
+    h->dom = D;
+    const int R = cfg->n_ranks;
+    unsigned char *hb = (unsigned char *)handles192;
+    int rc = SOGPU_OK;
+    /* receive buffers: two (step parity) when there are peers that can run ahead, one otherwise */
+    rc = sogpu_peer_alloc(h, (size_t)cfg->recv_cap * sizeof(float4), (void **)&D->recv[0], hb);
+    if (!rc) {
+        if (R > 1) rc = sogpu_peer_alloc(h, (size_t)cfg->recv_cap * sizeof(float4), (void **)&D->recv[1], hb + 64);
+        else { D->recv[1] = D->recv[0]; memcpy(hb + 64, hb, 64); }
+    }
+    if (!rc) rc = sogpu_peer_alloc(h, sizeof(DomCtrl), (void **)&D->ctrl, hb + 128);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(D->ctrl, 0, sizeof(DomCtrl), h->stream));
+    if (R > 1) CU(cudaMalloc(&D->stage, (size_t)R * (size_t)cfg->stage_cap * sizeof(float4)));
+    CU(cudaMalloc(&D->d_counts, (3 * ROUTE_MAXR + 1) * sizeof(unsigned long long)));
+    CU(cudaMalloc(&D->d_flags, sizeof(uint32_t)));
+    CU(cudaMalloc(&D->d_nrecv32, sizeof(uint32_t)));
+    CU(cudaMalloc(&D->d_bins, (DOM_ASSIGN_BINS + 1) * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(D->d_flags, 0, sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(D->d_counts, 0, (3 * ROUTE_MAXR + 1) * sizeof(unsigned long long), h->stream));
+    {   /* destination table + bitmaps at the mask resolution of this snapshot; cleared once, then kept clean */
+        for (int k = 0; k < 3; ++k) { h->period[k] = cfg->period[k]; h->center[k] = cfg->center[k]; }
+        GridDev g;
+        domain_geometry(h, cfg->n_total, g);
+        const size_t n_cells = (size_t)1 << (3 * g.mb), words = n_cells / 32 + 1;
+        const size_t swords = ((size_t)1 << (3 * std::min(g.mb, DOM_SUPER_LOG))) / 32 + 1;
+        CU(cudaMalloc(&D->d_table, (n_cells + 2) * sizeof(unsigned short)));
+        CU(cudaMalloc(&D->d_any, words * sizeof(uint32_t)));
+        CU(cudaMalloc(&D->d_mymask, words * sizeof(uint32_t)));
+        CU(cudaMalloc(&D->d_super, swords * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(D->d_table, 0, (n_cells + 2) * sizeof(unsigned short), h->stream));
+        CU(cudaMemsetAsync(D->d_any, 0, words * sizeof(uint32_t), h->stream));
+        CU(cudaMemsetAsync(D->d_mymask, 0, words * sizeof(uint32_t), h->stream));
+        CU(cudaMemsetAsync(D->d_super, 0, swords * sizeof(uint32_t), h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    for (int d = 0; d < R; ++d) { D->peer_recv[0][d] = D->peer_recv[1][d] = nullptr; D->peer_ctrl[d] = nullptr; }
+    D->peer_recv[0][cfg->rank] = D->recv[0];
+    D->peer_recv[1][cfg->rank] = D->recv[1];
+    D->peer_ctrl[cfg->rank] = D->ctrl;
+    D->connected = (R == 1);
+    D->n_hint = std::max<int64_t>(cfg->recv_cap / 2, 1);
+    return SOGPU_OK;
+}
+
+/* pointers (valid in THIS process: sogpu_peer_open, or plain device pointers of a one-process run with peer
+ * access enabled) to every rank's two receive buffers and control block; entries of the own rank are ignored */
+extern "C" int sogpu_domain_connect(sogpu_t *h, void *const *recv0, void *const *recv1, void *const *ctrl)
+{
+    if (!h || !h->dom || !recv0 || !recv1 || !ctrl) return set_err(SOGPU_ERR_ARG, "sogpu_domain_connect: bad argument");
+    DomainState *D = h->dom;
+    for (int d = 0; d < D->cfg.n_ranks; ++d) {
+        if (d == D->cfg.rank) continue;
+        if (!recv0[d] || !recv1[d] || !ctrl[d]) return set_err(SOGPU_ERR_ARG, "sogpu_domain_connect: NULL pointer for rank %d", d);
+        D->peer_recv[0][d] = (float4 *)recv0[d];
+        D->peer_recv[1][d] = (float4 *)recv1[d];
+        D->peer_ctrl[d] = (DomCtrl *)ctrl[d];
+    }
+    D->connected = true;
+    return SOGPU_OK;
+}
+
+/* this rank's own buffers as plain device pointers (one-process runs: hand them to the other handles) */
+extern "C" int sogpu_domain_pointers(sogpu_t *h, void **recv0, void **recv1, void **ctrl)
+{
+    if (!h || !h->dom || !recv0 || !recv1 || !ctrl) return set_err(SOGPU_ERR_ARG, "sogpu_domain_pointers: bad argument");
+    *recv0 = h->dom->recv[0]; *recv1 = h->dom->recv[1]; *ctrl = h->dom->ctrl;
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_enable_peer_access(sogpu_t *h, int peer_device)
+{
+    if (!h) return set_err(SOGPU_ERR_ARG, "NULL handle");
+    CU(cudaSetDevice(h->device));
+    if (peer_device == h->device) return SOGPU_OK;
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return SOGPU_OK; }
+    if (e != cudaSuccess) return set_err(SOGPU_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e));
+    return SOGPU_OK;
+}
+
+extern "C" int sogpu_domain_close(sogpu_t *h)
+{
+    if (!h || !h->dom) return SOGPU_OK;
+    DomainState *D = h->dom;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(D->recv[0]);
+    if (D->recv[1] != D->recv[0]) cudaFree(D->recv[1]);
+    cudaFree(D->ctrl); cudaFree(D->stage); cudaFree(D->d_counts); cudaFree(D->d_flags); cudaFree(D->d_nrecv32);
+    cudaFree(D->d_owner); cudaFree(D->d_bins);
+    cudaFree(D->d_table); cudaFree(D->d_any); cudaFree(D->d_mymask); cudaFree(D->d_super);
+    delete D;
+    h->mask_ready = nullptr;
+    h->dom = nullptr;
+    h->d_n_dev = nullptr;
+    return SOGPU_OK;
+}
+
+/* start of a step: ownership, destination table, this rank's mask.  d_centers / d_rgtp: the WHOLE catalog (device). */
+extern "C" int sogpu_domain_begin(sogpu_t *h, const void *d_centers, const void *d_rgtp, int32_t nh, int32_t n_balls)
+{
+    if (!h || !h->dom || !d_centers || !d_rgtp || nh <= 0 || n_balls < 1)
+        return set_err(SOGPU_ERR_ARG, "sogpu_domain_begin: bad argument");
+    DomainState *D = h->dom;
+    if (!D->connected) return set_err(SOGPU_ERR_ARG, "sogpu_domain_begin: call sogpu_domain_connect first");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int R = D->cfg.n_ranks, me = D->cfg.rank;
+    int rc = ensure_query(h, nh);
+    if (rc) return rc;
+    if (nh > D->owner_cap) {
+        cudaFree(D->d_owner); D->d_owner = nullptr; D->owner_cap = 0;
+        CU(cudaMalloc(&D->d_owner, (size_t)std::max(nh, 1024)));
+        D->owner_cap = std::max(nh, 1024);
+    }
+    GridDev g;
+    dom_geometry(h, g);
+    if (D->marked) {      /* un-mark the previous catalog (still in h->d_centers / d_rgtp / d_owner): the tables are clean again */
+        ProfScope p(h, KID_MARK_MASK);
+        k_mark_table<<<std::min((D->marked_nh + 7) / 8, h->sm_count * 8), 256, 0, s>>>(
+            g, h->d_centers, h->d_rgtp, D->marked_nh, D->marked_balls, D->d_owner, me, (uint32_t *)D->d_table, D->d_any,
+            D->d_super, D->d_mymask, 1);
+        D->marked = false;
+    }
+    if (d_centers != h->d_centers)
+        CU(cudaMemcpyAsync(h->d_centers, d_centers, (size_t)nh * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (d_rgtp != h->d_rgtp)
+        CU(cudaMemcpyAsync(h->d_rgtp, d_rgtp, (size_t)nh * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    D->epoch += 1u;
+    D->parity = (int)(D->epoch & 1u);
+    D->n_balls = n_balls;
+    D->nh = nh;
+    /* the OTHER parity's cursor was last used one step ago, by reservations that all happened before that
+     * step's barrier: clearing it here, ahead of this step's barrier, is safe (see the header comment) */
+    CU(cudaMemsetAsync(&D->ctrl->cursor[D->parity ^ 1], 0, sizeof(unsigned long long), s));
+    if (R == 1) CU(cudaMemsetAsync(&D->ctrl->cursor[D->parity], 0, sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(D->d_counts, 0, (3 * ROUTE_MAXR + 1) * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(D->d_flags, 0, sizeof(uint32_t), s));
+    h->stats.last_kernel_launches = 0;
+    {
+        ProfScope p(h, KID_ASSIGN, 0.0, 3);
+        if (R > 1) {
+            CU(cudaMemsetAsync(D->d_bins, 0, (DOM_ASSIGN_BINS + 1) * sizeof(unsigned long long), s));
+            double vol = (double)D->cfg.period[0] * D->cfg.period[1] * D->cfg.period[2];
+            k_assign_hist<<<(nh + 255) / 256, 256, 0, s>>>(g, h->d_centers, h->d_rgtp, nh, (double)D->cfg.n_total / vol, D->d_bins);
+            k_assign_scan<<<1, 1024, 0, s>>>(D->d_bins);
+            k_assign_owner<<<(nh + 255) / 256, 256, 0, s>>>(g, h->d_centers, nh, R, D->d_bins, D->d_owner);
+        } else {
+            CU(cudaMemsetAsync(D->d_owner, 0, (size_t)nh, s));
+        }
+    }
+    {
+        ProfScope p(h, KID_MARK_MASK);
+        k_mark_table<<<std::min((nh + 7) / 8, h->sm_count * 8), 256, 0, s>>>(g, h->d_centers, h->d_rgtp, nh, n_balls, D->d_owner, me,
+                                                                             (uint32_t *)D->d_table, D->d_any, D->d_super, D->d_mymask, 0);
+        D->marked = true; D->marked_balls = n_balls; D->marked_nh = nh;
+    }
+    CU(cudaGetLastError());
+    D->routed = false;
+    h->built = false;
+    h->have_result = false;
+    return SOGPU_OK;
+}
+
+static int dom_stage_args(sogpu *h, StageArgs &a, const void *d_chunk, int64_t n, int64_t index_base)
+{
+    DomainState *D = h->dom;
+    if (index_base < 0 || index_base + n > 0x7FFFFFF0LL) return set_err(SOGPU_ERR_ARG, "sogpu_domain_route: index out of range");
+    memset(&a, 0, sizeof(a));
+    dom_geometry(h, a.g);
+    a.slice = (const float4 *)d_chunk; a.n = n; a.index_base = (uint32_t)index_base;
+    a.table = D->d_table; a.any = D->d_any; a.super = D->d_super; a.R = D->cfg.n_ranks;
+    a.flags = D->d_flags;
+    for (int d = 0; d < a.R; ++d) {
+        if (d == D->cfg.rank) {
+            a.dst[d] = D->recv[D->parity]; a.cursor[d] = &D->ctrl->cursor[D->parity];
+            a.cap[d] = (unsigned long long)D->cfg.recv_cap; a.flag_bit[d] = 2u;
+        } else {
+            a.dst[d] = D->stage + (size_t)d * (size_t)D->cfg.stage_cap; a.cursor[d] = D->d_counts + d;
+            a.cap[d] = (unsigned long long)D->cfg.stage_cap; a.flag_bit[d] = 1u;
+        }
+    }
+    return SOGPU_OK;
+}
+
+/* route n particles (float4 {x,y,z,m}, device) whose first one has global index index_base; may be called
+ * several times per step (chunks of the slice, e.g. as they arrive from the host) */
+extern "C" int sogpu_domain_route(sogpu_t *h, const void *d_chunk, int64_t n, int64_t index_base)
+{
+    if (!h || !h->dom || (n > 0 && !d_chunk) || n < 0) return set_err(SOGPU_ERR_ARG, "sogpu_domain_route: bad argument");
+    if (n == 0) return SOGPU_OK;
+    CU(cudaSetDevice(h->device));
+    StageArgs a;
+    int rc = dom_stage_args(h, a, d_chunk, n, index_base);
+    if (rc) return rc;
+    {
+        ProfScope p(h, KID_ROUTE, 16.0 * (double)n);
+        /* persistent grid of exactly the CTAs that are resident at once: a second, partial wave would leave
+         * the SMs of the finished CTAs idle */
+        static int per_sm = 0;
+        if (!per_sm) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_route_stage, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+        }
+        k_route_stage<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * per_sm), 256, 0, h->stream>>>(a);
+    }
+    CU(cudaGetLastError());
+    return SOGPU_OK;
+}
+
+/* same from page-locked HOST memory: n xyz triplets (+ the shared mass) are copied in pieces, unpacked into
+ * d_slice_dst (device float4, caller-owned, n entries) and routed piece by piece — the copy of the next piece
+ * is queued behind the routing of this one on the same stream */
+extern "C" int sogpu_domain_route_host(sogpu_t *h, const float *xyz_pinned, int64_t n, int64_t index_base, void *d_slice_dst)
+{
+    if (!h || !h->dom || !xyz_pinned || !d_slice_dst || n <= 0) return set_err(SOGPU_ERR_ARG, "sogpu_domain_route_host: bad argument");
+    CU(cudaSetDevice(h->device));
+    const int64_t rchunk = 1 << 23;   /* 96 MB of xyz per piece */
+    if (!h->d_raw) CU(cudaMalloc(&h->d_raw, (size_t)rchunk * 3 * sizeof(float)));
+    float4 *dst = (float4 *)d_slice_dst;
+    for (int64_t i0 = 0; i0 < n; i0 += rchunk) {
+        const int64_t k = std::min(rchunk, n - i0);
+        CU(cudaMemcpyAsync(h->d_raw, xyz_pinned + 3 * i0, (size_t)k * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        k_expand_xyz<<<h->sm_count * 8, 256, 0, h->stream>>>(h->d_raw, h->dom->cfg.mass, dst + i0, k);
+        int rc = sogpu_domain_route(h, dst + i0, k, index_base + i0);
+        if (rc) return rc;
+    }
+    return SOGPU_OK;
+}
+
+/* end of the routing: reservations at the receivers, copies over NVLink, barrier (barrier = 0: the caller
+ * makes sure by other means that every rank's push has completed before sogpu_domain_solve is enqueued) */
+extern "C" int sogpu_domain_push(sogpu_t *h, int barrier)
+{
+    if (!h || !h->dom) return set_err(SOGPU_ERR_ARG, "sogpu_domain_push: no open domain");
+    DomainState *D = h->dom;
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int R = D->cfg.n_ranks;
+    if (R > 1) {
+        PushArgs a;
+        memset(&a, 0, sizeof(a));
+        a.R = R; a.me = D->cfg.rank; a.parity = D->parity;
+        for (int d = 0; d < R; ++d) { a.peer_ctrl[d] = D->peer_ctrl[d]; a.peer_recv[d] = D->peer_recv[D->parity][d]; }
+        a.stage = D->stage; a.stage_cap = (unsigned long long)D->cfg.stage_cap; a.recv_cap = (unsigned long long)D->cfg.recv_cap;
+        a.counts = D->d_counts; a.flags = D->d_flags;
+        {
+            ProfScope p(h, KID_PUSH, 0.0, 2);
+            k_push_reserve<<<1, 32, 0, s>>>(a);
+            k_push_copy<<<dim3((unsigned)std::max(1, h->sm_count * 4 / R), (unsigned)R), 256, 0, s>>>(a);
+        }
+        if (barrier) {
+            ProfScope p(h, KID_BARRIER);
+            k_dom_barrier<<<1, 32, 0, s>>>(a, D->ctrl, D->epoch, (long long)20000000000LL);   /* ~10 s */
+        }
+    }
+    CU(cudaGetLastError());
+    D->routed = true;
+    return SOGPU_OK;
+}
+
+/* grid over what arrived + SO solve of the halos this rank owns.  d_out_n / d_out_m (device, nh entries of the
+ * WHOLE catalog, may be NULL): N_Delta or code / M_Delta for own halos, CODE_NOT_MINE (0x80808080) elsewhere. */
+extern "C" int sogpu_domain_solve(sogpu_t *h, float thr, int32_t nM, void *d_out_n, void *d_out_m)
+{
+    if (!h || !h->dom) return set_err(SOGPU_ERR_ARG, "sogpu_domain_solve: no open domain");
+    DomainState *D = h->dom;
+    if (!D->routed) return set_err(SOGPU_ERR_ARG, "sogpu_domain_solve: call sogpu_domain_push first");
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int32_t nh = D->nh;
+    k_dom_nrecv<<<1, 32, 0, s>>>(D->ctrl, D->parity, (unsigned long long)D->cfg.recv_cap, D->d_nrecv32,
+                                 D->d_counts + 3 * ROUTE_MAXR, D->d_flags);
+    /* the grid build reads the count on the device */
+    h->n = D->cfg.recv_cap;
+    h->d_in = D->recv[D->parity];
+    h->indexed = true;
+    h->indexed_mass = D->cfg.mass;
+    h->n_total = D->cfg.n_total;
+    h->mass_state = -1;
+    h->d_n_dev = D->d_nrecv32;
+    h->n_hint = D->n_hint;
+    const int keep_launches = h->stats.last_kernel_launches;
+    h->mask_ready = D->d_mymask;
+    int rc = build_grid_impl(h, -1, D->n_balls);
+    h->d_n_dev = nullptr;
+    if (rc) return rc;
+    const int build_launches = h->stats.last_kernel_launches;
+    rc = ensure_query(h, nh);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(h->d_out_n, 0x80, (size_t)nh * sizeof(int32_t), s));
+    CU(cudaMemsetAsync(h->d_out_m, 0x80, (size_t)nh * sizeof(float), s));
+    h->q_owner = D->d_owner; h->q_me = D->cfg.rank;
+    rc = run_query(h, h->d_centers, h->d_rgtp, nh, thr, nM);
+    h->q_owner = nullptr;
+    if (rc) return rc;
+    h->stats.last_kernel_launches += keep_launches + build_launches;
+    if (d_out_n) CU(cudaMemcpyAsync(d_out_n, h->d_out_n, (size_t)nh * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+    if (d_out_m) CU(cudaMemcpyAsync(d_out_m, h->d_out_m, (size_t)nh * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return SOGPU_OK;
+}
+
+/* synchronises: what this rank received / sent in the last step and the step's error flags
+ * (bit0 staging overflow, bit1 receive overflow here, bit2 receive overflow at a peer, bit3 barrier timeout);
+ * owner (host, nh bytes, may be NULL) = owner rank of every halo */
+extern "C" int sogpu_domain_result(sogpu_t *h, int64_t *n_recv, int64_t *n_sent, uint32_t *flags, unsigned char *owner)
+{
+    if (!h || !h->dom) return set_err(SOGPU_ERR_ARG, "sogpu_domain_result: no open domain");
+    DomainState *D = h->dom;
+    CU(cudaSetDevice(h->device));
+    unsigned long long c[3 * ROUTE_MAXR + 1];
+    uint32_t f = 0;
+    CU(cudaMemcpyAsync(c, D->d_counts, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(&f, D->d_flags, sizeof(f), cudaMemcpyDeviceToHost, h->stream));
+    if (owner) CU(cudaMemcpyAsync(owner, D->d_owner, (size_t)D->nh, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    int64_t sent = 0;
+    for (int d = 0; d < D->cfg.n_ranks; ++d) sent += (int64_t)c[d];
+    if (n_recv) *n_recv = (int64_t)c[3 * ROUTE_MAXR];
+    if (n_sent) *n_sent = sent;
+    if (flags) *flags = f;
+    if (!(f & 2u) && c[3 * ROUTE_MAXR] > 0) D->n_hint = (int64_t)c[3 * ROUTE_MAXR];
+    return SOGPU_OK;
+}

@@ -652,10 +652,6 @@ __global__ void __launch_bounds__(RT_NT, 3) k_lvl_partition_rt(const float4 *__r
  * (an L2 hit).  Stores go straight to the final slot: the bucket's whole output range (16-50 KB)
  * is written by this CTA within a microsecond, so the 16-byte stores merge in L2.  Only the cell
  * counts live in shared memory (16 KB), which leaves room for 4 CTAs per SM. */
-#ifndef BR_NT
-#define BR_NT 256
-#define BR_MINB 4
-#endif
 #define BR_IT 8
 
 /* focused builds: most final buckets are empty and lie outside the focus mask.  One thread per bucket
@@ -700,6 +696,18 @@ __global__ void __launch_bounds__(256) k_bucket_live(GridDev g, int cell_bits, u
     }
 }
 
+/* `count` (<= 32) consecutive bits of the focus mask starting at bit `bit0` */
+__device__ __forceinline__ uint32_t mask_bits_at(const uint32_t *__restrict__ mask, uint32_t bit0, uint32_t count)
+{
+    const uint32_t w = bit0 >> 5, lo = bit0 & 31u;
+    uint32_t v = __ldg(mask + w) >> lo;
+    if (lo + count > 32u) v |= __ldg(mask + w + 1) << (32u - lo);
+    return count >= 32u ? v : (v & ((1u << count) - 1u));
+}
+
+/* BR_NT threads per bucket: 256 for buckets of ~1000 particles, 64 for the sparse buckets of focused grids
+ * (a few hundred particles in 4096 cells: four times as many buckets in flight per SM) */
+template <int BR_NT, int BR_MINB>
 __global__ void __launch_bounds__(BR_NT, BR_MINB) k_bucket_sort_rt(const float4 *__restrict__ in4, GridDev g, int cell_bits,
                                                              uint32_t n_buckets, const uint32_t *__restrict__ bstart,
                                                              float4 *__restrict__ sorted, uint32_t *__restrict__ ce,
@@ -708,7 +716,7 @@ __global__ void __launch_bounds__(BR_NT, BR_MINB) k_bucket_sort_rt(const float4 
                                                              const uint32_t *__restrict__ live_n)
 {
     __shared__ __align__(16) uint32_t cnt[BKT_CELLS];
-    __shared__ uint32_t ws[BR_NT / 32];
+    __shared__ uint32_t ws[BR_NT / 32 + 1];
     const int ncells = 1 << cell_bits;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     /* scan layout: thread t owns the `per` consecutive cells starting at t*per; with >= 1024 cells
@@ -731,8 +739,36 @@ __global__ void __launch_bounds__(BR_NT, BR_MINB) k_bucket_sort_rt(const float4 
             nx0 = __ldg(bstart + nxb); nx1 = __ldg(bstart + nxb + 1);
         }
         uint32_t *ceb = ce + ((size_t)b << cell_bits);
+        /* Focused grids: the queries read ce[] only at cells inside the mask and at the entry right behind
+         * one (every ball is checked against the mask first), so a group of four entries is stored only if
+         * one of the cells [c-1, c+3] is marked: a sparse grid writes a few percent of its cell table.
+         * This thread's `per` cells lie in one row of cells (per <= 64 <= cells per row). */
+        const bool sparse = vec && g.mask != nullptr && per <= g.nc && g.nc >= 64;
+        uint32_t mrow = 0, ix0 = 0;
+        if (sparse) {
+            const uint32_t key0 = (b << cell_bits) + (uint32_t)(t * per);
+            const uint32_t rk = key0 >> g.lb;
+            const uint32_t m = (1u << g.tb) - 1u, lo = rk & ((1u << (2 * g.tb)) - 1u), hi = rk >> (2 * g.tb);
+            const uint32_t iy = ((hi & ((1u << (g.lb - g.tb)) - 1u)) << g.tb) | (lo & m);
+            const uint32_t iz = ((hi >> (g.lb - g.tb)) << g.tb) | (lo >> g.tb);
+            ix0 = key0 & (uint32_t)(g.nc - 1);
+            mrow = ((iz >> g.ms) << (2 * g.mb)) | ((iy >> g.ms) << g.mb);
+        }
+        auto group_needed = [&](int k) -> bool {
+            if (!sparse) return true;
+            const uint32_t c = ix0 + 4u * (uint32_t)k;                    /* first cell of the group, inside the row */
+            if (c == 0u) return true;                                     /* (its predecessor is the previous row's last cell) */
+            const uint32_t m0 = (c - 1u) >> g.ms, m1 = (c + 3u) >> g.ms;
+            return mask_bits_at(g.mask, mrow + m0, m1 - m0 + 1u) != 0u;
+        };
         if (nb == 0) {                   /* empty bucket (focused builds): only its cell-table slice */
-            for (int c = t; c < ncells; c += BR_NT) ceb[c] = b0;
+            if (sparse) {
+                uint4 *ce4 = reinterpret_cast<uint4 *>(ceb);
+                for (int k = 0; k < per / 4; ++k)
+                    if (group_needed(k)) ce4[t * (per / 4) + k] = make_uint4(b0, b0, b0, b0);
+            } else {
+                for (int c = t; c < ncells; c += BR_NT) ceb[c] = b0;
+            }
             continue;
         }
         const bool in_regs = nb <= (uint32_t)(BR_NT * BR_IT);
@@ -790,7 +826,7 @@ __global__ void __launch_bounds__(BR_NT, BR_MINB) k_bucket_sort_rt(const float4 
                 e.x = run; e.y = e.x + v.x; e.z = e.y + v.y; e.w = e.z + v.z;
                 run = e.w + v.w;
                 cnt4[t * G + k] = e;
-                ce4[t * G + k] = make_uint4(b0 + e.x, b0 + e.y, b0 + e.z, b0 + e.w);
+                if (group_needed(k)) ce4[t * G + k] = make_uint4(b0 + e.x, b0 + e.y, b0 + e.z, b0 + e.w);
             }
         } else {
             uint32_t s = 0;

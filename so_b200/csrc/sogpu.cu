@@ -104,6 +104,7 @@ struct GridDev {
     double dg0[3], dinvh[3], dh[3];
     double bmax_pruned;       /* balls at least this large visit every cell                  */
     const uint32_t *mask;     /* focused build: bit per coarse cell that was kept (NULL = all) */
+    int nofilter;             /* the build keeps every input particle (the mask still bounds the balls) */
     int mb, ms;               /* mask cells per axis = 2^mb; fine cell coordinate >> ms        */
     double mask_rmin;         /* smallest half-width a halo marks in the mask                  */
 };
@@ -158,7 +159,7 @@ __device__ __forceinline__ uint32_t cell_key_kept(const float4 &p, const GridDev
     uint32_t ix = cell_coord(p.x, g.g0[0], g.invh[0], mask);
     uint32_t iy = cell_coord(p.y, g.g0[1], g.invh[1], mask);
     uint32_t iz = cell_coord(p.z, g.g0[2], g.invh[2], mask);
-    kept = !g.mask || mask_bit(g, ix >> g.ms, iy >> g.ms, iz >> g.ms);
+    kept = !g.mask || g.nofilter || mask_bit(g, ix >> g.ms, iy >> g.ms, iz >> g.ms);
     return (row_key(iy, iz, g.lb, g.tb) << g.lb) | ix;
 }
 
@@ -1209,10 +1210,11 @@ __device__ __forceinline__ void warp_append(bool pred, int32_t item, int32_t *li
  * ball (1.2 R) about 1.3x that */
 __global__ void k_classify(const float *__restrict__ rgtp, int nh, float thr, const so_mass_table *mt,
                            float small_max, float huge_min, int32_t *small_list, uint32_t *small_n,
-                           int32_t *big_list, uint32_t *big_n, int32_t *huge_list, uint32_t *huge_n)
+                           int32_t *big_list, uint32_t *big_n, int32_t *huge_list, uint32_t *huge_n,
+                           const unsigned char *__restrict__ owner, int me)
 {
     int h = blockIdx.x * blockDim.x + threadIdx.x;          /* blockDim is a multiple of 32: whole warps stay */
-    const bool in = h < nh;
+    const bool in = h < nh && (!owner || owner[h] == (unsigned char)me);   /* domain steps: my share only */
     float r = 1.25f * (in ? rgtp[h] : 0.0f);
     float m = mt->n > 0 ? mt->m : 1.0f;
     float est = 1.3f * thr * 4.18879f * r * r * r / m;
@@ -2004,12 +2006,13 @@ __global__ void __launch_bounds__(256) k_member_unkeys(const unsigned long long 
 enum {
     KID_LVL_HIST = 0, KID_LVL_SCAN, KID_LVL_PARTITION, KID_BUCKET_SORT, KID_MASS_TABLE, KID_CLASSIFY,
     KID_QUERY_WARP, KID_QUERY_BLOCK, KID_OFFSETS, KID_EMIT_WARP, KID_EMIT_BLOCK, KID_BALL_GATHER,
-    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_VCIRC, KID_TAG, KID_ROUTE, KID_N
+    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_VCIRC, KID_TAG, KID_ROUTE, KID_ASSIGN, KID_PUSH, KID_BARRIER, KID_N
 };
 static const char *const g_kernel_names[KID_N] = {
     "k_lvl_hist", "k_scan", "k_lvl_partition", "k_bucket_sort", "k_mass_table", "k_classify",
     "k_so_query<32>", "k_so_query<256>", "k_offsets", "k_so_emit<32>", "k_so_emit<256>", "k_ball_gather",
-    "k_so_query<1024>", "k_so_emit<1024>", "k_mark_mask", "k_vcirc", "k_tag_claim+settle", "k_route"};
+    "k_so_query<1024>", "k_so_emit<1024>", "k_mark_mask", "k_vcirc", "k_tag_claim+settle", "k_route",
+    "k_assign", "k_push", "k_dom_barrier"};
 
 struct ProfRec { int kid, launches; cudaEvent_t a, b; };
 
@@ -2054,6 +2057,8 @@ struct sogpu {
     size_t scan1_max;                /* bucket tables up to this many entries are scanned by one block */
     bool use_tma;                    /* sogpu_set_tma_staging */
     double mask_rmin_cells;          /* focus masks: minimum half-width per halo, in coarse cells */
+    int mask_bits;                   /* focus masks: at most 2^mask_bits coarse cells per axis */
+    const uint32_t *mask_ready;      /* build_grid_impl(focus_nh < 0): this mask, prepared by the caller */
     bool indexed;                    /* d_in is {x,y,z,global index} of one rank's share (domain runs) */
     float indexed_mass;
     int64_t n_total;                 /* particles of the whole snapshot (grid resolution of a domain run) */
@@ -2129,6 +2134,13 @@ struct sogpu {
 
     sogpu_stats_t stats;
     int sm_count;
+
+    /* device-side particle count of the next build (domain steps: what arrived is only known on the device) */
+    const uint32_t *d_n_dev;         /* NULL: h->n is exact */
+    int64_t n_hint;                  /* expected count: sizes the launch and the bucket table */
+    const unsigned char *q_owner;    /* query only the halos with q_owner[h] == q_me (NULL: all) */
+    int q_me;
+    struct DomainState *dom;         /* sogpu_domain_open */
 };
 
 static cudaEvent_t prof_event(sogpu *h)
@@ -2200,6 +2212,8 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     h->two_level = -1;
     h->first_ball = 2;
     h->mask_rmin_cells = 0.75;
+    h->mask_bits = 9;
+    if (const char *e = getenv("SOGPU_MASK_BITS")) h->mask_bits = std::min(9, std::max(4, atoi(e)));
     h->scan1_max = (size_t)1 << 18;
     h->qgrid32 = 4; h->qgrid256 = 1; h->qorder = 0;    /* (measured: pending CTAs of the 256-thread class hold back the warp class) */
     if (const char *e = getenv("SOGPU_QGRID32")) h->qgrid32 = std::max(1, atoi(e));
@@ -2287,11 +2301,14 @@ static void free_query(sogpu *h)
     h->cap_h = 0;
 }
 
+extern "C" int sogpu_domain_close(sogpu_t *h);
+
 extern "C" void sogpu_destroy(sogpu_t *h)
 {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    sogpu_domain_close(h);
     free_grid(h);
     free_query(h);
     cudaFree(h->d_in_owned);
@@ -2613,9 +2630,13 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
     const int nc = pick_cells(h->indexed ? h->n_total : h->n, h->ppc, &lb);   /* one resolution for every rank of a domain run */
     const int64_t ncell = (int64_t)nc * nc * nc;
     const int keybits = 3 * lb;
+    /* device-side particle count (domain steps): h->n is the capacity of the input buffer, n_work the
+     * expected count that sizes the bucket table and the launches; every kernel reads the true count */
+    const uint32_t *n_dev0 = h->d_n_dev;
+    const int64_t n_work = n_dev0 ? std::max<int64_t>(std::min(h->n_hint, h->n), 1) : h->n;
     /* final buckets: ~1024 particles on average and at most BKT_CELLS cells each */
     int cbt = 0;
-    while (((int64_t)BKT_AVG << cbt) < h->n) ++cbt;
+    while (((int64_t)BKT_AVG << cbt) < n_work) ++cbt;
     if (h->two_level == 0) cbt = 0;
     if (cbt < keybits - 12) cbt = keybits - 12;
     if (cbt > keybits) cbt = keybits;
@@ -2662,28 +2683,29 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         lmin = std::min(lmin, Lk);
     }
     g.bmax_pruned = 0.5 * lmin - 2.0 * hmax;
-    g.mask = nullptr; g.mb = 0; g.ms = 0;
+    g.mask = nullptr; g.mb = 0; g.ms = 0; g.nofilter = 0;
     g.indexed = h->indexed ? 1 : 0;
     g.use_tma = h->use_tma ? 1 : 0;
 
     cudaStream_t s = h->stream;
-    const double N = (double)h->n;
+    const double N = (double)n_work;
     h->focused = false;
-    if (focus_nh > 0) {   /* (L == 0, tiny inputs: nothing is filtered, but the mask still guards the balls) */
-        const int mb = std::min(lb, 8);
+    if (focus_nh != 0) {   /* (L == 0, tiny inputs: nothing is filtered, but the mask still guards the balls) */
+        const int mb = std::min(lb, h->mask_bits);
         const size_t words = ((size_t)1 << (3 * mb)) / 32 + 1;
-        if (!h->d_mask) CU(cudaMalloc(&h->d_mask, (((size_t)1 << 24) / 32 + 1) * sizeof(uint32_t)));
-        CU(cudaMemsetAsync(h->d_mask, 0, words * sizeof(uint32_t), s));
+        if (!h->d_mask) CU(cudaMalloc(&h->d_mask, (((size_t)1 << 27) / 32 + 1) * sizeof(uint32_t)));
         g.mb = mb; g.ms = lb - mb;
         g.mask_rmin = h->mask_rmin_cells * hmax * (double)(1 << g.ms);
-        GridDev gm = g;
-        gm.mask = h->d_mask;
-        {
+        if (focus_nh > 0) {     /* (focus_nh < 0: h->d_mask already holds this rank's mask, see domain_step.cuh) */
+            CU(cudaMemsetAsync(h->d_mask, 0, words * sizeof(uint32_t), s));
+            GridDev gm = g;
+            gm.mask = h->d_mask;
             ProfScope p(h, KID_MARK_MASK);
             k_mark_mask<<<std::min((focus_nh + 7) / 8, h->sm_count * 8), 256, 0, s>>>(gm, h->d_centers, h->d_rgtp,
                                                                                       focus_nh, focus_balls, h->d_mask);
         }
-        g.mask = h->d_mask;
+        g.mask = (focus_nh < 0 && h->mask_ready) ? h->mask_ready : h->d_mask;
+        g.nofilter = (focus_nh < 0) ? 1 : 0;       /* domain steps: everything that was routed here lies inside the mask */
         h->focused = true;
         h->focus_balls = focus_balls;
     }
@@ -2727,7 +2749,7 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         CU(cudaFuncSetAttribute(k_lvl_partition_rt<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RT_SMEM));
         attr_done = true;
     }
-    const int64_t tiles = (h->n + LVL_T - 1) / LVL_T;
+    const int64_t tiles = (n_work + LVL_T - 1) / LVL_T;
     const int hist_grid = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 8);
     const int part_grid = (int)std::min<int64_t>(tiles, (int64_t)h->sm_count * 2);
 
@@ -2738,9 +2760,10 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         LevelDesc lv; lv.shift = 0; lv.db = 0; lv.pshift = 32; lv.n_parents = 1;
         CU(cudaMemsetAsync(h->d_lvl_cursor[0], 0, 2 * sizeof(uint32_t), s));
         { ProfScope p(h, KID_LVL_HIST, 16.0 * N);
-          k_lvl_hist<true><<<hist_grid, 256, 0, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[0], h->d_massmm, nullptr); }
+          k_lvl_hist<true><<<hist_grid, 256, 0, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[0], h->d_massmm, n_dev0); }
         { int rc = launch_mass_table(h); if (rc) return rc; }
         k_store_u32<<<1, 32, 0, s>>>(h->d_lvl_start[0], 0u, h->d_lvl_start[0] + 1, (uint32_t)h->n);
+        if (n_dev0) k_copy_u32<<<1, 32, 0, s>>>(h->d_lvl_start[0] + 1, n_dev0);
     }
     for (int l = 0; l < L; ++l) {
         LevelDesc lv;
@@ -2754,11 +2777,11 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         uint32_t *dst_key = h->d_key[l & 1];
         const uint32_t *pstart = l ? h->d_lvl_start[l - 1] : nullptr;
         /* particles that survive level 0 (== N unless the build is focused): sentinel of its scan */
-        const uint32_t *n_dev = (l && h->focused) ? h->d_lvl_start[0] + ((size_t)1 << db[0]) : nullptr;
+        const uint32_t *n_dev = (l && h->focused) ? h->d_lvl_start[0] + ((size_t)1 << db[0]) : n_dev0;
         CU(cudaMemsetAsync(h->d_lvl_cursor[l], 0, M * sizeof(uint32_t), s));
         {
             ProfScope p(h, KID_LVL_HIST, (l ? 4.0 : 16.0) * N);
-            if (l == 0) k_lvl_hist<true><<<hist_grid, 256, 0, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], h->d_massmm, nullptr);
+            if (l == 0) k_lvl_hist<true><<<hist_grid, 256, 0, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], h->d_massmm, n_dev);
             else k_lvl_hist<false><<<hist_grid, 256, 0, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], h->d_massmm, n_dev);
         }
         if (l == 0) { int rc = launch_mass_table(h); if (rc) return rc; }
@@ -2777,14 +2800,14 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         {
             ProfScope p(h, KID_LVL_PARTITION, ((l ? 20.0 : 16.0) + 16.0 + (last ? 0.0 : 4.0)) * N);
             if (h->two_level == 2) {       /* staged variant (tile sorted in shared memory first) */
-                if (l == 0 && !last) k_lvl_partition<true, true><<<part_grid, LVL_THREADS, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, nullptr);
-                else if (l == 0) k_lvl_partition<true, false><<<part_grid, LVL_THREADS, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, nullptr);
+                if (l == 0 && !last) k_lvl_partition<true, true><<<part_grid, LVL_THREADS, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, n_dev);
+                else if (l == 0) k_lvl_partition<true, false><<<part_grid, LVL_THREADS, part_smem, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, n_dev);
                 else if (!last) k_lvl_partition<false, true><<<part_grid, LVL_THREADS, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key, n_dev);
                 else k_lvl_partition<false, false><<<part_grid, LVL_THREADS, part_smem, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key, n_dev);
             } else {
-                const int sg = (int)std::min<int64_t>((h->n + RT_T - 1) / RT_T, (int64_t)h->sm_count * 3);
-                if (l == 0 && !last) k_lvl_partition_rt<true, true><<<sg, RT_NT, RT_SMEM, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, nullptr);
-                else if (l == 0) k_lvl_partition_rt<true, false><<<sg, RT_NT, RT_SMEM, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, nullptr);
+                const int sg = (int)std::min<int64_t>((n_work + RT_T - 1) / RT_T, (int64_t)h->sm_count * 3);
+                if (l == 0 && !last) k_lvl_partition_rt<true, true><<<sg, RT_NT, RT_SMEM, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, n_dev);
+                else if (l == 0) k_lvl_partition_rt<true, false><<<sg, RT_NT, RT_SMEM, s>>>(src, nullptr, h->n, g, lv, nullptr, h->d_lvl_cursor[l], dst, dst_key, n_dev);
                 else if (!last) k_lvl_partition_rt<false, true><<<sg, RT_NT, RT_SMEM, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key, n_dev);
                 else k_lvl_partition_rt<false, false><<<sg, RT_NT, RT_SMEM, s>>>(src, src_key, h->n, g, lv, pstart, h->d_lvl_cursor[l], dst, dst_key, n_dev);
             }
@@ -2814,11 +2837,18 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
                 k_bucket_live<<<(nb + 255) / 256, 256, 0, s>>>(g, cell_bits, nb, bstart, h->d_ce, h->d_live, h->d_live + nb);
                 live = h->d_live; live_n = h->d_live + nb;
             }
-            k_bucket_sort_rt<<<grid, BR_NT, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce,
-                                                    (L == 0 && !g.indexed) ? 1 : 0, live, live_n);
+            if (n_work / (int64_t)nb < 160 && nb >= 4096u) {      /* sparse buckets: small CTAs, many in flight */
+                grid = (int)std::min<int64_t>((int64_t)nb, (int64_t)h->sm_count * 48);
+                k_bucket_sort_rt<64, 12><<<grid, 64, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce,
+                                                             (L == 0 && !g.indexed) ? 1 : 0, live, live_n);
+            } else {
+                k_bucket_sort_rt<256, 4><<<grid, 256, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce,
+                                                              (L == 0 && !g.indexed) ? 1 : 0, live, live_n);
+            }
         }
     }
     if (h->focused) k_copy_u32<<<1, 32, 0, s>>>(h->d_ce + ncell, h->d_lvl_start[0] + ((size_t)1 << db[0]));
+    else if (n_dev0) k_copy_u32<<<1, 32, 0, s>>>(h->d_ce + ncell, n_dev0);
     else k_store_u32<<<1, 32, 0, s>>>(h->d_ce + ncell, (uint32_t)h->n, nullptr, 0u);
     CU(cudaStreamWaitEvent(s, h->ev_join[0], 0));         /* the mass table (side stream) */
     CU(cudaGetLastError());
@@ -2945,7 +2975,7 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
         ProfScope p(h, KID_CLASSIFY);
         k_classify<<<(nh + 255) / 256, 256, 0, s>>>(d_rgtp, nh, thr, h->d_mt, small_max, huge_min, h->d_small,
                                                     h->d_counters + 0, h->d_big, h->d_counters + 1, h->d_huge,
-                                                    h->d_counters + 13);
+                                                    h->d_counters + 13, h->q_owner, h->q_me);
     }
     QueryArgs a;
     a.g = h->g;
@@ -3659,7 +3689,7 @@ static void domain_geometry(sogpu *h, int64_t n_total, GridDev &g)
         lmin = std::min(lmin, Lk);
     }
     g.bmax_pruned = 0.5 * lmin - 2.0 * hmax;
-    g.mb = std::min(lb, 8); g.ms = lb - g.mb;
+    g.mb = std::min(lb, h->mask_bits); g.ms = lb - g.mb;
     g.mask_rmin = h->mask_rmin_cells * hmax * (double)(1 << g.ms);
 }
 
@@ -3668,7 +3698,7 @@ extern "C" int sogpu_domain_mask_words(sogpu_t *h, int64_t n_total, int64_t *wor
     if (!h || !words || n_total <= 0) return set_err(SOGPU_ERR_ARG, "sogpu_domain_mask_words: bad argument");
     int lb;
     pick_cells(n_total, h->ppc, &lb);
-    *words = (int64_t)(((size_t)1 << (3 * std::min(lb, 8))) / 32 + 1);
+    *words = (int64_t)(((size_t)1 << (3 * std::min(lb, h->mask_bits))) / 32 + 1);
     return SOGPU_OK;
 }
 
@@ -3718,8 +3748,8 @@ static int route_args(sogpu *h, RouteArgs &a, int64_t n_total, const void *d_sli
     a.R = n_ranks;
     const uint32_t n_cells = 1u << (3 * a.g.mb);
     if (!h->d_route_table) {
-        CU(cudaMalloc(&h->d_route_table, ((size_t)1 << 24) * sizeof(unsigned short)));
-        CU(cudaMalloc(&h->d_route_any, (((size_t)1 << 24) / 32 + 1) * sizeof(uint32_t)));
+        CU(cudaMalloc(&h->d_route_table, ((size_t)1 << 27) * sizeof(unsigned short)));
+        CU(cudaMalloc(&h->d_route_any, (((size_t)1 << 27) / 32 + 1) * sizeof(uint32_t)));
     }
     if (build_table)
         k_route_table<<<(unsigned)((words + 255) / 256), 256, 0, h->stream>>>((const uint32_t *)d_masks, (uint32_t)words, n_ranks,
@@ -3831,6 +3861,8 @@ extern "C" int sogpu_peer_free(sogpu_t *h, void *ptr)
     CU(cudaFree(ptr));
     return SOGPU_OK;
 }
+
+#include "domain_step.cuh"
 
 /* debug: device clock (ns) of the first CTA start / last CTA end of the huge, big, small, deferred query kernels */
 extern "C" int sogpu_debug_timeline(sogpu_t *h, uint64_t *out16)

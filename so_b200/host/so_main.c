@@ -130,7 +130,7 @@ int main(int argc, char **argv)
 
     kdInit(&kd, nBucket, fPeriod, fCenter, 0, nMembers, bPeriodic, bDark, bGas, bStar, bMark, bPot);
     kd->iDevice = iDevice;
-    kd->bSkipGrpArray = !bGrp;                        /* PINIT.iGrp of conflict-free groups is only read by kdWriteArray */
+    kd->bSkipGrpArray = 0;                            /* PINIT.iGrp is read by kdWriteArray AND by kdOutStats (kd2.c:1360), which always runs */
     kd->bSkipVcm = !bGtp;                             /* GRPNODE.vcm is only read by kdWriteGTP */
     kdGpu(kd);                                        /* the snapshot is streamed to the device as it is read */
     kdPhase(NULL, &tPhase);

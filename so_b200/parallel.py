@@ -380,3 +380,184 @@ def _as_tensor_i32(ptr, n, dev):
     a = _Arr()
     a.__cuda_array_interface__ = {"shape": (max(n, 1),), "typestr": "<i4", "data": (int(ptr), False), "version": 3}
     return torch.as_tensor(a, device=dev)[:n]
+
+
+# ---------------------------------------------------------------------------------------------
+# the domain STEP: stream-ordered from the slice to the results (so_b200/csrc/domain_step.cuh)
+# ---------------------------------------------------------------------------------------------
+
+NOT_MINE = np.int32(-2139062144)      # 0x80808080: halo solved by another rank
+
+FLAG_TEXT = {1: "staging area too small", 2: "receive buffer too small", 4: "a peer's receive buffer too small",
+             8: "a peer never reached the barrier"}
+
+
+def flags_text(flags):
+    return ", ".join(t for b, t in FLAG_TEXT.items() if flags & b) or "ok"
+
+
+def default_caps(n_total, n_ranks, frac=0.30):
+    """(recv_cap, stage_cap) in records: the share of the snapshot some halo can reach is well below `frac`
+    for the BASELINE catalogs (0.18 at 1024^3 / 10^5 halos); overflow is detected and reported, never silent."""
+    recv = int(n_total * frac / n_ranks * 1.5) + (1 << 16)
+    stage = int(n_total * frac / (n_ranks * n_ranks) * 2.0) + (1 << 16) if n_ranks > 1 else 0
+    return min(recv, int(n_total) + 1024), stage
+
+
+class DomainStep:
+    """One rank of a domain run (one process per GPU).  Per step, identical calls on every rank:
+
+        begin(catalog) -> route(slice) -> push -> solve        all enqueued, no host round trip
+        result()                                                synchronises: flags, counts, owners
+
+    The ranks only meet at the flag barrier inside push (peer memory); torch.distributed is used once,
+    at construction, to exchange the cudaIpc handles of the receive buffers."""
+
+    def __init__(self, gpu, n_total, mass, recv_cap=None, stage_cap=None, period=(1.0, 1.0, 1.0),
+                 center=(0.0, 0.0, 0.0), group=None):
+        import torch.distributed as dist
+        self.g = gpu
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        rc, sc = default_caps(n_total, self.world)
+        self.recv_cap, self.stage_cap = int(recv_cap or rc), int(stage_cap if stage_cap is not None else sc)
+        handles = gpu.domain_open(self.rank, self.world, n_total, mass, self.recv_cap, self.stage_cap, period, center)
+        self._opened = []
+        if self.world > 1:
+            allh = [None] * self.world
+            dist.all_gather_object(allh, handles, group=group)
+            ptrs = [[0] * self.world for _ in range(3)]
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                for k in range(3):
+                    if k == 1 and allh[r][1] == allh[r][0]:
+                        ptrs[1][r] = ptrs[0][r]
+                        continue
+                    ptrs[k][r] = gpu.peer_open(allh[r][k])
+                    self._opened.append(ptrs[k][r])
+            gpu.domain_connect(ptrs[0], ptrs[1], ptrs[2])
+            dist.barrier(group=group)          # every control block is zeroed and mapped before the first step
+        self.group = group
+
+    def step(self, d_centers, d_rgtp, nh, n_balls, d_slice, n_slice, index_base, thr, n_members=8,
+             d_out_n=0, d_out_m=0, host_xyz=0):
+        g = self.g
+        g.domain_begin(d_centers, d_rgtp, nh, n_balls)
+        if host_xyz:
+            g.domain_route_host(host_xyz, n_slice, index_base, d_slice)
+        else:
+            g.domain_route(d_slice, n_slice, index_base)
+        g.domain_push(True)
+        g.domain_solve(thr, n_members, d_out_n, d_out_m)
+
+    def result(self, nh=0):
+        return self.g.domain_result(nh)
+
+    def close(self):
+        import torch
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+        for p in self._opened:
+            self.g.peer_close(p)
+        self._opened = []
+        self.g.domain_close()
+
+
+class VirtualDomainStep:
+    """All ranks of a domain run inside ONE process (tests; also a one-process multi-GPU run when `devices`
+    lists several ordinals): one handle per rank, plain device pointers instead of cudaIpc handles.  On a single
+    device the peer barrier is replaced by a device synchronisation between the push and the solve phases (the
+    ranks' kernels are serialised there anyway)."""
+
+    def __init__(self, n_ranks, n_total, mass, devices=None, recv_cap=None, stage_cap=None, period=(1.0, 1.0, 1.0)):
+        from so_b200 import api
+        self.R = int(n_ranks)
+        self.devices = list(devices) if devices else [0] * self.R
+        self.multi = len(set(self.devices)) > 1
+        rc, sc = default_caps(n_total, self.R)
+        self.recv_cap, self.stage_cap = int(recv_cap or rc), int(stage_cap if stage_cap is not None else sc)
+        self.gs = [api.SoGpu(device=self.devices[r]) for r in range(self.R)]
+        self.n_total, self.mass, self.period = int(n_total), mass, tuple(period)
+        for r, g in enumerate(self.gs):
+            g.domain_open(r, self.R, n_total, mass, self.recv_cap, self.stage_cap, period)
+        ptr = [g.domain_pointers() for g in self.gs]
+        for r, g in enumerate(self.gs):
+            for q in range(self.R):
+                if self.devices[q] != self.devices[r]:
+                    g.enable_peer_access(self.devices[q])
+            if self.R > 1:
+                g.domain_connect([p[0] for p in ptr], [p[1] for p in ptr], [p[2] for p in ptr])
+
+    def _sync(self):
+        import torch
+        for d in set(self.devices):
+            torch.cuda.synchronize(d)
+
+    def run(self, xyzm, centers, rgtp, thr, n_members=8, n_balls=4, want_members=True):
+        """xyzm: list of per-rank device tensors (n_r, 4) float32, rank r's slice starting at global index
+        sum(n_0..n_{r-1}); centers/rgtp: the whole catalog (numpy).  Returns merged catalog-order results."""
+        import torch
+        R, nh = self.R, len(rgtp)
+        base = np.concatenate([[0], np.cumsum([len(x) for x in xyzm])]).astype(np.int64)
+        cat = []
+        for r in range(R):
+            dev = torch.device("cuda", self.devices[r])
+            cat.append((torch.from_numpy(np.ascontiguousarray(centers, np.float32)).to(dev),
+                        torch.from_numpy(np.ascontiguousarray(rgtp, np.float32)).to(dev),
+                        torch.empty(nh, dtype=torch.int32, device=dev), torch.empty(nh, dtype=torch.float32, device=dev)))
+        out = {"rvir": np.zeros(nh, np.float32), "mvir": np.zeros(nh, np.float32), "ndelta": np.zeros(nh, np.int32),
+               "members": [None] * nh, "rounds": 0, "n_recv": [], "owner": None}
+        balls = int(n_balls)
+        done = np.zeros(nh, bool)
+        while not done.all():
+            out["rounds"] += 1
+            self._sync()
+            for r, g in enumerate(self.gs):
+                g.domain_begin(cat[r][0].data_ptr(), cat[r][1].data_ptr(), nh, balls)
+                g.domain_route(xyzm[r].data_ptr(), len(xyzm[r]), int(base[r]))
+            if not self.multi:
+                self._sync()                      # one device: reservations of every rank before any push reads them
+            for g in self.gs:
+                g.domain_push(barrier=self.multi)
+            if not self.multi:
+                self._sync()
+            for r, g in enumerate(self.gs):
+                g.keep_member_d2(True)
+                g.domain_solve(thr, n_members, cat[r][2].data_ptr(), cat[r][3].data_ptr())
+            self._sync()
+            n_recv = []
+            for r, g in enumerate(self.gs):
+                res = g.domain_result(nh)
+                if res["flags"]:
+                    raise RuntimeError("domain step, rank %d: %s" % (r, flags_text(res["flags"])))
+                n_recv.append(res["n_recv"])
+                owner = res["owner"]
+                if out["owner"] is None:
+                    out["owner"] = owner.copy()
+                assert np.array_equal(owner, out["owner"]), "ranks disagree on the halo ownership"
+                code, m = cat[r][2].cpu().numpy(), cat[r][3].cpu().numpy()
+                mine = np.nonzero((owner == r) & ~done)[0]
+                assert np.all(code[owner != r] == NOT_MINE)
+                ok = mine[code[mine] != -103]
+                if len(ok):
+                    fin = g.finish_host(code[ok], m[ok], thr)
+                    out["rvir"][ok], out["mvir"][ok], out["ndelta"][ok] = fin["rvir"], fin["mvir"], fin["ndelta"]
+                    if want_members:
+                        off, mem = g.members(sorted=True, copy=True)
+                        for i in ok:
+                            out["members"][i] = mem[off[i]:off[i + 1]].copy()
+                    done[ok] = True
+            out["n_recv"].append(n_recv)
+            balls += 4                            # balls that left the mask: again, further out (whole step)
+            if out["rounds"] > 16:
+                raise RuntimeError("domain step does not converge")
+        return out
+
+    def close(self):
+        self._sync()
+        for g in self.gs:
+            g.domain_close()
+            g.close()

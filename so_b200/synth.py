@@ -138,7 +138,19 @@ def make_snapshot(n_particles, n_halos, seed, *, nmin=20, nmax=2.0e4, slope=-0.9
         k = min(step, n_particles - off)
         pos[off:off + k] = _wrap(rng.random((k, 3)) - 0.5)
         off += k
-    if shuffle:
+    if shuffle == "blocks":
+        # file order with spatially coherent runs: blocks of 2^16 particles in a seeded random order (the halo
+        # blocks end up spread over the whole file, hence over the slices of a multi-GPU run); a full
+        # particle-level permutation of 10^9 records costs minutes of host time and changes nothing downstream
+        bs = 1 << 16
+        nblk = n_particles // bs
+        order = np.random.default_rng(seed + 77).permutation(nblk)
+        out = np.empty_like(pos)
+        for k, src in enumerate(order):
+            out[k * bs:(k + 1) * bs] = pos[src * bs:(src + 1) * bs]
+        out[nblk * bs:] = pos[nblk * bs:]
+        pos = out
+    elif shuffle:
         perm = rng.permutation(n_particles)
         pos = pos[perm]
 
@@ -157,8 +169,19 @@ def make_snapshot(n_particles, n_halos, seed, *, nmin=20, nmax=2.0e4, slope=-0.9
 
 # --- the BASELINE.json configurations ---------------------------------------
 
-def config(idx: int, scale: float = 1.0) -> Snapshot:
-    """BASELINE.json configs[idx]; `scale` < 1 shrinks N and H together for smoke runs."""
+def config(idx: int, scale: float = 1.0, big_shuffle="blocks") -> Snapshot:
+    """BASELINE.json configs[idx]; `scale` < 1 shrinks N and H together for smoke runs.  Snapshots of 512^3
+    particles and more are shuffled block-wise (see make_snapshot) instead of particle-wise."""
+    if idx in (2, 3, 4) and 512 ** 3 * (8 if idx == 3 else 1) * scale >= 512 ** 3:
+        if idx == 2:
+            return make_snapshot(int(512 ** 3 * scale), max(1, int(50000 * scale)), seed=1002, omega0=0.3, z=0.5,
+                                 shuffle=big_shuffle, name="cfg2_512^3_50000halos")
+        if idx == 3:
+            return make_snapshot(int(1024 ** 3 * scale), max(1, int(100000 * scale)), seed=1003,
+                                 shuffle=big_shuffle, name="cfg3_1024^3_100000halos")
+        sizes = np.concatenate([np.full(64, 1.0e6 * scale), np.full(436, 3.0e4 * scale)])
+        return make_snapshot(int(512 ** 3 * scale), 500, seed=1004, sizes=np.maximum(sizes, 20), nmax=1e6, trunc=1.3,
+                             shuffle=big_shuffle, name="cfg4_512^3_clusterheavy")
     if idx == 0:
         return make_snapshot(int(128 ** 3 * scale), max(1, int(1000 * scale)), seed=1000,
                              name="cfg0_128^3_1000halos")

@@ -189,3 +189,66 @@ def test_cli_pot_recentring_live(tmp_path):
     b = np.frombuffer(open(outs["ref"] + ".sogtp", "rb").read(), np.uint8)[32:].view(np.float32).reshape(-1, 11)
     assert a[:, [0, 1, 2, 3, 8, 9]].tobytes() == b[:, [0, 1, 2, 3, 8, 9]].tobytes()     # incl. the new centres
     assert not np.array_equal(a[:, 1:4], s.centers)                                    # centres did move
+
+
+def _stats_block(hdr):
+    """The '#STATS:' block kdOutStats writes into the .sovcirc header (kd2.c:1371-1413)."""
+    i = [k for k, l in enumerate(hdr) if l.startswith("#STATS")]
+    assert i, "no #STATS block"
+    return [l.rstrip() for l in hdr[i[0]:] if l.startswith("#")]
+
+
+@pytest.mark.skipif(not po.ref_available("so_ref"), reason="reference binary not built")
+@pytest.mark.parametrize("flags", [[], ["-grp"], ["-gtp"], ["-grp", "-gtp"]])
+def test_cli_stats_block_without_grp_gtp_live(tmp_path, flags):
+    """kdOutStats (kd2.c:1334-1415, always called: so.c:546) sums fMass over PINIT.iGrp > 0 whatever the output
+    flags are: the '#STATS:' block must equal the reference's with and without -grp / -gtp."""
+    s = synth.make_snapshot(40 ** 3, 30, seed=91, nmax=4000, overlap_pairs=4)
+    snap, gtp = str(tmp_path / "s.tipsy"), str(tmp_path / "h.gtp")
+    vel = np.random.default_rng(4).normal(size=(s.n, 3)).astype(np.float32)
+    tipsy.write_tipsy(snap, s.time, dark=tipsy.dark_from_arrays(s.pos, s.mass, vel=vel))
+    tipsy.write_gtp(gtp, s.time, s.centers, s.rgtp, s.gtp_mass)
+    outs, errs = {}, {}
+    for who, exe in (("ref", os.path.join(po.REF_DIR, "so_ref")), ("ours", SO)):
+        out = str(tmp_path / who)
+        with open(snap, "rb") as fin:
+            r = subprocess.run([exe, "-i", gtp, "-o", out, "-delta", "200"] + flags, stdin=fin, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[who], errs[who] = out, r.stderr
+    ha, ra = tipsy.parse_sovcirc(outs["ours"] + ".sovcirc")
+    hb, rb = tipsy.parse_sovcirc(outs["ref"] + ".sovcirc")
+    assert _stats_block(ha) == _stats_block(hb)
+    compare_rows(ra, np.array(rb))
+    # the same block goes to stderr (kd2.c:1371)
+    pick = lambda e: [l.strip() for l in e.splitlines() if "Total Mass" in l or "Mass Deviation" in l or "subsumed" in l]
+    assert pick(errs["ours"]) == pick(errs["ref"])
+
+
+@pytest.mark.skipif(not po.ref_available("so_ref"), reason="reference binary not built")
+@pytest.mark.parametrize("cosmo", [["-O", "0.3", "-L"], ["-O", "0.3"], ["-O", "1.0"], ["-O", "0.3", "-L", "-z", "1.0"]])
+def test_cli_virial_threshold_default_live(tmp_path, cosmo):
+    """No -delta: the threshold is the virial overdensity of so.c:57-86 (Kitayama & Suto 1996) times Omega0
+    (so.c:477-481), with z from the snapshot header time unless -z is given (so.c:470-472) — flat-Lambda,
+    open and Einstein-de Sitter branches.  BASELINE configs[2] run A is this path."""
+    omega0 = float(cosmo[1])
+    s = synth.make_snapshot(40 ** 3, 30, seed=92, nmax=4000, omega0=omega0, z=0.5)
+    snap, gtp = str(tmp_path / "s.tipsy"), str(tmp_path / "h.gtp")
+    tipsy.write_tipsy(snap, s.time, dark=tipsy.dark_from_arrays(s.pos, s.mass))
+    tipsy.write_gtp(gtp, s.time, s.centers, s.rgtp, s.gtp_mass)
+    outs = {}
+    for who, exe in (("ref", os.path.join(po.REF_DIR, "so_ref")), ("ours", SO)):
+        out = str(tmp_path / who)
+        with open(snap, "rb") as fin:
+            r = subprocess.run([exe, "-i", gtp, "-o", out, "-grp", "-gtp"] + cosmo, stdin=fin, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[who] = out
+    ha, ra = tipsy.parse_sovcirc(outs["ours"] + ".sovcirc")
+    hb, rb = tipsy.parse_sovcirc(outs["ref"] + ".sovcirc")
+    thr = lambda hdr: [l for l in hdr if "fThreshold" in l or "fRedshift" in l]
+    assert thr(ha) == thr(hb) and "VIRIAL DENSITY" in thr(ha)[0]
+    assert sum(1 for row in rb if row[2] > 0) >= 20
+    compare_rows(ra, np.array(rb))
+    assert open(outs["ours"] + ".sogrp").read() == open(outs["ref"] + ".sogrp").read()
+    a = np.frombuffer(open(outs["ours"] + ".sogtp", "rb").read(), np.uint8)[32:].view(np.float32).reshape(-1, 11)
+    b = np.frombuffer(open(outs["ref"] + ".sogtp", "rb").read(), np.uint8)[32:].view(np.float32).reshape(-1, 11)
+    assert a[:, [0, 1, 2, 3, 8, 9]].tobytes() == b[:, [0, 1, 2, 3, 8, 9]].tobytes()

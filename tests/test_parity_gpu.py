@@ -551,3 +551,96 @@ def test_domain_run_matches_single_grid(n_ranks, n_balls):
         assert np.array_equal(np.sort(a), np.sort(b)), i
     if n_ranks > 1:
         assert out["sent"] < n_ranks * s.n        # far from "everything to everyone"
+
+
+def _domain_step_inputs():
+    s = synth.make_snapshot(64 ** 3, 150, seed=81, nmax=6000)
+    rng = np.random.default_rng(11)
+    vc = (rng.random((10, 3)) - 0.5).astype(np.float32)
+    centers = np.concatenate([s.centers, vc, np.array([[0.4999, 0.4999, -0.4999]], np.float32)])
+    rgtp = np.concatenate([s.rgtp, np.full(5, 0.004, np.float32), np.full(5, 0.03, np.float32), [np.float32(0.01)]])
+    return s, centers, rgtp
+
+
+def _check_domain_step(out, ref, n_ranks):
+    assert_so_equal(out, ref["rvir"], ref["mvir"], ref["ndelta"])
+    for i in range(len(ref["ndelta"])):
+        a = ref["members"][ref["member_offset"][i]:ref["member_offset"][i + 1]]
+        b = out["members"][i] if out["members"][i] is not None else np.zeros(0, np.int32)
+        assert np.array_equal(a, b), i            # same (r^2, index) order, global indices
+    if n_ranks > 1:
+        assert len(np.unique(out["owner"])) == n_ranks          # every rank owns some halos
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_ranks,n_balls", [(1, 4), (2, 1), (3, 2), (8, 4)])
+def test_domain_step_matches_single_grid(n_ranks, n_balls):
+    """The stream-ordered domain step (device-side ownership, destination table, one-pass routing into staging
+    runs, receiver-side reservations, grid build with the particle count read on the device) with all ranks
+    simulated on one device: results of the single full grid bit for bit, incl. error codes, the periodic
+    boundary and halos whose balls outgrow the first masks."""
+    import torch
+    from so_b200 import parallel
+    s, centers, rgtp = _domain_step_inputs()
+    ref = run_gpu(s.pos, s.mass, centers, rgtp, 200.0)
+    dev = torch.device("cuda", 0)
+    full = torch.empty((s.n, 4), dtype=torch.float32, device=dev)
+    full[:, :3] = torch.from_numpy(s.pos).to(dev)
+    full[:, 3] = float(s.mass)
+    bounds = parallel.slice_bounds(s.n, n_ranks)
+    slices = [full[a:b].contiguous() for a, b in bounds]
+    torch.cuda.synchronize()
+    run = parallel.VirtualDomainStep(n_ranks, s.n, s.mass)
+    try:
+        out = run.run(slices, centers, rgtp, np.float32(200.0), 8, n_balls)
+    finally:
+        run.close()
+    _check_domain_step(out, ref, n_ranks)
+    assert sum(out["n_recv"][0]) < n_ranks * s.n
+
+
+@pytest.mark.gpu
+def test_domain_step_reports_overflow_instead_of_writing_past_the_buffers():
+    import torch
+    from so_b200 import parallel
+    s, centers, rgtp = _domain_step_inputs()
+    dev = torch.device("cuda", 0)
+    full = torch.empty((s.n, 4), dtype=torch.float32, device=dev)
+    full[:, :3] = torch.from_numpy(s.pos).to(dev)
+    full[:, 3] = float(s.mass)
+    torch.cuda.synchronize()
+    for recv_cap, stage_cap, what in [(2000, 1 << 16, "receive"), (1 << 18, 500, "staging")]:
+        run = parallel.VirtualDomainStep(2, s.n, s.mass, recv_cap=recv_cap, stage_cap=stage_cap)
+        try:
+            with pytest.raises(RuntimeError, match=what):
+                run.run([full[: s.n // 2].contiguous(), full[s.n // 2:].contiguous()], centers, rgtp, np.float32(200.0))
+        finally:
+            run.close()
+
+
+@pytest.mark.gpu
+def test_domain_step_across_devices():
+    """The same step with one rank per visible GPU inside this process: pushes travel over NVLink peer memory
+    and the ranks meet at the flag barrier.  Runs when more than one device is visible."""
+    import torch
+    from so_b200 import parallel
+    nd = torch.cuda.device_count()
+    if nd < 2:
+        pytest.skip("one device visible")
+    R = min(nd, 8)
+    s, centers, rgtp = _domain_step_inputs()
+    ref = run_gpu(s.pos, s.mass, centers, rgtp, 200.0)
+    bounds = parallel.slice_bounds(s.n, R)
+    slices = []
+    for r, (a, b) in enumerate(bounds):
+        dev = torch.device("cuda", r)
+        t = torch.empty((b - a, 4), dtype=torch.float32, device=dev)
+        t[:, :3] = torch.from_numpy(s.pos[a:b]).to(dev)
+        t[:, 3] = float(s.mass)
+        slices.append(t)
+    run = parallel.VirtualDomainStep(R, s.n, s.mass, devices=list(range(R)))
+    try:
+        out = run.run(slices, centers, rgtp, np.float32(200.0), 8, 4)
+    finally:
+        run.close()
+    _check_domain_step(out, ref, R)
