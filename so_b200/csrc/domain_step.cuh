@@ -94,21 +94,19 @@ __global__ void __launch_bounds__(256) k_assign_hist(GridDev g, const float *__r
     atomicAdd(&bins[assign_bin(centers + 3 * (size_t)h, g)], assign_cost(rgtp[h], nbar));
 }
 
-/* exclusive scan of the DOM_ASSIGN_BINS costs by one block; bins[DOM_ASSIGN_BINS] = total */
+/* exclusive scan of the DOM_ASSIGN_BINS costs by one block; bins[DOM_ASSIGN_BINS] = total.  Warp w owns the
+ * contiguous chunk [w * CH, (w + 1) * CH): every load and store of a warp is 256 contiguous bytes. */
 __global__ void __launch_bounds__(1024) k_assign_scan(unsigned long long *bins)
 {
-    constexpr int PER = DOM_ASSIGN_BINS / 1024;
+    constexpr int CH = DOM_ASSIGN_BINS / 32, IT = CH / 32;
     __shared__ unsigned long long ws[32];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    unsigned long long s = 0;
-    for (int k = 0; k < PER; ++k) s += bins[t * PER + k];
-    unsigned long long x = s;
+    unsigned long long v[IT], s = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, x, o);
-        if (lane >= o) x += u;
-    }
-    if (lane == 31) ws[w] = x;
+    for (int i = 0; i < IT; ++i) { v[i] = bins[w * CH + i * 32 + lane]; s += v[i]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);      /* chunk total, on every lane */
+    if (lane == 0) ws[w] = s;
     __syncthreads();
     if (w == 0) {
         unsigned long long y = ws[lane];
@@ -120,9 +118,19 @@ __global__ void __launch_bounds__(1024) k_assign_scan(unsigned long long *bins)
         ws[lane] = y;
     }
     __syncthreads();
-    unsigned long long run = x - s + (w ? ws[w - 1] : 0ull);
-    for (int k = 0; k < PER; ++k) { const unsigned long long v = bins[t * PER + k]; bins[t * PER + k] = run; run += v; }
-    if (t == 1023) bins[DOM_ASSIGN_BINS] = run;
+    unsigned long long carry = w ? ws[w - 1] : 0ull;
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+        unsigned long long x = v[i];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long u = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += u;
+        }
+        bins[w * CH + i * 32 + lane] = carry + x - v[i];
+        carry += __shfl_sync(0xFFFFFFFFu, x, 31);
+    }
+    if (t == 1023) bins[DOM_ASSIGN_BINS] = carry;
 }
 
 __global__ void __launch_bounds__(256) k_assign_owner(GridDev g, const float *__restrict__ centers, int nh, int R,
@@ -224,88 +232,117 @@ struct StageArgs {
     uint32_t *flags;
 };
 
+#define RB_CAP 2048          /* records a CTA collects in shared memory before it writes them out */
+#define RB_FLUSH 1024
+
+/* Records are collected per CTA in shared memory (one aggregated shared-memory atomic per warp and step) and
+ * written out RB_FLUSH.. at a time: one reservation per destination and flush, coalesced 16-byte stores.
+ * Per particle the pass costs the load, three cell coordinates and one to three bitmap lookups — the
+ * first version, which reserved and wrote per round of 1024 particles, spent ~100 warp instructions per 32
+ * particles and ran at 2.9 TB/s, bound by instruction issue (profiles/r2_ncu_route_bucket.md). */
 __global__ void __launch_bounds__(256) k_route_stage(const __grid_constant__ StageArgs a)
 {
-    __shared__ uint32_t wcnt[8][ROUTE_MAXR];                   /* records per (warp, destination) of a round */
-    __shared__ unsigned long long wbase[8][ROUTE_MAXR];        /* ... and where each warp's run starts       */
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const uint32_t lt = (1u << lane) - 1u;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t nround = (a.n + stride * ROUTE_U - 1) / (stride * ROUTE_U);
-    for (int64_t it = 0; it < nround; ++it) {               /* every thread runs every round (ballots, barriers) */
-        const int64_t i0 = it * stride * ROUTE_U + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float4 buf[RB_CAP];
+    __shared__ unsigned char bdst[RB_CAP];
+    __shared__ unsigned short brank[RB_CAP];
+    __shared__ uint32_t cnt, dcount[ROUTE_MAXR];
+    __shared__ unsigned long long dbase[ROUTE_MAXR];
+    if (threadIdx.x == 0) cnt = 0u;
+    __syncthreads();
+    const int mask = a.g.nc - 1, mb = a.g.mb, ms = a.g.ms;
+    const int sb = min(mb, DOM_SUPER_LOG), ss = mb - sb;
+    const float g0x = a.g.g0[0], g0y = a.g.g0[1], g0z = a.g.g0[2], ihx = a.g.invh[0], ihy = a.g.invh[1], ihz = a.g.invh[2];
+    const uint32_t n = (uint32_t)a.n, stride = gridDim.x * blockDim.x;
+
+    auto flush = [&](uint32_t m) {            /* all threads; m records in buf[0..m) */
+        if (a.R == 1) {
+            if (threadIdx.x == 0) {
+                unsigned long long base = atomicAdd(a.cursor[0], (unsigned long long)m);
+                if (base + m > a.cap[0]) { atomicOr(a.flags, a.flag_bit[0]); base = ~0ull; }
+                dbase[0] = base;
+            }
+            __syncthreads();
+            const unsigned long long base = dbase[0];
+            if (base != ~0ull)
+                for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) a.dst[0][base + i] = buf[i];
+        } else {
+            if (threadIdx.x < ROUTE_MAXR) dcount[threadIdx.x] = 0u;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) brank[i] = (unsigned short)atomicAdd(&dcount[bdst[i]], 1u);
+            __syncthreads();
+            if (threadIdx.x < (uint32_t)a.R) {
+                const int d = threadIdx.x;
+                const uint32_t c = dcount[d];
+                unsigned long long base = c ? atomicAdd(a.cursor[d], (unsigned long long)c) : 0ull;
+                if (base + c > a.cap[d]) { if (c) atomicOr(a.flags, a.flag_bit[d]); base = ~0ull; }
+                dbase[d] = base;
+            }
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
+                const int d = bdst[i];
+                const unsigned long long base = dbase[d];
+                if (base != ~0ull) a.dst[d][base + brank[i]] = buf[i];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) cnt = 0u;
+        __syncthreads();
+    };
+
+    const uint32_t per_round = stride * ROUTE_U;
+    const uint32_t nround = (n + per_round - 1) / per_round;
+    for (uint32_t it = 0; it < nround; ++it) {               /* every thread runs every round (barriers) */
+        const uint32_t i0 = it * per_round + blockIdx.x * blockDim.x + threadIdx.x;
         float4 q[ROUTE_U];
         uint32_t set[ROUTE_U];
 #pragma unroll
         for (int u = 0; u < ROUTE_U; ++u) {
-            const int64_t i = i0 + u * stride;
-            if (i < a.n) q[u] = ld_stream(a.slice + i);
+            const uint32_t i = i0 + u * stride;
+            if (i < n) q[u] = ld_stream(a.slice + i);
         }
 #pragma unroll
         for (int u = 0; u < ROUTE_U; ++u) {
-            const int64_t i = i0 + u * stride;
+            const uint32_t i = i0 + u * stride;
             set[u] = 0u;
-            if (i < a.n) {
-                const int mask = a.g.nc - 1, mb = a.g.mb;
-                const uint32_t cx = cell_coord(q[u].x, a.g.g0[0], a.g.invh[0], mask) >> a.g.ms;
-                const uint32_t cy = cell_coord(q[u].y, a.g.g0[1], a.g.invh[1], mask) >> a.g.ms;
-                const uint32_t cz = cell_coord(q[u].z, a.g.g0[2], a.g.invh[2], mask) >> a.g.ms;
+            if (i < n) {
+                /* (the same expressions as the grid build's cell_coord: a particle is routed by the cell it will be sorted into) */
+                const uint32_t cx = cell_coord(q[u].x, g0x, ihx, mask) >> ms;
+                const uint32_t cy = cell_coord(q[u].y, g0y, ihy, mask) >> ms;
+                const uint32_t cz = cell_coord(q[u].z, g0z, ihz, mask) >> ms;
                 /* three lookups, cheapest first: 64^3 pre-filter (32 KB: L1), "somebody wants it" bitmap (L2),
                  * destination set (only for the few particles that pass both) */
-                const int sb = min(mb, DOM_SUPER_LOG), ss = mb - sb;
                 const uint32_t sbit = ((cz >> ss) << (2 * sb)) | ((cy >> ss) << sb) | (cx >> ss);
                 if ((__ldg(a.super + (sbit >> 5)) >> (sbit & 31)) & 1u) {
                     const uint32_t bit = (cz << (2 * mb)) | (cy << mb) | cx;
-                    if ((__ldg(a.any + (bit >> 5)) >> (bit & 31)) & 1u) set[u] = a.R > 1 ? __ldg(a.table + bit) : 1u;
+                    if ((__ldg(a.any + (bit >> 5)) >> (bit & 31)) & 1u) {
+                        set[u] = a.R > 1 ? (uint32_t)__ldg(a.table + bit) : 1u;
+                        q[u].w = __uint_as_float(a.index_base + i);
+                    }
                 }
-                q[u].w = __uint_as_float(a.index_base + (uint32_t)i);
             }
         }
-        uint32_t wset = 0u;                                 /* destinations some lane of this warp has */
-#pragma unroll
-        for (int u = 0; u < ROUTE_U; ++u) wset |= set[u];
-        wset = __reduce_or_sync(0xFFFFFFFFu, wset);
-        /* (whole CTA without a single record this round: nothing to reserve — the common case away from halos) */
-        if (!__syncthreads_or((int)wset)) continue;
-        if (lane < a.R) wcnt[w][lane] = 0u;
-        __syncwarp();
-        for (uint32_t rem = wset; rem; rem &= rem - 1u) {
-            const int d = __ffs(rem) - 1;
-            uint32_t c = 0;
-#pragma unroll
-            for (int u = 0; u < ROUTE_U; ++u) c += __popc(__ballot_sync(0xFFFFFFFFu, (set[u] >> d) & 1u));
-            if (lane == 0) wcnt[w][d] = c;
-        }
-        __syncthreads();
-        if (threadIdx.x < a.R) {
-            const int d = threadIdx.x;
-            uint32_t tot = 0;
-            for (int k = 0; k < 8; ++k) tot += wcnt[k][d];
-            unsigned long long base = tot ? atomicAdd(a.cursor[d], (unsigned long long)tot) : 0ull;
-            if (base + tot > a.cap[d]) {                    /* no room: drop the run, report (the host grows the buffers) */
-                if (tot) atomicOr(a.flags, a.flag_bit[d]);
-                base = ~0ull;
-            }
-            for (int k = 0; k < 8; ++k) {
-                wbase[k][d] = base;
-                if (base != ~0ull) base += wcnt[k][d];
-            }
-        }
-        __syncthreads();
-        for (uint32_t rem = wset; rem; rem &= rem - 1u) {
-            const int d = __ffs(rem) - 1;
-            unsigned long long pos = wbase[w][d];
-            const bool ok = pos != ~0ull;
+        for (;;) {
+            int pending = 0;
 #pragma unroll
             for (int u = 0; u < ROUTE_U; ++u) {
-                const bool want = (set[u] >> d) & 1u;
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, want);
-                if (want && ok) a.dst[d][pos + (unsigned long long)__popc(m & lt)] = q[u];
-                pos += (unsigned long long)__popc(m);
+                while (set[u]) {
+                    const int d = __ffs(set[u]) - 1;
+                    const uint32_t pos = agg_append(&cnt);
+                    if (pos >= RB_CAP) { pending = 1; break; }
+                    buf[pos] = q[u];
+                    bdst[pos] = (unsigned char)d;
+                    set[u] &= set[u] - 1u;
+                }
             }
+            const int more = __syncthreads_or(pending);
+            const uint32_t c = cnt;
+            if (c >= RB_FLUSH) flush(min(c, (uint32_t)RB_CAP));
+            if (!more) break;
         }
-        __syncthreads();                                    /* wcnt / wbase are reused by the next round */
     }
+    __syncthreads();
+    const uint32_t c = cnt;
+    if (c) flush(min(c, (uint32_t)RB_CAP));
 }
 
 /* ---- push: staging runs -> the receivers' buffers over NVLink ---------------------------------------- */
@@ -604,10 +641,8 @@ extern "C" int sogpu_domain_route(sogpu_t *h, const void *d_chunk, int64_t n, in
         ProfScope p(h, KID_ROUTE, 16.0 * (double)n);
         /* persistent grid of exactly the CTAs that are resident at once: a second, partial wave would leave
          * the SMs of the finished CTAs idle */
-        static int per_sm = 0;
-        if (!per_sm) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_route_stage, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-        }
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_route_stage, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
         k_route_stage<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * per_sm), 256, 0, h->stream>>>(a);
     }
     CU(cudaGetLastError());

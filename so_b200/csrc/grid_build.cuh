@@ -715,15 +715,20 @@ __global__ void __launch_bounds__(BR_NT, BR_MINB) k_bucket_sort_rt(const float4 
                                                              const uint32_t *__restrict__ live,
                                                              const uint32_t *__restrict__ live_n)
 {
-    __shared__ __align__(16) uint32_t cnt[BKT_CELLS];
+    /* cell counts, padded: thread t scans the `per` consecutive cells starting at t*per, so without padding
+     * the 16-byte accesses of a warp would lie `per` words apart — the same banks for every lane (measured:
+     * 82 M bank conflicts in 99 M shared-memory wavefronts, the kernel bound by exactly that).  Four words of
+     * padding per chunk of `per` cells make the lanes of a quarter warp hit eight different bank groups. */
+    __shared__ __align__(16) uint32_t cnt[BKT_CELLS + BKT_CELLS / 4];
     __shared__ uint32_t ws[BR_NT / 32 + 1];
     const int ncells = 1 << cell_bits;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    /* scan layout: thread t owns the `per` consecutive cells starting at t*per; with >= 1024 cells
-     * per bucket (every build large enough to matter) `per` is a multiple of 4 and the counts are
-     * moved as uint4 */
+    /* with >= 1024 cells per bucket (every build large enough to matter) `per` is a multiple of 4 (a power of
+     * two) and the counts are moved as uint4 */
     const int per = (ncells + BR_NT - 1) / BR_NT;
     const bool vec = (ncells >= 4 * BR_NT);
+    const int per_log = 31 - __clz(per);
+    auto phys = [&](uint32_t c) -> uint32_t { return vec ? c + ((c >> per_log) << 2) : c; };
     uint4 *cnt4 = reinterpret_cast<uint4 *>(cnt);
     if (live) n_buckets = __ldg(live_n);                 /* iterate over the live buckets only (k_bucket_live) */
     uint32_t nxb = 0, nx0 = 0, nx1 = 0;
@@ -741,38 +746,33 @@ __global__ void __launch_bounds__(BR_NT, BR_MINB) k_bucket_sort_rt(const float4 
         uint32_t *ceb = ce + ((size_t)b << cell_bits);
         /* Focused grids: the queries read ce[] only at cells inside the mask and at the entry right behind
          * one (every ball is checked against the mask first), so a group of four entries is stored only if
-         * one of the cells [c-1, c+3] is marked: a sparse grid writes a few percent of its cell table.
-         * This thread's `per` cells lie in one row of cells (per <= 64 <= cells per row). */
-        const bool sparse = vec && g.mask != nullptr && per <= g.nc && g.nc >= 64;
-        uint32_t mrow = 0, ix0 = 0;
-        if (sparse) {
-            const uint32_t key0 = (b << cell_bits) + (uint32_t)(t * per);
+         * one of the cells [c-1, c+3] is marked: a sparse grid writes a few percent of its cell table. */
+        const bool sparse = vec && g.mask != nullptr && g.nc >= 64;
+        auto group_needed = [&](uint32_t c4) -> bool {                    /* group = cells 4*c4 .. 4*c4+3 of this bucket */
+            if (!sparse) return true;
+            const uint32_t key0 = (b << cell_bits) + 4u * c4;
+            const uint32_t c = key0 & (uint32_t)(g.nc - 1);               /* first cell of the group, inside its row */
+            if (c == 0u) return true;                                     /* (its predecessor is the previous row's last cell) */
             const uint32_t rk = key0 >> g.lb;
             const uint32_t m = (1u << g.tb) - 1u, lo = rk & ((1u << (2 * g.tb)) - 1u), hi = rk >> (2 * g.tb);
             const uint32_t iy = ((hi & ((1u << (g.lb - g.tb)) - 1u)) << g.tb) | (lo & m);
             const uint32_t iz = ((hi >> (g.lb - g.tb)) << g.tb) | (lo >> g.tb);
-            ix0 = key0 & (uint32_t)(g.nc - 1);
-            mrow = ((iz >> g.ms) << (2 * g.mb)) | ((iy >> g.ms) << g.mb);
-        }
-        auto group_needed = [&](int k) -> bool {
-            if (!sparse) return true;
-            const uint32_t c = ix0 + 4u * (uint32_t)k;                    /* first cell of the group, inside the row */
-            if (c == 0u) return true;                                     /* (its predecessor is the previous row's last cell) */
+            const uint32_t mrow = ((iz >> g.ms) << (2 * g.mb)) | ((iy >> g.ms) << g.mb);
             const uint32_t m0 = (c - 1u) >> g.ms, m1 = (c + 3u) >> g.ms;
             return mask_bits_at(g.mask, mrow + m0, m1 - m0 + 1u) != 0u;
         };
         if (nb == 0) {                   /* empty bucket (focused builds): only its cell-table slice */
-            if (sparse) {
+            if (vec) {
                 uint4 *ce4 = reinterpret_cast<uint4 *>(ceb);
-                for (int k = 0; k < per / 4; ++k)
-                    if (group_needed(k)) ce4[t * (per / 4) + k] = make_uint4(b0, b0, b0, b0);
+                for (int c4 = t; c4 < ncells / 4; c4 += BR_NT)
+                    if (group_needed((uint32_t)c4)) ce4[c4] = make_uint4(b0, b0, b0, b0);
             } else {
                 for (int c = t; c < ncells; c += BR_NT) ceb[c] = b0;
             }
             continue;
         }
         const bool in_regs = nb <= (uint32_t)(BR_NT * BR_IT);
-        if (vec) for (int c = t; c < ncells / 4; c += BR_NT) cnt4[c] = make_uint4(0u, 0u, 0u, 0u);
+        if (vec) for (int c = t; c < (ncells + (ncells >> per_log) * 4) / 4; c += BR_NT) cnt4[c] = make_uint4(0u, 0u, 0u, 0u);
         else for (int c = t; c < ncells; c += BR_NT) cnt[c] = 0u;
         __syncthreads();
         float4 q[BR_IT];
@@ -790,13 +790,13 @@ __global__ void __launch_bounds__(BR_NT, BR_MINB) k_bucket_sort_rt(const float4 
                 if (i < nb) {
                     if (first_pass_input_is_raw) q[k].w = __int_as_float((int)(b0 + i));
                     uint32_t c = cell_key_low(q[k], g, cell_bits);
-                    cr[k] = (c << 16) | atomicAdd(&cnt[c], 1u);
+                    cr[k] = (c << 16) | atomicAdd(&cnt[phys(c)], 1u);
                 }
             }
         } else {
             for (uint32_t i = t; i < nb; i += BR_NT) {
                 float4 qq = __ldg(in4 + b0 + i);
-                atomicAdd(&cnt[cell_key_low(qq, g, cell_bits)], 1u);
+                atomicAdd(&cnt[phys(cell_key_low(qq, g, cell_bits))], 1u);
             }
         }
         __syncthreads();
@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(BR_NT, BR_MINB) k_bucket_sort_rt(const float4 
             const int G = per / 4;
             uint32_t s = 0;
             for (int k = 0; k < G; ++k) {
-                uint4 v = cnt4[t * G + k];
+                uint4 v = cnt4[t * (G + 1) + k];
                 s += v.x + v.y + v.z + v.w;
             }
             uint32_t x = s;
@@ -820,13 +820,19 @@ __global__ void __launch_bounds__(BR_NT, BR_MINB) k_bucket_sort_rt(const float4 
 #pragma unroll
             for (int k = 0; k < BR_NT / 32; ++k) off += (k < w) ? ws[k] : 0u;
             uint32_t run = off + x - s;
-            uint4 *ce4 = reinterpret_cast<uint4 *>(ceb);                  /* (b << cell_bits) is a multiple of 1024 */
             for (int k = 0; k < G; ++k) {
-                uint4 v = cnt4[t * G + k], e;
+                uint4 v = cnt4[t * (G + 1) + k], e;
                 e.x = run; e.y = e.x + v.x; e.z = e.y + v.y; e.w = e.z + v.z;
                 run = e.w + v.w;
-                cnt4[t * G + k] = e;
-                if (group_needed(k)) ce4[t * G + k] = make_uint4(b0 + e.x, b0 + e.y, b0 + e.z, b0 + e.w);
+                cnt4[t * (G + 1) + k] = e;
+            }
+            __syncthreads();
+            /* the bucket's slice of the cell table, coalesced: consecutive threads store consecutive groups */
+            uint4 *ce4 = reinterpret_cast<uint4 *>(ceb);                  /* (b << cell_bits) is a multiple of 1024 */
+            for (int c4 = t; c4 < ncells / 4; c4 += BR_NT) {
+                if (!group_needed((uint32_t)c4)) continue;
+                const uint4 e = cnt4[c4 + ((4 * c4) >> per_log)];
+                ce4[c4] = make_uint4(b0 + e.x, b0 + e.y, b0 + e.z, b0 + e.w);
             }
         } else {
             uint32_t s = 0;
@@ -856,7 +862,7 @@ __global__ void __launch_bounds__(BR_NT, BR_MINB) k_bucket_sort_rt(const float4 
             for (int k = 0; k < BR_IT; ++k) {
                 if ((uint32_t)(k * BR_NT) >= nb) break;
                 uint32_t i = t + k * BR_NT;
-                if (i < nb) sorted[b0 + cnt[cr[k] >> 16] + (cr[k] & 0xFFFFu)] = q[k];
+                if (i < nb) sorted[b0 + cnt[phys(cr[k] >> 16)] + (cr[k] & 0xFFFFu)] = q[k];
             }
         } else {
             /* oversized bucket (a dense halo core): second read (L2), ranks from the shared cursors */
@@ -864,7 +870,7 @@ __global__ void __launch_bounds__(BR_NT, BR_MINB) k_bucket_sort_rt(const float4 
                 float4 qq = __ldg(in4 + b0 + i);
                 if (first_pass_input_is_raw) qq.w = __int_as_float((int)(b0 + i));
                 uint32_t c = cell_key_low(qq, g, cell_bits);
-                uint32_t dst = atomicAdd(&cnt[c], 1u);
+                uint32_t dst = atomicAdd(&cnt[phys(c)], 1u);
                 sorted[b0 + dst] = qq;
             }
         }

@@ -55,14 +55,17 @@
                          * registers the two excluded each other by 0.1 % of the register file */
 #endif
 template <int NT> struct Cfg;
+/* SCAP: (r^2 bits, index) keys of ONE ball that a group can stage in shared memory during the histogram pass.
+ * A ball that fits is traversed in global memory exactly once: window collection, refinement and the member
+ * emission then read the staged keys. */
 template <> struct Cfg<32> {   /* warp per halo */
-    static const int CAP = 256, WTARGET = 128, NLEV = 1, GROUPS = 8, MINB = Q32_MINB;
+    static const int CAP = 256, WTARGET = 128, NLEV = 1, GROUPS = 8, MINB = Q32_MINB, SCAP = 384;
 };
 template <> struct Cfg<256> {  /* block per halo */
-    static const int CAP = 4096, WTARGET = 1024, NLEV = 4, GROUPS = 1, MINB = Q256_MINB;
+    static const int CAP = 4096, WTARGET = 1024, NLEV = 4, GROUPS = 1, MINB = Q256_MINB, SCAP = 6144;
 };
 template <> struct Cfg<1024> { /* one full-SM block per halo: cluster-size halos (>= ~10^5 particles) */
-    static const int CAP = 4096, WTARGET = 2048, NLEV = 4, GROUPS = 1, MINB = 1;
+    static const int CAP = 4096, WTARGET = 2048, NLEV = 4, GROUPS = 1, MINB = 1, SCAP = 4096;
 };
 
 /* ============================================================================================
@@ -345,9 +348,16 @@ template <int NT> struct GroupSmem {
     uint32_t seg_pre[2 * NT];                   /* inclusive prefix of their lengths           */
     uint32_t tmp[40];                           /* scan / reduce scratch                       */
     uint32_t cnt;                               /* append cursor                               */
+    uint32_t scnt;                              /* keys appended to skey during the histogram pass */
     uint32_t bcast[4];
+    unsigned long long bcast64;
     uint8_t wflag[Cfg<NT>::CAP];                /* below-threshold flag per window element     */
-    alignas(128) TmaStage<NT> tma;              /* LAST: only allocated when TMA staging is on (query_smem_bytes) */
+    /* LAST: the staged keys of the current ball — or, for the 1024-thread class with TMA staging on, the tiles
+     * of the bulk-copy ring (the two are never used together) */
+    union alignas(128) {
+        unsigned long long skey[Cfg<NT>::SCAP];
+        TmaStage<NT> tma;
+    };
 };
 
 __device__ __forceinline__ float mt_eval(const MassTableS &mt, uint32_t k)
@@ -595,20 +605,42 @@ __device__ __forceinline__ void for_each_in_ball(const GridDev &g, GroupSmem<NT>
 /* ============================================================================================
  * functors of the passes
  * ============================================================================================ */
+/* append slot for the threads that reach this point together: ONE atomic per converged group of lanes */
+__device__ __forceinline__ uint32_t agg_append(uint32_t *cnt)
+{
+    const unsigned m = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(cnt, (uint32_t)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+
+/* The passes over a ball come in two forms: operator()(slot, particle) for a traversal of the grid, and
+ * take(r^2 bits, index) for a walk over the keys the histogram pass staged in shared memory. */
 struct HistF {          /* count particles with bits(r^2) in [lo,hi] into level bins */
     const GridDev *g;
     Center c;
     uint32_t lo_bits, hi_bits, shift, base;
     uint32_t *hist;
     uint32_t first_bits, n_first;   /* side count: particles inside the FIRST ball of the schedule */
-    __device__ __forceinline__ void operator()(uint32_t, const float4 &q)
+    unsigned long long *skey;       /* staging of every key of the ball (scap = 0: off)             */
+    uint32_t *scnt, scap;
+    __device__ __forceinline__ void take(uint32_t bits, uint32_t idx)
     {
-        uint32_t bits = __float_as_uint(dist2(c, q, *g));
         if (bits >= lo_bits && bits <= hi_bits) {   /* NaN (> 0x7f800000) never passes: hi is finite */
             uint32_t hb = bits >> shift;
             atomicAdd(&hist[hb > base ? hb - base : 0u], 1u);
             n_first += (bits <= first_bits);
+            if (scap) {
+                const uint32_t pos = agg_append(scnt);
+                if (pos < scap) skey[pos] = ((unsigned long long)bits << 32) | idx;
+            }
         }
+    }
+    __device__ __forceinline__ void operator()(uint32_t, const float4 &q)
+    {
+        take(__float_as_uint(dist2(c, q, *g)), __float_as_uint(q.w));
     }
 };
 
@@ -618,14 +650,16 @@ template <int CAP> struct CollectF {   /* append (r^2 bits, original index) of t
     uint32_t lo_bits, hi_bits;
     unsigned long long *wkey;
     uint32_t *cnt;
+    __device__ __forceinline__ void take(uint32_t bits, uint32_t idx)
+    {
+        if (bits >= lo_bits && bits <= hi_bits) {
+            const uint32_t pos = agg_append(cnt);
+            if (pos < (uint32_t)CAP) wkey[pos] = ((unsigned long long)bits << 32) | idx;
+        }
+    }
     __device__ __forceinline__ void operator()(uint32_t p, const float4 &q)
     {
-        uint32_t bits = __float_as_uint(dist2(c, q, *g));
-        if (bits >= lo_bits && bits <= hi_bits) {
-            uint32_t pos = atomicAdd(cnt, 1u);
-            if (pos < (uint32_t)CAP)
-                wkey[pos] = ((unsigned long long)bits << 32) | __float_as_uint(q.w);
-        }
+        take(__float_as_uint(dist2(c, q, *g)), __float_as_uint(q.w));
     }
 };
 
@@ -637,23 +671,31 @@ struct EmitF {          /* members: (r^2 bits, index) < key_j */
     float *md2;
     uint32_t *cnt;
     uint32_t limit;
-    __device__ __forceinline__ void operator()(uint32_t p, const float4 &q)
+    __device__ __forceinline__ void take(uint32_t bits, uint32_t idx)
     {
-        float d2 = dist2(c, q, *g);
-        uint32_t bits = __float_as_uint(d2);
-        uint32_t bj = (uint32_t)(key_j >> 32);
-        if (bits <= bj) {
-            int32_t oi = __float_as_int(q.w);
-            if (bits < bj || (uint32_t)oi < (uint32_t)key_j) {
-                uint32_t pos = atomicAdd(cnt, 1u);
-                if (pos < limit) {
-                    members[pos] = oi;
-                    if (md2) md2[pos] = d2;
-                }
+        if ((((unsigned long long)bits << 32) | idx) < key_j) {
+            const uint32_t pos = agg_append(cnt);
+            if (pos < limit) {
+                members[pos] = (int32_t)idx;
+                if (md2) md2[pos] = __uint_as_float(bits);
             }
         }
     }
+    __device__ __forceinline__ void operator()(uint32_t p, const float4 &q)
+    {
+        take(__float_as_uint(dist2(c, q, *g)), __float_as_uint(q.w));
+    }
 };
+
+/* walk over the keys staged by the histogram pass (all NT threads of the group) */
+template <int NT, typename F>
+__device__ __forceinline__ void for_each_staged(const unsigned long long *skey, uint32_t n, int tid, F &f)
+{
+    for (uint32_t i = tid; i < n; i += NT) {
+        const unsigned long long k = skey[i];
+        f.take((uint32_t)(k >> 32), (uint32_t)k);
+    }
+}
 
 struct GatherF {        /* sogpu_ball_gather: everything with r^2 <= ball2 */
     const GridDev *g;
@@ -829,12 +871,57 @@ struct HaloResult {
     int32_t n;                 /* N_Delta, or -1/-2/-3, CODE_UNSUPPORTED, CODE_DEFER           */
     float m;                   /* M_Delta                                                      */
     unsigned long long key_j;  /* (r^2 bits, index) of sorted element j = first non-member     */
+    unsigned long long off;    /* where the member list starts in the member buffer            */
 };
+
+struct EmitCtx {               /* member emission from inside the solver */
+    int32_t *members;
+    float *md2;
+    unsigned long long cap;
+    unsigned long long *cursor;    /* global append cursor of the member buffer: one atomicAdd(N_Delta) per halo */
+    uint32_t *flags;               /* bit0 member buffer too small, bit1 emit count mismatch */
+    int stage;                     /* stage the ball's keys in shared memory (off with TMA staging: they share it) */
+};
+
+/* The member list of a solved halo: every particle with (r^2 bits, index) < key_j, written behind a slot of j
+ * entries reserved with one atomic on the buffer's cursor.  From the staged keys when the ball was staged
+ * (no global traversal at all), else by one more traversal of the ball of radius r_j (an L2 hit: the solver
+ * has just read it). */
+template <int NT>
+__device__ __forceinline__ void emit_members_here(const GridDev &g, GroupSmem<NT> &sm, int tid, const Center &c,
+                                                  const EmitCtx &ec, HaloResult &res, bool staged, uint32_t n_staged,
+                                                  uint32_t &ev_other)
+{
+    const uint32_t j = (uint32_t)res.n;
+    if (tid == 0) { sm.bcast64 = atomicAdd(ec.cursor, (unsigned long long)j); sm.cnt = 0u; }
+    gsync<NT>();
+    const unsigned long long off = sm.bcast64;
+    res.off = off;
+    if (off + j > ec.cap) {
+        if (tid == 0) atomicOr(ec.flags, 1u);
+        gsync<NT>();
+        return;
+    }
+    EmitF f;
+    f.g = &g; f.c = c; f.key_j = res.key_j;
+    f.members = ec.members + off; f.md2 = ec.md2 ? ec.md2 + off : nullptr;
+    f.cnt = &sm.cnt; f.limit = j;
+    if (staged) {
+        for_each_staged<NT>(sm.skey, n_staged, tid, f);
+    } else {
+        const float r2j = __uint_as_float((uint32_t)(res.key_j >> 32));
+        BallGeom B = make_geom(g, c, sqrt((double)r2j) * (1.0 + 1.0e-6));
+        for_each_in_ball<NT>(g, sm, tid, B, f, ev_other);
+    }
+    gsync<NT>();
+    if (tid == 0 && sm.cnt != j) atomicOr(ec.flags, 2u);
+    gsync<NT>();
+}
 
 template <int NT>
 __device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &sm, int tid,
                         Center c, float rgtp, float thr, int nM, int first_ball, HaloResult &res,
-                        uint32_t &ev_hist, uint32_t &ev_other)
+                        uint32_t &ev_hist, uint32_t &ev_other, const EmitCtx &ec)
 {
     typedef Cfg<NT> CF;
     const float root = so_root_period(g.L[0], g.L[1], g.L[2]);           /* kd2.c:765 */
@@ -849,7 +936,7 @@ __device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &s
      * (and the same -3), provided the -1 test still counts the FIRST ball (done on the side below).
      * `steps` = how many schedule steps to advance before the next gather. */
     int steps = first_ball;
-    res.n = -3; res.m = -3.0f; res.key_j = 0ull;                         /* kd2.c:837-838 */
+    res.n = -3; res.m = -3.0f; res.key_j = 0ull; res.off = 0ull;         /* kd2.c:837-838 */
 
     while ((double)ball < 0.25 * (double)root) {                         /* kd2.c:766 */
         ball = so_next_ball(ball);                                       /* kd2.c:767 */
@@ -869,6 +956,7 @@ __device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &s
             lev[0].rank0 = 0u; lev[0].clamp = 1; lev[0].cur = 0;
         }
         for (int b = tid; b <= NB; b += NT) sm.hist[0][b] = 0u;
+        if (tid == 0) sm.scnt = 0u;
         gsync<NT>();
         if (!ball_covered<NT>(g, sm, tid, c, sqrt((double)ball2) * (1.0 + 1.0e-6))) {
             res.n = CODE_NEED_FULL; res.m = 0.0f;      /* focused grid too small for this ball */
@@ -881,10 +969,13 @@ __device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &s
             f.g = &g; f.c = c; f.lo_bits = 0u; f.hi_bits = ball_bits;
             f.shift = SHIFT0; f.base = lev[0].base; f.hist = sm.hist[0];
             f.first_bits = __float_as_uint(__fmul_rn(ball_k1, ball_k1)); f.n_first = 0u;
+            f.skey = sm.skey; f.scnt = &sm.scnt; f.scap = ec.stage ? (uint32_t)CF::SCAP : 0u;
             for_each_in_ball<NT>(g, sm, tid, B, f, ev_hist);
             n_first = f.n_first;
         }
         const uint32_t n = scan_hist<NT>(sm.hist[0], sm.tmp, tid);       /* nParticles, kd2.c:769 */
+        /* the whole ball sits in shared memory: every later pass of this ball reads it there */
+        const bool staged = ec.stage && n <= (uint32_t)CF::SCAP;
 
         if (kball == 0) {                                                /* kd2.c:772-778 */
             if (ball != ball_k1) n_first = gsum<NT>(n_first, sm.tmp, tid); else n_first = n;
@@ -952,12 +1043,18 @@ __device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &s
                     ++L;
                     for (int b = tid; b <= NB; b += NT) sm.hist[L][b] = 0u;
                     gsync<NT>();
-                    BallGeom B2 = make_geom(g, c, sqrt((double)__uint_as_float(nl.hi_bits)) * (1.0 + 1.0e-6));
                     HistF f;
                     f.g = &g; f.c = c; f.lo_bits = nl.lo_bits; f.hi_bits = nl.hi_bits;
                     f.shift = nl.shift; f.base = nl.base; f.hist = sm.hist[L];
                     f.first_bits = 0u; f.n_first = 0u;
-                    for_each_in_ball<NT>(g, sm, tid, B2, f, ev_other);
+                    f.skey = nullptr; f.scnt = nullptr; f.scap = 0u;
+                    if (staged) {
+                        for_each_staged<NT>(sm.skey, n, tid, f);
+                        gsync<NT>();
+                    } else {
+                        BallGeom B2 = make_geom(g, c, sqrt((double)__uint_as_float(nl.hi_bits)) * (1.0 + 1.0e-6));
+                        for_each_in_ball<NT>(g, sm, tid, B2, f, ev_other);
+                    }
                     scan_hist<NT>(sm.hist[L], sm.tmp, tid);
                     continue;
                 }
@@ -982,11 +1079,16 @@ __device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &s
                 for (int i = tid; i < P; i += NT) sm.wkey[i] = ~0ull;
                 gsync<NT>();
                 {
-                    BallGeom B2 = make_geom(g, c, sqrt((double)__uint_as_float(w_hi)) * (1.0 + 1.0e-6));
                     CollectF<CF::CAP> f;
                     f.g = &g; f.c = c; f.lo_bits = w_lo; f.hi_bits = w_hi;
                     f.wkey = sm.wkey; f.cnt = &sm.cnt;
-                    for_each_in_ball<NT>(g, sm, tid, B2, f, ev_other);
+                    if (staged) {
+                        for_each_staged<NT>(sm.skey, n, tid, f);
+                        gsync<NT>();
+                    } else {
+                        BallGeom B2 = make_geom(g, c, sqrt((double)__uint_as_float(w_hi)) * (1.0 + 1.0e-6));
+                        for_each_in_ball<NT>(g, sm, tid, B2, f, ev_other);
+                    }
                 }
                 if (sm.cnt != wn) {              /* cannot happen; guards the exactness claim  */
                     res.n = CODE_UNSUPPORTED; res.m = 1.0f;
@@ -1020,6 +1122,8 @@ __device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &s
                     res.m = __fsub_rn(mass, mt.m);                            /* kd2.c:816 */
                     res.n = (int32_t)j;
                     res.key_j = key_j;
+                    gsync<NT>();
+                    if (ec.members) emit_members_here<NT>(g, sm, tid, c, ec, res, staged, n, ev_other);   /* kd2.c:823 */
                     return;
                 }
                 carry = sm.wflag[wn - 1] != 0;
@@ -1061,7 +1165,9 @@ struct QueryArgs {
     int32_t *out_n;            /* N_Delta or a negative code */
     float *out_m;              /* M_Delta */
     unsigned long long *out_key;   /* (r^2 bits, index) of sorted element j */
-    const unsigned long long *out_off;   /* (emit) first member slot per halo */
+    unsigned long long *out_off;   /* first member slot per halo: written by the query (emit_in_query) or read by k_so_emit */
+    unsigned long long *member_cursor;   /* emit_in_query: append cursor of the member buffer */
+    int emit_in_query;
     int32_t *members;
     float *md2;
     unsigned long long member_cap;
@@ -1118,11 +1224,15 @@ __global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS, Cfg<NT>::MINB) k_so_query
         const int h = a.list[item];
         HaloResult res;
         if (mtn <= 0) {                      /* unequal particle masses: not handled by this path */
-            res.n = CODE_UNEQUAL_MASS; res.m = 0.0f; res.key_j = 0ull;
+            res.n = CODE_UNEQUAL_MASS; res.m = 0.0f; res.key_j = 0ull; res.off = 0ull;
         } else {
             Center c;
             c.x = a.centers[3 * h + 0]; c.y = a.centers[3 * h + 1]; c.z = a.centers[3 * h + 2];
-            so_halo<NT>(a.g, mt, sm, tid, c, a.rgtp[h], a.thr, a.nM, a.first_ball, res, ev_hist, ev_other);
+            EmitCtx ec;
+            ec.members = a.emit_in_query ? a.members : nullptr; ec.md2 = a.md2; ec.cap = a.member_cap;
+            ec.cursor = a.member_cursor; ec.flags = a.flags;
+            ec.stage = (NT == 1024 && a.g.use_tma) ? 0 : 1;
+            so_halo<NT>(a.g, mt, sm, tid, c, a.rgtp[h], a.thr, a.nM, a.first_ball, res, ev_hist, ev_other, ec);
             gsync<NT>();
         }
         if (res.n == CODE_DEFER) {
@@ -1133,6 +1243,7 @@ __global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS, Cfg<NT>::MINB) k_so_query
             a.out_n[h] = res.n;
             a.out_m[h] = res.m;
             a.out_key[h] = res.key_j;
+            if (a.emit_in_query) a.out_off[h] = res.off;
         }
     }
     if (a.timeline && threadIdx.x == 0) atomicMax(&a.timeline[2 * a.tl_slot + 1], global_ns());
@@ -1189,7 +1300,7 @@ template <int NT> static size_t query_smem_bytes(bool with_tma = true)
 {
     size_t mt_bytes = (sizeof(MassTableS) + 15) & ~(size_t)15;
     size_t g_bytes = (sizeof(GroupSmem<NT>) + 15) & ~(size_t)15;
-    if (NT == 1024 && !with_tma) g_bytes = offsetof(GroupSmem<NT>, tma);      /* GROUPS == 1: nothing behind it */
+    (void)with_tma;
     return mt_bytes + g_bytes * Cfg<NT>::GROUPS;
 }
 
@@ -1364,6 +1475,37 @@ __global__ void __launch_bounds__(256) k_ball_count(const __grid_constant__ Quer
     }
     ev = __reduce_add_sync(0xFFFFFFFFu, ev);
     if ((threadIdx.x & 31) == 0 && ev) atomicAdd(&a.evals[1], (unsigned long long)ev);
+}
+
+/* member lists from solve order (one slot per halo, reserved by the query kernels with an atomic cursor) into
+ * catalog order (CSR): warp per halo, the CTA together for the large ones */
+__global__ void __launch_bounds__(256) k_compact_members(const int32_t *__restrict__ out_n, int nh,
+                                                         const unsigned long long *__restrict__ src_off,
+                                                         const unsigned long long *__restrict__ csr_off,
+                                                         const int32_t *__restrict__ src, int32_t *__restrict__ dst,
+                                                         const float *__restrict__ src2, float *__restrict__ dst2)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int h0 = blockIdx.x * 8; h0 < nh; h0 += gridDim.x * 8) {
+        const int h = h0 + w;
+        const int n = h < nh ? max(out_n[h], 0) : 0;
+        if (n > 0 && n <= 8192) {
+            const unsigned long long a = src_off[h], b = csr_off[h];
+            for (int i = lane; i < n; i += 32) {
+                dst[b + i] = src[a + i];
+                if (src2) dst2[b + i] = src2[a + i];
+            }
+        }
+        for (int k = 0; k < 8 && h0 + k < nh; ++k) {
+            const int nn = max(out_n[h0 + k], 0);
+            if (nn <= 8192) continue;
+            const unsigned long long a = src_off[h0 + k], b = csr_off[h0 + k];
+            for (int i = threadIdx.x; i < nn; i += 256) {
+                dst[b + i] = src[a + i];
+                if (src2) dst2[b + i] = src2[a + i];
+            }
+        }
+    }
 }
 
 /* identity work list 0..n-1 */
@@ -2106,6 +2248,12 @@ struct sogpu {
     float *d_vc;                     /* sogpu_vcirc: per-group inputs and outputs */
     size_t vc_cap;
     bool members_sorted;             /* the device member lists are already in (r^2, index) order */
+    float last_thr;                  /* parameters of the last solve (its centres / radii are in d_centers / d_rgtp) */
+    int32_t last_nM;
+    bool members_csr;                /* d_out_off / d_members are in catalog (CSR) order; false: one slot per halo in solve order */
+    int32_t *d_members2;             /* second member buffers: target of the compaction into catalog order */
+    float *d_md2_2;
+    unsigned long long *d_csr_off;
 
     /* general (unequal-mass) path */
     GenState *d_gen_state;
@@ -2215,14 +2363,14 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     h->mask_bits = 9;
     if (const char *e = getenv("SOGPU_MASK_BITS")) h->mask_bits = std::min(9, std::max(4, atoi(e)));
     h->scan1_max = (size_t)1 << 18;
-    h->qgrid32 = 4; h->qgrid256 = 1; h->qorder = 0;    /* (measured: pending CTAs of the 256-thread class hold back the warp class) */
+    h->qgrid32 = 3; h->qgrid256 = 2; h->qorder = 0;    /* persistent grids of exactly the CTAs that can be resident (pending CTAs of one class hold back the next kernel's) */
     if (const char *e = getenv("SOGPU_QGRID32")) h->qgrid32 = std::max(1, atoi(e));
     if (const char *e = getenv("SOGPU_QGRID256")) h->qgrid256 = std::max(1, atoi(e));
     if (const char *e = getenv("SOGPU_QORDER")) h->qorder = atoi(e);
     if (const char *e = getenv("SOGPU_SCAN1_MAX")) h->scan1_max = (size_t)atoll(e);
     if (const char *e = getenv("SOGPU_TMA")) h->use_tma = atoi(e) != 0;
     if (const char *e = getenv("SOGPU_MASK_RMIN")) h->mask_rmin_cells = atof(e);
-    h->cls_small_max = 1024.0f; h->cls_huge_min = 4096.0f;
+    h->cls_small_max = 256.0f; h->cls_huge_min = 32768.0f;   /* warp class: balls that fit its 384 staged keys */
     h->emit_small_max = 2048; h->emit_huge_min = 4096;
     if (const char *e = getenv("SOGPU_SMALL_MAX")) h->cls_small_max = (float)atof(e);
     if (const char *e = getenv("SOGPU_HUGE_MIN")) h->cls_huge_min = (float)atof(e);
@@ -2294,7 +2442,8 @@ static void free_query(sogpu *h)
 {
     cudaFree(h->d_centers); cudaFree(h->d_rgtp); cudaFree(h->d_small); cudaFree(h->d_big);
     cudaFree(h->d_esmall); cudaFree(h->d_ebig); cudaFree(h->d_huge); cudaFree(h->d_ehuge); cudaFree(h->d_defer);
-    cudaFree(h->d_out_n); cudaFree(h->d_out_m); cudaFree(h->d_out_key); cudaFree(h->d_out_off);
+    cudaFree(h->d_out_n); cudaFree(h->d_out_m); cudaFree(h->d_out_key); cudaFree(h->d_out_off); cudaFree(h->d_csr_off);
+    h->d_csr_off = nullptr;
     h->d_centers = h->d_rgtp = nullptr; h->d_small = h->d_big = h->d_esmall = h->d_ebig = nullptr;
     h->d_huge = h->d_ehuge = h->d_defer = nullptr;
     h->d_out_n = nullptr; h->d_out_m = nullptr; h->d_out_key = h->d_out_off = nullptr;
@@ -2328,6 +2477,8 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     cudaFree(h->d_u64);
     cudaFree(h->d_members);
     cudaFree(h->d_md2);
+    cudaFree(h->d_members2);
+    cudaFree(h->d_md2_2);
     cudaFree(h->d_gen_state); cudaFree(h->d_gen_list[0]); cudaFree(h->d_gen_list[1]); cudaFree(h->d_gen_round);
     cudaFree(h->d_seg_n); cudaFree(h->d_seg_begin); cudaFree(h->d_seg_end);
     cudaFree(h->d_gkeys[0]); cudaFree(h->d_gkeys[1]); cudaFree(h->d_gmass[0]); cudaFree(h->d_gmass[1]);
@@ -2933,11 +3084,12 @@ static int ensure_query(sogpu *h, int32_t nh)
         CU(cudaMalloc(&h->d_out_m, (size_t)cap * sizeof(float)));
         CU(cudaMalloc(&h->d_out_key, (size_t)cap * sizeof(unsigned long long)));
         CU(cudaMalloc(&h->d_out_off, ((size_t)cap + 1) * sizeof(unsigned long long)));
+        CU(cudaMalloc(&h->d_csr_off, ((size_t)cap + 1) * sizeof(unsigned long long)));
         h->cap_h = cap;
     }
     if (!h->d_members || h->member_cap < (unsigned long long)h->n) {
-        cudaFree(h->d_members); cudaFree(h->d_md2);
-        h->d_members = nullptr; h->d_md2 = nullptr;
+        cudaFree(h->d_members); cudaFree(h->d_md2); cudaFree(h->d_members2); cudaFree(h->d_md2_2);
+        h->d_members = nullptr; h->d_md2 = nullptr; h->d_members2 = nullptr; h->d_md2_2 = nullptr;
         h->member_cap = (unsigned long long)std::max<int64_t>(h->n, 1 << 20);
         CU(cudaMalloc(&h->d_members, (size_t)h->member_cap * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_md2, (size_t)h->member_cap * sizeof(float)));
@@ -2965,6 +3117,14 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
     if (rc) return rc;
     cudaStream_t s = h->stream;
     h->stats.last_kernel_launches = 0;
+    /* the library keeps its own copy of the catalog: a member buffer that turns out too small is grown and the
+     * lists are emitted again from it, whenever the caller asks for them */
+    if (d_centers != h->d_centers)
+        CU(cudaMemcpyAsync(h->d_centers, d_centers, (size_t)nh * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (d_rgtp != h->d_rgtp)
+        CU(cudaMemcpyAsync(h->d_rgtp, d_rgtp, (size_t)nh * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    d_centers = h->d_centers; d_rgtp = h->d_rgtp;
+    h->last_thr = thr; h->last_nM = nM;
     CU(cudaMemsetAsync(h->d_counters, 0, 24 * sizeof(uint32_t), s));
     CU(cudaMemsetAsync(h->d_u64, 0, 4 * sizeof(unsigned long long), s));
 
@@ -2984,6 +3144,7 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
     a.out_n = h->d_out_n; a.out_m = h->d_out_m; a.out_key = h->d_out_key; a.out_off = h->d_out_off;
     a.members = h->d_members; a.md2 = h->want_d2 ? h->d_md2 : nullptr;
     a.member_cap = h->member_cap;
+    a.member_cursor = h->d_u64 + 0; a.emit_in_query = 1;
     a.evals = h->d_u64 + 1;
     a.flags = h->d_counters + 4;
     a.mt = h->d_mt;
@@ -3027,30 +3188,9 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
     h->launch_stream = s;
     CU(cudaStreamWaitEvent(s, h->ev_join[0], 0));
     CU(cudaStreamWaitEvent(s, h->ev_join[1], 0));
-    /* member offsets in catalog order, then the member lists (again three classes side by side) */
-    {
-        ProfScope p(h, KID_OFFSETS);
-        k_offsets<<<1, 1024, 0, s>>>(h->d_out_n, nh, h->d_out_off, h->d_u64 + 0, h->emit_small_max, h->d_esmall,
-                                     h->d_counters + 5, h->d_ebig, h->d_counters + 6, h->emit_huge_min, h->d_ehuge,
-                                     h->d_counters + 15);
-    }
-    CU(cudaEventRecord(h->ev_fork, s));
-    CU(cudaStreamWaitEvent(h->aux[0], h->ev_fork, 0));
-    CU(cudaStreamWaitEvent(h->aux[1], h->ev_fork, 0));
-    h->launch_stream = s;                                  /* (same order as the solve: whole-SM CTAs first) */
-    a.list = h->d_ehuge; a.list_n = h->d_counters + 15; a.work_counter = h->d_counters + 16;
-    { ProfScope p(h, KID_EMIT_HUGE); launch_persistent<1024>(h, k_so_emit<1024>, a, std::min(nh, h->sm_count)); }
-    h->launch_stream = h->aux[0];
-    a.list = h->d_ebig; a.list_n = h->d_counters + 6; a.work_counter = h->d_counters + 8;
-    { ProfScope p(h, KID_EMIT_BLOCK); launch_persistent<256>(h, k_so_emit<256>, a, nh); }
-    CU(cudaEventRecord(h->ev_join[0], h->aux[0]));
-    h->launch_stream = h->aux[1];
-    a.list = h->d_esmall; a.list_n = h->d_counters + 5; a.work_counter = h->d_counters + 7;
-    { ProfScope p(h, KID_EMIT_WARP); launch_persistent<32>(h, k_so_emit<32>, a, nh); }
-    CU(cudaEventRecord(h->ev_join[1], h->aux[1]));
-    h->launch_stream = s;
-    CU(cudaStreamWaitEvent(s, h->ev_join[0], 0));
-    CU(cudaStreamWaitEvent(s, h->ev_join[1], 0));
+    /* the member lists were written by the query kernels themselves, one slot per halo in the order the halos
+     * finished (d_out_off[h] = start, N_Delta entries); ensure_csr() puts them in catalog order on demand */
+    h->members_csr = false;
     CU(cudaGetLastError());
     h->last_h = nh;
     h->have_result = true;
@@ -3208,6 +3348,36 @@ static int emit_members(sogpu *h, const float *d_centers, const float *d_rgtp, i
     h->last_h = nh;
     h->have_result = true;
     h->members_sorted = false;
+    h->members_csr = true;
+    return SOGPU_OK;
+}
+
+/* member lists of the last solve in catalog order: d_out_off becomes the CSR offset array (nh + 1 entries) */
+static int ensure_csr(sogpu *h)
+{
+    if (!h->have_result || h->members_csr) return SOGPU_OK;
+    const int32_t nh = h->last_h;
+    cudaStream_t s = h->stream;
+    if (!h->d_members2) {
+        CU(cudaMalloc(&h->d_members2, (size_t)h->member_cap * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_md2_2, (size_t)h->member_cap * sizeof(float)));
+    }
+    CU(cudaMemsetAsync(h->d_counters + 5, 0, 4 * sizeof(uint32_t), s));
+    CU(cudaMemsetAsync(h->d_counters + 15, 0, 2 * sizeof(uint32_t), s));
+    {
+        ProfScope p(h, KID_OFFSETS, 0.0, 2);
+        k_offsets<<<1, 1024, 0, s>>>(h->d_out_n, nh, h->d_csr_off, h->d_u64 + 0, h->emit_small_max, h->d_esmall,
+                                     h->d_counters + 5, h->d_ebig, h->d_counters + 6, h->emit_huge_min, h->d_ehuge,
+                                     h->d_counters + 15);
+        k_compact_members<<<std::min((nh + 7) / 8, h->sm_count * 8), 256, 0, s>>>(
+            h->d_out_n, nh, h->d_out_off, h->d_csr_off, h->d_members, h->d_members2,
+            h->want_d2 ? h->d_md2 : nullptr, h->d_md2_2);
+    }
+    CU(cudaGetLastError());
+    std::swap(h->d_members, h->d_members2);
+    std::swap(h->d_md2, h->d_md2_2);
+    std::swap(h->d_out_off, h->d_csr_off);
+    h->members_csr = true;
     return SOGPU_OK;
 }
 
@@ -3234,8 +3404,8 @@ static int grow_members_and_reemit(sogpu *h, const float *d_centers, const float
                                    int32_t nM)
 {
     unsigned long long need = (unsigned long long)h->stats.last_members;
-    cudaFree(h->d_members); cudaFree(h->d_md2);
-    h->d_members = nullptr; h->d_md2 = nullptr;
+    cudaFree(h->d_members); cudaFree(h->d_md2); cudaFree(h->d_members2); cudaFree(h->d_md2_2);
+    h->d_members = nullptr; h->d_md2 = nullptr; h->d_members2 = nullptr; h->d_md2_2 = nullptr;
     h->member_cap = need + need / 16 + 1024;
     CU(cudaMalloc(&h->d_members, (size_t)h->member_cap * sizeof(int32_t)));
     CU(cudaMalloc(&h->d_md2, (size_t)h->member_cap * sizeof(float)));
@@ -3402,6 +3572,10 @@ extern "C" int sogpu_members(sogpu_t *h, int64_t *offsets, const int32_t **membe
     CU(cudaSetDevice(h->device));
     const int32_t nh = h->last_h;
     int rc = fetch_stats(h);
+    if (rc && h->member_overflow)      /* (asynchronous solves cannot retry by themselves: sogpu_so_device, domain steps) */
+        rc = grow_members_and_reemit(h, h->d_centers, h->d_rgtp, nh, h->last_thr, h->last_nM);
+    if (rc) return rc;
+    rc = ensure_csr(h);
     if (rc) return rc;
     const size_t tot = (size_t)h->stats.last_members;
     const bool dbg = getenv("SOGPU_DEBUG_TIMING") != nullptr;
@@ -3542,8 +3716,8 @@ extern "C" int sogpu_ball_gather_batch(sogpu_t *h, const float *centers, const f
         if (getenv("SOGPU_DEBUG_TIMING")) fprintf(stderr, "    [sogpu] ball batch attempt %d: %llu entries (cap %llu)\n", attempt, tot, h->member_cap);
         if (tot <= h->member_cap) break;
         if (attempt == 1) return set_err(SOGPU_ERR_NOMEM, "ball lists need %llu entries", tot);
-        cudaFree(h->d_members); cudaFree(h->d_md2);
-        h->d_members = nullptr; h->d_md2 = nullptr;
+        cudaFree(h->d_members); cudaFree(h->d_md2); cudaFree(h->d_members2); cudaFree(h->d_md2_2);
+        h->d_members = nullptr; h->d_md2 = nullptr; h->d_members2 = nullptr; h->d_md2_2 = nullptr;
         h->member_cap = tot + tot / 8;
         CU(cudaMalloc(&h->d_members, (size_t)h->member_cap * sizeof(int32_t)));
         CU(cudaMalloc(&h->d_md2, (size_t)h->member_cap * sizeof(float)));
@@ -3551,6 +3725,7 @@ extern "C" int sogpu_ball_gather_batch(sogpu_t *h, const float *centers, const f
     h->last_h = nh;
     h->have_result = true;
     h->members_sorted = false;
+    h->members_csr = true;
     h->want_d2 = true;
     return SOGPU_OK;
 }
@@ -3631,6 +3806,7 @@ extern "C" int sogpu_tag_members(sogpu_t *h, const int32_t *index, int32_t nh, u
     if (!h->have_result || h->last_h != nh)
         return set_err(SOGPU_ERR_ARG, "sogpu_tag_members: needs the member lists of a sogpu_so() call over the same %d groups", nh);
     CU(cudaSetDevice(h->device));
+    { int rc0 = ensure_csr(h); if (rc0) return rc0; }
     cudaStream_t s = h->stream;
     if (h->n > h->tag_cap) {
         cudaFree(h->d_tag); h->d_tag = nullptr; h->tag_cap = 0;
@@ -3891,6 +4067,8 @@ extern "C" int sogpu_vcm(sogpu_t *h, const float *mvir, int32_t nh, float *vcm)
     if (!h->want_d2) return set_err(SOGPU_ERR_ARG, "sogpu_vcm: call sogpu_keep_member_d2(h,1) before sogpu_so (the sum runs in r^2 order)");
     CU(cudaSetDevice(h->device));
     int rc = fetch_stats(h);
+    if (rc) return rc;
+    rc = ensure_csr(h);
     if (rc) return rc;
     const size_t tot = (size_t)h->stats.last_members;
     if (!h->members_sorted) {
