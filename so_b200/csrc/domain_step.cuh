@@ -232,117 +232,117 @@ struct StageArgs {
     uint32_t *flags;
 };
 
-#define RB_CAP 2048          /* records a CTA collects in shared memory before it writes them out */
-#define RB_FLUSH 1024
+#define RW_CAP 128           /* records a WARP collects in shared memory before it writes them out */
+#define RT_THREADS 512
+#define RT_U 8               /* independent 16-byte loads in flight per thread */
 
-/* Records are collected per CTA in shared memory (one aggregated shared-memory atomic per warp and step) and
- * written out RB_FLUSH.. at a time: one reservation per destination and flush, coalesced 16-byte stores.
- * Per particle the pass costs the load, three cell coordinates and one to three bitmap lookups — the
- * first version, which reserved and wrote per round of 1024 particles, spent ~100 warp instructions per 32
- * particles and ran at 2.9 TB/s, bound by instruction issue (profiles/r2_ncu_route_bucket.md). */
-__global__ void __launch_bounds__(256) k_route_stage(const __grid_constant__ StageArgs a)
+/* Every warp works on its own: it streams runs of 32 x RT_U particles, collects the few records they yield in a
+ * private shared-memory buffer and writes them out RW_CAP at a time (one reservation per destination and
+ * flush).  No block-wide barrier after the start: the first two versions reserved / flushed per CTA and round
+ * and spent their time waiting — 6.5 warps stalled on loads and 4 at the barrier per instruction issued, 3 TB/s
+ * (profiles/r2_ncu_route_bucket.md).  The 64^3 pre-filter (32 KB) is copied into shared memory once per CTA. */
+__global__ void __launch_bounds__(RT_THREADS, 2) k_route_stage(const __grid_constant__ StageArgs a)
 {
-    __shared__ float4 buf[RB_CAP];
-    __shared__ unsigned char bdst[RB_CAP];
-    __shared__ unsigned short brank[RB_CAP];
-    __shared__ uint32_t cnt, dcount[ROUTE_MAXR];
-    __shared__ unsigned long long dbase[ROUTE_MAXR];
-    if (threadIdx.x == 0) cnt = 0u;
-    __syncthreads();
+    extern __shared__ __align__(16) uint32_t s_dyn[];
     const int mask = a.g.nc - 1, mb = a.g.mb, ms = a.g.ms;
     const int sb = min(mb, DOM_SUPER_LOG), ss = mb - sb;
+    const uint32_t swords = ((1u << (3 * sb)) / 32u + 4u) & ~3u;           /* (multiple of 4: what follows stays 16-byte aligned) */
+    uint32_t *s_super = s_dyn;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float4 *wbuf = reinterpret_cast<float4 *>(s_dyn + swords) + (size_t)w * RW_CAP;
+    unsigned char *wdst = reinterpret_cast<unsigned char *>(reinterpret_cast<float4 *>(s_dyn + swords) + (size_t)(RT_THREADS / 32) * RW_CAP) +
+                          (size_t)w * RW_CAP;
+    for (uint32_t i = threadIdx.x; i < swords; i += blockDim.x) s_super[i] = i < (1u << (3 * sb)) / 32u + 1u ? __ldg(a.super + i) : 0u;
+    __syncthreads();
     const float g0x = a.g.g0[0], g0y = a.g.g0[1], g0z = a.g.g0[2], ihx = a.g.invh[0], ihy = a.g.invh[1], ihz = a.g.invh[2];
-    const uint32_t n = (uint32_t)a.n, stride = gridDim.x * blockDim.x;
+    const uint32_t S1 = 1u << mb, S2 = 1u << (2 * mb), T1 = 1u << sb, T2 = 1u << (2 * sb);
+    const uint32_t n = (uint32_t)a.n;
+    const int R = a.R;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t wcnt = 0;                                     /* records in this warp's buffer (same value on every lane) */
 
-    auto flush = [&](uint32_t m) {            /* all threads; m records in buf[0..m) */
-        if (a.R == 1) {
-            if (threadIdx.x == 0) {
-                unsigned long long base = atomicAdd(a.cursor[0], (unsigned long long)m);
-                if (base + m > a.cap[0]) { atomicOr(a.flags, a.flag_bit[0]); base = ~0ull; }
-                dbase[0] = base;
+    auto flush = [&]() {
+        if (R == 1) {
+            unsigned long long base = 0ull;
+            if (lane == 0) {
+                base = atomicAdd(a.cursor[0], (unsigned long long)wcnt);
+                if (base + wcnt > a.cap[0]) { atomicOr(a.flags, a.flag_bit[0]); base = ~0ull; }
             }
-            __syncthreads();
-            const unsigned long long base = dbase[0];
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
             if (base != ~0ull)
-                for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) a.dst[0][base + i] = buf[i];
+                for (uint32_t i = lane; i < wcnt; i += 32) a.dst[0][base + i] = wbuf[i];
         } else {
-            if (threadIdx.x < ROUTE_MAXR) dcount[threadIdx.x] = 0u;
-            __syncthreads();
-            for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) brank[i] = (unsigned short)atomicAdd(&dcount[bdst[i]], 1u);
-            __syncthreads();
-            if (threadIdx.x < (uint32_t)a.R) {
-                const int d = threadIdx.x;
-                const uint32_t c = dcount[d];
-                unsigned long long base = c ? atomicAdd(a.cursor[d], (unsigned long long)c) : 0ull;
-                if (base + c > a.cap[d]) { if (c) atomicOr(a.flags, a.flag_bit[d]); base = ~0ull; }
-                dbase[d] = base;
-            }
-            __syncthreads();
-            for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
-                const int d = bdst[i];
-                const unsigned long long base = dbase[d];
-                if (base != ~0ull) a.dst[d][base + brank[i]] = buf[i];
+            for (int d = 0; d < R; ++d) {
+                uint32_t mk[RW_CAP / 32], c = 0;
+#pragma unroll
+                for (int k = 0; k < RW_CAP / 32; ++k) {
+                    const uint32_t i = (uint32_t)k * 32u + lane;
+                    mk[k] = __ballot_sync(0xFFFFFFFFu, i < wcnt && wdst[i] == (unsigned char)d);
+                    c += __popc(mk[k]);
+                }
+                if (!c) continue;
+                unsigned long long base = 0ull;
+                if (lane == 0) {
+                    base = atomicAdd(a.cursor[d], (unsigned long long)c);
+                    if (base + c > a.cap[d]) { atomicOr(a.flags, a.flag_bit[d]); base = ~0ull; }
+                }
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                uint32_t before = 0;
+#pragma unroll
+                for (int k = 0; k < RW_CAP / 32; ++k) {
+                    if (base != ~0ull && ((mk[k] >> lane) & 1u))
+                        a.dst[d][base + before + __popc(mk[k] & lt)] = wbuf[k * 32 + lane];
+                    before += __popc(mk[k]);
+                }
             }
         }
-        __syncthreads();
-        if (threadIdx.x == 0) cnt = 0u;
-        __syncthreads();
+        __syncwarp();
+        wcnt = 0;
     };
 
-    const uint32_t per_round = stride * ROUTE_U;
-    const uint32_t nround = (n + per_round - 1) / per_round;
-    for (uint32_t it = 0; it < nround; ++it) {               /* every thread runs every round (barriers) */
-        const uint32_t i0 = it * per_round + blockIdx.x * blockDim.x + threadIdx.x;
-        float4 q[ROUTE_U];
-        uint32_t set[ROUTE_U];
+    const uint32_t gw = blockIdx.x * (RT_THREADS / 32) + (uint32_t)w, nwarp = gridDim.x * (RT_THREADS / 32);
+    const uint32_t run = 32u * RT_U;
+    const uint32_t nrun = (n + run - 1) / run;
+    for (uint32_t r = gw; r < nrun; r += nwarp) {
+        const uint32_t i0 = r * run + lane;
+        float4 q[RT_U];
 #pragma unroll
-        for (int u = 0; u < ROUTE_U; ++u) {
-            const uint32_t i = i0 + u * stride;
-            if (i < n) q[u] = ld_stream(a.slice + i);
+        for (int u = 0; u < RT_U; ++u) {
+            const uint32_t i = i0 + u * 32u;
+            q[u] = ld_stream(a.slice + (i < n ? i : n - 1u));
         }
 #pragma unroll
-        for (int u = 0; u < ROUTE_U; ++u) {
-            const uint32_t i = i0 + u * stride;
-            set[u] = 0u;
-            if (i < n) {
-                /* (the same expressions as the grid build's cell_coord: a particle is routed by the cell it will be sorted into) */
-                const uint32_t cx = cell_coord(q[u].x, g0x, ihx, mask) >> ms;
-                const uint32_t cy = cell_coord(q[u].y, g0y, ihy, mask) >> ms;
-                const uint32_t cz = cell_coord(q[u].z, g0z, ihz, mask) >> ms;
-                /* three lookups, cheapest first: 64^3 pre-filter (32 KB: L1), "somebody wants it" bitmap (L2),
-                 * destination set (only for the few particles that pass both) */
-                const uint32_t sbit = ((cz >> ss) << (2 * sb)) | ((cy >> ss) << sb) | (cx >> ss);
-                if ((__ldg(a.super + (sbit >> 5)) >> (sbit & 31)) & 1u) {
-                    const uint32_t bit = (cz << (2 * mb)) | (cy << mb) | cx;
-                    if ((__ldg(a.any + (bit >> 5)) >> (bit & 31)) & 1u) {
-                        set[u] = a.R > 1 ? (uint32_t)__ldg(a.table + bit) : 1u;
-                        q[u].w = __uint_as_float(a.index_base + i);
-                    }
-                }
+        for (int u = 0; u < RT_U; ++u) {
+            const uint32_t i = i0 + u * 32u;
+            /* (the same expressions as the grid build's cell_coord: a particle is routed by the cell it will be sorted into) */
+            const uint32_t cx = cell_coord(q[u].x, g0x, ihx, mask) >> ms;
+            const uint32_t cy = cell_coord(q[u].y, g0y, ihy, mask) >> ms;
+            const uint32_t cz = cell_coord(q[u].z, g0z, ihz, mask) >> ms;
+            /* three lookups, cheapest first: 64^3 pre-filter (shared memory), "somebody wants it" bitmap (L2),
+             * destination set (only for the few particles that pass both) */
+            const uint32_t sbit = (cz >> ss) * T2 + (cy >> ss) * T1 + (cx >> ss);
+            uint32_t set = 0u;
+            if (i < n && ((s_super[sbit >> 5] >> (sbit & 31)) & 1u)) {
+                const uint32_t bit = cz * S2 + cy * S1 + cx;
+                if ((__ldg(a.any + (bit >> 5)) >> (bit & 31)) & 1u) set = R > 1 ? (uint32_t)__ldg(a.table + bit) : 1u;
             }
-        }
-        for (;;) {
-            int pending = 0;
-#pragma unroll
-            for (int u = 0; u < ROUTE_U; ++u) {
-                while (set[u]) {
-                    const int d = __ffs(set[u]) - 1;
-                    const uint32_t pos = agg_append(&cnt);
-                    if (pos >= RB_CAP) { pending = 1; break; }
-                    buf[pos] = q[u];
-                    bdst[pos] = (unsigned char)d;
-                    set[u] &= set[u] - 1u;
+            uint32_t wset = __reduce_or_sync(0xFFFFFFFFu, set);
+            if (!wset) continue;
+            q[u].w = __uint_as_float(a.index_base + i);
+            for (; wset; wset &= wset - 1u) {
+                const int d = __ffs(wset) - 1;
+                if (wcnt + 32u > RW_CAP) flush();
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, (set >> d) & 1u);
+                if ((set >> d) & 1u) {
+                    const uint32_t pos = wcnt + __popc(m & lt);
+                    wbuf[pos] = q[u];
+                    wdst[pos] = (unsigned char)d;
                 }
+                wcnt += __popc(m);
             }
-            const int more = __syncthreads_or(pending);
-            const uint32_t c = cnt;
-            if (c >= RB_FLUSH) flush(min(c, (uint32_t)RB_CAP));
-            if (!more) break;
         }
     }
-    __syncthreads();
-    const uint32_t c = cnt;
-    if (c) flush(min(c, (uint32_t)RB_CAP));
+    if (wcnt) flush();
 }
 
 /* ---- push: staging runs -> the receivers' buffers over NVLink ---------------------------------------- */
@@ -641,9 +641,12 @@ extern "C" int sogpu_domain_route(sogpu_t *h, const void *d_chunk, int64_t n, in
         ProfScope p(h, KID_ROUTE, 16.0 * (double)n);
         /* persistent grid of exactly the CTAs that are resident at once: a second, partial wave would leave
          * the SMs of the finished CTAs idle */
+        const size_t swords = ((((size_t)1 << (3 * std::min(a.g.mb, DOM_SUPER_LOG))) / 32 + 4) & ~(size_t)3);
+        const size_t ssm = swords * sizeof(uint32_t) + (size_t)(RT_THREADS / 32) * RW_CAP * (sizeof(float4) + 1);
+        CU(cudaFuncSetAttribute(k_route_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024)));   /* (more than 48 KB: opt in) */
         int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_route_stage, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-        k_route_stage<<<(int)std::min<int64_t>((n + 255) / 256, (int64_t)h->sm_count * per_sm), 256, 0, h->stream>>>(a);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_route_stage, RT_THREADS, ssm) != cudaSuccess || per_sm < 1) per_sm = 1;
+        k_route_stage<<<(int)std::min<int64_t>((n + RT_THREADS - 1) / RT_THREADS, (int64_t)h->sm_count * per_sm), RT_THREADS, ssm, h->stream>>>(a);
     }
     CU(cudaGetLastError());
     return SOGPU_OK;

@@ -877,3 +877,159 @@ __global__ void __launch_bounds__(BR_NT, BR_MINB) k_bucket_sort_rt(const float4 
         __syncthreads();
     }
 }
+
+/* ---- final pass of a FOCUSED grid: work proportional to the marked cells -------------------------------
+ * A focused grid holds particles only in the coarse cells of the mask — a few percent of the volume, spread
+ * over nearly every final bucket.  The dense kernel above zeroes, scans and stores 4096 counters per bucket for
+ * a few hundred particles (measured: 3000 warp instructions per bucket, 2.3 ms of an 11 ms step at 1024^3).
+ * Here a bucket first reads its slice of the mask (<= 128 words), numbers its marked cells with a popcount
+ * prefix, and then counts, scans and stores over those compact cells only.  The queries read ce[] at marked
+ * cells and at the entry right behind one; exactly those entries are written (plus the bucket's first). */
+#define BS_NT 128
+#define BS_IT 8
+__global__ void __launch_bounds__(BS_NT, 8) k_bucket_sort_sparse(const float4 *__restrict__ in4, GridDev g, int cell_bits,
+                                                                 uint32_t n_buckets, const uint32_t *__restrict__ bstart,
+                                                                 float4 *__restrict__ sorted, uint32_t *__restrict__ ce,
+                                                                 const uint32_t *__restrict__ live,
+                                                                 const uint32_t *__restrict__ live_n)
+{
+    __shared__ uint32_t mw[128], mpre[129];
+    __shared__ uint32_t cnt[BKT_CELLS + 1];
+    __shared__ uint32_t ws[BS_NT / 32 + 1];
+    __shared__ uint32_t carry_s;
+    const int ncells = 1 << cell_bits;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int nrow = ncells >> g.lb;                         /* fine rows of a bucket (host: cell_bits >= lb) */
+    const int wpr = (g.nc >> g.ms) >> 5;                     /* mask words per row (host: nc >> ms >= 32)     */
+    const int nwords = nrow * wpr;                           /* <= 128                                        */
+    const uint32_t sub = (1u << g.ms) - 1u;
+    if (live) n_buckets = __ldg(live_n);
+    for (uint32_t bi = blockIdx.x; bi < n_buckets; bi += gridDim.x) {
+        const uint32_t b = live ? __ldg(live + bi) : bi;
+        const uint32_t b0 = __ldg(bstart + b), b1 = __ldg(bstart + b + 1), nb = b1 - b0;
+        uint32_t *ceb = ce + ((size_t)b << cell_bits);
+        /* the bucket's mask words and their popcount prefix */
+        uint32_t myw = 0u;
+        if (t < nwords) {
+            const int r = t / wpr, j = t - r * wpr;
+            const uint32_t rk = (b << (cell_bits - g.lb)) + (uint32_t)r;           /* row key */
+            const uint32_t m = (1u << g.tb) - 1u, lo = rk & ((1u << (2 * g.tb)) - 1u), hi = rk >> (2 * g.tb);
+            const uint32_t iy = ((hi & ((1u << (g.lb - g.tb)) - 1u)) << g.tb) | (lo & m);
+            const uint32_t iz = ((hi >> (g.lb - g.tb)) << g.tb) | (lo >> g.tb);
+            const uint32_t mrow = ((iz >> g.ms) << (2 * g.mb)) | ((iy >> g.ms) << g.mb);
+            myw = __ldg(g.mask + (mrow >> 5) + j);
+        }
+        float4 q[BS_IT];
+        const bool in_regs = nb <= (uint32_t)(BS_NT * BS_IT);
+        if (in_regs) {
+#pragma unroll
+            for (int k = 0; k < BS_IT; ++k) {
+                const uint32_t i = t + k * BS_NT;
+                if (i < nb) q[k] = ld_stream(in4 + b0 + i);
+            }
+        }
+        {
+            uint32_t x = __popc(myw);
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t u = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                if (lane >= o) x += u;
+            }
+            if (lane == 31) ws[w] = x;
+            __syncthreads();
+            uint32_t off = 0;
+#pragma unroll
+            for (int k = 0; k < BS_NT / 32; ++k) off += (k < w) ? ws[k] : 0u;
+            mw[t] = myw;
+            mpre[t] = off + x - __popc(myw);
+            if (t == BS_NT - 1) mpre[BS_NT] = off + x;
+        }
+        __syncthreads();
+        const uint32_t ncomp = mpre[BS_NT] << g.ms;          /* compact (marked) fine cells of this bucket */
+        for (uint32_t i = t; i <= ncomp; i += BS_NT) cnt[i] = 0u;
+        __syncthreads();
+        auto compact = [&](uint32_t c) -> uint32_t {          /* cell inside the bucket -> compact index */
+            const uint32_t r = c >> g.lb, x = c & (uint32_t)(g.nc - 1), xc = x >> g.ms;
+            const uint32_t wi = r * (uint32_t)wpr + (xc >> 5), bp = xc & 31u;
+            return ((mpre[wi] + __popc(mw[wi] & ((1u << bp) - 1u))) << g.ms) | (x & sub);
+        };
+        uint32_t cr[BS_IT];
+        if (in_regs) {
+#pragma unroll
+            for (int k = 0; k < BS_IT; ++k) {
+                const uint32_t i = t + k * BS_NT;
+                if (i < nb) {
+                    const uint32_t ci = compact(cell_key_low(q[k], g, cell_bits));
+                    cr[k] = (ci << 16) | atomicAdd(&cnt[ci], 1u);
+                }
+            }
+        } else {
+            for (uint32_t i = t; i < nb; i += BS_NT) {
+                const float4 qq = __ldg(in4 + b0 + i);
+                atomicAdd(&cnt[compact(cell_key_low(qq, g, cell_bits))], 1u);
+            }
+        }
+        __syncthreads();
+        /* exclusive scan over the compact cells, BS_NT at a time; cnt[ncomp] = particles of the bucket */
+        if (t == 0) carry_s = 0u;
+        __syncthreads();
+        for (uint32_t base = 0; base < ncomp; base += BS_NT) {
+            const uint32_t i = base + t;
+            const uint32_t v = i < ncomp ? cnt[i] : 0u;
+            uint32_t x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t u = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                if (lane >= o) x += u;
+            }
+            if (lane == 31) ws[w] = x;
+            __syncthreads();
+            uint32_t off = carry_s;
+#pragma unroll
+            for (int k = 0; k < BS_NT / 32; ++k) off += (k < w) ? ws[k] : 0u;
+            if (i < ncomp) cnt[i] = off + x - v;
+            __syncthreads();
+            if (t == BS_NT - 1) carry_s = off + x;
+            __syncthreads();
+        }
+        if (t == 0) cnt[ncomp] = carry_s;
+        __syncthreads();
+        /* particles to their final slots */
+        if (in_regs) {
+#pragma unroll
+            for (int k = 0; k < BS_IT; ++k) {
+                const uint32_t i = t + k * BS_NT;
+                if (i < nb) sorted[b0 + cnt[cr[k] >> 16] + (cr[k] & 0xFFFFu)] = q[k];
+            }
+        }
+        /* cell table: the bucket's first entry, every marked cell, and the entry right behind a marked cell */
+        if (t == 0) ceb[0] = b0;
+        if (t < nwords) {
+            const int r = t / wpr, j = t - r * wpr;
+            uint32_t word = mw[t], k0 = mpre[t];
+            while (word) {
+                const int bp = __ffs(word) - 1;
+                word &= word - 1u;
+                const uint32_t xc = (uint32_t)j * 32u + (uint32_t)bp;
+                for (uint32_t sx = 0; sx <= sub; ++sx) {
+                    const uint32_t c = ((uint32_t)r << g.lb) + ((xc << g.ms) | sx), kc = (k0 << g.ms) | sx;
+                    ceb[c] = b0 + cnt[kc];
+                    /* the next cell in key order: written here unless it is marked itself (then it writes its own
+                     * start, the same value) or lies in the next bucket (whose first entry is always written) */
+                    if (sx == sub && c + 1u < (uint32_t)ncells) ceb[c + 1u] = b0 + cnt[kc + 1u];
+                }
+                ++k0;
+            }
+        }
+        __syncthreads();
+        if (!in_regs) {
+            /* oversized bucket (a dense halo core): second read (L2), slots from the scanned counters as cursors */
+            for (uint32_t i = t; i < nb; i += BS_NT) {
+                const float4 qq = __ldg(in4 + b0 + i);
+                const uint32_t dst = atomicAdd(&cnt[compact(cell_key_low(qq, g, cell_bits))], 1u);
+                sorted[b0 + dst] = qq;
+            }
+            __syncthreads();
+        }
+    }
+}

@@ -62,7 +62,7 @@ template <> struct Cfg<32> {   /* warp per halo */
     static const int CAP = 256, WTARGET = 128, NLEV = 1, GROUPS = 8, MINB = Q32_MINB, SCAP = 384;
 };
 template <> struct Cfg<256> {  /* block per halo */
-    static const int CAP = 4096, WTARGET = 1024, NLEV = 4, GROUPS = 1, MINB = Q256_MINB, SCAP = 6144;
+    static const int CAP = 1024, WTARGET = 256, NLEV = 4, GROUPS = 1, MINB = Q256_MINB, SCAP = 6144;
 };
 template <> struct Cfg<1024> { /* one full-SM block per halo: cluster-size halos (>= ~10^5 particles) */
     static const int CAP = 4096, WTARGET = 2048, NLEV = 4, GROUPS = 1, MINB = 1, SCAP = 4096;
@@ -785,19 +785,49 @@ __device__ __forceinline__ int find_candidate(const uint32_t *cum, const Level &
     return gmin<NT>(best, tmp, tid);
 }
 
+/* Bitonic sort of P (a power of two) keys in shared memory.  CTA groups: every warp owns a contiguous chunk of
+ * C = P / warps >= 64 keys, and the P/2 compare-exchanges of a stage are dealt so that a stage whose stride j is
+ * below C stays inside the warps' own chunks — those stages need __syncwarp only.  Block-wide barriers remain
+ * around the few stages with j >= C (9 instead of 55 for P = 1024 and 8 warps). */
 template <int NT> __device__ __forceinline__ void bitonic_sort(unsigned long long *key, int P, int tid)
 {
+    if (NT == 32) {
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < P; i += NT) {
+                    int ixj = i ^ j;
+                    if (ixj > i) {
+                        unsigned long long a = key[i], b = key[ixj];
+                        bool up = ((i & k) == 0);
+                        if ((a > b) == up) { key[i] = b; key[ixj] = a; }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        return;
+    }
+    int nw = P / 64;
+    if (nw > NT / 32) nw = NT / 32;
+    if (nw < 1) nw = 1;
+    const int C = P / nw, halfC = C >> 1;
+    const int w = tid >> 5, lane = tid & 31;
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < P; i += NT) {
-                int ixj = i ^ j;
-                if (ixj > i) {
+            if (w < nw) {
+                for (int m = lane; m < halfC; m += 32) {
+                    const int pr = w * halfC + m;
+                    const int i = ((pr & ~(j - 1)) << 1) | (pr & (j - 1));       /* a zero bit inserted at log2(j) */
+                    const int ixj = i | j;
                     unsigned long long a = key[i], b = key[ixj];
-                    bool up = ((i & k) == 0);
+                    const bool up = ((i & k) == 0);
                     if ((a > b) == up) { key[i] = b; key[ixj] = a; }
                 }
             }
-            gsync<NT>();
+            /* what the NEXT stage reads decides the barrier: chunk-local strides only need the warp's own writes */
+            const int nk = (j > 1) ? k : (k << 1), nj = (j > 1) ? (j >> 1) : (nk >> 1);
+            const bool next_cross = (nk > P) || nj >= C;
+            if (j >= C || next_cross) __syncthreads(); else __syncwarp();
         }
     }
 }
@@ -1157,6 +1187,9 @@ struct QueryArgs {
     const int32_t *list;       /* halo ids this kernel processes */
     const uint32_t *list_n;    /* how many */
     uint32_t *work_counter;    /* dynamic scheduling */
+    const int32_t *list2;      /* (fused kernel) the warp-per-halo list, processed after `list` */
+    const uint32_t *list2_n;
+    uint32_t *work_counter2;
     int32_t *defer_list;       /* (warp kernel) halos handed to the block kernel */
     uint32_t *defer_n;
     float thr;
@@ -1198,12 +1231,12 @@ __device__ __forceinline__ uint32_t next_item(uint32_t *counter, GroupSmem<NT> &
 template <int NT>
 __global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS, Cfg<NT>::MINB) k_so_query(const __grid_constant__ QueryArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     MassTableS &mt = *reinterpret_cast<MassTableS *>(smem_raw);
-    const size_t mt_bytes = (sizeof(MassTableS) + 15) & ~(size_t)15;
+    const size_t mt_bytes = (sizeof(MassTableS) + 127) & ~(size_t)127;
     const int grp = threadIdx.x / NT, tid = threadIdx.x % NT;
     GroupSmem<NT> &sm = *reinterpret_cast<GroupSmem<NT> *>(
-        smem_raw + mt_bytes + (size_t)grp * ((sizeof(GroupSmem<NT>) + 15) & ~(size_t)15));
+        smem_raw + mt_bytes + (size_t)grp * ((sizeof(GroupSmem<NT>) + 127) & ~(size_t)127));
 
     /* CTA-wide: copy the mass table (built on the device by k_mass_table) */
     const int mtn = a.mt->n;
@@ -1255,15 +1288,106 @@ __global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS, Cfg<NT>::MINB) k_so_query
     }
 }
 
+/* The two common size classes in ONE persistent kernel: every CTA (256 threads) first takes mid-size halos from
+ * `list` as a whole (one CTA per halo), then splits into its 8 warps, each of which takes small halos from `list2`
+ * on its own.  Identical CTAs on every SM: no kernel of one class keeps the other off the SMs (with separate
+ * kernels the first one resident held the shared memory until it drained), the long items are started first,
+ * and the machine stays full until both lists are empty.  The shared memory is a union of the two layouts. */
+#ifndef QF_MINB
+#define QF_MINB 3
+#endif
+static size_t fused_smem_bytes()
+{
+    size_t mt_bytes = (sizeof(MassTableS) + 127) & ~(size_t)127;
+    size_t a = sizeof(GroupSmem<256>), b = 8 * sizeof(GroupSmem<32>);
+    return mt_bytes + (a > b ? a : b);
+}
+
+__global__ void __launch_bounds__(256, QF_MINB) k_so_query_fused(const __grid_constant__ QueryArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    MassTableS &mt = *reinterpret_cast<MassTableS *>(smem_raw);
+    const size_t mt_bytes = (sizeof(MassTableS) + 127) & ~(size_t)127;
+    unsigned char *base = smem_raw + mt_bytes;
+    const int mtn = a.mt->n;
+    if (mtn > 0) {
+        if (threadIdx.x == 0) { mt.n = mtn; mt.m = a.mt->m; }
+        for (int i = threadIdx.x; i <= mtn; i += blockDim.x) mt.k0[i] = a.mt->k0[i];
+        for (int i = threadIdx.x; i < mtn; i += blockDim.x) { mt.s0[i] = a.mt->s0[i]; mt.inc[i] = a.mt->inc[i]; }
+    }
+    __syncthreads();
+    EmitCtx ec;
+    ec.members = a.emit_in_query ? a.members : nullptr; ec.md2 = a.md2; ec.cap = a.member_cap;
+    ec.cursor = a.member_cursor; ec.flags = a.flags; ec.stage = 1;
+    uint32_t ev_hist = 0, ev_other = 0;
+    {   /* ---- CTA per halo ---- */
+        GroupSmem<256> &sm = *reinterpret_cast<GroupSmem<256> *>(base);
+        const int tid = threadIdx.x;
+        const uint32_t nlist = *a.list_n;
+        for (;;) {
+            const uint32_t item = next_item<256>(a.work_counter, sm, tid);
+            if (item >= nlist) break;
+            const int h = a.list[item];
+            HaloResult res;
+            if (mtn <= 0) {
+                res.n = CODE_UNEQUAL_MASS; res.m = 0.0f; res.key_j = 0ull; res.off = 0ull;
+            } else {
+                Center c;
+                c.x = a.centers[3 * h + 0]; c.y = a.centers[3 * h + 1]; c.z = a.centers[3 * h + 2];
+                so_halo<256>(a.g, mt, sm, tid, c, a.rgtp[h], a.thr, a.nM, a.first_ball, res, ev_hist, ev_other, ec);
+                __syncthreads();
+            }
+            if (tid == 0) {
+                a.out_n[h] = res.n; a.out_m[h] = res.m; a.out_key[h] = res.key_j;
+                if (a.emit_in_query) a.out_off[h] = res.off;
+            }
+        }
+    }
+    __syncthreads();
+    {   /* ---- warp per halo ---- */
+        const int grp = threadIdx.x >> 5, tid = threadIdx.x & 31;
+        GroupSmem<32> &sm = reinterpret_cast<GroupSmem<32> *>(base)[grp];
+        const uint32_t nlist = *a.list2_n;
+        for (;;) {
+            const uint32_t item = next_item<32>(a.work_counter2, sm, tid);
+            if (item >= nlist) break;
+            const int h = a.list2[item];
+            HaloResult res;
+            if (mtn <= 0) {
+                res.n = CODE_UNEQUAL_MASS; res.m = 0.0f; res.key_j = 0ull; res.off = 0ull;
+            } else {
+                Center c;
+                c.x = a.centers[3 * h + 0]; c.y = a.centers[3 * h + 1]; c.z = a.centers[3 * h + 2];
+                so_halo<32>(a.g, mt, sm, tid, c, a.rgtp[h], a.thr, a.nM, a.first_ball, res, ev_hist, ev_other, ec);
+                __syncwarp();
+            }
+            if (res.n == CODE_DEFER) {       /* a bin too large for a warp's window: a CTA takes the halo (kernel behind this one) */
+                if (tid == 0) a.defer_list[atomicAdd(a.defer_n, 1u)] = h;
+                continue;
+            }
+            if (tid == 0) {
+                a.out_n[h] = res.n; a.out_m[h] = res.m; a.out_key[h] = res.key_j;
+                if (a.emit_in_query) a.out_off[h] = res.off;
+            }
+        }
+    }
+    ev_hist = __reduce_add_sync(0xFFFFFFFFu, ev_hist);
+    ev_other = __reduce_add_sync(0xFFFFFFFFu, ev_other);
+    if ((threadIdx.x & 31) == 0) {
+        if (ev_hist) atomicAdd(&a.evals[0], (unsigned long long)ev_hist);
+        if (ev_other) atomicAdd(&a.evals[1], (unsigned long long)ev_other);
+    }
+}
+
 /* K5: member lists in CSR form.  Halo h owns members[out_off[h] .. out_off[h]+N_Delta). */
 template <int NT>
 __global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS) k_so_emit(const __grid_constant__ QueryArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const size_t mt_bytes = (sizeof(MassTableS) + 15) & ~(size_t)15;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const size_t mt_bytes = (sizeof(MassTableS) + 127) & ~(size_t)127;
     const int grp = threadIdx.x / NT, tid = threadIdx.x % NT;
     GroupSmem<NT> &sm = *reinterpret_cast<GroupSmem<NT> *>(
-        smem_raw + mt_bytes + (size_t)grp * ((sizeof(GroupSmem<NT>) + 15) & ~(size_t)15));
+        smem_raw + mt_bytes + (size_t)grp * ((sizeof(GroupSmem<NT>) + 127) & ~(size_t)127));
     tma_stage_init<NT>(sm, tid, a.g.use_tma);
     const uint32_t nlist = *a.list_n;
     uint32_t ev = 0;
@@ -1298,8 +1422,8 @@ __global__ void __launch_bounds__(NT *Cfg<NT>::GROUPS) k_so_emit(const __grid_co
 
 template <int NT> static size_t query_smem_bytes(bool with_tma = true)
 {
-    size_t mt_bytes = (sizeof(MassTableS) + 15) & ~(size_t)15;
-    size_t g_bytes = (sizeof(GroupSmem<NT>) + 15) & ~(size_t)15;
+    size_t mt_bytes = (sizeof(MassTableS) + 127) & ~(size_t)127;
+    size_t g_bytes = (sizeof(GroupSmem<NT>) + 127) & ~(size_t)127;
     (void)with_tma;
     return mt_bytes + g_bytes * Cfg<NT>::GROUPS;
 }
@@ -1447,11 +1571,11 @@ struct CountF {
 
 __global__ void __launch_bounds__(256) k_ball_count(const __grid_constant__ QueryArgs a, const float *ball2)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const size_t mt_bytes = (sizeof(MassTableS) + 15) & ~(size_t)15;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const size_t mt_bytes = (sizeof(MassTableS) + 127) & ~(size_t)127;
     const int grp = threadIdx.x / 32, tid = threadIdx.x % 32;
     GroupSmem<32> &sm = *reinterpret_cast<GroupSmem<32> *>(
-        smem_raw + mt_bytes + (size_t)grp * ((sizeof(GroupSmem<32>) + 15) & ~(size_t)15));
+        smem_raw + mt_bytes + (size_t)grp * ((sizeof(GroupSmem<32>) + 127) & ~(size_t)127));
     const uint32_t nlist = *a.list_n;
     uint32_t ev = 0;
     for (;;) {
@@ -1594,8 +1718,8 @@ struct EmitPairF {
 /* advance every active halo to its next ball and count the particles in it (kd2.c:766-778) */
 __global__ void __launch_bounds__(256) k_gen_count(const __grid_constant__ GenArgs a)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const size_t mt_bytes = (sizeof(MassTableS) + 15) & ~(size_t)15;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const size_t mt_bytes = (sizeof(MassTableS) + 127) & ~(size_t)127;
     GroupSmem<256> &sm = *reinterpret_cast<GroupSmem<256> *>(smem_raw + mt_bytes);
     const int tid = threadIdx.x;
     const uint32_t nlist = *a.list_n;
@@ -1672,8 +1796,8 @@ __global__ void __launch_bounds__(1024) k_gen_offsets(const unsigned long long *
 /* write (key, mass) of every particle of the ball into the halo's scratch segment */
 __global__ void __launch_bounds__(256) k_gen_emit(const __grid_constant__ GenArgs a, uint32_t s0, uint32_t s1)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const size_t mt_bytes = (sizeof(MassTableS) + 15) & ~(size_t)15;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const size_t mt_bytes = (sizeof(MassTableS) + 127) & ~(size_t)127;
     GroupSmem<256> &sm = *reinterpret_cast<GroupSmem<256> *>(smem_raw + mt_bytes);
     const int tid = threadIdx.x;
     uint32_t ev = 0;
@@ -2148,13 +2272,13 @@ __global__ void __launch_bounds__(256) k_member_unkeys(const unsigned long long 
 enum {
     KID_LVL_HIST = 0, KID_LVL_SCAN, KID_LVL_PARTITION, KID_BUCKET_SORT, KID_MASS_TABLE, KID_CLASSIFY,
     KID_QUERY_WARP, KID_QUERY_BLOCK, KID_OFFSETS, KID_EMIT_WARP, KID_EMIT_BLOCK, KID_BALL_GATHER,
-    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_VCIRC, KID_TAG, KID_ROUTE, KID_ASSIGN, KID_PUSH, KID_BARRIER, KID_N
+    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_VCIRC, KID_TAG, KID_ROUTE, KID_ASSIGN, KID_PUSH, KID_BARRIER, KID_QUERY_FUSED, KID_N
 };
 static const char *const g_kernel_names[KID_N] = {
     "k_lvl_hist", "k_scan", "k_lvl_partition", "k_bucket_sort", "k_mass_table", "k_classify",
     "k_so_query<32>", "k_so_query<256>", "k_offsets", "k_so_emit<32>", "k_so_emit<256>", "k_ball_gather",
     "k_so_query<1024>", "k_so_emit<1024>", "k_mark_mask", "k_vcirc", "k_tag_claim+settle", "k_route",
-    "k_assign", "k_push", "k_dom_barrier"};
+    "k_assign", "k_push", "k_dom_barrier", "k_so_query_fused"};
 
 struct ProfRec { int kid, launches; cudaEvent_t a, b; };
 
@@ -2196,6 +2320,7 @@ struct sogpu {
     int emit_small_max, emit_huge_min;   /* same split for the member emission, by N_Delta */
     int qgrid32, qgrid256;           /* persistent CTAs per SM of the warp / 256-thread halo kernels */
     int qorder;                      /* launch order of the classes behind the 1024-thread one (tuning) */
+    int fused_query;                 /* 1: warp and 256-thread classes in one persistent kernel (default) */
     size_t scan1_max;                /* bucket tables up to this many entries are scanned by one block */
     bool use_tma;                    /* sogpu_set_tma_staging */
     double mask_rmin_cells;          /* focus masks: minimum half-width per halo, in coarse cells */
@@ -2367,6 +2492,8 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     if (const char *e = getenv("SOGPU_QGRID32")) h->qgrid32 = std::max(1, atoi(e));
     if (const char *e = getenv("SOGPU_QGRID256")) h->qgrid256 = std::max(1, atoi(e));
     if (const char *e = getenv("SOGPU_QORDER")) h->qorder = atoi(e);
+    h->fused_query = 1;
+    if (const char *e = getenv("SOGPU_FUSED")) h->fused_query = atoi(e) != 0;
     if (const char *e = getenv("SOGPU_SCAN1_MAX")) h->scan1_max = (size_t)atoll(e);
     if (const char *e = getenv("SOGPU_TMA")) h->use_tma = atoi(e) != 0;
     if (const char *e = getenv("SOGPU_MASK_RMIN")) h->mask_rmin_cells = atof(e);
@@ -2400,6 +2527,8 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_so_query<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<32>());
     if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_so_query_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem_bytes());
+    if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_so_emit<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<256>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(k_so_emit<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)query_smem_bytes<32>());
@@ -2414,7 +2543,7 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
      * (measured with %globaltimer: whichever class started first kept the others out for 70-120 us).
      * Every query / emit kernel therefore asks for the same (maximum shared memory) carve-out. */
     {
-        const void *fns[] = {(const void *)k_so_query<32>, (const void *)k_so_query<256>, (const void *)k_so_query<1024>,
+        const void *fns[] = {(const void *)k_so_query<32>, (const void *)k_so_query<256>, (const void *)k_so_query<1024>, (const void *)k_so_query_fused,
                              (const void *)k_so_emit<32>, (const void *)k_so_emit<256>, (const void *)k_so_emit<1024>};
         for (const void *f : fns)
             if (e == cudaSuccess)
@@ -2988,7 +3117,12 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
                 k_bucket_live<<<(nb + 255) / 256, 256, 0, s>>>(g, cell_bits, nb, bstart, h->d_ce, h->d_live, h->d_live + nb);
                 live = h->d_live; live_n = h->d_live + nb;
             }
-            if (n_work / (int64_t)nb < 160 && nb >= 4096u) {      /* sparse buckets: small CTAs, many in flight */
+            if (g.mask && cell_bits >= lb && (nc >> g.ms) >= 32 && ((ncell >> cbt) >> lb) * ((nc >> g.ms) >> 5) <= 128 &&
+                !(L == 0 && !g.indexed) && !getenv("SOGPU_DENSE_BUCKETS")) {
+                /* focused grid: per-bucket work proportional to its marked cells (k_bucket_sort_sparse) */
+                grid = (int)std::min<int64_t>((int64_t)nb, (int64_t)h->sm_count * 8);
+                k_bucket_sort_sparse<<<grid, BS_NT, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, live, live_n);
+            } else if (n_work / (int64_t)nb < 160 && nb >= 4096u) {      /* sparse buckets: small CTAs, many in flight */
                 grid = (int)std::min<int64_t>((int64_t)nb, (int64_t)h->sm_count * 48);
                 k_bucket_sort_rt<64, 12><<<grid, 64, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce,
                                                              (L == 0 && !g.indexed) ? 1 : 0, live, live_n);
@@ -3169,6 +3303,21 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
     h->launch_stream = s;
     a.list = h->d_huge; a.list_n = h->d_counters + 13; a.work_counter = h->d_counters + 14; a.tl_slot = 0;
     { ProfScope p(h, KID_QUERY_HUGE); launch_persistent<1024>(h, k_so_query<1024>, a, std::min(nh, h->sm_count)); }
+    if (h->fused_query) {
+        /* the two common classes in one persistent kernel (see k_so_query_fused), then the few halos a warp deferred */
+        h->launch_stream = h->aux[0];
+        a.list = h->d_big; a.list_n = h->d_counters + 1; a.work_counter = h->d_counters + 3;
+        a.list2 = h->d_small; a.list2_n = h->d_counters + 0; a.work_counter2 = h->d_counters + 2;
+        {
+            ProfScope p(h, KID_QUERY_FUSED);
+            const int ctas = std::max(1, std::min(h->sm_count * QF_MINB, (nh + 7) / 8 + h->sm_count));
+            k_so_query_fused<<<ctas, 256, fused_smem_bytes(), h->aux[0]>>>(a);
+        }
+        a.list = h->d_defer; a.list_n = h->d_counters + 17; a.work_counter = h->d_counters + 18; a.tl_slot = 3;
+        { ProfScope p(h, KID_QUERY_BLOCK); launch_persistent<256>(h, k_so_query<256>, a, 64); }
+        CU(cudaEventRecord(h->ev_join[0], h->aux[0]));
+        CU(cudaEventRecord(h->ev_join[1], h->aux[1]));
+    } else
     for (int pass = 0; pass < 2; ++pass) {
         const bool big_now = (pass == 0) == (h->qorder == 0);
         if (big_now) {      /* mid-size halos: one 256-thread CTA each */
