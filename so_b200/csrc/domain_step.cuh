@@ -161,7 +161,8 @@ __device__ __forceinline__ void bit_run(uint32_t *map, uint32_t b0, uint32_t len
     }
 }
 
-/* One warp per halo: the cube it can reach after n_balls steps of the ball schedule (same rule as k_mark_mask).
+#define MARK_LANES 8
+/* A group of lanes per halo: the cube it can reach after n_balls steps of the ball schedule (same rule as k_mark_mask).
  * Sets the owner's bit in the destination table, the "somebody wants this cell" bitmap, its 64^3 pre-filter and
  * (own halos) this rank's focus mask.  A lane takes a whole x-row of the cube: consecutive cells are consecutive
  * bits / table entries, so a row is a handful of word-wide reductions with nothing to wait for.
@@ -173,8 +174,13 @@ __global__ void __launch_bounds__(256) k_mark_table(GridDev g, const float *__re
                                                     uint32_t *__restrict__ table32, uint32_t *__restrict__ any,
                                                     uint32_t *__restrict__ super, uint32_t *__restrict__ mymask, int clear)
 {
-    const int lane = threadIdx.x & 31;
-    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    /* clear = 1: only the destination table is un-marked (the bitmaps are small enough to be cleared by a
+     * memset every step; the table — 2 bytes per coarse cell — is not).  A NULL array is skipped: a single rank
+     * needs neither the table nor a second bitmap. */
+    /* MARK_LANES lanes per halo: the typical cube has 9-25 rows, and with a whole warp per halo the kernel was
+     * bound by the number of halos in flight (100 000 halos: 90 us) */
+    const int lane = threadIdx.x & (MARK_LANES - 1);
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) / MARK_LANES, nw = (gridDim.x * blockDim.x) / MARK_LANES;
     const float root = so_root_period(g.L[0], g.L[1], g.L[2]);
     const int nm = 1 << g.mb, nm1 = nm - 1;
     const int sb = min(g.mb, DOM_SUPER_LOG), ss = g.mb - sb;
@@ -191,16 +197,29 @@ __global__ void __launch_bounds__(256) k_mark_table(GridDev g, const float *__re
         const uint32_t ob = (1u << own) * 0x00010001u;             /* the owner's bit in both halves of a table word */
         const int xa = x0 & nm1;                                   /* the row's x-range, split where it wraps */
         const int n0 = min(nx, nm - xa), n1 = nx - n0;
-        for (int r = lane; r < ny * nz; r += 32) {
+        if (!clear) {
+            /* the 64^3 pre-filter once per halo (not per row): the cube covers a handful of its cells */
+            const int sx0 = x0 >> ss, sx1 = (x0 + nx - 1) >> ss, sy0 = y0 >> ss, sy1 = (y0 + ny - 1) >> ss;
+            const int sz0 = z0 >> ss, sz1 = (z0 + nz - 1) >> ss, snx = sx1 - sx0 + 1, sny = sy1 - sy0 + 1, snz = sz1 - sz0 + 1;
+            const int sm1 = (1 << sb) - 1;
+            for (int i = lane; i < snx * sny * snz; i += MARK_LANES) {
+                const uint32_t cx = (uint32_t)((sx0 + i % snx) & sm1), cy = (uint32_t)((sy0 + (i / snx) % sny) & sm1),
+                               cz = (uint32_t)((sz0 + i / (snx * sny)) & sm1);
+                const uint32_t sbit = (cz << (2 * sb)) | (cy << sb) | cx;
+                atomicOr(&super[sbit >> 5], 1u << (sbit & 31));
+            }
+        }
+        for (int r = lane; r < ny * nz; r += MARK_LANES) {
             const uint32_t cy = (uint32_t)((y0 + r % ny) & nm1), cz = (uint32_t)((z0 + r / ny) & nm1);
             const uint32_t row = (cz << (2 * g.mb)) | (cy << g.mb);
-            const uint32_t srow = ((cz >> ss) << (2 * sb)) | ((cy >> ss) << sb);
             for (int piece = 0; piece < 2; ++piece) {
                 const int px = piece ? 0 : xa, pn = piece ? n1 : n0;
                 if (pn <= 0) continue;
-                bit_run(any, row + (uint32_t)px, (uint32_t)pn, clear);
-                if (own == me) bit_run(mymask, row + (uint32_t)px, (uint32_t)pn, clear);
-                bit_run(super, srow + ((uint32_t)px >> ss), (((uint32_t)(px + pn - 1)) >> ss) - ((uint32_t)px >> ss) + 1u, clear);
+                if (!clear) {
+                    if (any) bit_run(any, row + (uint32_t)px, (uint32_t)pn, 0);
+                    if (own == me) bit_run(mymask, row + (uint32_t)px, (uint32_t)pn, 0);
+                }
+                if (!table32) continue;
                 /* table: 16-bit entries, two per word */
                 uint32_t c = row + (uint32_t)px, e = c + (uint32_t)pn;
                 while (c < e) {
@@ -311,6 +330,10 @@ __global__ void __launch_bounds__(RT_THREADS, 2) k_route_stage(const __grid_cons
             const uint32_t i = i0 + u * 32u;
             q[u] = ld_stream(a.slice + (i < n ? i : n - 1u));
         }
+        /* the lookups of the RT_U particles are issued level by level, so that a level's loads are all in flight
+         * together: 64^3 pre-filter (shared memory), "somebody wants it" bitmap (L2), destination set (the few
+         * particles that pass both; a 16-bit gather from a table far larger than the L2) */
+        uint32_t bit[RT_U], set[RT_U];
 #pragma unroll
         for (int u = 0; u < RT_U; ++u) {
             const uint32_t i = i0 + u * 32u;
@@ -318,22 +341,32 @@ __global__ void __launch_bounds__(RT_THREADS, 2) k_route_stage(const __grid_cons
             const uint32_t cx = cell_coord(q[u].x, g0x, ihx, mask) >> ms;
             const uint32_t cy = cell_coord(q[u].y, g0y, ihy, mask) >> ms;
             const uint32_t cz = cell_coord(q[u].z, g0z, ihz, mask) >> ms;
-            /* three lookups, cheapest first: 64^3 pre-filter (shared memory), "somebody wants it" bitmap (L2),
-             * destination set (only for the few particles that pass both) */
             const uint32_t sbit = (cz >> ss) * T2 + (cy >> ss) * T1 + (cx >> ss);
-            uint32_t set = 0u;
-            if (i < n && ((s_super[sbit >> 5] >> (sbit & 31)) & 1u)) {
-                const uint32_t bit = cz * S2 + cy * S1 + cx;
-                if ((__ldg(a.any + (bit >> 5)) >> (bit & 31)) & 1u) set = R > 1 ? (uint32_t)__ldg(a.table + bit) : 1u;
-            }
-            uint32_t wset = __reduce_or_sync(0xFFFFFFFFu, set);
+            bit[u] = cz * S2 + cy * S1 + cx;
+            set[u] = (i < n && ((s_super[sbit >> 5] >> (sbit & 31)) & 1u)) ? 1u : 0u;
+        }
+        uint32_t anyw[RT_U];
+#pragma unroll
+        for (int u = 0; u < RT_U; ++u) anyw[u] = set[u] ? __ldg(a.any + (bit[u] >> 5)) : 0u;
+#pragma unroll
+        for (int u = 0; u < RT_U; ++u) set[u] = (anyw[u] >> (bit[u] & 31)) & 1u;
+        if (R > 1) {
+            unsigned short tb[RT_U];
+#pragma unroll
+            for (int u = 0; u < RT_U; ++u) tb[u] = set[u] ? __ldg(a.table + bit[u]) : (unsigned short)0;
+#pragma unroll
+            for (int u = 0; u < RT_U; ++u) set[u] = tb[u];
+        }
+#pragma unroll
+        for (int u = 0; u < RT_U; ++u) {
+            uint32_t wset = __reduce_or_sync(0xFFFFFFFFu, set[u]);
             if (!wset) continue;
-            q[u].w = __uint_as_float(a.index_base + i);
+            q[u].w = __uint_as_float(a.index_base + i0 + u * 32u);
             for (; wset; wset &= wset - 1u) {
                 const int d = __ffs(wset) - 1;
                 if (wcnt + 32u > RW_CAP) flush();
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, (set >> d) & 1u);
-                if ((set >> d) & 1u) {
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, (set[u] >> d) & 1u);
+                if ((set[u] >> d) & 1u) {
                     const uint32_t pos = wcnt + __popc(m & lt);
                     wbuf[pos] = q[u];
                     wdst[pos] = (unsigned char)d;
@@ -559,12 +592,18 @@ extern "C" int sogpu_domain_begin(sogpu_t *h, const void *d_centers, const void 
     }
     GridDev g;
     dom_geometry(h, g);
-    if (D->marked) {      /* un-mark the previous catalog (still in h->d_centers / d_rgtp / d_owner): the tables are clean again */
+    if (D->marked && R > 1) {      /* un-mark the previous catalog (still in h->d_centers / d_rgtp / d_owner) in the destination table */
         ProfScope p(h, KID_MARK_MASK);
-        k_mark_table<<<std::min((D->marked_nh + 7) / 8, h->sm_count * 8), 256, 0, s>>>(
+        k_mark_table<<<std::min((D->marked_nh * MARK_LANES + 255) / 256, h->sm_count * 8), 256, 0, s>>>(
             g, h->d_centers, h->d_rgtp, D->marked_nh, D->marked_balls, D->d_owner, me, (uint32_t *)D->d_table, D->d_any,
             D->d_super, D->d_mymask, 1);
-        D->marked = false;
+    }
+    D->marked = false;
+    {   /* the bitmaps: 2 x 2^(3 mb) bits + the 64^3 pre-filter — a few to 32 MB, microseconds */
+        const size_t words = ((size_t)1 << (3 * g.mb)) / 32 + 1, swords = ((size_t)1 << (3 * std::min(g.mb, DOM_SUPER_LOG))) / 32 + 1;
+        if (R > 1) CU(cudaMemsetAsync(D->d_any, 0, words * sizeof(uint32_t), s));
+        CU(cudaMemsetAsync(D->d_mymask, 0, words * sizeof(uint32_t), s));
+        CU(cudaMemsetAsync(D->d_super, 0, swords * sizeof(uint32_t), s));
     }
     if (d_centers != h->d_centers)
         CU(cudaMemcpyAsync(h->d_centers, d_centers, (size_t)nh * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -595,8 +634,9 @@ extern "C" int sogpu_domain_begin(sogpu_t *h, const void *d_centers, const void 
     }
     {
         ProfScope p(h, KID_MARK_MASK);
-        k_mark_table<<<std::min((nh + 7) / 8, h->sm_count * 8), 256, 0, s>>>(g, h->d_centers, h->d_rgtp, nh, n_balls, D->d_owner, me,
-                                                                             (uint32_t *)D->d_table, D->d_any, D->d_super, D->d_mymask, 0);
+        k_mark_table<<<std::min((nh * MARK_LANES + 255) / 256, h->sm_count * 8), 256, 0, s>>>(
+            g, h->d_centers, h->d_rgtp, nh, n_balls, D->d_owner, me, R > 1 ? (uint32_t *)D->d_table : nullptr,
+            R > 1 ? D->d_any : nullptr, D->d_super, D->d_mymask, 0);
         D->marked = true; D->marked_balls = n_balls; D->marked_nh = nh;
     }
     CU(cudaGetLastError());
@@ -613,7 +653,7 @@ static int dom_stage_args(sogpu *h, StageArgs &a, const void *d_chunk, int64_t n
     memset(&a, 0, sizeof(a));
     dom_geometry(h, a.g);
     a.slice = (const float4 *)d_chunk; a.n = n; a.index_base = (uint32_t)index_base;
-    a.table = D->d_table; a.any = D->d_any; a.super = D->d_super; a.R = D->cfg.n_ranks;
+    a.table = D->d_table; a.any = D->cfg.n_ranks > 1 ? D->d_any : D->d_mymask; a.super = D->d_super; a.R = D->cfg.n_ranks;
     a.flags = D->d_flags;
     for (int d = 0; d < a.R; ++d) {
         if (d == D->cfg.rank) {

@@ -896,7 +896,6 @@ __global__ void __launch_bounds__(BS_NT, 8) k_bucket_sort_sparse(const float4 *_
     __shared__ uint32_t mw[128], mpre[129];
     __shared__ uint32_t cnt[BKT_CELLS + 1];
     __shared__ uint32_t ws[BS_NT / 32 + 1];
-    __shared__ uint32_t carry_s;
     const int ncells = 1 << cell_bits;
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int nrow = ncells >> g.lb;                         /* fine rows of a bucket (host: cell_bits >= lb) */
@@ -970,29 +969,36 @@ __global__ void __launch_bounds__(BS_NT, 8) k_bucket_sort_sparse(const float4 *_
             }
         }
         __syncthreads();
-        /* exclusive scan over the compact cells, BS_NT at a time; cnt[ncomp] = particles of the bucket */
-        if (t == 0) carry_s = 0u;
-        __syncthreads();
-        for (uint32_t base = 0; base < ncomp; base += BS_NT) {
-            const uint32_t i = base + t;
-            const uint32_t v = i < ncomp ? cnt[i] : 0u;
-            uint32_t x = v;
+        /* exclusive scan over the compact cells: every warp scans its quarter 32 cells at a time with a running
+         * carry (no block barrier inside), the warps' totals are added by the readers; cnt[ncomp] = particles */
+        {
+            const uint32_t Q = ((ncomp + (BS_NT / 32) - 1) / (BS_NT / 32) + 31u) & ~31u;      /* cells per warp */
+            const uint32_t lo = (uint32_t)w * Q, hi = min(ncomp, lo + Q);
+            uint32_t carry = 0;
+            for (uint32_t base = lo; base < hi; base += 32) {
+                const uint32_t i = base + lane;
+                const uint32_t v = i < hi ? cnt[i] : 0u;
+                uint32_t x = v;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t u = __shfl_up_sync(0xFFFFFFFFu, x, o);
-                if (lane >= o) x += u;
+                for (int o = 1; o < 32; o <<= 1) {
+                    uint32_t u = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                    if (lane >= o) x += u;
+                }
+                if (i < hi) cnt[i] = carry + x - v;
+                carry += __shfl_sync(0xFFFFFFFFu, x, 31);
             }
-            if (lane == 31) ws[w] = x;
+            if (lane == 0) ws[w] = carry;
             __syncthreads();
-            uint32_t off = carry_s;
+            uint32_t off = 0;
 #pragma unroll
             for (int k = 0; k < BS_NT / 32; ++k) off += (k < w) ? ws[k] : 0u;
-            if (i < ncomp) cnt[i] = off + x - v;
-            __syncthreads();
-            if (t == BS_NT - 1) carry_s = off + x;
-            __syncthreads();
+            if (off) for (uint32_t i = lo + lane; i < hi; i += 32) cnt[i] += off;
+            if (t == 0) {
+                uint32_t tot = 0;
+                for (int k = 0; k < BS_NT / 32; ++k) tot += ws[k];
+                cnt[ncomp] = tot;
+            }
         }
-        if (t == 0) cnt[ncomp] = carry_s;
         __syncthreads();
         /* particles to their final slots */
         if (in_regs) {

@@ -2487,7 +2487,7 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     h->mask_rmin_cells = 0.75;
     h->mask_bits = 9;
     if (const char *e = getenv("SOGPU_MASK_BITS")) h->mask_bits = std::min(9, std::max(4, atoi(e)));
-    h->scan1_max = (size_t)1 << 18;
+    h->scan1_max = (size_t)1 << 15;          /* (one block scans 2^18 entries in ~80 us, three small launches in ~15) */
     h->qgrid32 = 3; h->qgrid256 = 2; h->qorder = 0;    /* persistent grids of exactly the CTAs that can be resident (pending CTAs of one class hold back the next kernel's) */
     if (const char *e = getenv("SOGPU_QGRID32")) h->qgrid32 = std::max(1, atoi(e));
     if (const char *e = getenv("SOGPU_QGRID256")) h->qgrid256 = std::max(1, atoi(e));
@@ -2921,7 +2921,10 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
     if (cbt < keybits - 12) cbt = keybits - 12;
     if (cbt > keybits) cbt = keybits;
     const int cell_bits = keybits - cbt;
-    const int L = (cbt + 7) / 8;                       /* partition levels, digits of <= 8 bits */
+    int lvl_bits = (focus_nh != 0) ? 9 : 8;            /* partition levels, digits of <= 8 bits; sparse (focused) inputs: 9,
+                                                        * one pass fewer over few particles (measured at 1024^3: -2.5 %) */
+    if (const char *e = getenv("SOGPU_LEVEL_BITS")) lvl_bits = std::min(9, std::max(4, atoi(e)));
+    const int L = (cbt + lvl_bits - 1) / lvl_bits;
     if (L > 4) return set_err(SOGPU_ERR_UNSUPPORTED, "too many partition levels");
     if (!h->d_ce || h->nc != nc) {
         cudaFree(h->d_ce); h->d_ce = nullptr;
