@@ -440,7 +440,9 @@ def run_ours(args):
     t_setup = time.time() - t_setup
 
     g = api.SoGpu(device=local, stream=stream.cuda_stream)
-    ds = parallel.DomainStep(g, n, mass)
+    frac = 0.9 if args.config == 4 else 0.30          # share of the snapshot the receive buffers are sized for
+    rc_, sc_ = parallel.default_caps(n, world, frac)
+    ds = parallel.DomainStep(g, n, mass, recv_cap=rc_, stage_cap=sc_)
     d_out_n = torch.empty(h, dtype=torch.int32, device=dev)
     d_out_m = torch.empty(h, dtype=torch.float32, device=dev)
 

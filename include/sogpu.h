@@ -186,6 +186,17 @@ int sogpu_vcirc(sogpu_t *h, const float *centers, const float *rvir, const float
                 float G, int32_t nMembers, float *vcirc, float *rmass, float *rmax, float *vmax,
                 float *profile);
 
+/* The same for ANY particle masses and several species (gas + dark + star, -mark): the cumulative mass is the
+ * reference's sequential fp32 sum over the sorted list, evaluated literally on the device (one warp per group).
+ * ptype (host, N bytes, may be NULL = every particle counts everywhere): species bits of each particle;
+ * masks[k] (k < nmasks <= 4): the particles with (ptype & masks[k]) != 0 count for profile k, as kdMassProfile's
+ * per-species sums do (kd2.c:458-496); profiles: nmasks x nh x 16 floats, profile k of group i at
+ * (k * nh + i) * 16.  Ties in r^2 between particles of different mass are ordered by particle index (the
+ * reference orders them by its kd-tree walk: out of contract). */
+int sogpu_vcirc_species(sogpu_t *h, const float *centers, const float *rvir, const float *mvir, int32_t nh,
+                        float G, int32_t nMembers, const unsigned char *ptype, const int32_t *masks,
+                        int32_t nmasks, float *vcirc, float *rmass, float *rmax, float *vmax, float *profiles);
+
 /* ---- _VcmParticles replacement (kd2.c:595-609) -------------------------------------------------- */
 
 /* Centre-of-mass velocity of every group of the last sogpu_so() call (same nh, sogpu_keep_member_d2 on):
@@ -204,6 +215,21 @@ int sogpu_vcm(sogpu_t *h, const float *mvir, int32_t nh, float *vcm);
  * that replay).  igrp (host, N ints, may be NULL) receives the per-particle tags (PINIT.iGrp). */
 int sogpu_tag_members(sogpu_t *h, const int32_t *index, int32_t nh, unsigned char *in_conflict,
                       int32_t *igrp);
+
+/* ---- kdTagParticles, the order-dependent part (kd2.c:663-720, kdZeroGroup 617-643) ------------------------ */
+
+/* Replays kdTagParticles on the device for the groups that sogpu_tag_members reported in conflict, in the
+ * caller's processing order (the reference's: ascending catalog mass, kd2.c:873-879):
+ *   order[n_order]   slots (0..nh-1) of the groups to replay — those with in_conflict set and rvir > 0
+ *   index, centers   catalog id (GRPNODE.index, 1..max_index) and position of every slot
+ *   rvir, mvir       in: kdRvir's results; out: with the subsume / slurp marks (-10 * index, -Mvir; kd2.c:633-634)
+ *   igrp, nsubsumed, nignored   (host, N ints, any may be NULL) PINIT.iGrp / nSubsumed / nIgnored of every particle
+ *   still_valid[nh]  1 if the group's radius was still positive right after its own pass (kd2.c:884: kdVcirc runs)
+ * Requires the sorted member lists of the last sogpu_so call (sogpu_members(.., sorted = 1)) and a preceding
+ * sogpu_tag_members over the same groups. */
+int sogpu_tag_replay(sogpu_t *h, const int32_t *order, int32_t n_order, const int32_t *index, const float *centers,
+                     float *rvir, float *mvir, int32_t nh, int32_t max_index, int32_t *igrp, int32_t *nsubsumed,
+                     int32_t *nignored, int32_t *groups_removed, int32_t *groups_slurped, unsigned char *still_valid);
 
 /* ---- several GPUs: domain runs ----------------------------------------- */
 

@@ -297,3 +297,36 @@ def run_so_ref_timed(snap_path, gtp_path, thr, n_members=8, period=1.0, out_base
     if r.returncode != 0:
         raise RuntimeError("so_ref_timed failed rc=%d\n%s" % (r.returncode, r.stderr[-2000:]))
     return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+# ---- the reference's default threshold (so.c:57-86, 470-481): restated here as test infrastructure ----------
+
+def virial_threshold(omega0, flat_lambda, time=None, z=None):
+    """fThreshold exactly as so.c computes it when no -delta is given: Kitayama & Suto (1996) virial overdensity
+    (so.c:57-86) times Omega0 (so.c:478), with z = 1/h.time - 1 from the snapshot header unless -z sets it
+    (so.c:470-472).  fOmega, fRedshift, kd->fTime and fThreshold are floats in the reference (so.c:200, kd2.h:119);
+    the formula itself runs in double."""
+    import math
+    f_omega = np.float32(omega0)
+    if z is None:
+        f_time = np.float32(time)
+        z = np.float32(1.0 / float(f_time) - 1.0)             # (1.0/kd->fTime)-1.0 in double, stored in a float
+    else:
+        z = np.float32(z)
+    om, zz = float(f_omega), float(z)
+
+    def omegaf(omega, lam, zv):                               # so.c:57-66
+        zp2 = (1.0 + zv) * (1.0 + zv)
+        zp3 = zp2 * (1.0 + zv)
+        return omega * zp3 / (omega * zp3 + (1.0 - omega - lam) * zp2 + lam)
+
+    if om == 1.0:
+        ratio = 178.0
+    elif flat_lambda:
+        wf = 1.0 / omegaf(om, 1.0 - om, zz) - 1.0
+        ratio = 18.0 * (math.pi * math.pi) * (1.0 + 0.4093 * math.pow(wf, 0.9052))
+    else:
+        etaf = math.acosh(2.0 / omegaf(om, 0.0, zz) - 1.0)
+        ratio = 4.0 * (math.pi * math.pi) / math.pow(math.sinh(etaf) - etaf, 2)
+        ratio *= math.pow(math.cosh(etaf) - 1.0, 3)
+    return np.float32(ratio * om)                             # double product, stored in a float

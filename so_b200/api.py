@@ -33,7 +33,7 @@ SYMBOLS = [
     "sogpu_peer_alloc", "sogpu_peer_open", "sogpu_peer_close", "sogpu_peer_free",
     "sogpu_domain_open", "sogpu_domain_connect", "sogpu_enable_peer_access", "sogpu_domain_begin",
     "sogpu_domain_route", "sogpu_domain_route_host", "sogpu_domain_push", "sogpu_domain_solve",
-    "sogpu_domain_result", "sogpu_domain_close", "sogpu_domain_pointers",
+    "sogpu_domain_result", "sogpu_domain_close", "sogpu_domain_pointers", "sogpu_vcirc_species", "sogpu_tag_replay",
 ]
 
 
@@ -76,6 +76,12 @@ def lib():
     L.sogpu_set_cell_occupancy.argtypes = [vp, C.c_float]
     L.sogpu_vcirc.argtypes = [vp, fp, fp, fp, C.c_int32, C.c_float, C.c_int32, fp, fp, fp, fp, fp]
     L.sogpu_vcirc.restype = C.c_int
+    L.sogpu_vcirc_species.argtypes = [vp, fp, fp, fp, C.c_int32, C.c_float, C.c_int32, C.POINTER(C.c_ubyte), i32p, C.c_int32,
+                                      fp, fp, fp, fp, fp]
+    L.sogpu_vcirc_species.restype = C.c_int
+    L.sogpu_tag_replay.argtypes = [vp, i32p, C.c_int32, i32p, fp, fp, fp, C.c_int32, C.c_int32, i32p, i32p, i32p, i32p, i32p,
+                                   C.POINTER(C.c_ubyte)]
+    L.sogpu_tag_replay.restype = C.c_int
     L.sogpu_tag_members.argtypes = [vp, i32p, C.c_int32, C.POINTER(C.c_ubyte), i32p]
     L.sogpu_tag_members.restype = C.c_int
     L.sogpu_vcm.argtypes = [vp, fp, C.c_int32, fp]
@@ -417,6 +423,26 @@ class SoGpu:
         self._last_h = h
         return out
 
+    def vcirc_species(self, centers, rvir, mvir, ptype=None, masks=(), G=1.0, n_members=8):
+        """kdVcirc / kdMassProfile for any particle masses and several species: ptype = species bits per particle
+        (uint8[N]), masks = up to 4 bit masks, one mass profile each.  profiles: (len(masks), h, 16)."""
+        centers = np.ascontiguousarray(centers, np.float32).reshape(-1, 3)
+        rvir = np.ascontiguousarray(rvir, np.float32)
+        mvir = np.ascontiguousarray(mvir, np.float32)
+        h, nm = len(rvir), len(masks)
+        out = {"vcirc": np.zeros((h, 8), np.float32), "rmass": np.zeros((h, 2), np.float32),
+               "rmax": np.zeros(h, np.float32), "vmax": np.zeros(h, np.float32),
+               "profiles": np.zeros((max(nm, 1), h, 16), np.float32)}
+        pt = np.ascontiguousarray(ptype, np.uint8) if ptype is not None else None
+        mk = np.ascontiguousarray(masks, np.int32) if nm else None
+        _check(lib().sogpu_vcirc_species(self._h, _fp(centers), _fp(rvir), _fp(mvir), h, C.c_float(G), int(n_members),
+                                         pt.ctypes.data_as(C.POINTER(C.c_ubyte)) if pt is not None else None,
+                                         mk.ctypes.data_as(C.POINTER(C.c_int32)) if nm else None, nm,
+                                         _fp(out["vcirc"]), _fp(out["rmass"]), _fp(out["rmax"]), _fp(out["vmax"]),
+                                         _fp(out["profiles"]) if nm else None))
+        self._last_h = h
+        return out
+
     def vcm(self, mvir):
         """_VcmParticles of the last so() call (velocities kept by ingest_records(keep_velocities=True))."""
         mvir = np.ascontiguousarray(mvir, np.float32)
@@ -556,6 +582,25 @@ class SoGpu:
                                        dirty.ctypes.data_as(C.POINTER(C.c_ubyte)),
                                        igrp.ctypes.data_as(C.POINTER(C.c_int32)) if igrp is not None else None))
         return dirty.astype(bool), igrp
+
+    def tag_replay(self, order, index, centers, rvir, mvir, n_particles):
+        """Ordered replay of kdTagParticles for the groups in conflict, on the device (after members(sorted=True)
+        and tag_members).  Returns dict(rvir, mvir, igrp, nsub, nign, groups_removed, groups_slurped, still_valid)."""
+        order = np.ascontiguousarray(order, np.int32)
+        index = np.ascontiguousarray(index, np.int32)
+        centers = np.ascontiguousarray(centers, np.float32).reshape(-1, 3)
+        rv = np.array(rvir, np.float32, copy=True)
+        mv = np.array(mvir, np.float32, copy=True)
+        nh = len(index)
+        igrp, nsub, nign = (np.zeros(int(n_particles), np.int32) for _ in range(3))
+        rem, slu = C.c_int32(), C.c_int32()
+        valid = np.zeros(nh, np.uint8)
+        ip = lambda x: x.ctypes.data_as(C.POINTER(C.c_int32))
+        _check(lib().sogpu_tag_replay(self._h, ip(order), len(order), ip(index), _fp(centers), _fp(rv), _fp(mv), nh,
+                                      int(index.max()), ip(igrp), ip(nsub), ip(nign), C.byref(rem), C.byref(slu),
+                                      valid.ctypes.data_as(C.POINTER(C.c_ubyte))))
+        return dict(rvir=rv, mvir=mv, igrp=igrp, nsub=nsub, nign=nign, groups_removed=int(rem.value),
+                    groups_slurped=int(slu.value), still_valid=valid.astype(bool))
 
     def stats(self):
         s = Stats()

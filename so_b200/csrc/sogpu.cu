@@ -20,7 +20,6 @@
 #include "so_math.h"
 
 #include <cuda_runtime.h>
-#include <cub/device/device_segmented_sort.cuh>
 
 #include <algorithm>
 #include <climits>
@@ -831,6 +830,8 @@ template <int NT> __device__ __forceinline__ void bitonic_sort(unsigned long lon
         }
     }
 }
+
+#include "seg_sort.cuh"
 
 /* ============================================================================================
  * focused grid: only the coarse cells some halo can ever look at are kept by the build
@@ -1760,7 +1761,8 @@ __global__ void __launch_bounds__(256) k_gen_count(const __grid_constant__ GenAr
 /* exclusive scan of the per-slot counts of slots [s0, s1) (one block) */
 __global__ void __launch_bounds__(1024) k_gen_offsets(const unsigned long long *__restrict__ seg_n, uint32_t s0,
                                                       uint32_t s1, unsigned long long *__restrict__ seg_begin,
-                                                      unsigned long long *__restrict__ seg_end)
+                                                      unsigned long long *__restrict__ seg_end,
+                                                      unsigned long long *__restrict__ csr)
 {
     __shared__ unsigned long long ws[32];
     __shared__ unsigned long long carry;
@@ -1786,11 +1788,21 @@ __global__ void __launch_bounds__(1024) k_gen_offsets(const unsigned long long *
         }
         __syncthreads();
         unsigned long long incl = x + (w ? ws[w - 1] : 0ull) + carry;
-        if (i < s1) { seg_begin[i] = incl - v; seg_end[i] = incl; }
+        if (i < s1) { seg_begin[i] = incl - v; seg_end[i] = incl; csr[i - s0] = incl - v; }
         __syncthreads();
         if (threadIdx.x == 1023) carry = incl;
         __syncthreads();
     }
+    if (threadIdx.x == 0) csr[s1 - s0] = carry;
+}
+
+/* masses in the order of the sorted keys (the key's low half is the particle index) */
+__global__ void __launch_bounds__(256) k_gen_mass(const unsigned long long *__restrict__ keys, unsigned long long n,
+                                                  const float4 *__restrict__ in, float *__restrict__ mass)
+{
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        mass[i] = __ldg(&in[(uint32_t)keys[i]].w);
 }
 
 /* write (key, mass) of every particle of the ball into the halo's scratch segment */
@@ -2033,6 +2045,156 @@ __global__ void __launch_bounds__(256) k_vcirc(const __grid_constant__ VcircArgs
     }
 }
 
+/* ---- kdVcirc / kdMassProfile for ANY masses and several species (kd2.c:458-496, 498-586) ----------------
+ * With unequal masses the cumulative mass after k sorted particles is a sequential fp32 sum that depends on
+ * which particle sits at which rank; k_vc_prefix evaluates it literally — one warp per group walks the sorted
+ * 2 Rvir list 32 entries at a time, the adds replicated serially on every lane (they cannot be reassociated) —
+ * for all particles and for up to four species masks (kdMassProfile's per-species sums, each its own sequential
+ * chain).  Every output of kdVcirc is then a rank query on those prefix arrays (k_vcirc_gen). */
+#define VC_MAXMASK 4
+__global__ void __launch_bounds__(256) k_vc_prefix(const unsigned long long *__restrict__ off, const int32_t *__restrict__ idx,
+                                                   int nh, const float4 *__restrict__ in, const unsigned char *__restrict__ ptype,
+                                                   int nmask, uint32_t masks4, unsigned long long stride, float *__restrict__ C)
+{
+    const int lane = threadIdx.x & 31;
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int h = wid; h < nh; h += nw) {
+        const unsigned long long a = off[h];
+        const uint32_t n = (uint32_t)(off[h + 1] - a);
+        float S[1 + VC_MAXMASK];
+#pragma unroll
+        for (int k = 0; k <= VC_MAXMASK; ++k) S[k] = 0.0f;
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t e = base + lane;
+            float m_l = 0.0f;
+            uint32_t t_l = 0u;
+            if (e < n) {
+                const int32_t p = __ldg(idx + a + e);
+                m_l = __ldg(&in[p].w);
+                t_l = ptype ? (uint32_t)__ldg(ptype + p) : 0xFFu;
+            }
+            float mine[1 + VC_MAXMASK];
+#pragma unroll
+            for (int k = 0; k <= VC_MAXMASK; ++k) mine[k] = 0.0f;
+            for (int t = 0; t < 32; ++t) {
+                const float mt = __shfl_sync(0xFFFFFFFFu, m_l, t);      /* (padding entries add +0.0f: exact) */
+                const uint32_t tt = __shfl_sync(0xFFFFFFFFu, t_l, t);
+                S[0] = __fadd_rn(S[0], mt);
+#pragma unroll
+                for (int k = 0; k < VC_MAXMASK; ++k)
+                    if (k < nmask && (tt & ((masks4 >> (8 * k)) & 0xFFu))) S[1 + k] = __fadd_rn(S[1 + k], mt);
+                if (t == lane) {
+#pragma unroll
+                    for (int k = 0; k <= VC_MAXMASK; ++k) mine[k] = S[k];
+                }
+            }
+            if (e < n) {
+                C[a + e] = mine[0];
+#pragma unroll
+                for (int k = 0; k < VC_MAXMASK; ++k)
+                    if (k < nmask) C[(unsigned long long)(1 + k) * stride + a + e] = mine[1 + k];
+            }
+        }
+    }
+}
+
+struct VcircGenArgs {
+    const float *d2;                      /* sorted r^2 of all lists, CSR */
+    const unsigned long long *off;        /* nh + 1 */
+    const float *C;                       /* (1 + nmask) x stride inclusive prefixes */
+    unsigned long long stride;
+    const float *rvir, *mvir;
+    float G;
+    int nM, nh, nmask;
+    float *vcirc, *rmass, *rmax, *vmax, *profiles;   /* 8, 2, 1, 1 per group; profiles: nmask x nh x 16 */
+};
+
+__global__ void __launch_bounds__(256) k_vcirc_gen(const __grid_constant__ VcircGenArgs a)
+{
+    __shared__ float s_v[8];
+    __shared__ uint32_t s_j[8];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    for (int h = blockIdx.x; h < a.nh; h += gridDim.x) {
+        const unsigned long long o = a.off[h];
+        const uint32_t n = (uint32_t)(a.off[h + 1] - o);
+        const float *d2 = a.d2 + o;
+        const float *C = a.C + o;
+        const float rvir = a.rvir[h], mvir = a.mvir[h];
+        auto massk = [&](const float *P, uint32_t k) -> float { return k ? __ldg(P + k - 1u) : 0.0f; };   /* mass of the first k */
+        if (n == 0) {
+            if (t < SO_NVCIRC) a.vcirc[(size_t)h * SO_NVCIRC + t] = 0.0f;
+            if (t < 2) a.rmass[(size_t)h * 2 + t] = 0.0f;
+            if (t == 0) { a.rmax[h] = 0.0f; a.vmax[h] = 0.0f; }
+            for (int k = 0; k < a.nmask; ++k)
+                if (t < SO_NMASSPROFILE) a.profiles[((size_t)k * a.nh + h) * SO_NMASSPROFILE + t] = 0.0f;
+            continue;
+        }
+        if (t < SO_NVCIRC) {                       /* kd2.c:517-531 */
+            const float fmin = (float)(2.0 / SO_NVCIRC);
+            float f = fmin;
+            for (int i = 0; i < t; ++i) f = __fadd_rn(f, fmin);
+            float v;
+            if (t < SO_NVCIRC - 1) {
+                const float r = __fmul_rn(f, rvir), r2 = __fmul_rn(r, r);
+                v = __fsqrt_rn(__fdiv_rn(__fmul_rn(a.G, massk(C, lower_bound_f(d2, n, r2))), r));
+            } else {
+                const float fBall = 2.0f * rvir;
+                v = __fsqrt_rn(__fdiv_rn(__fmul_rn(a.G, massk(C, n)), fBall));
+            }
+            a.vcirc[(size_t)h * SO_NVCIRC + t] = v;
+        } else if (t >= 32 && t < 32 + 2) {        /* kd2.c:537-546: first j whose cumulative mass reaches f * Mvir */
+            const int i = t - 32;
+            const float f = i ? 0.5f : 0.25f, m = __fmul_rn(f, mvir);
+            uint32_t lo = 0, hi = n - 1;
+            while (lo < hi) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(C + mid) < m) lo = mid + 1; else hi = mid;
+            }
+            a.rmass[(size_t)h * 2 + i] = __fsqrt_rn(__ldg(d2 + lo));
+        } else if (t >= 64 && t < 64 + SO_NMASSPROFILE * VC_MAXMASK) {   /* kd2.c:458-496, one species mask per 16 threads */
+            const int k = (t - 64) / SO_NMASSPROFILE, i = (t - 64) % SO_NMASSPROFILE;
+            if (k < a.nmask) {
+                const float *Cs = a.C + (unsigned long long)(1 + k) * a.stride + o;
+                const float fmin = (float)(2.0 / SO_NMASSPROFILE);
+                float f = fmin;
+                for (int q = 0; q < i; ++q) f = __fadd_rn(f, fmin);
+                float mass;
+                if (i < SO_NMASSPROFILE - 1) {
+                    const float r = __fmul_rn(f, rvir), r2 = __fmul_rn(r, r);
+                    mass = massk(Cs, lower_bound_f(d2, n, r2));
+                } else {
+                    mass = massk(Cs, n);
+                }
+                a.profiles[((size_t)k * a.nh + h) * SO_NMASSPROFILE + i] = mass;
+            }
+        }
+        /* kd2.c:551-569: maximum of Vc from the nMembers-th particle on, the first maximum wins */
+        const uint32_t j0 = ((uint32_t)a.nM <= n ? (uint32_t)a.nM : n) - 1u;
+        float best = -1.0f;
+        uint32_t bj = 0xFFFFFFFFu;
+        for (uint32_t j = j0 + (uint32_t)t; j < n; j += 256u) {
+            const float r = __fsqrt_rn(__ldg(d2 + j));
+            const float vc = __fsqrt_rn(__fdiv_rn(__fmul_rn(a.G, __ldg(C + j)), r));
+            if (vc > best) { best = vc; bj = j; }
+        }
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+            float ov = __shfl_down_sync(0xFFFFFFFFu, best, o2);
+            uint32_t oj = __shfl_down_sync(0xFFFFFFFFu, bj, o2);
+            if (ov > best || (ov == best && oj < bj)) { best = ov; bj = oj; }
+        }
+        if (lane == 0) { s_v[w] = best; s_j[w] = bj; }
+        __syncthreads();
+        if (t == 0) {
+            for (int k = 1; k < 8; ++k)
+                if (s_v[k] > best || (s_v[k] == best && s_j[k] < bj)) { best = s_v[k]; bj = s_j[k]; }
+            a.vmax[h] = best;
+            a.rmax[h] = __fsqrt_rn(__ldg(d2 + bj));
+        }
+        __syncthreads();
+    }
+}
+
 /* ============================================================================================
  * domain runs (several GPUs): every rank holds a SLICE of the snapshot and a
  * spatially compact share of the halos.  A rank's "focus mask" marks the coarse cells its halos can
@@ -2211,6 +2373,102 @@ __global__ void __launch_bounds__(256) k_tag_settle(const unsigned long long *__
     }
 }
 
+/* kdTagParticles, the ORDER-DEPENDENT part (kd2.c:663-720): the groups that share particles are replayed in the
+ * reference's processing order (ascending catalog mass, kd2.c:873-879) by ONE CTA.  A group walks its r^2-sorted
+ * member list 256 entries at a time.  What happens at an already-tagged particle depends only on the pair of
+ * groups and their current radii (kd2.c:677-703): "ignore" leaves everything but the particle's counter as it is,
+ * so all entries in front of the first subsume / slurp event of a chunk are applied in parallel; the event itself
+ * (kdZeroGroup over the loser's member list, kd2.c:617-643) is applied by the whole CTA, and the walk resumes
+ * behind it.  State: tag[] = PINIT.iGrp, nsub[] / nign[] = PINIT.nSubsumed / nIgnored, rvir / mvir = GRPNODE. */
+struct ReplayArgs {
+    const int32_t *order;                 /* slots of the groups to replay, in processing order */
+    int n_order;
+    const unsigned long long *off;
+    const int32_t *mem;
+    const int32_t *index;                 /* catalog id per slot */
+    const int32_t *slot_of_index;
+    const float *pos;                     /* 3 per slot */
+    float *rvir, *mvir;
+    int32_t *tag, *nsub, *nign;
+    int32_t *counters;                    /* [0] groups removed, [1] groups slurped, [2] error */
+    unsigned char *do_vcirc;              /* per slot: still valid right after its own walk (kd2.c:884) */
+};
+
+__global__ void __launch_bounds__(256) k_tag_replay(const __grid_constant__ ReplayArgs a)
+{
+    __shared__ int s_first;               /* first subsume / slurp event of the chunk */
+    __shared__ int s_kind, s_other;
+    const int t = threadIdx.x;
+    for (int it = 0; it < a.n_order; ++it) {
+        const int A = a.order[it];
+        const unsigned long long a0 = a.off[A], a1 = a.off[A + 1];
+        const int32_t idA = a.index[A];
+        const float ax = a.pos[3 * A], ay = a.pos[3 * A + 1], az = a.pos[3 * A + 2];
+        bool slurped = false;
+        unsigned long long k0 = a0;
+        while (k0 < a1 && !slurped) {
+            const float rA = a.rvir[A];
+            const float rA2 = __fmul_rn(rA, rA);
+            if (t == 0) s_first = 0x7FFFFFFF;
+            __syncthreads();
+            const unsigned long long k = k0 + (unsigned long long)t;
+            int32_t p = -1, tg = 0;
+            int kind = 0, other = -1;     /* 0 untagged, 1 ignore, 2 subsume, 3 slurp */
+            if (k < a1) {
+                p = a.mem[k];
+                tg = a.tag[p];
+                if (tg != 0) {
+                    other = a.slot_of_index[tg];
+                    const float dx = __fsub_rn(ax, a.pos[3 * other]), dy = __fsub_rn(ay, a.pos[3 * other + 1]),
+                                dz = __fsub_rn(az, a.pos[3 * other + 2]);
+                    const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));   /* kd2.c:677-680 */
+                    const float rB = a.rvir[other];
+                    if (r2 <= rA2) kind = 2;
+                    else if (r2 <= __fmul_rn(rB, rB)) kind = 3;
+                    else kind = 1;
+                    if (kind >= 2) atomicMin(&s_first, t);
+                }
+            }
+            __syncthreads();
+            const int first = s_first;
+            if (k < a1 && t < first) {                        /* everything in front of the event: independent */
+                if (kind == 0) a.tag[p] = idA;
+                else ++a.nign[p];                             /* (a particle appears once in this list) */
+            }
+            if (t == first) { s_kind = kind; s_other = other; }
+            __syncthreads();
+            if (first == 0x7FFFFFFF) { k0 += 256ull; continue; }
+            const int ev_kind = s_kind, B = s_other;
+            const int loser = ev_kind == 2 ? B : A, winner = ev_kind == 2 ? A : B;
+            if (t == 0) {                                     /* kdZeroGroup's bookkeeping (kd2.c:617-634) */
+                if (a.mvir[loser] < 0.0f) a.counters[2] = 1;
+                a.rvir[loser] = (float)(-10.0 * (double)a.index[winner]);
+                a.mvir[loser] = -a.mvir[loser];
+                ++a.counters[ev_kind == 2 ? 0 : 1];
+            }
+            {
+                const int32_t idL = a.index[loser];
+                const unsigned long long l0 = a.off[loser], l1 = a.off[loser + 1];
+                for (unsigned long long q = l0 + (unsigned long long)t; q < l1; q += 256ull) {
+                    const int32_t pp = a.mem[q];
+                    if (a.tag[pp] == idL) { a.tag[pp] = 0; ++a.nsub[pp]; }
+                }
+            }
+            __syncthreads();
+            if (ev_kind == 2) {
+                if (t == first) a.tag[p] = idA;               /* kd2.c:691: the particle goes to the subsuming group */
+                k0 += (unsigned long long)first + 1ull;       /* resume behind the event: the loser's particles are free now */
+            } else {
+                slurped = true;                               /* kd2.c:671: nothing after the slurp */
+            }
+            __threadfence_block();
+            __syncthreads();
+        }
+        if (t == 0) a.do_vcirc[A] = a.rvir[A] > 0.0f ? 1 : 0;
+        __syncthreads();
+    }
+}
+
 /* _VcmParticles (kd2.c:595-609): vcm[l] = (sum over the members, in sorted order, of fl(m * v[l])) / Mvir,
  * a sequential fp32 sum per group.  One thread per group walks its (r^2, index)-sorted member list; the
  * loads of 8 members are issued together, the adds stay in list order. */
@@ -2272,13 +2530,13 @@ __global__ void __launch_bounds__(256) k_member_unkeys(const unsigned long long 
 enum {
     KID_LVL_HIST = 0, KID_LVL_SCAN, KID_LVL_PARTITION, KID_BUCKET_SORT, KID_MASS_TABLE, KID_CLASSIFY,
     KID_QUERY_WARP, KID_QUERY_BLOCK, KID_OFFSETS, KID_EMIT_WARP, KID_EMIT_BLOCK, KID_BALL_GATHER,
-    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_VCIRC, KID_TAG, KID_ROUTE, KID_ASSIGN, KID_PUSH, KID_BARRIER, KID_QUERY_FUSED, KID_N
+    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_VCIRC, KID_TAG, KID_ROUTE, KID_ASSIGN, KID_PUSH, KID_BARRIER, KID_QUERY_FUSED, KID_SEGSORT, KID_N
 };
 static const char *const g_kernel_names[KID_N] = {
     "k_lvl_hist", "k_scan", "k_lvl_partition", "k_bucket_sort", "k_mass_table", "k_classify",
     "k_so_query<32>", "k_so_query<256>", "k_offsets", "k_so_emit<32>", "k_so_emit<256>", "k_ball_gather",
     "k_so_query<1024>", "k_so_emit<1024>", "k_mark_mask", "k_vcirc", "k_tag_claim+settle", "k_route",
-    "k_assign", "k_push", "k_dom_barrier", "k_so_query_fused"};
+    "k_assign", "k_push", "k_dom_barrier", "k_so_query_fused", "k_segsort"};
 
 struct ProfRec { int kid, launches; cudaEvent_t a, b; };
 
@@ -2367,11 +2625,19 @@ struct sogpu {
     unsigned short *d_route_table;   /* destination ranks per coarse cell */
     uint32_t *d_route_any;
     int32_t *d_tag, *d_tag_index;    /* sogpu_tag_members: owner per particle, catalog ids */
+    int32_t *d_nsub, *d_nign;        /* sogpu_tag_replay: PINIT.nSubsumed / nIgnored */
+    int64_t replay_cap;
+    void *d_replay;                  /* ... and its per-group arrays */
+    size_t replay_bytes;
     unsigned char *d_dirty;
     int64_t tag_cap;
     int32_t tagh_cap;
     float *d_vc;                     /* sogpu_vcirc: per-group inputs and outputs */
     size_t vc_cap;
+    unsigned char *d_ptype;          /* sogpu_vcirc_species: species bits per particle */
+    int64_t ptype_cap;
+    float *d_vcC;                    /* ... and the sequential mass prefixes */
+    size_t vcC_cap;
     bool members_sorted;             /* the device member lists are already in (r^2, index) order */
     float last_thr;                  /* parameters of the last solve (its centres / radii are in d_centers / d_rgtp) */
     int32_t last_nM;
@@ -2387,8 +2653,9 @@ struct sogpu {
     unsigned long long *d_gkeys[2];
     float *d_gmass[2];
     size_t gen_cap;                  /* entries of the (key, mass) scratch */
-    void *d_cub_tmp;
-    size_t cub_tmp_bytes;
+    uint32_t *d_ss_tiles;            /* segmented sort: tile_base[nseg + 1] */
+    unsigned long long *d_ss_max, *d_ss_off;
+    int32_t ss_cap;
     int32_t gen_cap_h;
 
     /* pinned host staging */
@@ -2598,10 +2865,10 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     cudaFree(h->d_tmp4); cudaFree(h->d_key[0]); cudaFree(h->d_key[1]);
     for (int l = 0; l < 4; ++l) { cudaFree(h->d_lvl_start[l]); cudaFree(h->d_lvl_cursor[l]); }
     cudaFree(h->d_mt);
-    cudaFree(h->d_vc);
+    cudaFree(h->d_vc); cudaFree(h->d_ptype); cudaFree(h->d_vcC);
     cudaFree(h->d_route); cudaFree(h->d_route_table); cudaFree(h->d_route_any);
     cudaFree(h->d_live); cudaFree(h->d_timeline);
-    cudaFree(h->d_tag); cudaFree(h->d_tag_index); cudaFree(h->d_dirty);
+    cudaFree(h->d_tag); cudaFree(h->d_tag_index); cudaFree(h->d_dirty); cudaFree(h->d_nsub); cudaFree(h->d_nign); cudaFree(h->d_replay);
     cudaFree(h->d_counters);
     cudaFree(h->d_u64);
     cudaFree(h->d_members);
@@ -2611,7 +2878,7 @@ extern "C" void sogpu_destroy(sogpu_t *h)
     cudaFree(h->d_gen_state); cudaFree(h->d_gen_list[0]); cudaFree(h->d_gen_list[1]); cudaFree(h->d_gen_round);
     cudaFree(h->d_seg_n); cudaFree(h->d_seg_begin); cudaFree(h->d_seg_end);
     cudaFree(h->d_gkeys[0]); cudaFree(h->d_gkeys[1]); cudaFree(h->d_gmass[0]); cudaFree(h->d_gmass[1]);
-    cudaFree(h->d_cub_tmp);
+    cudaFree(h->d_ss_tiles); cudaFree(h->d_ss_max); cudaFree(h->d_ss_off);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     if (h->h_members) cudaFreeHost(h->h_members);
     if (h->h_md2) cudaFreeHost(h->h_md2);
@@ -3350,6 +3617,48 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
     return SOGPU_OK;
 }
 
+/* ---- segmented sort of the keys in d_gkeys[0] (seg_sort.cuh); *result = the buffer that holds them sorted ---- */
+static int seg_sort_scratch(sogpu *h, int nseg)
+{
+    if (nseg + 1 > h->ss_cap) {
+        cudaFree(h->d_ss_tiles); cudaFree(h->d_ss_off);
+        h->d_ss_tiles = nullptr; h->d_ss_off = nullptr; h->ss_cap = 0;
+        const int cap = std::max(nseg + 1, 4096);
+        CU(cudaMalloc(&h->d_ss_tiles, (size_t)(cap + 1) * sizeof(uint32_t)));
+        CU(cudaMalloc(&h->d_ss_off, (size_t)(cap + 1) * sizeof(unsigned long long)));
+        h->ss_cap = cap;
+    }
+    if (!h->d_ss_max) CU(cudaMalloc(&h->d_ss_max, sizeof(unsigned long long)));
+    return SOGPU_OK;
+}
+
+static int seg_sort_keys(sogpu *h, int nseg, const unsigned long long *d_off, size_t tot, unsigned long long **result)
+{
+    cudaStream_t s = h->stream;
+    *result = h->d_gkeys[0];
+    if (tot == 0 || nseg <= 0) return SOGPU_OK;
+    int rc = seg_sort_scratch(h, nseg);
+    if (rc) return rc;
+    k_segsort_plan<<<1, 1024, 0, s>>>(d_off, nseg, h->d_ss_tiles, h->d_ss_max);
+    unsigned long long max_n = 0;
+    CU(cudaMemcpyAsync(&max_n, h->d_ss_max, sizeof(max_n), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const size_t tiles_ub = tot / SS_T + (size_t)nseg;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>(tiles_ub, (size_t)h->sm_count * 8));
+    int cur = 1;
+    {
+        ProfScope p(h, KID_SEGSORT);
+        k_segsort_tiles<<<grid, SS_NT, 0, s>>>(d_off, nseg, h->d_ss_tiles, h->d_gkeys[0], h->d_gkeys[1]);
+        for (unsigned long long run = SS_T; run < max_n; run *= 2ull) {
+            k_segsort_merge<<<grid, SS_NT, 0, s>>>(d_off, nseg, h->d_ss_tiles, run, h->d_gkeys[cur], h->d_gkeys[cur ^ 1]);
+            cur ^= 1;
+        }
+    }
+    CU(cudaGetLastError());
+    *result = h->d_gkeys[cur];
+    return SOGPU_OK;
+}
+
 /* ---- general path driver: rounds over the ball schedule, batches bounded by the scratch size ---- */
 static int gen_scratch(sogpu *h, size_t entries)
 {
@@ -3434,29 +3743,24 @@ static int run_query_general(sogpu *h, const float *d_centers, const float *d_rg
                 rc = gen_scratch(h, tot);                     /* a single ball larger than the budget */
                 if (rc) return rc;
                 a.keys = h->d_gkeys[0]; a.mass = h->d_gmass[0];
-                k_gen_offsets<<<1, 1024, 0, s>>>(h->d_seg_n, s0, s1, h->d_seg_begin, h->d_seg_end);
+                rc = seg_sort_scratch(h, (int)(s1 - s0));
+                if (rc) return rc;
+                k_gen_offsets<<<1, 1024, 0, s>>>(h->d_seg_n, s0, s1, h->d_seg_begin, h->d_seg_end, h->d_ss_off);
                 {
                     ProfScope p(h, KID_EMIT_BLOCK);
                     int ctas = (int)std::min<uint32_t>(s1 - s0, (uint32_t)h->sm_count * 4);
                     k_gen_emit<<<ctas, 256, smem, s>>>(a, s0, s1);
                 }
-                size_t need = 0;
-                cub::DeviceSegmentedSort::SortPairs(nullptr, need, h->d_gkeys[0], h->d_gkeys[1], h->d_gmass[0],
-                                                    h->d_gmass[1], (int64_t)tot, (int64_t)(s1 - s0), h->d_seg_begin + s0,
-                                                    h->d_seg_end + s0, s);
-                if (need > h->cub_tmp_bytes) {
-                    cudaFree(h->d_cub_tmp); h->d_cub_tmp = nullptr; h->cub_tmp_bytes = 0;
-                    CU(cudaMalloc(&h->d_cub_tmp, need));
-                    h->cub_tmp_bytes = need;
-                }
-                CU(cub::DeviceSegmentedSort::SortPairs(h->d_cub_tmp, need, h->d_gkeys[0], h->d_gkeys[1], h->d_gmass[0],
-                                                       h->d_gmass[1], (int64_t)tot, (int64_t)(s1 - s0),
-                                                       h->d_seg_begin + s0, h->d_seg_end + s0, s));
+                unsigned long long *sorted_keys = nullptr;
+                rc = seg_sort_keys(h, (int)(s1 - s0), h->d_ss_off, tot, &sorted_keys);   /* qsort(CmpList), kd2.c:781 */
+                if (rc) return rc;
+                k_gen_mass<<<(int)std::min<size_t>((tot + 255) / 256, (size_t)h->sm_count * 16), 256, 0, s>>>(sorted_keys, tot, h->d_in,
+                                                                                                          h->d_gmass[1]);
                 {
                     ProfScope p(h, KID_QUERY_WARP);
                     int warps = (int)(s1 - s0);
                     int ctas = std::min((warps + 7) / 8, h->sm_count * 8);
-                    k_gen_scan<<<ctas, 256, 0, s>>>(a, s0, s1, h->d_gkeys[1], h->d_gmass[1]);
+                    k_gen_scan<<<ctas, 256, 0, s>>>(a, s0, s1, sorted_keys, h->d_gmass[1]);
                 }
                 s0 = s1;
             }
@@ -3700,17 +4004,10 @@ static int sort_members_device(sogpu *h, int32_t nh, size_t tot)
     cudaStream_t s = h->stream;
     const int grid = (int)std::min<size_t>((tot + 255) / 256, (size_t)h->sm_count * 16);
     k_member_keys<<<grid, 256, 0, s>>>(h->d_members, h->d_md2, tot, h->d_gkeys[0]);
-    size_t need = 0;
-    cub::DeviceSegmentedSort::SortKeys(nullptr, need, h->d_gkeys[0], h->d_gkeys[1], (int64_t)tot, (int64_t)nh,
-                                       h->d_out_off, h->d_out_off + 1, s);
-    if (need > h->cub_tmp_bytes) {
-        cudaFree(h->d_cub_tmp); h->d_cub_tmp = nullptr; h->cub_tmp_bytes = 0;
-        CU(cudaMalloc(&h->d_cub_tmp, need));
-        h->cub_tmp_bytes = need;
-    }
-    CU(cub::DeviceSegmentedSort::SortKeys(h->d_cub_tmp, need, h->d_gkeys[0], h->d_gkeys[1], (int64_t)tot, (int64_t)nh,
-                                          h->d_out_off, h->d_out_off + 1, s));
-    k_member_unkeys<<<grid, 256, 0, s>>>(h->d_gkeys[1], tot, h->d_members, h->d_md2);
+    unsigned long long *sorted_keys = nullptr;
+    rc = seg_sort_keys(h, nh, h->d_out_off, tot, &sorted_keys);
+    if (rc) return rc;
+    k_member_unkeys<<<grid, 256, 0, s>>>(sorted_keys, tot, h->d_members, h->d_md2);
     CU(cudaGetLastError());
     return SOGPU_OK;
 }
@@ -3950,6 +4247,88 @@ extern "C" int sogpu_vcirc(sogpu_t *h, const float *centers, const float *rvir, 
     return SOGPU_OK;
 }
 
+/* kdVcirc / kdMassProfile for snapshots with unequal masses and / or several species (kd2.c:458-496, 498-586):
+ * ptype[i] (host, N bytes, may be NULL) holds the species bits of particle i, masks[k] selects the particles that
+ * count for profile k; profiles = nmasks x nh x 16 floats. */
+extern "C" int sogpu_vcirc_species(sogpu_t *h, const float *centers, const float *rvir, const float *mvir, int32_t nh,
+                                   float G, int32_t nMembers, const unsigned char *ptype, const int32_t *masks,
+                                   int32_t nmasks, float *vcirc, float *rmass, float *rmax, float *vmax, float *profiles)
+{
+    if (!h || !centers || !rvir || !mvir || !vcirc || !rmass || !rmax || !vmax || nh <= 0 || nMembers < 1 || nmasks < 0 ||
+        nmasks > VC_MAXMASK || (nmasks > 0 && (!masks || !profiles)))
+        return set_err(SOGPU_ERR_ARG, "sogpu_vcirc_species: bad argument (at most %d species masks)", VC_MAXMASK);
+    if (!h->built) return set_err(SOGPU_ERR_ARG, "sogpu_vcirc_species: call sogpu_build_grid first");
+    if (h->indexed) return set_err(SOGPU_ERR_UNSUPPORTED, "sogpu_vcirc_species: not available on one rank's share of a domain run");
+    CU(cudaSetDevice(h->device));
+    std::vector<float> ball2((size_t)nh);
+    for (int32_t i = 0; i < nh; ++i) {
+        float fBall = (float)(2. * rvir[i]);                              /* kd2.c:511-512 */
+        ball2[i] = fBall * fBall;
+    }
+    int rc = sogpu_ball_gather_batch(h, centers, ball2.data(), nh);
+    if (rc) return rc;
+    rc = fetch_stats(h);
+    if (rc) return rc;
+    const size_t tot = (size_t)h->stats.last_members;
+    rc = sort_members_device(h, nh, tot);
+    if (rc) return rc;
+    h->members_sorted = true;
+    cudaStream_t s = h->stream;
+    if (ptype) {
+        if (h->n > h->ptype_cap) {
+            cudaFree(h->d_ptype); h->d_ptype = nullptr; h->ptype_cap = 0;
+            CU(cudaMalloc(&h->d_ptype, (size_t)h->n));
+            h->ptype_cap = h->n;
+        }
+        CU(cudaMemcpyAsync(h->d_ptype, ptype, (size_t)h->n, cudaMemcpyHostToDevice, s));
+    }
+    const size_t need = (size_t)(1 + nmasks) * std::max<size_t>(tot, 1);
+    if (need > h->vcC_cap) {
+        cudaFree(h->d_vcC); h->d_vcC = nullptr; h->vcC_cap = 0;
+        CU(cudaMalloc(&h->d_vcC, need * sizeof(float)));
+        h->vcC_cap = need;
+    }
+    const size_t per = 2 + SO_NVCIRC + 2 + 1 + 1 + (size_t)SO_NMASSPROFILE * VC_MAXMASK;
+    if ((size_t)nh * per > h->vc_cap) {
+        cudaFree(h->d_vc); h->d_vc = nullptr; h->vc_cap = 0;
+        CU(cudaMalloc(&h->d_vc, (size_t)nh * per * sizeof(float)));
+        h->vc_cap = (size_t)nh * per;
+    }
+    rc = ensure_pinned(h, (size_t)nh * per * sizeof(float));
+    if (rc) return rc;
+    float *pin = (float *)h->h_pin;
+    memcpy(pin, rvir, (size_t)nh * sizeof(float));
+    memcpy(pin + nh, mvir, (size_t)nh * sizeof(float));
+    CU(cudaMemcpyAsync(h->d_vc, pin, (size_t)nh * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    uint32_t masks4 = 0;
+    for (int k = 0; k < nmasks; ++k) masks4 |= ((uint32_t)masks[k] & 0xFFu) << (8 * k);
+    VcircGenArgs a;
+    a.d2 = h->d_md2; a.off = h->d_out_off; a.C = h->d_vcC; a.stride = (unsigned long long)std::max<size_t>(tot, 1);
+    a.rvir = h->d_vc; a.mvir = h->d_vc + nh; a.G = G; a.nM = nMembers; a.nh = nh; a.nmask = nmasks;
+    a.vcirc = h->d_vc + (size_t)2 * nh;
+    a.rmass = a.vcirc + (size_t)SO_NVCIRC * nh;
+    a.rmax = a.rmass + (size_t)2 * nh;
+    a.vmax = a.rmax + nh;
+    a.profiles = a.vmax + nh;
+    {
+        ProfScope p(h, KID_VCIRC, 0.0, 2);
+        k_vc_prefix<<<std::min((nh + 7) / 8, h->sm_count * 8), 256, 0, s>>>(h->d_out_off, h->d_members, nh, h->d_in,
+                                                                            ptype ? h->d_ptype : nullptr, nmasks, masks4, a.stride, h->d_vcC);
+        k_vcirc_gen<<<std::min(nh, h->sm_count * 16), 256, 0, s>>>(a);
+    }
+    CU(cudaGetLastError());
+    const size_t n_out = (size_t)nh * (SO_NVCIRC + 2 + 1 + 1) + (size_t)nmasks * nh * SO_NMASSPROFILE;
+    CU(cudaMemcpyAsync(pin + (size_t)2 * nh, h->d_vc + (size_t)2 * nh, n_out * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const float *o = pin + (size_t)2 * nh;
+    memcpy(vcirc, o, (size_t)SO_NVCIRC * nh * sizeof(float)); o += (size_t)SO_NVCIRC * nh;
+    memcpy(rmass, o, (size_t)2 * nh * sizeof(float)); o += (size_t)2 * nh;
+    memcpy(rmax, o, (size_t)nh * sizeof(float)); o += nh;
+    memcpy(vmax, o, (size_t)nh * sizeof(float)); o += nh;
+    if (nmasks) memcpy(profiles, o, (size_t)nmasks * nh * SO_NMASSPROFILE * sizeof(float));
+    return SOGPU_OK;
+}
+
 /* Conflict detection + tagging of the conflict-free groups of the last sogpu_so() result (see k_tag_claim). */
 extern "C" int sogpu_tag_members(sogpu_t *h, const int32_t *index, int32_t nh, unsigned char *in_conflict,
                                  int32_t *igrp)
@@ -3991,6 +4370,81 @@ extern "C" int sogpu_tag_members(sogpu_t *h, const int32_t *index, int32_t nh, u
     if (igrp) CU(cudaMemcpyAsync(igrp, h->d_tag, (size_t)h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     memcpy(in_conflict, pd, (size_t)nh);
+    return SOGPU_OK;
+}
+
+/* kdTagParticles for the groups sogpu_tag_members reported in conflict, replayed in order on the device
+ * (k_tag_replay).  Must follow sogpu_tag_members over the same nh groups, member lists sorted. */
+extern "C" int sogpu_tag_replay(sogpu_t *h, const int32_t *order, int32_t n_order, const int32_t *index, const float *centers,
+                                float *rvir, float *mvir, int32_t nh, int32_t max_index, int32_t *igrp, int32_t *nsubsumed,
+                                int32_t *nignored, int32_t *groups_removed, int32_t *groups_slurped, unsigned char *still_valid)
+{
+    if (!h || !order || !index || !centers || !rvir || !mvir || nh <= 0 || n_order < 0 || max_index < 1 || !groups_removed ||
+        !groups_slurped || !still_valid)
+        return set_err(SOGPU_ERR_ARG, "sogpu_tag_replay: bad argument");
+    if (!h->have_result || h->last_h != nh || !h->d_tag || !h->members_csr || !h->members_sorted)
+        return set_err(SOGPU_ERR_ARG, "sogpu_tag_replay: call sogpu_members(sorted) and sogpu_tag_members over the same %d groups first", nh);
+    CU(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    if (h->n > h->replay_cap) {
+        cudaFree(h->d_nsub); cudaFree(h->d_nign);
+        h->d_nsub = h->d_nign = nullptr; h->replay_cap = 0;
+        CU(cudaMalloc(&h->d_nsub, (size_t)h->n * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_nign, (size_t)h->n * sizeof(int32_t)));
+        h->replay_cap = h->n;
+    }
+    /* one block of per-group data: order | index | slot_of_index | pos | rvir | mvir | counters | do_vcirc */
+    const size_t n_ord = (size_t)std::max(n_order, 1);
+    const size_t words = n_ord + (size_t)nh + ((size_t)max_index + 1) + 3 * (size_t)nh + 2 * (size_t)nh + 4 + ((size_t)nh + 3) / 4;
+    if (words * 4 > h->replay_bytes) {
+        cudaFree(h->d_replay); h->d_replay = nullptr; h->replay_bytes = 0;
+        CU(cudaMalloc(&h->d_replay, words * 4));
+        h->replay_bytes = words * 4;
+    }
+    std::vector<int32_t> host(words, 0);
+    int32_t *p_order = host.data(), *p_index = p_order + n_ord, *p_slot = p_index + nh;
+    float *p_pos = (float *)(p_slot + max_index + 1), *p_rvir = p_pos + 3 * (size_t)nh, *p_mvir = p_rvir + nh;
+    int32_t *p_cnt = (int32_t *)(p_mvir + nh);
+    unsigned char *p_dov = (unsigned char *)(p_cnt + 4);
+    memcpy(p_order, order, (size_t)n_order * sizeof(int32_t));
+    memcpy(p_index, index, (size_t)nh * sizeof(int32_t));
+    for (int32_t i = 0; i <= max_index; ++i) p_slot[i] = -1;
+    for (int32_t i = 0; i < nh; ++i) {
+        if (index[i] < 1 || index[i] > max_index) return set_err(SOGPU_ERR_ARG, "sogpu_tag_replay: catalog id %d out of range", index[i]);
+        p_slot[index[i]] = i;
+    }
+    memcpy(p_pos, centers, (size_t)nh * 3 * sizeof(float));
+    memcpy(p_rvir, rvir, (size_t)nh * sizeof(float));
+    memcpy(p_mvir, mvir, (size_t)nh * sizeof(float));
+    for (int32_t i = 0; i < nh; ++i) p_dov[i] = rvir[i] > 0.0f ? 1 : 0;
+    CU(cudaMemcpyAsync(h->d_replay, host.data(), words * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(h->d_nsub, 0, (size_t)h->n * sizeof(int32_t), s));
+    CU(cudaMemsetAsync(h->d_nign, 0, (size_t)h->n * sizeof(int32_t), s));
+    int32_t *d = (int32_t *)h->d_replay;
+    ReplayArgs a;
+    a.order = d; a.n_order = n_order; a.off = h->d_out_off; a.mem = h->d_members;
+    a.index = d + n_ord; a.slot_of_index = a.index + nh;
+    a.pos = (const float *)(a.slot_of_index + max_index + 1);
+    a.rvir = (float *)a.pos + 3 * (size_t)nh; a.mvir = a.rvir + nh;
+    a.counters = (int32_t *)(a.mvir + nh);
+    a.do_vcirc = (unsigned char *)(a.counters + 4);
+    a.tag = h->d_tag; a.nsub = h->d_nsub; a.nign = h->d_nign;
+    if (n_order > 0) {
+        ProfScope p(h, KID_TAG);
+        k_tag_replay<<<1, 256, 0, s>>>(a);
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host.data(), h->d_replay, words * 4, cudaMemcpyDeviceToHost, s));
+    if (igrp) CU(cudaMemcpyAsync(igrp, h->d_tag, (size_t)h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (nsubsumed) CU(cudaMemcpyAsync(nsubsumed, h->d_nsub, (size_t)h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (nignored) CU(cudaMemcpyAsync(nignored, h->d_nign, (size_t)h->n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (p_cnt[2]) return set_err(SOGPU_ERR_UNSUPPORTED, "kdZeroGroup: zeroed group mass is already negative (kd2.c:626-632)");
+    memcpy(rvir, p_rvir, (size_t)nh * sizeof(float));
+    memcpy(mvir, p_mvir, (size_t)nh * sizeof(float));
+    memcpy(still_valid, p_dov, (size_t)nh);
+    *groups_removed = p_cnt[0];
+    *groups_slurped = p_cnt[1];
     return SOGPU_OK;
 }
 

@@ -337,7 +337,9 @@ void kdSO(KD kd, float rhovir, int nSmooth)
     sogpu_stats_t st;
     TAGCTX c;
     double t0 = wall(), tp;
-    int i, it, equal_mass = 0;
+    int i, it, equal_mass = 0, device_replay = 0;
+    float *rv2 = NULL, *mv2 = NULL;
+    unsigned char *still_valid = NULL;
     (void)nSmooth;
     phase(NULL, &tp);                 /* sized the reference's neighbour list (smInit); nothing to size here */
     if (h == 0) return;
@@ -415,10 +417,34 @@ void kdSO(KD kd, float rhovir, int nSmooth)
         for (i = 0; i < h; ++i) ids[i] = kd->grps[i].index;
         if (sogpu_tag_members(kd->gpu, ids, h, in_conflict, kd->bSkipGrpArray ? NULL : kd->p.iGrp))
             die_gpu("kdSO (sogpu_tag_members)");
-        free(ids);
         for (i = 0; i < h; ++i) kd->nGrpsInConflict += in_conflict[i];
+        phase("tagging on the device", &tp);
+        indexx(h, masses, order);
+        /* the groups that share particles: kdTagParticles replayed in processing order ON THE DEVICE
+         * (sogpu_tag_replay; SO_HOST_REPLAY=1 keeps the host replay below for comparison) */
+        if (kd->nGrpsInConflict > 0 && !getenv("SO_HOST_REPLAY")) {
+            int32_t *ord = (int32_t *)malloc((size_t)h * sizeof(int32_t)), no = 0, rem = 0, slu = 0;
+            rv2 = (float *)malloc((size_t)h * sizeof(float));
+            mv2 = (float *)malloc((size_t)h * sizeof(float));
+            still_valid = (unsigned char *)malloc((size_t)h);
+            assert(ord && rv2 && mv2 && still_valid);
+            for (it = 1; it <= h; ++it) {
+                int g = order[it] - 1;
+                if (in_conflict[g] && rvir[g] > 0.0f) ord[no++] = g;
+            }
+            memcpy(rv2, rvir, (size_t)h * sizeof(float));
+            memcpy(mv2, mvir, (size_t)h * sizeof(float));
+            if (sogpu_tag_replay(kd->gpu, ord, no, ids, centers, rv2, mv2, h, kd->nInGTP + 1, kd->p.iGrp, kd->p.nSubsumed,
+                                 kd->p.nIgnored, &rem, &slu, still_valid))
+                die_gpu("kdSO (sogpu_tag_replay)");
+            kd->iGroupsRemoved += rem;
+            kd->iGroupsSlurped += slu;
+            device_replay = 1;
+            free(ord);
+            phase("conflict replay on the device", &tp);
+        }
+        free(ids);
     }
-    phase("tagging on the device", &tp);
     if (!kd->bSkipVcm && kd->p.v == NULL) {
         /* _VcmParticles (kd2.c:595-609, 826) of every resolved group on the device: the same sequential fp32
          * sum over the (r^2, index)-sorted members; the velocities were kept there by the ingest */
@@ -431,18 +457,18 @@ void kdSO(KD kd, float rhovir, int nSmooth)
         phase("vcm on the device", &tp);
     }
     c.off = off; c.mem = mem; c.slot_of_index = slot_of_index;
-    indexx(h, masses, order);
     for (it = 1; it <= h; ++it) {
         int g = order[it] - 1;
         GRPNODE *grp = &kd->grps[g];
-        grp->fRvir = rvir[g];                              /* kd2.c:819-820 or the error code */
-        grp->fMvir = mvir[g];
+        grp->fRvir = device_replay ? rv2[g] : rvir[g];     /* kd2.c:819-820 or the error code (with the subsume / slurp marks) */
+        grp->fMvir = device_replay ? mv2[g] : mvir[g];
         if (rvir[g] > 0.0f) {
-            if (in_conflict[g]) tag_particles(kd, &c, g);  /* kd2.c:823 */
+            if (in_conflict[g] && !device_replay) tag_particles(kd, &c, g);  /* kd2.c:823 */
             if (!kd->bSkipVcm && kd->p.v) vcm_particles(kd, &c, g, mvir[g]);   /* kd2.c:826; host copy of the velocities only */
-            if (grp->fRvir > 0.0f) do_vcirc[g] = 1;        /* kd2.c:884: not slurped */
+            if (device_replay ? still_valid[g] : (grp->fRvir > 0.0f)) do_vcirc[g] = 1;        /* kd2.c:884: not slurped */
         }
     }
+    free(rv2); free(mv2); free(still_valid);
 
     phase("conflict replay", &tp);
     /* kdVcirc for every group that was valid when the reference would have called it */
@@ -490,6 +516,42 @@ void kdSO(KD kd, float rhovir, int nSmooth)
                     if (kd->bStar && kd->nStar) memcpy(g->fStar, o_pr + (size_t)k * NMASSPROFILE, NMASSPROFILE * sizeof(float));
                 }
                 free(vr); free(o_vc);
+            } else if (!getenv("SO_HOST_VCIRC")) {
+                /* unequal masses, several species or -mark: the reference's sequential fp32 sums over the sorted
+                 * 2 Rvir lists, per species, evaluated on the device (sogpu_vcirc_species) */
+                int32_t masks[4], nm = 0, km;
+                float *dst_of[4];
+                unsigned char *pt = (unsigned char *)malloc((size_t)kd->nParticles);
+                float *vr = (float *)malloc((size_t)nv * 2 * sizeof(float)), *vm = vr + nv;
+                float *o_vc = (float *)malloc((size_t)nv * (NVCIRC + 2 + 1 + 1 + 4 * NMASSPROFILE) * sizeof(float));
+                float *o_rm = o_vc + (size_t)nv * NVCIRC, *o_rx = o_rm + (size_t)nv * 2, *o_vx = o_rx + nv;
+                float *o_pr = o_vx + nv;
+                assert(pt && vr && o_vc);
+                for (i = 0; i < kd->nParticles; ++i)
+                    pt[i] = (unsigned char)(kdParticleType(kd, i) | ((kd->bMark && kd->bMarkList && kd->bMarkList[i]) ? MARK : 0));
+                if (kd->bDark) masks[nm++] = DARK;
+                if (kd->bGas) masks[nm++] = GAS;
+                if (kd->bStar) masks[nm++] = STAR;
+                if (kd->bMark) masks[nm++] = MARK;
+                for (k = 0; k < nv; ++k) { vr[k] = rvir[slots[k]]; vm[k] = mvir[slots[k]]; }
+                if (sogpu_vcirc_species(kd->gpu, vc, vr, vm, nv, kd->G, kd->nMembers, pt, masks, nm, o_vc, o_rm, o_rx, o_vx, o_pr))
+                    die_gpu("kdSO (sogpu_vcirc_species)");
+                phase("kdVcirc (species) on the device", &tp);
+                for (k = 0; k < nv; ++k) {
+                    GRPNODE *g = &kd->grps[slots[k]];
+                    memcpy(g->fVcirc, o_vc + (size_t)k * NVCIRC, NVCIRC * sizeof(float));
+                    memcpy(g->fRmass, o_rm + (size_t)k * 2, 2 * sizeof(float));
+                    g->fRmax = o_rx[k];
+                    g->fVmax = o_vx[k];
+                    km = 0;
+                    if (kd->bDark) dst_of[km++] = g->fDark;
+                    if (kd->bGas) dst_of[km++] = g->fGas;
+                    if (kd->bStar) dst_of[km++] = g->fStar;
+                    if (kd->bMark) dst_of[km++] = g->fMark;
+                    for (km = 0; km < nm; ++km)
+                        memcpy(dst_of[km], o_pr + ((size_t)km * nv + k) * NMASSPROFILE, NMASSPROFILE * sizeof(float));
+                }
+                free(pt); free(vr); free(o_vc);
             } else {
                 const int32_t *vi;
                 const float *vd;

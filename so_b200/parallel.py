@@ -472,12 +472,13 @@ class VirtualDomainStep:
     device the peer barrier is replaced by a device synchronisation between the push and the solve phases (the
     ranks' kernels are serialised there anyway)."""
 
-    def __init__(self, n_ranks, n_total, mass, devices=None, recv_cap=None, stage_cap=None, period=(1.0, 1.0, 1.0)):
+    def __init__(self, n_ranks, n_total, mass, devices=None, recv_cap=None, stage_cap=None, period=(1.0, 1.0, 1.0),
+                 frac=0.30):
         from so_b200 import api
         self.R = int(n_ranks)
         self.devices = list(devices) if devices else [0] * self.R
         self.multi = len(set(self.devices)) > 1
-        rc, sc = default_caps(n_total, self.R)
+        rc, sc = default_caps(n_total, self.R, frac)
         self.recv_cap, self.stage_cap = int(recv_cap or rc), int(stage_cap if stage_cap is not None else sc)
         self.gs = [api.SoGpu(device=self.devices[r]) for r in range(self.R)]
         self.n_total, self.mass, self.period = int(n_total), mass, tuple(period)

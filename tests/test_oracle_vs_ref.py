@@ -90,3 +90,22 @@ def test_oracle_vcirc_and_species_profiles_against_reference_binary(tmp_path):
                     ptype_of=ptype, ptype_mask=bit)["profile"]
         np.testing.assert_allclose(p[ok], prow[ok, 1:17], rtol=2e-5, err_msg=ext)
         assert (p[ok, -1] > 0).all()
+
+
+@pytest.mark.skipif(not po.ref_available("so_ref"), reason="reference binary not built")
+@pytest.mark.parametrize("omega0,flat,extra", [(0.3, True, ["-L"]), (0.3, False, []), (1.0, False, []), (0.25, True, ["-L", "-z", "1.5"])])
+def test_virial_threshold_restatement_matches_the_reference_header(tmp_path, omega0, flat, extra):
+    """po.virial_threshold restates so.c:57-86,470-481; the reference prints the value it used in the .sovcirc
+    header ('# fThreshold = %g  (VIRIAL DENSITY)'): same 6 significant digits for both cosmology branches."""
+    from so_b200 import synth, tipsy
+    s = synth.make_snapshot(20 ** 3, 3, seed=5, nmax=300, omega0=omega0, z=0.5)
+    snap, gtp, out = str(tmp_path / "s.tipsy"), str(tmp_path / "h.gtp"), str(tmp_path / "ref")
+    tipsy.write_tipsy(snap, s.time, dark=tipsy.dark_from_arrays(s.pos, s.mass))
+    tipsy.write_gtp(gtp, s.time, s.centers, s.rgtp, s.gtp_mass)
+    po.run_so_ref(snap, gtp, out, delta=None, extra=["-O", repr(omega0), "-s", "64"] + extra)
+    hdr, _ = tipsy.parse_sovcirc(out + ".sovcirc")
+    line = [l for l in hdr if "fThreshold" in l][0]
+    assert "VIRIAL DENSITY" in line
+    z = 1.5 if "-z" in extra else None
+    mine = po.virial_threshold(omega0, flat, time=np.float32(s.time), z=z)
+    assert line.split("=")[1].split()[0] == "%g" % mine, (line, mine)

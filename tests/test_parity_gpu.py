@@ -377,6 +377,35 @@ def test_vcirc_and_mass_profile_match_oracle(nmem):
         g.close()
 
 
+def test_vcirc_species_with_mixed_masses_matches_oracle():
+    """sogpu_vcirc_species: kdVcirc + the per-species kdMassProfile sums (kd2.c:458-496, 498-586) for a gas + dark +
+    star snapshot with three different masses — the cumulative mass is the reference's sequential fp32 sum in
+    sorted order, evaluated on the device; bit-exact against the oracle's literal walk (r^2 ties between different
+    masses are out of contract and do not occur in this seeded input)."""
+    s = synth.make_snapshot(40 ** 3, 30, seed=64, nmax=5000)
+    rng = np.random.default_rng(64)
+    ptype = rng.choice(np.array([1, 2, 4], np.uint8), size=s.n, p=[0.6, 0.3, 0.1])      # dark / gas / star bits
+    mass = np.where(ptype == 1, s.mass, np.where(ptype == 2, s.mass * np.float32(0.37), s.mass * np.float32(0.11))).astype(np.float32)
+    mark = (rng.random(s.n) < 0.05)
+    ptype = (ptype | (mark.astype(np.uint8) << 3)).astype(np.uint8)
+    thr = np.float32(120.0)
+    o = po.Oracle(s.pos, mass)
+    ref = o.so(s.centers, s.rgtp, thr, 8)
+    ok = ref["rvir"] > 0
+    assert ok.sum() > 15
+    g = api.SoGpu()
+    g.set_particles(s.pos, mass)
+    g.build_grid()
+    got = g.vcirc_species(s.centers[ok], ref["rvir"][ok], ref["mvir"][ok], ptype, masks=(1, 2, 4, 8))
+    g.close()
+    want = o.vcirc(s.centers[ok], ref["rvir"][ok], ref["mvir"][ok], 1.0, 8)
+    for k in ("vcirc", "rmass", "rmax", "vmax"):
+        assert got[k].tobytes() == want[k].tobytes(), k
+    for m, bit in enumerate((1, 2, 4, 8)):
+        w = o.vcirc(s.centers[ok], ref["rvir"][ok], ref["mvir"][ok], 1.0, 8, ptype_of=ptype, ptype_mask=bit)
+        assert got["profiles"][m].tobytes() == w["profile"].tobytes(), bit
+
+
 def test_vcirc_refuses_mixed_masses():
     s = synth.make_snapshot(20 ** 3, 4, seed=63, nmax=500)
     mass = np.full(s.n, s.mass, np.float32)
@@ -426,6 +455,47 @@ def test_device_tagging_of_conflict_free_groups(name):
         assert dirty.any() and changed.any()
     else:
         assert not dirty.any() and np.array_equal(igrp, t["igrp"])
+
+
+def _replay_case(s, centers, rgtp, gtp_mass, thr, nmem=8):
+    h = len(rgtp)
+    ids = np.arange(1, h + 1, dtype=np.int32)
+    o = po.Oracle(s.pos, s.mass)
+    ref = o.so(centers, rgtp, thr, nmem)
+    t = o.tag(ids, centers, gtp_mass, ref["rvir"].copy(), ref["mvir"].copy(), ref["member_offset"], ref["members"])
+    gpu = api.SoGpu()
+    gpu.set_particles(s.pos, s.mass)
+    gpu.build_grid()
+    gpu.keep_member_d2(True)
+    r = gpu.so(centers, rgtp, thr, nmem)
+    gpu.members(sorted=True)
+    dirty, _ = gpu.tag_members(ids, s.n)
+    order = [g for g in (po.indexx(gtp_mass) - 1) if dirty[g] and r["rvir"][g] > 0]     # kdSortMass order (kd2.c:843-861)
+    out = gpu.tag_replay(order, ids, centers, r["rvir"], r["mvir"], s.n)
+    gpu.close()
+    assert np.array_equal(out["igrp"], t["igrp"]), "PINIT.iGrp differs"
+    assert np.array_equal(out["nsub"], t["nsub"]) and np.array_equal(out["nign"], t["nign"])
+    assert out["rvir"].tobytes() == t["rvir"].tobytes() and out["mvir"].tobytes() == t["mvir"].tobytes()
+    assert (out["groups_removed"], out["groups_slurped"]) == (t["groups_removed"], t["groups_slurped"])
+    return t, dirty
+
+
+def test_ordered_conflict_replay_on_the_device_golden():
+    """sogpu_tag_replay (kdTagParticles incl. subsume / slurp / ignore and kdZeroGroup, kd2.c:617-720) on the
+    `conflict` golden: PINIT.iGrp / nSubsumed / nIgnored, the -10*index / -Mvir marks and both counters equal the
+    oracle's sequential replay, which is pinned to the reference's .sogrp."""
+    s, g = load_golden("conflict")
+    t, dirty = _replay_case(s, g["centers"], g["rgtp"], g["gtp_mass"], g["thr"], int(g["n_members"]))
+    assert np.array_equal(t["igrp"], g["igrp"])              # the reference binary's own .sogrp
+    assert t["groups_removed"] == int(g["groups_removed"]) and dirty.any()
+
+
+def test_ordered_conflict_replay_with_a_thousand_conflicts():
+    """A catalog built to collide: 1200 of 2500 halos sit next to a bigger neighbour (subsume, slurp and ignore
+    all occur, chains of events inside one group's walk included)."""
+    s = synth.make_snapshot(96 ** 3, 2500, seed=83, nmax=3000, overlap_pairs=1200)
+    t, dirty = _replay_case(s, s.centers, s.rgtp, s.gtp_mass, np.float32(200.0))
+    assert dirty.sum() >= 1000 and t["groups_removed"] > 100 and (t["nign"] > 0).sum() > 1000
 
 
 def test_unequal_masses_general_path():
