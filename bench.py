@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cfg1", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end steps (default min(steps, 10))")
+    ap.add_argument("--ab", action="append", default=[],
+                    help="debug: KEY=VALUE environment setting to time as a variant of the device-resident leg (repeatable)")
     ap.add_argument("--ref-scale", type=float, default=0.0,
                     help="--impl reference: fraction of the workload timed per step (default: 1/64 of configs[3])")
     return ap.parse_args()
@@ -562,6 +564,42 @@ def run_ours(args):
 
     ds.close()
     g.close()
+    # ---- debug: variants of the device-resident leg under other tuning switches (same inputs) ----------
+    ab = {}
+    for spec in args.ab:
+        keep = {}
+        for kv in spec.split("+"):
+            k_, v_ = kv.split("=", 1)
+            keep[k_] = os.environ.get(k_)
+            os.environ[k_] = v_
+        g2 = api.SoGpu(device=local, stream=stream.cuda_stream)
+        ds2 = parallel.DomainStep(g2, n, mass, recv_cap=rc_, stage_cap=sc_)
+
+        def step2():
+            ds2.step(d_centers.data_ptr(), d_rgtp.data_ptr(), h, N_BALLS, d_slice.data_ptr(), n_slice, a, thr, NMEM,
+                     d_out_n.data_ptr(), d_out_m.data_ptr())
+        for _ in range(warmup):
+            step2()
+            check_flags(ds2.result(), "variant warm-up")
+        barrier()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record(stream)
+        for _ in range(args.steps):
+            step2()
+        q1.record(stream)
+        barrier()
+        ab[spec] = allmax(q0.elapsed_time(q1)) / args.steps
+        check_flags(ds2.result(), "variant")
+        same = bool(torch.equal(torch.where(d_out_n == int(parallel.NOT_MINE), torch.zeros_like(d_out_n), d_out_n),
+                                torch.where(code == int(parallel.NOT_MINE), torch.zeros_like(code), code)) if world == 1 else True)
+        ab[spec + " same_n_delta"] = same
+        ds2.close()
+        g2.close()
+        for k_, v_ in keep.items():
+            if v_ is None:
+                os.environ.pop(k_, None)
+            else:
+                os.environ[k_] = v_
     del d_slice, pos_pin
     torch.cuda.empty_cache()
     if rank != 0:
@@ -594,6 +632,17 @@ def run_ours(args):
                       "frac": gbs / peak, "alg_bytes": 36.0 * n_recv, "ms_per_step": t_build,
                       "note": "SURVEY 8(d): 36 B per particle sorted for the whole build; particles = records this rank received"}
 
+    if args.scale == 1.0:
+        if roof_gather:
+            tg, src = traffic_for("k_so_query_fused", name)
+            if tg is not None:
+                roof_gather["traffic"], roof_gather["traffic_source"] = tg, src
+                roof_gather["traffic_over_16B_evals_min"] = tg / (16.0 * max(roof_gather["evals_min"], 1.0))
+        if roof_build:
+            parts = [traffic_for(k_, name)[0] for k_ in ("k_lvl_hist<0>", "k_lvl_hist<1>", "k_lvl_partition_rt<0, 0>",
+                                                            "k_lvl_partition_rt<1, 1>", "k_bucket_sort_sparse")]
+            if all(p_ is not None for p_ in parts):
+                roof_build["traffic"] = sum(parts)
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         frac = REF_SAMPLE.get(args.config, 1.0)
@@ -629,7 +678,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "roofline": roofline, "roofline_gather": roof_gather, "roofline_build": roof_build,
         "kernels": kernels, "ms_per_step_with_kernel_events": ms_profiled,
-        "cpu_baseline": cpu_baseline, "cfg1": cfg1, "setup_s": t_setup,
+        "cpu_baseline": cpu_baseline, "cfg1": cfg1, "setup_s": t_setup, "ab_ms_per_step": ab or None,
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if outgrown or not m_ok:

@@ -59,6 +59,9 @@ struct DomainState {
     int32_t nh;
     int64_t n_hint;
     bool routed;
+    bool direct;                        /* records are written straight into the receivers' buffers by the routing kernel
+                                         * (run of <= 128 per warp and destination, one remote reservation each) instead of
+                                         * being staged locally and pushed in bulk */
 };
 
 /* ---- ownership -------------------------------------------------------------------------------------- */
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(RT_THREADS, 2) k_route_stage(const __grid_cons
         if (R == 1) {
             unsigned long long base = 0ull;
             if (lane == 0) {
-                base = atomicAdd(a.cursor[0], (unsigned long long)wcnt);
+                base = atomicAdd_system(a.cursor[0], (unsigned long long)wcnt);
                 if (base + wcnt > a.cap[0]) { atomicOr(a.flags, a.flag_bit[0]); base = ~0ull; }
             }
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(RT_THREADS, 2) k_route_stage(const __grid_cons
                 if (!c) continue;
                 unsigned long long base = 0ull;
                 if (lane == 0) {
-                    base = atomicAdd(a.cursor[d], (unsigned long long)c);
+                    base = atomicAdd_system(a.cursor[d], (unsigned long long)c);
                     if (base + c > a.cap[d]) { atomicOr(a.flags, a.flag_bit[d]); base = ~0ull; }
                 }
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
@@ -516,6 +519,7 @@ extern "C" int sogpu_domain_open(sogpu_t *h, const sogpu_domain_cfg_t *cfg, void
     D->peer_ctrl[cfg->rank] = D->ctrl;
     D->connected = (R == 1);
     D->n_hint = std::max<int64_t>(cfg->recv_cap / 2, 1);
+    D->direct = getenv("SOGPU_DIRECT_PUSH") != nullptr && atoi(getenv("SOGPU_DIRECT_PUSH")) != 0;
     return SOGPU_OK;
 }
 
@@ -659,6 +663,9 @@ static int dom_stage_args(sogpu *h, StageArgs &a, const void *d_chunk, int64_t n
         if (d == D->cfg.rank) {
             a.dst[d] = D->recv[D->parity]; a.cursor[d] = &D->ctrl->cursor[D->parity];
             a.cap[d] = (unsigned long long)D->cfg.recv_cap; a.flag_bit[d] = 2u;
+        } else if (D->direct) {
+            a.dst[d] = D->peer_recv[D->parity][d]; a.cursor[d] = &D->peer_ctrl[d]->cursor[D->parity];
+            a.cap[d] = (unsigned long long)D->cfg.recv_cap; a.flag_bit[d] = 4u;
         } else {
             a.dst[d] = D->stage + (size_t)d * (size_t)D->cfg.stage_cap; a.cursor[d] = D->d_counts + d;
             a.cap[d] = (unsigned long long)D->cfg.stage_cap; a.flag_bit[d] = 1u;
@@ -724,11 +731,12 @@ extern "C" int sogpu_domain_push(sogpu_t *h, int barrier)
     if (R > 1) {
         PushArgs a;
         memset(&a, 0, sizeof(a));
+        const bool direct = D->direct;
         a.R = R; a.me = D->cfg.rank; a.parity = D->parity;
         for (int d = 0; d < R; ++d) { a.peer_ctrl[d] = D->peer_ctrl[d]; a.peer_recv[d] = D->peer_recv[D->parity][d]; }
         a.stage = D->stage; a.stage_cap = (unsigned long long)D->cfg.stage_cap; a.recv_cap = (unsigned long long)D->cfg.recv_cap;
         a.counts = D->d_counts; a.flags = D->d_flags;
-        {
+        if (!direct) {
             ProfScope p(h, KID_PUSH, 0.0, 2);
             k_push_reserve<<<1, 32, 0, s>>>(a);
             k_push_copy<<<dim3((unsigned)std::max(1, h->sm_count * 4 / R), (unsigned)R), 256, 0, s>>>(a);
@@ -774,7 +782,7 @@ extern "C" int sogpu_domain_solve(sogpu_t *h, float thr, int32_t nM, void *d_out
     if (rc) return rc;
     CU(cudaMemsetAsync(h->d_out_n, 0x80, (size_t)nh * sizeof(int32_t), s));
     CU(cudaMemsetAsync(h->d_out_m, 0x80, (size_t)nh * sizeof(float), s));
-    h->q_owner = D->d_owner; h->q_me = D->cfg.rank;
+    h->q_owner = D->d_owner; h->q_me = D->cfg.rank; h->q_ranks = D->cfg.n_ranks;
     rc = run_query(h, h->d_centers, h->d_rgtp, nh, thr, nM);
     h->q_owner = nullptr;
     if (rc) return rc;

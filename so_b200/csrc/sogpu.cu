@@ -364,6 +364,27 @@ __device__ __forceinline__ float mt_eval(const MassTableS &mt, uint32_t k)
     return so_mass_prefix_eval(mt.k0, mt.s0, mt.inc, mt.n, k);
 }
 
+/* Cheap fp32 screening of rhoEnclosed(S[k], r2) < thr (kd2.c:588-593): S[k] differs from k*m by at most
+ * k * 2^-24 relative (k roundings of at most half an ulp of the running sum each), and the fp32 evaluation of
+ * m k / (C r2^1.5) is good to a few ulp.  Outside a band of (1e-5 + 2.4e-7 k) around the threshold the answer of
+ * the exact mixed-precision expression is certain; only inside it the mass table and the fp64 sqrt / div are
+ * evaluated.  Returns 0 = certainly not below, 1 = certainly below, 2 = undecided. */
+__device__ __forceinline__ int rho_screen(const MassTableS &mt, uint32_t k, float r2, float thr)
+{
+    if (k >= (1u << 22) || !(r2 > 0.0f)) return 2;
+    const float kf = (float)k;
+    const float eps = 1.0e-5f + 2.4e-7f * kf;
+    const float rho = __fdividef(kf * mt.m, 4.18879f * r2 * sqrtf(r2));
+    if (rho > thr * (1.0f + eps)) return 0;
+    if (rho < thr * (1.0f - eps)) return 1;
+    return 2;
+}
+__device__ __forceinline__ bool rho_below(const MassTableS &mt, uint32_t k, float r2, float thr)
+{
+    const int s = rho_screen(mt, k, r2, thr);
+    return s == 2 ? so_rho_below(mt_eval(mt, k), r2, thr) != 0 : s == 1;
+}
+
 /* ============================================================================================
  * geometry: exact r^2 and the row segments that overlap a ball
  * ============================================================================================ */
@@ -777,8 +798,9 @@ __device__ __forceinline__ int find_candidate(const uint32_t *cum, const Level &
         uint32_t r0 = lv.rank0 + c0, r1 = lv.rank0 + c1;
         if (r1 <= jmin) continue;
         uint32_t klo = r0 > jmin ? r0 : jmin;
-        float mass_lo = mt_eval(mt, klo + 1u);
         float r2hi = __uint_as_float(bin_hi(lv, b));
+        if (rho_screen(mt, klo + 1u, r2hi, thr) == 0) continue;      /* even the densest case of this bin is clearly above */
+        float mass_lo = mt_eval(mt, klo + 1u);
         if (!so_surely_not_below(mass_lo, r2hi, thr)) { best = b; break; }
     }
     return gmin<NT>(best, tmp, tid);
@@ -1130,9 +1152,7 @@ __device__ void so_halo(const GridDev &g, const MassTableS &mt, GroupSmem<NT> &s
                 for (uint32_t i = tid; i < wn; i += NT) {
                     uint32_t k = rank_first + i;
                     uint8_t fl = 0;
-                    if (k >= jmin)
-                        fl = (uint8_t)so_rho_below(mt_eval(mt, k + 1u),
-                                                   __uint_as_float((uint32_t)(sm.wkey[i] >> 32)), thr);
+                    if (k >= jmin) fl = (uint8_t)rho_below(mt, k + 1u, __uint_as_float((uint32_t)(sm.wkey[i] >> 32)), thr);
                     sm.wflag[i] = fl;
                 }
                 gsync<NT>();
@@ -2679,7 +2699,7 @@ struct sogpu {
     const uint32_t *d_n_dev;         /* NULL: h->n is exact */
     int64_t n_hint;                  /* expected count: sizes the launch and the bucket table */
     const unsigned char *q_owner;    /* query only the halos with q_owner[h] == q_me (NULL: all) */
-    int q_me;
+    int q_me, q_ranks;
     struct DomainState *dom;         /* sogpu_domain_open */
 };
 
@@ -2764,7 +2784,9 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     if (const char *e = getenv("SOGPU_SCAN1_MAX")) h->scan1_max = (size_t)atoll(e);
     if (const char *e = getenv("SOGPU_TMA")) h->use_tma = atoi(e) != 0;
     if (const char *e = getenv("SOGPU_MASK_RMIN")) h->mask_rmin_cells = atof(e);
-    h->cls_small_max = 256.0f; h->cls_huge_min = 32768.0f;   /* warp class: balls that fit its 384 staged keys */
+    h->cls_small_max = 256.0f; h->cls_huge_min = 32768.0f;   /* warp class: balls that fit its 384 staged keys; above 32768: a
+                                                              * 1024-thread CTA per halo, beside the fused kernel (8192 was
+                                                              * measured 5 % slower at 1024^3: the big CTAs crowd out the fused ones) */
     h->emit_small_max = 2048; h->emit_huge_min = 4096;
     if (const char *e = getenv("SOGPU_SMALL_MAX")) h->cls_small_max = (float)atof(e);
     if (const char *e = getenv("SOGPU_HUGE_MIN")) h->cls_huge_min = (float)atof(e);
@@ -3534,7 +3556,11 @@ static int run_query(sogpu *h, const float *d_centers, const float *d_rgtp, int3
 
     /* counters: 0 small_n 1 big_n 2 work_small 3 work_big 4 flags 5 esmall_n 6 ebig_n 7 work_es 8 work_eb
      *           13 huge_n 14 work_huge 15 ehuge_n 16 work_ehuge   (9-12: general path) */
-    const float small_max = h->cls_small_max, huge_min = h->cls_huge_min;
+    /* few halos per GPU (domain steps over several ranks): the step ends with the tail of the largest halos, so more
+     * of them get a 1024-thread CTA of their own beside the fused kernel (measured at 1024^3: 8 GPUs -6 %, 1 GPU +1 %) */
+    const int per_rank = h->q_owner ? nh / std::max(1, h->q_ranks) : nh;
+    const float small_max = h->cls_small_max,
+                huge_min = (!getenv("SOGPU_HUGE_MIN") && per_rank < 25000) ? std::min(h->cls_huge_min, 8192.0f) : h->cls_huge_min;
     {
         ProfScope p(h, KID_CLASSIFY);
         k_classify<<<(nh + 255) / 256, 256, 0, s>>>(d_rgtp, nh, thr, h->d_mt, small_max, huge_min, h->d_small,

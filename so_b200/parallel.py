@@ -562,3 +562,46 @@ class VirtualDomainStep:
         for g in self.gs:
             g.domain_close()
             g.close()
+
+
+def owner_numpy(centers, rgtp, n_total, n_ranks, period=(1.0, 1.0, 1.0), center=(0.0, 0.0, 0.0)):
+    """The halo ownership of a domain step, restated in numpy operation for operation (k_assign_hist / _scan /
+    _owner in so_b200/csrc/domain_step.cuh: 32^3 bins along a tiled curve, integer costs, cut at equal cost).
+    Every rank of a domain step computes exactly this on its device; host-side planning and the CPU tests use it."""
+    centers = np.asarray(centers, np.float32).reshape(-1, 3)
+    rgtp = np.asarray(rgtp, np.float32)
+    h = len(rgtp)
+    if n_ranks <= 1:
+        return np.zeros(h, np.uint8)
+    L = np.asarray(period, np.float32).astype(np.float64)
+    g0 = (np.asarray(center, np.float32).astype(np.float64) - 0.5 * L).astype(np.float32).astype(np.float64)
+    t = (centers.astype(np.float64) - g0) / L
+    t -= np.floor(t)
+    c = np.clip((t * 32.0).astype(np.int64), 0, 31)
+    hi, lo = c >> 3, c & 7
+    key = ((((hi[:, 2] * 4 + hi[:, 1]) * 4 + hi[:, 0]) << 9) | (lo[:, 2] << 6) | (lo[:, 1] << 3) | lo[:, 0]).astype(np.int64)
+    nbar = float(n_total) / float(np.prod(L))
+    r = 1.2 * 1.25 * rgtp.astype(np.float64)
+    cost = (200.0 * nbar * 4.18879020478639 * r * r * r * 0.6 + 64.0).astype(np.uint64)
+    bins = np.zeros(32768 + 1, np.uint64)
+    np.add.at(bins, key, cost)
+    excl = np.concatenate([[0], np.cumsum(bins[:-1], dtype=np.uint64)]).astype(np.uint64)   # excl[b], excl[32768] = total
+    total = int(excl[32768])
+    lo_, hi_ = excl[key].astype(object), excl[key + 1].astype(object)
+    mid = lo_ + (hi_ - lo_) // 2
+    own = np.array([min(n_ranks - 1, (int(m) * n_ranks) // total) if total else 0 for m in mid], np.uint8)
+    return own
+
+
+def merge_owned(code, m, group=None):
+    """Per-halo results of a domain step (torch tensors over the WHOLE catalog: N_Delta / code and M_Delta for the
+    halos this rank owns, the NOT_MINE pattern elsewhere) -> the complete arrays on every rank.  Every halo is owned
+    by exactly one rank, so a MAX reduction over (code, mass-or-minus-infinity) merges them; works on any backend."""
+    import torch
+    import torch.distributed as dist
+    code = code.clone()
+    mm = torch.where(code == int(NOT_MINE), torch.full_like(m, -float("inf")), m)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(code, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(mm, op=dist.ReduceOp.MAX, group=group)
+    return code, mm

@@ -203,3 +203,69 @@ def test_domain_run_protocol_over_gloo(tmp_path, world):
             b = ref["members"][ref["member_offset"][i]:ref["member_offset"][i + 1]]
             assert np.array_equal(np.sort(a), np.sort(b))
     assert seen.all()
+
+
+def _worker_domain_step(rank, world, port, seed, out_dir):
+    """The host side of the domain step on CPU ranks: ownership restated in numpy (every rank computes the same
+    one, no exchange), each rank solves only the halos it owns over only the particles routed to it, the
+    results are merged with the NOT_MINE convention by MAX reductions (gloo)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import pyoracle as po
+        s = synth.make_snapshot(28 ** 3, 60, seed=seed, nmax=1500)
+        owner = parallel.owner_numpy(s.centers, s.rgtp, s.n, world)
+        mine = np.nonzero(owner == rank)[0]
+        # routing stand-in: the particles inside the cubes this rank's halos can reach after 4 schedule balls
+        keep = np.zeros(s.n, bool)
+        for i in mine:
+            w = float(s.rgtp[i]) * 1.2 ** 4 * 1.05 + 2.0 / 32
+            d = s.pos - s.centers[i]
+            d -= np.rint(d)
+            keep |= (np.abs(d) < w).all(axis=1)
+        idx = np.nonzero(keep)[0]
+        code = torch.full((s.h,), int(parallel.NOT_MINE), dtype=torch.int32)
+        m = torch.full((s.h,), float("nan"), dtype=torch.float32)
+        if len(mine):
+            o = po.Oracle(s.pos[idx], s.mass)
+            res = o.so(s.centers[mine], s.rgtp[mine], np.float32(200.0), 8, want_members=False)
+            code[torch.from_numpy(mine)] = torch.from_numpy(np.where(res["ndelta"] > 0, res["ndelta"], res["rvir"].astype(np.int32)))
+            m[torch.from_numpy(mine)] = torch.from_numpy(res["mvir"])
+        code, m = parallel.merge_owned(code, m)
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), code=code.numpy(), m=m.numpy(), owner=owner)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_domain_step_host_logic_on_cpu_ranks(tmp_path, world):
+    from oracle import pyoracle as po
+    seed = 700 + world
+    port = _free_port()
+    mp.spawn(_worker_domain_step, args=(world, port, seed, str(tmp_path)), nprocs=world, join=True)
+    s = synth.make_snapshot(28 ** 3, 60, seed=seed, nmax=1500)
+    ref = po.Oracle(s.pos, s.mass).so(s.centers, s.rgtp, np.float32(200.0), 8, want_members=False)
+    want = np.where(ref["ndelta"] > 0, ref["ndelta"], ref["rvir"].astype(np.int32))
+    owners = None
+    for r in range(world):
+        z = np.load(str(tmp_path / ("rank%d.npz" % r)))
+        assert np.array_equal(z["code"], want)
+        ok = want > 0
+        assert z["m"][ok].tobytes() == ref["mvir"][ok].tobytes()
+        owners = z["owner"] if owners is None else owners
+        assert np.array_equal(z["owner"], owners)            # every rank derived the same ownership
+    assert len(np.unique(owners)) == world
+
+
+def test_owner_numpy_is_balanced_and_compact():
+    s = synth.make_snapshot(64 ** 3, 400, seed=9, nmax=300)
+    for world in (1, 2, 4, 8, 16):
+        own = parallel.owner_numpy(s.centers, s.rgtp, s.n, world)
+        assert own.min() == 0 and own.max() == world - 1
+        cost = parallel.halo_cost(s.rgtp, s.n, 1.0)
+        load = np.array([cost[own == r].sum() for r in range(world)])
+        assert load.max() < 1.6 * cost.sum() / world + cost.max()
+    assert parallel.flags_text(0) == "ok" and "receive" in parallel.flags_text(2)
+    rc, sc = parallel.default_caps(1 << 30, 8)
+    assert rc > (1 << 30) * 0.3 / 8 and sc > 0 and parallel.default_caps(1000, 1)[1] == 0

@@ -667,6 +667,8 @@ def test_domain_step_matches_single_grid(n_ranks, n_balls):
         run.close()
     _check_domain_step(out, ref, n_ranks)
     assert sum(out["n_recv"][0]) < n_ranks * s.n
+    # the ownership every rank derived on its device == the numpy restatement the CPU tests use
+    assert np.array_equal(out["owner"], parallel.owner_numpy(centers, rgtp, s.n, n_ranks))
 
 
 @pytest.mark.gpu
