@@ -305,6 +305,15 @@ int sogpu_domain_push(sogpu_t *h, int barrier);
 int sogpu_domain_solve(sogpu_t *h, float rho_thr, int32_t n_members, void *d_out_n, void *d_out_m);
 int sogpu_domain_result(sogpu_t *h, int64_t *n_recv, int64_t *n_sent, uint32_t *flags, unsigned char *owner);
 int sogpu_domain_close(sogpu_t *h);
+/* Helpers of a one-process, several-devices host program (`so -gpus N`, so_b200/host/kd_multi.c):
+ *   sogpu_particles_device  the handle's particle array (device float4 {x,y,z,m}) and its length
+ *   sogpu_copy              synchronous copy on the handle's device: kind 0 host->device, 1 device->host,
+ *                           2 device->device (also across devices with peer access or through the driver)
+ *   sogpu_set_members       installs CSR member lists (sorted by (r^2, index), e.g. merged from several devices)
+ *                           as this handle's "last result" for sogpu_tag_members / _tag_replay / _vcm */
+int sogpu_particles_device(sogpu_t *h, void **d_xyzm, int64_t *n);
+int sogpu_copy(sogpu_t *h, void *dst, const void *src, size_t bytes, int kind);
+int sogpu_set_members(sogpu_t *h, const int64_t *offsets, const int32_t *members, const float *d2, int32_t nh);
 
 /* ---- introspection --------------------------------------------------------------------------- */
 

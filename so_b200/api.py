@@ -34,6 +34,7 @@ SYMBOLS = [
     "sogpu_domain_open", "sogpu_domain_connect", "sogpu_enable_peer_access", "sogpu_domain_begin",
     "sogpu_domain_route", "sogpu_domain_route_host", "sogpu_domain_push", "sogpu_domain_solve",
     "sogpu_domain_result", "sogpu_domain_close", "sogpu_domain_pointers", "sogpu_vcirc_species", "sogpu_tag_replay",
+    "sogpu_particles_device", "sogpu_copy", "sogpu_set_members",
 ]
 
 

@@ -814,3 +814,65 @@ extern "C" int sogpu_domain_result(sogpu_t *h, int64_t *n_recv, int64_t *n_sent,
     if (!(f & 2u) && c[3 * ROUTE_MAXR] > 0) D->n_hint = (int64_t)c[3 * ROUTE_MAXR];
     return SOGPU_OK;
 }
+
+/* ---- small helpers for a one-process, several-devices host program (so -gpus N) ---------------------------- */
+
+/* the handle's particle array as set by the last sogpu_set_particles_* / ingest (device float4 {x,y,z,m}) */
+extern "C" int sogpu_particles_device(sogpu_t *h, void **d_xyzm, int64_t *n)
+{
+    if (!h || !d_xyzm || !n) return set_err(SOGPU_ERR_ARG, "sogpu_particles_device: NULL argument");
+    *d_xyzm = (void *)h->d_in;
+    *n = h->n;
+    return SOGPU_OK;
+}
+
+/* synchronous copies on the handle's device / stream: host <-> device, and from another handle's device */
+extern "C" int sogpu_copy(sogpu_t *h, void *dst, const void *src, size_t bytes, int kind)
+{
+    if (!h || (bytes && (!dst || !src)) || kind < 0 || kind > 2) return set_err(SOGPU_ERR_ARG, "sogpu_copy: bad argument");
+    CU(cudaSetDevice(h->device));
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDefault;
+    if (bytes) CU(cudaMemcpyAsync(dst, src, bytes, k, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return SOGPU_OK;
+}
+
+/* make CSR member lists (ascending (r^2, index) per group, e.g. merged from several devices) the "last result" of
+ * this handle, so that sogpu_tag_members / sogpu_tag_replay / sogpu_vcm work on them */
+extern "C" int sogpu_set_members(sogpu_t *h, const int64_t *offsets, const int32_t *members, const float *d2, int32_t nh)
+{
+    if (!h || !offsets || nh <= 0 || offsets[0] != 0 || (offsets[nh] > 0 && (!members || !d2)))
+        return set_err(SOGPU_ERR_ARG, "sogpu_set_members: bad argument");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_query(h, nh);
+    if (rc) return rc;
+    const unsigned long long tot = (unsigned long long)offsets[nh];
+    if (tot > h->member_cap) {
+        cudaFree(h->d_members); cudaFree(h->d_md2); cudaFree(h->d_members2); cudaFree(h->d_md2_2);
+        h->d_members = nullptr; h->d_md2 = nullptr; h->d_members2 = nullptr; h->d_md2_2 = nullptr;
+        h->member_cap = tot + tot / 16 + 1024;
+        CU(cudaMalloc(&h->d_members, (size_t)h->member_cap * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_md2, (size_t)h->member_cap * sizeof(float)));
+    }
+    cudaStream_t s = h->stream;
+    CU(cudaMemcpyAsync(h->d_out_off, offsets, ((size_t)nh + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    if (tot) {
+        CU(cudaMemcpyAsync(h->d_members, members, (size_t)tot * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(h->d_md2, d2, (size_t)tot * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    std::vector<int32_t> nd((size_t)nh);
+    for (int32_t i = 0; i < nh; ++i) nd[i] = (int32_t)(offsets[i + 1] - offsets[i]);
+    CU(cudaMemcpyAsync(h->d_out_n, nd.data(), (size_t)nh * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    unsigned long long u4[4] = {tot, 0ull, 0ull, 0ull};
+    CU(cudaMemcpyAsync(h->d_u64, u4, sizeof(u4), cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(h->d_counters, 0, 24 * sizeof(uint32_t), s));
+    CU(cudaStreamSynchronize(s));
+    h->last_h = nh;
+    h->have_result = true;
+    h->members_csr = true;
+    h->members_sorted = true;
+    h->want_d2 = true;
+    h->member_overflow = false;
+    return SOGPU_OK;
+}
+

@@ -79,6 +79,7 @@ typedef struct kdContext {
     int uSecond, uMicro;
     sogpu_t *gpu;
     int iDevice;
+    int nGpus;             /* -gpus N: kdBuildTree + kdRvir over N devices of this process (kd_multi.c) */
     int bIngested;         /* kdReadTipsy streamed the particles to the device already */
     int bSkipGrpArray;     /* main() sets these when nothing will print the per-particle tags (.sogrp) ... */
     int bSkipVcm;          /* ... or the centre-of-mass velocities (.sogtp)                                  */
@@ -101,6 +102,8 @@ void kdSO(KD, float rhovir, int nSmooth);
 void kdWriteProfile(KD, char *achOutFileBase, time_t, FILE *, int ptype);
 void kdWriteOut(KD, FILE *);
 int kdBuildTree(KD);
+int kdRvirSeveralDevices(KD kd, const float *centers, const float *rgtp, int h, float thr, float *rvir, float *mvir,
+                         int32_t *ndelta, int64_t *off, int32_t **mem, float **d2);
 sogpu_t *kdGpu(KD);                              /* the device handle, created on first use */
 void kdPhase(const char *name, double *t);       /* SO_TIMING=1: phase wall-clock on stderr */
 void kdFinish(KD);

@@ -394,13 +394,27 @@ void kdSO(KD kd, float rhovir, int nSmooth)
     /* the hot path: R_Delta, M_Delta, N_Delta and the member lists of every group */
     if (sogpu_keep_member_d2(kd->gpu, 1)) die_gpu("kdSO");
     phase("kdSO setup", &tp);
-    if (sogpu_so(kd->gpu, centers, rgtp, h, rhovir, kd->nMembers, rvir, mvir, ndelta)) die_gpu("kdSO (sogpu_so)");
-    phase("sogpu_so (build+query)", &tp);
-    if (sogpu_members(kd->gpu, off, &lib_mem, &lib_d2, 1)) die_gpu("kdSO (sogpu_members)");
-    phase("member lists (sorted)", &tp);
-    mem = (int32_t *)malloc((size_t)(off[h] > 0 ? off[h] : 1) * sizeof(int32_t));
-    assert(mem != NULL);
-    memcpy(mem, lib_mem, (size_t)off[h] * sizeof(int32_t));
+    {
+        int several = kd->nGpus > 1;
+        if (several) {               /* the domain step needs one particle mass (it ships {x,y,z,index} records) */
+            for (i = 1; i < kd->nParticles && several; ++i) several = kd->p.fMass[i] == kd->p.fMass[0];
+            if (!several) fprintf(stderr, "so: -gpus %d ignored: particles of unequal mass run on one device\n", kd->nGpus);
+        }
+        if (several) {
+            float *md2 = NULL;
+            kdRvirSeveralDevices(kd, centers, rgtp, h, rhovir, rvir, mvir, ndelta, off, &mem, &md2);
+            free(md2);
+            phase("kdBuildTree + kdRvir over several devices", &tp);
+        } else {
+            if (sogpu_so(kd->gpu, centers, rgtp, h, rhovir, kd->nMembers, rvir, mvir, ndelta)) die_gpu("kdSO (sogpu_so)");
+            phase("sogpu_so (build+query)", &tp);
+            if (sogpu_members(kd->gpu, off, &lib_mem, &lib_d2, 1)) die_gpu("kdSO (sogpu_members)");
+            phase("member lists (sorted)", &tp);
+            mem = (int32_t *)malloc((size_t)(off[h] > 0 ? off[h] : 1) * sizeof(int32_t));
+            assert(mem != NULL);
+            memcpy(mem, lib_mem, (size_t)off[h] * sizeof(int32_t));
+        }
+    }
     if (sogpu_get_stats(kd->gpu, &st) == 0) {
         kd->nEvals = st.last_evals;
         kd->nMembersTotal = st.last_members;

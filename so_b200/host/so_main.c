@@ -49,7 +49,7 @@ static void usage(void)
           "      [-O <fOmega0>]  [-L]  [-z <fRedshift>]\n"
           "      [-p <xyzPeriod>]  [-c <xyzCenter>]\n"
           "      [-cx <xCenter>]  [-cy <yCenter>]  [-cz <zCenter>]\n"
-          "      [-u <fMassUnit> <fMpcUnit>]   [-gpu <device>] [-bench-json <file>]\n\n"
+          "      [-u <fMassUnit> <fMpcUnit>]   [-gpu <device>] [-gpus <N devices>] [-bench-json <file>]\n\n"
           "  B200 build of the spherical-overdensity finder: for every group of the .gtp catalog finds the\n"
           "  smallest radius at which the mean enclosed density drops below <fThreshold> (x Omega0), and\n"
           "  writes <outfilebase>.sovcirc (+ .sogrp/.sogtp/.sosub/.soign/.sodark... on request).\n"
@@ -74,7 +74,7 @@ int main(int argc, char **argv)
     int i, j, sec, usec;
     int bThreshold = 0, bStandard = 0, bLambda = 0, bPeriodic = 1, bRedshift = 0;
     int bDark = 0, bGas = 0, bStar = 0, bMark = 0, bGrp = 0, bGtp = 0, bPot = 0, bSubsumed = 0, bIgnored = 0;
-    int nBucket = 16, nMembers = 8, nSmooth = 1028, iDevice = -1;
+    int nBucket = 16, nMembers = 8, nSmooth = 1028, iDevice = -1, nGpus = 1;
     float fOmega = 1.0f, fLambda = 0.0f, fRedshift = -9.9999f, fThreshold = 0.0f, fMinMass = 0.0f;
     float fPeriod[3] = {1.0f, 1.0f, 1.0f}, fCenter[3] = {0.0f, 0.0f, 0.0f};
     float fMassUnit = -9.9f, fMpcUnit = -9.9f, G = 1.0f, H0 = 2.8944f;
@@ -121,6 +121,7 @@ int main(int argc, char **argv)
         else if (!strcmp(a, "-star")) bStar = 1;
         else if (!strcmp(a, "-all")) bDark = bGas = bStar = 1;
         else if (!strcmp(a, "-gpu")) iDevice = atoi(next_arg(&i, argc, argv));
+        else if (!strcmp(a, "-gpus")) { nGpus = atoi(next_arg(&i, argc, argv)); if (nGpus < 1 || nGpus > 16) usage(); }
         else if (!strcmp(a, "-bench-json")) achBenchJson = next_arg(&i, argc, argv);
         else usage();
     }
@@ -130,6 +131,7 @@ int main(int argc, char **argv)
 
     kdInit(&kd, nBucket, fPeriod, fCenter, 0, nMembers, bPeriodic, bDark, bGas, bStar, bMark, bPot);
     kd->iDevice = iDevice;
+    kd->nGpus = nGpus;
     kd->bSkipGrpArray = 0;                            /* PINIT.iGrp is read by kdWriteArray AND by kdOutStats (kd2.c:1360), which always runs */
     kd->bSkipVcm = !bGtp;                             /* GRPNODE.vcm is only read by kdWriteGTP */
     kdGpu(kd);                                        /* the snapshot is streamed to the device as it is read */

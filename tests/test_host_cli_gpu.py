@@ -252,3 +252,61 @@ def test_cli_virial_threshold_default_live(tmp_path, cosmo):
     a = np.frombuffer(open(outs["ours"] + ".sogtp", "rb").read(), np.uint8)[32:].view(np.float32).reshape(-1, 11)
     b = np.frombuffer(open(outs["ref"] + ".sogtp", "rb").read(), np.uint8)[32:].view(np.float32).reshape(-1, 11)
     assert a[:, [0, 1, 2, 3, 8, 9]].tobytes() == b[:, [0, 1, 2, 3, 8, 9]].tobytes()
+
+
+def _n_devices():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("n_gpus", [2, 4])
+def test_cli_several_devices_give_identical_files(tmp_path, n_gpus):
+    """`so -gpus N` (so_b200/host/kd_multi.c: one host thread per device, the C-ABI's domain step, member lists
+    merged by owner): every output file is byte-identical to the one-device run.  Subsumption conflicts included."""
+    if _n_devices() < n_gpus:
+        pytest.skip("needs %d devices" % n_gpus)
+    s = synth.make_snapshot(64 ** 3, 400, seed=91, nmax=3000, overlap_pairs=30)
+    flags = ["-delta", "200", "-grp", "-gtp", "-subsumed", "-ignored", "-all"]
+    outs = {}
+    for who, extra in (("one", []), ("several", ["-gpus", str(n_gpus)])):
+        d = tmp_path / who
+        d.mkdir()
+        _, _, out, err = run_so(str(d), s, s.centers, s.rgtp, s.gtp_mass, flags + extra)
+        outs[who] = out
+        if extra:
+            assert "over several devices" in err or "SO CPU Time" in err
+    for ext in (".sogrp", ".sosub", ".soign", ".sovcirc", ".sodark", ".sogtp"):
+        a, b = open(outs["one"] + ext, "rb").read(), open(outs["several"] + ext, "rb").read()
+        if ext == ".sogtp":
+            a, b = a[:28] + a[32:], b[:28] + b[32:]                  # 28..31: struct padding
+        else:                                                        # header: time of the run, paths of the files
+            a, b = (b"\n".join(l for l in x.split(b"\n") if not l.startswith(b"# Run on")) for x in (a, b))
+            a, b = a.replace(str(tmp_path / "one").encode(), b"."), b.replace(str(tmp_path / "several").encode(), b".")
+        assert a == b, ext
+
+
+def _no_date(path):
+    return b"\n".join(l for l in open(path, "rb").read().split(b"\n") if not l.startswith(b"# Run on"))
+
+
+def test_cli_gpus_flag_fallbacks(tmp_path):
+    """-gpus 1 is the default path; -gpus N on a snapshot with particles of unequal mass runs on one device (the
+    domain step ships {x, y, z, index} records) and says so."""
+    s = synth.make_snapshot(32 ** 3, 20, seed=92, nmax=1500)
+    _, _, out, _ = run_so(str(tmp_path), s, s.centers, s.rgtp, s.gtp_mass, ["-delta", "200", "-gtp"])
+    a = _no_date(out + ".sovcirc")
+    _, _, out, _ = run_so(str(tmp_path), s, s.centers, s.rgtp, s.gtp_mass, ["-delta", "200", "-gtp", "-gpus", "1"])
+    assert a == _no_date(out + ".sovcirc")
+    mass = np.full(s.n, s.mass, np.float32)
+    mass[::7] *= np.float32(1.5)
+    snap, gtp = str(tmp_path / "m.tipsy"), str(tmp_path / "m.gtp")
+    tipsy.write_tipsy(snap, s.time, dark=tipsy.dark_from_arrays(s.pos, mass))
+    tipsy.write_gtp(gtp, s.time, s.centers, s.rgtp, s.gtp_mass)
+    res = {}
+    for extra in ([], ["-gpus", "2"]):
+        with open(snap, "rb") as fin:
+            r = subprocess.run([SO, "-i", gtp, "-o", str(tmp_path / "m"), "-delta", "200", "-gtp"] + extra, stdin=fin,
+                               capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[len(extra)] = (_no_date(str(tmp_path / "m.sovcirc")), r.stderr)
+    assert res[0][0] == res[2][0] and "unequal mass" in res[2][1]
