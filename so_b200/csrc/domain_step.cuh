@@ -40,16 +40,17 @@ struct DomainState {
     float4 *recv[2];
     DomCtrl *ctrl;
     float4 *stage;                      /* n_ranks x stage_cap records (unused slot: own rank) */
+    float4 *hits;                       /* several ranks: what k_route_stage keeps of the slice (recv_cap records), input of k_route_split */
     float4 *peer_recv[2][ROUTE_MAXR];
     DomCtrl *peer_ctrl[ROUTE_MAXR];
     bool connected;
-    unsigned long long *d_counts;       /* [0..R) staged, [R..2R) push base, [2R..3R) push count, [3R] received (clamped) */
+    unsigned long long *d_counts;       /* [0..R) staged, [R..2R) push base, [2R..3R) push count, [3 MAXR] received (clamped), [3 MAXR + 1] hits */
     uint32_t *d_flags;                  /* bit0 staging overflow, bit1 own receive overflow, bit2 peer receive overflow, bit3 barrier timeout */
     uint32_t *d_nrecv32;
     unsigned char *d_owner;
     int32_t owner_cap;
     unsigned short *d_table;            /* destination ranks per coarse cell (2^(3 mb) entries)                */
-    uint32_t *d_any, *d_super, *d_mymask; /* bit per coarse cell: somebody's / (64^3 pre-filter) / this rank's  */
+    uint32_t *d_any, *d_super, *d_mymask; /* bit per coarse cell: somebody's / (pre-filter, per block) / this rank's */
     bool marked;                        /* the tables hold the marks of the previous step's catalog            */
     int marked_balls;
     int32_t marked_nh;
@@ -150,7 +151,26 @@ __global__ void __launch_bounds__(256) k_assign_owner(GridDev g, const float *__
 }
 
 /* ---- destination table -------------------------------------------------------------------------------- */
-#define DOM_SUPER_LOG 6       /* 64^3-bit pre-filter: 32 KB, stays in every SM's L1 during the routing pass */
+/* pre-filter of the routing pass: one bit per block of 8 x 4 x 4 coarse cells (64 x 128 x 128 blocks at the 512^3
+ * mask resolution: 128 KB, one copy in the shared memory of every SM).  The first version (64^3 blocks, 32 KB)
+ * let 60 % of a uniform background through to the bitmap lookup in L2; this one 26 % (profiles/r2_experiments.md). */
+#define DOM_SUPER_LOGX 6
+#define DOM_SUPER_LOGY 7
+#define DOM_SUPER_LOGZ 7
+struct SuperGeom { int bx, by, bz, sx, sy, sz; };       /* log2 blocks per axis, log2 coarse cells per block */
+__host__ __device__ __forceinline__ SuperGeom super_geom(int mb)
+{
+    SuperGeom q;
+    q.bx = mb < DOM_SUPER_LOGX ? mb : DOM_SUPER_LOGX; q.by = mb < DOM_SUPER_LOGY ? mb : DOM_SUPER_LOGY;
+    q.bz = mb < DOM_SUPER_LOGZ ? mb : DOM_SUPER_LOGZ;
+    q.sx = mb - q.bx; q.sy = mb - q.by; q.sz = mb - q.bz;
+    return q;
+}
+static inline size_t super_words(int mb)                 /* 32-bit words, a multiple of 4 */
+{
+    const SuperGeom q = super_geom(mb);
+    return ((((size_t)1 << (q.bx + q.by + q.bz)) / 32) + 4) & ~(size_t)3;
+}
 
 /* run of `len` bits starting at bit `b0` of a bitmap: OR it in (or clear the words) — at most len/32 + 2 operations */
 __device__ __forceinline__ void bit_run(uint32_t *map, uint32_t b0, uint32_t len, int clear)
@@ -186,7 +206,7 @@ __global__ void __launch_bounds__(256) k_mark_table(GridDev g, const float *__re
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) / MARK_LANES, nw = (gridDim.x * blockDim.x) / MARK_LANES;
     const float root = so_root_period(g.L[0], g.L[1], g.L[2]);
     const int nm = 1 << g.mb, nm1 = nm - 1;
-    const int sb = min(g.mb, DOM_SUPER_LOG), ss = g.mb - sb;
+    const SuperGeom sg = super_geom(g.mb);
     for (int h = wid; h < nh; h += nw) {
         float ball = rgtp[h];
         for (int k = 0; k < n_balls && (double)ball < 0.25 * (double)root; ++k) ball = so_next_ball(ball);
@@ -201,14 +221,13 @@ __global__ void __launch_bounds__(256) k_mark_table(GridDev g, const float *__re
         const int xa = x0 & nm1;                                   /* the row's x-range, split where it wraps */
         const int n0 = min(nx, nm - xa), n1 = nx - n0;
         if (!clear) {
-            /* the 64^3 pre-filter once per halo (not per row): the cube covers a handful of its cells */
-            const int sx0 = x0 >> ss, sx1 = (x0 + nx - 1) >> ss, sy0 = y0 >> ss, sy1 = (y0 + ny - 1) >> ss;
-            const int sz0 = z0 >> ss, sz1 = (z0 + nz - 1) >> ss, snx = sx1 - sx0 + 1, sny = sy1 - sy0 + 1, snz = sz1 - sz0 + 1;
-            const int sm1 = (1 << sb) - 1;
+            /* the pre-filter once per halo (not per row): the cube covers a handful of its blocks */
+            const int sx0 = x0 >> sg.sx, sx1 = (x0 + nx - 1) >> sg.sx, sy0 = y0 >> sg.sy, sy1 = (y0 + ny - 1) >> sg.sy;
+            const int sz0 = z0 >> sg.sz, sz1 = (z0 + nz - 1) >> sg.sz, snx = sx1 - sx0 + 1, sny = sy1 - sy0 + 1, snz = sz1 - sz0 + 1;
             for (int i = lane; i < snx * sny * snz; i += MARK_LANES) {
-                const uint32_t cx = (uint32_t)((sx0 + i % snx) & sm1), cy = (uint32_t)((sy0 + (i / snx) % sny) & sm1),
-                               cz = (uint32_t)((sz0 + i / (snx * sny)) & sm1);
-                const uint32_t sbit = (cz << (2 * sb)) | (cy << sb) | cx;
+                const uint32_t cx = (uint32_t)((sx0 + i % snx) & ((1 << sg.bx) - 1)), cy = (uint32_t)((sy0 + (i / snx) % sny) & ((1 << sg.by) - 1)),
+                               cz = (uint32_t)((sz0 + i / (snx * sny)) & ((1 << sg.bz) - 1));
+                const uint32_t sbit = (cz << (sg.bx + sg.by)) | (cy << sg.bx) | cx;
                 atomicOr(&super[sbit >> 5], 1u << (sbit & 31));
             }
         }
@@ -244,8 +263,158 @@ struct StageArgs {
     const float4 *slice;
     int64_t n;
     uint32_t index_base;
-    const unsigned short *table;
     const uint32_t *any, *super;
+    float4 *dst;                     /* one rank: its receive buffer; several: the hit list k_route_split works on */
+    unsigned long long *cursor;      /* records appended so far */
+    unsigned long long cap;
+    uint32_t flag_bit;
+    uint32_t *flags;
+};
+
+#define RW_CAP 128           /* records a WARP collects in shared memory before it writes them out */
+#define RT_THREADS 1024      /* one CTA per SM: all its warps share one copy of the pre-filter */
+#define RT_U 8               /* independent 16-byte loads in flight per thread */
+
+/* coarse (mask-grid) coordinate of a particle: ((int)floorf(t) & (nc - 1)) >> ms with t = (x - g0) * invh, the grid
+ * build's cell_coord, WITHOUT the conversion instruction (F2I runs on the quarter-rate pipe; three per particle were
+ * 17 % of this kernel's time).  Adding magic = 1.5 * 2^(23 + ms) with rounding towards -inf leaves
+ * floor(t / 2^ms) in the low mantissa bits (the sum's ulp is 2^ms and it is rounded once, downwards), so the
+ * coordinate is one add and one AND.  Exact for |t| < 2^(22 + ms), i.e. for particles within 2048 box lengths of
+ * the box; beyond that neither this nor the conversion names a meaningful cell. */
+__device__ __forceinline__ uint32_t coarse_coord(float x, float g0, float invh, float magic, uint32_t nm1)
+{
+    const float t = __fmul_rn(__fsub_rn(x, g0), invh);
+    return __float_as_uint(__fadd_rd(t, magic)) & nm1;
+}
+__device__ __forceinline__ float coarse_magic(int ms) { return __uint_as_float(((uint32_t)(127 + 23 + ms) << 23) | 0x400000u); }
+
+/* Every warp works on its own: it streams runs of 32 x RT_U particles, collects the few records they yield in a
+ * private shared-memory buffer and writes them out RW_CAP at a time (one reservation per flush).  No block-wide
+ * barrier after the start: the first two versions reserved / flushed per CTA and round and spent their time
+ * waiting — 6.5 warps stalled on loads and 4 at the barrier per instruction issued, 3 TB/s
+ * (profiles/r2_ncu_route_bucket.md).
+ *
+ * The third version was bound by instruction issue (93 warp instructions per 32 particles, issue slots 65 % busy
+ * at 4.1 TB/s): a vote + compaction per 32 particles and destination, bounds checks and conversions per particle.
+ * This one keeps a run's hits in registers and compacts them ONCE per run (a warp scan of the per-lane counts),
+ * has a check-free body for full runs, and computes cell coordinates on the full-rate pipe (coarse_coord).
+ *
+ * The kernel only answers "does ANY rank need this particle" (pre-filter in shared memory, then the bitmap in
+ * L2).  With several ranks the hits (5-6 % of the slice) go to a list that k_route_split distributes: looking the
+ * destination set up here — a dependent 16-bit gather from a table far larger than the L2, plus a tag and a
+ * per-destination sort-out at every flush — halved the speed of the whole pass (2.2 against 4.6 TB/s). */
+__global__ void __launch_bounds__(RT_THREADS, 1) k_route_stage(const __grid_constant__ StageArgs a)
+{
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    const int mb = a.g.mb, ms = a.g.ms;
+    const SuperGeom sg = super_geom(mb);
+    const uint32_t sbits = 1u << (sg.bx + sg.by + sg.bz), swords = (sbits / 32u + 4u) & ~3u;   /* (multiple of 4: what follows stays 16-byte aligned) */
+    uint32_t *s_super = s_dyn;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float4 *wbuf = reinterpret_cast<float4 *>(s_dyn + swords) + (size_t)w * RW_CAP;
+    for (uint32_t i = threadIdx.x; i < swords; i += blockDim.x) s_super[i] = i < sbits / 32u + 1u ? __ldg(a.super + i) : 0u;
+    __syncthreads();
+    const float g0x = a.g.g0[0], g0y = a.g.g0[1], g0z = a.g.g0[2], ihx = a.g.invh[0], ihy = a.g.invh[1], ihz = a.g.invh[2];
+    const float magic = coarse_magic(ms);
+    const uint32_t nm1 = (1u << mb) - 1u;
+    const uint32_t S1 = 1u << mb, S2 = 1u << (2 * mb), T1 = 1u << sg.bx, T2 = 1u << (sg.bx + sg.by);
+    const uint32_t n = (uint32_t)a.n;
+    uint32_t wcnt = 0;                                     /* records in this warp's buffer (same value on every lane) */
+
+    auto flush = [&]() {
+        __syncwarp();
+        unsigned long long base = 0ull;
+        if (lane == 0) {
+            base = atomicAdd(a.cursor, (unsigned long long)wcnt);
+            if (base + wcnt > a.cap) { atomicOr(a.flags, a.flag_bit); base = ~0ull; }
+        }
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base != ~0ull)
+            for (uint32_t i = lane; i < wcnt; i += 32) a.dst[base + i] = wbuf[i];
+        __syncwarp();
+        wcnt = 0;
+    };
+
+    /* the records of the run's particles [U0, U1) of every lane, appended in one go: per-lane counts, a warp scan,
+     * every lane stores its own.  Returns false (nothing stored) if they cannot fit even into an empty buffer. */
+    auto append = [&](const float4 (&q)[RT_U], const uint32_t (&set)[RT_U], uint32_t i0, auto u0c, auto u1c) -> bool {
+        constexpr int U0 = decltype(u0c)::value, U1 = decltype(u1c)::value;
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int u = U0; u < U1; ++u) cnt += set[u];
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (!total) return true;
+        if (total > RW_CAP) return false;
+        if (wcnt + total > RW_CAP) flush();
+        uint32_t pos = wcnt + incl - cnt;
+#pragma unroll
+        for (int u = U0; u < U1; ++u) {
+            if (set[u]) {
+                wbuf[pos] = make_float4(q[u].x, q[u].y, q[u].z, __uint_as_float(a.index_base + i0 + u * 32u));
+                ++pos;
+            }
+        }
+        wcnt += total;
+        return true;
+    };
+
+    auto body = [&](uint32_t r, auto fullc) {
+        constexpr bool FULL = decltype(fullc)::value;
+        const uint32_t i0 = r * (32u * RT_U) + lane;
+        float4 q[RT_U];
+#pragma unroll
+        for (int u = 0; u < RT_U; ++u) {
+            const uint32_t i = i0 + u * 32u;
+            q[u] = ld_stream(a.slice + (FULL || i < n ? i : n - 1u));
+        }
+        /* the lookups of the RT_U particles are issued level by level, so that a level's loads are all in flight
+         * together: pre-filter (shared memory), then the "somebody wants it" bitmap (L2) */
+        uint32_t bit[RT_U], set[RT_U];
+#pragma unroll
+        for (int u = 0; u < RT_U; ++u) {
+            /* (a particle is routed by the coarse cell of the cell the grid build will sort it into) */
+            const uint32_t cx = coarse_coord(q[u].x, g0x, ihx, magic, nm1);
+            const uint32_t cy = coarse_coord(q[u].y, g0y, ihy, magic, nm1);
+            const uint32_t cz = coarse_coord(q[u].z, g0z, ihz, magic, nm1);
+            const uint32_t sbit = (cz >> sg.sz) * T2 + (cy >> sg.sy) * T1 + (cx >> sg.sx);
+            bit[u] = cz * S2 + cy * S1 + cx;
+            set[u] = (s_super[sbit >> 5] >> (sbit & 31)) & 1u;
+            if (!FULL && i0 + u * 32u >= n) set[u] = 0u;
+        }
+        uint32_t anyw[RT_U];
+#pragma unroll
+        for (int u = 0; u < RT_U; ++u) anyw[u] = set[u] ? __ldg(a.any + (bit[u] >> 5)) : 0u;
+#pragma unroll
+        for (int u = 0; u < RT_U; ++u) set[u] = (anyw[u] >> (bit[u] & 31)) & 1u;
+        using std::integral_constant;
+        if (append(q, set, i0, integral_constant<int, 0>(), integral_constant<int, RT_U>())) return;
+        /* more than RW_CAP hits in one run (the core of a cluster): two halves, each of which always fits */
+        append(q, set, i0, integral_constant<int, 0>(), integral_constant<int, RT_U / 2>());
+        append(q, set, i0, integral_constant<int, RT_U / 2>(), integral_constant<int, RT_U>());
+    };
+
+    const uint32_t gw = blockIdx.x * (RT_THREADS / 32) + (uint32_t)w, nwarp = gridDim.x * (RT_THREADS / 32);
+    const uint32_t run = 32u * RT_U;
+    const uint32_t nfull = n / run, nrun = (n + run - 1) / run;
+    uint32_t r = gw;
+    for (; r < nfull; r += nwarp) body(r, std::true_type());
+    if (r < nrun) body(r, std::false_type());
+    if (wcnt) flush();
+}
+
+/* ---- several ranks: the hit list -> one run per destination ------------------------------------------ */
+struct SplitArgs {
+    GridDev g;
+    const float4 *hits;
+    const unsigned long long *n_hits;
+    unsigned long long hits_cap;
+    const unsigned short *table;
     int R;
     float4 *dst[ROUTE_MAXR];                 /* staging area per destination; own rank: its receive buffer */
     unsigned long long *cursor[ROUTE_MAXR];  /* records appended so far                                    */
@@ -254,131 +423,64 @@ struct StageArgs {
     uint32_t *flags;
 };
 
-#define RW_CAP 128           /* records a WARP collects in shared memory before it writes them out */
-#define RT_THREADS 512
-#define RT_U 8               /* independent 16-byte loads in flight per thread */
-
-/* Every warp works on its own: it streams runs of 32 x RT_U particles, collects the few records they yield in a
- * private shared-memory buffer and writes them out RW_CAP at a time (one reservation per destination and
- * flush).  No block-wide barrier after the start: the first two versions reserved / flushed per CTA and round
- * and spent their time waiting — 6.5 warps stalled on loads and 4 at the barrier per instruction issued, 3 TB/s
- * (profiles/r2_ncu_route_bucket.md).  The 64^3 pre-filter (32 KB) is copied into shared memory once per CTA. */
-__global__ void __launch_bounds__(RT_THREADS, 2) k_route_stage(const __grid_constant__ StageArgs a)
+#define SP_NT 256
+#define SP_U 8
+/* Tiles of SP_NT x SP_U hits: destination set of every record (16-bit gather from the table; a record's cell is
+ * recomputed from its position exactly as the routing pass did), the tile's count per destination in shared
+ * memory, ONE reservation per destination and tile, then every record is stored once per destination. */
+__global__ void __launch_bounds__(SP_NT) k_route_split(const __grid_constant__ SplitArgs a)
 {
-    extern __shared__ __align__(16) uint32_t s_dyn[];
-    const int mask = a.g.nc - 1, mb = a.g.mb, ms = a.g.ms;
-    const int sb = min(mb, DOM_SUPER_LOG), ss = mb - sb;
-    const uint32_t swords = ((1u << (3 * sb)) / 32u + 4u) & ~3u;           /* (multiple of 4: what follows stays 16-byte aligned) */
-    uint32_t *s_super = s_dyn;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    float4 *wbuf = reinterpret_cast<float4 *>(s_dyn + swords) + (size_t)w * RW_CAP;
-    unsigned char *wdst = reinterpret_cast<unsigned char *>(reinterpret_cast<float4 *>(s_dyn + swords) + (size_t)(RT_THREADS / 32) * RW_CAP) +
-                          (size_t)w * RW_CAP;
-    for (uint32_t i = threadIdx.x; i < swords; i += blockDim.x) s_super[i] = i < (1u << (3 * sb)) / 32u + 1u ? __ldg(a.super + i) : 0u;
-    __syncthreads();
+    __shared__ uint32_t s_cnt[ROUTE_MAXR], s_pos[ROUTE_MAXR];
+    __shared__ unsigned long long s_base[ROUTE_MAXR];
+    unsigned long long n = *a.n_hits;
+    if (n > a.hits_cap) n = a.hits_cap;                      /* (the overflow was flagged by k_route_stage) */
+    const int mb = a.g.mb;
     const float g0x = a.g.g0[0], g0y = a.g.g0[1], g0z = a.g.g0[2], ihx = a.g.invh[0], ihy = a.g.invh[1], ihz = a.g.invh[2];
-    const uint32_t S1 = 1u << mb, S2 = 1u << (2 * mb), T1 = 1u << sb, T2 = 1u << (2 * sb);
-    const uint32_t n = (uint32_t)a.n;
-    const int R = a.R;
-    const uint32_t lt = (1u << lane) - 1u;
-    uint32_t wcnt = 0;                                     /* records in this warp's buffer (same value on every lane) */
-
-    auto flush = [&]() {
-        if (R == 1) {
+    const float magic = coarse_magic(a.g.ms);
+    const uint32_t nm1 = (1u << mb) - 1u;
+    const unsigned long long tile = (unsigned long long)SP_NT * SP_U, ntiles = (n + tile - 1) / tile;
+    for (unsigned long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        if (threadIdx.x < ROUTE_MAXR) { s_cnt[threadIdx.x] = 0u; s_pos[threadIdx.x] = 0u; }
+        __syncthreads();
+        float4 q[SP_U];
+        uint32_t set[SP_U];
+#pragma unroll
+        for (int u = 0; u < SP_U; ++u) {
+            const unsigned long long i = t * tile + (unsigned long long)u * SP_NT + threadIdx.x;
+            q[u] = ld_stream(a.hits + (i < n ? i : n - 1ull));
+        }
+#pragma unroll
+        for (int u = 0; u < SP_U; ++u) {
+            const unsigned long long i = t * tile + (unsigned long long)u * SP_NT + threadIdx.x;
+            const uint32_t cx = coarse_coord(q[u].x, g0x, ihx, magic, nm1);
+            const uint32_t cy = coarse_coord(q[u].y, g0y, ihy, magic, nm1);
+            const uint32_t cz = coarse_coord(q[u].z, g0z, ihz, magic, nm1);
+            set[u] = i < n ? (uint32_t)__ldg(a.table + (((size_t)cz << (2 * mb)) | ((size_t)cy << mb) | cx)) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < SP_U; ++u)
+            for (uint32_t m = set[u]; m; m &= m - 1u) atomicAdd(&s_cnt[__ffs(m) - 1], 1u);
+        __syncthreads();
+        if (threadIdx.x < a.R) {
+            const int d = threadIdx.x;
+            const uint32_t c = s_cnt[d];
             unsigned long long base = 0ull;
-            if (lane == 0) {
-                base = atomicAdd_system(a.cursor[0], (unsigned long long)wcnt);
-                if (base + wcnt > a.cap[0]) { atomicOr(a.flags, a.flag_bit[0]); base = ~0ull; }
+            if (c) {
+                base = atomicAdd_system(a.cursor[d], (unsigned long long)c);
+                if (base + c > a.cap[d]) { atomicOr(a.flags, a.flag_bit[d]); base = ~0ull; }
             }
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (base != ~0ull)
-                for (uint32_t i = lane; i < wcnt; i += 32) a.dst[0][base + i] = wbuf[i];
-        } else {
-            for (int d = 0; d < R; ++d) {
-                uint32_t mk[RW_CAP / 32], c = 0;
+            s_base[d] = base;
+        }
+        __syncthreads();
 #pragma unroll
-                for (int k = 0; k < RW_CAP / 32; ++k) {
-                    const uint32_t i = (uint32_t)k * 32u + lane;
-                    mk[k] = __ballot_sync(0xFFFFFFFFu, i < wcnt && wdst[i] == (unsigned char)d);
-                    c += __popc(mk[k]);
-                }
-                if (!c) continue;
-                unsigned long long base = 0ull;
-                if (lane == 0) {
-                    base = atomicAdd_system(a.cursor[d], (unsigned long long)c);
-                    if (base + c > a.cap[d]) { atomicOr(a.flags, a.flag_bit[d]); base = ~0ull; }
-                }
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                uint32_t before = 0;
-#pragma unroll
-                for (int k = 0; k < RW_CAP / 32; ++k) {
-                    if (base != ~0ull && ((mk[k] >> lane) & 1u))
-                        a.dst[d][base + before + __popc(mk[k] & lt)] = wbuf[k * 32 + lane];
-                    before += __popc(mk[k]);
-                }
+        for (int u = 0; u < SP_U; ++u)
+            for (uint32_t m = set[u]; m; m &= m - 1u) {
+                const int d = __ffs(m) - 1;
+                const uint32_t slot = atomicAdd(&s_pos[d], 1u);
+                if (s_base[d] != ~0ull) a.dst[d][s_base[d] + slot] = q[u];
             }
-        }
-        __syncwarp();
-        wcnt = 0;
-    };
-
-    const uint32_t gw = blockIdx.x * (RT_THREADS / 32) + (uint32_t)w, nwarp = gridDim.x * (RT_THREADS / 32);
-    const uint32_t run = 32u * RT_U;
-    const uint32_t nrun = (n + run - 1) / run;
-    for (uint32_t r = gw; r < nrun; r += nwarp) {
-        const uint32_t i0 = r * run + lane;
-        float4 q[RT_U];
-#pragma unroll
-        for (int u = 0; u < RT_U; ++u) {
-            const uint32_t i = i0 + u * 32u;
-            q[u] = ld_stream(a.slice + (i < n ? i : n - 1u));
-        }
-        /* the lookups of the RT_U particles are issued level by level, so that a level's loads are all in flight
-         * together: 64^3 pre-filter (shared memory), "somebody wants it" bitmap (L2), destination set (the few
-         * particles that pass both; a 16-bit gather from a table far larger than the L2) */
-        uint32_t bit[RT_U], set[RT_U];
-#pragma unroll
-        for (int u = 0; u < RT_U; ++u) {
-            const uint32_t i = i0 + u * 32u;
-            /* (the same expressions as the grid build's cell_coord: a particle is routed by the cell it will be sorted into) */
-            const uint32_t cx = cell_coord(q[u].x, g0x, ihx, mask) >> ms;
-            const uint32_t cy = cell_coord(q[u].y, g0y, ihy, mask) >> ms;
-            const uint32_t cz = cell_coord(q[u].z, g0z, ihz, mask) >> ms;
-            const uint32_t sbit = (cz >> ss) * T2 + (cy >> ss) * T1 + (cx >> ss);
-            bit[u] = cz * S2 + cy * S1 + cx;
-            set[u] = (i < n && ((s_super[sbit >> 5] >> (sbit & 31)) & 1u)) ? 1u : 0u;
-        }
-        uint32_t anyw[RT_U];
-#pragma unroll
-        for (int u = 0; u < RT_U; ++u) anyw[u] = set[u] ? __ldg(a.any + (bit[u] >> 5)) : 0u;
-#pragma unroll
-        for (int u = 0; u < RT_U; ++u) set[u] = (anyw[u] >> (bit[u] & 31)) & 1u;
-        if (R > 1) {
-            unsigned short tb[RT_U];
-#pragma unroll
-            for (int u = 0; u < RT_U; ++u) tb[u] = set[u] ? __ldg(a.table + bit[u]) : (unsigned short)0;
-#pragma unroll
-            for (int u = 0; u < RT_U; ++u) set[u] = tb[u];
-        }
-#pragma unroll
-        for (int u = 0; u < RT_U; ++u) {
-            uint32_t wset = __reduce_or_sync(0xFFFFFFFFu, set[u]);
-            if (!wset) continue;
-            q[u].w = __uint_as_float(a.index_base + i0 + u * 32u);
-            for (; wset; wset &= wset - 1u) {
-                const int d = __ffs(wset) - 1;
-                if (wcnt + 32u > RW_CAP) flush();
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, (set[u] >> d) & 1u);
-                if ((set[u] >> d) & 1u) {
-                    const uint32_t pos = wcnt + __popc(m & lt);
-                    wbuf[pos] = q[u];
-                    wdst[pos] = (unsigned char)d;
-                }
-                wcnt += __popc(m);
-            }
-        }
+        __syncthreads();
     }
-    if (wcnt) flush();
 }
 
 /* ---- push: staging runs -> the receivers' buffers over NVLink ---------------------------------------- */
@@ -491,18 +593,19 @@ extern "C" int sogpu_domain_open(sogpu_t *h, const sogpu_domain_cfg_t *cfg, void
     if (rc) return rc;
     CU(cudaMemsetAsync(D->ctrl, 0, sizeof(DomCtrl), h->stream));
     if (R > 1) CU(cudaMalloc(&D->stage, (size_t)R * (size_t)cfg->stage_cap * sizeof(float4)));
-    CU(cudaMalloc(&D->d_counts, (3 * ROUTE_MAXR + 1) * sizeof(unsigned long long)));
+    if (R > 1) CU(cudaMalloc(&D->hits, (size_t)cfg->recv_cap * sizeof(float4)));
+    CU(cudaMalloc(&D->d_counts, (3 * ROUTE_MAXR + 2) * sizeof(unsigned long long)));
     CU(cudaMalloc(&D->d_flags, sizeof(uint32_t)));
     CU(cudaMalloc(&D->d_nrecv32, sizeof(uint32_t)));
     CU(cudaMalloc(&D->d_bins, (DOM_ASSIGN_BINS + 1) * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(D->d_flags, 0, sizeof(uint32_t), h->stream));
-    CU(cudaMemsetAsync(D->d_counts, 0, (3 * ROUTE_MAXR + 1) * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(D->d_counts, 0, (3 * ROUTE_MAXR + 2) * sizeof(unsigned long long), h->stream));
     {   /* destination table + bitmaps at the mask resolution of this snapshot; cleared once, then kept clean */
         for (int k = 0; k < 3; ++k) { h->period[k] = cfg->period[k]; h->center[k] = cfg->center[k]; }
         GridDev g;
         domain_geometry(h, cfg->n_total, g);
         const size_t n_cells = (size_t)1 << (3 * g.mb), words = n_cells / 32 + 1;
-        const size_t swords = ((size_t)1 << (3 * std::min(g.mb, DOM_SUPER_LOG))) / 32 + 1;
+        const size_t swords = super_words(g.mb);
         CU(cudaMalloc(&D->d_table, (n_cells + 2) * sizeof(unsigned short)));
         CU(cudaMalloc(&D->d_any, words * sizeof(uint32_t)));
         CU(cudaMalloc(&D->d_mymask, words * sizeof(uint32_t)));
@@ -567,7 +670,7 @@ extern "C" int sogpu_domain_close(sogpu_t *h)
     cudaStreamSynchronize(h->stream);
     cudaFree(D->recv[0]);
     if (D->recv[1] != D->recv[0]) cudaFree(D->recv[1]);
-    cudaFree(D->ctrl); cudaFree(D->stage); cudaFree(D->d_counts); cudaFree(D->d_flags); cudaFree(D->d_nrecv32);
+    cudaFree(D->ctrl); cudaFree(D->stage); cudaFree(D->hits); cudaFree(D->d_counts); cudaFree(D->d_flags); cudaFree(D->d_nrecv32);
     cudaFree(D->d_owner); cudaFree(D->d_bins);
     cudaFree(D->d_table); cudaFree(D->d_any); cudaFree(D->d_mymask); cudaFree(D->d_super);
     delete D;
@@ -603,8 +706,8 @@ extern "C" int sogpu_domain_begin(sogpu_t *h, const void *d_centers, const void 
             D->d_super, D->d_mymask, 1);
     }
     D->marked = false;
-    {   /* the bitmaps: 2 x 2^(3 mb) bits + the 64^3 pre-filter — a few to 32 MB, microseconds */
-        const size_t words = ((size_t)1 << (3 * g.mb)) / 32 + 1, swords = ((size_t)1 << (3 * std::min(g.mb, DOM_SUPER_LOG))) / 32 + 1;
+    {   /* the bitmaps: 2 x 2^(3 mb) bits + the pre-filter — a few to 32 MB, microseconds */
+        const size_t words = ((size_t)1 << (3 * g.mb)) / 32 + 1, swords = super_words(g.mb);
         if (R > 1) CU(cudaMemsetAsync(D->d_any, 0, words * sizeof(uint32_t), s));
         CU(cudaMemsetAsync(D->d_mymask, 0, words * sizeof(uint32_t), s));
         CU(cudaMemsetAsync(D->d_super, 0, swords * sizeof(uint32_t), s));
@@ -621,7 +724,7 @@ extern "C" int sogpu_domain_begin(sogpu_t *h, const void *d_centers, const void 
      * step's barrier: clearing it here, ahead of this step's barrier, is safe (see the header comment) */
     CU(cudaMemsetAsync(&D->ctrl->cursor[D->parity ^ 1], 0, sizeof(unsigned long long), s));
     if (R == 1) CU(cudaMemsetAsync(&D->ctrl->cursor[D->parity], 0, sizeof(unsigned long long), s));
-    CU(cudaMemsetAsync(D->d_counts, 0, (3 * ROUTE_MAXR + 1) * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(D->d_counts, 0, (3 * ROUTE_MAXR + 2) * sizeof(unsigned long long), s));
     CU(cudaMemsetAsync(D->d_flags, 0, sizeof(uint32_t), s));
     h->stats.last_kernel_launches = 0;
     {
@@ -657,19 +760,12 @@ static int dom_stage_args(sogpu *h, StageArgs &a, const void *d_chunk, int64_t n
     memset(&a, 0, sizeof(a));
     dom_geometry(h, a.g);
     a.slice = (const float4 *)d_chunk; a.n = n; a.index_base = (uint32_t)index_base;
-    a.table = D->d_table; a.any = D->cfg.n_ranks > 1 ? D->d_any : D->d_mymask; a.super = D->d_super; a.R = D->cfg.n_ranks;
-    a.flags = D->d_flags;
-    for (int d = 0; d < a.R; ++d) {
-        if (d == D->cfg.rank) {
-            a.dst[d] = D->recv[D->parity]; a.cursor[d] = &D->ctrl->cursor[D->parity];
-            a.cap[d] = (unsigned long long)D->cfg.recv_cap; a.flag_bit[d] = 2u;
-        } else if (D->direct) {
-            a.dst[d] = D->peer_recv[D->parity][d]; a.cursor[d] = &D->peer_ctrl[d]->cursor[D->parity];
-            a.cap[d] = (unsigned long long)D->cfg.recv_cap; a.flag_bit[d] = 4u;
-        } else {
-            a.dst[d] = D->stage + (size_t)d * (size_t)D->cfg.stage_cap; a.cursor[d] = D->d_counts + d;
-            a.cap[d] = (unsigned long long)D->cfg.stage_cap; a.flag_bit[d] = 1u;
-        }
+    a.super = D->d_super; a.flags = D->d_flags;
+    a.cap = (unsigned long long)D->cfg.recv_cap;
+    if (D->cfg.n_ranks > 1) {           /* several ranks: everything somebody needs -> the hit list */
+        a.any = D->d_any; a.dst = D->hits; a.cursor = D->d_counts + 3 * ROUTE_MAXR + 1; a.flag_bit = 1u;
+    } else {                            /* one rank: straight into its receive buffer */
+        a.any = D->d_mymask; a.dst = D->recv[D->parity]; a.cursor = &D->ctrl->cursor[D->parity]; a.flag_bit = 2u;
     }
     return SOGPU_OK;
 }
@@ -686,14 +782,11 @@ extern "C" int sogpu_domain_route(sogpu_t *h, const void *d_chunk, int64_t n, in
     if (rc) return rc;
     {
         ProfScope p(h, KID_ROUTE, 16.0 * (double)n);
-        /* persistent grid of exactly the CTAs that are resident at once: a second, partial wave would leave
-         * the SMs of the finished CTAs idle */
-        const size_t swords = ((((size_t)1 << (3 * std::min(a.g.mb, DOM_SUPER_LOG))) / 32 + 4) & ~(size_t)3);
-        const size_t ssm = swords * sizeof(uint32_t) + (size_t)(RT_THREADS / 32) * RW_CAP * (sizeof(float4) + 1);
-        CU(cudaFuncSetAttribute(k_route_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(96 * 1024)));   /* (more than 48 KB: opt in) */
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_route_stage, RT_THREADS, ssm) != cudaSuccess || per_sm < 1) per_sm = 1;
-        k_route_stage<<<(int)std::min<int64_t>((n + RT_THREADS - 1) / RT_THREADS, (int64_t)h->sm_count * per_sm), RT_THREADS, ssm, h->stream>>>(a);
+        /* persistent grid of exactly the CTAs that are resident at once (one per SM): a second, partial wave
+         * would leave the SMs of the finished CTAs idle */
+        const size_t ssm = super_words(a.g.mb) * sizeof(uint32_t) + (size_t)(RT_THREADS / 32) * RW_CAP * sizeof(float4);
+        CU(cudaFuncSetAttribute(k_route_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));   /* (more than 48 KB: opt in) */
+        k_route_stage<<<(int)std::min<int64_t>((n + RT_THREADS - 1) / RT_THREADS, (int64_t)h->sm_count), RT_THREADS, ssm, h->stream>>>(a);
     }
     CU(cudaGetLastError());
     return SOGPU_OK;
@@ -736,6 +829,27 @@ extern "C" int sogpu_domain_push(sogpu_t *h, int barrier)
         for (int d = 0; d < R; ++d) { a.peer_ctrl[d] = D->peer_ctrl[d]; a.peer_recv[d] = D->peer_recv[D->parity][d]; }
         a.stage = D->stage; a.stage_cap = (unsigned long long)D->cfg.stage_cap; a.recv_cap = (unsigned long long)D->cfg.recv_cap;
         a.counts = D->d_counts; a.flags = D->d_flags;
+        {   /* the hits of this rank's slice -> its own receive buffer and one staging run per peer */
+            SplitArgs sa;
+            memset(&sa, 0, sizeof(sa));
+            dom_geometry(h, sa.g);
+            sa.hits = D->hits; sa.n_hits = D->d_counts + 3 * ROUTE_MAXR + 1; sa.hits_cap = (unsigned long long)D->cfg.recv_cap;
+            sa.table = D->d_table; sa.R = R; sa.flags = D->d_flags;
+            for (int d = 0; d < R; ++d) {
+                if (d == D->cfg.rank) {
+                    sa.dst[d] = D->recv[D->parity]; sa.cursor[d] = &D->ctrl->cursor[D->parity];
+                    sa.cap[d] = (unsigned long long)D->cfg.recv_cap; sa.flag_bit[d] = 2u;
+                } else if (direct) {
+                    sa.dst[d] = D->peer_recv[D->parity][d]; sa.cursor[d] = &D->peer_ctrl[d]->cursor[D->parity];
+                    sa.cap[d] = (unsigned long long)D->cfg.recv_cap; sa.flag_bit[d] = 4u;
+                } else {
+                    sa.dst[d] = D->stage + (size_t)d * (size_t)D->cfg.stage_cap; sa.cursor[d] = D->d_counts + d;
+                    sa.cap[d] = (unsigned long long)D->cfg.stage_cap; sa.flag_bit[d] = 1u;
+                }
+            }
+            ProfScope p(h, KID_ROUTE, 0.0);
+            k_route_split<<<h->sm_count * 4, SP_NT, 0, s>>>(sa);
+        }
         if (!direct) {
             ProfScope p(h, KID_PUSH, 0.0, 2);
             k_push_reserve<<<1, 32, 0, s>>>(a);
@@ -800,7 +914,7 @@ extern "C" int sogpu_domain_result(sogpu_t *h, int64_t *n_recv, int64_t *n_sent,
     if (!h || !h->dom) return set_err(SOGPU_ERR_ARG, "sogpu_domain_result: no open domain");
     DomainState *D = h->dom;
     CU(cudaSetDevice(h->device));
-    unsigned long long c[3 * ROUTE_MAXR + 1];
+    unsigned long long c[3 * ROUTE_MAXR + 2];
     uint32_t f = 0;
     CU(cudaMemcpyAsync(c, D->d_counts, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(&f, D->d_flags, sizeof(f), cudaMemcpyDeviceToHost, h->stream));
