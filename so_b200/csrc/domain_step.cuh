@@ -48,9 +48,12 @@ struct DomainState {
     uint32_t *d_flags;                  /* bit0 staging overflow, bit1 own receive overflow, bit2 peer receive overflow, bit3 barrier timeout */
     uint32_t *d_nrecv32;
     unsigned char *d_owner;
+    int4 *d_cubes;                      /* per halo: the cube of coarse cells it marks (k_halo_cubes) */
     int32_t owner_cap;
     unsigned short *d_table;            /* destination ranks per coarse cell (2^(3 mb) entries)                */
     uint32_t *d_any, *d_super, *d_mymask; /* bit per coarse cell: somebody's / (pre-filter, per block) / this rank's */
+    uint32_t *d_plain, *d_listed;       /* several ranks: cells under a plain / a crossing halo (k_mark_table)   */
+    unsigned char *d_bin_owner;         /* DOM_ASSIGN_BINS owners */
     bool marked;                        /* the tables hold the marks of the previous step's catalog            */
     int marked_balls;
     int32_t marked_nh;
@@ -66,6 +69,13 @@ struct DomainState {
 };
 
 /* ---- ownership -------------------------------------------------------------------------------------- */
+/* bins in 8x8x8 blocks, blocks row-major, bins row-major inside a block */
+__device__ __forceinline__ uint32_t assign_bin_index(uint32_t kx, uint32_t ky, uint32_t kz)
+{
+    const uint32_t nb = 1u << (DOM_ASSIGN_LOG - 3);
+    const uint32_t hx = kx >> 3, hy = ky >> 3, hz = kz >> 3, lx = kx & 7u, ly = ky & 7u, lz = kz & 7u;
+    return ((((hz * nb + hy) * nb + hx)) << 9) | (lz << 6) | (ly << 3) | lx;
+}
 __device__ __forceinline__ uint32_t assign_bin(const float *c, const GridDev &g)
 {
     uint32_t k[3];
@@ -76,10 +86,7 @@ __device__ __forceinline__ uint32_t assign_bin(const float *c, const GridDev &g)
         int ci = (int)(t * (double)(1 << DOM_ASSIGN_LOG));
         k[a] = (uint32_t)min(max(ci, 0), (1 << DOM_ASSIGN_LOG) - 1);
     }
-    /* 8x8x8 blocks of cells, blocks row-major, cells row-major inside a block */
-    const uint32_t nb = 1u << (DOM_ASSIGN_LOG - 3);
-    const uint32_t hx = k[0] >> 3, hy = k[1] >> 3, hz = k[2] >> 3, lx = k[0] & 7u, ly = k[1] & 7u, lz = k[2] & 7u;
-    return ((((hz * nb + hy) * nb + hx)) << 9) | (lz << 6) | (ly << 3) | lx;
+    return assign_bin_index(k[0], k[1], k[2]);
 }
 /* estimated r^2 evaluations of one halo: the final ball (1.2 R, R ~ 1.25 rgtp) at 200 x the mean number density,
  * plus a floor for the fixed per-halo work (so_b200/parallel.py: halo_cost) */
@@ -137,17 +144,25 @@ __global__ void __launch_bounds__(1024) k_assign_scan(unsigned long long *bins)
     if (t == 1023) bins[DOM_ASSIGN_BINS] = carry;
 }
 
-__global__ void __launch_bounds__(256) k_assign_owner(GridDev g, const float *__restrict__ centers, int nh, int R,
-                                                      const unsigned long long *__restrict__ bins,
+/* owner of every bin: the rank whose share of the total cost holds the middle of the bin's cost interval */
+__global__ void __launch_bounds__(256) k_assign_bin_owner(int R, const unsigned long long *__restrict__ bins,
+                                                          unsigned char *__restrict__ bin_owner)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= DOM_ASSIGN_BINS) return;
+    const unsigned long long lo = bins[b], hi = bins[b + 1], total = bins[DOM_ASSIGN_BINS];
+    const unsigned long long mid = lo + (hi - lo) / 2ull;
+    unsigned long long r = total ? (mid * (unsigned long long)R) / total : 0ull;
+    bin_owner[b] = (unsigned char)(r < (unsigned long long)R ? r : (unsigned long long)(R - 1));
+}
+
+__global__ void __launch_bounds__(256) k_assign_owner(GridDev g, const float *__restrict__ centers, int nh,
+                                                      const unsigned char *__restrict__ bin_owner,
                                                       unsigned char *__restrict__ owner)
 {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= nh) return;
-    const uint32_t b = assign_bin(centers + 3 * (size_t)h, g);
-    const unsigned long long lo = bins[b], hi = bins[b + 1], total = bins[DOM_ASSIGN_BINS];
-    const unsigned long long mid = lo + (hi - lo) / 2ull;
-    unsigned long long r = total ? (mid * (unsigned long long)R) / total : 0ull;
-    owner[h] = (unsigned char)(r < (unsigned long long)R ? r : (unsigned long long)(R - 1));
+    owner[h] = bin_owner[assign_bin(centers + 3 * (size_t)h, g)];
 }
 
 /* ---- destination table -------------------------------------------------------------------------------- */
@@ -184,6 +199,43 @@ __device__ __forceinline__ void bit_run(uint32_t *map, uint32_t b0, uint32_t len
     }
 }
 
+/* the cube of coarse cells every halo can reach after n_balls steps of the ball schedule (same rule as
+ * k_mark_mask), once per step and one thread per halo: the marking kernels then start from one 16-byte load per
+ * halo instead of a chain of five loads and a page of double-precision arithmetic per group of lanes (ncu: 60 % of
+ * their stall samples).  .w = nx | ny << 10 | nz << 20 (each <= 512). */
+__global__ void __launch_bounds__(256) k_halo_cubes(GridDev g, const float *__restrict__ centers, const float *__restrict__ rgtp,
+                                                    int nh, int n_balls, int4 *__restrict__ cubes,
+                                                    const unsigned char *__restrict__ owner,
+                                                    const unsigned char *__restrict__ bin_owner)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= nh) return;
+    const float root = so_root_period(g.L[0], g.L[1], g.L[2]);
+    float ball = rgtp[h];
+    for (int k = 0; k < n_balls && (double)ball < 0.25 * (double)root; ++k) ball = so_next_ball(ball);
+    const float ball2 = __fmul_rn(ball, ball);
+    const double b = fmax(sqrt((double)ball2) * (1.0 + 1.0e-6), g.mask_rmin);
+    int x0, nx, y0, ny, z0, nz;
+    mask_range(g, 0, centers[3 * h + 0], b, x0, nx);
+    mask_range(g, 1, centers[3 * h + 1], b, y0, ny);
+    mask_range(g, 2, centers[3 * h + 2], b, z0, nz);
+    /* bit 30: the cube reaches into a bin of another owner ("crossing" halo, see k_mark_table); bin_owner == NULL
+     * (a single rank) never sets it */
+    int crossing = 0;
+    if (bin_owner) {
+        const int sh = g.mb - DOM_ASSIGN_LOG;
+        if (sh < 0) crossing = 1;
+        else {
+            const int own = owner[h], m = (1 << DOM_ASSIGN_LOG) - 1;
+            for (int bz = z0 >> sh; bz <= (z0 + nz - 1) >> sh; ++bz)
+                for (int by = y0 >> sh; by <= (y0 + ny - 1) >> sh; ++by)
+                    for (int bx = x0 >> sh; bx <= (x0 + nx - 1) >> sh; ++bx)
+                        crossing |= (bin_owner[assign_bin_index((uint32_t)(bx & m), (uint32_t)(by & m), (uint32_t)(bz & m))] != own);
+        }
+    }
+    cubes[h] = make_int4(x0, y0, z0, nx | (ny << 10) | (nz << 20) | (crossing << 30));
+}
+
 #define MARK_LANES 8
 /* A group of lanes per halo: the cube it can reach after n_balls steps of the ball schedule (same rule as k_mark_mask).
  * Sets the owner's bit in the destination table, the "somebody wants this cell" bitmap, its 64^3 pre-filter and
@@ -191,12 +243,20 @@ __device__ __forceinline__ void bit_run(uint32_t *map, uint32_t b0, uint32_t len
  * bits / table entries, so a row is a handful of word-wide reductions with nothing to wait for.
  * clear = 1 undoes exactly those marks: the tables are kept clean between steps by un-marking the previous
  * catalog (a few million stores) instead of clearing hundreds of megabytes. */
-__global__ void __launch_bounds__(256) k_mark_table(GridDev g, const float *__restrict__ centers,
-                                                    const float *__restrict__ rgtp, int nh, int n_balls,
+__global__ void __launch_bounds__(256) k_mark_table(GridDev g, const int4 *__restrict__ cubes, int nh,
                                                     const unsigned char *__restrict__ owner, int me,
                                                     uint32_t *__restrict__ table32, uint32_t *__restrict__ any,
-                                                    uint32_t *__restrict__ super, uint32_t *__restrict__ mymask, int clear)
+                                                    uint32_t *__restrict__ super, uint32_t *__restrict__ mymask,
+                                                    uint32_t *__restrict__ plain, uint32_t *__restrict__ listed, int clear)
 {
+    /* Several ranks.  Ownership follows the bins of k_assign_*: a halo whose cube stays inside bins of its own
+     * owner ("plain", the large majority) only sets a bit per cell in `plain` — whoever finds a particle in such a
+     * cell knows the destination from the cell's bin.  Only the halos that reach across an ownership boundary
+     * ("crossing") enter their owner in the 16-bit table and set `listed`.  A cell's destinations are then
+     *     (plain ? {owner of its bin} : {}) | (listed ? table : {})            (k_route_split)
+     * which is exact: every plain halo over the cell is owned by the owner of the cell's bin.  The table — 256 MB
+     * at 512^3, random read-modify-writes in DRAM, 0.13 ms per step when every halo went through it — is touched
+     * by the few crossing halos only. */
     /* clear = 1: only the destination table is un-marked (the bitmaps are small enough to be cleared by a
      * memset every step; the table — 2 bytes per coarse cell — is not).  A NULL array is skipped: a single rank
      * needs neither the table nor a second bitmap. */
@@ -204,19 +264,15 @@ __global__ void __launch_bounds__(256) k_mark_table(GridDev g, const float *__re
      * bound by the number of halos in flight (100 000 halos: 90 us) */
     const int lane = threadIdx.x & (MARK_LANES - 1);
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) / MARK_LANES, nw = (gridDim.x * blockDim.x) / MARK_LANES;
-    const float root = so_root_period(g.L[0], g.L[1], g.L[2]);
     const int nm = 1 << g.mb, nm1 = nm - 1;
     const SuperGeom sg = super_geom(g.mb);
     for (int h = wid; h < nh; h += nw) {
-        float ball = rgtp[h];
-        for (int k = 0; k < n_balls && (double)ball < 0.25 * (double)root; ++k) ball = so_next_ball(ball);
-        const float ball2 = __fmul_rn(ball, ball);
-        const double b = fmax(sqrt((double)ball2) * (1.0 + 1.0e-6), g.mask_rmin);
-        int x0, nx, y0, ny, z0, nz;
-        mask_range(g, 0, centers[3 * h + 0], b, x0, nx);
-        mask_range(g, 1, centers[3 * h + 1], b, y0, ny);
-        mask_range(g, 2, centers[3 * h + 2], b, z0, nz);
+        const int4 cube = __ldg(cubes + h);
         const int own = owner[h];
+        const int x0 = cube.x, y0 = cube.y, z0 = cube.z;
+        const int nx = cube.w & 1023, ny = (cube.w >> 10) & 1023, nz = (cube.w >> 20) & 1023;
+        const bool crossing = (cube.w >> 30) & 1;
+        if (clear && !crossing) continue;
         const uint32_t ob = (1u << own) * 0x00010001u;             /* the owner's bit in both halves of a table word */
         const int xa = x0 & nm1;                                   /* the row's x-range, split where it wraps */
         const int n0 = min(nx, nm - xa), n1 = nx - n0;
@@ -242,6 +298,8 @@ __global__ void __launch_bounds__(256) k_mark_table(GridDev g, const float *__re
                     if (own == me) bit_run(mymask, row + (uint32_t)px, (uint32_t)pn, 0);
                 }
                 if (!table32) continue;
+                if (!clear) bit_run(crossing ? listed : plain, row + (uint32_t)px, (uint32_t)pn, 0);
+                if (!crossing) continue;
                 /* table: 16-bit entries, two per word */
                 uint32_t c = row + (uint32_t)px, e = c + (uint32_t)pn;
                 while (c < e) {
@@ -415,6 +473,8 @@ struct SplitArgs {
     const unsigned long long *n_hits;
     unsigned long long hits_cap;
     const unsigned short *table;
+    const uint32_t *plain, *listed;          /* bit per coarse cell (k_mark_table) */
+    const unsigned char *bin_owner;
     int R;
     float4 *dst[ROUTE_MAXR];                 /* staging area per destination; own rank: its receive buffer */
     unsigned long long *cursor[ROUTE_MAXR];  /* records appended so far                                    */
@@ -425,9 +485,10 @@ struct SplitArgs {
 
 #define SP_NT 256
 #define SP_U 8
-/* Tiles of SP_NT x SP_U hits: destination set of every record (16-bit gather from the table; a record's cell is
- * recomputed from its position exactly as the routing pass did), the tile's count per destination in shared
- * memory, ONE reservation per destination and tile, then every record is stored once per destination. */
+/* Tiles of SP_NT x SP_U hits: destination set of every record (owner of the cell's bin if a plain halo covers the
+ * cell, table entry if a crossing one does — see k_mark_table; a record's cell is recomputed from its position
+ * exactly as the routing pass did), the tile's count per destination in shared memory, ONE reservation per
+ * destination and tile, then every record is stored once per destination. */
 __global__ void __launch_bounds__(SP_NT) k_route_split(const __grid_constant__ SplitArgs a)
 {
     __shared__ uint32_t s_cnt[ROUTE_MAXR], s_pos[ROUTE_MAXR];
@@ -438,6 +499,7 @@ __global__ void __launch_bounds__(SP_NT) k_route_split(const __grid_constant__ S
     const float g0x = a.g.g0[0], g0y = a.g.g0[1], g0z = a.g.g0[2], ihx = a.g.invh[0], ihy = a.g.invh[1], ihz = a.g.invh[2];
     const float magic = coarse_magic(a.g.ms);
     const uint32_t nm1 = (1u << mb) - 1u;
+    const int bsh = mb > DOM_ASSIGN_LOG ? mb - DOM_ASSIGN_LOG : 0;
     const unsigned long long tile = (unsigned long long)SP_NT * SP_U, ntiles = (n + tile - 1) / tile;
     for (unsigned long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         if (threadIdx.x < ROUTE_MAXR) { s_cnt[threadIdx.x] = 0u; s_pos[threadIdx.x] = 0u; }
@@ -455,7 +517,15 @@ __global__ void __launch_bounds__(SP_NT) k_route_split(const __grid_constant__ S
             const uint32_t cx = coarse_coord(q[u].x, g0x, ihx, magic, nm1);
             const uint32_t cy = coarse_coord(q[u].y, g0y, ihy, magic, nm1);
             const uint32_t cz = coarse_coord(q[u].z, g0z, ihz, magic, nm1);
-            set[u] = i < n ? (uint32_t)__ldg(a.table + (((size_t)cz << (2 * mb)) | ((size_t)cy << mb) | cx)) : 0u;
+            const uint32_t bit = (cz << (2 * mb)) | (cy << mb) | cx;
+            uint32_t st = 0u;
+            if (i < n) {
+                const uint32_t pw = __ldg(a.plain + (bit >> 5)), lw = __ldg(a.listed + (bit >> 5));
+                if ((pw >> (bit & 31)) & 1u)
+                    st = 1u << a.bin_owner[assign_bin_index(cx >> bsh, cy >> bsh, cz >> bsh)];      /* (plain bits only exist with mb >= DOM_ASSIGN_LOG) */
+                if ((lw >> (bit & 31)) & 1u) st |= (uint32_t)__ldg(a.table + bit);
+            }
+            set[u] = st;
         }
 #pragma unroll
         for (int u = 0; u < SP_U; ++u)
@@ -608,6 +678,11 @@ extern "C" int sogpu_domain_open(sogpu_t *h, const sogpu_domain_cfg_t *cfg, void
         const size_t swords = super_words(g.mb);
         CU(cudaMalloc(&D->d_table, (n_cells + 2) * sizeof(unsigned short)));
         CU(cudaMalloc(&D->d_any, words * sizeof(uint32_t)));
+        CU(cudaMalloc(&D->d_bin_owner, DOM_ASSIGN_BINS));
+        if (R > 1) {
+            CU(cudaMalloc(&D->d_plain, words * sizeof(uint32_t)));
+            CU(cudaMalloc(&D->d_listed, words * sizeof(uint32_t)));
+        }
         CU(cudaMalloc(&D->d_mymask, words * sizeof(uint32_t)));
         CU(cudaMalloc(&D->d_super, swords * sizeof(uint32_t)));
         CU(cudaMemsetAsync(D->d_table, 0, (n_cells + 2) * sizeof(unsigned short), h->stream));
@@ -671,8 +746,9 @@ extern "C" int sogpu_domain_close(sogpu_t *h)
     cudaFree(D->recv[0]);
     if (D->recv[1] != D->recv[0]) cudaFree(D->recv[1]);
     cudaFree(D->ctrl); cudaFree(D->stage); cudaFree(D->hits); cudaFree(D->d_counts); cudaFree(D->d_flags); cudaFree(D->d_nrecv32);
-    cudaFree(D->d_owner); cudaFree(D->d_bins);
+    cudaFree(D->d_owner); cudaFree(D->d_cubes); cudaFree(D->d_bins);
     cudaFree(D->d_table); cudaFree(D->d_any); cudaFree(D->d_mymask); cudaFree(D->d_super);
+    cudaFree(D->d_plain); cudaFree(D->d_listed); cudaFree(D->d_bin_owner);
     delete D;
     h->mask_ready = nullptr;
     h->dom = nullptr;
@@ -692,23 +768,30 @@ extern "C" int sogpu_domain_begin(sogpu_t *h, const void *d_centers, const void 
     const int R = D->cfg.n_ranks, me = D->cfg.rank;
     int rc = ensure_query(h, nh);
     if (rc) return rc;
+    GridDev g;
+    dom_geometry(h, g);
+    if (D->marked && R > 1) {      /* un-mark the previous catalog (its cubes are still in d_cubes) in the destination table */
+        ProfScope p(h, KID_MARK_MASK);
+        k_mark_table<<<std::min((D->marked_nh * MARK_LANES + 255) / 256, h->sm_count * 8), 256, 0, s>>>(
+            g, D->d_cubes, D->marked_nh, D->d_owner, me, (uint32_t *)D->d_table, D->d_any, D->d_super, D->d_mymask,
+            D->d_plain, D->d_listed, 1);
+    }
+    D->marked = false;
     if (nh > D->owner_cap) {
+        CU(cudaStreamSynchronize(s));        /* (the un-marking above reads the buffers that are replaced here) */
         cudaFree(D->d_owner); D->d_owner = nullptr; D->owner_cap = 0;
+        cudaFree(D->d_cubes); D->d_cubes = nullptr;
+        CU(cudaMalloc(&D->d_cubes, (size_t)std::max(nh, 1024) * sizeof(int4)));
         CU(cudaMalloc(&D->d_owner, (size_t)std::max(nh, 1024)));
         D->owner_cap = std::max(nh, 1024);
     }
-    GridDev g;
-    dom_geometry(h, g);
-    if (D->marked && R > 1) {      /* un-mark the previous catalog (still in h->d_centers / d_rgtp / d_owner) in the destination table */
-        ProfScope p(h, KID_MARK_MASK);
-        k_mark_table<<<std::min((D->marked_nh * MARK_LANES + 255) / 256, h->sm_count * 8), 256, 0, s>>>(
-            g, h->d_centers, h->d_rgtp, D->marked_nh, D->marked_balls, D->d_owner, me, (uint32_t *)D->d_table, D->d_any,
-            D->d_super, D->d_mymask, 1);
-    }
-    D->marked = false;
     {   /* the bitmaps: 2 x 2^(3 mb) bits + the pre-filter — a few to 32 MB, microseconds */
         const size_t words = ((size_t)1 << (3 * g.mb)) / 32 + 1, swords = super_words(g.mb);
-        if (R > 1) CU(cudaMemsetAsync(D->d_any, 0, words * sizeof(uint32_t), s));
+        if (R > 1) {
+            CU(cudaMemsetAsync(D->d_any, 0, words * sizeof(uint32_t), s));
+            CU(cudaMemsetAsync(D->d_plain, 0, words * sizeof(uint32_t), s));
+            CU(cudaMemsetAsync(D->d_listed, 0, words * sizeof(uint32_t), s));
+        }
         CU(cudaMemsetAsync(D->d_mymask, 0, words * sizeof(uint32_t), s));
         CU(cudaMemsetAsync(D->d_super, 0, swords * sizeof(uint32_t), s));
     }
@@ -728,22 +811,25 @@ extern "C" int sogpu_domain_begin(sogpu_t *h, const void *d_centers, const void 
     CU(cudaMemsetAsync(D->d_flags, 0, sizeof(uint32_t), s));
     h->stats.last_kernel_launches = 0;
     {
-        ProfScope p(h, KID_ASSIGN, 0.0, 3);
+        ProfScope p(h, KID_ASSIGN, 0.0, R > 1 ? 4 : 0);
         if (R > 1) {
             CU(cudaMemsetAsync(D->d_bins, 0, (DOM_ASSIGN_BINS + 1) * sizeof(unsigned long long), s));
             double vol = (double)D->cfg.period[0] * D->cfg.period[1] * D->cfg.period[2];
             k_assign_hist<<<(nh + 255) / 256, 256, 0, s>>>(g, h->d_centers, h->d_rgtp, nh, (double)D->cfg.n_total / vol, D->d_bins);
             k_assign_scan<<<1, 1024, 0, s>>>(D->d_bins);
-            k_assign_owner<<<(nh + 255) / 256, 256, 0, s>>>(g, h->d_centers, nh, R, D->d_bins, D->d_owner);
+            k_assign_bin_owner<<<DOM_ASSIGN_BINS / 256, 256, 0, s>>>(R, D->d_bins, D->d_bin_owner);
+            k_assign_owner<<<(nh + 255) / 256, 256, 0, s>>>(g, h->d_centers, nh, D->d_bin_owner, D->d_owner);
         } else {
             CU(cudaMemsetAsync(D->d_owner, 0, (size_t)nh, s));
         }
     }
     {
-        ProfScope p(h, KID_MARK_MASK);
+        ProfScope p(h, KID_MARK_MASK, 0.0, 2);
+        k_halo_cubes<<<(nh + 255) / 256, 256, 0, s>>>(g, h->d_centers, h->d_rgtp, nh, n_balls, D->d_cubes, D->d_owner,
+                                                        R > 1 ? D->d_bin_owner : nullptr);
         k_mark_table<<<std::min((nh * MARK_LANES + 255) / 256, h->sm_count * 8), 256, 0, s>>>(
-            g, h->d_centers, h->d_rgtp, nh, n_balls, D->d_owner, me, R > 1 ? (uint32_t *)D->d_table : nullptr,
-            R > 1 ? D->d_any : nullptr, D->d_super, D->d_mymask, 0);
+            g, D->d_cubes, nh, D->d_owner, me, R > 1 ? (uint32_t *)D->d_table : nullptr,
+            R > 1 ? D->d_any : nullptr, D->d_super, D->d_mymask, D->d_plain, D->d_listed, 0);
         D->marked = true; D->marked_balls = n_balls; D->marked_nh = nh;
     }
     CU(cudaGetLastError());
@@ -834,7 +920,8 @@ extern "C" int sogpu_domain_push(sogpu_t *h, int barrier)
             memset(&sa, 0, sizeof(sa));
             dom_geometry(h, sa.g);
             sa.hits = D->hits; sa.n_hits = D->d_counts + 3 * ROUTE_MAXR + 1; sa.hits_cap = (unsigned long long)D->cfg.recv_cap;
-            sa.table = D->d_table; sa.R = R; sa.flags = D->d_flags;
+            sa.table = D->d_table; sa.plain = D->d_plain; sa.listed = D->d_listed; sa.bin_owner = D->d_bin_owner;
+            sa.R = R; sa.flags = D->d_flags;
             for (int d = 0; d < R; ++d) {
                 if (d == D->cfg.rank) {
                     sa.dst[d] = D->recv[D->parity]; sa.cursor[d] = &D->ctrl->cursor[D->parity];

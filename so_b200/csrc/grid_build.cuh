@@ -1039,3 +1039,137 @@ __global__ void __launch_bounds__(BS_NT, 8) k_bucket_sort_sparse(const float4 *_
         }
     }
 }
+
+/* The same for the many SMALL live buckets, one WARP per bucket: at 1024^3 a final bucket of a focused grid is a
+ * pencil of 4 rows of cells that meets three or four halos — ~240 particles in ~80 marked cells — and a CTA spent
+ * its time in barriers and in the latency chain bounds -> mask words -> particles -> stores of one bucket at a
+ * time (ncu: 40 % of the stall samples on those three loads, 3.2 warps per issue at the barrier).  Here 32 warps
+ * per SM each own a bucket: no block barrier, two mask words and up to BW_IT particles per lane; the particles are
+ * read twice (the second time from L1/L2) instead of being held in registers.  Buckets with more than
+ * 32 x BW_IT particles or more than BW_CAP marked cells are appended to `big` for k_bucket_sort_sparse. */
+#define BW_NT 256
+#define BW_IT 16
+#define BW_CAP 1024
+__global__ void __launch_bounds__(BW_NT, 4) k_bucket_sort_sparse_warp(const float4 *__restrict__ in4, GridDev g, int cell_bits,
+                                                                      const uint32_t *__restrict__ bstart,
+                                                                      float4 *__restrict__ sorted, uint32_t *__restrict__ ce,
+                                                                      const uint32_t *__restrict__ live,
+                                                                      const uint32_t *__restrict__ live_n,
+                                                                      uint32_t *__restrict__ big, uint32_t *__restrict__ big_n)
+{
+    __shared__ uint32_t s_mw[BW_NT / 32][128], s_mpre[BW_NT / 32][132];
+    __shared__ uint32_t s_cnt[BW_NT / 32][BW_CAP + 4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t *mw = s_mw[w], *mpre = s_mpre[w], *cnt = s_cnt[w];
+    const int ncells = 1 << cell_bits;
+    const int nrow = ncells >> g.lb;                         /* fine rows of a bucket (host: cell_bits >= lb) */
+    const int wpr = (g.nc >> g.ms) >> 5;                     /* mask words per row (host: nc >> ms >= 32)     */
+    const int nwords = nrow * wpr;                           /* <= 128                                        */
+    const uint32_t sub = (1u << g.ms) - 1u;
+    const uint32_t n_buckets = __ldg(live_n);
+    const uint32_t gw = blockIdx.x * (BW_NT / 32) + (uint32_t)w, nwarp = gridDim.x * (BW_NT / 32);
+    for (uint32_t bi = gw; bi < n_buckets; bi += nwarp) {
+        const uint32_t b = __ldg(live + bi);
+        const uint32_t b0 = __ldg(bstart + b), b1 = __ldg(bstart + b + 1), nb = b1 - b0;
+        if (nb > 32u * BW_IT) {
+            if (lane == 0) big[atomicAdd(big_n, 1u)] = b;
+            continue;
+        }
+        /* the bucket's mask words and their popcount prefix */
+        uint32_t carry = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int t = lane + 32 * k;
+            uint32_t myw = 0u;
+            if (t < nwords) {
+                const int r = t / wpr, j = t - r * wpr;
+                const uint32_t rk = (b << (cell_bits - g.lb)) + (uint32_t)r;           /* row key */
+                const uint32_t m = (1u << g.tb) - 1u, lo = rk & ((1u << (2 * g.tb)) - 1u), hi = rk >> (2 * g.tb);
+                const uint32_t iy = ((hi & ((1u << (g.lb - g.tb)) - 1u)) << g.tb) | (lo & m);
+                const uint32_t iz = ((hi >> (g.lb - g.tb)) << g.tb) | (lo >> g.tb);
+                const uint32_t mrow = ((iz >> g.ms) << (2 * g.mb)) | ((iy >> g.ms) << g.mb);
+                myw = __ldg(g.mask + (mrow >> 5) + j);
+            }
+            const uint32_t pc = __popc(myw);
+            uint32_t x = pc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                if (lane >= o) x += u;
+            }
+            mw[t] = myw;
+            mpre[t] = carry + x - pc;
+            carry += __shfl_sync(0xFFFFFFFFu, x, 31);
+        }
+        const uint32_t ncomp = carry << g.ms;                /* compact (marked) fine cells of this bucket */
+        if (ncomp > BW_CAP) {
+            if (lane == 0) big[atomicAdd(big_n, 1u)] = b;
+            __syncwarp();
+            continue;
+        }
+        for (uint32_t i = lane; i <= ncomp; i += 32) cnt[i] = 0u;
+        __syncwarp();
+        auto compact = [&](uint32_t c) -> uint32_t {          /* cell inside the bucket -> compact index */
+            const uint32_t r = c >> g.lb, x = c & (uint32_t)(g.nc - 1), xc = x >> g.ms;
+            const uint32_t wi = r * (uint32_t)wpr + (xc >> 5), bp = xc & 31u;
+            return ((mpre[wi] + __popc(mw[wi] & ((1u << bp) - 1u))) << g.ms) | (x & sub);
+        };
+        uint32_t cr[BW_IT];
+#pragma unroll
+        for (int k = 0; k < BW_IT; ++k) {
+            const uint32_t i = lane + 32 * k;
+            if (i < nb) {
+                const float4 q = __ldg(in4 + b0 + i);
+                const uint32_t ci = compact(cell_key_low(q, g, cell_bits));
+                cr[k] = (ci << 16) | atomicAdd(&cnt[ci], 1u);
+            }
+        }
+        __syncwarp();
+        {   /* exclusive scan over the compact cells, 32 at a time with a running carry; cnt[ncomp] = particles */
+            uint32_t run = 0;
+            for (uint32_t base = 0; base < ncomp; base += 32) {
+                const uint32_t i = base + lane;
+                const uint32_t v = i < ncomp ? cnt[i] : 0u;
+                uint32_t x = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                    if (lane >= o) x += u;
+                }
+                if (i < ncomp) cnt[i] = run + x - v;
+                run += __shfl_sync(0xFFFFFFFFu, x, 31);
+            }
+            if (lane == 0) cnt[ncomp] = run;
+        }
+        __syncwarp();
+        /* particles to their final slots (second read: L1 / L2) */
+#pragma unroll
+        for (int k = 0; k < BW_IT; ++k) {
+            const uint32_t i = lane + 32 * k;
+            if (i < nb) sorted[b0 + cnt[cr[k] >> 16] + (cr[k] & 0xFFFFu)] = __ldg(in4 + b0 + i);
+        }
+        /* cell table: the bucket's first entry, every marked cell, and the entry right behind a marked cell */
+        uint32_t *ceb = ce + ((size_t)b << cell_bits);
+        if (lane == 0) ceb[0] = b0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int t = lane + 32 * k;
+            if (t < nwords) {
+                const int r = t / wpr, j = t - r * wpr;
+                uint32_t word = mw[t], k0 = mpre[t];
+                while (word) {
+                    const int bp = __ffs(word) - 1;
+                    word &= word - 1u;
+                    const uint32_t xc = (uint32_t)j * 32u + (uint32_t)bp;
+                    for (uint32_t sx = 0; sx <= sub; ++sx) {
+                        const uint32_t c = ((uint32_t)r << g.lb) + ((xc << g.ms) | sx), kc = (k0 << g.ms) | sx;
+                        ceb[c] = b0 + cnt[kc];
+                        if (sx == sub && c + 1u < (uint32_t)ncells) ceb[c + 1u] = b0 + cnt[kc + 1u];
+                    }
+                    ++k0;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}

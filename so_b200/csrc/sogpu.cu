@@ -2640,6 +2640,7 @@ struct sogpu {
     bool build_attr_done;
     unsigned long long *d_timeline;  /* SOGPU_DEBUG_TIMELINE */
     uint32_t *d_live;                /* focused builds: list of live final buckets (+ its length) */
+    bool bucket_warp;                /* focused builds: small final buckets are sorted one per warp */
     size_t live_cap;
     unsigned long long *d_route;     /* domain runs: per-destination counters */
     unsigned short *d_route_table;   /* destination ranks per coarse cell */
@@ -2720,6 +2721,7 @@ struct ProfScope {   /* brackets one (group of) kernel launch(es) with events wh
         r.kid = kid; r.launches = launches; r.a = prof_event(h); r.b = prof_event(h);
         cudaEventRecord(r.a, h->launch_stream);
     }
+    void add_launch() { h->stats.last_kernel_launches += 1; if (on) r.launches += 1; }
     ~ProfScope()
     {
         if (!on) return;
@@ -2784,6 +2786,8 @@ extern "C" int sogpu_create(sogpu_t **out, int device)
     if (const char *e = getenv("SOGPU_SCAN1_MAX")) h->scan1_max = (size_t)atoll(e);
     if (const char *e = getenv("SOGPU_TMA")) h->use_tma = atoi(e) != 0;
     if (const char *e = getenv("SOGPU_MASK_RMIN")) h->mask_rmin_cells = atof(e);
+    h->bucket_warp = true;
+    if (const char *e = getenv("SOGPU_BUCKET_WARP")) h->bucket_warp = atoi(e) != 0;
     h->cls_small_max = 256.0f; h->cls_huge_min = 32768.0f;   /* warp class: balls that fit its 384 staged keys; above 32768: a
                                                               * 1024-thread CTA per halo, beside the fused kernel (8192 was
                                                               * measured 5 % slower at 1024^3: the big CTAs crowd out the fused ones) */
@@ -3400,9 +3404,9 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
             const uint32_t *live = nullptr, *live_n = nullptr;
             if (g.mask && nb >= 4096u) {
                 /* focused build with many final buckets: settle the empty ones outside the mask first */
-                if ((size_t)nb + 1 > h->live_cap) {
+                if ((size_t)nb + 1 > h->live_cap) {          /* two lists: live buckets, and those left to the CTA kernel */
                     cudaFree(h->d_live); h->d_live = nullptr; h->live_cap = 0;
-                    CU(cudaMalloc(&h->d_live, ((size_t)nb + 1) * sizeof(uint32_t)));
+                    CU(cudaMalloc(&h->d_live, 2 * ((size_t)nb + 1) * sizeof(uint32_t)));
                     h->live_cap = (size_t)nb + 1;
                 }
                 CU(cudaMemsetAsync(h->d_live + nb, 0, sizeof(uint32_t), s));
@@ -3413,6 +3417,15 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
                 !(L == 0 && !g.indexed) && !getenv("SOGPU_DENSE_BUCKETS")) {
                 /* focused grid: per-bucket work proportional to its marked cells (k_bucket_sort_sparse) */
                 grid = (int)std::min<int64_t>((int64_t)nb, (int64_t)h->sm_count * 8);
+                if (live && h->bucket_warp) {
+                    /* small buckets one per warp; what is left (many particles / marked cells) one per CTA */
+                    uint32_t *big = h->d_live + (size_t)nb + 1, *big_n = big + nb;
+                    CU(cudaMemsetAsync(big_n, 0, sizeof(uint32_t), s));
+                    k_bucket_sort_sparse_warp<<<h->sm_count * 4, BW_NT, 0, s>>>(src, g, cell_bits, bstart, h->d_sorted, h->d_ce,
+                                                                               live, live_n, big, big_n);
+                    live = big; live_n = big_n;
+                    p.add_launch();
+                }
                 k_bucket_sort_sparse<<<grid, BS_NT, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, live, live_n);
             } else if (n_work / (int64_t)nb < 160 && nb >= 4096u) {      /* sparse buckets: small CTAs, many in flight */
                 grid = (int)std::min<int64_t>((int64_t)nb, (int64_t)h->sm_count * 48);

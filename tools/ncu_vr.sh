@@ -1,4 +1,5 @@
+# ncu --set full on the kernels one rank of an 8-rank domain step runs (virtual ranks on one GPU); usage: bash tools/ncu_vr.sh
 set -x
-timeout 600 python tools/virtual_ranks_probe.py --ranks 8 --scale 0.5 --steps 1 > gpurun_out/vr8_half.json 2> gpurun_out/vr8_half.err || exit 1
-timeout 800 ncu --set full --clock-control none --import-source on -k regex:k_route_stage --launch-skip 26 --launch-count 2 -o gpurun_out/r2_route_multi -f python tools/virtual_ranks_probe.py --ranks 8 --scale 0.5 --steps 1 > gpurun_out/ncu_vr.log 2>&1
+timeout 600 python tools/virtual_ranks_probe.py --ranks 8 --steps 1 > gpurun_out/vr8_s1.json 2> gpurun_out/vr8_s1.err || exit 1
+timeout 1000 ncu --set full --clock-control none --import-source on -k regex:'k_bucket_sort_sparse|k_lvl_partition|k_so_query|k_mark_table|k_route_split|k_lvl_hist' --launch-skip 264 --launch-count 32 -o gpurun_out/r2_rank8 -f python tools/virtual_ranks_probe.py --ranks 8 --steps 1 > gpurun_out/ncu_vr.log 2>&1
 tail -3 gpurun_out/ncu_vr.log
