@@ -623,7 +623,8 @@ def run_ours(args):
     roof_gather = roofline_entry(kernels, "gather(k_so_query*)", peak, peak_src,
                                  {"evals": units["eval"], "evals_min": float(st["last_members"]) + float((owner == 0).sum()),
                                   "note": "rank 0's halos; E_min = sum(N_Delta + 1)"})
-    build_names = [k_ for k_ in ("k_lvl_hist", "k_scan", "k_lvl_partition", "k_bucket_sort") if k_ in kernels]
+    build_names = [k_ for k_ in ("k_lvl_hist", "k_scan", "k_lvl_partition", "k_bucket_live", "k_bucket_sort", "k_bucket_sort(big)")
+                   if k_ in kernels]
     t_build = sum(kernels[k_]["ms_per_step"] for k_ in build_names)
     roof_build = None
     if t_build > 0:

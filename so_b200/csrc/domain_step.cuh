@@ -934,7 +934,7 @@ extern "C" int sogpu_domain_push(sogpu_t *h, int barrier)
                     sa.cap[d] = (unsigned long long)D->cfg.stage_cap; sa.flag_bit[d] = 1u;
                 }
             }
-            ProfScope p(h, KID_ROUTE, 0.0);
+            ProfScope p(h, KID_ROUTE_SPLIT, 0.0);
             k_route_split<<<h->sm_count * 4, SP_NT, 0, s>>>(sa);
         }
         if (!direct) {

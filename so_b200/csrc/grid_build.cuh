@@ -661,13 +661,17 @@ __global__ void __launch_bounds__(RT_NT, 3) k_lvl_partition_rt(const float4 *__r
  * bucket with a marked cell (live: written in full) or is the first entry of the next bucket. */
 __global__ void __launch_bounds__(256) k_bucket_live(GridDev g, int cell_bits, uint32_t n_buckets,
                                                      const uint32_t *__restrict__ bstart, uint32_t *__restrict__ ce,
-                                                     uint32_t *__restrict__ live, uint32_t *__restrict__ live_n)
+                                                     uint32_t *__restrict__ live, uint32_t *__restrict__ live_n,
+                                                     uint32_t big_from, uint32_t *__restrict__ big, uint32_t *__restrict__ big_n)
 {
+    /* big != NULL: live buckets with more than big_from particles go to a list of their own (one CTA each,
+     * k_bucket_sort_sparse, concurrently with the warp-per-bucket kernel that takes the others) */
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    bool is_live = false;
+    bool is_live = false, is_big = false;
     if (b < n_buckets) {
         const uint32_t b0 = __ldg(bstart + b), b1 = __ldg(bstart + b + 1);
         is_live = b1 > b0;
+        is_big = big != nullptr && b1 - b0 > big_from;
         if (!is_live) {
             /* the bucket is a stretch of one row of cells, or a few whole rows: per row its coarse cells
              * are consecutive mask bits, tested a word at a time */
@@ -686,13 +690,22 @@ __global__ void __launch_bounds__(256) k_bucket_live(GridDev g, int cell_bits, u
             if (!is_live) ce[(size_t)b << cell_bits] = b0;
         }
     }
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_live);
+    const int lane = threadIdx.x & 31;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_live && !is_big);
     if (m) {
-        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        const int leader = __ffs(m) - 1;
         uint32_t base = 0;
         if (lane == leader) base = atomicAdd(live_n, (uint32_t)__popc(m));
         base = __shfl_sync(0xFFFFFFFFu, base, leader);
-        if (is_live) live[base + __popc(m & ((1u << lane) - 1u))] = b;
+        if (is_live && !is_big) live[base + __popc(m & ((1u << lane) - 1u))] = b;
+    }
+    const uint32_t mb = __ballot_sync(0xFFFFFFFFu, is_big);
+    if (mb) {
+        const int leader = __ffs(mb) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(big_n, (uint32_t)__popc(mb));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (is_big) big[base + __popc(mb & ((1u << lane) - 1u))] = b;
     }
 }
 

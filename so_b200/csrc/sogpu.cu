@@ -2550,13 +2550,14 @@ __global__ void __launch_bounds__(256) k_member_unkeys(const unsigned long long 
 enum {
     KID_LVL_HIST = 0, KID_LVL_SCAN, KID_LVL_PARTITION, KID_BUCKET_SORT, KID_MASS_TABLE, KID_CLASSIFY,
     KID_QUERY_WARP, KID_QUERY_BLOCK, KID_OFFSETS, KID_EMIT_WARP, KID_EMIT_BLOCK, KID_BALL_GATHER,
-    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_VCIRC, KID_TAG, KID_ROUTE, KID_ASSIGN, KID_PUSH, KID_BARRIER, KID_QUERY_FUSED, KID_SEGSORT, KID_N
+    KID_QUERY_HUGE, KID_EMIT_HUGE, KID_MARK_MASK, KID_VCIRC, KID_TAG, KID_ROUTE, KID_ASSIGN, KID_PUSH, KID_BARRIER, KID_QUERY_FUSED, KID_SEGSORT,
+    KID_ROUTE_SPLIT, KID_BUCKET_LIVE, KID_BUCKET_BIG, KID_N
 };
 static const char *const g_kernel_names[KID_N] = {
     "k_lvl_hist", "k_scan", "k_lvl_partition", "k_bucket_sort", "k_mass_table", "k_classify",
     "k_so_query<32>", "k_so_query<256>", "k_offsets", "k_so_emit<32>", "k_so_emit<256>", "k_ball_gather",
     "k_so_query<1024>", "k_so_emit<1024>", "k_mark_mask", "k_vcirc", "k_tag_claim+settle", "k_route",
-    "k_assign", "k_push", "k_dom_barrier", "k_so_query_fused", "k_segsort"};
+    "k_assign", "k_push", "k_dom_barrier", "k_so_query_fused", "k_segsort", "k_route_split", "k_bucket_live", "k_bucket_sort(big)"};
 
 struct ProfRec { int kid, launches; cudaEvent_t a, b; };
 
@@ -2721,7 +2722,6 @@ struct ProfScope {   /* brackets one (group of) kernel launch(es) with events wh
         r.kid = kid; r.launches = launches; r.a = prof_event(h); r.b = prof_event(h);
         cudaEventRecord(r.a, h->launch_stream);
     }
-    void add_launch() { h->stats.last_kernel_launches += 1; if (on) r.launches += 1; }
     ~ProfScope()
     {
         if (!on) return;
@@ -3396,42 +3396,72 @@ static int build_grid_impl(sogpu *h, int32_t focus_nh, int focus_balls)
         const uint32_t nb = 1u << cbt;
         const uint32_t *bstart = h->d_lvl_start[L ? L - 1 : 0];
         int grid = (int)std::min<int64_t>((int64_t)nb, (int64_t)h->sm_count * 16);
-        ProfScope p(h, KID_BUCKET_SORT, 32.0 * N + 4.0 * (double)ncell);
-        if (h->two_level == 2)
+        const double sort_bytes = 32.0 * N + 4.0 * (double)ncell;
+        if (h->two_level == 2) {
+            ProfScope p(h, KID_BUCKET_SORT, sort_bytes);
             k_bucket_sort<<<grid, BKT_THREADS, bkt_smem, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, (L == 0 && !g.indexed) ? 1 : 0);
-        else
-        {
+        } else {
             const uint32_t *live = nullptr, *live_n = nullptr;
+            const bool sparse_ok = g.mask && cell_bits >= lb && (nc >> g.ms) >= 32 &&
+                                   ((ncell >> cbt) >> lb) * ((nc >> g.ms) >> 5) <= 128 && !(L == 0 && !g.indexed) &&
+                                   !getenv("SOGPU_DENSE_BUCKETS");
+            bool split_big = false;
             if (g.mask && nb >= 4096u) {
                 /* focused build with many final buckets: settle the empty ones outside the mask first */
-                if ((size_t)nb + 1 > h->live_cap) {          /* two lists: live buckets, and those left to the CTA kernel */
+                /* three lists of nb + 1 words (the last one is the length): live buckets (those for the
+                 * warp-per-bucket kernel when it is used), buckets with many particles, buckets the warp kernel left */
+                if ((size_t)nb + 1 > h->live_cap) {
                     cudaFree(h->d_live); h->d_live = nullptr; h->live_cap = 0;
-                    CU(cudaMalloc(&h->d_live, 2 * ((size_t)nb + 1) * sizeof(uint32_t)));
+                    CU(cudaMalloc(&h->d_live, 3 * ((size_t)nb + 1) * sizeof(uint32_t)));
                     h->live_cap = (size_t)nb + 1;
                 }
+                split_big = sparse_ok && h->bucket_warp;
+                uint32_t *big = h->d_live + (size_t)nb + 1;
                 CU(cudaMemsetAsync(h->d_live + nb, 0, sizeof(uint32_t), s));
-                k_bucket_live<<<(nb + 255) / 256, 256, 0, s>>>(g, cell_bits, nb, bstart, h->d_ce, h->d_live, h->d_live + nb);
+                if (split_big) CU(cudaMemsetAsync(big + nb, 0, sizeof(uint32_t), s));
+                ProfScope pl(h, KID_BUCKET_LIVE);
+                k_bucket_live<<<(nb + 255) / 256, 256, 0, s>>>(g, cell_bits, nb, bstart, h->d_ce, h->d_live, h->d_live + nb,
+                                                               32u * BW_IT, split_big ? big : nullptr, big + nb);
                 live = h->d_live; live_n = h->d_live + nb;
             }
-            if (g.mask && cell_bits >= lb && (nc >> g.ms) >= 32 && ((ncell >> cbt) >> lb) * ((nc >> g.ms) >> 5) <= 128 &&
-                !(L == 0 && !g.indexed) && !getenv("SOGPU_DENSE_BUCKETS")) {
+            if (sparse_ok) {
                 /* focused grid: per-bucket work proportional to its marked cells (k_bucket_sort_sparse) */
                 grid = (int)std::min<int64_t>((int64_t)nb, (int64_t)h->sm_count * 8);
-                if (live && h->bucket_warp) {
-                    /* small buckets one per warp; what is left (many particles / marked cells) one per CTA */
-                    uint32_t *big = h->d_live + (size_t)nb + 1, *big_n = big + nb;
-                    CU(cudaMemsetAsync(big_n, 0, sizeof(uint32_t), s));
-                    k_bucket_sort_sparse_warp<<<h->sm_count * 4, BW_NT, 0, s>>>(src, g, cell_bits, bstart, h->d_sorted, h->d_ce,
-                                                                               live, live_n, big, big_n);
-                    live = big; live_n = big_n;
-                    p.add_launch();
+                if (split_big) {
+                    /* buckets with many particles one per CTA on a side stream, the others one per warp beside them;
+                     * what the warp kernel cannot hold (too many marked cells for its counters: rare) afterwards */
+                    uint32_t *big = h->d_live + (size_t)nb + 1, *rest = big + (size_t)nb + 1;
+                    CU(cudaMemsetAsync(rest + nb, 0, sizeof(uint32_t), s));
+                    CU(cudaEventRecord(h->ev_fork, s));
+                    CU(cudaStreamWaitEvent(h->aux[1], h->ev_fork, 0));
+                    {
+                        h->launch_stream = h->aux[1];
+                        ProfScope pb(h, KID_BUCKET_BIG);
+                        k_bucket_sort_sparse<<<grid, BS_NT, 0, h->aux[1]>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, big, big + nb);
+                    }
+                    h->launch_stream = s;
+                    CU(cudaEventRecord(h->ev_join[1], h->aux[1]));
+                    {
+                        ProfScope p(h, KID_BUCKET_SORT, sort_bytes);
+                        k_bucket_sort_sparse_warp<<<h->sm_count * 4, BW_NT, 0, s>>>(src, g, cell_bits, bstart, h->d_sorted, h->d_ce,
+                                                                                   live, live_n, rest, rest + nb);
+                    }
+                    {
+                        ProfScope pb(h, KID_BUCKET_BIG);
+                        k_bucket_sort_sparse<<<h->sm_count, BS_NT, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, rest, rest + nb);
+                    }
+                    CU(cudaStreamWaitEvent(s, h->ev_join[1], 0));
+                } else {
+                    ProfScope p(h, KID_BUCKET_SORT, sort_bytes);
+                    k_bucket_sort_sparse<<<grid, BS_NT, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, live, live_n);
                 }
-                k_bucket_sort_sparse<<<grid, BS_NT, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce, live, live_n);
             } else if (n_work / (int64_t)nb < 160 && nb >= 4096u) {      /* sparse buckets: small CTAs, many in flight */
                 grid = (int)std::min<int64_t>((int64_t)nb, (int64_t)h->sm_count * 48);
+                ProfScope p(h, KID_BUCKET_SORT, sort_bytes);
                 k_bucket_sort_rt<64, 12><<<grid, 64, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce,
                                                              (L == 0 && !g.indexed) ? 1 : 0, live, live_n);
             } else {
+                ProfScope p(h, KID_BUCKET_SORT, sort_bytes);
                 k_bucket_sort_rt<256, 4><<<grid, 256, 0, s>>>(src, g, cell_bits, nb, bstart, h->d_sorted, h->d_ce,
                                                               (L == 0 && !g.indexed) ? 1 : 0, live, live_n);
             }
