@@ -63,9 +63,8 @@ struct DomainState {
     int32_t nh;
     int64_t n_hint;
     bool routed;
-    bool direct;                        /* records are written straight into the receivers' buffers by the routing kernel
-                                         * (run of <= 128 per warp and destination, one remote reservation each) instead of
-                                         * being staged locally and pushed in bulk */
+    bool direct;                        /* k_route_split writes its runs straight into the receivers' buffers (one remote
+                                         * reservation per tile and destination) instead of staging them for k_push_copy */
 };
 
 /* ---- ownership -------------------------------------------------------------------------------------- */
@@ -485,13 +484,21 @@ struct SplitArgs {
 
 #define SP_NT 256
 #define SP_U 8
-/* Tiles of SP_NT x SP_U hits: destination set of every record (owner of the cell's bin if a plain halo covers the
+#define SP_TILE (SP_NT * SP_U)
+/* Tiles of SP_TILE hits: destination set of every record (owner of the cell's bin if a plain halo covers the
  * cell, table entry if a crossing one does — see k_mark_table; a record's cell is recomputed from its position
  * exactly as the routing pass did), the tile's count per destination in shared memory, ONE reservation per
- * destination and tile, then every record is stored once per destination. */
+ * destination and tile; the records are then put in destination order in shared memory and written out as one
+ * contiguous run per destination (consecutive threads, consecutive addresses).
+ *
+ * The destinations are either local staging runs that k_push_copy ships in bulk, or — the default — the peers'
+ * receive buffers themselves: reservation (one system-scope atomic on the peer's cursor per tile and destination)
+ * and stores go over NVLink from here, 4-16 KB per run, and the transfer overlaps the lookups of the other CTAs
+ * instead of following them as a second pass over the same records. */
 __global__ void __launch_bounds__(SP_NT) k_route_split(const __grid_constant__ SplitArgs a)
 {
-    __shared__ uint32_t s_cnt[ROUTE_MAXR], s_pos[ROUTE_MAXR];
+    __shared__ float4 s_rec[SP_TILE];
+    __shared__ uint32_t s_cnt[ROUTE_MAXR], s_pos[ROUTE_MAXR], s_off[ROUTE_MAXR + 1];
     __shared__ unsigned long long s_base[ROUTE_MAXR];
     unsigned long long n = *a.n_hits;
     if (n > a.hits_cap) n = a.hits_cap;                      /* (the overflow was flagged by k_route_stage) */
@@ -500,7 +507,7 @@ __global__ void __launch_bounds__(SP_NT) k_route_split(const __grid_constant__ S
     const float magic = coarse_magic(a.g.ms);
     const uint32_t nm1 = (1u << mb) - 1u;
     const int bsh = mb > DOM_ASSIGN_LOG ? mb - DOM_ASSIGN_LOG : 0;
-    const unsigned long long tile = (unsigned long long)SP_NT * SP_U, ntiles = (n + tile - 1) / tile;
+    const unsigned long long tile = (unsigned long long)SP_TILE, ntiles = (n + tile - 1) / tile;
     for (unsigned long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
         if (threadIdx.x < ROUTE_MAXR) { s_cnt[threadIdx.x] = 0u; s_pos[threadIdx.x] = 0u; }
         __syncthreads();
@@ -541,16 +548,30 @@ __global__ void __launch_bounds__(SP_NT) k_route_split(const __grid_constant__ S
             }
             s_base[d] = base;
         }
+        if (threadIdx.x == 32) {                              /* where every destination's run starts in s_rec */
+            uint32_t o = 0;
+            for (int d = 0; d < a.R; ++d) { s_off[d] = o; o += s_cnt[d]; }
+            s_off[a.R] = o;
+        }
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < SP_U; ++u)
             for (uint32_t m = set[u]; m; m &= m - 1u) {
                 const int d = __ffs(m) - 1;
-                const uint32_t slot = atomicAdd(&s_pos[d], 1u);
-                if (s_base[d] != ~0ull) a.dst[d][s_base[d] + slot] = q[u];
+                const uint32_t slot = atomicAdd(&s_pos[d], 1u), p = s_off[d] + slot;
+                if (p < (uint32_t)SP_TILE) s_rec[p] = q[u];
+                else if (s_base[d] != ~0ull) a.dst[d][s_base[d] + slot] = q[u];      /* (records with several destinations can overfill the tile) */
             }
         __syncthreads();
+        const uint32_t tot = min(s_off[a.R], (uint32_t)SP_TILE);
+        for (uint32_t p = threadIdx.x; p < tot; p += SP_NT) {
+            int d = 0;
+            while (d + 1 < a.R && p >= s_off[d + 1]) ++d;
+            if (s_base[d] != ~0ull) a.dst[d][s_base[d] + (p - s_off[d])] = s_rec[p];
+        }
+        __syncthreads();
     }
+    __threadfence_system();
 }
 
 /* ---- push: staging runs -> the receivers' buffers over NVLink ---------------------------------------- */
@@ -697,7 +718,8 @@ extern "C" int sogpu_domain_open(sogpu_t *h, const sogpu_domain_cfg_t *cfg, void
     D->peer_ctrl[cfg->rank] = D->ctrl;
     D->connected = (R == 1);
     D->n_hint = std::max<int64_t>(cfg->recv_cap / 2, 1);
-    D->direct = getenv("SOGPU_DIRECT_PUSH") != nullptr && atoi(getenv("SOGPU_DIRECT_PUSH")) != 0;
+    D->direct = true;                   /* k_route_split stores into the peers' buffers itself (SOGPU_DIRECT_PUSH=0: staging + k_push_copy) */
+    if (const char *e = getenv("SOGPU_DIRECT_PUSH")) D->direct = atoi(e) != 0;
     return SOGPU_OK;
 }
 

@@ -643,13 +643,15 @@ def _check_domain_step(out, ref, n_ranks):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_ranks,n_balls", [(1, 4), (2, 1), (3, 2), (8, 4)])
-def test_domain_step_matches_single_grid(n_ranks, n_balls):
-    """The stream-ordered domain step (device-side ownership, destination table, one-pass routing into staging
-    runs, receiver-side reservations, grid build with the particle count read on the device) with all ranks
-    simulated on one device: results of the single full grid bit for bit, incl. error codes, the periodic
-    boundary and halos whose balls outgrow the first masks."""
+@pytest.mark.parametrize("n_ranks,n_balls,direct", [(1, 4, "1"), (2, 1, "1"), (3, 2, "1"), (3, 2, "0"), (8, 4, "1"), (8, 4, "0")])
+def test_domain_step_matches_single_grid(n_ranks, n_balls, direct, monkeypatch):
+    """The stream-ordered domain step (device-side ownership, plain / listed cells and the destination table of the
+    halos at ownership boundaries, one-pass routing into the hit list, k_route_split into the receivers' buffers
+    — direct = "0": into staging runs shipped by k_push_copy —, receiver-side reservations, grid build with the
+    particle count read on the device) with all ranks simulated on one device: results of the single full grid bit
+    for bit, incl. error codes, the periodic boundary and halos whose balls outgrow the first masks."""
     import torch
+    monkeypatch.setenv("SOGPU_DIRECT_PUSH", direct)
     from so_b200 import parallel
     s, centers, rgtp = _domain_step_inputs()
     ref = run_gpu(s.pos, s.mass, centers, rgtp, 200.0)
@@ -672,7 +674,7 @@ def test_domain_step_matches_single_grid(n_ranks, n_balls):
 
 
 @pytest.mark.gpu
-def test_domain_step_reports_overflow_instead_of_writing_past_the_buffers():
+def test_domain_step_reports_overflow_instead_of_writing_past_the_buffers(monkeypatch):
     import torch
     from so_b200 import parallel
     s, centers, rgtp = _domain_step_inputs()
@@ -681,7 +683,11 @@ def test_domain_step_reports_overflow_instead_of_writing_past_the_buffers():
     full[:, :3] = torch.from_numpy(s.pos).to(dev)
     full[:, 3] = float(s.mass)
     torch.cuda.synchronize()
-    for recv_cap, stage_cap, what in [(2000, 1 << 16, "receive"), (1 << 18, 500, "staging")]:
+    for recv_cap, stage_cap, what, direct in [(2000, 1 << 16, "receive", "1"), (2000, 1 << 16, "receive", "0"),
+                                              (1 << 18, 500, "staging", "0")]:
+        # SOGPU_DIRECT_PUSH=0: runs are staged locally and shipped by k_push_copy (default: k_route_split stores
+        # into the receivers' buffers itself, so only the receive buffers can overflow)
+        monkeypatch.setenv("SOGPU_DIRECT_PUSH", direct)
         run = parallel.VirtualDomainStep(2, s.n, s.mass, recv_cap=recv_cap, stage_cap=stage_cap)
         try:
             with pytest.raises(RuntimeError, match=what):
