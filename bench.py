@@ -259,7 +259,8 @@ def traffic_for(name, workload):
     tj = json.load(open(tpath))
     for entry in (tj if isinstance(tj, list) else [tj]):
         if entry.get("workload", "") and workload.startswith(entry["workload"]):
-            hit = [v["dram_bytes_per_launch"] for k, v in entry["kernels"].items() if k.startswith(name)]
+            hit = [v["dram_bytes_per_launch"] for k, v in entry["kernels"].items() if k == name] or \
+                  [v["dram_bytes_per_launch"] for k, v in entry["kernels"].items() if k.startswith(name)]
             if hit:
                 return sum(hit) / len(hit), entry.get("source")
     return None, None
@@ -641,7 +642,8 @@ def run_ours(args):
                 roof_gather["traffic_over_16B_evals_min"] = tg / (16.0 * max(roof_gather["evals_min"], 1.0))
         if roof_build:
             parts = [traffic_for(k_, name)[0] for k_ in ("k_lvl_hist<0>", "k_lvl_hist<1>", "k_lvl_partition_rt<0, 0>",
-                                                            "k_lvl_partition_rt<1, 1>", "k_bucket_sort_sparse")]
+                                                            "k_lvl_partition_rt<1, 1>", "k_bucket_sort_sparse",
+                                                            "k_bucket_sort_sparse_warp")]
             if all(p_ is not None for p_ in parts):
                 roof_build["traffic"] = sum(parts)
     cpu_baseline = None
