@@ -267,20 +267,22 @@ int sogpu_peer_free(sogpu_t *h, void *ptr);
 /* ---- several GPUs: the domain STEP, stream-ordered from the slice to the results ---------------------
  *
  * The calls above keep the host in the loop (masks and counts are read back to size the buffers).  The step
- * below does not: every rank derives the halo ownership and the destination table from the catalog on its own
- * device (identical integer arithmetic everywhere, so nothing is exchanged), routes its slice in ONE pass into
- * local staging runs, reserves its range in every receiver's buffer with one system-scope atomic on the
- * receiver's cursor, copies the runs over NVLink, and meets the other ranks at a flag barrier in peer memory.
+ * below does not: every rank derives the halo ownership and the destinations of every cell from the catalog on
+ * its own device (identical integer arithmetic everywhere, so nothing is exchanged), keeps what some halo can
+ * reach of its slice in ONE streaming pass, sorts those records out by destination tile by tile — one
+ * system-scope atomic per tile on the receiver's cursor reserves the range, the run is stored straight into the
+ * receiver's buffer over NVLink peer memory — and meets the other ranks at a flag barrier in peer memory.
  * The grid build then reads the number of records that arrived from the device.
+ * (SOGPU_DIRECT_PUSH=0: the runs are staged locally and shipped in bulk, which is what stage_cap sizes.)
  *
  *   sogpu_domain_open     buffers of this rank; handles192 = three 64-byte cudaIpc handles (receive buffer 0,
  *                         receive buffer 1, control block) for the other processes of the node
  *   sogpu_domain_connect  pointers to every rank's buffers as seen from THIS process (sogpu_peer_open of the
  *                         handles, or the plain device pointers in a one-process run after sogpu_enable_peer_access)
  *   per step, every rank, same arguments:
- *     sogpu_domain_begin        whole catalog (device): ownership, destination table, own focus mask
+ *     sogpu_domain_begin        whole catalog (device): ownership, destinations per cell, own focus mask
  *     sogpu_domain_route[_host] this rank's slice (or pieces of it), device float4 {x,y,z,m} / pinned host xyz
- *     sogpu_domain_push         reservations + copies (+ barrier)
+ *     sogpu_domain_push         hits -> receivers' buffers (reservations + stores over NVLink), barrier
  *     sogpu_domain_solve        grid over what arrived, SO solve of the owned halos; outputs cover the WHOLE
  *                               catalog: N_Delta / code and M_Delta for owned halos, 0x80808080 elsewhere;
  *                               code -103 = the halo's ball left the mask: step again with a larger n_balls
@@ -291,7 +293,7 @@ typedef struct {
     int64_t n_total;          /* particles of the whole snapshot (fixes the cell size on every rank) */
     float mass;               /* the particle mass (domain steps are for equal-mass snapshots)       */
     float period[3], center[3];
-    int64_t recv_cap;         /* records each receive buffer holds                                   */
+    int64_t recv_cap;         /* records each receive buffer (and the list of this slice's hits) holds */
     int64_t stage_cap;        /* records one per-destination staging area holds (n_ranks > 1)        */
 } sogpu_domain_cfg_t;
 int sogpu_domain_open(sogpu_t *h, const sogpu_domain_cfg_t *cfg, void *handles192);

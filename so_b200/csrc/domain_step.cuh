@@ -4,20 +4,21 @@
  * snapshot and ONE catalog.  Every rank holds a slice of the particle array and the whole (small) catalog.
  * All of the following is enqueued on the rank's stream; nothing is read back by the host before the results:
  *
- *   k_assign_hist/_scan/_owner  owner rank of every halo: halos ordered along a tiled curve through the box, cut
+ *   k_assign_hist/_scan/_bin_owner/_owner
+ *                               owner rank of every halo: 32^3 bins ordered along a tiled curve through the box, cut
  *                               into pieces of equal estimated cost.  Integer arithmetic on identical inputs, so
  *                               every rank computes the same assignment without talking to the others.
- *   k_mark_table                destination table: for every halo, its owner's bit is set in every coarse cell the
- *                               halo can reach within n_balls steps of kdRvir's ball schedule (kd2.c:765-768).
- *                               Again computed redundantly by every rank from the catalog: no mask exchange.
- *   k_table_to_mask             this rank's own focus mask (what the grid build and the ball checks use)
- *   k_route_stage               ONE pass over the slice: each particle is looked up in the table and appended, as a
- *                               {x, y, z, global index} record, to a local staging run per destination (runs are
- *                               reserved per (CTA, round, destination) with local atomics); the rank's own records
- *                               go straight into its receive buffer.
- *   k_push_reserve              one system-scope atomicAdd per destination on the RECEIVER's cursor (peer memory,
- *                               NVLink) reserves the range this rank's records will occupy there
- *   k_push_copy                 staging runs -> the receivers' buffers: large coalesced 16-byte stores over NVLink
+ *   k_halo_cubes, k_mark_table  the coarse cells every halo can reach within n_balls steps of kdRvir's ball schedule
+ *                               (kd2.c:765-768) -> bitmaps: somebody needs the cell / this rank's own focus mask /
+ *                               routing pre-filter; several ranks: cells under "plain" halos (destination = owner of
+ *                               the cell's bin) and under halos at an ownership boundary ("listed": destinations in
+ *                               a 16-bit table).  Computed redundantly by every rank: no mask exchange.
+ *   k_route_stage               ONE streaming pass over the slice: what somebody needs, as {x, y, z, global index}
+ *                               records; one rank: into its receive buffer, several: into the hit list
+ *   k_route_split               hit list -> one contiguous run per destination and tile, reserved with one
+ *                               system-scope atomicAdd on the RECEIVER's cursor and stored straight into the
+ *                               receiver's buffer (peer memory, NVLink)
+ *   (k_push_reserve, k_push_copy  SOGPU_DIRECT_PUSH=0: local staging runs shipped in bulk instead)
  *   k_dom_barrier               flag barrier through peer memory (release / acquire at system scope)
  *   build (n read on the device) + SO solve of the halos this rank owns.
  *

@@ -388,7 +388,7 @@ def _as_tensor_i32(ptr, n, dev):
 
 NOT_MINE = np.int32(-2139062144)      # 0x80808080: halo solved by another rank
 
-FLAG_TEXT = {1: "staging area too small", 2: "receive buffer too small", 4: "a peer's receive buffer too small",
+FLAG_TEXT = {1: "staging area / hit list too small", 2: "receive buffer too small", 4: "a peer's receive buffer too small",
              8: "a peer never reached the barrier"}
 
 
