@@ -564,7 +564,7 @@ class VirtualDomainStep:
             g.close()
 
 
-def owner_numpy(centers, rgtp, n_total, n_ranks, period=(1.0, 1.0, 1.0), center=(0.0, 0.0, 0.0)):
+def owner_numpy(centers, rgtp, n_total, n_ranks, period=(1.0, 1.0, 1.0), center=(0.0, 0.0, 0.0), return_bins=False):
     """The halo ownership of a domain step, restated in numpy operation for operation (k_assign_hist / _scan /
     _owner in so_b200/csrc/domain_step.cuh: 32^3 bins along a tiled curve, integer costs, cut at equal cost).
     Every rank of a domain step computes exactly this on its device; host-side planning and the CPU tests use it."""
@@ -572,7 +572,7 @@ def owner_numpy(centers, rgtp, n_total, n_ranks, period=(1.0, 1.0, 1.0), center=
     rgtp = np.asarray(rgtp, np.float32)
     h = len(rgtp)
     if n_ranks <= 1:
-        return np.zeros(h, np.uint8)
+        return (np.zeros(h, np.uint8), np.zeros(32768, np.uint8)) if return_bins else np.zeros(h, np.uint8)
     L = np.asarray(period, np.float32).astype(np.float64)
     g0 = (np.asarray(center, np.float32).astype(np.float64) - 0.5 * L).astype(np.float32).astype(np.float64)
     t = (centers.astype(np.float64) - g0) / L
@@ -590,7 +590,70 @@ def owner_numpy(centers, rgtp, n_total, n_ranks, period=(1.0, 1.0, 1.0), center=
     lo_, hi_ = excl[key].astype(object), excl[key + 1].astype(object)
     mid = lo_ + (hi_ - lo_) // 2
     own = np.array([min(n_ranks - 1, (int(m) * n_ranks) // total) if total else 0 for m in mid], np.uint8)
+    if return_bins:                       # k_assign_bin_owner: the same rule for every bin, occupied or not
+        lo_, hi_ = excl[:-1].astype(object), excl[1:].astype(object)
+        mid = lo_ + (hi_ - lo_) // 2
+        bin_own = np.array([min(n_ranks - 1, (int(m) * n_ranks) // total) if total else 0 for m in mid], np.uint8)
+        return own, bin_own
     return own
+
+
+def bin_index_numpy(kx, ky, kz):
+    """Index of the ownership bin with coordinates (kx, ky, kz) in 0..31 along the tiled curve (assign_bin_index)."""
+    kx, ky, kz = (np.asarray(v, np.int64) for v in (kx, ky, kz))
+    return ((((kz >> 3) * 4 + (ky >> 3)) * 4 + (kx >> 3)) << 9) | ((kz & 7) << 6) | ((ky & 7) << 3) | (kx & 7)
+
+
+def destinations_numpy(cubes, owner, bin_owner, mb):
+    """Destination ranks of every coarse cell (2^mb per axis) as the domain step derives them (k_halo_cubes,
+    k_mark_table, k_route_split in so_b200/csrc/domain_step.cuh), restated in numpy:
+
+      * a halo is "crossing" if its cube (x0, y0, z0, nx, ny, nz in coarse cells, periodic) touches a 32^3 ownership
+        bin of another owner, "plain" otherwise;
+      * plain halos set a bit per cell in `plain`, crossing halos set `listed` and OR their owner into `table`;
+      * destinations(cell) = (plain ? {owner of the cell's bin} : {}) | (listed ? table : {}).
+
+    Returns (dest, crossing): dest = uint32 bit mask of ranks per cell, shape (2^mb,)*3 indexed [z, y, x]."""
+    nm = 1 << mb
+    sh = mb - 5
+    plain = np.zeros((nm, nm, nm), bool)
+    listed = np.zeros((nm, nm, nm), bool)
+    table = np.zeros((nm, nm, nm), np.uint32)
+    crossing = np.zeros(len(cubes), bool)
+    for h, (x0, y0, z0, nx, ny, nz) in enumerate(cubes):
+        xs, ys, zs = (np.arange(a, a + n) for a, n in ((x0, nx), (y0, ny), (z0, nz)))
+        if sh < 0:
+            crossing[h] = True
+        else:
+            bx, by, bz = (np.unique((v >> sh) & 31) for v in (xs, ys, zs))
+            b = bin_index_numpy(*np.meshgrid(bx, by, bz, indexing="ij"))
+            crossing[h] = bool(np.any(bin_owner[b] != owner[h]))
+        ix = np.ix_(zs % nm, ys % nm, xs % nm)
+        if crossing[h]:
+            listed[ix] = True
+            table[ix] |= np.uint32(1 << int(owner[h]))
+        else:
+            plain[ix] = True
+    dest = np.where(listed, table, np.uint32(0))
+    if sh >= 0:
+        c = np.arange(nm) >> sh
+        kz, ky, kx = np.meshgrid(c, c, c, indexing="ij")
+        of_bin = (np.uint32(1) << bin_owner[bin_index_numpy(kx, ky, kz)].astype(np.uint32)).astype(np.uint32)
+        dest = dest | np.where(plain, of_bin, np.uint32(0))
+    return dest, crossing
+
+
+def coarse_coord_numpy(x, g0, invh, ms, mb):
+    """The routing kernels' cell coordinate (coarse_coord in domain_step.cuh): t = fl(fl(x - g0) * invh) in fp32, then
+    ONE fp32 add of 1.5 * 2^(23 + ms) rounded towards -infinity, whose low mantissa bits are floor(t / 2^ms); & (2^mb - 1).
+    Emulated exactly: the sum of two fp32 numbers is exact in fp64, and rounding it down to fp32 is a comparison."""
+    x = np.asarray(x, np.float32)
+    t = ((x - np.float32(g0)).astype(np.float32) * np.float32(invh)).astype(np.float32)
+    magic = np.float32(1.5 * 2.0 ** (23 + ms))
+    exact = t.astype(np.float64) + np.float64(magic)
+    f = exact.astype(np.float32)
+    f = np.where(f.astype(np.float64) > exact, np.nextafter(f, np.float32(-np.inf)), f).astype(np.float32)
+    return f.view(np.uint32) & np.uint32((1 << mb) - 1)
 
 
 def merge_owned(code, m, group=None):

@@ -269,3 +269,47 @@ def test_owner_numpy_is_balanced_and_compact():
     assert parallel.flags_text(0) == "ok" and "receive" in parallel.flags_text(2)
     rc, sc = parallel.default_caps(1 << 30, 8)
     assert rc > (1 << 30) * 0.3 / 8 and sc > 0 and parallel.default_caps(1000, 1)[1] == 0
+
+
+def test_destination_rule_of_the_domain_step_is_exact():
+    """plain / listed cells (so_b200/csrc/domain_step.cuh: k_halo_cubes, k_mark_table, k_route_split): the destination
+    set derived from "owner of the cell's bin" for plain halos and from the table for halos at an ownership boundary
+    equals the brute-force union of the owners of all halos whose cube covers the cell — for every cell, on
+    catalogs with many overlapping cubes, for 2 .. 16 ranks and for mask grids coarser and finer than the bins."""
+    rng = np.random.default_rng(5)
+    for mb, world, nh in [(6, 2, 300), (6, 8, 600), (7, 5, 1500), (7, 16, 1500), (4, 3, 40)]:
+        nm = 1 << mb
+        centers = (rng.random((nh, 3)) - 0.5).astype(np.float32)
+        rgtp = (0.004 + 0.02 * rng.random(nh) ** 3).astype(np.float32)
+        owner, bin_owner = parallel.owner_numpy(centers, rgtp, 1 << 24, world, return_bins=True)
+        assert len(np.unique(owner)) == world
+        half = np.maximum(1, np.ceil(rgtp * 2.1 * nm).astype(np.int64))               # ~ the 4-ball cube, in cells
+        c0 = np.floor((centers.astype(np.float64) + 0.5) * nm).astype(np.int64)
+        cubes = [(int(c0[h, 0] - half[h]), int(c0[h, 1] - half[h]), int(c0[h, 2] - half[h]),
+                  int(min(nm, 2 * half[h] + 1)), int(min(nm, 2 * half[h] + 1)), int(min(nm, 2 * half[h] + 1))) for h in range(nh)]
+        dest, crossing = parallel.destinations_numpy(cubes, owner, bin_owner, mb)
+        brute = np.zeros((nm, nm, nm), np.uint32)
+        for h, (x0, y0, z0, nx, ny, nz) in enumerate(cubes):
+            brute[np.ix_(np.arange(z0, z0 + nz) % nm, np.arange(y0, y0 + ny) % nm, np.arange(x0, x0 + nx) % nm)] |= np.uint32(1 << int(owner[h]))
+        assert np.array_equal(dest, brute), (mb, world)
+        if mb >= 6 and world <= 8:
+            assert crossing.mean() < 0.9 and not crossing.all()          # the table is the exception, not the rule
+        if mb < 5:
+            assert crossing.all()                                        # bins finer than cells: everything is listed
+
+
+def test_conversion_free_cell_coordinate_equals_floor():
+    """coarse_coord (routing kernels) == ((int)floorf(t) & (nc - 1)) >> ms (the grid build's cell_coord), incl. negative t,
+    exact cell edges and the values just below them."""
+    rng = np.random.default_rng(6)
+    for lb, mb in [(10, 9), (11, 9), (9, 9), (6, 6), (7, 5)]:
+        nc, ms = 1 << lb, lb - mb
+        g0, invh = np.float32(-0.5), np.float32(nc)
+        x = np.concatenate([rng.random(200000).astype(np.float32) - np.float32(0.5),
+                            (rng.random(20000).astype(np.float32) * np.float32(3.0) - np.float32(1.5)),      # outside the box: wraps
+                            (np.arange(-nc, 2 * nc, dtype=np.float64) / nc - 0.5).astype(np.float32)])
+        x = np.concatenate([x, np.nextafter(x, np.float32(-np.inf)), np.nextafter(x, np.float32(np.inf))])
+        t = ((x - g0).astype(np.float32) * invh).astype(np.float32)
+        want = ((np.floor(t).astype(np.int64) & (nc - 1)) >> ms).astype(np.uint32)
+        got = parallel.coarse_coord_numpy(x, g0, invh, ms, mb)
+        assert np.array_equal(got, want), (lb, mb)
