@@ -576,8 +576,10 @@ def run_ours(args):
         g2 = api.SoGpu(device=local, stream=stream.cuda_stream)
         ds2 = parallel.DomainStep(g2, n, mass, recv_cap=rc_, stage_cap=sc_)
 
+        balls2 = int(os.environ.get("SO_BENCH_BALLS", N_BALLS))
+
         def step2():
-            ds2.step(d_centers.data_ptr(), d_rgtp.data_ptr(), h, N_BALLS, d_slice.data_ptr(), n_slice, a, thr, NMEM,
+            ds2.step(d_centers.data_ptr(), d_rgtp.data_ptr(), h, balls2, d_slice.data_ptr(), n_slice, a, thr, NMEM,
                      d_out_n.data_ptr(), d_out_m.data_ptr())
         for _ in range(warmup):
             step2()
@@ -594,6 +596,7 @@ def run_ours(args):
         same = bool(torch.equal(torch.where(d_out_n == int(parallel.NOT_MINE), torch.zeros_like(d_out_n), d_out_n),
                                 torch.where(code == int(parallel.NOT_MINE), torch.zeros_like(code), code)) if world == 1 else True)
         ab[spec + " same_n_delta"] = same
+        ab[spec + " n_recv"] = allsum([float(ds2.result()["n_recv"])])[0]
         ds2.close()
         g2.close()
         for k_, v_ in keep.items():

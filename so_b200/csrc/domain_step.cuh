@@ -64,6 +64,7 @@ struct DomainState {
     int32_t nh;
     int64_t n_hint;
     bool routed;
+    int route_prefetch;                 /* SOGPU_ROUTE_PREFETCH: L2 prefetch of a warp's next run in k_route_stage */
     bool direct;                        /* k_route_split writes its runs straight into the receivers' buffers (one remote
                                          * reservation per tile and destination) instead of staging them for k_push_copy */
 };
@@ -327,6 +328,7 @@ struct StageArgs {
     unsigned long long cap;
     uint32_t flag_bit;
     uint32_t *flags;
+    int prefetch;                    /* ask the L2 for the warp's next run while this one is being looked up */
 };
 
 #define RW_CAP 128           /* records a WARP collects in shared memory before it writes them out */
@@ -461,7 +463,15 @@ __global__ void __launch_bounds__(RT_THREADS, 1) k_route_stage(const __grid_cons
     const uint32_t run = 32u * RT_U;
     const uint32_t nfull = n / run, nrun = (n + run - 1) / run;
     uint32_t r = gw;
-    for (; r < nfull; r += nwarp) body(r, std::true_type());
+    for (; r < nfull; r += nwarp) {
+        if (a.prefetch && r + nwarp < nfull) {
+            const float4 *nx = a.slice + (size_t)(r + nwarp) * run + lane;
+#pragma unroll
+            for (int u = 0; u < RT_U; u += 2)            /* a lane's 16 bytes: two lanes per 32-byte sector, 128-byte lines */
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + u * 32));
+        }
+        body(r, std::true_type());
+    }
     if (r < nrun) body(r, std::false_type());
     if (wcnt) flush();
 }
@@ -721,6 +731,8 @@ extern "C" int sogpu_domain_open(sogpu_t *h, const sogpu_domain_cfg_t *cfg, void
     D->n_hint = std::max<int64_t>(cfg->recv_cap / 2, 1);
     D->direct = true;                   /* k_route_split stores into the peers' buffers itself (SOGPU_DIRECT_PUSH=0: staging + k_push_copy) */
     if (const char *e = getenv("SOGPU_DIRECT_PUSH")) D->direct = atoi(e) != 0;
+    D->route_prefetch = 1;              /* measured at 1024^3, one GPU: 7.68 -> 7.33 ms per step */
+    if (const char *e = getenv("SOGPU_ROUTE_PREFETCH")) D->route_prefetch = atoi(e);
     return SOGPU_OK;
 }
 
@@ -871,6 +883,7 @@ static int dom_stage_args(sogpu *h, StageArgs &a, const void *d_chunk, int64_t n
     a.slice = (const float4 *)d_chunk; a.n = n; a.index_base = (uint32_t)index_base;
     a.super = D->d_super; a.flags = D->d_flags;
     a.cap = (unsigned long long)D->cfg.recv_cap;
+    a.prefetch = D->route_prefetch;
     if (D->cfg.n_ranks > 1) {           /* several ranks: everything somebody needs -> the hit list */
         a.any = D->d_any; a.dst = D->hits; a.cursor = D->d_counts + 3 * ROUTE_MAXR + 1; a.flag_bit = 1u;
     } else {                            /* one rank: straight into its receive buffer */
