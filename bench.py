@@ -9,9 +9,10 @@ Delta = 200 rho_crit (the configuration north_star's target is stated on; 73 of 
 A "step" is one pass of the hot path over that input:
     kdBuildTree (so.c:515) + kdSO/kdRvir for every halo (so.c:540; R/M/N + member lists),
 run as a DOMAIN STEP (so_b200/csrc/domain_step.cuh): every rank holds 1/N of the particle array (as a parallel
-reader delivers it) and the whole catalog; per step each rank derives halo ownership and the destination table
-on its own device, routes its slice in one pass, pushes {x,y,z,index} records into the owners' buffers over
-NVLink peer memory, meets the others at a flag barrier, builds a grid over what arrived and solves its halos.
+reader delivers it) and the whole catalog; per step each rank derives halo ownership and every cell's
+destinations on its own device, keeps what some halo can reach of its slice in one streaming pass, stores those
+{x,y,z,index} records straight into the owners' buffers over NVLink peer memory (k_route_split), meets the others
+at a flag barrier, builds a grid over what arrived and solves its halos.
 At N = 1 the same code is the best single-GPU path (routing = compaction to the 5-20 % of the particles any
 halo can reach).  There is no collective in the timed region.
 
