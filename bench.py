@@ -631,12 +631,16 @@ def run_ours(args):
     build_names = [k_ for k_ in ("k_lvl_hist", "k_scan", "k_lvl_partition", "k_bucket_live", "k_bucket_sort", "k_bucket_sort(big)")
                    if k_ in kernels]
     t_build = sum(kernels[k_]["ms_per_step"] for k_ in build_names)
+    if "k_bucket_sort" in kernels and "k_bucket_sort(big)" in kernels:
+        # the two bucket kernels run side by side on two streams: the longer one is what the step waits for
+        t_build -= min(kernels["k_bucket_sort"]["ms_per_step"], kernels["k_bucket_sort(big)"]["ms_per_step"])
     roof_build = None
     if t_build > 0:
         gbs = 36.0 * n_recv / (t_build * 1e-3) / 1e9
         roof_build = {"bound": "hbm", "kernel": "+".join(build_names), "achieved": gbs, "peak": peak, "unit": "GB/s",
                       "frac": gbs / peak, "alg_bytes": 36.0 * n_recv, "ms_per_step": t_build,
-                      "note": "SURVEY 8(d): 36 B per particle sorted for the whole build; particles = records this rank received"}
+                      "note": "SURVEY 8(d): 36 B per particle sorted for the whole build; particles = records this rank "
+                              "received; the two concurrent bucket kernels count once (the longer one)"}
 
     if args.scale == 1.0:
         if roof_gather:
